@@ -1,0 +1,939 @@
+// orb_oracle.cpp — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+//
+// A plain, serial, OpenCV-free restatement of the reference hot path
+//   /root/reference/src/ORBextractor.cc   (ORBextractor ctor, operator(), ComputePyramid,
+//                                           ComputeKeyPointsOctTree, DistributeOctTree, IC_Angle,
+//                                           computeOrbDescriptor)
+//   /root/reference/src/ORBmatcher.cc     (DescriptorDistance, SearchByBoW x2, SearchForTriangulation,
+//                                           CheckDistEpipolarLine, ComputeThreeMaxima)
+// plus the four OpenCV primitives that path delegates to (cv::FAST, cv::resize INTER_LINEAR,
+// cv::GaussianBlur 7x7 sigma 2, cv::fastAtan2), restated from OpenCV 4.13 behaviour.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this
+// library, and only as the checker / reported CPU baseline.  The product (orbslam_mapsave_b200/csrc) never
+// links, loads or calls it.
+//
+// PARITY PINNING: the reference ships no tests, golden vectors or fixtures for this path
+// and cannot be compiled here (needs OpenCV/Boost/DBoW2 C++ headers that are absent) => "parity unpinned" by
+// the reference itself.  What IS pinned: every OpenCV primitive below is checked bit-for-bit against cv2 4.13.0
+// golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py), and the full extractor is checked
+// against an independent Python chain of the real cv2 primitives (same script).
+//
+// Known, documented deviations from "whatever binary the reference authors ran":
+//   * DistributeOctTree sorts (size, node pointer) pairs (ORBextractor.cc:683); pointer order is allocator
+//     dependent.  Canonical rule here: the pointer is replaced by the node's creation sequence number.
+//   * GaussianBlur follows OpenCV 4.13 (fixed-point 8.8 kernel), the only OpenCV available.
+//   * No FMA contraction anywhere (build with -ffp-contract=off).
+//
+// Build: see oracle/Makefile  (g++ -O2 -ffp-contract=off -shared -fPIC).
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cfloat>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <list>
+#include <thread>
+#include <utility>
+#include <vector>
+
+typedef unsigned char u8;
+
+extern "C" {
+struct orc_kp { float x, y, size, angle, response; int octave, class_id; };  // == cv::KeyPoint layout (28 B)
+struct orc_xyr { int x, y, r; };
+}
+
+static const signed char kPattern[1024] = {
+#include "../orbslam_mapsave_b200/csrc/orb_pattern_31.inc"
+};
+
+// ----------------------------------------------------------------------------------------------
+// Rounding helpers (OpenCV cvRound = round-half-to-even via cvtsd2si; cvFloor/cvCeil as named)
+// ----------------------------------------------------------------------------------------------
+static inline int cvRoundD(double v) { return (int)std::nearbyint(v); }   // default FE_TONEAREST
+static inline int cvRoundF(float v) { return (int)std::nearbyintf(v); }
+static inline int cvFloorD(double v) { int i = (int)v; return i - (i > v); }
+static inline int cvCeilD(double v) { int i = (int)v; return i + (i < v); }
+
+// ----------------------------------------------------------------------------------------------
+// cv::FAST(img, kps, threshold, nonmaxSuppression) — FAST-9/16.   (call sites ORBextractor.cc:808,813)
+// ----------------------------------------------------------------------------------------------
+static const int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+static const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+// Is (x,y) a FAST-9 corner at threshold t: >=9 contiguous ring pixels all < v-t or all > v+t.
+static bool fast_is_corner(const u8* p, int stride, int t) {
+    const int v = p[0];
+    int ring[25];
+    for (int k = 0; k < 16; k++) ring[k] = p[kRingDy[k] * stride + kRingDx[k]];
+    for (int k = 16; k < 25; k++) ring[k] = ring[k - 16];
+    int cd = 0, cb = 0;
+    for (int k = 0; k < 25; k++) {
+        if (ring[k] < v - t) { if (++cd > 8) return true; } else cd = 0;
+        if (ring[k] > v + t) { if (++cb > 8) return true; } else cb = 0;
+    }
+    return false;
+}
+
+// OpenCV cornerScore<16>(ptr, pixel, threshold): largest threshold for which the pixel stays a corner.
+static int fast_corner_score(const u8* p, int stride, int threshold) {
+    int d[25];
+    const int v = p[0];
+    for (int k = 0; k < 16; k++) d[k] = v - p[kRingDy[k] * stride + kRingDx[k]];
+    for (int k = 16; k < 25; k++) d[k] = d[k - 16];
+    int a0 = threshold;
+    for (int k = 0; k < 16; k += 2) {
+        int a = std::min(d[k + 1], d[k + 2]);
+        a = std::min(a, d[k + 3]);
+        if (a <= a0) continue;
+        a = std::min(a, d[k + 4]); a = std::min(a, d[k + 5]); a = std::min(a, d[k + 6]);
+        a = std::min(a, d[k + 7]); a = std::min(a, d[k + 8]);
+        a0 = std::max(a0, std::min(a, d[k]));
+        a0 = std::max(a0, std::min(a, d[k + 9]));
+    }
+    int b0 = -a0;
+    for (int k = 0; k < 16; k += 2) {
+        int b = std::max(d[k + 1], d[k + 2]);
+        b = std::max(b, d[k + 3]); b = std::max(b, d[k + 4]); b = std::max(b, d[k + 5]);
+        if (b >= b0) continue;
+        b = std::max(b, d[k + 6]); b = std::max(b, d[k + 7]); b = std::max(b, d[k + 8]);
+        b0 = std::min(b0, std::max(b, d[k]));
+        b0 = std::min(b0, std::max(b, d[k + 9]));
+    }
+    return -b0 - 1;
+}
+
+static void fast9(const u8* img, int w, int h, int stride, int threshold, bool nms, std::vector<orc_xyr>& out) {
+    out.clear();
+    if (w < 7 || h < 7) return;
+    std::vector<u8> score((size_t)w * h, 0);
+    std::vector<u8> corner((size_t)w * h, 0);
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            const u8* p = img + (size_t)y * stride + x;
+            if (fast_is_corner(p, stride, threshold)) {
+                corner[(size_t)y * w + x] = 1;
+                score[(size_t)y * w + x] = (u8)fast_corner_score(p, stride, threshold);
+            }
+        }
+    for (int y = 3; y < h - 3; y++)
+        for (int x = 3; x < w - 3; x++) {
+            if (!corner[(size_t)y * w + x]) continue;
+            const int s = score[(size_t)y * w + x];
+            if (nms) {
+                bool keep = true;
+                for (int dy = -1; dy <= 1 && keep; dy++)
+                    for (int dx = -1; dx <= 1; dx++) {
+                        if (!dx && !dy) continue;
+                        if (!(s > score[(size_t)(y + dy) * w + (x + dx)])) { keep = false; break; }
+                    }
+                if (!keep) continue;
+            }
+            out.push_back({x, y, s});
+        }
+}
+
+// ----------------------------------------------------------------------------------------------
+// cv::resize(src, dst, dsize, 0, 0, INTER_LINEAR) for 8UC1   (call site ORBextractor.cc:1123)
+// ----------------------------------------------------------------------------------------------
+static void resize_linear_u8(const u8* src, int sw, int sh, int sstride, u8* dst, int dw, int dh, int dstride) {
+    const double inv_scale_x = (double)dw / sw, inv_scale_y = (double)dh / sh;
+    const double scale_x = 1. / inv_scale_x, scale_y = 1. / inv_scale_y;
+    std::vector<int> xofs(dw), yofs(dh);
+    std::vector<short> ialpha(2 * (size_t)dw), ibeta(2 * (size_t)dh);
+    for (int dx = 0; dx < dw; dx++) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = cvFloorD(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xofs[dx] = sx;
+        ialpha[2 * dx] = (short)cvRoundF((1.f - fx) * 2048.f);
+        ialpha[2 * dx + 1] = (short)cvRoundF(fx * 2048.f);
+    }
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = cvFloorD(fy);
+        fy -= sy;
+        yofs[dy] = sy;
+        ibeta[2 * dy] = (short)cvRoundF((1.f - fy) * 2048.f);
+        ibeta[2 * dy + 1] = (short)cvRoundF(fy * 2048.f);
+    }
+    std::vector<int> r0(dw), r1(dw);
+    for (int dy = 0; dy < dh; dy++) {
+        const int sy0 = std::min(std::max(yofs[dy], 0), sh - 1);
+        const int sy1 = std::min(std::max(yofs[dy] + 1, 0), sh - 1);
+        const u8* S0 = src + (size_t)sy0 * sstride;
+        const u8* S1 = src + (size_t)sy1 * sstride;
+        for (int dx = 0; dx < dw; dx++) {
+            const int sx = xofs[dx], sx1 = std::min(sx + 1, sw - 1);
+            const int a0 = ialpha[2 * dx], a1 = ialpha[2 * dx + 1];
+            r0[dx] = S0[sx] * a0 + S0[sx1] * a1;
+            r1[dx] = S1[sx] * a0 + S1[sx1] * a1;
+        }
+        const int b0 = ibeta[2 * dy], b1 = ibeta[2 * dy + 1];
+        u8* D = dst + (size_t)dy * dstride;
+        for (int dx = 0; dx < dw; dx++) {
+            int v = (((b0 * (r0[dx] >> 4)) >> 16) + ((b1 * (r1[dx] >> 4)) >> 16) + 2) >> 2;
+            D[dx] = (u8)std::min(std::max(v, 0), 255);
+        }
+    }
+}
+
+static inline int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) { if (p < 0) p = -p; else p = 2 * (n - 1) - p; }
+    return p;
+}
+
+// cv::copyMakeBorder(src, dst, b,b,b,b, BORDER_REFLECT_101) into a (w+2b)x(h+2b) buffer.
+static void copy_make_border101(const u8* src, int w, int h, int sstride, u8* dst, int dstride, int b) {
+    for (int y = -b; y < h + b; y++) {
+        const u8* S = src + (size_t)reflect101(y, h) * sstride;
+        u8* D = dst + (size_t)(y + b) * dstride;
+        for (int x = -b; x < w + b; x++) D[x + b] = S[reflect101(x, w)];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// cv::GaussianBlur(img, img, Size(7,7), 2, 2, BORDER_REFLECT_101) for 8UC1, OpenCV 4.13 fixed-point path
+// (call site ORBextractor.cc:1089)
+// ----------------------------------------------------------------------------------------------
+static void gaussian_blur7(const u8* src, int w, int h, int sstride, u8* dst, int dstride) {
+    static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
+    std::vector<int> H((size_t)w * h);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int s = 0;
+            for (int i = -3; i <= 3; i++) s += K[i + 3] * src[(size_t)y * sstride + reflect101(x + i, w)];
+            H[(size_t)y * w + x] = s;
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int s = 0;
+            for (int i = -3; i <= 3; i++) s += K[i + 3] * H[(size_t)reflect101(y + i, h) * w + x];
+            dst[(size_t)y * dstride + x] = (u8)((s + 32768) >> 16);
+        }
+}
+
+// ----------------------------------------------------------------------------------------------
+// cv::fastAtan2(y, x) scalar path (degrees)   (call site ORBextractor.cc:102)
+// ----------------------------------------------------------------------------------------------
+static float fast_atan2(float y, float x) {
+    const float scale = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float ax = std::fabs(x), ay = std::fabs(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// ----------------------------------------------------------------------------------------------
+// ORBextractor restatement
+// ----------------------------------------------------------------------------------------------
+namespace {
+
+const int PATCH_SIZE = 31, HALF_PATCH_SIZE = 15, EDGE_THRESHOLD = 19;   // ORBextractor.cc:71-73
+
+struct Img {           // a level: ROI (w x h) inside a bordered buffer
+    int w = 0, h = 0, stride = 0;
+    std::vector<u8> buf;                 // (w+38) x (h+38)
+    u8* roi() { return buf.data() + (size_t)EDGE_THRESHOLD * stride + EDGE_THRESHOLD; }
+    const u8* roi() const { return buf.data() + (size_t)EDGE_THRESHOLD * stride + EDGE_THRESHOLD; }
+};
+
+struct Key { float x, y, response; };    // the fields of cv::KeyPoint the octree touches
+
+struct Node {                            // ExtractorNode, include/ORBextractor.h:37-48
+    std::vector<Key> keys;
+    int ULx, ULy, URx, URy, BLx, BLy, BRx, BRy;
+    std::list<Node>::iterator lit;
+    bool noMore = false;
+    long seq = 0;                        // creation sequence: canonical stand-in for the heap pointer
+};
+
+// ExtractorNode::DivideNode, ORBextractor.cc:480-536
+void divide_node(const Node& p, Node& n1, Node& n2, Node& n3, Node& n4) {
+    const int halfX = (int)std::ceil(static_cast<float>(p.URx - p.ULx) / 2);
+    const int halfY = (int)std::ceil(static_cast<float>(p.BRy - p.ULy) / 2);
+    n1.ULx = p.ULx; n1.ULy = p.ULy;
+    n1.URx = p.ULx + halfX; n1.URy = p.ULy;
+    n1.BLx = p.ULx; n1.BLy = p.ULy + halfY;
+    n1.BRx = p.ULx + halfX; n1.BRy = p.ULy + halfY;
+    n2.ULx = n1.URx; n2.ULy = n1.URy;
+    n2.URx = p.URx; n2.URy = p.URy;
+    n2.BLx = n1.BRx; n2.BLy = n1.BRy;
+    n2.BRx = p.URx; n2.BRy = p.ULy + halfY;
+    n3.ULx = n1.BLx; n3.ULy = n1.BLy;
+    n3.URx = n1.BRx; n3.URy = n1.BRy;
+    n3.BLx = p.BLx; n3.BLy = p.BLy;
+    n3.BRx = n1.BRx; n3.BRy = p.BLy;
+    n4.ULx = n3.URx; n4.ULy = n3.URy;
+    n4.URx = n2.BRx; n4.URy = n2.BRy;
+    n4.BLx = n3.BRx; n4.BLy = n3.BRy;
+    n4.BRx = p.BRx; n4.BRy = p.BRy;
+    for (const Key& kp : p.keys) {
+        if (kp.x < n1.URx) {
+            if (kp.y < n1.BRy) n1.keys.push_back(kp); else n3.keys.push_back(kp);
+        } else if (kp.y < n1.BRy) n2.keys.push_back(kp);
+        else n4.keys.push_back(kp);
+    }
+    if (n1.keys.size() == 1) n1.noMore = true;
+    if (n2.keys.size() == 1) n2.noMore = true;
+    if (n3.keys.size() == 1) n3.noMore = true;
+    if (n4.keys.size() == 1) n4.noMore = true;
+}
+
+// ORBextractor::DistributeOctTree, ORBextractor.cc:538-762
+std::vector<Key> distribute_octtree(const std::vector<Key>& in, int minX, int maxX, int minY, int maxY, int N) {
+    long seq = 0;
+    const int nIni = (int)std::round(static_cast<float>(maxX - minX) / (maxY - minY));
+    const float hX = static_cast<float>(maxX - minX) / nIni;
+    std::list<Node> L;
+    std::vector<Node*> ini(nIni);
+    for (int i = 0; i < nIni; i++) {
+        Node ni;
+        ni.ULx = (int)(hX * static_cast<float>(i)); ni.ULy = 0;
+        ni.URx = (int)(hX * static_cast<float>(i + 1)); ni.URy = 0;
+        ni.BLx = ni.ULx; ni.BLy = maxY - minY;
+        ni.BRx = ni.URx; ni.BRy = maxY - minY;
+        ni.seq = seq++;
+        L.push_back(ni);
+        ini[i] = &L.back();
+    }
+    for (const Key& kp : in) ini[(int)(kp.x / hX)]->keys.push_back(kp);
+    for (auto lit = L.begin(); lit != L.end();) {
+        if (lit->keys.size() == 1) { lit->noMore = true; ++lit; }
+        else if (lit->keys.empty()) lit = L.erase(lit);
+        else ++lit;
+    }
+    bool finish = false;
+    typedef std::pair<int, std::pair<long, Node*> > SizeSeqNode;     // (size, (seq, node)): seq replaces the pointer
+    std::vector<SizeSeqNode> vSize;
+    auto push_child = [&](Node& c, int& nToExpand) {
+        if (c.keys.empty()) return;
+        c.seq = seq++;
+        L.push_front(c);
+        if (c.keys.size() > 1) {
+            nToExpand++;
+            vSize.push_back(std::make_pair((int)c.keys.size(), std::make_pair(L.front().seq, &L.front())));
+            L.front().lit = L.begin();
+        }
+    };
+    while (!finish) {
+        const int prevSize = (int)L.size();
+        auto lit = L.begin();
+        int nToExpand = 0;
+        vSize.clear();
+        while (lit != L.end()) {
+            if (lit->noMore) { ++lit; continue; }
+            Node n1, n2, n3, n4;
+            divide_node(*lit, n1, n2, n3, n4);
+            push_child(n1, nToExpand); push_child(n2, nToExpand);
+            push_child(n3, nToExpand); push_child(n4, nToExpand);
+            lit = L.erase(lit);
+        }
+        if ((int)L.size() >= N || (int)L.size() == prevSize) {
+            finish = true;
+        } else if (((int)L.size() + nToExpand * 3) > N) {
+            while (!finish) {
+                const int prev2 = (int)L.size();
+                std::vector<SizeSeqNode> vPrev = vSize;
+                vSize.clear();
+                std::sort(vPrev.begin(), vPrev.end());
+                for (int j = (int)vPrev.size() - 1; j >= 0; j--) {
+                    Node n1, n2, n3, n4;
+                    Node* pn = vPrev[j].second.second;
+                    divide_node(*pn, n1, n2, n3, n4);
+                    int dummy = 0;
+                    push_child(n1, dummy); push_child(n2, dummy);
+                    push_child(n3, dummy); push_child(n4, dummy);
+                    L.erase(pn->lit);
+                    if ((int)L.size() >= N) break;
+                }
+                if ((int)L.size() >= N || (int)L.size() == prev2) finish = true;
+            }
+        }
+    }
+    std::vector<Key> res;
+    res.reserve(L.size());
+    for (auto& nd : L) {
+        const Key* best = &nd.keys[0];
+        float maxR = best->response;
+        for (size_t k = 1; k < nd.keys.size(); k++)
+            if (nd.keys[k].response > maxR) { best = &nd.keys[k]; maxR = nd.keys[k].response; }
+        res.push_back(*best);
+    }
+    return res;
+}
+
+struct Extractor {
+    int nfeatures; double scaleFactor; int nlevels, iniThFAST, minThFAST;       // include/ORBextractor.h:102-106
+    std::vector<float> sf, isf, s2, is2;
+    std::vector<int> quota, umax;
+    std::vector<Img> pyr;
+    std::vector<std::vector<Key> > cand;       // per level vToDistributeKeys (coords relative to minBorder)
+    std::vector<std::vector<orc_kp> > lvlkp;   // per level keypoints after octree + orientation (level coords)
+    std::vector<std::vector<u8> > blurred;     // per level blurred clone (w x h, contiguous)
+
+    // ORBextractor::ORBextractor, ORBextractor.cc:409-469
+    Extractor(int nf, float sfac, int nl, int ini, int mn)
+        : nfeatures(nf), scaleFactor(sfac), nlevels(nl), iniThFAST(ini), minThFAST(mn) {
+        sf.resize(nl); s2.resize(nl); isf.resize(nl); is2.resize(nl);
+        sf[0] = 1.0f; s2[0] = 1.0f;
+        for (int i = 1; i < nl; i++) {
+            sf[i] = (float)(sf[i - 1] * scaleFactor);      // float * double -> double -> float
+            s2[i] = sf[i] * sf[i];
+        }
+        for (int i = 0; i < nl; i++) { isf[i] = 1.0f / sf[i]; is2[i] = 1.0f / s2[i]; }
+        pyr.resize(nl);
+        quota.resize(nl);
+        float factor = (float)(1.0f / scaleFactor);
+        float nDesired = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; l++) {
+            quota[l] = cvRoundF(nDesired);
+            sum += quota[l];
+            nDesired *= factor;
+        }
+        quota[nl - 1] = std::max(nfeatures - sum, 0);
+        umax.resize(HALF_PATCH_SIZE + 1);
+        int v, v0, vmax = cvFloorD(HALF_PATCH_SIZE * std::sqrt(2.f) / 2 + 1);
+        int vmin = cvCeilD(HALF_PATCH_SIZE * std::sqrt(2.f) / 2);
+        const double hp2 = HALF_PATCH_SIZE * HALF_PATCH_SIZE;
+        for (v = 0; v <= vmax; ++v) umax[v] = cvRoundD(std::sqrt(hp2 - v * v));
+        for (v = HALF_PATCH_SIZE, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+    }
+
+    // ORBextractor::ComputePyramid, ORBextractor.cc:1110-1135
+    void compute_pyramid(const u8* image, int cols, int rows, int stride) {
+        for (int level = 0; level < nlevels; ++level) {
+            const float scale = isf[level];
+            const int w = cvRoundF((float)cols * scale), h = cvRoundF((float)rows * scale);
+            Img& im = pyr[level];
+            im.w = w; im.h = h; im.stride = w + 2 * EDGE_THRESHOLD;
+            im.buf.assign((size_t)im.stride * (h + 2 * EDGE_THRESHOLD), 0);
+            if (level != 0) {
+                const Img& pv = pyr[level - 1];
+                std::vector<u8> tmp((size_t)w * h);
+                resize_linear_u8(pv.roi(), pv.w, pv.h, pv.stride, tmp.data(), w, h, w);
+                copy_make_border101(tmp.data(), w, h, w, im.buf.data(), im.stride, EDGE_THRESHOLD);
+            } else {
+                copy_make_border101(image, cols, rows, stride, im.buf.data(), im.stride, EDGE_THRESHOLD);
+            }
+        }
+    }
+
+    // IC_Angle, ORBextractor.cc:76-103
+    float ic_angle(const Img& im, float px, float py) const {
+        int m_01 = 0, m_10 = 0;
+        const int step = im.stride;
+        const u8* center = im.roi() + (size_t)cvRoundF(py) * step + cvRoundF(px);
+        for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+        for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+            int v_sum = 0;
+            const int d = umax[v];
+            for (int u = -d; u <= d; ++u) {
+                const int val_plus = center[u + v * step], val_minus = center[u - v * step];
+                v_sum += (val_plus - val_minus);
+                m_10 += u * (val_plus + val_minus);
+            }
+            m_01 += v * v_sum;
+        }
+        return fast_atan2((float)m_01, (float)m_10);
+    }
+
+    // ORBextractor::ComputeKeyPointsOctTree, ORBextractor.cc:764-852
+    void compute_keypoints() {
+        cand.assign(nlevels, std::vector<Key>());
+        lvlkp.assign(nlevels, std::vector<orc_kp>());
+        const float W = 30;
+        std::vector<orc_xyr> cell;
+        for (int level = 0; level < nlevels; ++level) {
+            const Img& im = pyr[level];
+            const int minBorderX = EDGE_THRESHOLD - 3, minBorderY = minBorderX;
+            const int maxBorderX = im.w - EDGE_THRESHOLD + 3, maxBorderY = im.h - EDGE_THRESHOLD + 3;
+            std::vector<Key>& toDist = cand[level];
+            const float width = (float)(maxBorderX - minBorderX), height = (float)(maxBorderY - minBorderY);
+            const int nCols = (int)(width / W), nRows = (int)(height / W);
+            const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+            for (int i = 0; i < nRows; i++) {
+                const float iniY = (float)(minBorderY + i * hCell);
+                float maxY = iniY + hCell + 6;
+                if (iniY >= maxBorderY - 3) continue;
+                if (maxY > maxBorderY) maxY = (float)maxBorderY;
+                for (int j = 0; j < nCols; j++) {
+                    const float iniX = (float)(minBorderX + j * wCell);
+                    float maxX = iniX + wCell + 6;
+                    if (iniX >= maxBorderX - 6) continue;
+                    if (maxX > maxBorderX) maxX = (float)maxBorderX;
+                    const int x0 = (int)iniX, x1 = (int)maxX, y0 = (int)iniY, y1 = (int)maxY;
+                    const u8* roi = im.roi() + (size_t)y0 * im.stride + x0;
+                    fast9(roi, x1 - x0, y1 - y0, im.stride, iniThFAST, true, cell);
+                    if (cell.empty()) fast9(roi, x1 - x0, y1 - y0, im.stride, minThFAST, true, cell);
+                    for (const orc_xyr& c : cell)
+                        toDist.push_back({(float)c.x + j * wCell, (float)c.y + i * hCell, (float)c.r});
+                }
+            }
+            std::vector<Key> kept = distribute_octtree(toDist, minBorderX, maxBorderX, minBorderY, maxBorderY, quota[level]);
+            const int scaledPatchSize = (int)(PATCH_SIZE * sf[level]);
+            for (const Key& k : kept) {
+                orc_kp kp;
+                kp.x = k.x + minBorderX; kp.y = k.y + minBorderY;
+                kp.size = (float)scaledPatchSize; kp.angle = -1; kp.response = k.response;
+                kp.octave = level; kp.class_id = -1;
+                lvlkp[level].push_back(kp);
+            }
+        }
+        for (int level = 0; level < nlevels; ++level)
+            for (orc_kp& kp : lvlkp[level]) kp.angle = ic_angle(pyr[level], kp.x, kp.y);
+    }
+
+    // computeOrbDescriptor, ORBextractor.cc:107-146
+    static void orb_descriptor(const orc_kp& kpt, const u8* img, int step, u8* desc) {
+        const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+        const float angle = (float)kpt.angle * factorPI;
+        const float a = (float)cosf(angle), b = (float)sinf(angle);
+        const u8* center = img + (size_t)cvRoundF(kpt.y) * step + cvRoundF(kpt.x);
+        const signed char* pat = kPattern;
+        for (int i = 0; i < 32; ++i, pat += 32) {
+            int val = 0;
+            for (int k = 0; k < 8; k++) {
+                const int x0 = pat[4 * k], y0 = pat[4 * k + 1], x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];
+                const int t0 = center[cvRoundF(x0 * b + y0 * a) * step + cvRoundF(x0 * a - y0 * b)];
+                const int t1 = center[cvRoundF(x1 * b + y1 * a) * step + cvRoundF(x1 * a - y1 * b)];
+                val |= (t0 < t1) << k;
+            }
+            desc[i] = (u8)val;
+        }
+    }
+
+    // ORBextractor::operator(), ORBextractor.cc:1042-1108.  Returns number of keypoints (or -1 if cap too small).
+    int extract(const u8* img, int cols, int rows, int stride, const u8* mask, int mstride,
+                orc_kp* kp_out, u8* desc_out, int cap) {
+        if (!img || cols <= 0 || rows <= 0) return 0;
+        std::vector<u8> image((size_t)cols * rows, 0);           // imageIn.copyTo(image, Mask)
+        for (int y = 0; y < rows; y++)
+            for (int x = 0; x < cols; x++)
+                if (!mask || mask[(size_t)y * mstride + x]) image[(size_t)y * cols + x] = img[(size_t)y * stride + x];
+        compute_pyramid(image.data(), cols, rows, cols);
+        compute_keypoints();
+        int nk = 0;
+        for (int l = 0; l < nlevels; l++) nk += (int)lvlkp[l].size();
+        if (nk > cap) return -1;
+        blurred.assign(nlevels, std::vector<u8>());
+        int offset = 0;
+        for (int level = 0; level < nlevels; ++level) {
+            std::vector<orc_kp>& kps = lvlkp[level];
+            if (kps.empty()) continue;
+            const Img& im = pyr[level];
+            blurred[level].resize((size_t)im.w * im.h);
+            gaussian_blur7(im.roi(), im.w, im.h, im.stride, blurred[level].data(), im.w);
+            for (size_t i = 0; i < kps.size(); i++)
+                orb_descriptor(kps[i], blurred[level].data(), im.w, desc_out + (size_t)(offset + i) * 32);
+            for (size_t i = 0; i < kps.size(); i++) {
+                orc_kp kp = kps[i];
+                if (level != 0) { const float scale = sf[level]; kp.x *= scale; kp.y *= scale; }
+                kp_out[offset + i] = kp;
+            }
+            offset += (int)kps.size();
+        }
+        return nk;
+    }
+};
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// ORBmatcher restatement (flat-array form of the KeyFrame/Frame fields the functions touch)
+// ----------------------------------------------------------------------------------------------
+static const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;      // ORBmatcher.cc:37-39
+
+// ORBmatcher::DescriptorDistance, ORBmatcher.cc:1650-1666 (the bit-hack popcount, verbatim arithmetic)
+static int descriptor_distance(const u8* a, const u8* b) {
+    int32_t pa[8], pb[8];
+    std::memcpy(pa, a, 32); std::memcpy(pb, b, 32);
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        unsigned int v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+// ORBmatcher::ComputeThreeMaxima, ORBmatcher.cc:1604-1645 (on bin sizes)
+static void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// A DBoW2::FeatureVector flattened: node ids ascending, CSR offsets, feature indices (ascending inside a node).
+struct FeatVec { int nnodes; const int* ids; const int* off; const int* feat; };
+
+static inline int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+extern "C" {
+
+// ---- primitives ----
+int orc_fast(const u8* img, int w, int h, int stride, int threshold, int nms, orc_xyr* out, int cap) {
+    std::vector<orc_xyr> v;
+    fast9(img, w, h, stride, threshold, nms != 0, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+void orc_resize(const u8* src, int sw, int sh, int sstride, u8* dst, int dw, int dh, int dstride) {
+    resize_linear_u8(src, sw, sh, sstride, dst, dw, dh, dstride);
+}
+void orc_blur(const u8* src, int w, int h, int sstride, u8* dst, int dstride) { gaussian_blur7(src, w, h, sstride, dst, dstride); }
+void orc_border101(const u8* src, int w, int h, int sstride, u8* dst, int dstride, int b) { copy_make_border101(src, w, h, sstride, dst, dstride, b); }
+float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+int orc_cv_round(double v) { return cvRoundD(v); }
+const signed char* orc_pattern() { return kPattern; }
+
+// ---- extractor ----
+void* orc_extractor_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+    return new Extractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+}
+void orc_extractor_destroy(void* h) { delete (Extractor*)h; }
+void orc_extractor_tables(void* h, float* sf, float* isf, float* s2, float* is2, int* quota, int* umax) {
+    Extractor* e = (Extractor*)h;
+    for (int i = 0; i < e->nlevels; i++) {
+        if (sf) sf[i] = e->sf[i];
+        if (isf) isf[i] = e->isf[i];
+        if (s2) s2[i] = e->s2[i];
+        if (is2) is2[i] = e->is2[i];
+        if (quota) quota[i] = e->quota[i];
+    }
+    if (umax) for (int i = 0; i <= HALF_PATCH_SIZE; i++) umax[i] = e->umax[i];
+}
+int orc_extractor_extract(void* h, const u8* img, int cols, int rows, int stride, const u8* mask, int mstride,
+                          orc_kp* kp_out, u8* desc_out, int cap) {
+    return ((Extractor*)h)->extract(img, cols, rows, stride, mask, mstride, kp_out, desc_out, cap);
+}
+void orc_extractor_level_dims(void* h, int level, int* w, int* hh) {
+    Extractor* e = (Extractor*)h; *w = e->pyr[level].w; *hh = e->pyr[level].h;
+}
+// bordered != 0: copy the whole (w+38)x(h+38) buffer, else the w x h ROI
+void orc_extractor_level_copy(void* h, int level, int bordered, u8* dst, int dstride) {
+    Extractor* e = (Extractor*)h; const Img& im = e->pyr[level];
+    if (bordered) for (int y = 0; y < im.h + 2 * EDGE_THRESHOLD; y++) std::memcpy(dst + (size_t)y * dstride, im.buf.data() + (size_t)y * im.stride, im.stride);
+    else for (int y = 0; y < im.h; y++) std::memcpy(dst + (size_t)y * dstride, im.roi() + (size_t)y * im.stride, im.w);
+}
+int orc_extractor_blurred_copy(void* h, int level, u8* dst, int dstride) {
+    Extractor* e = (Extractor*)h; const Img& im = e->pyr[level];
+    if (e->blurred[level].empty()) return 0;
+    for (int y = 0; y < im.h; y++) std::memcpy(dst + (size_t)y * dstride, e->blurred[level].data() + (size_t)y * im.w, im.w);
+    return 1;
+}
+// FAST candidates of a level in octree input order, coordinates in level pixels (minBorder added back)
+int orc_extractor_candidates(void* h, int level, orc_xyr* out, int cap) {
+    Extractor* e = (Extractor*)h; const std::vector<Key>& c = e->cand[level];
+    for (size_t i = 0; i < c.size() && (int)i < cap; i++) out[i] = {(int)c[i].x + 16, (int)c[i].y + 16, (int)c[i].response};
+    return (int)c.size();
+}
+int orc_extractor_level_keypoints(void* h, int level, orc_kp* out, int cap) {
+    Extractor* e = (Extractor*)h; const std::vector<orc_kp>& c = e->lvlkp[level];
+    for (size_t i = 0; i < c.size() && (int)i < cap; i++) out[i] = c[i];
+    return (int)c.size();
+}
+// stand-alone octree on an explicit candidate list (coords relative to minBorder, as the reference passes them)
+int orc_octree(const float* x, const float* y, const float* resp, int n, int minX, int maxX, int minY, int maxY, int N,
+               float* ox, float* oy, float* oresp, int cap) {
+    std::vector<Key> in(n);
+    for (int i = 0; i < n; i++) in[i] = {x[i], y[i], resp[i]};
+    std::vector<Key> r = distribute_octtree(in, minX, maxX, minY, maxY, N);
+    for (size_t i = 0; i < r.size() && (int)i < cap; i++) { ox[i] = r[i].x; oy[i] = r[i].y; oresp[i] = r[i].response; }
+    return (int)r.size();
+}
+// descriptor of one keypoint on an already blurred image
+void orc_descriptor(const u8* blurred, int step, float x, float y, float angle, u8* desc) {
+    orc_kp kp; kp.x = x; kp.y = y; kp.angle = angle;
+    Extractor::orb_descriptor(kp, blurred, step, desc);
+}
+
+// CPU baseline helper: extract `nframes` frames (contiguous cols x rows each) with `nthreads` threads, one extractor
+// instance per thread, frames dealt round-robin.  Returns wall seconds; total keypoints in *nkp_total.
+double orc_extract_batch_mt(const u8* frames, int nframes, int cols, int rows, int nfeatures, float scaleFactor, int nlevels,
+                            int iniTh, int minTh, int nthreads, long* nkp_total) {
+    std::atomic<long> total(0);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&, t]() {
+            Extractor e(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+            const int cap = nfeatures + 4 * nlevels + 64;
+            std::vector<orc_kp> kp(cap); std::vector<u8> desc((size_t)cap * 32);
+            long s = 0;
+            for (int f = t; f < nframes; f += nthreads) {
+                int n = e.extract(frames + (size_t)f * cols * rows, cols, rows, cols, nullptr, 0, kp.data(), desc.data(), cap);
+                if (n > 0) s += n;
+            }
+            total += s;
+        });
+    for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (nkp_total) *nkp_total = total.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- matcher ----
+int orc_descriptor_distance(const u8* a, const u8* b) { return descriptor_distance(a, b); }
+
+void orc_three_maxima(const int* histo, int L, int* ind) {
+    int i1 = -1, i2 = -1, i3 = -1;
+    three_maxima(histo, L, i1, i2, i3);
+    ind[0] = i1; ind[1] = i2; ind[2] = i3;
+}
+
+// Brute-force top-2 (the inner loop shape of SearchByBoW, ORBmatcher.cc:205-229, over the whole set):
+// best_idx = first index attaining the minimum distance, best = that distance, second = second smallest (256 if none).
+void orc_hamming_top2(const u8* q, int nq, const u8* db, int ndb, int* best_idx, int* best, int* second) {
+    for (int i = 0; i < nq; i++) {
+        int b1 = 256, b2 = 256, bi = -1;
+        for (int j = 0; j < ndb; j++) {
+            const int d = descriptor_distance(q + (size_t)i * 32, db + (size_t)j * 32);
+            if (d < b1) { b2 = b1; b1 = d; bi = j; } else if (d < b2) { b2 = d; }
+        }
+        best_idx[i] = bi; best[i] = b1; second[i] = b2;
+    }
+}
+// multi-threaded variant for the CPU baseline; returns wall seconds
+double orc_hamming_top2_mt(const u8* q, int nq, const u8* db, int ndb, int* best_idx, int* best, int* second, int nthreads) {
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([=]() {
+            const int lo = (int)((long)nq * t / nthreads), hi = (int)((long)nq * (t + 1) / nthreads);
+            orc_hamming_top2(q + (size_t)lo * 32, hi - lo, db, ndb, best_idx + lo, best + lo, second + lo);
+        });
+    for (auto& x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// SearchByBoW(KeyFrame*, Frame&, ...), ORBmatcher.cc:159-291.
+//   valid1[i] = KF feature i has a MapPoint that is not bad.   match21[j] (size n2) = KF feature index whose
+//   MapPoint the reference would store in vpMapPointMatches[j], or -1.   Returns nmatches.
+int orc_search_bow_kf_f(const u8* desc1, int n1, const u8* valid1, const float* angle1,
+                        int nn1, const int* ids1, const int* off1, const int* feat1,
+                        const u8* desc2, int n2, const float* angle2,
+                        int nn2, const int* ids2, const int* off2, const int* feat2,
+                        float nnratio, int checkOri, int* match21) {
+    (void)n1;
+    for (int j = 0; j < n2; j++) match21[j] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int iKF = off1[a]; iKF < off1[a + 1]; iKF++) {
+                const int realIdxKF = feat1[iKF];
+                if (!valid1[realIdxKF]) continue;
+                const u8* dKF = desc1 + (size_t)realIdxKF * 32;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int iF = off2[b]; iF < off2[b + 1]; iF++) {
+                    const int realIdxF = feat2[iF];
+                    if (match21[realIdxF] >= 0) continue;
+                    const int dist = descriptor_distance(dKF, desc2 + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) { bestDist2 = dist; }
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                        match21[bestIdxF] = realIdxKF;
+                        if (checkOri) rotHist[rot_bin(angle1[realIdxKF], angle2[bestIdxF])].push_back(bestIdxF);
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (ids1[a] < ids2[b]) {
+            a = (int)(std::lower_bound(ids1, ids1 + nn1, ids2[b]) - ids1);
+        } else {
+            b = (int)(std::lower_bound(ids2, ids2 + nn2, ids1[a]) - ids2);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match21[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// SearchByBoW(KeyFrame*, KeyFrame*, ...), ORBmatcher.cc:525-658.  match12[i] (size n1) = idx2 or -1.
+int orc_search_bow_kf_kf(const u8* desc1, int n1, const u8* valid1, const float* angle1,
+                         int nn1, const int* ids1, const int* off1, const int* feat1,
+                         const u8* desc2, int n2, const u8* valid2, const float* angle2,
+                         int nn2, const int* ids2, const int* off2, const int* feat2,
+                         float nnratio, int checkOri, int* match12) {
+    for (int i = 0; i < n1; i++) match12[i] = -1;
+    std::vector<bool> matched2(n2, false);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0, a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int i1 = off1[a]; i1 < off1[a + 1]; i1++) {
+                const int idx1 = feat1[i1];
+                if (!valid1[idx1]) continue;
+                const u8* d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int i2 = off2[b]; i2 < off2[b + 1]; i2++) {
+                    const int idx2 = feat2[i2];
+                    if (matched2[idx2] || !valid2[idx2]) continue;
+                    const int dist = descriptor_distance(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) { bestDist2 = dist; }
+                }
+                if (bestDist1 < TH_LOW) {
+                    if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                        match12[idx1] = bestIdx2;
+                        matched2[bestIdx2] = true;
+                        if (checkOri) rotHist[rot_bin(angle1[idx1], angle2[bestIdx2])].push_back(idx1);
+                        nmatches++;
+                    }
+                }
+            }
+            a++; b++;
+        } else if (ids1[a] < ids2[b]) {
+            a = (int)(std::lower_bound(ids1, ids1 + nn1, ids2[b]) - ids1);
+        } else {
+            b = (int)(std::lower_bound(ids2, ids2 + nn2, ids1[a]) - ids2);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { match12[j] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// CheckDistEpipolarLine, ORBmatcher.cc:140-157   (F12 row-major 3x3 float)
+static bool check_dist_epipolar_line(float x1, float y1, float x2, float y2, int octave2, const float* F12, const float* sigma2_2) {
+    const float a = x1 * F12[0] + y1 * F12[3] + F12[6];
+    const float b = x1 * F12[1] + y1 * F12[4] + F12[7];
+    const float c = x1 * F12[2] + y1 * F12[5] + F12[8];
+    const float num = a * x2 + b * y2 + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * sigma2_2[octave2];
+}
+
+// SearchForTriangulation, ORBmatcher.cc:660-826.
+//   hasmp{1,2}[i] = GetMapPoint(i) != NULL; kp = mvKeysUn (x, y, angle, octave); uright = mvuRight;
+//   (ex, ey) = epipole of KF1's centre in KF2 (ORBmatcher.cc:667-673, computed by the caller);
+//   sf2 / sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2.  pairs_out = (idx1, idx2) ascending idx1.
+int orc_search_triangulation(const u8* desc1, int n1, const u8* hasmp1, const float* uright1,
+                             const float* kx1, const float* ky1, const float* ang1,
+                             int nn1, const int* ids1, const int* off1, const int* feat1,
+                             const u8* desc2, int n2, const u8* hasmp2, const float* uright2,
+                             const float* kx2, const float* ky2, const float* ang2, const int* oct2,
+                             int nn2, const int* ids2, const int* off2, const int* feat2,
+                             const float* F12, float ex, float ey, const float* sf2, const float* sigma2_2,
+                             int onlyStereo, int checkOri, int* pairs_out, int* npairs_out) {
+    int nmatches = 0;
+    std::vector<bool> matched2(n2, false);
+    std::vector<int> m12(n1, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int a = 0, b = 0;
+    while (a < nn1 && b < nn2) {
+        if (ids1[a] == ids2[b]) {
+            for (int i1 = off1[a]; i1 < off1[a + 1]; i1++) {
+                const int idx1 = feat1[i1];
+                if (hasmp1[idx1]) continue;
+                const bool bStereo1 = uright1[idx1] >= 0;
+                if (onlyStereo) if (!bStereo1) continue;
+                const u8* d1 = desc1 + (size_t)idx1 * 32;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int i2 = off2[b]; i2 < off2[b + 1]; i2++) {
+                    const int idx2 = feat2[i2];
+                    if (matched2[idx2] || hasmp2[idx2]) continue;
+                    const bool bStereo2 = uright2[idx2] >= 0;
+                    if (onlyStereo) if (!bStereo2) continue;
+                    const int dist = descriptor_distance(d1, desc2 + (size_t)idx2 * 32);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kx2[idx2], distey = ey - ky2[idx2];
+                        if (distex * distex + distey * distey < 100 * sf2[oct2[idx2]]) continue;
+                    }
+                    if (check_dist_epipolar_line(kx1[idx1], ky1[idx1], kx2[idx2], ky2[idx2], oct2[idx2], F12, sigma2_2)) {
+                        bestIdx2 = idx2; bestDist = dist;
+                    }
+                }
+                if (bestIdx2 >= 0) {
+                    m12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (checkOri) rotHist[rot_bin(ang1[idx1], ang2[bestIdx2])].push_back(idx1);
+                }
+            }
+            a++; b++;
+        } else if (ids1[a] < ids2[b]) {
+            a = (int)(std::lower_bound(ids1, ids1 + nn1, ids2[b]) - ids1);
+        } else {
+            b = (int)(std::lower_bound(ids2, ids2 + nn2, ids1[a]) - ids2);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j : rotHist[i]) { m12[j] = -1; nmatches--; }
+        }
+    }
+    int np = 0;
+    for (int i = 0; i < n1; i++) {
+        if (m12[i] < 0) continue;
+        pairs_out[2 * np] = i; pairs_out[2 * np + 1] = m12[i];
+        np++;
+    }
+    *npairs_out = np;
+    return nmatches;
+}
+
+}  // extern "C"

@@ -1,0 +1,321 @@
+"""ctypes binding of the CPU oracle (oracle/orb_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg; never by
+the product package (orbslam_mapsave_b200), which must fail loudly without its CUDA library instead.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+XYR_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("r", "<i4")])
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "orb_oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
+        L.orc_fast.restype = i32
+        L.orc_fast.argtypes = [vp, i32, i32, i32, i32, i32, vp, i32]
+        L.orc_resize.restype = None
+        L.orc_resize.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32]
+        L.orc_blur.restype = None
+        L.orc_blur.argtypes = [vp, i32, i32, i32, vp, i32]
+        L.orc_border101.restype = None
+        L.orc_border101.argtypes = [vp, i32, i32, i32, vp, i32, i32]
+        L.orc_fast_atan2.restype = f32
+        L.orc_fast_atan2.argtypes = [f32, f32]
+        L.orc_cv_round.restype = i32
+        L.orc_cv_round.argtypes = [C.c_double]
+        L.orc_pattern.restype = vp
+        L.orc_extractor_create.restype = vp
+        L.orc_extractor_create.argtypes = [i32, f32, i32, i32, i32]
+        L.orc_extractor_destroy.restype = None
+        L.orc_extractor_destroy.argtypes = [vp]
+        L.orc_extractor_tables.restype = None
+        L.orc_extractor_tables.argtypes = [vp] * 7
+        L.orc_extractor_extract.restype = i32
+        L.orc_extractor_extract.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32]
+        L.orc_extractor_level_dims.restype = None
+        L.orc_extractor_level_dims.argtypes = [vp, i32, vp, vp]
+        L.orc_extractor_level_copy.restype = None
+        L.orc_extractor_level_copy.argtypes = [vp, i32, i32, vp, i32]
+        L.orc_extractor_blurred_copy.restype = i32
+        L.orc_extractor_blurred_copy.argtypes = [vp, i32, vp, i32]
+        L.orc_extractor_candidates.restype = i32
+        L.orc_extractor_candidates.argtypes = [vp, i32, vp, i32]
+        L.orc_extractor_level_keypoints.restype = i32
+        L.orc_extractor_level_keypoints.argtypes = [vp, i32, vp, i32]
+        L.orc_octree.restype = i32
+        L.orc_octree.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32]
+        L.orc_descriptor.restype = None
+        L.orc_descriptor.argtypes = [vp, i32, f32, f32, f32, vp]
+        L.orc_extract_batch_mt.restype = C.c_double
+        L.orc_extract_batch_mt.argtypes = [vp, i32, i32, i32, i32, f32, i32, i32, i32, i32, vp]
+        L.orc_descriptor_distance.restype = i32
+        L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_three_maxima.restype = None
+        L.orc_three_maxima.argtypes = [vp, i32, vp]
+        L.orc_hamming_top2.restype = None
+        L.orc_hamming_top2.argtypes = [vp, i32, vp, i32, vp, vp, vp]
+        L.orc_hamming_top2_mt.restype = C.c_double
+        L.orc_hamming_top2_mt.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32]
+        L.orc_search_bow_kf_f.restype = i32
+        L.orc_search_bow_kf_f.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, f32, i32, vp]
+        L.orc_search_bow_kf_kf.restype = i32
+        L.orc_search_bow_kf_kf.argtypes = [vp, i32, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, f32, i32, vp]
+        L.orc_search_triangulation.restype = i32
+        L.orc_search_triangulation.argtypes = ([vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp] +
+                                               [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp] +
+                                               [vp, f32, f32, vp, vp, i32, i32, vp, vp])
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+# ------------------------------------------------------------------ primitives
+def fast(img, threshold, nms=True):
+    img = np.asarray(img)
+    assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+    cap = img.shape[0] * img.shape[1]
+    out = np.zeros(max(cap, 1), XYR_DTYPE)
+    n = lib().orc_fast(_p(img), img.shape[1], img.shape[0], img.strides[0], int(threshold), int(nms), _p(out), cap)
+    return out[:n]
+
+
+def resize(src, dw, dh):
+    src = np.asarray(src)
+    assert src.dtype == np.uint8 and src.strides[1] == 1
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def blur(src):
+    src = np.asarray(src)
+    assert src.dtype == np.uint8 and src.strides[1] == 1
+    dst = np.zeros(src.shape, np.uint8)
+    lib().orc_blur(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), src.shape[1])
+    return dst
+
+
+def border101(src, b=19):
+    src = _u8(src)
+    h, w = src.shape
+    dst = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    lib().orc_border101(_p(src), w, h, w, _p(dst), w + 2 * b, b)
+    return dst
+
+
+def fast_atan2(y, x):
+    return float(lib().orc_fast_atan2(float(y), float(x)))
+
+
+def pattern():
+    buf = (C.c_byte * 1024).from_address(lib().orc_pattern())
+    return np.frombuffer(buf, dtype=np.int8).copy()
+
+
+# ------------------------------------------------------------------ extractor
+class Extractor:
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.h = lib().orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_extractor_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sf, isf, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        quota = np.zeros(n, np.int32)
+        umax = np.zeros(16, np.int32)
+        lib().orc_extractor_tables(self.h, _p(sf), _p(isf), _p(s2), _p(is2), _p(quota), _p(umax))
+        return dict(scale=sf, inv_scale=isf, sigma2=s2, inv_sigma2=is2, quota=quota, umax=umax)
+
+    def extract(self, img, mask=None):
+        img = np.asarray(img)
+        assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+        cap = self.nfeatures + 4 * self.nlevels + 64
+        while True:
+            kp = np.zeros(cap, KP_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            m = None
+            if mask is not None:
+                m = np.ascontiguousarray(mask, dtype=np.uint8)
+            n = lib().orc_extractor_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                                            _p(m), (m.shape[1] if m is not None else 0), _p(kp), _p(desc), cap)
+            if n >= 0:
+                return kp[:n].copy(), desc[:n].copy()
+            cap *= 2
+
+    def level(self, l, bordered=False):
+        w, h = C.c_int(), C.c_int()
+        lib().orc_extractor_level_dims(self.h, l, C.byref(w), C.byref(h))
+        w, h = w.value, h.value
+        if bordered:
+            out = np.zeros((h + 38, w + 38), np.uint8)
+        else:
+            out = np.zeros((h, w), np.uint8)
+        lib().orc_extractor_level_copy(self.h, l, int(bordered), _p(out), out.shape[1])
+        return out
+
+    def blurred(self, l):
+        out = np.zeros_like(self.level(l))
+        ok = lib().orc_extractor_blurred_copy(self.h, l, _p(out), out.shape[1])
+        return out if ok else None
+
+    def candidates(self, l):
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, XYR_DTYPE)
+            n = lib().orc_extractor_candidates(self.h, l, _p(out), cap)
+            if n <= cap:
+                return out[:n].copy()
+            cap = n
+
+    def level_keypoints(self, l):
+        cap = self.nfeatures + 64
+        while True:
+            out = np.zeros(cap, KP_DTYPE)
+            n = lib().orc_extractor_level_keypoints(self.h, l, _p(out), cap)
+            if n <= cap:
+                return out[:n].copy()
+            cap = n
+
+
+def octree(x, y, resp, min_x, max_x, min_y, max_y, N):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.ascontiguousarray(y, np.float32)
+    r = np.ascontiguousarray(resp, np.float32)
+    cap = len(x) + 8
+    ox, oy, orr = (np.zeros(cap, np.float32) for _ in range(3))
+    n = lib().orc_octree(_p(x), _p(y), _p(r), len(x), min_x, max_x, min_y, max_y, N, _p(ox), _p(oy), _p(orr), cap)
+    return ox[:n], oy[:n], orr[:n]
+
+
+def descriptor(blurred, x, y, angle):
+    blurred = np.asarray(blurred)
+    assert blurred.dtype == np.uint8 and blurred.strides[1] == 1
+    d = np.zeros(32, np.uint8)
+    lib().orc_descriptor(_p(blurred), blurred.strides[0], float(x), float(y), float(angle), _p(d))
+    return d
+
+
+def extract_batch_mt(frames, nfeatures, scale_factor, nlevels, ini_th, min_th, nthreads):
+    frames = np.ascontiguousarray(frames, np.uint8)
+    n, h, w = frames.shape
+    tot = C.c_long()
+    secs = lib().orc_extract_batch_mt(_p(frames), n, w, h, nfeatures, scale_factor, nlevels, ini_th, min_th, nthreads,
+                                      C.byref(tot))
+    return secs, tot.value
+
+
+# ------------------------------------------------------------------ matcher
+def descriptor_distance(a, b):
+    a, b = _u8(a), _u8(b)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def three_maxima(hist):
+    hist = np.ascontiguousarray(hist, np.int32)
+    ind = np.zeros(3, np.int32)
+    lib().orc_three_maxima(_p(hist), len(hist), _p(ind))
+    return tuple(int(v) for v in ind)
+
+
+def hamming_top2(q, db, nthreads=1):
+    q, db = _u8(q), _u8(db)
+    nq, ndb = len(q), len(db)
+    bi, b1, b2 = (np.zeros(nq, np.int32) for _ in range(3))
+    if nthreads <= 1:
+        lib().orc_hamming_top2(_p(q), nq, _p(db), ndb, _p(bi), _p(b1), _p(b2))
+        return bi, b1, b2
+    secs = lib().orc_hamming_top2_mt(_p(q), nq, _p(db), ndb, _p(bi), _p(b1), _p(b2), nthreads)
+    return bi, b1, b2, secs
+
+
+class FeatVec:
+    """Flattened DBoW2::FeatureVector: node ids ascending, CSR offsets, feature indices."""
+
+    def __init__(self, node_of_feature):
+        node_of_feature = np.asarray(node_of_feature, np.int64)
+        order = np.argsort(node_of_feature, kind="stable")
+        ids, counts = np.unique(node_of_feature, return_counts=True)
+        self.ids = ids.astype(np.int32)
+        self.off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self.feat = order.astype(np.int32)
+
+    @property
+    def n(self):
+        return len(self.ids)
+
+
+def search_bow_kf_f(desc1, valid1, angle1, fv1, desc2, angle2, fv2, nnratio, check_ori):
+    desc1, desc2 = _u8(desc1), _u8(desc2)
+    valid1 = _u8(valid1)
+    angle1 = np.ascontiguousarray(angle1, np.float32)
+    angle2 = np.ascontiguousarray(angle2, np.float32)
+    m = np.zeros(len(desc2), np.int32)
+    n = lib().orc_search_bow_kf_f(_p(desc1), len(desc1), _p(valid1), _p(angle1), fv1.n, _p(fv1.ids), _p(fv1.off), _p(fv1.feat),
+                                  _p(desc2), len(desc2), _p(angle2), fv2.n, _p(fv2.ids), _p(fv2.off), _p(fv2.feat),
+                                  float(nnratio), int(check_ori), _p(m))
+    return n, m
+
+
+def search_bow_kf_kf(desc1, valid1, angle1, fv1, desc2, valid2, angle2, fv2, nnratio, check_ori):
+    desc1, desc2 = _u8(desc1), _u8(desc2)
+    valid1, valid2 = _u8(valid1), _u8(valid2)
+    angle1 = np.ascontiguousarray(angle1, np.float32)
+    angle2 = np.ascontiguousarray(angle2, np.float32)
+    m = np.zeros(len(desc1), np.int32)
+    n = lib().orc_search_bow_kf_kf(_p(desc1), len(desc1), _p(valid1), _p(angle1), fv1.n, _p(fv1.ids), _p(fv1.off), _p(fv1.feat),
+                                   _p(desc2), len(desc2), _p(valid2), _p(angle2), fv2.n, _p(fv2.ids), _p(fv2.off), _p(fv2.feat),
+                                   float(nnratio), int(check_ori), _p(m))
+    return n, m
+
+
+def search_triangulation(desc1, hasmp1, uright1, kx1, ky1, ang1, fv1,
+                         desc2, hasmp2, uright2, kx2, ky2, ang2, oct2, fv2,
+                         F12, ex, ey, sf2, sigma2_2, only_stereo, check_ori):
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    desc1, desc2, hasmp1, hasmp2 = _u8(desc1), _u8(desc2), _u8(hasmp1), _u8(hasmp2)
+    uright1, kx1, ky1, ang1 = f(uright1), f(kx1), f(ky1), f(ang1)
+    uright2, kx2, ky2, ang2 = f(uright2), f(kx2), f(ky2), f(ang2)
+    oct2 = np.ascontiguousarray(oct2, np.int32)
+    F12, sf2, sigma2_2 = f(F12).reshape(9), f(sf2), f(sigma2_2)
+    pairs = np.zeros((len(desc1), 2), np.int32)
+    npairs = C.c_int()
+    n = lib().orc_search_triangulation(
+        _p(desc1), len(desc1), _p(hasmp1), _p(uright1), _p(kx1), _p(ky1), _p(ang1), fv1.n, _p(fv1.ids), _p(fv1.off), _p(fv1.feat),
+        _p(desc2), len(desc2), _p(hasmp2), _p(uright2), _p(kx2), _p(ky2), _p(ang2), _p(oct2), fv2.n, _p(fv2.ids), _p(fv2.off), _p(fv2.feat),
+        _p(F12), float(ex), float(ey), _p(sf2), _p(sigma2_2), int(only_stereo), int(check_ori), _p(pairs), C.byref(npairs))
+    return n, pairs[:npairs.value].copy()
