@@ -1,0 +1,195 @@
+/* orb_b200.h — C ABI of the B200-native ORB front-end (liborb_b200.so).
+ *
+ * The reference (skaegy/ORBSLAM_MapSave) is a C++ library with no FFI; the drop-in boundary for its feature hot path is
+ * the pair of C++ classes ORB_SLAM2::ORBextractor (include/ORBextractor.h:50-116) and ORB_SLAM2::ORBmatcher
+ * (include/ORBmatcher.h:37-101).  orbslam_mapsave_b200/host/ re-implements those classes with the same signatures on
+ * top of THIS header; every entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain pointers + sizes, no C++/torch types.  All functions return 0 (ORB_OK) or a negative orb_status.
+ * "host" pointers are ordinary CPU memory (pinned memory makes the copies asynchronous and faster); "device"
+ * pointers (suffix _device entry points) are CUDA device memory on the handle's device and the call is asynchronous on
+ * the given cudaStream_t (passed as void*; NULL = the handle's own stream).  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails with ORB_ERR_CUDA.
+ */
+#ifndef ORB_B200_H_
+#define ORB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum orb_status {
+    ORB_OK = 0,
+    ORB_ERR_CUDA = -1,          /* a CUDA runtime call failed; orb_last_error() has the text */
+    ORB_ERR_ARG = -2,           /* bad argument (null pointer, size mismatch, unsupported geometry) */
+    ORB_ERR_CAPACITY = -3,      /* an output capacity given by the caller is too small */
+    ORB_ERR_OVERFLOW = -4,      /* an internal candidate buffer overflowed (raise cand_per_cell at create) */
+    ORB_ERR_GEOMETRY = -5       /* a pyramid level is < 62 px: the reference divides by zero there (ORBextractor.cc:783-786) */
+} orb_status;
+
+/* Same 28-byte layout as cv::KeyPoint {Point2f pt; float size, angle, response; int octave, class_id}. */
+typedef struct orbx_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_keypoint;
+
+/* FAST candidate as fed to the octree (debug / parity view of ORBextractor.cc:788-828 `vToDistributeKeys`). */
+typedef struct orbx_candidate {
+    int32_t x, y, response;     /* level pixel coordinates */
+} orbx_candidate;
+
+typedef struct orbx_extractor orbx_extractor;
+
+const char* orb_last_error(void);           /* thread-local text of the last failure */
+int orb_device_count(void);                 /* number of CUDA devices, 0 if none / no driver */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ORBextractor
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Replaces ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+ * (include/ORBextractor.h:56-57, src/ORBextractor.cc:409-469).  width/height fix the image geometry the handle is
+ * planned for (the C++ class re-plans when operator() sees another size); max_batch = frames processed per device
+ * pass (workspace is allocated for that many).  device = CUDA ordinal. */
+int orbx_create(orbx_extractor** out, int nfeatures, float scale_factor, int nlevels, int ini_th_fast, int min_th_fast,
+                int width, int height, int max_batch, int device);
+void orbx_destroy(orbx_extractor* ex);
+
+/* Replaces GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:74-88) and exposes mnFeaturesPerLevel (src/ORBextractor.cc:434-445).  Any pointer may be
+ * NULL; arrays have nlevels entries. */
+int orbx_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota);
+/* Level sizes (src/ORBextractor.cc:1114-1115). */
+int orbx_level_size(const orbx_extractor* ex, int level, int* w, int* h);
+/* Upper bound on keypoints per frame: nfeatures + 3 per level (the octree may overshoot each quota). */
+int orbx_max_keypoints(const orbx_extractor* ex);
+
+/* Replaces ORBextractor::operator()(image, mask, keypoints, descriptors) (src/ORBextractor.cc:1042-1108) for ONE host
+ * image.  image: 8-bit gray, `stride` bytes per row.  mask: NULL/empty = none, else 8-bit, same size: pixels where
+ * mask==0 are zeroed before the pyramid (this fork's behaviour, :1048-1053).  kp_out[cap], desc_out[cap*32].
+ * *n_out = number of keypoints (level-major order, as the reference).  Blocks until the result is in host memory. */
+int orbx_extract(orbx_extractor* ex, const uint8_t* image, int width, int height, int stride,
+                 const uint8_t* mask, int mask_stride,
+                 orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
+
+/* Batch form (not in the reference: N frames per call for throughput).  Frames are `frame_stride` bytes apart, rows
+ * `stride` bytes; masks (or NULL) laid out likewise with mask_frame_stride/mask_stride.  kp_out[n_frames*cap],
+ * desc_out[n_frames*cap*32], n_out[n_frames].  Host pointers; blocks until done. */
+int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int n_frames, int width, int height, int stride,
+                       size_t frame_stride, const uint8_t* masks, int mask_stride, size_t mask_frame_stride,
+                       orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
+
+/* Same, with every buffer already in device memory (frames tightly packed: stride = width, frame_stride = w*h).
+ * n_frames may exceed max_batch (processed in passes).  Asynchronous on `stream`. */
+int orbx_extract_batch_device(orbx_extractor* ex, const uint8_t* d_images, int n_frames,
+                              const uint8_t* d_masks, orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap,
+                              int* d_n_out, void* stream);
+/* Poll the device-side status word after a *_device call has completed (ORB_OK / ORB_ERR_OVERFLOW / ORB_ERR_CAPACITY). */
+int orbx_check_status(orbx_extractor* ex);
+
+/* Replaces the public member `std::vector<cv::Mat> mvImagePyramid` (include/ORBextractor.h:90; read by
+ * Frame::ComputeStereoMatches, src/Frame.cc:589-696): copies level `level` of frame `frame` of the LAST pass to host.
+ * bordered != 0 copies the (w+38)x(h+38) buffer with its REFLECT_101 border (src/ORBextractor.cc:1125-1132), else
+ * the w x h image. */
+int orbx_get_pyramid_level(orbx_extractor* ex, int frame, int level, int bordered, uint8_t* dst, int dst_stride);
+/* Parity/debug views of the last pass: the blurred level (src/ORBextractor.cc:1088-1089) and the FAST candidates of a
+ * level in the reference's octree input order (:788-828).  *n_out receives the count (may exceed cap). */
+int orbx_get_blurred_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, int dst_stride);
+int orbx_get_candidates(orbx_extractor* ex, int frame, int level, orbx_candidate* out, int cap, int* n_out);
+/* Number of kernels launched by this handle so far (bench bookkeeping). */
+long long orbx_launch_count(const orbx_extractor* ex);
+
+/* Stage timing hooks for bench.py: run only some stages of a device pass (bit mask) on data of the last full pass. */
+enum { ORBX_STAGE_PYRAMID = 1, ORBX_STAGE_FAST = 2, ORBX_STAGE_OCTREE = 4, ORBX_STAGE_BLUR = 8, ORBX_STAGE_DESCRIBE = 16,
+       ORBX_STAGE_ALL = 31 };
+int orbx_run_stages_device(orbx_extractor* ex, const uint8_t* d_images, int n_frames, const uint8_t* d_masks,
+                           orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_n_out, int stage_mask,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ORBmatcher
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define ORBM_TH_HIGH 100        /* ORBmatcher::TH_HIGH  (src/ORBmatcher.cc:37) */
+#define ORBM_TH_LOW 50          /* ORBmatcher::TH_LOW   (src/ORBmatcher.cc:38) */
+#define ORBM_HISTO_LENGTH 30    /* ORBmatcher::HISTO_LENGTH (src/ORBmatcher.cc:39) */
+
+/* Replaces static ORBmatcher::DescriptorDistance(a, b) (src/ORBmatcher.cc:1650-1666) for n descriptor pairs:
+ * dist[i] = Hamming(a[i], b[i]) over 256 bits.  Host pointers. */
+int orbm_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int* dist, int device);
+
+/* The inner loop of SearchByBoW (src/ORBmatcher.cc:205-229) over whole sets: for each of nq query descriptors the
+ * first database index attaining the minimum distance, that distance, and the second-smallest distance (256 if
+ * ndb < 2; index -1 and 256 if ndb == 0).  Host pointers. */
+int orbm_hamming_top2(const uint8_t* q, int nq, const uint8_t* db, int ndb,
+                      int* best_idx, int* best_dist, int* second_dist, int device);
+/* Batched device form: `npairs` independent (query set, db set) problems.  Query set p = d_q + q_off[p]*32 with
+ * q_cnt[p] descriptors, likewise db; outputs at d_out_* + q_off[p].  q_off/q_cnt/db_off/db_cnt are DEVICE int arrays.
+ * max_q = max over p of q_cnt[p] (sizes the grid).  Asynchronous on `stream`. */
+int orbm_hamming_top2_batch_device(const uint8_t* d_q, const int* d_q_off, const int* d_q_cnt,
+                                   const uint8_t* d_db, const int* d_db_off, const int* d_db_cnt,
+                                   int npairs, int max_q, int* d_best_idx, int* d_best_dist, int* d_second_dist,
+                                   void* stream);
+/* All-pairs keyframe matching (BASELINE.json config 4): every keyframe holds `per_kf` descriptors; query keyframes
+ * [q_begin, q_end) of d_desc are matched against all n_kf keyframes.  d_count[(q-q_begin)*n_kf + k] = number of query
+ * descriptors of q whose top-2 against keyframe k passes best <= th_low && best < ratio*second (uint16).
+ * If d_best_kf / d_best_dist are non-NULL they receive, per query descriptor, the keyframe (!= q) holding its
+ * overall nearest descriptor and that distance.  Asynchronous on `stream`. */
+int orbm_allpairs_device(const uint8_t* d_desc, int n_kf, int per_kf, int q_begin, int q_end, int th_low, float ratio,
+                         uint16_t* d_count, int* d_best_kf, int* d_best_dist, void* stream);
+
+/* A DBoW2::FeatureVector (Thirdparty/DBoW2/DBoW2/FeatureVector.h:21-22, std::map<NodeId, vector<unsigned>>) flattened:
+ * node ids ascending, CSR offsets (n_nodes+1), feature indices (ascending inside a node, as transform() appends). */
+typedef struct orbm_featvec {
+    int n_nodes;
+    const int* node_ids;
+    const int* offsets;
+    const int* features;
+} orbm_featvec;
+
+/* One side of a search: the fields of KeyFrame / Frame the reference reads (include/KeyFrame.h:179-204,
+ * include/Frame.h:141-189), snapshotted by the caller under the reference's own locks. */
+typedef struct orbm_view {
+    int n;                      /* N */
+    const uint8_t* desc;        /* mDescriptors, n x 32 */
+    const uint8_t* flag;        /* per feature: SearchByBoW: 1 = has a MapPoint that is not bad;
+                                   SearchForTriangulation: 1 = GetMapPoint(i) != NULL.  May be NULL where unused. */
+    const float* angle;         /* mvKeysUn[i].angle (KeyFrame) / mvKeys[i].angle (Frame) */
+    const float* x;             /* mvKeysUn[i].pt.x   (triangulation only, else NULL) */
+    const float* y;             /* mvKeysUn[i].pt.y   (triangulation only) */
+    const int* octave;          /* mvKeysUn[i].octave (triangulation only) */
+    const float* uright;        /* mvuRight[i]        (triangulation only) */
+    orbm_featvec fv;            /* mFeatVec */
+} orbm_view;
+
+/* Replaces int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+ * (src/ORBmatcher.cc:159-291).  match21[F.n]: index of the KF feature whose MapPoint the reference stores in
+ * vpMapPointMatches[j], or -1.  *n_matches = return value of the reference. */
+int orbm_search_by_bow_kf_frame(const orbm_view* kf, const orbm_view* frame, float nnratio, int check_orientation,
+                                int* match21, int* n_matches, int device);
+/* Replaces int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+ * (src/ORBmatcher.cc:525-658).  match12[kf1.n]: index into KF2 (whose MapPoint the reference stores) or -1. */
+int orbm_search_by_bow_kf_kf(const orbm_view* kf1, const orbm_view* kf2, float nnratio, int check_orientation,
+                             int* match12, int* n_matches, int device);
+/* Replaces int ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)
+ * (src/ORBmatcher.cc:660-826, CheckDistEpipolarLine :140-157).  F12: row-major 3x3 float.  (ex, ey): epipole of KF1's
+ * centre in KF2 (:667-673).  scale_factors2 / level_sigma2_2: pKF2->mvScaleFactors / mvLevelSigma2 (n_levels2 entries).
+ * pairs_out[2*kf1.n] receives (idx1, idx2) ascending idx1; *n_pairs their number; *n_matches the reference's return. */
+int orbm_search_for_triangulation(const orbm_view* kf1, const orbm_view* kf2, const float* F12, float ex, float ey,
+                                  const float* scale_factors2, const float* level_sigma2_2, int n_levels2,
+                                  int only_stereo, int check_orientation,
+                                  int* pairs_out, int* n_pairs, int* n_matches, int device);
+/* Replaces ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1604-1645) on bin sizes; runs on the device as part of the
+ * searches above; this entry exposes it for tests.  ind[3]. */
+int orbm_three_maxima(const int* histo, int n_bins, int* ind, int device);
+
+/* POPC issue-rate microbenchmark (defines the matching roofline): returns measured 32-bit POPC results
+ * per second on `device` over a register-resident loop. */
+int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORB_B200_H_ */

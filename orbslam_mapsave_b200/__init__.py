@@ -1,0 +1,8 @@
+"""orbslam_mapsave_b200 — B200-native (sm_100a) ORB front-end: ORBextractor + ORBmatcher Hamming searches.
+
+The product is the CUDA library liborb_b200.so (csrc/, C ABI in include/orb_b200.h) and the C++ drop-in classes in
+host/.  This Python package only binds the C ABI for tests and bench.py.
+"""
+from .capi import OrbError, KP_DTYPE, LIB_PATH, lib, device_count   # noqa: F401
+from .extractor import ORBextractor                                  # noqa: F401
+from .matcher import ORBmatcher, FeatureVector, View, popc_peak      # noqa: F401

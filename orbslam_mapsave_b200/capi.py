@@ -1,0 +1,130 @@
+"""ctypes binding of liborb_b200.so (include/orb_b200.h) plus thin numpy/torch conveniences.
+
+This is plumbing only: every computation happens in the CUDA library.  Importing works without a GPU (so the CPU
+test-suite can check that the library loads and exports every symbol of the header); any compute call without a CUDA
+device raises OrbError — there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborb_b200.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+CAND_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("r", "<i4")])
+
+ORB_OK, ORB_ERR_CUDA, ORB_ERR_ARG, ORB_ERR_CAPACITY, ORB_ERR_OVERFLOW, ORB_ERR_GEOMETRY = 0, -1, -2, -3, -4, -5
+STAGE_PYRAMID, STAGE_FAST, STAGE_OCTREE, STAGE_BLUR, STAGE_DESCRIBE, STAGE_ALL = 1, 2, 4, 8, 16, 31
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+# every symbol include/orb_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "orb_last_error", "orb_device_count",
+    "orbx_create", "orbx_destroy", "orbx_tables", "orbx_level_size", "orbx_max_keypoints", "orbx_extract",
+    "orbx_extract_batch", "orbx_extract_batch_device", "orbx_check_status", "orbx_get_pyramid_level",
+    "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device",
+    "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
+    "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
+    "orbm_popc_peak",
+]
+
+
+class OrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"orb_b200 error {code}: {msg}")
+        self.code = code
+
+
+class FeatVecC(C.Structure):
+    _fields_ = [("n_nodes", C.c_int), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("features", C.c_void_p)]
+
+
+class ViewC(C.Structure):
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("flag", C.c_void_p), ("angle", C.c_void_p), ("x", C.c_void_p),
+                ("y", C.c_void_p), ("octave", C.c_void_p), ("uright", C.c_void_p), ("fv", FeatVecC)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raise loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OrbError(ORB_ERR_CUDA, f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                     "(make -C orbslam_mapsave_b200/csrc); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    L.orb_last_error.restype = C.c_char_p
+    L.orb_device_count.restype = i32
+    L.orbx_create.restype = i32
+    L.orbx_create.argtypes = [C.POINTER(vp), i32, f32, i32, i32, i32, i32, i32, i32, i32]
+    L.orbx_destroy.restype = None
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_tables.restype = i32
+    L.orbx_tables.argtypes = [vp] * 6
+    L.orbx_level_size.restype = i32
+    L.orbx_level_size.argtypes = [vp, i32, vp, vp]
+    L.orbx_max_keypoints.restype = i32
+    L.orbx_max_keypoints.argtypes = [vp]
+    L.orbx_extract.restype = i32
+    L.orbx_extract.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp]
+    L.orbx_extract_batch.restype = i32
+    L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, vp, i32, sz, vp, vp, i32, vp]
+    L.orbx_extract_batch_device.restype = i32
+    L.orbx_extract_batch_device.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp, vp]
+    L.orbx_check_status.restype = i32
+    L.orbx_check_status.argtypes = [vp]
+    L.orbx_get_pyramid_level.restype = i32
+    L.orbx_get_pyramid_level.argtypes = [vp, i32, i32, i32, vp, i32]
+    L.orbx_get_blurred_level.restype = i32
+    L.orbx_get_blurred_level.argtypes = [vp, i32, i32, vp, i32]
+    L.orbx_get_candidates.restype = i32
+    L.orbx_get_candidates.argtypes = [vp, i32, i32, vp, i32, vp]
+    L.orbx_launch_count.restype = C.c_longlong
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_run_stages_device.restype = i32
+    L.orbx_run_stages_device.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp, i32, vp]
+    L.orbm_descriptor_distance.restype = i32
+    L.orbm_descriptor_distance.argtypes = [vp, vp, i32, vp, i32]
+    L.orbm_hamming_top2.restype = i32
+    L.orbm_hamming_top2.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32]
+    L.orbm_hamming_top2_batch_device.restype = i32
+    L.orbm_hamming_top2_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.orbm_allpairs_device.restype = i32
+    L.orbm_allpairs_device.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.orbm_search_by_bow_kf_frame.restype = i32
+    L.orbm_search_by_bow_kf_frame.argtypes = [C.POINTER(ViewC), C.POINTER(ViewC), f32, i32, vp, vp, i32]
+    L.orbm_search_by_bow_kf_kf.restype = i32
+    L.orbm_search_by_bow_kf_kf.argtypes = [C.POINTER(ViewC), C.POINTER(ViewC), f32, i32, vp, vp, i32]
+    L.orbm_search_for_triangulation.restype = i32
+    L.orbm_search_for_triangulation.argtypes = [C.POINTER(ViewC), C.POINTER(ViewC), vp, f32, f32, vp, vp, i32, i32, i32,
+                                                vp, vp, vp, i32]
+    L.orbm_three_maxima.restype = i32
+    L.orbm_three_maxima.argtypes = [vp, i32, vp, i32]
+    L.orbm_popc_peak.restype = i32
+    L.orbm_popc_peak.argtypes = [i32, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != ORB_OK:
+        raise OrbError(rc, lib().orb_last_error().decode("utf-8", "replace"))
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a.data_ptr()))          # torch tensor
+
+
+def device_count():
+    return lib().orb_device_count()

@@ -1,0 +1,1070 @@
+// orb_extract.cu — B200 (sm_100a) implementation of ORB_SLAM2::ORBextractor's hot path behind the C ABI of
+// include/orb_b200.h.  Replaces src/ORBextractor.cc:409-478 (ctor, tables), :1110-1135 (ComputePyramid),
+// :764-852 (ComputeKeyPointsOctTree, cv::FAST per cell with the iniThFAST/minThFAST retry), :538-762
+// (DistributeOctTree), :76-103 (IC_Angle), :1088-1089 (GaussianBlur) and :107-146 (computeOrbDescriptor) of the
+// reference.  Designed batch-first: every kernel runs over (work item, frame) so that a pass over B frames is ~20
+// launches; nothing here is a translation of the reference's serial loops.
+//
+// HBM layout per frame (all u8):  [level 0 buffer][level 1 buffer]...   each buffer = (h+38) rows x pitch bytes, the
+// level's pixel (x,y) at row y+19, column x+32 (32 keeps 4-pixel groups word-aligned; columns [13,32) and
+// [32+w, 32+w+19) hold the REFLECT_101 border the reference's copyMakeBorder produces).  The blurred pyramid uses
+// the same geometry in a second block.
+#include "orb_common.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+void orb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* orb_last_error(void) { return g_err; }
+extern "C" int orb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_OX 32            // column of level pixel x=0 inside a level buffer
+#define ORBX_OY 19            // row of level pixel y=0  (EDGE_THRESHOLD, ORBextractor.cc:73)
+#define ORBX_EDGE 19
+#define ORBX_MINB 16          // minBorder = EDGE_THRESHOLD-3 (ORBextractor.cc:772)
+#define ORBX_FAST_THREADS 128
+#define ORBX_FAST_LOCAL_CAP 1024
+#define ORBX_OCT_THREADS 512
+
+struct LevelPlan {
+    int w, h, pitch, brows;
+    unsigned off;                         // byte offset of the level buffer inside a frame block
+    int nCols, nRows, wCell, hCell, cellBase;
+    int maxBX, maxBY;                     // w-16, h-16
+    int quota, nIni;
+    float hX;
+    int candOff, candCap, selOff, selCap;
+    float scale, kpSize;
+    int xtabOff, ytabOff;
+};
+struct Plan {
+    int nlevels, iniTh, minTh;
+    int totalCells, candTotal, selTotal, maxNodes, sortN;
+    int tilePitch, tileRows, scorePitch, scoreRows;   // FAST shared-memory tile geometry (max over levels)
+    int width, height;
+    unsigned long long frameBytes;
+    int umax[16];
+    LevelPlan lv[ORBX_MAX_LEVELS];
+};
+struct ResizeTap { int s; short c0, c1; };
+
+// =====================================================================================================
+// K1  pyramid.  Level 0 = masked copy + REFLECT_101 border; level l = fixed-point bilinear resize of level l-1
+// (cv::resize INTER_LINEAR 8UC1: 11-bit coefficients, the (>>4, *b, >>16, +2, >>2) vertical pass) + border, fused:
+// border pixels are evaluated at their reflected coordinate, so each level is produced in one pass.
+// One thread = 4 horizontally adjacent buffer bytes -> one 32-bit store.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_level0(const __grid_constant__ Plan P, const u8* __restrict__ images,
+                                                const u8* __restrict__ masks, u8* __restrict__ pyr) {
+    const LevelPlan& L = P.lv[0];
+    const int bx = (blockIdx.x * 64 + threadIdx.x) * 4, by = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
+    if (bx >= L.pitch || by >= L.brows) return;
+    const size_t fo = (size_t)f * P.width * P.height;
+    const int ry = dev_reflect101(by - ORBX_OY, L.h);
+    const u8* src = images + fo + (size_t)ry * P.width;
+    const u8* msk = masks ? masks + fo + (size_t)ry * P.width : nullptr;
+    u32 out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int rx = dev_reflect101(bx + k - ORBX_OX, L.w);
+        u32 v = __ldg(src + rx);
+        if (msk && __ldg(msk + rx) == 0) v = 0;
+        out |= v << (8 * k);
+    }
+    *reinterpret_cast<u32*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)by * L.pitch + bx) = out;
+}
+
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, int level, u8* __restrict__ pyr,
+                                                const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab) {
+    const LevelPlan& L = P.lv[level];
+    const LevelPlan& S = P.lv[level - 1];
+    const int bx = (blockIdx.x * 64 + threadIdx.x) * 4, by = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
+    if (bx >= L.pitch || by >= L.brows) return;
+    u8* frame = pyr + (size_t)f * P.frameBytes;
+    const u8* src = frame + S.off + (size_t)ORBX_OY * S.pitch + ORBX_OX;
+    const ResizeTap ty = ytab[L.ytabOff + dev_reflect101(by - ORBX_OY, L.h)];
+    const int sy0 = min(max(ty.s, 0), S.h - 1), sy1 = min(max(ty.s + 1, 0), S.h - 1);
+    const u8* r0p = src + (size_t)sy0 * S.pitch;
+    const u8* r1p = src + (size_t)sy1 * S.pitch;
+    u32 out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const ResizeTap tx = xtab[L.xtabOff + dev_reflect101(bx + k - ORBX_OX, L.w)];
+        const int sx = tx.s, sx1 = min(sx + 1, S.w - 1);
+        const int r0 = r0p[sx] * tx.c0 + r0p[sx1] * tx.c1;
+        const int r1 = r1p[sx] * tx.c0 + r1p[sx1] * tx.c1;
+        int v = (((ty.c0 * (r0 >> 4)) >> 16) + ((ty.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        out |= (u32)v << (8 * k);
+    }
+    *reinterpret_cast<u32*>(frame + L.off + (size_t)by * L.pitch + bx) = out;
+}
+
+// =====================================================================================================
+// K2+K3  FAST-9/16 per grid cell: score map, in-cell 3x3 NMS, iniThFAST -> minThFAST retry, emission.
+// One CTA per (cell, frame).  Uses the single-score-map formulation: the FAST score does not depend on
+// the threshold, so "cv::FAST(cell, ini) or, if empty, cv::FAST(cell, min)" == NMS over scores computed at minTh,
+// then keep score >= ini unless that set is empty.  Candidates carry (cell id, y, x) as their order key, which is
+// the reference's vToDistributeKeys order (cell row-major, then FAST's y-then-x order).
+// =====================================================================================================
+__device__ __forceinline__ bool has9(u32 m) {
+    m |= m << 16;
+    u32 r = m & (m >> 1);
+    r &= r >> 2;
+    r &= r >> 4;
+    r &= m >> 8;
+    return (r & 0xFFFFu) != 0;
+}
+
+__device__ __forceinline__ int fast_score(const u8* c, int TP, int t) {
+    // returns 0 if not a FAST-9 corner at threshold t, else cornerScore (max threshold keeping it a corner)
+    const int v = c[0];
+    const int p0 = c[3 * TP], p4 = c[3], p8 = c[-3 * TP], p12 = c[-3];
+    const int hi = v + t, lo = v - t;
+    const int nb = (p0 > hi) + (p4 > hi) + (p8 > hi) + (p12 > hi);
+    const int nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
+    if (nb < 2 && nd < 2) return 0;
+    int d[16];
+    d[0] = v - p0; d[4] = v - p4; d[8] = v - p8; d[12] = v - p12;
+    d[1] = v - c[3 * TP + 1]; d[2] = v - c[2 * TP + 2]; d[3] = v - c[TP + 3];
+    d[5] = v - c[-TP + 3]; d[6] = v - c[-2 * TP + 2]; d[7] = v - c[-3 * TP + 1];
+    d[9] = v - c[-3 * TP - 1]; d[10] = v - c[-2 * TP - 2]; d[11] = v - c[-TP - 3];
+    d[13] = v - c[TP - 3]; d[14] = v - c[2 * TP - 2]; d[15] = v - c[3 * TP - 1];
+    u32 md = 0, mb = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        md |= (u32)(d[k] > t) << k;
+        mb |= (u32)(d[k] < -t) << k;
+    }
+    if (!has9(md) && !has9(mb)) return 0;
+    // A = max over the 16 arcs of min(d over 9 contiguous), B likewise on -d; score = max(A,B)-1
+    int lo2[16], hi2[16], lo4[16], hi4[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
+#pragma unroll
+    for (int k = 0; k < 16; k++) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
+    int A = -256, Bm = 256;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+        A = max(A, lo9);
+        Bm = min(Bm, hi9);
+    }
+    return max(A, -Bm) - 1;
+}
+
+__global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
+                                                             uint2* __restrict__ cand, int* __restrict__ candCount,
+                                                             int* __restrict__ status) {
+    extern __shared__ __align__(16) u8 smem[];
+    __shared__ u32 s_list[ORBX_FAST_LOCAL_CAP];
+    __shared__ int s_nloc, s_nini, s_base, s_emit;
+
+    int l = 0;
+    while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].cellBase) l++;
+    const LevelPlan& L = P.lv[l];
+    const int c = blockIdx.x - L.cellBase, f = blockIdx.y;
+    const int ci = c / L.nCols, cj = c - ci * L.nCols;
+    const int iniX = ORBX_MINB + cj * L.wCell, iniY = ORBX_MINB + ci * L.hCell;
+    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6) return;          // ORBextractor.cc:793,802
+    const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
+    const int tw = maxX - iniX, th = maxY - iniY, dw = tw - 6, dh = th - 6;
+    if (dw <= 0 || dh <= 0) return;                                   // cv::FAST on a ROI < 7 px finds nothing
+
+    const int TP = P.tilePitch, SP = P.scorePitch;
+    u8* tile = smem;
+    u8* score = smem + (size_t)P.tileRows * TP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_nloc = 0; s_nini = 0; s_emit = 0; }
+
+    const u8* src = pyr + (size_t)f * P.frameBytes + L.off + (size_t)(iniY + ORBX_OY) * L.pitch + iniX + ORBX_OX;
+    for (int ty = warp; ty < th; ty += ORBX_FAST_THREADS / 32)
+        for (int tx = lane; tx < tw; tx += 32) tile[ty * TP + tx] = __ldg(src + (size_t)ty * L.pitch + tx);
+    for (int i = tid; i < (dh + 2) * SP; i += ORBX_FAST_THREADS) score[i] = 0;
+    __syncthreads();
+
+    const int t = P.minTh;
+    for (int py = warp; py < dh; py += ORBX_FAST_THREADS / 32)
+        for (int px = lane; px < dw; px += 32) {
+            const int s = fast_score(tile + (py + 3) * TP + px + 3, TP, t);
+            if (s > 0) score[(py + 1) * SP + px + 1] = (u8)s;
+        }
+    __syncthreads();
+
+    for (int py = warp; py < dh; py += ORBX_FAST_THREADS / 32)
+        for (int px = lane; px < dw; px += 32) {
+            const u8* sp = score + (py + 1) * SP + px + 1;
+            const int s = sp[0];
+            if (s == 0) continue;
+            const bool keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
+                              s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
+            if (!keep) continue;
+            const int slot = atomicAdd(&s_nloc, 1);
+            if (slot < ORBX_FAST_LOCAL_CAP) s_list[slot] = ((u32)s << 16) | ((u32)py << 8) | (u32)px;
+            if (s >= P.iniTh) atomicAdd(&s_nini, 1);
+        }
+    __syncthreads();
+    const int nloc = min(s_nloc, ORBX_FAST_LOCAL_CAP);
+    if (nloc == 0) return;
+    const int T = s_nini > 0 ? P.iniTh : P.minTh;
+    const int nEmit = s_nini > 0 ? s_nini : nloc;
+    if (tid == 0) {
+        const int base = atomicAdd(&candCount[f * P.nlevels + l], nEmit);
+        if (base + nEmit > L.candCap) atomicOr(status, ORB_DEV_CAND_OVERFLOW);
+        s_base = base;
+    }
+    __syncthreads();
+    uint2* out = cand + (size_t)f * P.candTotal + L.candOff;
+    for (int e = tid; e < nloc; e += ORBX_FAST_THREADS) {
+        const u32 k = s_list[e];
+        const int s = k >> 16;
+        if (s < T) continue;
+        const int slot = s_base + atomicAdd(&s_emit, 1);
+        if (slot >= L.candCap) continue;
+        const int x = iniX + 3 + (int)(k & 0xFF), y = iniY + 3 + (int)((k >> 8) & 0xFF);
+        out[slot] = make_uint2((u32)x | ((u32)y << 16), ((u32)s << 24) | (u32)c);
+    }
+}
+
+// =====================================================================================================
+// K4  DistributeOctTree, one CTA per (level, frame).  The reference's std::list walk is restated as data-parallel
+// passes: node membership is a pure function of the root box and (x,y), list order after a pass is
+// [children in reverse creation order][untouched nodes in their old order], and the sequential "expand the largest
+// node until there are N" tail is a sort + prefix sum + cut (see DESIGN.md for the proof sketch).
+// Tie-break among equal-size nodes = creation sequence (the reference's is the heap pointer; canonical rule).
+// =====================================================================================================
+struct OctSmem {
+    int4* boxA; int4* boxB;
+    int* cntA; int* cntB;
+    int* cc;        // 4 per node: child counts, then child list positions
+    int* aux;       // per node scratch (nch / creation prefix)
+    int* aux2;      // per node scratch (stay rank / sorted nch)
+    int* div;       // per node: divides in this step
+    u64* sortb;     // sortN entries
+};
+
+__device__ int block_excl_scan(int* a, int n, int* wsum) {
+    // in-place exclusive prefix sum of a[0..n) by the whole CTA; returns the total.  wsum: 34 ints of smem.
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int K = (n + T - 1) / T;
+    const int beg = min(tid * K, n), end = min(beg + K, n);
+    int s = 0;
+    for (int i = beg; i < end; i++) s += a[i];
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int ws = lane < (T >> 5) ? wsum[lane] : 0;
+        int wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+        wsum[lane] = wi - ws;
+        if (lane == 31) wsum[32] = wi;
+    }
+    __syncthreads();
+    int base = wsum[w] + inc - s;
+    for (int i = beg; i < end; i++) { const int v = a[i]; a[i] = base; base += v; }
+    const int total = wsum[32];
+    __syncthreads();
+    return total;
+}
+
+__device__ void block_bitonic_sort(u64* a, int n /*pow2*/) {
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const u64 x = a[i], y = a[p];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_constant__ Plan P, const uint2* __restrict__ cand,
+                                                              const int* __restrict__ candCount, u32* __restrict__ nodeOf,
+                                                              uint2* __restrict__ sel, int* __restrict__ selCount,
+                                                              int* __restrict__ status) {
+    extern __shared__ __align__(16) u8 smem[];
+    __shared__ int s_wsum[34];
+    __shared__ int s_nToExpand, s_cut, s_rootMap[64];
+    const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+    const LevelPlan& L = P.lv[l];
+    const int M = P.maxNodes, N = L.quota;
+    const int n = min(candCount[f * P.nlevels + l], L.candCap);
+    const uint2* keys = cand + (size_t)f * P.candTotal + L.candOff;
+    u32* nof = nodeOf + (size_t)f * P.candTotal + L.candOff;
+    uint2* out = sel + (size_t)f * P.selTotal + L.selOff;
+
+    OctSmem S;
+    {
+        u8* p = smem;
+        S.boxA = (int4*)p; p += sizeof(int4) * M;
+        S.boxB = (int4*)p; p += sizeof(int4) * M;
+        S.sortb = (u64*)p; p += sizeof(u64) * P.sortN;
+        S.cntA = (int*)p; p += 4 * M;
+        S.cntB = (int*)p; p += 4 * M;
+        S.cc = (int*)p; p += 16 * M;
+        S.aux = (int*)p; p += 4 * M;
+        S.aux2 = (int*)p; p += 4 * M;
+        S.div = (int*)p; p += 4 * M;
+    }
+    if (n == 0) { if (tid == 0) selCount[f * P.nlevels + l] = 0; return; }
+
+    // ---- roots (ORBextractor.cc:542-584)
+    const int nIni = L.nIni;
+    const int bw = L.maxBX - ORBX_MINB, bh = L.maxBY - ORBX_MINB;
+    for (int i = tid; i < nIni; i += T) S.cntB[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < n; k += T) {
+        const int xr = (int)(keys[k].x & 0xFFFF) - ORBX_MINB;
+        int r = (int)__fdiv_rn((float)xr, L.hX);
+        r = min(max(r, 0), nIni - 1);
+        nof[k] = (u32)r;
+        atomicAdd(&S.cntB[r], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int i = 0; i < nIni; i++) {
+            if (S.cntB[i] > 0) {
+                S.boxA[m] = make_int4((int)(L.hX * (float)i), (int)(L.hX * (float)(i + 1)), 0, bh);
+                S.cntA[m] = S.cntB[i];
+                s_rootMap[i] = m++;
+            } else s_rootMap[i] = -1;
+        }
+        s_cut = m;
+    }
+    __syncthreads();
+    int size = s_cut;
+    for (int k = tid; k < n; k += T) nof[k] = (u32)s_rootMap[nof[k]];
+    __syncthreads();
+    (void)bw;
+
+    int4* box = S.boxA; int4* nbox = S.boxB;
+    int* cnt = S.cntA; int* ncnt = S.cntB;
+    bool sweep = false;
+    while (true) {
+        const int prevSize = size;
+        // 1. quadrant of every key that lives in a multi-key node; child counts
+        for (int i = tid; i < 4 * size; i += T) S.cc[i] = 0;
+        if (tid == 0) { s_nToExpand = 0; s_cut = 0x7fffffff; }
+        __syncthreads();
+        for (int k = tid; k < n; k += T) {
+            const int nd = (int)(nof[k] & 0xFFFF);
+            if (cnt[nd] > 1) {
+                const uint2 key = keys[k];
+                const int x = (int)(key.x & 0xFFFF) - ORBX_MINB, y = (int)(key.x >> 16) - ORBX_MINB;
+                const int4 b = box[nd];
+                const int mx = b.x + ((b.y - b.x + 1) >> 1), my = b.z + ((b.w - b.z + 1) >> 1);
+                const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+                atomicAdd(&S.cc[nd * 4 + q], 1);
+                nof[k] = (u32)nd | ((u32)q << 16);
+            }
+        }
+        __syncthreads();
+        // 2. number of non-empty children per multi node
+        for (int i = tid; i < size; i += T) {
+            int nch = 0;
+            if (cnt[i] > 1) nch = (S.cc[4 * i] > 0) + (S.cc[4 * i + 1] > 0) + (S.cc[4 * i + 2] > 0) + (S.cc[4 * i + 3] > 0);
+            S.aux[i] = nch;
+        }
+        __syncthreads();
+        int C, newSize;
+        if (!sweep) {
+            // full pass (ORBextractor.cc:597-664): every multi node divides, processed in list order
+            for (int i = tid; i < size; i += T) {
+                S.div[i] = cnt[i] > 1;
+                if (cnt[i] > 1) {
+                    const int e = (S.cc[4 * i] > 1) + (S.cc[4 * i + 1] > 1) + (S.cc[4 * i + 2] > 1) + (S.cc[4 * i + 3] > 1);
+                    if (e) atomicAdd(&s_nToExpand, e);
+                }
+            }
+            __syncthreads();
+            C = block_excl_scan(S.aux, size, s_wsum);          // aux[i] = creation index of node i's first child
+        } else {
+            // final phase sweep (ORBextractor.cc:675-736): multi nodes sorted by (size, creation seq) ascending and walked
+            // from the back == (size desc, list position asc); stop as soon as the list holds N nodes.
+            for (int i = tid; i < P.sortN; i += T) S.sortb[i] = ~0ull;
+            for (int i = tid; i < size; i += T) { S.aux2[i] = cnt[i] > 1; S.div[i] = 0; }
+            __syncthreads();
+            const int ncand = block_excl_scan(S.aux2, size, s_wsum);
+            for (int i = tid; i < size; i += T)
+                if (cnt[i] > 1) S.sortb[S.aux2[i]] = ((u64)(0xFFFFFFFFu - (u32)cnt[i]) << 32) | (u32)i;
+            __syncthreads();
+            if (ncand == 0) break;                                             // nothing left to expand (size == prevSize)
+            int sn = 2;
+            while (sn < ncand) sn <<= 1;
+            block_bitonic_sort(S.sortb, sn);
+            for (int t2 = tid; t2 < ncand; t2 += T) S.aux2[t2] = S.aux[(int)(S.sortb[t2] & 0xFFFFFFFFu)];
+            __syncthreads();
+            // inclusive list size after expanding sorted node t: size + sum_{u<=t}(nch_u - 1)
+            for (int t2 = tid; t2 < ncand; t2 += T) S.cc[t2] = S.aux2[t2];     // keep nch_t (cc is free now)
+            __syncthreads();
+            block_excl_scan(S.aux2, ncand, s_wsum);                            // aux2[t] = q_t
+            for (int t2 = tid; t2 < ncand; t2 += T) {
+                const int incl = size + S.aux2[t2] + S.cc[t2] - (t2 + 1);
+                if (incl >= N) atomicMin(&s_cut, t2);
+            }
+            __syncthreads();
+            const int cut = min(s_cut, ncand - 1);
+            C = S.aux2[cut] + S.cc[cut];
+            __syncthreads();
+            for (int t2 = tid; t2 <= cut; t2 += T) {
+                const int i = (int)(S.sortb[t2] & 0xFFFFFFFFu);
+                S.div[i] = 1;
+                S.aux[i] = S.aux2[t2];                                         // creation index of its first child
+            }
+            __syncthreads();
+            // recompute the child counts the scan scratch overwrote
+            for (int i = tid; i < 4 * size; i += T) S.cc[i] = 0;
+            __syncthreads();
+            for (int k = tid; k < n; k += T) {
+                const u32 v = nof[k];
+                const int nd = (int)(v & 0xFFFF);
+                if (cnt[nd] > 1) atomicAdd(&S.cc[nd * 4 + (int)((v >> 16) & 3)], 1);
+            }
+            __syncthreads();
+        }
+        // 3. list positions: children of dividing nodes go to the front in reverse creation order, the rest keep
+        //    their order behind them
+        for (int i = tid; i < size; i += T) S.aux2[i] = S.div[i] ? 0 : 1;
+        __syncthreads();
+        const int nStay = block_excl_scan(S.aux2, size, s_wsum);
+        newSize = C + nStay;
+        if (newSize > M) {                                                     // cannot happen (bound N+3); be safe
+            if (tid == 0) atomicOr(status, ORB_DEV_NODE_OVERFLOW);
+            newSize = size;
+            break;
+        }
+        for (int i = tid; i < size; i += T) {
+            if (S.div[i]) {
+                const int4 b = box[i];
+                const int mx = b.x + ((b.y - b.x + 1) >> 1), my = b.z + ((b.w - b.z + 1) >> 1);
+                int q = S.aux[i];
+                const int c0 = S.cc[4 * i], c1 = S.cc[4 * i + 1], c2 = S.cc[4 * i + 2], c3 = S.cc[4 * i + 3];
+                int pos;
+                if (c0 > 0) { pos = C - 1 - q++; nbox[pos] = make_int4(b.x, mx, b.z, my); ncnt[pos] = c0; S.cc[4 * i] = pos; }
+                if (c1 > 0) { pos = C - 1 - q++; nbox[pos] = make_int4(mx, b.y, b.z, my); ncnt[pos] = c1; S.cc[4 * i + 1] = pos; }
+                if (c2 > 0) { pos = C - 1 - q++; nbox[pos] = make_int4(b.x, mx, my, b.w); ncnt[pos] = c2; S.cc[4 * i + 2] = pos; }
+                if (c3 > 0) { pos = C - 1 - q++; nbox[pos] = make_int4(mx, b.y, my, b.w); ncnt[pos] = c3; S.cc[4 * i + 3] = pos; }
+            } else {
+                const int pos = C + S.aux2[i];
+                nbox[pos] = box[i];
+                ncnt[pos] = cnt[i];
+                S.aux2[i] = pos;
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < n; k += T) {
+            const u32 v = nof[k];
+            const int nd = (int)(v & 0xFFFF);
+            nof[k] = (u32)(S.div[nd] ? S.cc[nd * 4 + (int)((v >> 16) & 3)] : S.aux2[nd]);
+        }
+        const int nToExpand = s_nToExpand;
+        __syncthreads();
+        size = newSize;
+        { int4* tb = box; box = nbox; nbox = tb; int* tc = cnt; cnt = ncnt; ncnt = tc; }
+        if (size >= N || size == prevSize) break;                              // ORBextractor.cc:668, 733
+        if (!sweep && size + 3 * nToExpand > N) sweep = true;                  // :672
+    }
+
+    // ---- one keypoint per node: max response, first in input order wins ties (ORBextractor.cc:741-759)
+    u64* best = (u64*)S.cc;
+    for (int i = tid; i < size; i += T) best[i] = 0ull;
+    __syncthreads();
+    for (int k = tid; k < n; k += T) {
+        const uint2 key = keys[k];
+        const u64 order = ((u64)(key.y & 0xFFFFFFu) << 32) | ((u64)(key.x >> 16) << 16) | (u64)(key.x & 0xFFFF);
+        const u64 v = ((u64)(key.y >> 24) << 56) | (0x00FFFFFFFFFFFFFFull - order);
+        atomicMax(&best[nof[k] & 0xFFFF], v);
+    }
+    __syncthreads();
+    for (int i = tid; i < size; i += T) {
+        const u64 v = best[i];
+        const u64 order = 0x00FFFFFFFFFFFFFFull - (v & 0x00FFFFFFFFFFFFFFull);
+        const u32 x = (u32)(order & 0xFFFF), y = (u32)((order >> 16) & 0xFFFF);
+        if (i < L.selCap) out[i] = make_uint2(x | (y << 16), (u32)(v >> 56));
+    }
+    if (tid == 0) selCount[f * P.nlevels + l] = min(size, L.selCap);
+}
+
+// =====================================================================================================
+// K5  GaussianBlur 7x7 sigma 2 (OpenCV 4.13 fixed-point: taps [18,34,48,56,48,34,18]/256 each way,
+// out = (sum + 32768) >> 16).  Reads the bordered level (REFLECT_101 is already materialised), writes the blurred
+// level in the same geometry.  Tile 128x32 outputs per CTA; separable through shared memory.
+// =====================================================================================================
+#define BL_TW 128
+#define BL_TH 32
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, int level, const u8* __restrict__ pyr,
+                                              u8* __restrict__ blur) {
+    __shared__ u32 s_src[BL_TH + 6][BL_TW / 4 + 2];
+    __shared__ __align__(8) u16 s_h[BL_TH + 6][BL_TW];
+    const LevelPlan& L = P.lv[level];
+    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH, f = blockIdx.z;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const u8* src = pyr + (size_t)f * P.frameBytes + L.off;
+    const int wordsPerRow = L.pitch >> 2;
+    // stage rows y0-3 .. y0+TH+2, words covering x0-4 .. x0+TW+3
+    for (int i = tid; i < (BL_TH + 6) * (BL_TW / 4 + 2); i += 256) {
+        const int r = i / (BL_TW / 4 + 2), wx = i - r * (BL_TW / 4 + 2);
+        const int by = y0 - 3 + r + ORBX_OY, bwx = ((x0 + ORBX_OX) >> 2) - 1 + wx;
+        u32 v = 0;
+        if (by < L.brows && bwx < wordsPerRow) v = __ldg(reinterpret_cast<const u32*>(src + (size_t)by * L.pitch) + bwx);
+        s_src[r][wx] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < (BL_TH + 6) * (BL_TW / 4); i += 256) {
+        const int r = i / (BL_TW / 4), wx = i - r * (BL_TW / 4);
+        const u32 a = s_src[r][wx], b = s_src[r][wx + 1], c = s_src[r][wx + 2];
+        // bytes: a = x-4..x-1, b = x..x+3, c = x+4..x+7   (x = x0 + 4*wx)
+        int p[10];
+        p[0] = (a >> 8) & 0xFF; p[1] = (a >> 16) & 0xFF; p[2] = a >> 24;
+        p[3] = b & 0xFF; p[4] = (b >> 8) & 0xFF; p[5] = (b >> 16) & 0xFF; p[6] = b >> 24;
+        p[7] = c & 0xFF; p[8] = (c >> 8) & 0xFF; p[9] = (c >> 16) & 0xFF;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int h = 18 * (p[k] + p[k + 6]) + 34 * (p[k + 1] + p[k + 5]) + 48 * (p[k + 2] + p[k + 4]) + 56 * p[k + 3];
+            s_h[r][4 * wx + k] = (u16)h;
+        }
+    }
+    __syncthreads();
+    u8* dst = blur + (size_t)f * P.frameBytes + L.off;
+    for (int i = tid; i < BL_TH * (BL_TW / 4); i += 256) {
+        const int r = i / (BL_TW / 4), wx = i - r * (BL_TW / 4);
+        const int x = x0 + 4 * wx, y = y0 + r;
+        if (x >= L.w || y >= L.h) continue;
+        u32 o = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = 4 * wx + k;
+            const int v = 18 * ((int)s_h[r][c] + s_h[r + 6][c]) + 34 * ((int)s_h[r + 1][c] + s_h[r + 5][c]) +
+                          48 * ((int)s_h[r + 2][c] + s_h[r + 4][c]) + 56 * (int)s_h[r + 3][c];
+            o |= (u32)((v + 32768) >> 16) << (8 * k);
+        }
+        *reinterpret_cast<u32*>(dst + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = o;
+    }
+}
+
+// =====================================================================================================
+// K6  IC_Angle + rBRIEF, one warp per selected keypoint.  Orientation: int32 moments over the radius-15 disc of the
+// UNBLURRED level, cv::fastAtan2 polynomial with explicit round-to-nearest mul/add (no FMA contraction).
+// Descriptor: lane i computes byte i (8 point pairs) of the 256-bit string from the BLURRED level.
+// Writes the final cv::KeyPoint (coordinates scaled to level 0) and descriptor at their level-major position.
+// =====================================================================================================
+__constant__ signed char c_pattern[1024] = {
+#include "orb_pattern_31.inc"
+};
+
+__device__ __forceinline__ float dev_fast_atan2(float y, float x) {
+    const float s = (float)(180.0 / 3.1415926535897932384626433832795);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
+    const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
+                                                  const u8* __restrict__ blur, const uint2* __restrict__ sel,
+                                                  const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
+                                                  u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
+                                                  int* __restrict__ status) {
+    __shared__ signed char s_pat[1024];
+    for (int i = threadIdx.x; i < 256; i += 256) reinterpret_cast<int*>(s_pat)[i] = reinterpret_cast<const int*>(c_pattern)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, f = blockIdx.y;
+    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (slot >= P.selTotal) return;
+    int l = 0;
+    while (l + 1 < P.nlevels && slot >= P.lv[l + 1].selOff) l++;
+    const LevelPlan& L = P.lv[l];
+    const int idx = slot - L.selOff;
+    const int* sc = selCount + f * P.nlevels;
+    int before = 0, total = 0;
+    for (int i = 0; i < P.nlevels; i++) { const int c = sc[i]; if (i < l) before += c; total += c; }
+    if (slot == 0 && lane == 0) {
+        nOut[f] = total;
+        if (total > cap) atomicOr(status, ORB_DEV_OUT_OVERFLOW);
+    }
+    if (idx >= sc[l]) return;
+    const int pos = before + idx;
+    if (pos >= cap) return;
+    const uint2 k = sel[(size_t)f * P.selTotal + slot];
+    const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
+    const size_t cofs = (size_t)f * P.frameBytes + L.off + (size_t)(ky + ORBX_OY) * L.pitch + kx + ORBX_OX;
+
+    // ---- IC_Angle (ORBextractor.cc:76-103): lane v+15 sums row v of the disc
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - 15;
+        const int d = P.umax[v < 0 ? -v : v];
+        const u8* row = pyr + cofs + (ptrdiff_t)v * L.pitch;
+        int rs = 0;
+        for (int u = -d; u <= d; u++) { const int I = row[u]; m10 += u * I; rs += I; }
+        m01 = v * rs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+    const float angle = dev_fast_atan2((float)m01, (float)m10);
+
+    // ---- computeOrbDescriptor (ORBextractor.cc:107-146)
+    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    float a, b;
+    if (lane == 0) { a = (float)cos((double)ang); b = (float)sin((double)ang); }
+    a = __shfl_sync(0xffffffffu, a, 0);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    const u8* center = blur + cofs;
+    const signed char* pat = s_pat + lane * 32;
+    u32 val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = center[(ptrdiff_t)r0 * L.pitch + q0], t1 = center[(ptrdiff_t)r1 * L.pitch + q1];
+        val |= (u32)(t0 < t1) << j;
+    }
+    descOut[((size_t)f * cap + pos) * 32 + lane] = (u8)val;
+    if (lane == 0) {
+        orbx_keypoint kp;
+        kp.x = (float)kx; kp.y = (float)ky;
+        if (l != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // :1098-1104
+        kp.size = L.kpSize; kp.angle = angle; kp.response = (float)k.y; kp.octave = l; kp.class_id = -1;
+        kpOut[(size_t)f * cap + pos] = kp;
+    }
+}
+
+// =====================================================================================================
+// Host side: planning (the ORBextractor constructor's tables + geometry), workspace, launch sequencing
+// =====================================================================================================
+static inline int h_cvRoundF(float v) { return (int)nearbyintf(v); }
+static inline int h_cvRoundD(double v) { return (int)nearbyint(v); }
+static inline int h_cvFloor(double v) { int i = (int)v; return i - (i > v); }
+static inline int h_cvCeil(double v) { int i = (int)v; return i + (i < v); }
+
+struct orbx_extractor {
+    int nfeatures, nlevels, iniTh, minTh, device, maxBatch, candPerCell;
+    double scaleFactor;
+    std::vector<float> sf, isf, s2, is2;
+    std::vector<int> quota;
+    Plan plan;
+    cudaStream_t stream = nullptr;
+    // device workspace
+    u8 *d_pyr = nullptr, *d_blur = nullptr, *d_in = nullptr, *d_mask = nullptr, *d_desc = nullptr;
+    uint2 *d_cand = nullptr, *d_sel = nullptr;
+    u32* d_nodeOf = nullptr;
+    int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr, *d_n = nullptr;
+    orbx_keypoint* d_kp = nullptr;
+    ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
+    int capInternal = 0;
+    size_t fastSmem = 0, octSmem = 0;
+    long long launches = 0;
+    int lastFrames = 0;
+    std::mutex mu;
+};
+
+static void build_resize_taps(int ssize, int dsize, bool clampX, std::vector<ResizeTap>& out) {
+    // cv::resize INTER_LINEAR coefficient tables (OpenCV imgproc resize.cpp): scale = 1/((double)dsize/ssize)
+    const double inv_scale = (double)dsize / ssize, scale = 1. / inv_scale;
+    for (int d = 0; d < dsize; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int s = h_cvFloor(fx);
+        fx -= s;
+        if (clampX) {
+            if (s < 0) { fx = 0; s = 0; }
+            if (s >= ssize - 1) { fx = 0; s = ssize - 1; }
+        }
+        ResizeTap t;
+        t.s = s;
+        t.c0 = (short)h_cvRoundF((1.f - fx) * 2048.f);
+        t.c1 = (short)h_cvRoundF(fx * 2048.f);
+        out.push_back(t);
+    }
+}
+
+static int make_plan(orbx_extractor* ex, int width, int height) {
+    Plan& P = ex->plan;
+    memset(&P, 0, sizeof(P));
+    const int nl = ex->nlevels;
+    P.nlevels = nl; P.iniTh = ex->iniTh; P.minTh = ex->minTh; P.width = width; P.height = height;
+    // umax (ORBextractor.cc:451-468)
+    {
+        int v, v0, vmax = h_cvFloor(15 * sqrt(2.f) / 2 + 1), vmin = h_cvCeil(15 * sqrt(2.f) / 2);
+        const double hp2 = 15 * 15;
+        for (v = 0; v <= vmax; ++v) P.umax[v] = h_cvRoundD(sqrt(hp2 - v * v));
+        for (v = 15, v0 = 0; v >= vmin; --v) {
+            while (P.umax[v0] == P.umax[v0 + 1]) ++v0;
+            P.umax[v] = v0;
+            ++v0;
+        }
+    }
+    std::vector<ResizeTap> xt, yt;
+    size_t off = 0;
+    int cellBase = 0, candOff = 0, selOff = 0, maxNodes = 8, maxCW = 1, maxCH = 1;
+    for (int l = 0; l < nl; l++) {
+        LevelPlan& L = P.lv[l];
+        L.w = h_cvRoundF((float)width * ex->isf[l]);                       // ORBextractor.cc:1114-1115
+        L.h = h_cvRoundF((float)height * ex->isf[l]);
+        ORB_REQUIRE(L.w >= 62 && L.h >= 62 && L.w <= 65000 && L.h <= 65000, ORB_ERR_GEOMETRY,
+                    "pyramid level %d is %dx%d; the reference needs every level >= 62 px (ORBextractor.cc:783-786)", l, L.w, L.h);
+        L.pitch = (int)orb_align_up((size_t)ORBX_OX + L.w + ORBX_EDGE, 64);
+        L.brows = L.h + 2 * ORBX_EDGE;
+        L.off = (unsigned)off;
+        off += orb_align_up((size_t)L.pitch * L.brows, 256);
+        L.maxBX = L.w - ORBX_MINB; L.maxBY = L.h - ORBX_MINB;
+        const float fw = (float)(L.maxBX - ORBX_MINB), fh = (float)(L.maxBY - ORBX_MINB);   // :779-786
+        L.nCols = (int)(fw / 30.f); L.nRows = (int)(fh / 30.f);
+        L.wCell = (int)ceilf(fw / L.nCols); L.hCell = (int)ceilf(fh / L.nRows);
+        ORB_REQUIRE(L.wCell <= 250 && L.hCell <= 250, ORB_ERR_GEOMETRY, "cell too large");
+        L.cellBase = cellBase;
+        cellBase += L.nCols * L.nRows;
+        maxCW = std::max(maxCW, L.wCell); maxCH = std::max(maxCH, L.hCell);
+        L.quota = ex->quota[l];
+        L.nIni = (int)roundf((float)(L.maxBX - ORBX_MINB) / (float)(L.maxBY - ORBX_MINB));  // :542
+        ORB_REQUIRE(L.nIni >= 1 && L.nIni <= 64, ORB_ERR_GEOMETRY,
+                    "level %d aspect ratio gives nIni=%d root nodes (reference divides by zero at 0)", l, L.nIni);
+        L.hX = (float)(L.maxBX - ORBX_MINB) / L.nIni;                                       // :544
+        L.candOff = candOff;
+        L.candCap = std::min(L.nCols * L.nRows * ex->candPerCell, 65535 * 16);
+        candOff += L.candCap;
+        const int nodeBound = std::max(L.quota + 3, 4 * L.nIni) + 1;
+        L.selOff = selOff; L.selCap = nodeBound;
+        selOff += nodeBound;
+        maxNodes = std::max(maxNodes, nodeBound);
+        L.scale = ex->sf[l];
+        L.kpSize = (float)(int)(31 * ex->sf[l]);                                            // :837
+        L.xtabOff = (int)xt.size(); L.ytabOff = (int)yt.size();
+        if (l > 0) {
+            build_resize_taps(P.lv[l - 1].w, L.w, true, xt);
+            build_resize_taps(P.lv[l - 1].h, L.h, false, yt);
+        }
+    }
+    ORB_REQUIRE(maxNodes <= 60000, ORB_ERR_ARG, "nfeatures too large for the octree kernel");
+    P.totalCells = cellBase; P.candTotal = candOff; P.selTotal = selOff; P.maxNodes = maxNodes;
+    P.sortN = 2; while (P.sortN < maxNodes) P.sortN <<= 1;
+    P.frameBytes = off;
+    P.tilePitch = (int)orb_align_up(maxCW + 6, 4); P.tileRows = maxCH + 6;
+    P.scorePitch = (int)orb_align_up(maxCW + 2, 4); P.scoreRows = maxCH + 2;
+    ex->fastSmem = (size_t)P.tilePitch * P.tileRows + (size_t)P.scorePitch * P.scoreRows;
+    ex->octSmem = (size_t)maxNodes * (16 * 2 + 4 * 2 + 16 + 4 * 3) + (size_t)P.sortN * 8 + 64;
+    ORB_REQUIRE(ex->octSmem <= 220 * 1024, ORB_ERR_ARG, "nfeatures too large for the octree kernel's shared memory");
+    ORB_REQUIRE(maxCW <= 250 && maxCH <= 250, ORB_ERR_GEOMETRY, "cell too large");
+    ex->capInternal = selOff;
+
+    const int B = ex->maxBatch;
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_pyr, (size_t)B * P.frameBytes));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_blur, (size_t)B * P.frameBytes));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_cand, (size_t)B * P.candTotal * sizeof(uint2)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_nodeOf, (size_t)B * P.candTotal * sizeof(u32)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_sel, (size_t)B * P.selTotal * sizeof(uint2)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_candCount, (size_t)B * nl * sizeof(int)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_selCount, (size_t)B * nl * sizeof(int)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_status, sizeof(int)));
+    ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
+    ORB_CUDA_TRY(cudaMemset(ex->d_blur, 0, (size_t)B * P.frameBytes));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_xtab, std::max<size_t>(xt.size(), 1) * sizeof(ResizeTap)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_ytab, std::max<size_t>(yt.size(), 1) * sizeof(ResizeTap)));
+    if (!xt.empty()) ORB_CUDA_TRY(cudaMemcpy(ex->d_xtab, xt.data(), xt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+    if (!yt.empty()) ORB_CUDA_TRY(cudaMemcpy(ex->d_ytab, yt.data(), yt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+    {   // dynamic shared-memory opt-in is per function, shared by all handles: only ever raise it
+        static std::mutex amu;
+        static size_t maxFast = 0, maxOct = 0;
+        std::lock_guard<std::mutex> lk(amu);
+        if (ex->fastSmem > maxFast) {
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
+            maxFast = ex->fastSmem;
+        }
+        if (ex->octSmem > maxOct) {
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octSmem));
+            maxOct = ex->octSmem;
+        }
+    }
+    return ORB_OK;
+}
+
+extern "C" int orbx_create(orbx_extractor** out, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
+                           int width, int height, int max_batch, int device) {
+    ORB_REQUIRE(out, ORB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    ORB_REQUIRE(nfeatures > 0 && nlevels >= 1 && nlevels <= ORBX_MAX_LEVELS && scale_factor > 1.f && ini_th > 0 && min_th > 0 &&
+                ini_th < 255 && min_th <= ini_th && width > 0 && height > 0 && max_batch >= 1,
+                ORB_ERR_ARG, "bad extractor parameters");
+    ORB_REQUIRE(orb_device_count() > device && device >= 0, ORB_ERR_CUDA, "CUDA device %d not available (no CPU fallback)", device);
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    orbx_extractor* ex = new orbx_extractor();
+    ex->nfeatures = nfeatures; ex->nlevels = nlevels; ex->iniTh = ini_th; ex->minTh = min_th; ex->device = device;
+    ex->maxBatch = max_batch; ex->scaleFactor = scale_factor; ex->candPerCell = 64;
+    if (const char* e = getenv("ORBX_CAND_PER_CELL")) ex->candPerCell = std::max(8, atoi(e));
+    // scale tables and per-level quotas (ORBextractor.cc:414-445)
+    ex->sf.resize(nlevels); ex->s2.resize(nlevels); ex->isf.resize(nlevels); ex->is2.resize(nlevels); ex->quota.resize(nlevels);
+    ex->sf[0] = 1.0f; ex->s2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) { ex->sf[i] = (float)(ex->sf[i - 1] * ex->scaleFactor); ex->s2[i] = ex->sf[i] * ex->sf[i]; }
+    for (int i = 0; i < nlevels; i++) { ex->isf[i] = 1.0f / ex->sf[i]; ex->is2[i] = 1.0f / ex->s2[i]; }
+    float factor = (float)(1.0f / ex->scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) { ex->quota[l] = h_cvRoundF(nDesired); sum += ex->quota[l]; nDesired *= factor; }
+    ex->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    int rc = make_plan(ex, width, height);
+    if (rc == ORB_OK && cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        orb_set_error("cudaStreamCreate failed"); rc = ORB_ERR_CUDA;
+    }
+    if (rc != ORB_OK) { orbx_destroy(ex); return rc; }
+    *out = ex;
+    return ORB_OK;
+}
+
+extern "C" void orbx_destroy(orbx_extractor* ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_in); cudaFree(ex->d_mask); cudaFree(ex->d_desc);
+    cudaFree(ex->d_cand); cudaFree(ex->d_sel); cudaFree(ex->d_nodeOf); cudaFree(ex->d_candCount); cudaFree(ex->d_selCount);
+    cudaFree(ex->d_status); cudaFree(ex->d_n); cudaFree(ex->d_kp); cudaFree(ex->d_xtab); cudaFree(ex->d_ytab);
+    if (ex->stream) cudaStreamDestroy(ex->stream);
+    delete ex;
+}
+
+extern "C" int orbx_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota) {
+    ORB_REQUIRE(ex, ORB_ERR_ARG, "null handle");
+    for (int i = 0; i < ex->nlevels; i++) {
+        if (scale) scale[i] = ex->sf[i];
+        if (inv_scale) inv_scale[i] = ex->isf[i];
+        if (sigma2) sigma2[i] = ex->s2[i];
+        if (inv_sigma2) inv_sigma2[i] = ex->is2[i];
+        if (quota) quota[i] = ex->quota[i];
+    }
+    return ORB_OK;
+}
+extern "C" int orbx_level_size(const orbx_extractor* ex, int level, int* w, int* h) {
+    ORB_REQUIRE(ex && level >= 0 && level < ex->nlevels, ORB_ERR_ARG, "bad level");
+    if (w) *w = ex->plan.lv[level].w;
+    if (h) *h = ex->plan.lv[level].h;
+    return ORB_OK;
+}
+extern "C" int orbx_max_keypoints(const orbx_extractor* ex) { return ex ? ex->capInternal : 0; }
+extern "C" long long orbx_launch_count(const orbx_extractor* ex) { return ex ? ex->launches : 0; }
+
+// One device pass over nf <= maxBatch frames.
+static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, int nf, orbx_keypoint* d_kp, u8* d_desc,
+                    int cap, int* d_n, int stages, cudaStream_t st) {
+    const Plan& P = ex->plan;
+    const int nl = P.nlevels;
+    if (stages & ORBX_STAGE_PYRAMID) {
+        {
+            const LevelPlan& L = P.lv[0];
+            dim3 g(orb_div_up(L.pitch, 256), orb_div_up(L.brows, 4), nf), b(64, 4);
+            k_level0<<<g, b, 0, st>>>(P, d_images, d_masks, ex->d_pyr);
+            ex->launches++;
+        }
+        for (int l = 1; l < nl; l++) {
+            const LevelPlan& L = P.lv[l];
+            dim3 g(orb_div_up(L.pitch, 256), orb_div_up(L.brows, 4), nf), b(64, 4);
+            k_resize<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
+            ex->launches++;
+        }
+    }
+    if (stages & ORBX_STAGE_FAST) {
+        ORB_CUDA_TRY(cudaMemsetAsync(ex->d_candCount, 0, (size_t)nf * nl * sizeof(int), st));
+        dim3 g(P.totalCells, nf);
+        k_fast<<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
+        ex->launches++;
+    }
+    if (stages & ORBX_STAGE_OCTREE) {
+        dim3 g(nl, nf);
+        k_octree<<<g, ORBX_OCT_THREADS, ex->octSmem, st>>>(P, ex->d_cand, ex->d_candCount, ex->d_nodeOf, ex->d_sel,
+                                                           ex->d_selCount, ex->d_status);
+        ex->launches++;
+    }
+    if (stages & ORBX_STAGE_BLUR) {
+        for (int l = 0; l < nl; l++) {
+            const LevelPlan& L = P.lv[l];
+            dim3 g(orb_div_up(L.w, BL_TW), orb_div_up(L.h, BL_TH), nf), b(32, 8);
+            k_blur<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_blur);
+            ex->launches++;
+        }
+    }
+    if (stages & ORBX_STAGE_DESCRIBE) {
+        dim3 g(orb_div_up(P.selTotal, 8), nf);
+        k_describe<<<g, 256, 0, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc, d_n, cap, ex->d_status);
+        ex->launches++;
+    }
+    ORB_CUDA_TRY(cudaGetLastError());
+    ex->lastFrames = nf;
+    return ORB_OK;
+}
+
+extern "C" int orbx_run_stages_device(orbx_extractor* ex, const uint8_t* d_images, int n_frames, const uint8_t* d_masks,
+                                      orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_n_out, int stage_mask,
+                                      void* stream) {
+    ORB_REQUIRE(ex && d_images && d_kp_out && d_desc_out && d_n_out && n_frames >= 0 && cap > 0, ORB_ERR_ARG, "bad arguments");
+    std::lock_guard<std::mutex> lk(ex->mu);
+    ORB_CUDA_TRY(cudaSetDevice(ex->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ex->stream;
+    const size_t fpx = (size_t)ex->plan.width * ex->plan.height;
+    for (int f0 = 0; f0 < n_frames; f0 += ex->maxBatch) {
+        const int nf = std::min(ex->maxBatch, n_frames - f0);
+        int rc = run_pass(ex, d_images + f0 * fpx, d_masks ? d_masks + f0 * fpx : nullptr, nf, d_kp_out + (size_t)f0 * cap,
+                          d_desc_out + (size_t)f0 * cap * 32, cap, d_n_out + f0, stage_mask, st);
+        if (rc != ORB_OK) return rc;
+    }
+    return ORB_OK;
+}
+
+extern "C" int orbx_extract_batch_device(orbx_extractor* ex, const uint8_t* d_images, int n_frames, const uint8_t* d_masks,
+                                         orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_n_out, void* stream) {
+    return orbx_run_stages_device(ex, d_images, n_frames, d_masks, d_kp_out, d_desc_out, cap, d_n_out, ORBX_STAGE_ALL, stream);
+}
+
+extern "C" int orbx_check_status(orbx_extractor* ex) {
+    ORB_REQUIRE(ex, ORB_ERR_ARG, "null handle");
+    int s = 0;
+    ORB_CUDA_TRY(cudaSetDevice(ex->device));
+    ORB_CUDA_TRY(cudaMemcpy(&s, ex->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (s) ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
+    ORB_REQUIRE(!(s & (ORB_DEV_CAND_OVERFLOW | ORB_DEV_NODE_OVERFLOW)), ORB_ERR_OVERFLOW,
+                "FAST candidate buffer overflow (set ORBX_CAND_PER_CELL > %d)", ex->candPerCell);
+    ORB_REQUIRE(!(s & ORB_DEV_OUT_OVERFLOW), ORB_ERR_CAPACITY, "keypoint output capacity too small (need orbx_max_keypoints())");
+    return ORB_OK;
+}
+
+extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int n_frames, int width, int height, int stride,
+                                  size_t frame_stride, const uint8_t* masks, int mask_stride, size_t mask_frame_stride,
+                                  orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
+    ORB_REQUIRE(ex && images && kp_out && desc_out && n_out && n_frames >= 0 && cap > 0, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(width == ex->plan.width && height == ex->plan.height, ORB_ERR_ARG,
+                "image is %dx%d but the handle was planned for %dx%d", width, height, ex->plan.width, ex->plan.height);
+    ORB_REQUIRE(stride >= width && (!masks || mask_stride >= width), ORB_ERR_ARG, "stride < width");
+    const int B = ex->maxBatch;
+    const size_t fpx = (size_t)width * height;
+    {
+        std::lock_guard<std::mutex> lk(ex->mu);
+        ORB_CUDA_TRY(cudaSetDevice(ex->device));
+        if (!ex->d_in) ORB_CUDA_TRY(cudaMalloc(&ex->d_in, (size_t)B * fpx));
+        if (masks && !ex->d_mask) ORB_CUDA_TRY(cudaMalloc(&ex->d_mask, (size_t)B * fpx));
+        if (!ex->d_kp) {
+            ORB_CUDA_TRY(cudaMalloc(&ex->d_kp, (size_t)B * ex->capInternal * sizeof(orbx_keypoint)));
+            ORB_CUDA_TRY(cudaMalloc(&ex->d_desc, (size_t)B * ex->capInternal * 32));
+            ORB_CUDA_TRY(cudaMalloc(&ex->d_n, (size_t)B * sizeof(int)));
+        }
+    }
+    const int icap = ex->capInternal;
+    std::vector<int> ncount(B);
+    for (int f0 = 0; f0 < n_frames; f0 += B) {
+        const int nf = std::min(B, n_frames - f0);
+        cudaStream_t st = ex->stream;
+        if ((size_t)stride == (size_t)width && frame_stride == fpx) {
+            ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in, images + (size_t)f0 * frame_stride, (size_t)nf * fpx, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int f = 0; f < nf; f++)
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in + f * fpx, width, images + (size_t)(f0 + f) * frame_stride, stride, width,
+                                               height, cudaMemcpyHostToDevice, st));
+        }
+        if (masks)
+            for (int f = 0; f < nf; f++)
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_mask + f * fpx, width, masks + (size_t)(f0 + f) * mask_frame_stride, mask_stride,
+                                               width, height, cudaMemcpyHostToDevice, st));
+        {
+            std::lock_guard<std::mutex> lk(ex->mu);
+            int rc = run_pass(ex, ex->d_in, masks ? ex->d_mask : nullptr, nf, ex->d_kp, ex->d_desc, icap, ex->d_n, ORBX_STAGE_ALL, st);
+            if (rc != ORB_OK) return rc;
+        }
+        ORB_CUDA_TRY(cudaMemcpyAsync(ncount.data(), ex->d_n, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+        int rc = orbx_check_status(ex);
+        if (rc != ORB_OK) return rc;
+        for (int f = 0; f < nf; f++) {
+            const int n = ncount[f];
+            n_out[f0 + f] = n;
+            ORB_REQUIRE(n <= cap, ORB_ERR_CAPACITY, "frame %d has %d keypoints but cap is %d", f0 + f, n, cap);
+            if (n == 0) continue;
+            ORB_CUDA_TRY(cudaMemcpyAsync(kp_out + (size_t)(f0 + f) * cap, ex->d_kp + (size_t)f * icap, (size_t)n * sizeof(orbx_keypoint),
+                                         cudaMemcpyDeviceToHost, st));
+            ORB_CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)(f0 + f) * cap * 32, ex->d_desc + (size_t)f * icap * 32, (size_t)n * 32,
+                                         cudaMemcpyDeviceToHost, st));
+        }
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return ORB_OK;
+}
+
+extern "C" int orbx_extract(orbx_extractor* ex, const uint8_t* image, int width, int height, int stride, const uint8_t* mask,
+                            int mask_stride, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
+    return orbx_extract_batch(ex, image, 1, width, height, stride, (size_t)stride * height, mask, mask_stride,
+                              (size_t)mask_stride * height, kp_out, desc_out, cap, n_out);
+}
+
+static int copy_level(orbx_extractor* ex, const u8* base, int frame, int level, int bordered, uint8_t* dst, int dst_stride) {
+    ORB_REQUIRE(ex && dst && level >= 0 && level < ex->nlevels && frame >= 0 && frame < ex->lastFrames, ORB_ERR_ARG, "bad frame/level");
+    const LevelPlan& L = ex->plan.lv[level];
+    ORB_CUDA_TRY(cudaSetDevice(ex->device));
+    const u8* src = base + (size_t)frame * ex->plan.frameBytes + L.off;
+    if (bordered) {
+        ORB_REQUIRE(dst_stride >= L.w + 38, ORB_ERR_ARG, "dst_stride too small");
+        ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, src + ORBX_OX - ORBX_EDGE, L.pitch, L.w + 38, L.h + 38, cudaMemcpyDeviceToHost));
+    } else {
+        ORB_REQUIRE(dst_stride >= L.w, ORB_ERR_ARG, "dst_stride too small");
+        ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, src + (size_t)ORBX_OY * L.pitch + ORBX_OX, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    }
+    return ORB_OK;
+}
+extern "C" int orbx_get_pyramid_level(orbx_extractor* ex, int frame, int level, int bordered, uint8_t* dst, int dst_stride) {
+    return copy_level(ex, ex ? ex->d_pyr : nullptr, frame, level, bordered, dst, dst_stride);
+}
+extern "C" int orbx_get_blurred_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, int dst_stride) {
+    return copy_level(ex, ex ? ex->d_blur : nullptr, frame, level, 0, dst, dst_stride);
+}
+
+extern "C" int orbx_get_candidates(orbx_extractor* ex, int frame, int level, orbx_candidate* out, int cap, int* n_out) {
+    ORB_REQUIRE(ex && n_out && level >= 0 && level < ex->nlevels && frame >= 0 && frame < ex->lastFrames, ORB_ERR_ARG, "bad frame/level");
+    const LevelPlan& L = ex->plan.lv[level];
+    ORB_CUDA_TRY(cudaSetDevice(ex->device));
+    int n = 0;
+    ORB_CUDA_TRY(cudaMemcpy(&n, ex->d_candCount + frame * ex->nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    n = std::min(n, L.candCap);
+    std::vector<uint2> k(n);
+    if (n) ORB_CUDA_TRY(cudaMemcpy(k.data(), ex->d_cand + (size_t)frame * ex->plan.candTotal + L.candOff, n * sizeof(uint2), cudaMemcpyDeviceToHost));
+    // present in the reference's order: (cell id, y, x)
+    std::sort(k.begin(), k.end(), [](const uint2& a, const uint2& b) {
+        const unsigned long long ka = ((unsigned long long)(a.y & 0xFFFFFF) << 32) | ((unsigned long long)(a.x >> 16) << 16) | (a.x & 0xFFFF);
+        const unsigned long long kb = ((unsigned long long)(b.y & 0xFFFFFF) << 32) | ((unsigned long long)(b.x >> 16) << 16) | (b.x & 0xFFFF);
+        return ka < kb;
+    });
+    for (int i = 0; i < n && i < cap; i++) { out[i].x = k[i].x & 0xFFFF; out[i].y = k[i].x >> 16; out[i].response = k[i].y >> 24; }
+    return ORB_OK;
+}

@@ -1,0 +1,701 @@
+// orb_match.cu — B200 (sm_100a) implementation of ORB_SLAM2::ORBmatcher's Hamming searches behind the C ABI of
+// include/orb_b200.h.  Replaces src/ORBmatcher.cc:1650-1666 (DescriptorDistance), :159-291 and :525-658 (SearchByBoW),
+// :660-826 (SearchForTriangulation), :140-157 (CheckDistEpipolarLine), :1604-1645 (ComputeThreeMaxima).
+//
+// The distance kernel is LOP3(XOR) + POPC on descriptors held as 8 x u32 in registers (queries) and shared memory
+// (database tile, broadcast reads); top-2 is kept branch-free as two packed (distance<<23 | index) keys.
+// Integer pipe work only: no tensor cores.
+#include "orb_common.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#define KEY_SHIFT 23
+#define KEY_IDX_MASK 0x7FFFFFu
+#define KEY_NONE 0xFFFFFFFFu             // distance field 511 -> decoded as "no candidate" (256, -1)
+
+__device__ __forceinline__ int ham256(const u32 (&a)[8], const u32 (&b)[8]) {
+    return __popc(a[0] ^ b[0]) + __popc(a[1] ^ b[1]) + __popc(a[2] ^ b[2]) + __popc(a[3] ^ b[3]) +
+           __popc(a[4] ^ b[4]) + __popc(a[5] ^ b[5]) + __popc(a[6] ^ b[6]) + __popc(a[7] ^ b[7]);
+}
+__device__ __forceinline__ void load_desc(const u8* p, u32 (&d)[8]) {
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    d[0] = lo.x; d[1] = lo.y; d[2] = lo.z; d[3] = lo.w; d[4] = hi.x; d[5] = hi.y; d[6] = hi.z; d[7] = hi.w;
+}
+__device__ __forceinline__ int key_dist(u32 k) { return k == KEY_NONE ? 256 : (int)(k >> KEY_SHIFT); }
+
+// ---------------------------------------------------------------------------------------------------
+// DescriptorDistance for n pairs
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_pair_distance(const u8* __restrict__ a, const u8* __restrict__ b, int n, int* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 x[8], y[8];
+    load_desc(a + (size_t)i * 32, x);
+    load_desc(b + (size_t)i * 32, y);
+    dist[i] = ham256(x, y);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Brute-force top-2, batched over independent (query set, database set) problems.
+// CTA = 128 threads, QPT queries per thread in registers; database streamed through a 256-descriptor smem tile.
+// ---------------------------------------------------------------------------------------------------
+#define T2_THREADS 128
+#define T2_DBT 256
+
+template <int QPT>
+__device__ __forceinline__ void top2_scan_tile(const uint4* __restrict__ s_db, int cnt, int jbase, const u32 (&q)[QPT][8],
+                                               u32 (&best)[QPT], u32 (&sec)[QPT]) {
+#pragma unroll 2
+    for (int j = 0; j < cnt; j++) {
+        const uint4 lo = s_db[2 * j], hi = s_db[2 * j + 1];
+        const u32 w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int i = 0; i < QPT; i++) {
+            const u32 key = ((u32)ham256(q[i], w) << KEY_SHIFT) | (u32)(jbase + j);
+            sec[i] = min(sec[i], max(best[i], key));
+            best[i] = min(best[i], key);
+        }
+    }
+}
+
+template <int QPT>
+__global__ void __launch_bounds__(T2_THREADS) k_top2(const u8* __restrict__ q, const int* __restrict__ q_off,
+                                                     const int* __restrict__ q_cnt, const u8* __restrict__ db,
+                                                     const int* __restrict__ db_off, const int* __restrict__ db_cnt,
+                                                     int* __restrict__ best_idx, int* __restrict__ best_dist,
+                                                     int* __restrict__ second_dist) {
+    __shared__ uint4 s_db[T2_DBT * 2];
+    const int p = blockIdx.y, tid = threadIdx.x;
+    const int nq = q_cnt[p], qo = q_off[p], nd = db_cnt[p];
+    const int q0 = blockIdx.x * (T2_THREADS * QPT);
+    if (q0 >= nq) return;
+    const u8* dbp = db + (size_t)db_off[p] * 32;
+    u32 qr[QPT][8], best[QPT], sec[QPT];
+#pragma unroll
+    for (int i = 0; i < QPT; i++) {
+        const int qi = min(q0 + i * T2_THREADS + tid, nq - 1);
+        load_desc(q + (size_t)(qo + qi) * 32, qr[i]);
+        best[i] = KEY_NONE; sec[i] = KEY_NONE;
+    }
+    for (int j0 = 0; j0 < nd; j0 += T2_DBT) {
+        const int cnt = min(T2_DBT, nd - j0);
+        __syncthreads();
+        for (int i = tid; i < cnt * 2; i += T2_THREADS) s_db[i] = __ldg(reinterpret_cast<const uint4*>(dbp + (size_t)j0 * 32) + i);
+        __syncthreads();
+        top2_scan_tile<QPT>(s_db, cnt, j0, qr, best, sec);
+    }
+#pragma unroll
+    for (int i = 0; i < QPT; i++) {
+        const int qi = q0 + i * T2_THREADS + tid;
+        if (qi < nq) {
+            best_idx[qo + qi] = best[i] == KEY_NONE ? -1 : (int)(best[i] & KEY_IDX_MASK);
+            best_dist[qo + qi] = key_dist(best[i]);
+            second_dist[qo + qi] = key_dist(sec[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// All-pairs keyframe matching (config 4): CTA = (query tile of keyframe q, database keyframe k).
+// count[q][k] += #queries passing  best <= th_low && best < ratio * second ; optional global nearest keyframe.
+// ---------------------------------------------------------------------------------------------------
+template <int QPT>
+__global__ void __launch_bounds__(T2_THREADS) k_allpairs(const u8* __restrict__ desc, int n_kf, int per_kf, int q_begin,
+                                                         int th_low, float ratio, u32* __restrict__ count_words,
+                                                         u32* __restrict__ best_packed) {
+    __shared__ uint4 s_db[T2_DBT * 2];
+    __shared__ int s_cnt;
+    const int tid = threadIdx.x, k = blockIdx.y, qk = q_begin + blockIdx.z;
+    if (k == qk) return;
+    const int q0 = blockIdx.x * (T2_THREADS * QPT);
+    if (tid == 0) s_cnt = 0;
+    const u8* qp = desc + (size_t)qk * per_kf * 32;
+    const u8* dbp = desc + (size_t)k * per_kf * 32;
+    u32 qr[QPT][8], best[QPT], sec[QPT];
+#pragma unroll
+    for (int i = 0; i < QPT; i++) {
+        const int qi = min(q0 + i * T2_THREADS + tid, per_kf - 1);
+        load_desc(qp + (size_t)qi * 32, qr[i]);
+        best[i] = KEY_NONE; sec[i] = KEY_NONE;
+    }
+    for (int j0 = 0; j0 < per_kf; j0 += T2_DBT) {
+        const int cnt = min(T2_DBT, per_kf - j0);
+        __syncthreads();
+        for (int i = tid; i < cnt * 2; i += T2_THREADS) s_db[i] = __ldg(reinterpret_cast<const uint4*>(dbp + (size_t)j0 * 32) + i);
+        __syncthreads();
+        top2_scan_tile<QPT>(s_db, cnt, j0, qr, best, sec);
+    }
+    int ok = 0;
+#pragma unroll
+    for (int i = 0; i < QPT; i++) {
+        const int qi = q0 + i * T2_THREADS + tid;
+        if (qi < per_kf) {
+            const int b = key_dist(best[i]), s = key_dist(sec[i]);
+            ok += (b <= th_low && (float)b < __fmul_rn(ratio, (float)s)) ? 1 : 0;
+            if (best_packed) atomicMin(&best_packed[(size_t)blockIdx.z * per_kf + qi], ((u32)b << KEY_SHIFT) | (u32)k);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    if ((tid & 31) == 0 && ok) atomicAdd(&s_cnt, ok);
+    __syncthreads();
+    if (tid == 0 && s_cnt) {
+        const size_t e = (size_t)blockIdx.z * n_kf + k;                 // uint16 element index
+        atomicAdd(&count_words[e >> 1], (u32)s_cnt << ((e & 1) * 16));
+    }
+}
+__global__ void k_unpack_best(const u32* __restrict__ packed, int n, int* __restrict__ kf, int* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 v = packed[i];
+    kf[i] = v == KEY_NONE ? -1 : (int)(v & KEY_IDX_MASK);
+    dist[i] = key_dist(v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Node-constrained searches.  A FeatureVector arrives as CSR (ids ascending, offsets, features).
+// ---------------------------------------------------------------------------------------------------
+struct DevView {
+    int n;
+    const u8* desc; const u8* flag; const float* angle; const float* x; const float* y; const int* octave; const float* uright;
+    int nn; const int* ids; const int* off; const int* feat;
+};
+
+__device__ __forceinline__ int find_node(const int* ids, int n, int id) {     // index of id in ascending ids, or -1
+    int lo = 0, hi = n;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (ids[m] < id) lo = m + 1; else hi = m; }
+    return (lo < n && ids[lo] == id) ? lo : -1;
+}
+__device__ __forceinline__ int rot_bin(float a1, float a2) {                   // ORBmatcher.cc:241-246
+    const float factor = 1.0f / ORBM_HISTO_LENGTH;
+    float rot = __fsub_rn(a1, a2);
+    if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+    int bin = (int)roundf(__fmul_rn(rot, factor));
+    if (bin == ORBM_HISTO_LENGTH) bin = 0;
+    return bin;
+}
+// ComputeThreeMaxima (ORBmatcher.cc:1604-1645) on bin sizes
+__device__ void three_maxima_dev(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    ind1 = ind2 = ind3 = -1;
+    for (int i = 0; i < L; i++) {
+        const int s = histo[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
+}
+__global__ void k_three_maxima(const int* histo, int L, int* ind) {
+    int a, b, c;
+    three_maxima_dev(histo, L, a, b, c);
+    ind[0] = a; ind[1] = b; ind[2] = c;
+}
+
+// SearchByBoW, both overloads.  One CTA per call; one warp per shared vocabulary node (the greedy claim
+// `vpMapPointMatches[realIdxF]` / `vbMatched2[idx2]` only couples features of the same node, and a feature belongs to
+// exactly one node, so nodes are independent); inside a node the side-1 features are walked in order and the side-2
+// scan is spread over the lanes with a (distance, position) top-2 warp reduction.
+//   KFKF = false: SearchByBoW(KF, Frame)  -> out[j in side 2] = idx1, accept best <= TH_LOW        (:231)
+//   KFKF = true : SearchByBoW(KF1, KF2)   -> out[i in side 1] = idx2, accept best <  TH_LOW, side-2 flag filter (:601)
+template <bool KFKF>
+__global__ void __launch_bounds__(256) k_search_bow(DevView A, DevView B, float nnratio, int checkOri, int* __restrict__ out,
+                                                    int* __restrict__ taken2, int* __restrict__ binOf, int* __restrict__ nmatches) {
+    __shared__ int s_hist[ORBM_HISTO_LENGTH];
+    __shared__ int s_n, s_ind[3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) s_n = 0;
+    const int nOut = KFKF ? A.n : B.n;
+    for (int i = tid; i < nOut; i += blockDim.x) out[i] = -1;
+    for (int i = tid; i < B.n; i += blockDim.x) taken2[i] = 0;
+    __syncthreads();
+    for (int a = warp; a < A.nn; a += nwarps) {
+        const int b = find_node(B.ids, B.nn, A.ids[a]);
+        if (b < 0) continue;
+        const int o2 = B.off[b], c2 = B.off[b + 1] - o2;
+        for (int i1 = A.off[a]; i1 < A.off[a + 1]; i1++) {
+            const int idx1 = A.feat[i1];
+            if (!A.flag[idx1]) continue;
+            u32 d1[8];
+            load_desc(A.desc + (size_t)idx1 * 32, d1);
+            u32 best = KEY_NONE, sec = KEY_NONE;
+            for (int j = lane; j < c2; j += 32) {
+                const int idx2 = B.feat[o2 + j];
+                if (taken2[idx2]) continue;
+                if (KFKF && !B.flag[idx2]) continue;
+                u32 d2[8];
+                load_desc(B.desc + (size_t)idx2 * 32, d2);
+                const u32 key = ((u32)ham256(d1, d2) << KEY_SHIFT) | (u32)j;
+                sec = min(sec, max(best, key));
+                best = min(best, key);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const u32 ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, sec, o);
+                sec = min(min(sec, os), max(best, ob));
+                best = min(best, ob);
+            }
+            const int bd1 = key_dist(best), bd2 = key_dist(sec);
+            const bool th = KFKF ? (bd1 < ORBM_TH_LOW) : (bd1 <= ORBM_TH_LOW);
+            if (th && (float)bd1 < __fmul_rn(nnratio, (float)bd2)) {
+                const int idx2 = B.feat[o2 + (int)(best & KEY_IDX_MASK)];
+                if (lane == 0) {
+                    taken2[idx2] = 1;
+                    const int slot = KFKF ? idx1 : idx2;
+                    out[slot] = KFKF ? idx2 : idx1;
+                    if (checkOri) {
+                        const int bin = rot_bin(A.angle[idx1], B.angle[idx2]);
+                        binOf[slot] = bin;
+                        atomicAdd(&s_hist[bin], 1);
+                    }
+                    atomicAdd(&s_n, 1);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (checkOri) {
+        if (tid == 0) { int a, b, c; three_maxima_dev(s_hist, ORBM_HISTO_LENGTH, a, b, c); s_ind[0] = a; s_ind[1] = b; s_ind[2] = c; }
+        __syncthreads();
+        for (int i = tid; i < nOut; i += blockDim.x)
+            if (out[i] >= 0) {
+                const int bin = binOf[i];
+                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { out[i] = -1; atomicSub(&s_n, 1); }
+            }
+        __syncthreads();
+    }
+    if (tid == 0) *nmatches = s_n;
+}
+
+// SearchForTriangulation.  No cross-query coupling (vbMatched2 is never set in the reference, :680,728), so one thread
+// per side-1 CSR slot walks its node's side-2 features serially, which keeps the reference's "last candidate wins a
+// tie" (`dist>bestDist` rejects, :741) and "bestDist only moves when the epipolar test passes" (:754-758).
+struct TriParams { float F[9]; float ex, ey; int onlyStereo, checkOri; };
+
+__global__ void __launch_bounds__(256) k_search_tri(DevView A, DevView B, TriParams tp, const float* __restrict__ sf2,
+                                                    const float* __restrict__ sigma2, int* __restrict__ m12,
+                                                    int* __restrict__ pairs, int* __restrict__ npairs, int* __restrict__ nmatches) {
+    __shared__ int s_hist[ORBM_HISTO_LENGTH];
+    __shared__ int s_n, s_ind[3], s_wsum[34];
+    const int tid = threadIdx.x;
+    if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) s_n = 0;
+    for (int i = tid; i < A.n; i += blockDim.x) m12[i] = -1;
+    __syncthreads();
+    const int total1 = A.nn > 0 ? A.off[A.nn] : 0;
+    for (int p = tid; p < total1; p += blockDim.x) {
+        int lo = 0, hi = A.nn;                                   // node a with off[a] <= p < off[a+1]
+        while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (A.off[m] <= p) lo = m; else hi = m; }
+        const int b = find_node(B.ids, B.nn, A.ids[lo]);
+        if (b < 0) continue;
+        const int idx1 = A.feat[p];
+        if (A.flag[idx1]) continue;                              // already has a MapPoint (:706-708)
+        const bool st1 = A.uright[idx1] >= 0;
+        if (tp.onlyStereo && !st1) continue;
+        const float x1 = A.x[idx1], y1 = A.y[idx1];
+        u32 d1[8];
+        load_desc(A.desc + (size_t)idx1 * 32, d1);
+        // epipolar line l = x1' F12 (:143-145)
+        const float la = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[0]), __fmul_rn(y1, tp.F[3])), tp.F[6]);
+        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[1]), __fmul_rn(y1, tp.F[4])), tp.F[7]);
+        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[2]), __fmul_rn(y1, tp.F[5])), tp.F[8]);
+        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+        int bestDist = ORBM_TH_LOW, bestIdx2 = -1;
+        for (int i2 = B.off[b]; i2 < B.off[b + 1]; i2++) {
+            const int idx2 = B.feat[i2];
+            if (B.flag[idx2]) continue;
+            const bool st2 = B.uright[idx2] >= 0;
+            if (tp.onlyStereo && !st2) continue;
+            u32 d2[8];
+            load_desc(B.desc + (size_t)idx2 * 32, d2);
+            const int dist = ham256(d1, d2);
+            if (dist > ORBM_TH_LOW || dist > bestDist) continue;
+            const float x2 = B.x[idx2], y2 = B.y[idx2];
+            const int oc = B.octave[idx2];
+            if (!st1 && !st2) {
+                const float dx = __fsub_rn(tp.ex, x2), dy = __fsub_rn(tp.ey, y2);
+                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, sf2[oc])) continue;
+            }
+            if (den == 0) continue;
+            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
+            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+            if ((double)dsqr < 3.84 * (double)sigma2[oc]) { bestIdx2 = idx2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) {
+            m12[idx1] = bestIdx2;
+            atomicAdd(&s_n, 1);
+            if (tp.checkOri) atomicAdd(&s_hist[rot_bin(A.angle[idx1], B.angle[bestIdx2])], 1);
+        }
+    }
+    __syncthreads();
+    if (tp.checkOri) {
+        if (tid == 0) { int a, b, c; three_maxima_dev(s_hist, ORBM_HISTO_LENGTH, a, b, c); s_ind[0] = a; s_ind[1] = b; s_ind[2] = c; }
+        __syncthreads();
+        for (int i = tid; i < A.n; i += blockDim.x)
+            if (m12[i] >= 0) {
+                const int bin = rot_bin(A.angle[i], B.angle[m12[i]]);
+                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { m12[i] = -1; atomicSub(&s_n, 1); }
+            }
+        __syncthreads();
+    }
+    // ordered compaction of (i, m12[i]) (:818-823): chunked block scan
+    int base = 0;
+    const int lane = tid & 31, w = tid >> 5;
+    for (int c0 = 0; c0 < A.n; c0 += blockDim.x) {
+        const int i = c0 + tid;
+        const int has = (i < A.n && m12[i] >= 0) ? 1 : 0;
+        int inc = has;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) s_wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const int ws = lane < (int)(blockDim.x >> 5) ? s_wsum[lane] : 0;
+            int wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+            s_wsum[lane] = wi - ws;
+            if (lane == 31) s_wsum[32] = wi;
+        }
+        __syncthreads();
+        if (has) { const int pos = base + s_wsum[w] + inc - 1; pairs[2 * pos] = i; pairs[2 * pos + 1] = m12[i]; }
+        base += s_wsum[32];
+        __syncthreads();
+    }
+    if (tid == 0) { *npairs = base; *nmatches = s_n; }
+}
+
+// POPC issue-rate microbenchmark: 8 independent xor+popc chains per thread, register resident.
+__global__ void k_popc_peak(u32* out, int iters) {
+    u32 a[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { a[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x; acc[i] = 0; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { acc[i] += __popc(a[i] ^ acc[i]); }
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+namespace {
+// Per-thread device scratch arena (grows; freed at thread exit is skipped on purpose: process-lifetime cache).
+struct Arena {
+    int device = -1;
+    u8* base = nullptr;
+    size_t cap = 0, used = 0;
+    cudaStream_t stream = nullptr;
+    int ensure(int dev, size_t bytes) {
+        if (device != dev) {
+            if (base) { cudaSetDevice(device); cudaFree(base); base = nullptr; cap = 0; }
+            if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+            device = dev;
+        }
+        ORB_CUDA_TRY(cudaSetDevice(dev));
+        if (!stream) ORB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (bytes > cap) {
+            if (base) ORB_CUDA_TRY(cudaFree(base));
+            base = nullptr;
+            cap = orb_align_up(bytes + (bytes >> 2), 1 << 20);
+            ORB_CUDA_TRY(cudaMalloc(&base, cap));
+        }
+        used = 0;
+        return ORB_OK;
+    }
+    template <typename T>
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + used);
+        used += orb_align_up(count * sizeof(T), 256);
+        return p;
+    }
+};
+thread_local Arena g_arena;
+
+template <typename T>
+int upload(Arena& A, const T* host, size_t count, const T** dev) {
+    T* d = A.take<T>(std::max<size_t>(count, 1));
+    if (count) ORB_CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, A.stream));
+    *dev = d;
+    return ORB_OK;
+}
+size_t pad(size_t bytes) { return orb_align_up(std::max<size_t>(bytes, 1), 256); }
+
+int check_device(int device) {
+    ORB_REQUIRE(device >= 0 && device < orb_device_count(), ORB_ERR_CUDA, "CUDA device %d not available (no CPU fallback)", device);
+    return ORB_OK;
+}
+}  // namespace
+
+extern "C" int orbm_descriptor_distance(const uint8_t* a, const uint8_t* b, int n, int* dist, int device) {
+    ORB_REQUIRE(a && b && dist && n >= 0, ORB_ERR_ARG, "bad arguments");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n == 0) return ORB_OK;
+    Arena& A = g_arena;
+    rc = A.ensure(device, 2 * pad((size_t)n * 32) + pad((size_t)n * 4));
+    if (rc) return rc;
+    const u8 *da, *db;
+    if ((rc = upload(A, a, (size_t)n * 32, &da))) return rc;
+    if ((rc = upload(A, b, (size_t)n * 32, &db))) return rc;
+    int* dd = A.take<int>(n);
+    k_pair_distance<<<orb_div_up(n, 256), 256, 0, A.stream>>>(da, db, n, dd);
+    ORB_CUDA_TRY(cudaGetLastError());
+    ORB_CUDA_TRY(cudaMemcpyAsync(dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
+    return ORB_OK;
+}
+
+static int launch_top2(const u8* d_q, const int* d_q_off, const int* d_q_cnt, const u8* d_db, const int* d_db_off,
+                       const int* d_db_cnt, int npairs, int max_q, int* d_bi, int* d_bd, int* d_sd, cudaStream_t st) {
+    if (npairs == 0 || max_q == 0) return ORB_OK;
+    ORB_REQUIRE(npairs <= 65535, ORB_ERR_ARG, "npairs > 65535");
+    // enough CTAs to fill 148 SMs decides how many queries each thread keeps in registers
+    const long ctas4 = (long)orb_div_up(max_q, T2_THREADS * 4) * npairs;
+    if (ctas4 >= 148 * 4) {
+        dim3 g(orb_div_up(max_q, T2_THREADS * 4), npairs);
+        k_top2<4><<<g, T2_THREADS, 0, st>>>(d_q, d_q_off, d_q_cnt, d_db, d_db_off, d_db_cnt, d_bi, d_bd, d_sd);
+    } else if ((long)orb_div_up(max_q, T2_THREADS * 2) * npairs >= 148 * 2) {
+        dim3 g(orb_div_up(max_q, T2_THREADS * 2), npairs);
+        k_top2<2><<<g, T2_THREADS, 0, st>>>(d_q, d_q_off, d_q_cnt, d_db, d_db_off, d_db_cnt, d_bi, d_bd, d_sd);
+    } else {
+        dim3 g(orb_div_up(max_q, T2_THREADS), npairs);
+        k_top2<1><<<g, T2_THREADS, 0, st>>>(d_q, d_q_off, d_q_cnt, d_db, d_db_off, d_db_cnt, d_bi, d_bd, d_sd);
+    }
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+extern "C" int orbm_hamming_top2_batch_device(const uint8_t* d_q, const int* d_q_off, const int* d_q_cnt, const uint8_t* d_db,
+                                              const int* d_db_off, const int* d_db_cnt, int npairs, int max_q, int* d_best_idx,
+                                              int* d_best_dist, int* d_second_dist, void* stream) {
+    ORB_REQUIRE(d_q && d_q_off && d_q_cnt && d_db && d_db_off && d_db_cnt && d_best_idx && d_best_dist && d_second_dist &&
+                npairs >= 0 && max_q >= 0, ORB_ERR_ARG, "bad arguments");
+    return launch_top2(d_q, d_q_off, d_q_cnt, d_db, d_db_off, d_db_cnt, npairs, max_q, d_best_idx, d_best_dist, d_second_dist,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int orbm_hamming_top2(const uint8_t* q, int nq, const uint8_t* db, int ndb, int* best_idx, int* best_dist,
+                                 int* second_dist, int device) {
+    ORB_REQUIRE(q && (db || ndb == 0) && best_idx && best_dist && second_dist && nq >= 0 && ndb >= 0, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(ndb <= (int)KEY_IDX_MASK, ORB_ERR_ARG, "database larger than 8388607 descriptors");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (nq == 0) return ORB_OK;
+    Arena& A = g_arena;
+    rc = A.ensure(device, pad((size_t)nq * 32) + pad((size_t)ndb * 32) + 3 * pad((size_t)nq * 4) + 4 * 256);
+    if (rc) return rc;
+    const u8 *dq, *ddb;
+    if ((rc = upload(A, q, (size_t)nq * 32, &dq))) return rc;
+    if ((rc = upload(A, db, (size_t)ndb * 32, &ddb))) return rc;
+    const int meta[4] = {0, nq, 0, ndb};
+    const int* dmeta;
+    if ((rc = upload(A, meta, 4, &dmeta))) return rc;
+    int *bi = A.take<int>(nq), *bd = A.take<int>(nq), *sd = A.take<int>(nq);
+    rc = launch_top2(dq, dmeta, dmeta + 1, ddb, dmeta + 2, dmeta + 3, 1, nq, bi, bd, sd, A.stream);
+    if (rc) return rc;
+    ORB_CUDA_TRY(cudaMemcpyAsync(best_idx, bi, (size_t)nq * 4, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaMemcpyAsync(best_dist, bd, (size_t)nq * 4, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaMemcpyAsync(second_dist, sd, (size_t)nq * 4, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
+    return ORB_OK;
+}
+
+extern "C" int orbm_allpairs_device(const uint8_t* d_desc, int n_kf, int per_kf, int q_begin, int q_end, int th_low, float ratio,
+                                    uint16_t* d_count, int* d_best_kf, int* d_best_dist, void* stream) {
+    ORB_REQUIRE(d_desc && d_count && n_kf > 0 && per_kf > 0 && q_begin >= 0 && q_end >= q_begin && q_end <= n_kf, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(n_kf <= 65535 && (q_end - q_begin) <= 65535 && n_kf <= (int)KEY_IDX_MASK, ORB_ERR_ARG, "too many keyframes per call");
+    ORB_REQUIRE((d_best_kf == nullptr) == (d_best_dist == nullptr), ORB_ERR_ARG, "d_best_kf and d_best_dist go together");
+    ORB_REQUIRE(((uintptr_t)d_count & 3) == 0, ORB_ERR_ARG, "d_count must be 4-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nq = q_end - q_begin;
+    if (nq == 0) return ORB_OK;
+    const size_t cnt_bytes = orb_align_up((size_t)nq * n_kf * 2, 4);
+    ORB_CUDA_TRY(cudaMemsetAsync(d_count, 0, cnt_bytes, st));
+    u32* packed = reinterpret_cast<u32*>(d_best_dist);           // packed (dist<<23|kf) during the kernel, unpacked after
+    if (packed) ORB_CUDA_TRY(cudaMemsetAsync(packed, 0xFF, (size_t)nq * per_kf * 4, st));
+    if (per_kf >= T2_THREADS * 4) {
+        dim3 g(orb_div_up(per_kf, T2_THREADS * 4), n_kf, nq);
+        k_allpairs<4><<<g, T2_THREADS, 0, st>>>(d_desc, n_kf, per_kf, q_begin, th_low, ratio, reinterpret_cast<u32*>(d_count), packed);
+    } else {
+        dim3 g(orb_div_up(per_kf, T2_THREADS), n_kf, nq);
+        k_allpairs<1><<<g, T2_THREADS, 0, st>>>(d_desc, n_kf, per_kf, q_begin, th_low, ratio, reinterpret_cast<u32*>(d_count), packed);
+    }
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (packed) {
+        const int n = nq * per_kf;
+        k_unpack_best<<<orb_div_up(n, 256), 256, 0, st>>>(packed, n, d_best_kf, d_best_dist);
+        ORB_CUDA_TRY(cudaGetLastError());
+    }
+    return ORB_OK;
+}
+
+static size_t view_bytes(const orbm_view* v, bool tri) {
+    size_t b = pad((size_t)v->n * 32) + pad(v->n) + pad((size_t)v->n * 4);
+    if (tri) b += 4 * pad((size_t)v->n * 4);
+    b += pad((size_t)v->fv.n_nodes * 4) + pad((size_t)(v->fv.n_nodes + 1) * 4);
+    const int nf = v->fv.n_nodes > 0 ? v->fv.offsets[v->fv.n_nodes] : 0;
+    b += pad((size_t)nf * 4);
+    return b;
+}
+static int check_view(const orbm_view* v, bool needFlag, bool tri) {
+    ORB_REQUIRE(v && v->n >= 0 && v->fv.n_nodes >= 0, ORB_ERR_ARG, "bad view");
+    ORB_REQUIRE(v->n == 0 || v->desc, ORB_ERR_ARG, "view.desc is NULL");
+    ORB_REQUIRE(!needFlag || v->n == 0 || v->flag, ORB_ERR_ARG, "view.flag is NULL");
+    ORB_REQUIRE(v->n == 0 || v->angle, ORB_ERR_ARG, "view.angle is NULL");
+    ORB_REQUIRE(!tri || v->n == 0 || (v->x && v->y && v->octave && v->uright), ORB_ERR_ARG, "triangulation needs x, y, octave, uright");
+    ORB_REQUIRE(v->fv.n_nodes == 0 || (v->fv.node_ids && v->fv.offsets && v->fv.features), ORB_ERR_ARG, "bad feature vector");
+    const int nf = v->fv.n_nodes > 0 ? v->fv.offsets[v->fv.n_nodes] : 0;
+    for (int i = 0; i < v->fv.n_nodes; i++) {
+        ORB_REQUIRE(v->fv.offsets[i] <= v->fv.offsets[i + 1], ORB_ERR_ARG, "feature vector offsets not monotone");
+        ORB_REQUIRE(i == 0 || v->fv.node_ids[i - 1] < v->fv.node_ids[i], ORB_ERR_ARG, "feature vector node ids not ascending");
+    }
+    for (int i = 0; i < nf; i++) ORB_REQUIRE(v->fv.features[i] >= 0 && v->fv.features[i] < v->n, ORB_ERR_ARG, "feature index out of range");
+    return ORB_OK;
+}
+static int upload_view(Arena& A, const orbm_view* v, bool tri, DevView* d) {
+    int rc;
+    d->n = v->n; d->nn = v->fv.n_nodes;
+    d->flag = nullptr; d->x = d->y = d->uright = nullptr; d->octave = nullptr;
+    if ((rc = upload(A, v->desc, (size_t)v->n * 32, &d->desc))) return rc;
+    if (v->flag) { if ((rc = upload(A, v->flag, (size_t)v->n, &d->flag))) return rc; }
+    if ((rc = upload(A, v->angle, (size_t)v->n, &d->angle))) return rc;
+    if (tri) {
+        if ((rc = upload(A, v->x, (size_t)v->n, &d->x))) return rc;
+        if ((rc = upload(A, v->y, (size_t)v->n, &d->y))) return rc;
+        if ((rc = upload(A, v->octave, (size_t)v->n, &d->octave))) return rc;
+        if ((rc = upload(A, v->uright, (size_t)v->n, &d->uright))) return rc;
+    }
+    const int nf = v->fv.n_nodes > 0 ? v->fv.offsets[v->fv.n_nodes] : 0;
+    if ((rc = upload(A, v->fv.node_ids, (size_t)v->fv.n_nodes, &d->ids))) return rc;
+    if (v->fv.n_nodes > 0) { if ((rc = upload(A, v->fv.offsets, (size_t)v->fv.n_nodes + 1, &d->off))) return rc; }
+    else { static const int zero = 0; if ((rc = upload(A, &zero, 1, &d->off))) return rc; }
+    if ((rc = upload(A, v->fv.features, (size_t)nf, &d->feat))) return rc;
+    return ORB_OK;
+}
+
+template <bool KFKF>
+static int search_bow(const orbm_view* v1, const orbm_view* v2, float nnratio, int checkOri, int* match, int* n_matches, int device) {
+    ORB_REQUIRE(match && n_matches, ORB_ERR_ARG, "null output");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_view(v1, true, false))) return rc;
+    if ((rc = check_view(v2, KFKF, false))) return rc;
+    const int nOut = KFKF ? v1->n : v2->n;
+    Arena& A = g_arena;
+    rc = A.ensure(device, view_bytes(v1, false) + view_bytes(v2, false) + 2 * pad((size_t)nOut * 4) + pad((size_t)v2->n * 4) + 1024);
+    if (rc) return rc;
+    DevView d1, d2;
+    if ((rc = upload_view(A, v1, false, &d1))) return rc;
+    if ((rc = upload_view(A, v2, false, &d2))) return rc;
+    int* d_out = A.take<int>(std::max(nOut, 1));
+    int* d_bin = A.take<int>(std::max(nOut, 1));
+    int* d_taken = A.take<int>(std::max(v2->n, 1));
+    int* d_nm = A.take<int>(1);
+    k_search_bow<KFKF><<<1, 256, 0, A.stream>>>(d1, d2, nnratio, checkOri, d_out, d_taken, d_bin, d_nm);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (nOut) ORB_CUDA_TRY(cudaMemcpyAsync(match, d_out, (size_t)nOut * 4, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaMemcpyAsync(n_matches, d_nm, 4, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
+    return ORB_OK;
+}
+
+extern "C" int orbm_search_by_bow_kf_frame(const orbm_view* kf, const orbm_view* frame, float nnratio, int check_orientation,
+                                           int* match21, int* n_matches, int device) {
+    return search_bow<false>(kf, frame, nnratio, check_orientation, match21, n_matches, device);
+}
+extern "C" int orbm_search_by_bow_kf_kf(const orbm_view* kf1, const orbm_view* kf2, float nnratio, int check_orientation,
+                                        int* match12, int* n_matches, int device) {
+    return search_bow<true>(kf1, kf2, nnratio, check_orientation, match12, n_matches, device);
+}
+
+extern "C" int orbm_search_for_triangulation(const orbm_view* kf1, const orbm_view* kf2, const float* F12, float ex, float ey,
+                                             const float* scale_factors2, const float* level_sigma2_2, int n_levels2, int only_stereo,
+                                             int check_orientation, int* pairs_out, int* n_pairs, int* n_matches, int device) {
+    ORB_REQUIRE(F12 && scale_factors2 && level_sigma2_2 && n_levels2 > 0 && pairs_out && n_pairs && n_matches, ORB_ERR_ARG, "bad arguments");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_view(kf1, true, true))) return rc;
+    if ((rc = check_view(kf2, true, true))) return rc;
+    for (int i = 0; i < kf2->n; i++) ORB_REQUIRE(kf2->octave[i] >= 0 && kf2->octave[i] < n_levels2, ORB_ERR_ARG, "octave out of range");
+    Arena& A = g_arena;
+    rc = A.ensure(device, view_bytes(kf1, true) + view_bytes(kf2, true) + 3 * pad((size_t)kf1->n * 4) + 2 * pad((size_t)n_levels2 * 4) + 1024);
+    if (rc) return rc;
+    DevView d1, d2;
+    if ((rc = upload_view(A, kf1, true, &d1))) return rc;
+    if ((rc = upload_view(A, kf2, true, &d2))) return rc;
+    const float *d_sf, *d_s2;
+    if ((rc = upload(A, scale_factors2, (size_t)n_levels2, &d_sf))) return rc;
+    if ((rc = upload(A, level_sigma2_2, (size_t)n_levels2, &d_s2))) return rc;
+    int* d_m12 = A.take<int>(std::max(kf1->n, 1));
+    int* d_pairs = A.take<int>(std::max(2 * kf1->n, 1));
+    int* d_cnt = A.take<int>(2);
+    TriParams tp;
+    for (int i = 0; i < 9; i++) tp.F[i] = F12[i];
+    tp.ex = ex; tp.ey = ey; tp.onlyStereo = only_stereo; tp.checkOri = check_orientation;
+    k_search_tri<<<1, 256, 0, A.stream>>>(d1, d2, tp, d_sf, d_s2, d_m12, d_pairs, d_cnt, d_cnt + 1);
+    ORB_CUDA_TRY(cudaGetLastError());
+    int cnt[2] = {0, 0};
+    ORB_CUDA_TRY(cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
+    *n_pairs = cnt[0]; *n_matches = cnt[1];
+    if (cnt[0]) {
+        ORB_CUDA_TRY(cudaMemcpyAsync(pairs_out, d_pairs, (size_t)cnt[0] * 8, cudaMemcpyDeviceToHost, A.stream));
+        ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
+    }
+    return ORB_OK;
+}
+
+extern "C" int orbm_three_maxima(const int* histo, int n_bins, int* ind, int device) {
+    ORB_REQUIRE(histo && ind && n_bins > 0, ORB_ERR_ARG, "bad arguments");
+    int rc = check_device(device);
+    if (rc) return rc;
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, pad((size_t)n_bins * 4) + 256))) return rc;
+    const int* dh;
+    if ((rc = upload(A, histo, (size_t)n_bins, &dh))) return rc;
+    int* di = A.take<int>(3);
+    k_three_maxima<<<1, 1, 0, A.stream>>>(dh, n_bins, di);
+    ORB_CUDA_TRY(cudaGetLastError());
+    ORB_CUDA_TRY(cudaMemcpyAsync(ind, di, 12, cudaMemcpyDeviceToHost, A.stream));
+    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
+    return ORB_OK;
+}
+
+extern "C" int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used) {
+    ORB_REQUIRE(popc_per_second, ORB_ERR_ARG, "null output");
+    int rc = check_device(device);
+    if (rc) return rc;
+    ORB_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ORB_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    u32* d_out;
+    ORB_CUDA_TRY(cudaMalloc(&d_out, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    ORB_CUDA_TRY(cudaEventCreate(&e0));
+    ORB_CUDA_TRY(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        ORB_CUDA_TRY(cudaEventRecord(e0));
+        k_popc_peak<<<blocks, threads>>>(d_out, iters);
+        ORB_CUDA_TRY(cudaEventRecord(e1));
+        ORB_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms;
+        ORB_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best_ms = std::min(best_ms, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *popc_per_second = (double)blocks * threads * iters * 8.0 / (best_ms * 1e-3);
+    if (sm_clock_hz_used) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); *sm_clock_hz_used = khz * 1e3; }
+    return ORB_OK;
+}

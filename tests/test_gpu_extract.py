@@ -1,0 +1,172 @@
+"""GPU parity tests of the extractor path (through the C ABI) against the CPU oracle and the cv2 golden fixtures.
+
+Bars (BASELINE.json north_star): keypoint (x, y, octave, response) bit-exact; angles within 1e-3 deg; descriptor bit
+mismatch rate <= 0.01 %.  Intermediate stages (pyramid, FAST candidates, blur) are integer work and must be bit-exact.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import orbslam_mapsave_b200 as orb
+from orbslam_mapsave_b200.synth import synth
+from oracle import orb_oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+ANGLE_TOL_DEG = 1e-3
+DESC_BIT_MISMATCH_MAX = 1e-4      # 0.01 %
+
+
+def _compare(gpu_kp, gpu_desc, ref_kp, ref_desc):
+    assert len(gpu_kp) == len(ref_kp)
+    for f in ("x", "y", "octave", "response", "size", "class_id"):
+        assert np.array_equal(gpu_kp[f], ref_kp[f]), f
+    dang = np.abs(gpu_kp["angle"].astype(np.float64) - ref_kp["angle"].astype(np.float64))
+    dang = np.minimum(dang, 360.0 - dang)
+    assert dang.max(initial=0.0) <= ANGLE_TOL_DEG
+    bits = np.unpackbits(gpu_desc ^ ref_desc).sum()
+    rate = bits / max(1, gpu_desc.size * 8)
+    assert rate <= DESC_BIT_MISMATCH_MAX, rate
+    return int((gpu_kp["angle"] != ref_kp["angle"]).sum()), int(bits)
+
+
+def _stages_equal(ex, oex, nlevels):
+    for l in range(nlevels):
+        assert np.array_equal(ex.pyramid_level(0, l), oex.level(l)), f"pyramid level {l}"
+        assert np.array_equal(ex.pyramid_level(0, l, bordered=True), oex.level(l, bordered=True)), f"bordered level {l}"
+        got, want = ex.candidates(0, l), oex.candidates(l)
+        assert len(got) == len(want), (l, len(got), len(want))
+        for f in ("x", "y", "r"):
+            assert np.array_equal(got[f], want[f]), (l, f)
+        b = oex.blurred(l)
+        if b is not None:
+            assert np.array_equal(ex.blurred_level(0, l), b), f"blurred level {l}"
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "chain_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[6:-4])
+def test_against_cv2_chain_golden(path):
+    g = np.load(path)
+    W, H, seed, nf, nl, ini, mn, use_mask = (int(v) for v in g["params"])
+    img = g["image"]
+    mask = None
+    if use_mask:
+        mask = np.full(img.shape, 255, np.uint8)
+        mask[60:220, 150:260] = 0
+    ex = orb.ORBextractor(nf, float(g["scaleFactor"]), nl, ini, mn)
+    kp, desc = ex(img, mask)
+    assert np.array_equal(ex.features_per_level(), g["quota"])
+    assert np.array_equal(ex.pyramid_level(0, nl - 1), g["last_level"])
+    assert [len(ex.candidates(0, l)) for l in range(nl)] == g["cand_counts"].tolist()
+    _compare(kp, desc, g["kp"], g["desc"])
+
+
+@pytest.mark.parametrize("W,H,seed,nf,nl,sf,ini,mn", [
+    (640, 480, 1, 1000, 8, 1.2, 20, 7),          # C1/C2 geometry
+    (640, 480, 2, 2000, 8, 1.2, 32, 7),          # the fork's shipped ORB_RGB640x480.yaml values
+    (1280, 720, 3, 2000, 8, 1.2, 20, 7),         # C3 (nIni = 2 root nodes)
+    (424, 240, 4, 300, 3, 1.5, 15, 3),           # ORB_RGBD640x480.yaml-style scale 1.5
+    (200, 150, 5, 100, 4, 1.2, 20, 7),           # tiny: single-column cell grids at the top levels
+    (333, 777, 6, 400, 5, 1.3, 25, 5),           # portrait, odd sizes
+])
+def test_stage_by_stage_vs_oracle(W, H, seed, nf, nl, sf, ini, mn):
+    img = synth(W, H, seed)
+    ex = orb.ORBextractor(nf, sf, nl, ini, mn)
+    kp, desc = ex(img)
+    oex = orc.Extractor(nf, sf, nl, ini, mn)
+    okp, odesc = oex.extract(img)
+    t = oex.tables()
+    assert np.array_equal(ex.GetScaleFactors(), t["scale"])
+    assert np.array_equal(ex.GetInverseScaleFactors(), t["inv_scale"])
+    assert np.array_equal(ex.GetScaleSigmaSquares(), t["sigma2"])
+    assert np.array_equal(ex.GetInverseScaleSigmaSquares(), t["inv_sigma2"])
+    assert np.array_equal(ex.features_per_level(), t["quota"])
+    _stages_equal(ex, oex, nl)
+    _compare(kp, desc, okp, odesc)
+
+
+def test_edge_inputs():
+    ex = orb.ORBextractor(500, 1.2, 4, 20, 7)
+    # flat image: no corners anywhere -> zero keypoints, descriptors released
+    kp, desc = ex(np.full((240, 320), 77, np.uint8))
+    assert len(kp) == 0 and desc.shape == (0, 32)
+    # pure noise: far more candidates than the quota on every level (octree cull + dense cells)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (240, 320), dtype=np.uint8)
+    kp, desc = ex(img)
+    okp, odesc = orc.Extractor(500, 1.2, 4, 20, 7).extract(img)
+    _compare(kp, desc, okp, odesc)
+    # fully masked-out image == black image
+    kp, desc = ex(img, np.zeros_like(img))
+    assert len(kp) == 0
+    # empty image: silent no-op like the reference (ORBextractor.cc:1045-1046)
+    assert ex(np.zeros((0, 0), np.uint8)) is None
+    # a level below 62 px is a reference precondition violation -> explicit error instead of a division by zero
+    with pytest.raises(orb.OrbError):
+        orb.ORBextractor(100, 1.2, 8, 20, 7)(np.zeros((100, 100), np.uint8))
+
+
+def test_strided_input_and_mask():
+    big = synth(700, 500, 11)
+    view = big[10:490, 30:670]                         # non-contiguous rows
+    mask = np.full((480, 640), 255, np.uint8)
+    mask[100:300, 200:400] = 0
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7)
+    kp, desc = ex(view, mask)
+    okp, odesc = orc.Extractor(1000, 1.2, 8, 20, 7).extract(view, mask)
+    _compare(kp, desc, okp, odesc)
+    inside = (kp["octave"] == 0) & (kp["x"] > 210) & (kp["x"] < 390) & (kp["y"] > 110) & (kp["y"] < 290)
+    assert not inside.any()
+
+
+def test_batch_matches_single_and_oracle():
+    frames = np.stack([synth(640, 480, s) for s in range(20, 26)])
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=4)          # 6 frames through a 4-frame workspace: 2 passes
+    kp, desc, n = ex.extract_batch(frames)
+    oex = orc.Extractor(1000, 1.2, 8, 20, 7)
+    nang = nbits = 0
+    for f in range(len(frames)):
+        okp, odesc = oex.extract(frames[f])
+        a, b = _compare(kp[f, :n[f]], desc[f, :n[f]], okp, odesc)
+        nang += a
+        nbits += b
+    print(f"angle float mismatches: {nang}, descriptor bit mismatches: {nbits} over {int(n.sum())} keypoints")
+
+
+def test_device_resident_batch_idempotent():
+    import torch
+    frames = torch.from_numpy(np.stack([synth(640, 480, s) for s in range(30, 34)])).cuda()
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=4)
+    ex._plan(640, 480)
+    cap = ex.max_keypoints()
+    outs = []
+    for _ in range(2):
+        kp = torch.zeros((4, cap, 7), dtype=torch.float32, device="cuda")
+        desc = torch.zeros((4, cap, 32), dtype=torch.uint8, device="cuda")
+        n = torch.zeros(4, dtype=torch.int32, device="cuda")
+        ex.extract_batch_device(frames, kp, desc, n, cap, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ex.check_status()
+        outs.append((kp.cpu().numpy().copy(), desc.cpu().numpy().copy(), n.cpu().numpy().copy()))
+    assert np.array_equal(outs[0][2], outs[1][2])
+    for f in range(4):
+        k = outs[0][2][f]
+        assert np.array_equal(outs[0][0][f, :k], outs[1][0][f, :k]) and np.array_equal(outs[0][1][f, :k], outs[1][1][f, :k])
+    okp, odesc = orc.Extractor(1000, 1.2, 8, 20, 7).extract(frames[2].cpu().numpy())
+    k = outs[0][2][2]
+    gkp = outs[0][0][2, :k].copy().view(orb.KP_DTYPE).reshape(-1)
+    _compare(gkp, outs[0][1][2, :k], okp, odesc)
+
+
+@pytest.mark.parametrize("W,H,nf,nl", [(3840, 2160, 8000, 12)])
+def test_4k_config5(W, H, nf, nl):
+    img = synth(W, H, 0)
+    ex = orb.ORBextractor(nf, 1.2, nl, 20, 7)
+    kp, desc = ex(img, download_pyramid=False)
+    oex = orc.Extractor(nf, 1.2, nl, 20, 7)
+    okp, odesc = oex.extract(img)
+    for l in (0, 5, 11):
+        got, want = ex.candidates(0, l), oex.candidates(l)
+        assert np.array_equal(got["x"], want["x"]) and np.array_equal(got["y"], want["y"]) and np.array_equal(got["r"], want["r"])
+    _compare(kp, desc, okp, odesc)

@@ -1,0 +1,175 @@
+"""GPU parity tests of the ORBmatcher Hamming searches (through the C ABI) against the CPU oracle.  Integer/index
+work: everything must be bit-exact."""
+import numpy as np
+import pytest
+
+import orbslam_mapsave_b200 as orb
+from orbslam_mapsave_b200.synth import synth_descriptors
+from oracle import orb_oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _flip(d, nbits, rng):
+    d = d.copy()
+    for b in rng.choice(256, nbits, replace=False):
+        d[b >> 3] ^= np.uint8(1 << (b & 7))
+    return d
+
+
+def test_descriptor_distance_matches_bit_hack():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b[:10] = a[:10]
+    b[10] = ~a[10]
+    got = orb.ORBmatcher.DescriptorDistance(a, b)
+    want = np.array([orc.descriptor_distance(x, y) for x, y in zip(a, b)], np.int32)
+    assert np.array_equal(got, want)
+    assert got[0] == 0 and got[10] == 256
+    assert orb.ORBmatcher.DescriptorDistance(a[20], b[20]) == want[20]
+
+
+@pytest.mark.parametrize("nq,ndb", [(1, 1), (7, 0), (3, 1), (100, 2), (257, 513), (2000, 2000), (5000, 300), (129, 4097)])
+def test_hamming_top2_vs_oracle(nq, ndb):
+    db = synth_descriptors(ndb, 1)
+    q = synth_descriptors(nq, 2, dup_of=db if ndb else None)
+    if ndb >= 4 and nq >= 4:
+        db[3] = db[1]                     # exact duplicate rows: first index must win, second == best
+        q[0] = db[1]
+    bi, bd, sd = orb.ORBmatcher().hamming_top2(q, db)
+    obi, obd, osd = orc.hamming_top2(q, db)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(sd, osd)
+    if ndb >= 4 and nq >= 4:
+        assert bi[0] == 1 and bd[0] == 0 and sd[0] == 0
+
+
+def _scene(n1, n2, seed, nnodes=40, tri=False):
+    rng = np.random.default_rng(seed)
+    d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    node1 = rng.integers(0, nnodes, n1) * 3 + 5
+    node2 = rng.integers(0, nnodes + 6, n2) * 3 + 5          # some nodes exist on one side only
+    # plant true matches at controlled distances inside the same node, incl. the TH_LOW edge (49/50/51) and ties
+    k = min(n1, n2) // 2
+    src = rng.choice(n1, k, replace=False)
+    dst = rng.choice(n2, k, replace=False)
+    for s, t in zip(src, dst):
+        nb = int(rng.choice([0, 1, 5, 20, 35, 49, 50, 51, 60]))
+        d2[t] = _flip(d1[s], nb, rng)
+        node2[t] = node1[s]
+    # competing near-duplicates so that the ratio test and the greedy claim matter
+    for s, t in list(zip(src, dst))[: k // 3]:
+        u = int(rng.integers(0, n2))
+        d2[u] = _flip(d2[t], int(rng.choice([0, 1, 2, 30])), rng)
+        node2[u] = node2[t]
+    ang1 = rng.uniform(0, 360, n1).astype(np.float32)
+    ang2 = ang1[rng.integers(0, n1, n2)] + rng.choice([0.0, 2.0, 14.9, 15.0, 45.0, 200.0], n2).astype(np.float32)
+    ang2 = np.mod(ang2, 360).astype(np.float32)
+    flag1 = (rng.random(n1) < 0.7).astype(np.uint8)
+    flag2 = (rng.random(n2) < 0.7).astype(np.uint8)
+    out = dict(d1=d1, d2=d2, node1=node1, node2=node2, ang1=ang1, ang2=ang2, flag1=flag1, flag2=flag2)
+    if tri:
+        out.update(x1=rng.uniform(0, 640, n1).astype(np.float32), y1=rng.uniform(0, 480, n1).astype(np.float32),
+                   x2=rng.uniform(0, 640, n2).astype(np.float32), y2=rng.uniform(0, 480, n2).astype(np.float32),
+                   oct2=rng.integers(0, 8, n2).astype(np.int32),
+                   ur1=np.where(rng.random(n1) < 0.3, 100.0, -1.0).astype(np.float32),
+                   ur2=np.where(rng.random(n2) < 0.3, 100.0, -1.0).astype(np.float32))
+    return out
+
+
+@pytest.mark.parametrize("n1,n2,seed", [(300, 280, 0), (2000, 2000, 1), (1000, 40, 2), (50, 900, 3), (0, 10, 4), (10, 0, 5)])
+@pytest.mark.parametrize("ratio,ori", [(0.7, True), (0.75, True), (0.6, False), (1.0, True)])
+def test_search_by_bow_kf_frame(n1, n2, seed, ratio, ori):
+    s = _scene(n1, n2, seed)
+    fv1o, fv2o = orc.FeatVec(s["node1"]), orc.FeatVec(s["node2"])
+    on, om = orc.search_bow_kf_f(s["d1"], s["flag1"], s["ang1"], fv1o, s["d2"], s["ang2"], fv2o, ratio, ori)
+    kf = orb.View(s["d1"], orb.FeatureVector(s["node1"]), s["ang1"], flag=s["flag1"])
+    fr = orb.View(s["d2"], orb.FeatureVector(s["node2"]), s["ang2"])
+    n, m = orb.ORBmatcher(ratio, ori).SearchByBoW(kf, fr)
+    assert n == on and np.array_equal(m, om)
+    if n1 >= 300 and n2 >= 280:
+        assert n > 10
+
+
+@pytest.mark.parametrize("n1,n2,seed", [(300, 280, 10), (2000, 2000, 11), (700, 64, 12), (0, 0, 13)])
+@pytest.mark.parametrize("ratio,ori", [(0.75, True), (0.6, False)])
+def test_search_by_bow_kf_kf(n1, n2, seed, ratio, ori):
+    s = _scene(n1, n2, seed)
+    on, om = orc.search_bow_kf_kf(s["d1"], s["flag1"], s["ang1"], orc.FeatVec(s["node1"]), s["d2"], s["flag2"], s["ang2"],
+                                  orc.FeatVec(s["node2"]), ratio, ori)
+    k1 = orb.View(s["d1"], orb.FeatureVector(s["node1"]), s["ang1"], flag=s["flag1"])
+    k2 = orb.View(s["d2"], orb.FeatureVector(s["node2"]), s["ang2"], flag=s["flag2"])
+    n, m = orb.ORBmatcher(ratio, ori).SearchByBoW(k1, k2, kf_kf=True)
+    assert n == on and np.array_equal(m, om)
+
+
+@pytest.mark.parametrize("n1,n2,seed", [(300, 280, 20), (2000, 2000, 21), (64, 900, 22), (5, 0, 23)])
+@pytest.mark.parametrize("only_stereo,ori", [(False, False), (True, False), (False, True)])
+def test_search_for_triangulation(n1, n2, seed, only_stereo, ori):
+    s = _scene(n1, n2, seed, tri=True)
+    rng = np.random.default_rng(seed)
+    # a fundamental matrix that makes a good fraction of planted pairs pass: lines through random points
+    F12 = (rng.normal(0, 1, (3, 3)) * np.array([[1e-6, 1e-5, 1e-3], [1e-5, 1e-6, 1e-3], [1e-3, 1e-3, 1e-1]])).astype(np.float32)
+    sf2 = (1.2 ** np.arange(8)).astype(np.float32)
+    sig2 = (sf2 * sf2 * 5000).astype(np.float32)       # generous sigma so the epipolar gate passes often but not always
+    ex, ey = 320.0, 240.0
+    on, op = orc.search_triangulation(s["d1"], s["flag1"], s["ur1"], s["x1"], s["y1"], s["ang1"], orc.FeatVec(s["node1"]),
+                                      s["d2"], s["flag2"], s["ur2"], s["x2"], s["y2"], s["ang2"], s["oct2"], orc.FeatVec(s["node2"]),
+                                      F12, ex, ey, sf2, sig2, only_stereo, ori)
+    k1 = orb.View(s["d1"], orb.FeatureVector(s["node1"]), s["ang1"], flag=s["flag1"], x=s["x1"], y=s["y1"],
+                  octave=np.zeros(n1, np.int32), uright=s["ur1"])
+    k2 = orb.View(s["d2"], orb.FeatureVector(s["node2"]), s["ang2"], flag=s["flag2"], x=s["x2"], y=s["y2"], octave=s["oct2"],
+                  uright=s["ur2"])
+    n, p = orb.ORBmatcher(0.6, ori).SearchForTriangulation(k1, k2, F12, ex, ey, sf2, sig2, only_stereo)
+    assert n == on and np.array_equal(p, op)
+    if n1 >= 300 and n2 >= 280 and not only_stereo:
+        assert len(p) > 3
+
+
+def test_three_maxima():
+    rng = np.random.default_rng(3)
+    cases = [rng.integers(0, 50, 30) for _ in range(20)] + [np.zeros(30, int), np.full(30, 4), np.eye(30, dtype=int)[7] * 9,
+                                                            np.array([100, 9, 10, 11] + [0] * 26)]
+    for h in cases:
+        assert orb.ORBmatcher.ComputeThreeMaxima(h) == orc.three_maxima(h)
+
+
+def test_allpairs_counts_and_best_vs_oracle():
+    import torch
+    n_kf, per = 6, 300
+    base = synth_descriptors(per, 100)
+    kfs = [base] + [synth_descriptors(per, 101 + i, dup_of=base, dup_rate=0.4) for i in range(n_kf - 1)]
+    desc = np.stack(kfs)
+    d_desc = torch.from_numpy(desc).cuda()
+    q0, q1 = 1, 5
+    nq = q1 - q0
+    cnt = torch.zeros(nq * n_kf + 1, dtype=torch.int16, device="cuda")
+    bkf = torch.zeros(nq * per, dtype=torch.int32, device="cuda")
+    bd = torch.zeros(nq * per, dtype=torch.int32, device="cuda")
+    from orbslam_mapsave_b200 import capi
+    capi.check(capi.lib().orbm_allpairs_device(capi._p(d_desc), n_kf, per, q0, q1, 50, 0.75, capi._p(cnt), capi._p(bkf), capi._p(bd),
+                                               torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    cnt = cnt.cpu().numpy()[:nq * n_kf].astype(np.int64).reshape(nq, n_kf)
+    bkf, bd = bkf.cpu().numpy().reshape(nq, per), bd.cpu().numpy().reshape(nq, per)
+    for qi, q in enumerate(range(q0, q1)):
+        best_d = np.full(per, 1 << 30)
+        best_k = np.full(per, -1)
+        for k in range(n_kf):
+            if k == q:
+                assert cnt[qi, k] == 0
+                continue
+            _, b1, b2 = orc.hamming_top2(desc[q], desc[k])
+            ok = (b1 <= 50) & (b1.astype(np.float32) < np.float32(0.75) * b2.astype(np.float32))
+            assert cnt[qi, k] == int(ok.sum()), (q, k)
+            upd = b1 < best_d
+            best_k[upd] = k
+            best_d[upd] = b1[upd]
+        assert np.array_equal(bd[qi], best_d) and np.array_equal(bkf[qi], best_k)
+
+
+def test_popc_peak_is_sane():
+    v, clk = orb.popc_peak()
+    print(f"POPC peak {v / 1e12:.3f} T/s at nominal {clk / 1e9:.3f} GHz -> {v / clk / 148:.2f} POPC/clk/SM")
+    assert v > 1e11
