@@ -1,0 +1,358 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200 ORB front-end (BASELINE.json configs[1]).
+
+A "step" = ORB extraction (pyramid -> FAST cells -> octree -> blur -> orientation + rBRIEF) of one batch of
+`--frames` (default 4096) synthetic 640x480 frames per GPU, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7.
+  value      frames/s over all GPUs with the frames already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e        the same through the C-ABI call with HOST buffers (pinned): H2D of the frames and D2H of keypoints +
+             descriptors inside the timed region
+  roofline   dominant kernel (by measured share of the step) against the measured HBM copy peak
+  cpu_baseline  the CPU oracle (port of the reference path) on the host cores, bounded sample, rank 0, N=1
+  matching   secondary metric of BASELINE.json: Hamming top-2 + ratio pairs/s (all-pairs keyframe matching, sharded by
+             query keyframe, NCCL all-gather of the per-rank match tables when N>1) against the measured POPC peak
+
+`--impl reference` times the reference's CPU implementation of the path (the oracle port: the reference itself cannot be
+compiled here) on all host threads, on a bounded sample of the same workload per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
+B_FRAME = 1961064          # algorithmic bytes per frame, SURVEY.md §8(d)
+METRIC = "ORB frames/s (640x480, 1000 feat, 8 lvl)"
+
+
+def _gen_one(seed):
+    from orbslam_mapsave_b200.synth import synth
+    return synth(W, H, seed)
+
+
+def make_frames(n, seed0, unique):
+    """n frames; `unique` distinct synth() seeds (seed0...), repeated cyclically.  Cached under /tmp."""
+    unique = min(unique, n)
+    cache = f"/tmp/orb_synth_{W}x{H}_s{seed0}_u{unique}.npy"
+    if os.path.exists(cache):
+        base = np.load(cache)
+    else:
+        import multiprocessing as mp
+        nproc = max(1, min(32, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        with mp.get_context("fork").Pool(nproc) as pool:
+            base = np.stack(pool.map(_gen_one, range(seed0, seed0 + unique), chunksize=8))
+        try:
+            np.save(cache + f".{os.getpid()}.tmp.npy", base)
+            os.replace(cache + f".{os.getpid()}.tmp.npy", cache)
+        except OSError:
+            pass
+    reps = (n + unique - 1) // unique
+    return np.concatenate([base] * reps)[:n] if reps > 1 else base[:n]
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_extract_sample(frames, threads, budget_s):
+    """Oracle extraction on `threads` host threads over a bounded sample; returns (frames/s, n_frames, seconds)."""
+    from oracle import orb_oracle_py as orc
+    chunk = max(threads * 4, 8)
+    done, secs = 0, 0.0
+    while secs < budget_s and done + chunk <= len(frames):
+        s, _ = orc.extract_batch_mt(frames[done:done + chunk], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+        secs += s
+        done += chunk
+    return done / secs, done, secs
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_threads()
+    frames = make_frames(max(threads * 8, 64), 0, 4096)
+    per_step = len(frames)
+    from oracle import orb_oracle_py as orc
+    for _ in range(args.warmup):
+        orc.extract_batch_mt(frames[:threads], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+    total_s = 0.0
+    for _ in range(args.steps):
+        s, _ = orc.extract_batch_mt(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+        total_s += s
+    v = per_step * args.steps / total_s
+    sample = f"{per_step} of the 4096 frames per step, {threads} host threads, one extractor instance per thread"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C2: batch of 640x480 synthetic frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7",
+                   "frames_per_step": per_step, "note": "CPU oracle port of src/ORBextractor.cc (reference needs OpenCV/Boost to compile)"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step")
+    ap.add_argument("--unique", type=int, default=4096, help="distinct synthetic frames per GPU (others repeat them)")
+    ap.add_argument("--chunk", type=int, default=256, help="frames per device pass (workspace size)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-match", action="store_true", help="skip the matching sub-benchmark")
+    ap.add_argument("--match-q", type=int, default=32, help="query keyframes per GPU in the matching sub-benchmark")
+    ap.add_argument("--match-db", type=int, default=512, help="database keyframes in the matching sub-benchmark")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # synthetic frames first (fork pool) — before CUDA is touched
+    frames = make_frames(args.frames, rank * args.frames, args.unique)
+
+    import torch
+    import torch.distributed as dist
+    import orbslam_mapsave_b200 as orb
+    from orbslam_mapsave_b200 import capi
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nF = args.frames
+    h_frames = torch.from_numpy(frames).pin_memory()
+    d_frames = h_frames.cuda(non_blocking=True)
+    ex = orb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, max_batch=args.chunk, device=local_rank)
+    cap = ex.max_keypoints()
+    d_kp = torch.zeros((nF, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc = torch.zeros((nF, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(nF, dtype=torch.int32, device="cuda")
+    # a real (non-default) stream: the C ABI treats NULL as "the handle's own stream", and CUDA events must be recorded on
+    # the stream the kernels are launched on
+    tstream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+
+    def step(stages=capi.STAGE_ALL):
+        ex.extract_batch_device(d_frames, d_kp, d_desc, d_n, cap, stream=stream, stages=stages)
+
+    def timed(fn, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    ex.check_status()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ex.launch_count()
+    secs = timed(step, args.steps)
+    launches = ex.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ex.check_status()
+    value = world * nF * args.steps / secs
+    total_kp = int(d_n.sum().item())
+
+    # ---- per-stage device times (live, CUDA events) -> dominant kernel and its roofline
+    stage_names = [("pyramid", capi.STAGE_PYRAMID), ("fast", capi.STAGE_FAST), ("octree", capi.STAGE_OCTREE),
+                   ("blur", capi.STAGE_BLUR), ("describe", capi.STAGE_DESCRIBE)]
+    stage_s = {}
+    for nm, bit in stage_names:
+        step(bit)
+        stage_s[nm] = timed(lambda b=bit: step(b), max(1, min(args.steps, 3))) / max(1, min(args.steps, 3))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    kp_per_frame = total_kp / nF
+    pyr_px = 950532
+    # algorithmic bytes per frame of each stage (DESIGN.md "Kernels"): reads + writes that stage must do
+    stage_bytes = {
+        "pyramid": W * H + (pyr_px - W * H) + (pyr_px - W * H),         # read input, write levels>=1, read each level l-1 once... see DESIGN
+        "fast": pyr_px + 7100 * 8,                                      # read every level once + write ~7.1k candidates
+        "octree": 7100 * 8 + kp_per_frame * 8,
+        "blur": 2 * pyr_px,
+        "describe": kp_per_frame * (749 + 512 + 60),
+    }
+    stage_bytes["pyramid"] = W * H + 2 * (pyr_px - W * H) + W * H      # + level-0 copy write
+    dom = max(stage_s, key=stage_s.get)
+    launches_per_step = launches / args.steps
+    passes = (nF + args.chunk - 1) // args.chunk
+    dom_launches = {"pyramid": NLEVELS, "fast": 1, "octree": 1, "blur": NLEVELS, "describe": 1}[dom] * passes
+    dom_launch_s = stage_s[dom] / dom_launches
+    achieved = stage_bytes[dom] * nF / stage_s[dom] / 1e9
+    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast", "octree": "k_octree", "blur": "k_blur",
+                                           "describe": "k_describe"}[dom],
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": dom_launch_s * 1e3, "algorithmic_bytes_per_frame": stage_bytes[dom],
+                "stage_ms_per_step": {k: v * 1e3 for k, v in stage_s.items()},
+                "step_hbm_frac": (B_FRAME * nF / (secs / args.steps) / 1e9) / hbm_peak,
+                "note": "640x480 pyramids are L2-resident and this stage is integer-issue bound, not HBM bound (SURVEY.md §7)"}
+
+    # ---- end to end through the C ABI with host buffers
+    h_kp = torch.zeros((nF, cap, 7), dtype=torch.float32).pin_memory()
+    h_desc = torch.zeros((nF, cap, 32), dtype=torch.uint8).pin_memory()
+    h_n = np.zeros(nF, np.int32)
+
+    def e2e_step():
+        capi.check(capi.lib().orbx_extract_batch(ex.handle, capi._p(h_frames), nF, W, H, W, W * H, None, 0, 0,
+                                                 capi._p(h_kp), capi._p(h_desc), cap, capi._p(h_n)))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * nF * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(nF * W * H),
+           "d2h_bytes_per_step": int(h_n.sum()) * 60 + nF * 4, "ms_per_step": 1e3 * e2e_s / args.steps}
+
+    # ---- secondary metric: Hamming matches/s (all-pairs keyframe matching, sharded by query keyframe)
+    matching = None
+    if not args.no_match:
+        from orbslam_mapsave_b200.synth import synth_descriptors
+        per = 2000
+        nq, ndb = args.match_q, args.match_db
+        base = synth_descriptors(per, 7)
+        rng = np.random.default_rng(11)
+        db = rng.integers(0, 256, (ndb, per, 32), dtype=np.uint8)
+        flips = rng.integers(0, 256, (ndb, per // 4, 32), dtype=np.uint8) * (rng.random((ndb, per // 4, 32)) < 0.05)
+        db[:, : per // 4] = base[None, : per // 4] ^ flips.astype(np.uint8)      # planted near-duplicates across keyframes
+        d_db = torch.from_numpy(db).cuda()
+        q0 = (rank * nq) % ndb
+        q1 = min(q0 + nq, ndb)
+        cnt = torch.zeros(((q1 - q0) * ndb + 1) // 2 * 2, dtype=torch.int16, device="cuda")
+
+        def mstep():
+            capi.check(capi.lib().orbm_allpairs_device(capi._p(d_db), ndb, per, q0, q1, 50, 0.75, capi._p(cnt), None, None, stream))
+            if world > 1:
+                out = [torch.empty_like(cnt) for _ in range(world)]
+                dist.all_gather(out, cnt)
+        for _ in range(3):
+            mstep()
+        msteps = max(2, args.steps)
+        msecs = timed(mstep, msteps)
+        pairs = world * (q1 - q0) * (ndb - 1) * per * per * msteps
+        popc, clk = orb.popc_peak(local_rank)
+        matching = {"metric": "Hamming top-2+ratio descriptor pairs/s", "value": pairs / msecs, "unit": "pairs/s",
+                    "config": {"workload": f"all-pairs: {q1 - q0} query keyframes/GPU x {ndb} keyframes x {per} descriptors",
+                               "collective": "all_gather(match-count table)" if world > 1 else "none"},
+                    "roofline": {"bound": "popc", "achieved": pairs / msecs * 8 / 1e12, "peak": popc / 1e12 * world, "unit": "TPOPC/s",
+                                 "frac": pairs / msecs * 8 / (popc * world), "peak_source": "orbm_popc_peak microbenchmark, this run"}}
+        if rank == 0 and not args.no_cpu:
+            from oracle import orb_oracle_py as orc
+            thr = host_threads()
+            qs = db[0][: max(thr * 16, 64)]
+            _, _, _, s = orc.hamming_top2(qs, db[1], nthreads=thr)
+            matching["cpu_baseline"] = {"value": len(qs) * per / s, "unit": "pairs/s", "cores": thr, "kind": "port",
+                                        "sample": f"{len(qs)} queries x {per} descriptors, reference bit-hack popcount"}
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        thr = host_threads()
+        v, n_done, s = cpu_extract_sample(frames, thr, 12.0)
+        cpu = {"value": v, "unit": "frames/s", "cores": thr, "kind": "port",
+               "sample": f"first {n_done} of the {nF} frames ({s:.1f} s), one oracle extractor per thread, frames dealt round-robin"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C2: batch of 640x480 synthetic frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7",
+                       "frames_per_gpu_per_step": nF, "unique_frames_per_gpu": min(args.unique, nF), "frames_per_device_pass": args.chunk,
+                       "keypoints_per_frame": kp_per_frame, "l2": "inputs_exceed_l2 (1.26 GB of frames per step per GPU)",
+                       "parallelism": f"frame-sharded x{world}, no data-path collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "matching": matching,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,7 +26,7 @@ typedef enum orb_status {
     ORB_ERR_CUDA = -1,          /* a CUDA runtime call failed; orb_last_error() has the text */
     ORB_ERR_ARG = -2,           /* bad argument (null pointer, size mismatch, unsupported geometry) */
     ORB_ERR_CAPACITY = -3,      /* an output capacity given by the caller is too small */
-    ORB_ERR_OVERFLOW = -4,      /* an internal candidate buffer overflowed (raise cand_per_cell at create) */
+    ORB_ERR_OVERFLOW = -4,      /* a candidate buffer capped by ORBX_CAND_PER_CELL overflowed (default sizing cannot) */
     ORB_ERR_GEOMETRY = -5       /* a pyramid level is < 62 px: the reference divides by zero there (ORBextractor.cc:783-786) */
 } orb_status;
 

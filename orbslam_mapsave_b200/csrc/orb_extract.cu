@@ -760,7 +760,23 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
                     "level %d aspect ratio gives nIni=%d root nodes (reference divides by zero at 0)", l, L.nIni);
         L.hX = (float)(L.maxBX - ORBX_MINB) / L.nIni;                                       // :544
         L.candOff = candOff;
-        L.candCap = std::min(L.nCols * L.nRows * ex->candPerCell, 65535 * 16);
+        {   // worst case: 3x3 NMS survivors are never 8-adjacent, so a cell domain dw x dh holds <= ceil(dw/2)*ceil(dh/2).
+            // HBM is plentiful (180 GB): size for the bound so the candidate list can never overflow.
+            long bound = 0;
+            for (int i = 0; i < L.nRows; i++) {
+                const int iniY = ORBX_MINB + i * L.hCell;
+                if (iniY >= L.maxBY - 3) continue;
+                const int dh = std::min(iniY + L.hCell + 6, L.maxBY) - iniY - 6;
+                for (int j = 0; j < L.nCols; j++) {
+                    const int iniX = ORBX_MINB + j * L.wCell;
+                    if (iniX >= L.maxBX - 6) continue;
+                    const int dw = std::min(iniX + L.wCell + 6, L.maxBX) - iniX - 6;
+                    if (dw > 0 && dh > 0) bound += (long)((dw + 1) / 2) * ((dh + 1) / 2);
+                }
+            }
+            if (ex->candPerCell > 0) bound = std::min<long>(bound, (long)L.nCols * L.nRows * ex->candPerCell);
+            L.candCap = (int)std::max<long>(bound, 1);
+        }
         candOff += L.candCap;
         const int nodeBound = std::max(L.quota + 3, 4 * L.nIni) + 1;
         L.selOff = selOff; L.selCap = nodeBound;
@@ -828,7 +844,7 @@ extern "C" int orbx_create(orbx_extractor** out, int nfeatures, float scale_fact
     ORB_CUDA_TRY(cudaSetDevice(device));
     orbx_extractor* ex = new orbx_extractor();
     ex->nfeatures = nfeatures; ex->nlevels = nlevels; ex->iniTh = ini_th; ex->minTh = min_th; ex->device = device;
-    ex->maxBatch = max_batch; ex->scaleFactor = scale_factor; ex->candPerCell = 64;
+    ex->maxBatch = max_batch; ex->scaleFactor = scale_factor; ex->candPerCell = 0;   // 0 = size for the worst case
     if (const char* e = getenv("ORBX_CAND_PER_CELL")) ex->candPerCell = std::max(8, atoi(e));
     // scale tables and per-level quotas (ORBextractor.cc:414-445)
     ex->sf.resize(nlevels); ex->s2.resize(nlevels); ex->isf.resize(nlevels); ex->is2.resize(nlevels); ex->quota.resize(nlevels);
@@ -957,7 +973,7 @@ extern "C" int orbx_check_status(orbx_extractor* ex) {
     ORB_CUDA_TRY(cudaMemcpy(&s, ex->d_status, sizeof(int), cudaMemcpyDeviceToHost));
     if (s) ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
     ORB_REQUIRE(!(s & (ORB_DEV_CAND_OVERFLOW | ORB_DEV_NODE_OVERFLOW)), ORB_ERR_OVERFLOW,
-                "FAST candidate buffer overflow (set ORBX_CAND_PER_CELL > %d)", ex->candPerCell);
+                "FAST candidate buffer overflow (ORBX_CAND_PER_CELL=%d caps it; unset it to size for the worst case)", ex->candPerCell);
     ORB_REQUIRE(!(s & ORB_DEV_OUT_OVERFLOW), ORB_ERR_CAPACITY, "keypoint output capacity too small (need orbx_max_keypoints())");
     return ORB_OK;
 }

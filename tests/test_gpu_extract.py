@@ -68,7 +68,7 @@ def test_against_cv2_chain_golden(path):
     (1280, 720, 3, 2000, 8, 1.2, 20, 7),         # C3 (nIni = 2 root nodes)
     (424, 240, 4, 300, 3, 1.5, 15, 3),           # ORB_RGBD640x480.yaml-style scale 1.5
     (200, 150, 5, 100, 4, 1.2, 20, 7),           # tiny: single-column cell grids at the top levels
-    (333, 777, 6, 400, 5, 1.3, 25, 5),           # portrait, odd sizes
+    (487, 641, 6, 400, 5, 1.3, 25, 5),           # portrait, odd sizes
 ])
 def test_stage_by_stage_vs_oracle(W, H, seed, nf, nl, sf, ini, mn):
     img = synth(W, H, seed)
@@ -105,6 +105,9 @@ def test_edge_inputs():
     # a level below 62 px is a reference precondition violation -> explicit error instead of a division by zero
     with pytest.raises(orb.OrbError):
         orb.ORBextractor(100, 1.2, 8, 20, 7)(np.zeros((100, 100), np.uint8))
+    # aspect ratio < 0.5 gives nIni = round(w/h) = 0 root nodes: the reference divides by zero (ORBextractor.cc:542-544)
+    with pytest.raises(orb.OrbError):
+        orb.ORBextractor(100, 1.2, 2, 20, 7)(np.zeros((777, 333), np.uint8))
 
 
 def test_strided_input_and_mask():
@@ -152,7 +155,8 @@ def test_device_resident_batch_idempotent():
     assert np.array_equal(outs[0][2], outs[1][2])
     for f in range(4):
         k = outs[0][2][f]
-        assert np.array_equal(outs[0][0][f, :k], outs[1][0][f, :k]) and np.array_equal(outs[0][1][f, :k], outs[1][1][f, :k])
+        assert np.array_equal(outs[0][0][f, :k].view(np.uint32), outs[1][0][f, :k].view(np.uint32))
+        assert np.array_equal(outs[0][1][f, :k], outs[1][1][f, :k])
     okp, odesc = orc.Extractor(1000, 1.2, 8, 20, 7).extract(frames[2].cpu().numpy())
     k = outs[0][2][2]
     gkp = outs[0][0][2, :k].copy().view(orb.KP_DTYPE).reshape(-1)
