@@ -121,51 +121,39 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, 
 // then keep score >= ini unless that set is empty.  Candidates carry (cell id, y, x) as their order key, which is
 // the reference's vToDistributeKeys order (cell row-major, then FAST's y-then-x order).
 // =====================================================================================================
-__device__ __forceinline__ bool has9(u32 m) {
-    m |= m << 16;
-    u32 r = m & (m >> 1);
-    r &= r >> 2;
-    r &= r >> 4;
-    r &= m >> 8;
-    return (r & 0xFFFFu) != 0;
-}
+// Packed formulation: two horizontally adjacent pixels per thread, every value a u16x2.  With the shared tile stored as
+// u16 pixels in two copies (even-aligned pairs and pairs shifted by one pixel) every (ring pixel of x, ring pixel of x+1)
+// pair is ONE aligned 32-bit shared load.  d' = 256 + v - ring is one 32-bit subtract (no borrow between halves), and
+//   A = max over the 16 arcs of min(d over 9 contiguous)      B = max over arcs of min(-d) = -(min over arcs of max(d))
+// are 2 x (16 + 16 + 8) three-input packed min/max (VIMNMX3.U16x2 on sm_100a).  score = max(A, B) - 1 and the pixel is a
+// FAST-9 corner at threshold t iff score >= t — no segment test, no branches, identical to cv::FAST + cornerScore.
+__device__ __forceinline__ u32 min3x2(u32 a, u32 b, u32 c) { return __vimin3_u16x2(a, b, c); }
+__device__ __forceinline__ u32 max3x2(u32 a, u32 b, u32 c) { return __vimax3_u16x2(a, b, c); }
 
-__device__ __forceinline__ int fast_score(const u8* c, int TP, int t) {
-    // returns 0 if not a FAST-9 corner at threshold t, else cornerScore (max threshold keeping it a corner)
-    const int v = c[0];
-    const int p0 = c[3 * TP], p4 = c[3], p8 = c[-3 * TP], p12 = c[-3];
-    const int hi = v + t, lo = v - t;
-    const int nb = (p0 > hi) + (p4 > hi) + (p8 > hi) + (p12 > hi);
-    const int nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
-    if (nb < 2 && nd < 2) return 0;
-    int d[16];
-    d[0] = v - p0; d[4] = v - p4; d[8] = v - p8; d[12] = v - p12;
-    d[1] = v - c[3 * TP + 1]; d[2] = v - c[2 * TP + 2]; d[3] = v - c[TP + 3];
-    d[5] = v - c[-TP + 3]; d[6] = v - c[-2 * TP + 2]; d[7] = v - c[-3 * TP + 1];
-    d[9] = v - c[-3 * TP - 1]; d[10] = v - c[-2 * TP - 2]; d[11] = v - c[-TP - 3];
-    d[13] = v - c[TP - 3]; d[14] = v - c[2 * TP - 2]; d[15] = v - c[3 * TP - 1];
-    u32 md = 0, mb = 0;
+__device__ __forceinline__ void fast_score_pair(const u32 (&r)[16], u32 v, int& s0, int& s1) {
+    const u32 vb = v + 0x01000100u;
+    u32 d[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = vb - r[k];
+    u32 lo3[16], hi3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        md |= (u32)(d[k] > t) << k;
-        mb |= (u32)(d[k] < -t) << k;
+        lo3[k] = min3x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        hi3[k] = max3x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
     }
-    if (!has9(md) && !has9(mb)) return 0;
-    // A = max over the 16 arcs of min(d over 9 contiguous), B likewise on -d; score = max(A,B)-1
-    int lo2[16], hi2[16], lo4[16], hi4[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo2[k] = min(d[k], d[(k + 1) & 15]); hi2[k] = max(d[k], d[(k + 1) & 15]); }
-#pragma unroll
-    for (int k = 0; k < 16; k++) { lo4[k] = min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = max(hi2[k], hi2[(k + 2) & 15]); }
-    int A = -256, Bm = 256;
+    u32 lo9[16], hi9[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int lo9 = min(min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int hi9 = max(max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-        A = max(A, lo9);
-        Bm = min(Bm, hi9);
+        lo9[k] = min3x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        hi9[k] = max3x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
     }
-    return max(A, -Bm) - 1;
+    u32 A = max3x2(lo9[0], lo9[1], lo9[2]), Bm = min3x2(hi9[0], hi9[1], hi9[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) { A = max3x2(A, lo9[k], lo9[k + 1]); Bm = min3x2(Bm, hi9[k], hi9[k + 1]); }
+    A = __vmaxu2(A, lo9[15]);
+    Bm = __vminu2(Bm, hi9[15]);
+    s0 = max((int)(A & 0xFFFF) - 256, 256 - (int)(Bm & 0xFFFF)) - 1;
+    s1 = max((int)(A >> 16) - 256, 256 - (int)(Bm >> 16)) - 1;
 }
 
 __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
@@ -173,7 +161,7 @@ __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constan
                                                              int* __restrict__ status) {
     extern __shared__ __align__(16) u8 smem[];
     __shared__ u32 s_list[ORBX_FAST_LOCAL_CAP];
-    __shared__ int s_nloc, s_nini, s_base, s_emit;
+    __shared__ int s_ncorner, s_nloc, s_nini, s_base, s_emit;
 
     int l = 0;
     while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].cellBase) l++;
@@ -186,42 +174,85 @@ __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constan
     const int tw = maxX - iniX, th = maxY - iniY, dw = tw - 6, dh = th - 6;
     if (dw <= 0 || dh <= 0) return;                                   // cv::FAST on a ROI < 7 px finds nothing
 
-    const int TP = P.tilePitch, SP = P.scorePitch;
-    u8* tile = smem;
-    u8* score = smem + (size_t)P.tileRows * TP;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_nloc = 0; s_nini = 0; s_emit = 0; }
+    const int TPp = P.tilePitch, SP = P.scorePitch;                   // tile pitch in pixel PAIRS (u32), score pitch in bytes
+    u32* tA = reinterpret_cast<u32*>(smem);                           // pair j = pixels (2j, 2j+1)
+    u32* tB = tA + (size_t)P.tileRows * TPp;                          // pair j = pixels (2j+1, 2j+2)
+    u8* score = reinterpret_cast<u8*>(tB + (size_t)P.tileRows * TPp);
+    u16* clist = reinterpret_cast<u16*>(score + (size_t)P.scoreRows * SP);
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_ncorner = 0; s_nloc = 0; s_nini = 0; s_emit = 0; }
 
-    const u8* src = pyr + (size_t)f * P.frameBytes + L.off + (size_t)(iniY + ORBX_OY) * L.pitch + iniX + ORBX_OX;
-    for (int ty = warp; ty < th; ty += ORBX_FAST_THREADS / 32)
-        for (int tx = lane; tx < tw; tx += 32) tile[ty * TP + tx] = __ldg(src + (size_t)ty * L.pitch + tx);
-    for (int i = tid; i < (dh + 2) * SP; i += ORBX_FAST_THREADS) score[i] = 0;
+    // ---- stage the cell ROI: global-word aligned, expanded to u16 pixels, two copies
+    const int bx0 = iniX + ORBX_OX, gx0 = bx0 & ~3, lead = bx0 - gx0;
+    const int words = (lead + tw + 1 + 3) >> 2;
+    const u8* src = pyr + (size_t)f * P.frameBytes + L.off + (size_t)(iniY + ORBX_OY) * L.pitch + gx0;
+    {
+        const u32 inv = 0xFFFFFFFFu / (u32)words + 1;
+        for (int t = tid; t < th * words; t += ORBX_FAST_THREADS) {
+            const int r = (int)__umulhi((u32)t, inv), wi = t - r * words;
+            const u32* gp = reinterpret_cast<const u32*>(src + (size_t)r * L.pitch) + wi;
+            const u32 w = __ldg(gp), wn = __ldg(gp + 1);
+            uint2 a, b;
+            a.x = __byte_perm(w, 0, 0x4140); a.y = __byte_perm(w, 0, 0x4342);
+            b.x = __byte_perm(w, 0, 0x4241); b.y = (w >> 24) | ((wn & 0xFF) << 16);
+            *reinterpret_cast<uint2*>(tA + r * TPp + 2 * wi) = a;
+            *reinterpret_cast<uint2*>(tB + r * TPp + 2 * wi) = b;
+        }
+        for (int i = tid; i < (((dh + 2) * SP) >> 2); i += ORBX_FAST_THREADS) reinterpret_cast<u32*>(score)[i] = 0;
+    }
     __syncthreads();
 
-    const int t = P.minTh;
-    for (int py = warp; py < dh; py += ORBX_FAST_THREADS / 32)
-        for (int px = lane; px < dw; px += 32) {
-            const int s = fast_score(tile + (py + 3) * TP + px + 3, TP, t);
-            if (s > 0) score[(py + 1) * SP + px + 1] = (u8)s;
+    // ---- scores, two pixels per thread
+    {
+        const int t = P.minTh;
+        const int npr = (dw + 1) >> 1;
+        const u32 inv = 0xFFFFFFFFu / (u32)npr + 1;
+        const int X0 = lead + 3;                                      // tile x of domain pixel 0
+        // ring offsets (dx,dy) in cornerScore order; copy selected by the parity of the first pixel's tile x
+        const u32* cE = (X0 & 1) ? tB : tA;                           // pairs starting at X0 + even dx
+        const u32* cO = (X0 & 1) ? tA : tB;                           // pairs starting at X0 + odd dx
+#define PAIR(dx, dy) (((dx) & 1) ? cO : cE)[(row + 3 + (dy)) * TPp + ((X0 + (dx)) >> 1) + p]
+        for (int task = tid; task < npr * dh; task += ORBX_FAST_THREADS) {
+            const int row = npr == 1 ? task : (int)__umulhi((u32)task, inv), p = task - row * npr;   // (inv overflows for npr == 1)
+            u32 r[16];
+            r[0] = PAIR(0, 3); r[1] = PAIR(1, 3); r[2] = PAIR(2, 2); r[3] = PAIR(3, 1);
+            r[4] = PAIR(3, 0); r[5] = PAIR(3, -1); r[6] = PAIR(2, -2); r[7] = PAIR(1, -3);
+            r[8] = PAIR(0, -3); r[9] = PAIR(-1, -3); r[10] = PAIR(-2, -2); r[11] = PAIR(-3, -1);
+            r[12] = PAIR(-3, 0); r[13] = PAIR(-3, 1); r[14] = PAIR(-2, 2); r[15] = PAIR(-1, 3);
+            const u32 v = PAIR(0, 0);
+            int s0, s1;
+            fast_score_pair(r, v, s0, s1);
+            const int px = 2 * p;
+            if (s0 >= t) {
+                score[(row + 1) * SP + px + 1] = (u8)s0;
+                clist[atomicAdd(&s_ncorner, 1)] = (u16)((row << 8) | px);
+            }
+            if (s1 >= t && px + 1 < dw) {
+                score[(row + 1) * SP + px + 2] = (u8)s1;
+                clist[atomicAdd(&s_ncorner, 1)] = (u16)((row << 8) | (px + 1));
+            }
         }
+#undef PAIR
+    }
     __syncthreads();
 
-    for (int py = warp; py < dh; py += ORBX_FAST_THREADS / 32)
-        for (int px = lane; px < dw; px += 32) {
-            const u8* sp = score + (py + 1) * SP + px + 1;
-            const int s = sp[0];
-            if (s == 0) continue;
-            const bool keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
-                              s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
-            if (!keep) continue;
-            const int slot = atomicAdd(&s_nloc, 1);
-            if (slot < ORBX_FAST_LOCAL_CAP) s_list[slot] = ((u32)s << 16) | ((u32)py << 8) | (u32)px;
-            if (s >= P.iniTh) atomicAdd(&s_nini, 1);
-        }
+    // ---- 3x3 non-maximum suppression over the corners only (neighbours outside the cell's domain count as 0)
+    const int ncorner = s_ncorner;
+    for (int e = tid; e < ncorner; e += ORBX_FAST_THREADS) {
+        const int py = clist[e] >> 8, px = clist[e] & 0xFF;
+        const u8* sp = score + (py + 1) * SP + px + 1;
+        const int s = sp[0];
+        const bool keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
+                          s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
+        if (!keep) continue;
+        const int slot = atomicAdd(&s_nloc, 1);
+        if (slot < ORBX_FAST_LOCAL_CAP) s_list[slot] = ((u32)s << 16) | ((u32)py << 8) | (u32)px;
+        if (s >= P.iniTh) atomicAdd(&s_nini, 1);
+    }
     __syncthreads();
     const int nloc = min(s_nloc, ORBX_FAST_LOCAL_CAP);
     if (nloc == 0) return;
-    const int T = s_nini > 0 ? P.iniTh : P.minTh;
+    const int T = s_nini > 0 ? P.iniTh : P.minTh;                     // the iniThFAST -> minThFAST retry (:811-815)
     const int nEmit = s_nini > 0 ? s_nini : nloc;
     if (tid == 0) {
         const int base = atomicAdd(&candCount[f * P.nlevels + l], nEmit);
@@ -794,9 +825,10 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     P.totalCells = cellBase; P.candTotal = candOff; P.selTotal = selOff; P.maxNodes = maxNodes;
     P.sortN = 2; while (P.sortN < maxNodes) P.sortN <<= 1;
     P.frameBytes = off;
-    P.tilePitch = (int)orb_align_up(maxCW + 6, 4); P.tileRows = maxCH + 6;
-    P.scorePitch = (int)orb_align_up(maxCW + 2, 4); P.scoreRows = maxCH + 2;
-    ex->fastSmem = (size_t)P.tilePitch * P.tileRows + (size_t)P.scorePitch * P.scoreRows;
+    // FAST tile: pixel pairs (u32) per row = 2 * words, words = ceil((3 + cellW + 6 + 1) / 4); two copies; + score map + corner list
+    P.tilePitch = 2 * (int)((3 + maxCW + 6 + 1 + 3) / 4) + 2; P.tileRows = maxCH + 6;
+    P.scorePitch = (int)orb_align_up(maxCW + 3, 4); P.scoreRows = maxCH + 2;
+    ex->fastSmem = (size_t)P.tilePitch * P.tileRows * 4 * 2 + (size_t)P.scorePitch * P.scoreRows + (size_t)(maxCW + 1) * maxCH * 2 + 16;
     ex->octSmem = (size_t)maxNodes * (16 * 2 + 4 * 2 + 16 + 4 * 3) + (size_t)P.sortN * 8 + 64;
     ORB_REQUIRE(ex->octSmem <= 220 * 1024, ORB_ERR_ARG, "nfeatures too large for the octree kernel's shared memory");
     ORB_REQUIRE(maxCW <= 250 && maxCH <= 250, ORB_ERR_GEOMETRY, "cell too large");
