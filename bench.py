@@ -261,7 +261,7 @@ def main():
     dom = max(stage_s, key=stage_s.get)
     launches_per_step = launches / args.steps
     passes = (nF + args.chunk - 1) // args.chunk
-    dom_launches = {"pyramid": NLEVELS, "fast": 1, "octree": 1, "blur": NLEVELS, "describe": 1}[dom] * passes
+    dom_launches = {"pyramid": NLEVELS, "fast": 1, "octree": 1, "blur": 1, "describe": 1}[dom] * passes
     dom_launch_s = stage_s[dom] / dom_launches
     achieved = stage_bytes[dom] * nF / stage_s[dom] / 1e9
     roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast", "octree": "k_octree", "blur": "k_blur",

@@ -50,6 +50,7 @@ struct LevelPlan {
     int candOff, candCap, selOff, selCap;
     float scale, kpSize;
     int xtabOff, ytabOff;
+    int fastResize;                       // 1: k_resize (dp2a form) applies, 0: k_resize_generic
 };
 struct Plan {
     int nlevels, iniTh, minTh;
@@ -58,6 +59,7 @@ struct Plan {
     int width, height;
     unsigned long long frameBytes;
     int umax[16];
+    int blurTileBase[ORBX_MAX_LEVELS + 1];
     LevelPlan lv[ORBX_MAX_LEVELS];
 };
 struct ResizeTap { int s; short c0, c1; };
@@ -70,40 +72,41 @@ struct ResizeTap { int s; short c0, c1; };
 // =====================================================================================================
 __global__ void __launch_bounds__(256) k_level0(const __grid_constant__ Plan P, const u8* __restrict__ images,
                                                 const u8* __restrict__ masks, u8* __restrict__ pyr) {
+    // ROI of level 0 = input (zeroed where mask == 0, ORBextractor.cc:1048-1053); the border is filled by k_border
     const LevelPlan& L = P.lv[0];
-    const int bx = (blockIdx.x * 64 + threadIdx.x) * 4, by = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
-    if (bx >= L.pitch || by >= L.brows) return;
-    const size_t fo = (size_t)f * P.width * P.height;
-    const int ry = dev_reflect101(by - ORBX_OY, L.h);
-    const u8* src = images + fo + (size_t)ry * P.width;
-    const u8* msk = masks ? masks + fo + (size_t)ry * P.width : nullptr;
+    const int x = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
+    if (x >= L.w || y >= L.h) return;
+    const size_t fo = (size_t)f * P.width * P.height + (size_t)y * P.width;
+    const u8* src = images + fo;
+    const u8* msk = masks ? masks + fo : nullptr;
     u32 out = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int rx = dev_reflect101(bx + k - ORBX_OX, L.w);
-        u32 v = __ldg(src + rx);
-        if (msk && __ldg(msk + rx) == 0) v = 0;
+        const int xx = min(x + k, L.w - 1);
+        u32 v = __ldg(src + xx);
+        if (msk && __ldg(msk + xx) == 0) v = 0;
         out |= v << (8 * k);
     }
-    *reinterpret_cast<u32*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)by * L.pitch + bx) = out;
+    *reinterpret_cast<u32*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
 }
 
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, int level, u8* __restrict__ pyr,
-                                                const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab) {
+// Generic gather form (any scale factor): one thread = 4 adjacent ROI pixels, 4 byte gathers each.
+__global__ void __launch_bounds__(256) k_resize_generic(const __grid_constant__ Plan P, int level, u8* __restrict__ pyr,
+                                                        const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab) {
     const LevelPlan& L = P.lv[level];
     const LevelPlan& S = P.lv[level - 1];
-    const int bx = (blockIdx.x * 64 + threadIdx.x) * 4, by = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
-    if (bx >= L.pitch || by >= L.brows) return;
+    const int x = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
+    if (x >= L.w || y >= L.h) return;
     u8* frame = pyr + (size_t)f * P.frameBytes;
     const u8* src = frame + S.off + (size_t)ORBX_OY * S.pitch + ORBX_OX;
-    const ResizeTap ty = ytab[L.ytabOff + dev_reflect101(by - ORBX_OY, L.h)];
+    const ResizeTap ty = ytab[L.ytabOff + y];
     const int sy0 = min(max(ty.s, 0), S.h - 1), sy1 = min(max(ty.s + 1, 0), S.h - 1);
     const u8* r0p = src + (size_t)sy0 * S.pitch;
     const u8* r1p = src + (size_t)sy1 * S.pitch;
     u32 out = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const ResizeTap tx = xtab[L.xtabOff + dev_reflect101(bx + k - ORBX_OX, L.w)];
+        const ResizeTap tx = xtab[L.xtabOff + min(x + k, L.w - 1)];
         const int sx = tx.s, sx1 = min(sx + 1, S.w - 1);
         const int r0 = r0p[sx] * tx.c0 + r0p[sx1] * tx.c1;
         const int r1 = r1p[sx] * tx.c0 + r1p[sx1] * tx.c1;
@@ -111,7 +114,70 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, 
         v = min(max(v, 0), 255);
         out |= (u32)v << (8 * k);
     }
-    *reinterpret_cast<u32*>(frame + L.off + (size_t)by * L.pitch + bx) = out;
+    *reinterpret_cast<u32*>(frame + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
+}
+
+// Fast form for scale factors <= 2: the 4 outputs of a thread read source bytes inside 3 aligned words per source row,
+// the two horizontal taps of a pixel are cut out with a funnel shift and combined with their 11-bit coefficients by one
+// IDP2A (p0*c0 + p1*c1), the vertical pass is the reference's exact (>>4, *b, >>16, +2, >>2) sequence.
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, int level, u8* __restrict__ pyr,
+                                                const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab) {
+    const LevelPlan& L = P.lv[level];
+    const LevelPlan& S = P.lv[level - 1];
+    const int x = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
+    if (x >= L.w || y >= L.h) return;
+    u8* frame = pyr + (size_t)f * P.frameBytes;
+    const u8* src = frame + S.off + (size_t)ORBX_OY * S.pitch + ORBX_OX;
+    const ResizeTap ty = ytab[L.ytabOff + y];
+    const int sy0 = min(max(ty.s, 0), S.h - 1), sy1 = min(max(ty.s + 1, 0), S.h - 1);
+    // x taps of the 4 outputs: xtab rows are padded to a multiple of 4 entries, so two 16-byte loads
+    const uint4* tp = reinterpret_cast<const uint4*>(xtab + L.xtabOff + x);
+    const uint4 t01 = __ldg(tp), t23 = __ldg(tp + 1);
+    const int sx[4] = {(int)t01.x, (int)t01.z, (int)t23.x, (int)t23.z};
+    const u32 cf[4] = {t01.y, t01.w, t23.y, t23.w};
+    const int base = sx[0] & ~3;
+    const u32* r0p = reinterpret_cast<const u32*>(src + (size_t)sy0 * S.pitch + base);
+    const u32* r1p = reinterpret_cast<const u32*>(src + (size_t)sy1 * S.pitch + base);
+    const u32 a0 = r0p[0], a1 = r0p[1], a2 = r0p[2];
+    const u32 b0 = r1p[0], b1 = r1p[1], b2 = r1p[2];
+    u32 out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = sx[k] - base, sh = (i & 3) * 8;
+        const bool w0 = i < 4, w1 = i < 8;
+        const u32 pa = __funnelshift_r(w0 ? a0 : (w1 ? a1 : a2), w0 ? a1 : a2, sh);
+        const u32 pb = __funnelshift_r(w0 ? b0 : (w1 ? b1 : b2), w0 ? b1 : b2, sh);
+        const int r0 = (int)__dp2a_lo(cf[k], pa, 0u);
+        const int r1 = (int)__dp2a_lo(cf[k], pb, 0u);
+        int v = (((ty.c0 * (r0 >> 4)) >> 16) + ((ty.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        out |= (u32)v << (8 * k);
+    }
+    *reinterpret_cast<u32*>(frame + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
+}
+
+// REFLECT_101 border of every level (copyMakeBorder, ORBextractor.cc:1125-1132): `bw` columns left/right and `bh` rows
+// above/below.  The hot path only needs the 3 pixels the 7x7 blur reads (bw = 4, bh = 3); the full 19-pixel border of the
+// API-visible pyramid is produced on demand by orbx_get_pyramid_level(bordered = 1).
+__global__ void __launch_bounds__(256) k_border(const __grid_constant__ Plan P, u8* __restrict__ pyr, int bw, int bh, int level0,
+                                                int frame0) {
+    const int level = level0 + blockIdx.y, f = frame0 + blockIdx.z;
+    const LevelPlan& L = P.lv[level];
+    const int side = L.h * 2 * bw, rowlen = L.w + 2 * bw, total = side + 2 * bh * rowlen;
+    u8* img = pyr + (size_t)f * P.frameBytes + L.off + (size_t)ORBX_OY * L.pitch + ORBX_OX;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        int x, y;
+        if (i < side) {
+            y = i / (2 * bw);
+            const int j = i - y * 2 * bw;
+            x = j < bw ? j - bw : L.w + (j - bw);
+        } else {
+            const int i2 = i - side, r = i2 / rowlen;
+            x = i2 - r * rowlen - bw;
+            y = r < bh ? r - bh : L.h + (r - bh);
+        }
+        img[(ptrdiff_t)y * L.pitch + x] = img[(ptrdiff_t)dev_reflect101(y, L.h) * L.pitch + dev_reflect101(x, L.w)];
+    }
 }
 
 // =====================================================================================================
@@ -156,6 +222,11 @@ __device__ __forceinline__ void fast_score_pair(const u32 (&r)[16], u32 v, int& 
     s1 = max((int)(A >> 16) - 256, 256 - (int)(Bm >> 16)) - 1;
 }
 
+// TPP / SPP > 0: compile-time tile / score pitches (all 17 ring loads become one base register + immediates);
+// 0: runtime pitches from the plan (cells wider than 42 px, i.e. pyramid levels narrower than ~100 px).
+#define ORBX_FAST_TPP 28
+#define ORBX_FAST_SPP 48
+template <int TPP, int SPP>
 __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                              uint2* __restrict__ cand, int* __restrict__ candCount,
                                                              int* __restrict__ status) {
@@ -174,7 +245,7 @@ __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constan
     const int tw = maxX - iniX, th = maxY - iniY, dw = tw - 6, dh = th - 6;
     if (dw <= 0 || dh <= 0) return;                                   // cv::FAST on a ROI < 7 px finds nothing
 
-    const int TPp = P.tilePitch, SP = P.scorePitch;                   // tile pitch in pixel PAIRS (u32), score pitch in bytes
+    const int TPp = TPP > 0 ? TPP : P.tilePitch, SP = SPP > 0 ? SPP : P.scorePitch;   // tile pitch in pixel PAIRS (u32), score pitch in bytes
     u32* tA = reinterpret_cast<u32*>(smem);                           // pair j = pixels (2j, 2j+1)
     u32* tB = tA + (size_t)P.tileRows * TPp;                          // pair j = pixels (2j+1, 2j+2)
     u8* score = reinterpret_cast<u8*>(tB + (size_t)P.tileRows * TPp);
@@ -209,11 +280,13 @@ __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constan
         const u32 inv = 0xFFFFFFFFu / (u32)npr + 1;
         const int X0 = lead + 3;                                      // tile x of domain pixel 0
         // ring offsets (dx,dy) in cornerScore order; copy selected by the parity of the first pixel's tile x
-        const u32* cE = (X0 & 1) ? tB : tA;                           // pairs starting at X0 + even dx
-        const u32* cO = (X0 & 1) ? tA : tB;                           // pairs starting at X0 + odd dx
-#define PAIR(dx, dy) (((dx) & 1) ? cO : cE)[(row + 3 + (dy)) * TPp + ((X0 + (dx)) >> 1) + p]
+        const u32* cE = ((X0 & 1) ? tB : tA) + (X0 >> 1);             // pairs starting at X0 + even dx
+        const u32* cO = ((X0 & 1) ? tA : tB) + ((X0 + 1) >> 1);       // pairs starting at X0 + odd dx
+#define PAIR(dx, dy) (((dx) & 1) ? pO[(3 + (dy)) * TPp + (((dx) - 1) / 2)] : pE[(3 + (dy)) * TPp + ((dx) / 2)])
         for (int task = tid; task < npr * dh; task += ORBX_FAST_THREADS) {
             const int row = npr == 1 ? task : (int)__umulhi((u32)task, inv), p = task - row * npr;   // (inv overflows for npr == 1)
+            const u32* pE = cE + row * TPp + p;
+            const u32* pO = cO + row * TPp + p;
             u32 r[16];
             r[0] = PAIR(0, 3); r[1] = PAIR(1, 3); r[2] = PAIR(2, 2); r[3] = PAIR(3, 1);
             r[4] = PAIR(3, 0); r[5] = PAIR(3, -1); r[6] = PAIR(2, -2); r[7] = PAIR(1, -3);
@@ -547,52 +620,51 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
 // =====================================================================================================
 #define BL_TW 128
 #define BL_TH 32
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, int level, const u8* __restrict__ pyr,
-                                              u8* __restrict__ blur) {
-    __shared__ u32 s_src[BL_TH + 6][BL_TW / 4 + 2];
-    __shared__ __align__(8) u16 s_h[BL_TH + 6][BL_TW];
+// All levels in one launch: blockIdx.x walks the per-level tile lists (Plan::blurTileBase).  Horizontal pass: the 7 taps of
+// an output are two IDP4A over byte windows cut from three aligned words with funnel shifts (no byte unpacking);
+// results stay exact (<= 65280) and are kept as u32 x 4 in shared memory; vertical pass: 7 x LDS.128, symmetric taps folded.
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
+    __shared__ uint4 s_h[BL_TH + 6][BL_TW / 4];
+    int level = 0;
+    while (level + 1 < P.nlevels && (int)blockIdx.x >= P.blurTileBase[level + 1]) level++;
     const LevelPlan& L = P.lv[level];
-    const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH, f = blockIdx.z;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int t = blockIdx.x - P.blurTileBase[level];
+    const int tilesX = (L.w + BL_TW - 1) / BL_TW;
+    const int ty = t / tilesX, tx = t - ty * tilesX;
+    const int x0 = tx * BL_TW, y0 = ty * BL_TH, f = blockIdx.y;
+    const int tid = threadIdx.x;
     const u8* src = pyr + (size_t)f * P.frameBytes + L.off;
     const int wordsPerRow = L.pitch >> 2;
-    // stage rows y0-3 .. y0+TH+2, words covering x0-4 .. x0+TW+3
-    for (int i = tid; i < (BL_TH + 6) * (BL_TW / 4 + 2); i += 256) {
-        const int r = i / (BL_TW / 4 + 2), wx = i - r * (BL_TW / 4 + 2);
-        const int by = y0 - 3 + r + ORBX_OY, bwx = ((x0 + ORBX_OX) >> 2) - 1 + wx;
-        u32 v = 0;
-        if (by < L.brows && bwx < wordsPerRow) v = __ldg(reinterpret_cast<const u32*>(src + (size_t)by * L.pitch) + bwx);
-        s_src[r][wx] = v;
-    }
-    __syncthreads();
-    for (int i = tid; i < (BL_TH + 6) * (BL_TW / 4); i += 256) {
-        const int r = i / (BL_TW / 4), wx = i - r * (BL_TW / 4);
-        const u32 a = s_src[r][wx], b = s_src[r][wx + 1], c = s_src[r][wx + 2];
-        // bytes: a = x-4..x-1, b = x..x+3, c = x+4..x+7   (x = x0 + 4*wx)
-        int p[10];
-        p[0] = (a >> 8) & 0xFF; p[1] = (a >> 16) & 0xFF; p[2] = a >> 24;
-        p[3] = b & 0xFF; p[4] = (b >> 8) & 0xFF; p[5] = (b >> 16) & 0xFF; p[6] = b >> 24;
-        p[7] = c & 0xFF; p[8] = (c >> 8) & 0xFF; p[9] = (c >> 16) & 0xFF;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int h = 18 * (p[k] + p[k + 6]) + 34 * (p[k + 1] + p[k + 5]) + 48 * (p[k + 2] + p[k + 4]) + 56 * p[k + 3];
-            s_h[r][4 * wx + k] = (u16)h;
+    const u32 K1 = 18u | (34u << 8) | (48u << 16) | (56u << 24);      // taps for x-3, x-2, x-1, x
+    const u32 K2 = 48u | (34u << 8) | (18u << 16);                    // taps for x+1, x+2, x+3
+    const int rowsNeeded = min(BL_TH, L.h - y0) + 6;
+    for (int i = tid; i < rowsNeeded * (BL_TW / 4); i += 256) {
+        const int r = i >> 5, wx = i & 31;
+        const int by = y0 - 3 + r + ORBX_OY, bwx = ((x0 + ORBX_OX) >> 2) + wx;
+        uint4 h = make_uint4(0, 0, 0, 0);
+        if (bwx + 1 < wordsPerRow) {
+            const u32* rp = reinterpret_cast<const u32*>(src + (size_t)by * L.pitch) + bwx;
+            const u32 a = __ldg(rp - 1), b = __ldg(rp), c = __ldg(rp + 1);
+            h.x = __dp4a(__funnelshift_r(a, b, 8), K1, __dp4a(__funnelshift_r(b, c, 8), K2, 0u));
+            h.y = __dp4a(__funnelshift_r(a, b, 16), K1, __dp4a(__funnelshift_r(b, c, 16), K2, 0u));
+            h.z = __dp4a(__funnelshift_r(a, b, 24), K1, __dp4a(__funnelshift_r(b, c, 24), K2, 0u));
+            h.w = __dp4a(b, K1, __dp4a(c, K2, 0u));
         }
+        s_h[r][wx] = h;
     }
     __syncthreads();
     u8* dst = blur + (size_t)f * P.frameBytes + L.off;
     for (int i = tid; i < BL_TH * (BL_TW / 4); i += 256) {
-        const int r = i / (BL_TW / 4), wx = i - r * (BL_TW / 4);
+        const int r = i >> 5, wx = i & 31;
         const int x = x0 + 4 * wx, y = y0 + r;
         if (x >= L.w || y >= L.h) continue;
-        u32 o = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = 4 * wx + k;
-            const int v = 18 * ((int)s_h[r][c] + s_h[r + 6][c]) + 34 * ((int)s_h[r + 1][c] + s_h[r + 5][c]) +
-                          48 * ((int)s_h[r + 2][c] + s_h[r + 4][c]) + 56 * (int)s_h[r + 3][c];
-            o |= (u32)((v + 32768) >> 16) << (8 * k);
-        }
+        const uint4 h0 = s_h[r][wx], h1 = s_h[r + 1][wx], h2 = s_h[r + 2][wx], h3 = s_h[r + 3][wx];
+        const uint4 h4 = s_h[r + 4][wx], h5 = s_h[r + 5][wx], h6 = s_h[r + 6][wx];
+        const u32 v0 = 18u * (h0.x + h6.x) + 34u * (h1.x + h5.x) + 48u * (h2.x + h4.x) + 56u * h3.x + 32768u;
+        const u32 v1 = 18u * (h0.y + h6.y) + 34u * (h1.y + h5.y) + 48u * (h2.y + h4.y) + 56u * h3.y + 32768u;
+        const u32 v2 = 18u * (h0.z + h6.z) + 34u * (h1.z + h5.z) + 48u * (h2.z + h4.z) + 56u * h3.z + 32768u;
+        const u32 v3 = 18u * (h0.w + h6.w) + 34u * (h1.w + h5.w) + 48u * (h2.w + h4.w) + 56u * h3.w + 32768u;
+        const u32 o = (v0 >> 16) | ((v1 >> 16) << 8) | ((v2 >> 16) << 16) | ((v3 >> 16) << 24);
         *reinterpret_cast<u32*>(dst + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = o;
     }
 }
@@ -627,16 +699,19 @@ __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(256) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
-                                                  const u8* __restrict__ blur, const uint2* __restrict__ sel,
-                                                  const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
-                                                  u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
-                                                  int* __restrict__ status) {
+#define DESC_WARPS 8
+#define DESC_PW 11            // aligned words per staged patch row: covers kx-18 .. kx+18 for any alignment
+__global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
+                                                              const u8* __restrict__ blur, const uint2* __restrict__ sel,
+                                                              const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
+                                                              u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
+                                                              int* __restrict__ status) {
     __shared__ signed char s_pat[1024];
-    for (int i = threadIdx.x; i < 256; i += 256) reinterpret_cast<int*>(s_pat)[i] = reinterpret_cast<const int*>(c_pattern)[i];
+    __shared__ u32 s_patch[DESC_WARPS][37][DESC_PW];
+    for (int i = threadIdx.x; i < 256; i += 32 * DESC_WARPS) reinterpret_cast<int*>(s_pat)[i] = reinterpret_cast<const int*>(c_pattern)[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31, f = blockIdx.y;
-    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y;
+    const int slot = blockIdx.x * DESC_WARPS + warp;
     if (slot >= P.selTotal) return;
     int l = 0;
     while (l + 1 < P.nlevels && slot >= P.lv[l + 1].selOff) l++;
@@ -654,30 +729,48 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ Plan P
     if (pos >= cap) return;
     const uint2 k = sel[(size_t)f * P.selTotal + slot];
     const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
-    const size_t cofs = (size_t)f * P.frameBytes + L.off + (size_t)(ky + ORBX_OY) * L.pitch + kx + ORBX_OX;
+    const int pitch = L.pitch;
+    const size_t lofs = (size_t)f * P.frameBytes + L.off;
 
-    // ---- IC_Angle (ORBextractor.cc:76-103): lane v+15 sums row v of the disc
+    // ---- stage the 37x37 blurred patch (rows ky-18..ky+18) as aligned words: 2 rows per load instruction
+    const int pxs = kx - 18 + ORBX_OX, wx0 = pxs >> 2, shift = pxs & 3;
+    {
+        const int half = lane >> 4, wi = lane & 15;
+        const u32* bsrc = reinterpret_cast<const u32*>(blur + lofs + (size_t)(ky - 18 + ORBX_OY) * pitch) + wx0;
+        if (wi < DESC_PW)
+            for (int r = half; r < 37; r += 2) s_patch[warp][r][wi] = __ldg(bsrc + (size_t)r * (pitch >> 2) + wi);
+    }
+
+    // ---- IC_Angle (ORBextractor.cc:76-103): lane = column u (-15..15), loop over the rows of the disc (coalesced)
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        const int v = lane - 15;
-        const int d = P.umax[v < 0 ? -v : v];
-        const u8* row = pyr + cofs + (ptrdiff_t)v * L.pitch;
-        int rs = 0;
-        for (int u = -d; u <= d; u++) { const int I = row[u]; m10 += u * I; rs += I; }
-        m01 = v * rs;
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        const u8* cen = pyr + lofs + (size_t)(ky + ORBX_OY) * pitch + kx + ORBX_OX + u;
+        int colsum = 0;
+#pragma unroll
+        for (int v = -15; v <= 15; v++) {
+            const int av = v < 0 ? -v : v;
+            if (au <= P.umax[av]) {
+                const int I = cen[(ptrdiff_t)v * pitch];
+                colsum += I;
+                m01 += v * I;
+            }
+        }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
     const float angle = dev_fast_atan2((float)m01, (float)m10);
 
-    // ---- computeOrbDescriptor (ORBextractor.cc:107-146)
+    // ---- computeOrbDescriptor (ORBextractor.cc:107-146); cos on lane 0, sin on lane 1 (double, then rounded to float)
     const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
     const float ang = __fmul_rn(angle, factorPI);
-    float a, b;
-    if (lane == 0) { a = (float)cos((double)ang); b = (float)sin((double)ang); }
-    a = __shfl_sync(0xffffffffu, a, 0);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    const u8* center = blur + cofs;
+    float cs = 0.f;
+    if (lane == 0) cs = (float)cos((double)ang);
+    else if (lane == 1) cs = (float)sin((double)ang);
+    const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
+    __syncwarp();
+    const u8* center = reinterpret_cast<const u8*>(&s_patch[warp][18][0]) + 18 + shift;
     const signed char* pat = s_pat + lane * 32;
     u32 val = 0;
 #pragma unroll
@@ -687,7 +780,7 @@ __global__ void __launch_bounds__(256) k_describe(const __grid_constant__ Plan P
         const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = center[(ptrdiff_t)r0 * L.pitch + q0], t1 = center[(ptrdiff_t)r1 * L.pitch + q1];
+        const int t0 = center[r0 * (DESC_PW * 4) + q0], t1 = center[r1 * (DESC_PW * 4) + q1];
         val |= (u32)(t0 < t1) << j;
     }
     descOut[((size_t)f * cap + pos) * 32 + lane] = (u8)val;
@@ -716,14 +809,22 @@ struct orbx_extractor {
     Plan plan;
     cudaStream_t stream = nullptr;
     // device workspace
-    u8 *d_pyr = nullptr, *d_blur = nullptr, *d_in = nullptr, *d_mask = nullptr, *d_desc = nullptr;
+    u8 *d_pyr = nullptr, *d_blur = nullptr;
+    // host-buffer path: two staging slots so that H2D(chunk i+1), compute(chunk i) and D2H(chunk i-1) overlap
+    u8 *d_in[2] = {nullptr, nullptr}, *d_mask[2] = {nullptr, nullptr}, *d_desc[2] = {nullptr, nullptr};
+    orbx_keypoint* d_kp[2] = {nullptr, nullptr};
+    int* d_n[2] = {nullptr, nullptr};
+    int* h_n = nullptr;                    // pinned staging for the per-frame counts
+    size_t h_n_cap = 0;
+    cudaStream_t sH2D = nullptr, sD2H = nullptr;
+    cudaEvent_t evH2D[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evD2H[2] = {nullptr, nullptr};
     uint2 *d_cand = nullptr, *d_sel = nullptr;
     u32* d_nodeOf = nullptr;
-    int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr, *d_n = nullptr;
-    orbx_keypoint* d_kp = nullptr;
+    int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr;
     ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
     int capInternal = 0;
     size_t fastSmem = 0, octSmem = 0;
+    bool fastConst = false;
     long long launches = 0;
     int lastFrames = 0;
     std::mutex mu;
@@ -819,15 +920,28 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         if (l > 0) {
             build_resize_taps(P.lv[l - 1].w, L.w, true, xt);
             build_resize_taps(P.lv[l - 1].h, L.h, false, yt);
+            // fast form needs: each group of 4 outputs reads source bytes within [s0 & ~3, (s0 & ~3) + 11]
+            L.fastResize = 1;
+            for (int x = 0; x < L.w; x += 4) {
+                const int s0 = xt[L.xtabOff + x].s & ~3;
+                for (int k = 0; k < 4 && x + k < L.w; k++)
+                    if (xt[L.xtabOff + x + k].s + 1 - s0 > 11 || xt[L.xtabOff + x + k].s < s0) L.fastResize = 0;
+            }
+            while (xt.size() % 4) xt.push_back(xt.back());           // pad so a thread can always load 4 taps
         }
     }
     ORB_REQUIRE(maxNodes <= 60000, ORB_ERR_ARG, "nfeatures too large for the octree kernel");
+    P.blurTileBase[0] = 0;
+    for (int l = 0; l < nl; l++)
+        P.blurTileBase[l + 1] = P.blurTileBase[l] + orb_div_up(P.lv[l].w, BL_TW) * orb_div_up(P.lv[l].h, BL_TH);
     P.totalCells = cellBase; P.candTotal = candOff; P.selTotal = selOff; P.maxNodes = maxNodes;
     P.sortN = 2; while (P.sortN < maxNodes) P.sortN <<= 1;
     P.frameBytes = off;
     // FAST tile: pixel pairs (u32) per row = 2 * words, words = ceil((3 + cellW + 6 + 1) / 4); two copies; + score map + corner list
     P.tilePitch = 2 * (int)((3 + maxCW + 6 + 1 + 3) / 4) + 2; P.tileRows = maxCH + 6;
     P.scorePitch = (int)orb_align_up(maxCW + 3, 4); P.scoreRows = maxCH + 2;
+    ex->fastConst = P.tilePitch <= ORBX_FAST_TPP && P.scorePitch <= ORBX_FAST_SPP;
+    if (ex->fastConst) { P.tilePitch = ORBX_FAST_TPP; P.scorePitch = ORBX_FAST_SPP; }
     ex->fastSmem = (size_t)P.tilePitch * P.tileRows * 4 * 2 + (size_t)P.scorePitch * P.scoreRows + (size_t)(maxCW + 1) * maxCH * 2 + 16;
     ex->octSmem = (size_t)maxNodes * (16 * 2 + 4 * 2 + 16 + 4 * 3) + (size_t)P.sortN * 8 + 64;
     ORB_REQUIRE(ex->octSmem <= 220 * 1024, ORB_ERR_ARG, "nfeatures too large for the octree kernel's shared memory");
@@ -854,7 +968,8 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         static size_t maxFast = 0, maxOct = 0;
         std::lock_guard<std::mutex> lk(amu);
         if (ex->fastSmem > maxFast) {
-            ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
             maxFast = ex->fastSmem;
         }
         if (ex->octSmem > maxOct) {
@@ -900,9 +1015,18 @@ extern "C" int orbx_create(orbx_extractor** out, int nfeatures, float scale_fact
 extern "C" void orbx_destroy(orbx_extractor* ex) {
     if (!ex) return;
     cudaSetDevice(ex->device);
-    cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_in); cudaFree(ex->d_mask); cudaFree(ex->d_desc);
+    cudaFree(ex->d_pyr); cudaFree(ex->d_blur);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ex->d_in[i]); cudaFree(ex->d_mask[i]); cudaFree(ex->d_desc[i]); cudaFree(ex->d_kp[i]); cudaFree(ex->d_n[i]);
+        if (ex->evH2D[i]) cudaEventDestroy(ex->evH2D[i]);
+        if (ex->evComp[i]) cudaEventDestroy(ex->evComp[i]);
+        if (ex->evD2H[i]) cudaEventDestroy(ex->evD2H[i]);
+    }
+    if (ex->h_n) cudaFreeHost(ex->h_n);
+    if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
+    if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
     cudaFree(ex->d_cand); cudaFree(ex->d_sel); cudaFree(ex->d_nodeOf); cudaFree(ex->d_candCount); cudaFree(ex->d_selCount);
-    cudaFree(ex->d_status); cudaFree(ex->d_n); cudaFree(ex->d_kp); cudaFree(ex->d_xtab); cudaFree(ex->d_ytab);
+    cudaFree(ex->d_status); cudaFree(ex->d_xtab); cudaFree(ex->d_ytab);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
 }
@@ -935,21 +1059,30 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     if (stages & ORBX_STAGE_PYRAMID) {
         {
             const LevelPlan& L = P.lv[0];
-            dim3 g(orb_div_up(L.pitch, 256), orb_div_up(L.brows, 4), nf), b(64, 4);
+            dim3 g(orb_div_up(L.w, 256), orb_div_up(L.h, 4), nf), b(64, 4);
             k_level0<<<g, b, 0, st>>>(P, d_images, d_masks, ex->d_pyr);
             ex->launches++;
         }
         for (int l = 1; l < nl; l++) {
             const LevelPlan& L = P.lv[l];
-            dim3 g(orb_div_up(L.pitch, 256), orb_div_up(L.brows, 4), nf), b(64, 4);
-            k_resize<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
+            dim3 g(orb_div_up(L.w, 256), orb_div_up(L.h, 4), nf), b(64, 4);
+            if (L.fastResize) k_resize<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
+            else k_resize_generic<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
+            ex->launches++;
+        }
+        {
+            dim3 g(8, nl, nf);
+            k_border<<<g, 256, 0, st>>>(P, ex->d_pyr, 4, 3, 0, 0);
             ex->launches++;
         }
     }
     if (stages & ORBX_STAGE_FAST) {
         ORB_CUDA_TRY(cudaMemsetAsync(ex->d_candCount, 0, (size_t)nf * nl * sizeof(int), st));
         dim3 g(P.totalCells, nf);
-        k_fast<<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
+        if (ex->fastConst)
+            k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
+        else
+            k_fast<0, 0><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
         ex->launches++;
     }
     if (stages & ORBX_STAGE_OCTREE) {
@@ -959,16 +1092,13 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         ex->launches++;
     }
     if (stages & ORBX_STAGE_BLUR) {
-        for (int l = 0; l < nl; l++) {
-            const LevelPlan& L = P.lv[l];
-            dim3 g(orb_div_up(L.w, BL_TW), orb_div_up(L.h, BL_TH), nf), b(32, 8);
-            k_blur<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_blur);
-            ex->launches++;
-        }
+        dim3 g(P.blurTileBase[nl], nf);
+        k_blur<<<g, 256, 0, st>>>(P, ex->d_pyr, ex->d_blur);
+        ex->launches++;
     }
     if (stages & ORBX_STAGE_DESCRIBE) {
-        dim3 g(orb_div_up(P.selTotal, 8), nf);
-        k_describe<<<g, 256, 0, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc, d_n, cap, ex->d_status);
+        dim3 g(orb_div_up(P.selTotal, DESC_WARPS), nf);
+        k_describe<<<g, 32 * DESC_WARPS, 0, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc, d_n, cap, ex->d_status);
         ex->launches++;
     }
     ORB_CUDA_TRY(cudaGetLastError());
@@ -1017,55 +1147,79 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
     ORB_REQUIRE(width == ex->plan.width && height == ex->plan.height, ORB_ERR_ARG,
                 "image is %dx%d but the handle was planned for %dx%d", width, height, ex->plan.width, ex->plan.height);
     ORB_REQUIRE(stride >= width && (!masks || mask_stride >= width), ORB_ERR_ARG, "stride < width");
-    const int B = ex->maxBatch;
+    if (n_frames == 0) return ORB_OK;
+    const int B = ex->maxBatch, icap = ex->capInternal;
     const size_t fpx = (size_t)width * height;
-    {
-        std::lock_guard<std::mutex> lk(ex->mu);
-        ORB_CUDA_TRY(cudaSetDevice(ex->device));
-        if (!ex->d_in) ORB_CUDA_TRY(cudaMalloc(&ex->d_in, (size_t)B * fpx));
-        if (masks && !ex->d_mask) ORB_CUDA_TRY(cudaMalloc(&ex->d_mask, (size_t)B * fpx));
-        if (!ex->d_kp) {
-            ORB_CUDA_TRY(cudaMalloc(&ex->d_kp, (size_t)B * ex->capInternal * sizeof(orbx_keypoint)));
-            ORB_CUDA_TRY(cudaMalloc(&ex->d_desc, (size_t)B * ex->capInternal * 32));
-            ORB_CUDA_TRY(cudaMalloc(&ex->d_n, (size_t)B * sizeof(int)));
+    std::lock_guard<std::mutex> lk(ex->mu);
+    ORB_CUDA_TRY(cudaSetDevice(ex->device));
+    const int nslots = n_frames > B ? 2 : 1;
+    for (int i = 0; i < nslots; i++) {
+        if (!ex->d_in[i]) {
+            ORB_CUDA_TRY(cudaMalloc(&ex->d_in[i], (size_t)B * fpx));
+            ORB_CUDA_TRY(cudaMalloc(&ex->d_kp[i], (size_t)B * icap * sizeof(orbx_keypoint)));
+            ORB_CUDA_TRY(cudaMalloc(&ex->d_desc[i], (size_t)B * icap * 32));
+            ORB_CUDA_TRY(cudaMalloc(&ex->d_n[i], (size_t)B * sizeof(int)));
+            ORB_CUDA_TRY(cudaEventCreateWithFlags(&ex->evH2D[i], cudaEventDisableTiming));
+            ORB_CUDA_TRY(cudaEventCreateWithFlags(&ex->evComp[i], cudaEventDisableTiming));
+            ORB_CUDA_TRY(cudaEventCreateWithFlags(&ex->evD2H[i], cudaEventDisableTiming));
         }
+        if (masks && !ex->d_mask[i]) ORB_CUDA_TRY(cudaMalloc(&ex->d_mask[i], (size_t)B * fpx));
     }
-    const int icap = ex->capInternal;
-    std::vector<int> ncount(B);
-    for (int f0 = 0; f0 < n_frames; f0 += B) {
-        const int nf = std::min(B, n_frames - f0);
-        cudaStream_t st = ex->stream;
+    if (!ex->sH2D) {
+        ORB_CUDA_TRY(cudaStreamCreateWithFlags(&ex->sH2D, cudaStreamNonBlocking));
+        ORB_CUDA_TRY(cudaStreamCreateWithFlags(&ex->sD2H, cudaStreamNonBlocking));
+    }
+    if (ex->h_n_cap < (size_t)n_frames) {
+        if (ex->h_n) ORB_CUDA_TRY(cudaFreeHost(ex->h_n));
+        ex->h_n = nullptr; ex->h_n_cap = 0;
+        ORB_CUDA_TRY(cudaMallocHost(&ex->h_n, (size_t)n_frames * sizeof(int)));
+        ex->h_n_cap = n_frames;
+    }
+    const int ccap = std::min(cap, icap);             // keypoints copied back per frame (the rest of a row cannot be used)
+    int chunk = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += B, chunk++) {
+        const int nf = std::min(B, n_frames - f0), sl = chunk & 1;
+        // ---- H2D (slot's input buffer is free once the compute of chunk-2 has finished)
+        if (chunk >= 2) ORB_CUDA_TRY(cudaStreamWaitEvent(ex->sH2D, ex->evComp[sl], 0));
         if ((size_t)stride == (size_t)width && frame_stride == fpx) {
-            ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in, images + (size_t)f0 * frame_stride, (size_t)nf * fpx, cudaMemcpyHostToDevice, st));
+            ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[sl], images + (size_t)f0 * frame_stride, (size_t)nf * fpx, cudaMemcpyHostToDevice, ex->sH2D));
         } else {
             for (int f = 0; f < nf; f++)
-                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in + f * fpx, width, images + (size_t)(f0 + f) * frame_stride, stride, width,
-                                               height, cudaMemcpyHostToDevice, st));
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in[sl] + f * fpx, width, images + (size_t)(f0 + f) * frame_stride, stride, width,
+                                               height, cudaMemcpyHostToDevice, ex->sH2D));
         }
         if (masks)
             for (int f = 0; f < nf; f++)
-                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_mask + f * fpx, width, masks + (size_t)(f0 + f) * mask_frame_stride, mask_stride,
-                                               width, height, cudaMemcpyHostToDevice, st));
-        {
-            std::lock_guard<std::mutex> lk(ex->mu);
-            int rc = run_pass(ex, ex->d_in, masks ? ex->d_mask : nullptr, nf, ex->d_kp, ex->d_desc, icap, ex->d_n, ORBX_STAGE_ALL, st);
-            if (rc != ORB_OK) return rc;
-        }
-        ORB_CUDA_TRY(cudaMemcpyAsync(ncount.data(), ex->d_n, nf * sizeof(int), cudaMemcpyDeviceToHost, st));
-        ORB_CUDA_TRY(cudaStreamSynchronize(st));
-        int rc = orbx_check_status(ex);
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_mask[sl] + f * fpx, width, masks + (size_t)(f0 + f) * mask_frame_stride, mask_stride,
+                                               width, height, cudaMemcpyHostToDevice, ex->sH2D));
+        ORB_CUDA_TRY(cudaEventRecord(ex->evH2D[sl], ex->sH2D));
+        // ---- compute (slot's output buffers are free once the D2H of chunk-2 has finished)
+        ORB_CUDA_TRY(cudaStreamWaitEvent(ex->stream, ex->evH2D[sl], 0));
+        if (chunk >= 2) ORB_CUDA_TRY(cudaStreamWaitEvent(ex->stream, ex->evD2H[sl], 0));
+        int rc = run_pass(ex, ex->d_in[sl], masks ? ex->d_mask[sl] : nullptr, nf, ex->d_kp[sl], ex->d_desc[sl], icap, ex->d_n[sl],
+                          ORBX_STAGE_ALL, ex->stream);
         if (rc != ORB_OK) return rc;
-        for (int f = 0; f < nf; f++) {
-            const int n = ncount[f];
-            n_out[f0 + f] = n;
-            ORB_REQUIRE(n <= cap, ORB_ERR_CAPACITY, "frame %d has %d keypoints but cap is %d", f0 + f, n, cap);
-            if (n == 0) continue;
-            ORB_CUDA_TRY(cudaMemcpyAsync(kp_out + (size_t)(f0 + f) * cap, ex->d_kp + (size_t)f * icap, (size_t)n * sizeof(orbx_keypoint),
-                                         cudaMemcpyDeviceToHost, st));
-            ORB_CUDA_TRY(cudaMemcpyAsync(desc_out + (size_t)(f0 + f) * cap * 32, ex->d_desc + (size_t)f * icap * 32, (size_t)n * 32,
-                                         cudaMemcpyDeviceToHost, st));
-        }
-        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+        ORB_CUDA_TRY(cudaEventRecord(ex->evComp[sl], ex->stream));
+        // ---- D2H: counts, then the padded keypoint / descriptor rows in one 2-D copy each
+        ORB_CUDA_TRY(cudaStreamWaitEvent(ex->sD2H, ex->evComp[sl], 0));
+        ORB_CUDA_TRY(cudaMemcpyAsync(ex->h_n + f0, ex->d_n[sl], nf * sizeof(int), cudaMemcpyDeviceToHost, ex->sD2H));
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(kp_out + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), ex->d_kp[sl],
+                                       (size_t)icap * sizeof(orbx_keypoint), (size_t)ccap * sizeof(orbx_keypoint), nf,
+                                       cudaMemcpyDeviceToHost, ex->sD2H));
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(desc_out + (size_t)f0 * cap * 32, (size_t)cap * 32, ex->d_desc[sl], (size_t)icap * 32,
+                                       (size_t)ccap * 32, nf, cudaMemcpyDeviceToHost, ex->sD2H));
+        ORB_CUDA_TRY(cudaEventRecord(ex->evD2H[sl], ex->sD2H));
+    }
+    ORB_CUDA_TRY(cudaStreamSynchronize(ex->sD2H));
+    ORB_CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    int s = 0;
+    ORB_CUDA_TRY(cudaMemcpy(&s, ex->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (s) ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
+    ORB_REQUIRE(!(s & (ORB_DEV_CAND_OVERFLOW | ORB_DEV_NODE_OVERFLOW)), ORB_ERR_OVERFLOW,
+                "FAST candidate buffer overflow (ORBX_CAND_PER_CELL=%d caps it; unset it to size for the worst case)", ex->candPerCell);
+    for (int f = 0; f < n_frames; f++) {
+        n_out[f] = ex->h_n[f];
+        ORB_REQUIRE(ex->h_n[f] <= cap, ORB_ERR_CAPACITY, "frame %d has %d keypoints but cap is %d", f, ex->h_n[f], cap);
     }
     return ORB_OK;
 }
@@ -1083,6 +1237,14 @@ static int copy_level(orbx_extractor* ex, const u8* base, int frame, int level, 
     const u8* src = base + (size_t)frame * ex->plan.frameBytes + L.off;
     if (bordered) {
         ORB_REQUIRE(dst_stride >= L.w + 38, ORB_ERR_ARG, "dst_stride too small");
+        if (base == ex->d_pyr) {      // materialise the full 19-px REFLECT_101 border of this level (hot path keeps only 4x3)
+            std::lock_guard<std::mutex> lk(ex->mu);
+            dim3 g(8, 1, 1);
+            k_border<<<g, 256, 0, ex->stream>>>(ex->plan, ex->d_pyr, ORBX_EDGE, ORBX_EDGE, level, frame);
+            ex->launches++;
+            ORB_CUDA_TRY(cudaGetLastError());
+            ORB_CUDA_TRY(cudaStreamSynchronize(ex->stream));
+        }
         ORB_CUDA_TRY(cudaMemcpy2D(dst, dst_stride, src + ORBX_OX - ORBX_EDGE, L.pitch, L.w + 38, L.h + 38, cudaMemcpyDeviceToHost));
     } else {
         ORB_REQUIRE(dst_stride >= L.w, ORB_ERR_ARG, "dst_stride too small");
