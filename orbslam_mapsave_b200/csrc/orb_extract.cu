@@ -11,6 +11,7 @@
 // the same geometry in a second block.
 #include "orb_common.cuh"
 
+#include <cuda.h>            // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -56,6 +57,7 @@ struct Plan {
     int nlevels, iniTh, minTh;
     int totalCells, candTotal, selTotal, maxNodes, sortN;
     int tilePitch, tileRows, scorePitch, scoreRows;   // FAST shared-memory tile geometry (max over levels)
+    int fwBoxW, fwBoxH, fwTileBytes, fwScoreOff, fwPlistOff, fwBarOff, fwStride;   // k_fast_tma per-warp shared-memory layout
     int width, height;
     unsigned long long frameBytes;
     int umax[16];
@@ -222,99 +224,128 @@ __device__ __forceinline__ void fast_score_pair(const u32 (&r)[16], u32 v, int& 
     s1 = max((int)(A >> 16) - 256, 256 - (int)(Bm >> 16)) - 1;
 }
 
-// TPP / SPP > 0: compile-time tile / score pitches (all 17 ring loads become one base register + immediates);
-// 0: runtime pitches from the plan (cells wider than 42 px, i.e. pyramid levels narrower than ~100 px).
+// TPP / SPP > 0: compile-time tile / score pitches (ring loads become one base register + immediates);
+// 0: runtime pitches from the plan (cells wider than 40 px, i.e. pyramid levels narrower than ~100 px).
+//
+// Structure of one CTA (= one valid grid cell of one frame; the cell list is precomputed on the host):
+//   load    cell ROI -> shared tile of u16 pixels (aligned 32-bit global loads, PRMT expansion)
+//   phase A every pixel pair: the necessary condition "for each of 3 opposite ring pairs (k, k+8) at least one member is
+//           darker than v-t / brighter than v+t" on packed u16x2 values (13-18 % of pixels pass); passing pixels are
+//           compacted into a list (warp ballot + one shared atomic per warp iteration)
+//   phase B full 16-arc score (fast_score_pair) for the listed pixels only, two arbitrary pixels per thread
+//   NMS     3x3 strict maximum over the listed corners; iniThFAST -> minThFAST retry; emission
 #define ORBX_FAST_TPP 28
 #define ORBX_FAST_SPP 48
 template <int TPP, int SPP>
-__global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
-                                                             uint2* __restrict__ cand, int* __restrict__ candCount,
-                                                             int* __restrict__ status) {
+__global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constant__ Plan P, const uint4* __restrict__ cells,
+                                                             const u8* __restrict__ pyr, uint2* __restrict__ cand,
+                                                             int* __restrict__ candCount, int* __restrict__ status) {
     extern __shared__ __align__(16) u8 smem[];
     __shared__ u32 s_list[ORBX_FAST_LOCAL_CAP];
-    __shared__ int s_ncorner, s_nloc, s_nini, s_base, s_emit;
+    __shared__ int s_nlist, s_nloc, s_nini, s_base, s_emit;
 
-    int l = 0;
-    while (l + 1 < P.nlevels && (int)blockIdx.x >= P.lv[l + 1].cellBase) l++;
+    const uint4 ce = __ldg(cells + blockIdx.x);
+    const int iniX = (int)(ce.x & 0xFFFF), iniY = (int)(ce.x >> 16);
+    const int tw = (int)(ce.y & 0xFF), th = (int)((ce.y >> 8) & 0xFF), l = (int)((ce.y >> 16) & 0xFF), c = (int)ce.z;
+    const int dw = tw - 6, dh = th - 6, f = blockIdx.y;
     const LevelPlan& L = P.lv[l];
-    const int c = blockIdx.x - L.cellBase, f = blockIdx.y;
-    const int ci = c / L.nCols, cj = c - ci * L.nCols;
-    const int iniX = ORBX_MINB + cj * L.wCell, iniY = ORBX_MINB + ci * L.hCell;
-    if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6) return;          // ORBextractor.cc:793,802
-    const int maxX = min(iniX + L.wCell + 6, L.maxBX), maxY = min(iniY + L.hCell + 6, L.maxBY);
-    const int tw = maxX - iniX, th = maxY - iniY, dw = tw - 6, dh = th - 6;
-    if (dw <= 0 || dh <= 0) return;                                   // cv::FAST on a ROI < 7 px finds nothing
 
     const int TPp = TPP > 0 ? TPP : P.tilePitch, SP = SPP > 0 ? SPP : P.scorePitch;   // tile pitch in pixel PAIRS (u32), score pitch in bytes
-    u32* tA = reinterpret_cast<u32*>(smem);                           // pair j = pixels (2j, 2j+1)
-    u32* tB = tA + (size_t)P.tileRows * TPp;                          // pair j = pixels (2j+1, 2j+2)
-    u8* score = reinterpret_cast<u8*>(tB + (size_t)P.tileRows * TPp);
-    u16* clist = reinterpret_cast<u16*>(score + (size_t)P.scoreRows * SP);
-    const int tid = threadIdx.x;
-    if (tid == 0) { s_ncorner = 0; s_nloc = 0; s_nini = 0; s_emit = 0; }
+    u32* tile = reinterpret_cast<u32*>(smem);                         // pair j of a row = pixels (2j, 2j+1) as u16 each
+    u8* score = reinterpret_cast<u8*>(tile + (size_t)P.tileRows * TPp);
+    u16* plist = reinterpret_cast<u16*>(score + (size_t)P.scoreRows * SP);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) { s_nlist = 0; s_nloc = 0; s_nini = 0; s_emit = 0; }
 
-    // ---- stage the cell ROI: global-word aligned, expanded to u16 pixels, two copies
+    // ---- load: 16 lanes walk the words of a row, 8 rows per pass
     const int bx0 = iniX + ORBX_OX, gx0 = bx0 & ~3, lead = bx0 - gx0;
-    const int words = (lead + tw + 1 + 3) >> 2;
-    const u8* src = pyr + (size_t)f * P.frameBytes + L.off + (size_t)(iniY + ORBX_OY) * L.pitch + gx0;
     {
-        const u32 inv = 0xFFFFFFFFu / (u32)words + 1;
-        for (int t = tid; t < th * words; t += ORBX_FAST_THREADS) {
-            const int r = (int)__umulhi((u32)t, inv), wi = t - r * words;
-            const u32* gp = reinterpret_cast<const u32*>(src + (size_t)r * L.pitch) + wi;
-            const u32 w = __ldg(gp), wn = __ldg(gp + 1);
-            uint2 a, b;
-            a.x = __byte_perm(w, 0, 0x4140); a.y = __byte_perm(w, 0, 0x4342);
-            b.x = __byte_perm(w, 0, 0x4241); b.y = (w >> 24) | ((wn & 0xFF) << 16);
-            *reinterpret_cast<uint2*>(tA + r * TPp + 2 * wi) = a;
-            *reinterpret_cast<uint2*>(tB + r * TPp + 2 * wi) = b;
-        }
+        const int words = (lead + tw + 3) >> 2;
+        const int pitchW = L.pitch >> 2;
+        const u32* src = reinterpret_cast<const u32*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)(iniY + ORBX_OY) * L.pitch + gx0);
+        const int wx = tid & 15;
+        for (int r = tid >> 4; r < th; r += ORBX_FAST_THREADS / 16)
+            for (int wi = wx; wi < words; wi += 16) {
+                const u32 w = __ldg(src + r * pitchW + wi);
+                *reinterpret_cast<uint2*>(tile + r * TPp + 2 * wi) = make_uint2(__byte_perm(w, 0, 0x4140), __byte_perm(w, 0, 0x4342));
+            }
+        // score map: pixel (px, py) of the domain lives at byte (py + 1) * SP + px + 2; everything else stays 0
         for (int i = tid; i < (((dh + 2) * SP) >> 2); i += ORBX_FAST_THREADS) reinterpret_cast<u32*>(score)[i] = 0;
     }
     __syncthreads();
 
-    // ---- scores, two pixels per thread
+    const int t = P.minTh;
+    const int X0 = lead + 3;                                          // tile x of domain pixel 0
+    // ---- phase A
     {
-        const int t = P.minTh;
-        const int npr = (dw + 1) >> 1;
+        const int off = X0 & 1, npr = (off + dw + 1) >> 1;
         const u32 inv = 0xFFFFFFFFu / (u32)npr + 1;
-        const int X0 = lead + 3;                                      // tile x of domain pixel 0
-        // ring offsets (dx,dy) in cornerScore order; copy selected by the parity of the first pixel's tile x
-        const u32* cE = ((X0 & 1) ? tB : tA) + (X0 >> 1);             // pairs starting at X0 + even dx
-        const u32* cO = ((X0 & 1) ? tA : tB) + ((X0 + 1) >> 1);       // pairs starting at X0 + odd dx
-#define PAIR(dx, dy) (((dx) & 1) ? pO[(3 + (dy)) * TPp + (((dx) - 1) / 2)] : pE[(3 + (dy)) * TPp + ((dx) / 2)])
-        for (int task = tid; task < npr * dh; task += ORBX_FAST_THREADS) {
-            const int row = npr == 1 ? task : (int)__umulhi((u32)task, inv), p = task - row * npr;   // (inv overflows for npr == 1)
-            const u32* pE = cE + row * TPp + p;
-            const u32* pO = cO + row * TPp + p;
-            u32 r[16];
-            r[0] = PAIR(0, 3); r[1] = PAIR(1, 3); r[2] = PAIR(2, 2); r[3] = PAIR(3, 1);
-            r[4] = PAIR(3, 0); r[5] = PAIR(3, -1); r[6] = PAIR(2, -2); r[7] = PAIR(1, -3);
-            r[8] = PAIR(0, -3); r[9] = PAIR(-1, -3); r[10] = PAIR(-2, -2); r[11] = PAIR(-3, -1);
-            r[12] = PAIR(-3, 0); r[13] = PAIR(-3, 1); r[14] = PAIR(-2, 2); r[15] = PAIR(-1, 3);
-            const u32 v = PAIR(0, 0);
-            int s0, s1;
-            fast_score_pair(r, v, s0, s1);
-            const int px = 2 * p;
-            if (s0 >= t) {
-                score[(row + 1) * SP + px + 1] = (u8)s0;
-                clist[atomicAdd(&s_ncorner, 1)] = (u16)((row << 8) | px);
+        const u32* cE = tile + 3 * TPp + (X0 >> 1);
+        const int hiT = 256 + t, loT = 256 - t;
+        const int ntask = npr * dh;
+        for (int task0 = 0; task0 < ntask; task0 += ORBX_FAST_THREADS) {
+            const int task = task0 + tid;
+            bool pass0 = false, pass1 = false;
+            int row = 0, px0 = 0;
+            if (task < ntask) {
+                row = npr == 1 ? task : (int)__umulhi((u32)task, inv);
+                const int p = task - row * npr;
+                px0 = 2 * p - off;
+                const u32* pe = cE + row * TPp + p;
+                const u32 vb = pe[0] + 0x01000100u;
+                const u32 d0 = vb - pe[3 * TPp], d8 = vb - pe[-3 * TPp];
+                const u32 d2 = vb - pe[2 * TPp + 1], d10 = vb - pe[-2 * TPp - 1];
+                const u32 d6 = vb - pe[-2 * TPp + 1], d14 = vb - pe[2 * TPp - 1];
+                const u32 md = min3x2(__vmaxu2(d0, d8), __vmaxu2(d2, d10), __vmaxu2(d6, d14));    // dark arc possible iff > 256+t
+                const u32 mb = max3x2(__vminu2(d0, d8), __vminu2(d2, d10), __vminu2(d6, d14));    // bright arc possible iff < 256-t
+                pass0 = ((int)(md & 0xFFFF) > hiT || (int)(mb & 0xFFFF) < loT) && px0 >= 0;
+                pass1 = ((int)(md >> 16) > hiT || (int)(mb >> 16) < loT) && px0 + 1 < dw;
             }
-            if (s1 >= t && px + 1 < dw) {
-                score[(row + 1) * SP + px + 2] = (u8)s1;
-                clist[atomicAdd(&s_ncorner, 1)] = (u16)((row << 8) | (px + 1));
+            const u32 b0 = __ballot_sync(0xffffffffu, pass0), b1 = __ballot_sync(0xffffffffu, pass1);
+            const int n0 = __popc(b0), n = n0 + __popc(b1);
+            if (n) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nlist, n);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const u32 lt = (1u << lane) - 1;
+                if (pass0) plist[base + __popc(b0 & lt)] = (u16)((row << 8) | px0);
+                if (pass1) plist[base + n0 + __popc(b1 & lt)] = (u16)((row << 8) | (px0 + 1));
             }
         }
-#undef PAIR
     }
     __syncthreads();
 
-    // ---- 3x3 non-maximum suppression over the corners only (neighbours outside the cell's domain count as 0)
-    const int ncorner = s_ncorner;
-    for (int e = tid; e < ncorner; e += ORBX_FAST_THREADS) {
-        const int py = clist[e] >> 8, px = clist[e] & 0xFF;
-        const u8* sp = score + (py + 1) * SP + px + 1;
+    // ---- phase B: exact score of the listed pixels, two per thread (halves of the u16x2 lanes)
+    const int nlist = s_nlist;
+    {
+        const u16* t16 = reinterpret_cast<const u16*>(tile) + 3 * (2 * TPp) + X0;
+        const int RP = 2 * TPp;                                       // row pitch in u16 pixels
+#define RING(dx, dy) ((u32)q0[(dy) * RP + (dx)] | ((u32)q1[(dy) * RP + (dx)] << 16))
+        for (int i = tid; 2 * i < nlist; i += ORBX_FAST_THREADS) {
+            const int e0 = plist[2 * i], e1 = plist[min(2 * i + 1, nlist - 1)];
+            const u16* q0 = t16 + (e0 >> 8) * RP + (e0 & 0xFF);
+            const u16* q1 = t16 + (e1 >> 8) * RP + (e1 & 0xFF);
+            u32 r[16];
+            r[0] = RING(0, 3); r[1] = RING(1, 3); r[2] = RING(2, 2); r[3] = RING(3, 1);
+            r[4] = RING(3, 0); r[5] = RING(3, -1); r[6] = RING(2, -2); r[7] = RING(1, -3);
+            r[8] = RING(0, -3); r[9] = RING(-1, -3); r[10] = RING(-2, -2); r[11] = RING(-3, -1);
+            r[12] = RING(-3, 0); r[13] = RING(-3, 1); r[14] = RING(-2, 2); r[15] = RING(-1, 3);
+            const u32 v = RING(0, 0);
+            int s0, s1;
+            fast_score_pair(r, v, s0, s1);
+            if (s0 >= t) score[((e0 >> 8) + 1) * SP + (e0 & 0xFF) + 2] = (u8)s0;
+            if (s1 >= t) score[((e1 >> 8) + 1) * SP + (e1 & 0xFF) + 2] = (u8)s1;
+        }
+#undef RING
+    }
+    __syncthreads();
+
+    // ---- 3x3 non-maximum suppression over the listed pixels (neighbours outside the cell's domain count as 0)
+    for (int e = tid; e < nlist; e += ORBX_FAST_THREADS) {
+        const int py = plist[e] >> 8, px = plist[e] & 0xFF;
+        const u8* sp = score + (py + 1) * SP + px + 2;
         const int s = sp[0];
+        if (s == 0) continue;
         const bool keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
                           s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
         if (!keep) continue;
@@ -342,6 +373,205 @@ __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constan
         if (slot >= L.candCap) continue;
         const int x = iniX + 3 + (int)(k & 0xFF), y = iniY + 3 + (int)((k >> 8) & 0xFF);
         out[slot] = make_uint2((u32)x | ((u32)y << 16), ((u32)s << 24) | (u32)c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_fast_tma: the same per-cell algorithm with ONE WARP per cell and a persistent grid.  Each warp streams its cells through
+// two shared-memory tiles filled by TMA (cp.async.bulk.tensor.3d on a per-level tensor map of the pyramid, completion on an
+// mbarrier), so the load of the next cell overlaps the work on the current one and costs no per-thread instructions.
+// Nothing inside a cell needs a CTA barrier or a shared atomic: compaction is ballot + popc on a warp-uniform counter.
+// ---------------------------------------------------------------------------------------------------
+#define ORBX_FW_WARPS 4
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u32 bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    u32 done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(u32 dst, const CUtensorMap* map, int x, int y, int z, u32 bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+
+template <int BOXW, int SPP>
+__global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_constant__ Plan P, const CUtensorMap* __restrict__ maps,
+                                                                  const uint4* __restrict__ cells, int nCells, int nf,
+                                                                  uint2* __restrict__ cand, int* __restrict__ candCount,
+                                                                  int* __restrict__ status) {
+    extern __shared__ __align__(128) u8 smem_fw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int BW = BOXW > 0 ? BOXW : P.fwBoxW, SP = SPP > 0 ? SPP : P.scorePitch;
+    u8* wbase = smem_fw + (size_t)warp * P.fwStride;
+    u8* score = wbase + P.fwScoreOff;
+    u16* plist = reinterpret_cast<u16*>(wbase + P.fwPlistOff);
+    const u32 bar0 = smem_u32(wbase + P.fwBarOff), bar1 = bar0 + 8;
+    const u32 boxBytes = (u32)(BW * P.fwBoxH);
+    const int nItems = nCells * nf;
+    const int Wt = gridDim.x * ORBX_FW_WARPS;
+    int item = blockIdx.x * ORBX_FW_WARPS + warp;
+    if (item >= nItems) return;
+
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int it, int b) {          // lane 0 only
+        const int f = it / nCells, ci = it - f * nCells;
+        const uint4 ce = __ldg(cells + ci);
+        const u32 bar = b ? bar1 : bar0;
+        mbar_expect_tx(bar, boxBytes);
+        // TMA needs the box start 16-byte aligned in the innermost dimension: load from the aligned column, keep the lead
+        tma_load_3d(smem_u32(wbase + b * P.fwTileBytes), maps + ((ce.y >> 16) & 0xFF), ((int)(ce.x & 0xFFFF) + ORBX_OX) & ~15,
+                    (int)(ce.x >> 16) + ORBX_OY, f, bar);
+    };
+    if (lane == 0) issue(item, 0);
+    u32 ph0 = 0, ph1 = 0;
+    int buf = 0;
+    const int t = P.minTh, hiT = 256 + t, loT = 256 - t;
+    const u32 lt = (1u << lane) - 1;
+
+    for (; item < nItems; item += Wt, buf ^= 1) {
+        if (lane == 0 && item + Wt < nItems) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // our generic reads of that buffer are done (syncwarp below)
+            issue(item + Wt, buf ^ 1);
+        }
+        const int f = item / nCells, cidx = item - f * nCells;
+        const uint4 ce = __ldg(cells + cidx);
+        const int iniX = (int)(ce.x & 0xFFFF), iniY = (int)(ce.x >> 16);
+        const int tw = (int)(ce.y & 0xFF), th = (int)((ce.y >> 8) & 0xFF), l = (int)((ce.y >> 16) & 0xFF), c = (int)ce.z;
+        const int dw = tw - 6, dh = th - 6;
+        // score map: pixel (px, py) at byte (py + 1) * SP + px + 2; zero it while the tile is in flight
+        for (int i = lane; i < (((dh + 2) * SP) >> 2); i += 32) reinterpret_cast<u32*>(score)[i] = 0;
+        if (buf) { mbar_wait(bar1, ph1); ph1 ^= 1; } else { mbar_wait(bar0, ph0); ph0 ^= 1; }
+        __syncwarp();
+        const u8* tile = wbase + buf * P.fwTileBytes;
+
+        // ---- phase A (domain pixel 0 sits at tile (X0, 3); pairs are aligned to even tile x)
+        const int X0 = ((iniX + ORBX_OX) & 15) + 3;
+        int nl = 0;
+        {
+            const int off = X0 & 1, npr = (off + dw + 1) >> 1, ntask = npr * dh;
+            const u32 inv = 0xFFFFFFFFu / (u32)npr + 1;
+            const u8* cE = tile + 3 * BW + (X0 & ~1);
+            for (int task0 = 0; task0 < ntask; task0 += 32) {
+                const int task = task0 + lane;
+                bool pass0 = false, pass1 = false;
+                int row = 0, px0 = 0;
+                if (task < ntask) {
+                    row = npr == 1 ? task : (int)__umulhi((u32)task, inv);   // (inv overflows for npr == 1)
+                    const int p = task - row * npr;
+                    px0 = 2 * p - off;
+                    const u8* pe = cE + row * BW + 2 * p;
+#define LD2(o) __byte_perm((u32) * reinterpret_cast<const u16*>(pe + (o)), 0, 0x4140)
+                    const u32 vb = LD2(0) + 0x01000100u;
+                    const u32 d0 = vb - LD2(3 * BW), d8 = vb - LD2(-3 * BW);
+                    const u32 d2 = vb - LD2(2 * BW + 2), d10 = vb - LD2(-2 * BW - 2);
+                    const u32 d6 = vb - LD2(-2 * BW + 2), d14 = vb - LD2(2 * BW - 2);
+#undef LD2
+                    const u32 md = min3x2(__vmaxu2(d0, d8), __vmaxu2(d2, d10), __vmaxu2(d6, d14));    // dark arc possible iff > 256+t
+                    const u32 mb = max3x2(__vminu2(d0, d8), __vminu2(d2, d10), __vminu2(d6, d14));    // bright arc possible iff < 256-t
+                    // bit 15 of each half: md >= hiT+1  |  mb <= loT-1   (halves are 9-bit values: no carries between them)
+                    const u32 C1 = (u32)(0x8000 - (hiT + 1)) * 0x00010001u, C2 = (u32)(0x8000 + loT - 1) * 0x00010001u;
+                    const u32 fl = ((md + C1) | (C2 - mb)) & 0x80008000u;
+                    pass0 = (fl & 0x8000u) && px0 >= 0;
+                    pass1 = (fl & 0x80000000u) && px0 + 1 < dw;
+                }
+                const u32 b0 = __ballot_sync(0xffffffffu, pass0), b1 = __ballot_sync(0xffffffffu, pass1);
+                const int n0 = __popc(b0);
+                if (pass0) plist[nl + __popc(b0 & lt)] = (u16)((row << 8) | px0);
+                if (pass1) plist[nl + n0 + __popc(b1 & lt)] = (u16)((row << 8) | (px0 + 1));
+                nl += n0 + __popc(b1);
+            }
+        }
+        __syncwarp();
+
+        // ---- phase B: exact score of the listed pixels, two per lane
+        {
+            const u8* t8 = tile + 3 * BW + X0;
+#define RING(dx, dy) ((u32)q0[(dy) * BW + (dx)] | ((u32)q1[(dy) * BW + (dx)] << 16))
+            for (int i = lane; 2 * i < nl; i += 32) {
+                const int e0 = plist[2 * i], e1 = plist[min(2 * i + 1, nl - 1)];
+                const u8* q0 = t8 + (e0 >> 8) * BW + (e0 & 0xFF);
+                const u8* q1 = t8 + (e1 >> 8) * BW + (e1 & 0xFF);
+                u32 r[16];
+                r[0] = RING(0, 3); r[1] = RING(1, 3); r[2] = RING(2, 2); r[3] = RING(3, 1);
+                r[4] = RING(3, 0); r[5] = RING(3, -1); r[6] = RING(2, -2); r[7] = RING(1, -3);
+                r[8] = RING(0, -3); r[9] = RING(-1, -3); r[10] = RING(-2, -2); r[11] = RING(-3, -1);
+                r[12] = RING(-3, 0); r[13] = RING(-3, 1); r[14] = RING(-2, 2); r[15] = RING(-1, 3);
+                const u32 v = RING(0, 0);
+                int s0, s1;
+                fast_score_pair(r, v, s0, s1);
+                if (s0 >= t) score[((e0 >> 8) + 1) * SP + (e0 & 0xFF) + 2] = (u8)s0;
+                if (s1 >= t) score[((e1 >> 8) + 1) * SP + (e1 & 0xFF) + 2] = (u8)s1;
+            }
+#undef RING
+        }
+        __syncwarp();
+
+        // ---- 3x3 NMS over the listed pixels; survivors are flagged in place (bit 7), then the threshold retry and emission
+        int nKeep = 0, nIni = 0;
+        for (int e0 = 0; e0 < nl; e0 += 32) {
+            const int e = e0 + lane;
+            bool keep = false, ini = false;
+            if (e < nl) {
+                const int ent = plist[e], py = ent >> 8, px = ent & 0xFF;
+                const u8* sp = score + (py + 1) * SP + px + 2;
+                const int s = sp[0];
+                if (s) {
+                    keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
+                           s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
+                    ini = keep && s >= P.iniTh;
+                    if (keep) plist[e] = (u16)(ent | 0x80);
+                }
+            }
+            nKeep += __popc(__ballot_sync(0xffffffffu, keep));
+            nIni += __popc(__ballot_sync(0xffffffffu, ini));
+        }
+        if (nKeep) {
+            const LevelPlan& L = P.lv[l];
+            const int T = nIni > 0 ? P.iniTh : P.minTh;                 // the iniThFAST -> minThFAST retry (:811-815)
+            const int nEmit = nIni > 0 ? nIni : nKeep;
+            int base = 0;
+            if (lane == 0) {
+                base = atomicAdd(&candCount[f * P.nlevels + l], nEmit);
+                if (base + nEmit > L.candCap) atomicOr(status, ORB_DEV_CAND_OVERFLOW);
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+            __syncwarp();
+            uint2* out = cand + (size_t)f * P.candTotal + L.candOff;
+            for (int e0 = 0; e0 < nl; e0 += 32) {
+                const int e = e0 + lane;
+                bool emit = false;
+                int px = 0, py = 0, s = 0;
+                if (e < nl) {
+                    const int ent = plist[e];
+                    if (ent & 0x80) {
+                        py = ent >> 8; px = ent & 0x7F;
+                        s = score[(py + 1) * SP + px + 2];
+                        emit = s >= T;
+                    }
+                }
+                const u32 bm = __ballot_sync(0xffffffffu, emit);
+                if (emit) {
+                    const int slot = base + __popc(bm & lt);
+                    if (slot < L.candCap)
+                        out[slot] = make_uint2((u32)(iniX + 3 + px) | ((u32)(iniY + 3 + py) << 16), ((u32)s << 24) | (u32)c);
+                }
+                base += __popc(bm);
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -706,9 +936,9 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
                                                               const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
                                                               u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
                                                               int* __restrict__ status) {
-    __shared__ signed char s_pat[1024];
+    __shared__ __align__(16) float s_pat[32 * 36];                 // pattern as float (no I2F in the tap loop); row stride 36: conflict-free LDS.128
     __shared__ u32 s_patch[DESC_WARPS][37][DESC_PW];
-    for (int i = threadIdx.x; i < 256; i += 32 * DESC_WARPS) reinterpret_cast<int*>(s_pat)[i] = reinterpret_cast<const int*>(c_pattern)[i];
+    for (int i = threadIdx.x; i < 1024; i += 32 * DESC_WARPS) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y;
     const int slot = blockIdx.x * DESC_WARPS + warp;
@@ -744,14 +974,14 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
     // ---- IC_Angle (ORBextractor.cc:76-103): lane = column u (-15..15), loop over the rows of the disc (coalesced)
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        const int u = lane - 15, au = u < 0 ? -u : u;
+        // the disc is symmetric (ORBextractor.cc:461-468 makes umax its own transpose): column u spans rows |v| <= umax[|u|]
+        const int u = lane - 15, vlim = P.umax[u < 0 ? -u : u];
         const u8* cen = pyr + lofs + (size_t)(ky + ORBX_OY) * pitch + kx + ORBX_OX + u;
         int colsum = 0;
 #pragma unroll
         for (int v = -15; v <= 15; v++) {
-            const int av = v < 0 ? -v : v;
-            if (au <= P.umax[av]) {
-                const int I = cen[(ptrdiff_t)v * pitch];
+            if ((v < 0 ? -v : v) <= vlim) {
+                const int I = cen[v * pitch];
                 colsum += I;
                 m01 += v * I;
             }
@@ -771,15 +1001,18 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
     const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
     __syncwarp();
     const u8* center = reinterpret_cast<const u8*>(&s_patch[warp][18][0]) + 18 + shift;
-    const signed char* pat = s_pat + lane * 32;
+    const float4* pat = reinterpret_cast<const float4*>(s_pat + lane * 36);
     u32 val = 0;
+    // round-half-even without the XU pipe: x + 1.5*2^23 leaves rint(x) in the low mantissa bits (|x| < 2^22), == cvRound
+    const float MAGIC = 12582912.f;
+    const int MAGIC_I = 0x4B400000;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const float x0 = (float)pat[4 * j], y0 = (float)pat[4 * j + 1], x1 = (float)pat[4 * j + 2], y1 = (float)pat[4 * j + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int q0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int q1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const float4 pp = pat[j];                                   // x0, y0, x1, y1
+        const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)), MAGIC)) - MAGIC_I;
+        const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)), MAGIC)) - MAGIC_I;
+        const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.z, b), __fmul_rn(pp.w, a)), MAGIC)) - MAGIC_I;
+        const int q1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.z, a), __fmul_rn(pp.w, b)), MAGIC)) - MAGIC_I;
         const int t0 = center[r0 * (DESC_PW * 4) + q0], t1 = center[r1 * (DESC_PW * 4) + q1];
         val |= (u32)(t0 < t1) << j;
     }
@@ -822,6 +1055,12 @@ struct orbx_extractor {
     u32* d_nodeOf = nullptr;
     int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr;
     ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
+    CUtensorMap* d_maps = nullptr;         // one TMA descriptor per pyramid level (k_fast_tma)
+    bool useTma = false;
+    size_t fwSmem = 0;
+    int fwGrid = 0;
+    uint4* d_cells = nullptr;              // valid FAST cells: {iniX | iniY<<16, tw | th<<8 | level<<16, cell id, 0}
+    int nCells = 0;
     int capInternal = 0;
     size_t fastSmem = 0, octSmem = 0;
     bool fastConst = false;
@@ -866,6 +1105,7 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         }
     }
     std::vector<ResizeTap> xt, yt;
+    std::vector<uint4> cells;
     size_t off = 0;
     int cellBase = 0, candOff = 0, selOff = 0, maxNodes = 8, maxCW = 1, maxCH = 1;
     for (int l = 0; l < nl; l++) {
@@ -882,7 +1122,7 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         const float fw = (float)(L.maxBX - ORBX_MINB), fh = (float)(L.maxBY - ORBX_MINB);   // :779-786
         L.nCols = (int)(fw / 30.f); L.nRows = (int)(fh / 30.f);
         L.wCell = (int)ceilf(fw / L.nCols); L.hCell = (int)ceilf(fh / L.nRows);
-        ORB_REQUIRE(L.wCell <= 250 && L.hCell <= 250, ORB_ERR_GEOMETRY, "cell too large");
+        ORB_REQUIRE(L.wCell <= 120 && L.hCell <= 120, ORB_ERR_GEOMETRY, "cell too large");
         L.cellBase = cellBase;
         cellBase += L.nCols * L.nRows;
         maxCW = std::max(maxCW, L.wCell); maxCH = std::max(maxCH, L.hCell);
@@ -904,6 +1144,19 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
                     if (iniX >= L.maxBX - 6) continue;
                     const int dw = std::min(iniX + L.wCell + 6, L.maxBX) - iniX - 6;
                     if (dw > 0 && dh > 0) bound += (long)((dw + 1) / 2) * ((dh + 1) / 2);
+                }
+            }
+            for (int i = 0; i < L.nRows; i++) {          // the valid cells, in the reference's visiting order (:788-805)
+                const int iniY = ORBX_MINB + i * L.hCell;
+                if (iniY >= L.maxBY - 3) continue;
+                const int th = std::min(iniY + L.hCell + 6, L.maxBY) - iniY;
+                for (int j = 0; j < L.nCols; j++) {
+                    const int iniX = ORBX_MINB + j * L.wCell;
+                    if (iniX >= L.maxBX - 6) continue;
+                    const int tw = std::min(iniX + L.wCell + 6, L.maxBX) - iniX;
+                    if (tw - 6 <= 0 || th - 6 <= 0) continue;        // cv::FAST on a ROI < 7 px finds nothing
+                    cells.push_back(make_uint4((unsigned)iniX | ((unsigned)iniY << 16), (unsigned)tw | ((unsigned)th << 8) | ((unsigned)l << 16),
+                                               (unsigned)(i * L.nCols + j), 0u));
                 }
             }
             if (ex->candPerCell > 0) bound = std::min<long>(bound, (long)L.nCols * L.nRows * ex->candPerCell);
@@ -938,14 +1191,14 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     P.sortN = 2; while (P.sortN < maxNodes) P.sortN <<= 1;
     P.frameBytes = off;
     // FAST tile: pixel pairs (u32) per row = 2 * words, words = ceil((3 + cellW + 6 + 1) / 4); two copies; + score map + corner list
-    P.tilePitch = 2 * (int)((3 + maxCW + 6 + 1 + 3) / 4) + 2; P.tileRows = maxCH + 6;
-    P.scorePitch = (int)orb_align_up(maxCW + 3, 4); P.scoreRows = maxCH + 2;
+    P.tilePitch = 2 * (int)((3 + maxCW + 6 + 3) / 4) + 2; P.tileRows = maxCH + 6;
+    P.scorePitch = (int)orb_align_up(maxCW + 8, 4); P.scoreRows = maxCH + 2;
     ex->fastConst = P.tilePitch <= ORBX_FAST_TPP && P.scorePitch <= ORBX_FAST_SPP;
     if (ex->fastConst) { P.tilePitch = ORBX_FAST_TPP; P.scorePitch = ORBX_FAST_SPP; }
-    ex->fastSmem = (size_t)P.tilePitch * P.tileRows * 4 * 2 + (size_t)P.scorePitch * P.scoreRows + (size_t)(maxCW + 1) * maxCH * 2 + 16;
+    ex->fastSmem = (size_t)P.tilePitch * P.tileRows * 4 + (size_t)P.scorePitch * P.scoreRows + (size_t)(maxCW + 2) * maxCH * 2 + 16;
+    ex->nCells = (int)cells.size();
     ex->octSmem = (size_t)maxNodes * (16 * 2 + 4 * 2 + 16 + 4 * 3) + (size_t)P.sortN * 8 + 64;
     ORB_REQUIRE(ex->octSmem <= 220 * 1024, ORB_ERR_ARG, "nfeatures too large for the octree kernel's shared memory");
-    ORB_REQUIRE(maxCW <= 250 && maxCH <= 250, ORB_ERR_GEOMETRY, "cell too large");
     ex->capInternal = selOff;
 
     const int B = ex->maxBatch;
@@ -961,8 +1214,65 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     ORB_CUDA_TRY(cudaMemset(ex->d_blur, 0, (size_t)B * P.frameBytes));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_xtab, std::max<size_t>(xt.size(), 1) * sizeof(ResizeTap)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_ytab, std::max<size_t>(yt.size(), 1) * sizeof(ResizeTap)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_cells, std::max<size_t>(cells.size(), 1) * sizeof(uint4)));
+    if (!cells.empty()) ORB_CUDA_TRY(cudaMemcpy(ex->d_cells, cells.data(), cells.size() * sizeof(uint4), cudaMemcpyHostToDevice));
     if (!xt.empty()) ORB_CUDA_TRY(cudaMemcpy(ex->d_xtab, xt.data(), xt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
     if (!yt.empty()) ORB_CUDA_TRY(cudaMemcpy(ex->d_ytab, yt.data(), yt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+    // ---- k_fast_tma: per-warp shared-memory layout and one tensor map per level over the pyramid workspace
+    {
+        const int boxW = (int)orb_align_up(maxCW + 6 + 15, 16), boxH = maxCH + 6;   // + up to 15 lead bytes (16-byte aligned box start)
+        P.fwBoxW = boxW; P.fwBoxH = boxH;
+        P.fwTileBytes = (int)orb_align_up((size_t)boxW * boxH, 128);
+        P.fwScoreOff = 2 * P.fwTileBytes;
+        P.fwPlistOff = P.fwScoreOff + (int)orb_align_up((size_t)P.scorePitch * P.scoreRows, 16);
+        P.fwBarOff = P.fwPlistOff + (int)orb_align_up((size_t)(maxCW + 2) * maxCH * 2, 16);
+        P.fwStride = (int)orb_align_up((size_t)P.fwBarOff + 16, 128);
+        ex->fwSmem = (size_t)P.fwStride * ORBX_FW_WARPS;
+        ex->useTma = false;
+        const char* env = getenv("ORBX_FAST_TMA");
+        const bool want = !(env && atoi(env) == 0);
+        if (want && boxW <= 256 && boxH <= 256 && maxCW <= 62 && maxCH <= 62 && ex->fwSmem <= 200 * 1024) {
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+                qres == cudaDriverEntryPointSuccess) {
+                std::vector<CUtensorMap> maps(nl);
+                bool ok = true;
+                for (int l = 0; l < nl && ok; l++) {
+                    const LevelPlan& L = P.lv[l];
+                    cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.brows, (cuuint64_t)ex->maxBatch};
+                    cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)P.frameBytes};
+                    cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+                    cuuint32_t estr[3] = {1, 1, 1};
+                    ok = ((EncodeFn)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_pyr + L.off, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                }
+                if (ok) {
+                    ORB_CUDA_TRY(cudaMalloc(&ex->d_maps, nl * sizeof(CUtensorMap)));
+                    ORB_CUDA_TRY(cudaMemcpy(ex->d_maps, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+                    ex->useTma = true;
+                }
+            } else cudaGetLastError();
+        }
+        if (ex->useTma) {
+            cudaDeviceProp prop;
+            ORB_CUDA_TRY(cudaGetDeviceProperties(&prop, ex->device));
+            const int perSM = std::max(1, std::min(8, (int)((prop.sharedMemPerMultiprocessor - 4096) / (ex->fwSmem + 1024))));
+            ex->fwGrid = prop.multiProcessorCount * perSM;
+            static std::mutex amu2;
+            static size_t maxFw = 0;
+            std::lock_guard<std::mutex> lk(amu2);
+            if (ex->fwSmem > maxFw) {
+                ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, ORBX_FAST_SPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
+                ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
+                maxFw = ex->fwSmem;
+            }
+        }
+    }
     {   // dynamic shared-memory opt-in is per function, shared by all handles: only ever raise it
         static std::mutex amu;
         static size_t maxFast = 0, maxOct = 0;
@@ -1026,7 +1336,7 @@ extern "C" void orbx_destroy(orbx_extractor* ex) {
     if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
     if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
     cudaFree(ex->d_cand); cudaFree(ex->d_sel); cudaFree(ex->d_nodeOf); cudaFree(ex->d_candCount); cudaFree(ex->d_selCount);
-    cudaFree(ex->d_status); cudaFree(ex->d_xtab); cudaFree(ex->d_ytab);
+    cudaFree(ex->d_status); cudaFree(ex->d_xtab); cudaFree(ex->d_ytab); cudaFree(ex->d_cells); cudaFree(ex->d_maps);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
 }
@@ -1078,11 +1388,22 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     }
     if (stages & ORBX_STAGE_FAST) {
         ORB_CUDA_TRY(cudaMemsetAsync(ex->d_candCount, 0, (size_t)nf * nl * sizeof(int), st));
-        dim3 g(P.totalCells, nf);
-        if (ex->fastConst)
-            k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
-        else
-            k_fast<0, 0><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
+        dim3 g(ex->nCells, nf);
+        if (ex->nCells > 0 && ex->useTma) {
+            const int items = ex->nCells * nf;
+            const int grid = std::min(ex->fwGrid, orb_div_up(items, ORBX_FW_WARPS));
+            if (P.fwBoxW == 64 && ex->fastConst)
+                k_fast_tma<64, ORBX_FAST_SPP><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
+                                                                                          ex->d_candCount, ex->d_status);
+            else
+                k_fast_tma<0, 0><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
+                                                                             ex->d_candCount, ex->d_status);
+        } else if (ex->nCells > 0) {
+            if (ex->fastConst)
+                k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_cells, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
+            else
+                k_fast<0, 0><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_cells, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
+        }
         ex->launches++;
     }
     if (stages & ORBX_STAGE_OCTREE) {
