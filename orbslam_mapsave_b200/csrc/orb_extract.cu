@@ -496,47 +496,69 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
         }
         __syncwarp();
 
-        // ---- phase B: exact score of the listed pixels, two per lane
+        // ---- phase B: exact score of the listed pixels, ONE pixel per lane with d = v - ring in the low half and -d in the high
+        // half of every register (x = K + ring * 0xFFFF, K = (256 + v) | (256 - v) << 16), so that
+        //   A = max over arcs of min9(d)   and   B = max over arcs of min9(-d)
+        // come out of one min3/max3 sequence (40 VIMNMX3.U16x2 per pixel).  Corners are compacted in place at the list front.
+        int nc = 0;
         {
             const u8* t8 = tile + 3 * BW + X0;
-#define RING(dx, dy) ((u32)q0[(dy) * BW + (dx)] | ((u32)q1[(dy) * BW + (dx)] << 16))
-            for (int i = lane; 2 * i < nl; i += 32) {
-                const int e0 = plist[2 * i], e1 = plist[min(2 * i + 1, nl - 1)];
-                const u8* q0 = t8 + (e0 >> 8) * BW + (e0 & 0xFF);
-                const u8* q1 = t8 + (e1 >> 8) * BW + (e1 & 0xFF);
-                u32 r[16];
-                r[0] = RING(0, 3); r[1] = RING(1, 3); r[2] = RING(2, 2); r[3] = RING(3, 1);
-                r[4] = RING(3, 0); r[5] = RING(3, -1); r[6] = RING(2, -2); r[7] = RING(1, -3);
-                r[8] = RING(0, -3); r[9] = RING(-1, -3); r[10] = RING(-2, -2); r[11] = RING(-3, -1);
-                r[12] = RING(-3, 0); r[13] = RING(-3, 1); r[14] = RING(-2, 2); r[15] = RING(-1, 3);
-                const u32 v = RING(0, 0);
-                int s0, s1;
-                fast_score_pair(r, v, s0, s1);
-                if (s0 >= t) score[((e0 >> 8) + 1) * SP + (e0 & 0xFF) + 2] = (u8)s0;
-                if (s1 >= t) score[((e1 >> 8) + 1) * SP + (e1 & 0xFF) + 2] = (u8)s1;
-            }
+            for (int e0 = 0; e0 < nl; e0 += 32) {
+                const int e = e0 + lane;
+                int ent = 0, sc = 0;
+                if (e < nl) {
+                    ent = plist[e];
+                    const u8* q = t8 + (ent >> 8) * BW + (ent & 0xFF);
+                    const u32 v = q[0];
+                    const u32 K = (256u + v) | ((256u - v) << 16);
+#define RING(dx, dy) (K + (u32)q[(dy) * BW + (dx)] * 0xFFFFu)
+                    u32 d[16];
+                    d[0] = RING(0, 3); d[1] = RING(1, 3); d[2] = RING(2, 2); d[3] = RING(3, 1);
+                    d[4] = RING(3, 0); d[5] = RING(3, -1); d[6] = RING(2, -2); d[7] = RING(1, -3);
+                    d[8] = RING(0, -3); d[9] = RING(-1, -3); d[10] = RING(-2, -2); d[11] = RING(-3, -1);
+                    d[12] = RING(-3, 0); d[13] = RING(-3, 1); d[14] = RING(-2, 2); d[15] = RING(-1, 3);
 #undef RING
+                    u32 m3[16], m9[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) m3[k] = min3x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+#pragma unroll
+                    for (int k = 0; k < 16; k++) m9[k] = min3x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                    u32 A = max3x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+                    for (int k = 3; k < 15; k += 2) A = max3x2(A, m9[k], m9[k + 1]);
+                    A = __vmaxu2(A, m9[15]);
+                    sc = (int)max(A & 0xFFFF, A >> 16) - 257;        // max(A, B) - 1
+                    if (sc < t) sc = 0;
+                }
+                __syncwarp();                                          // everyone has read its entry before the in-place compaction
+                const u32 bm = __ballot_sync(0xffffffffu, sc > 0);
+                if (sc > 0) {
+                    score[((ent >> 8) + 1) * SP + (ent & 0xFF) + 2] = (u8)sc;
+                    plist[nc + __popc(bm & lt)] = (u16)ent;
+                }
+                nc += __popc(bm);
+            }
         }
         __syncwarp();
 
-        // ---- 3x3 NMS over the listed pixels; survivors are flagged in place (bit 7), then the threshold retry and emission
+        // ---- 3x3 NMS over the corners; survivors compacted in place again; then the threshold retry and emission
         int nKeep = 0, nIni = 0;
-        for (int e0 = 0; e0 < nl; e0 += 32) {
+        for (int e0 = 0; e0 < nc; e0 += 32) {
             const int e = e0 + lane;
-            bool keep = false, ini = false;
-            if (e < nl) {
-                const int ent = plist[e], py = ent >> 8, px = ent & 0xFF;
-                const u8* sp = score + (py + 1) * SP + px + 2;
-                const int s = sp[0];
-                if (s) {
-                    keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
-                           s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
-                    ini = keep && s >= P.iniTh;
-                    if (keep) plist[e] = (u16)(ent | 0x80);
-                }
+            bool keep = false;
+            int ent = 0, s = 0;
+            if (e < nc) {
+                ent = plist[e];
+                const u8* sp = score + ((ent >> 8) + 1) * SP + (ent & 0xFF) + 2;
+                s = sp[0];
+                keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
+                       s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
             }
-            nKeep += __popc(__ballot_sync(0xffffffffu, keep));
-            nIni += __popc(__ballot_sync(0xffffffffu, ini));
+            __syncwarp();
+            const u32 bk = __ballot_sync(0xffffffffu, keep);
+            if (keep) plist[nKeep + __popc(bk & lt)] = (u16)ent;
+            nKeep += __popc(bk);
+            nIni += __popc(__ballot_sync(0xffffffffu, keep && s >= P.iniTh));
         }
         if (nKeep) {
             const LevelPlan& L = P.lv[l];
@@ -548,19 +570,16 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                 if (base + nEmit > L.candCap) atomicOr(status, ORB_DEV_CAND_OVERFLOW);
             }
             base = __shfl_sync(0xffffffffu, base, 0);
-            __syncwarp();
             uint2* out = cand + (size_t)f * P.candTotal + L.candOff;
-            for (int e0 = 0; e0 < nl; e0 += 32) {
+            for (int e0 = 0; e0 < nKeep; e0 += 32) {
                 const int e = e0 + lane;
                 bool emit = false;
                 int px = 0, py = 0, s = 0;
-                if (e < nl) {
+                if (e < nKeep) {
                     const int ent = plist[e];
-                    if (ent & 0x80) {
-                        py = ent >> 8; px = ent & 0x7F;
-                        s = score[(py + 1) * SP + px + 2];
-                        emit = s >= T;
-                    }
+                    py = ent >> 8; px = ent & 0xFF;
+                    s = score[(py + 1) * SP + px + 2];
+                    emit = s >= T;
                 }
                 const u32 bm = __ballot_sync(0xffffffffu, emit);
                 if (emit) {
