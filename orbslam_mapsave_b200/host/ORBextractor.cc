@@ -1,0 +1,85 @@
+// ORBextractor.cc — host side of the drop-in class: marshals ORB_SLAM2::ORBextractor onto the C ABI (include/orb_b200.h).
+// Replaces src/ORBextractor.cc of the reference; every computation (tables included) happens in liborb_b200.so.
+#include "ORBextractor.h"
+
+#include <cassert>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/orb_b200.h"
+
+namespace ORB_SLAM2 {
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint must be the 28-byte POD the C ABI writes");
+
+ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
+    : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST) {
+    mvImagePyramid.resize(nlevels);
+    // The scale tables do not depend on the image size: plan once for a nominal VGA frame to obtain them
+    // (reference: computed in the constructor, ORBextractor.cc:414-445); operator() re-plans for the real size.
+    Plan(640, 480);
+}
+
+ORBextractor::~ORBextractor() { orbx_destroy(mHandle); }
+
+void ORBextractor::Plan(int width, int height) {
+    if (mHandle && width == mPlanW && height == mPlanH) return;
+    orbx_destroy(mHandle);
+    mHandle = nullptr;
+    mLastStatus = orbx_create(&mHandle, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, width, height, 1, mDevice);
+    if (mLastStatus != ORB_OK) {
+        std::fprintf(stderr, "ORBextractor: %s\n", orb_last_error());
+        return;
+    }
+    mPlanW = width; mPlanH = height;
+    mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+    mnFeaturesPerLevel.resize(nlevels);
+    orbx_tables(mHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(), mvInvLevelSigma2.data(),
+                mnFeaturesPerLevel.data());
+}
+
+void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint>& _keypoints,
+                              cv::OutputArray _descriptors) {
+    if (_image.empty()) return;                                  // reference :1045-1046: outputs untouched
+    cv::Mat image = _image.getMat();
+    cv::Mat mask = _mask.getMat();
+    assert(image.type() == CV_8UC1);                             // reference :1051
+    Plan(image.cols, image.rows);
+    if (!mHandle) return;
+
+    const int cap = orbx_max_keypoints(mHandle);
+    std::vector<cv::KeyPoint> kps(cap);
+    cv::Mat desc(cap, 32, CV_8U);
+    int n = 0;
+    mLastStatus = orbx_extract(mHandle, image.data, image.cols, image.rows, (int)image.step,
+                               mask.empty() ? nullptr : mask.data, mask.empty() ? 0 : (int)mask.step,
+                               reinterpret_cast<orbx_keypoint*>(kps.data()), desc.data, cap, &n);
+    if (mLastStatus != ORB_OK) {
+        std::fprintf(stderr, "ORBextractor: %s\n", orb_last_error());
+        return;
+    }
+    if (n == 0) _descriptors.release();                          // reference :1067-1073
+    else {
+        _descriptors.create(n, 32, CV_8U);
+        cv::Mat out = _descriptors.getMat();
+        for (int i = 0; i < n; i++) std::memcpy(out.ptr(i), desc.ptr(i), 32);
+    }
+    _keypoints.assign(kps.begin(), kps.begin() + n);             // reference :1075-1106
+
+    if (mbDownloadPyramid) {                                     // reference :1110-1135: ROI views inside (w+38)x(h+38) buffers
+        mvImagePyramid.resize(nlevels);
+        for (int l = 0; l < nlevels; l++) {
+            int w = 0, h = 0;
+            orbx_level_size(mHandle, l, &w, &h);
+            cv::Mat whole(h + 38, w + 38, CV_8U);
+            if (orbx_get_pyramid_level(mHandle, 0, l, 1, whole.data, (int)whole.step) != ORB_OK) break;
+#if defined(OPENCV_CORE_HPP) || defined(__OPENCV_CORE_HPP__)
+            mvImagePyramid[l] = whole(cv::Rect(19, 19, w, h));
+#else
+            mvImagePyramid[l] = whole.roi(19, 19, w, h);
+#endif
+        }
+    }
+}
+
+}  // namespace ORB_SLAM2

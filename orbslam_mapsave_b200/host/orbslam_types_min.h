@@ -1,0 +1,60 @@
+// orbslam_types_min.h — stand-ins for the reference's KeyFrame / Frame / MapPoint / DBoW2::FeatureVector exposing exactly the
+// members the hot-path ORBmatcher functions touch (include/KeyFrame.h:66-69,103-105,179-204; include/Frame.h:141-189;
+// include/MapPoint.h:73; Thirdparty/DBoW2/DBoW2/FeatureVector.h:21-22).  When ORBmatcher.cc is built inside the reference tree
+// (KeyFrame.h on the include path) the real classes are used instead.
+#pragma once
+#if !defined(ORB_B200_FORCE_MIN_TYPES) && __has_include("KeyFrame.h") && __has_include("Frame.h")
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "MapPoint.h"
+#else
+#include <map>
+#include <vector>
+#include "cv_compat.h"
+
+namespace DBoW2 {
+typedef unsigned int NodeId;
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {
+public:
+    void addFeature(NodeId id, unsigned int i_feature) { (*this)[id].push_back(i_feature); }
+};
+}  // namespace DBoW2
+
+namespace ORB_SLAM2 {
+
+class MapPoint {
+public:
+    bool isBad() { return mbBad; }
+    bool mbBad = false;
+};
+
+class Frame {
+public:
+    int N = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<float> mvuRight;
+    DBoW2::FeatureVector mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<MapPoint*> mvpMapPoints;
+};
+
+class KeyFrame {
+public:
+    int N = 0;
+    float fx = 0, fy = 0, cx = 0, cy = 0;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<float> mvuRight;
+    cv::Mat mDescriptors;
+    DBoW2::FeatureVector mFeatVec;
+    std::vector<float> mvScaleFactors, mvLevelSigma2;
+    std::vector<MapPoint*> mvpMapPoints;
+    cv::Mat Ow, Rcw, tcw;                               // 3x1, 3x3, 3x1 CV_32F
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    cv::Mat GetCameraCenter() { return Ow.clone(); }
+    cv::Mat GetRotation() { return Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.clone(); }
+};
+
+}  // namespace ORB_SLAM2
+#endif

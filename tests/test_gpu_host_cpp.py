@@ -1,0 +1,141 @@
+"""GPU parity tests of the C++ drop-in classes (orbslam_mapsave_b200/host: ORB_SLAM2::ORBextractor / ORBmatcher with the
+reference's own signatures) against the CPU oracle.  The driver tests/cpp/host_api_driver is built by
+__graft_entry__.build() and calls the classes the way Frame::ExtractORB / LocalMapping do in the reference."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from orbslam_mapsave_b200 import KP_DTYPE
+from orbslam_mapsave_b200.synth import synth
+from oracle import orb_oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "tests", "cpp", "host_api_driver")
+
+
+def _driver():
+    if not os.path.exists(DRIVER):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "orbslam_mapsave_b200", "host")])
+    return DRIVER
+
+
+@pytest.mark.parametrize("W,H,seed,nf,nl,sf,ini,mn,masked", [(640, 480, 40, 1000, 8, 1.2, 20, 7, False),
+                                                              (752, 480, 41, 1200, 8, 1.2, 20, 7, True)])
+def test_cpp_orbextractor_matches_oracle(tmp_path, W, H, seed, nf, nl, sf, ini, mn, masked):
+    img = synth(W, H, seed)
+    (tmp_path / "in.raw").write_bytes(img.tobytes())
+    args = [_driver(), "extract", str(tmp_path / "in.raw"), str(W), str(H), str(nf), str(sf), str(nl), str(ini), str(mn),
+            str(tmp_path / "out")]
+    mask = None
+    if masked:
+        mask = np.full((H, W), 255, np.uint8)
+        mask[100:300, 300:500] = 0
+        (tmp_path / "mask.raw").write_bytes(mask.tobytes())
+        args.append(str(tmp_path / "mask.raw"))
+    subprocess.check_call(args)
+    kp = np.frombuffer((tmp_path / "out.kp").read_bytes(), KP_DTYPE)
+    desc = np.frombuffer((tmp_path / "out.desc").read_bytes(), np.uint8).reshape(-1, 32)
+    oex = orc.Extractor(nf, sf, nl, ini, mn)
+    okp, odesc = oex.extract(img, mask)
+    assert len(kp) == len(okp) == len(desc)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kp[f], okp[f]), f
+    assert np.abs(kp["angle"].astype(np.float64) - okp["angle"]).max() <= 1e-3
+    assert np.unpackbits(desc ^ odesc).sum() <= 1e-4 * desc.size * 8
+    # getters and the public bordered pyramid
+    meta = (tmp_path / "out.meta").read_bytes()
+    nlev, = struct.unpack_from("<i", meta, 0)
+    sfac, = struct.unpack_from("<f", meta, 4)
+    assert nlev == nl and sfac == np.float32(sf)
+    tabs = np.frombuffer(meta, np.float32, 4 * nl, 8).reshape(4, nl)
+    t = oex.tables()
+    for got, key in zip(tabs, ("scale", "inv_scale", "sigma2", "inv_sigma2")):
+        assert np.array_equal(got, t[key]), key
+    pos = 8 + 16 * nl
+    for l in range(nl):
+        w, h = struct.unpack_from("<ii", meta, pos)
+        pos += 8
+        got = np.frombuffer(meta, np.uint8, (w + 38) * (h + 38), pos).reshape(h + 38, w + 38)
+        pos += (w + 38) * (h + 38)
+        assert np.array_equal(got, oex.level(l, bordered=True)), f"bordered pyramid level {l}"
+
+
+def _flip(d, nbits, rng):
+    d = d.copy()
+    for b in rng.choice(256, nbits, replace=False):
+        d[b >> 3] ^= np.uint8(1 << (b & 7))
+    return d
+
+
+@pytest.mark.parametrize("seed,ratio,ori,only_stereo", [(0, 0.7, 1, 0), (1, 0.6, 0, 0), (2, 0.75, 1, 1)])
+def test_cpp_orbmatcher_matches_oracle(tmp_path, seed, ratio, ori, only_stereo):
+    rng = np.random.default_rng(seed)
+    n = [900, 1100]
+    desc = [rng.integers(0, 256, (n[0], 32), dtype=np.uint8), rng.integers(0, 256, (n[1], 32), dtype=np.uint8)]
+    node = [rng.integers(0, 60, n[0]) * 2 + 1, rng.integers(0, 66, n[1]) * 2 + 1]
+    k = 400
+    src, dst = rng.choice(n[0], k, replace=False), rng.choice(n[1], k, replace=False)
+    for s, t in zip(src, dst):
+        desc[1][t] = _flip(desc[0][s], int(rng.choice([0, 2, 10, 30, 49, 50, 51])), rng)
+        node[1][t] = node[0][s]
+    state = [rng.choice([0, 1, 1, 2], n[i]).astype(np.uint8) for i in range(2)]
+    ang = [rng.uniform(0, 360, n[i]).astype(np.float32) for i in range(2)]
+    ang[1][dst] = np.mod(ang[0][src] + rng.choice([0, 1, 14, 44], k), 360).astype(np.float32)
+    x = [rng.uniform(0, 640, n[i]).astype(np.float32) for i in range(2)]
+    y = [rng.uniform(0, 480, n[i]).astype(np.float32) for i in range(2)]
+    ur = [np.where(rng.random(n[i]) < 0.4, 50.0, -1.0).astype(np.float32) for i in range(2)]
+    oc = [rng.integers(0, 8, n[i]).astype(np.int32) for i in range(2)]
+    F12 = (rng.normal(0, 1, (3, 3)) * np.array([[1e-6, 1e-5, 1e-3], [1e-5, 1e-6, 1e-3], [1e-3, 1e-3, 1e-1]])).astype(np.float32)
+    Ow = rng.normal(0, 1, 3).astype(np.float32)
+    R, _ = np.linalg.qr(rng.normal(0, 1, (3, 3)))
+    R = R.astype(np.float32)
+    t = np.array([0.1, -0.2, 2.5], np.float32)
+    K = np.array([500.0, 510.0, 320.0, 240.0], np.float32)
+    sf2 = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    sig2 = (sf2 * sf2 * 4000).astype(np.float32)
+    blob = b""
+    for i in range(2):
+        blob += struct.pack("<i", n[i]) + desc[i].tobytes() + node[i].astype(np.int32).tobytes() + state[i].tobytes()
+        blob += ang[i].tobytes() + x[i].tobytes() + y[i].tobytes() + ur[i].tobytes() + oc[i].tobytes()
+    blob += struct.pack("<fii", ratio, ori, only_stereo) + F12.tobytes() + Ow.tobytes() + R.tobytes() + t.tobytes() + K.tobytes()
+    blob += struct.pack("<i", 8) + sf2.tobytes() + sig2.tobytes()
+    (tmp_path / "in.bin").write_bytes(blob)
+    subprocess.check_call([_driver(), "match", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = (tmp_path / "out.bin").read_bytes()
+    pos = 0
+
+    def take(fmt):
+        nonlocal pos
+        v = struct.unpack_from(fmt, out, pos)
+        pos += struct.calcsize(fmt)
+        return v
+
+    fv = [orc.FeatVec(node[0]), orc.FeatVec(node[1])]
+    good = [(state[i] == 1).astype(np.uint8) for i in range(2)]
+    hasmp = [(state[i] != 0).astype(np.uint8) for i in range(2)]
+    # SearchByBoW(KF, Frame)
+    nm, sz = take("<ii")
+    got = np.frombuffer(out, np.int32, sz, pos); pos += 4 * sz
+    on, om = orc.search_bow_kf_f(desc[0], good[0], ang[0], fv[0], desc[1], ang[1], fv[1], np.float32(ratio), ori)
+    assert nm == on and np.array_equal(got, om)
+    # SearchByBoW(KF, KF)
+    nm, sz = take("<ii")
+    got = np.frombuffer(out, np.int32, sz, pos); pos += 4 * sz
+    on, om = orc.search_bow_kf_kf(desc[0], good[0], ang[0], fv[0], desc[1], good[1], ang[1], fv[1], np.float32(ratio), ori)
+    assert nm == on and np.array_equal(got, om)
+    # SearchForTriangulation: epipole as the class computes it (double accumulation like cv::gemm, then float)
+    C2 = (R.astype(np.float64) @ Ow.astype(np.float64) + t.astype(np.float64)).astype(np.float32)
+    invz = np.float32(1.0) / C2[2]
+    ex = K[0] * C2[0] * invz + K[2]
+    ey = K[1] * C2[1] * invz + K[3]
+    nm, sz = take("<ii")
+    got = np.frombuffer(out, np.int32, 2 * sz, pos).reshape(-1, 2); pos += 8 * sz
+    on, op = orc.search_triangulation(desc[0], hasmp[0], ur[0], x[0], y[0], ang[0], fv[0], desc[1], hasmp[1], ur[1], x[1], y[1], ang[1],
+                                      oc[1], fv[1], F12, ex, ey, sf2, sig2, only_stereo, ori)
+    assert nm == on and np.array_equal(got, op)
+    d, lo, hi, hl = take("<iiii")
+    assert d == orc.descriptor_distance(desc[0][0], desc[1][0]) and (lo, hi, hl) == (50, 100, 30)
