@@ -249,15 +249,15 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     kp_per_frame = total_kp / nF
     pyr_px = 950532
-    # algorithmic bytes per frame of each stage (DESIGN.md "Kernels"): reads + writes that stage must do
+    # algorithmic bytes per frame of each stage (DESIGN.md "Kernels"): the reads + writes the stage cannot avoid
+    cand_per_frame = 7100
     stage_bytes = {
-        "pyramid": W * H + (pyr_px - W * H) + (pyr_px - W * H),         # read input, write levels>=1, read each level l-1 once... see DESIGN
-        "fast": pyr_px + 7100 * 8,                                      # read every level once + write ~7.1k candidates
-        "octree": 7100 * 8 + kp_per_frame * 8,
-        "blur": 2 * pyr_px,
-        "describe": kp_per_frame * (749 + 512 + 60),
+        "pyramid": W * H + W * H + 2 * (pyr_px - W * H),               # read input, write level 0, write levels >= 1, read each source level once
+        "fast": pyr_px + cand_per_frame * 8,                            # read every level once, write ~7.1k candidates (8 B)
+        "octree": cand_per_frame * 8 + kp_per_frame * 8,                # read candidates, write selected keypoints
+        "blur": 2 * pyr_px,                                             # read every level, write every blurred level
+        "describe": kp_per_frame * (749 + 37 * 37 + 60),                # per keypoint: 749-px disc + 37x37 blurred patch + 28 B + 32 B out
     }
-    stage_bytes["pyramid"] = W * H + 2 * (pyr_px - W * H) + W * H      # + level-0 copy write
     dom = max(stage_s, key=stage_s.get)
     launches_per_step = launches / args.steps
     passes = (nF + args.chunk - 1) // args.chunk
@@ -306,11 +306,12 @@ def main():
         q1 = min(q0 + nq, ndb)
         cnt = torch.zeros(((q1 - q0) * ndb + 1) // 2 * 2, dtype=torch.int16, device="cuda")
 
+        from orbslam_mapsave_b200.sharding import gather_match_tables
+
         def mstep():
             capi.check(capi.lib().orbm_allpairs_device(capi._p(d_db), ndb, per, q0, q1, 50, 0.75, capi._p(cnt), None, None, stream))
-            if world > 1:
-                out = [torch.empty_like(cnt) for _ in range(world)]
-                dist.all_gather(out, cnt)
+            if world > 1:       # the one exchange step of the path: assemble the match table on every rank (NCCL over NVLink)
+                gather_match_tables(cnt[: (q1 - q0) * ndb].view(q1 - q0, ndb), world * (q1 - q0), rank, world)
         for _ in range(3):
             mstep()
         msteps = max(2, args.steps)

@@ -128,7 +128,8 @@ def test_cpp_orbmatcher_matches_oracle(tmp_path, seed, ratio, ori, only_stereo):
     on, om = orc.search_bow_kf_kf(desc[0], good[0], ang[0], fv[0], desc[1], good[1], ang[1], fv[1], np.float32(ratio), ori)
     assert nm == on and np.array_equal(got, om)
     # SearchForTriangulation: epipole as the class computes it (double accumulation like cv::gemm, then float)
-    C2 = (R.astype(np.float64) @ Ow.astype(np.float64) + t.astype(np.float64)).astype(np.float32)
+    C2 = np.array([np.float32(float(R[i, 0]) * float(Ow[0]) + float(R[i, 1]) * float(Ow[1]) + float(R[i, 2]) * float(Ow[2]) + float(t[i]))
+                   for i in range(3)], np.float32)
     invz = np.float32(1.0) / C2[2]
     ex = K[0] * C2[0] * invz + K[2]
     ey = K[1] * C2[1] * invz + K[3]
