@@ -68,6 +68,14 @@ static const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1,
 // Is (x,y) a FAST-9 corner at threshold t: >=9 contiguous ring pixels all < v-t or all > v+t.
 static bool fast_is_corner(const u8* p, int stride, int t) {
     const int v = p[0];
+    {   // cheap necessary condition first (same idea as OpenCV's own pre-test; does not change the result): any 9 contiguous
+        // ring pixels contain at least one of each opposite pair, so both (0,8) and (4,12) must have a darker or a brighter member
+        const int lo = v - t, hi = v + t;
+        const int a = p[3 * stride], b = p[-3 * stride], c = p[3], d = p[-3];
+        const bool dark = (a < lo || b < lo) && (c < lo || d < lo);
+        const bool bright = (a > hi || b > hi) && (c > hi || d > hi);
+        if (!dark && !bright) return false;
+    }
     int ring[25];
     for (int k = 0; k < 16; k++) ring[k] = p[kRingDy[k] * stride + kRingDx[k]];
     for (int k = 16; k < 25; k++) ring[k] = ring[k - 16];
@@ -206,18 +214,25 @@ static void copy_make_border101(const u8* src, int w, int h, int sstride, u8* ds
 static void gaussian_blur7(const u8* src, int w, int h, int sstride, u8* dst, int dstride) {
     static const int K[7] = {18, 34, 48, 56, 48, 34, 18};
     std::vector<int> H((size_t)w * h);
-    for (int y = 0; y < h; y++)
+    std::vector<int> pad(w + 6);
+    for (int y = 0; y < h; y++) {
+        const u8* S = src + (size_t)y * sstride;
+        for (int x = -3; x < w + 3; x++) pad[x + 3] = S[reflect101(x, w)];       // REFLECT_101 once per row, not per tap
+        int* Hr = &H[(size_t)y * w];
         for (int x = 0; x < w; x++) {
-            int s = 0;
-            for (int i = -3; i <= 3; i++) s += K[i + 3] * src[(size_t)y * sstride + reflect101(x + i, w)];
-            H[(size_t)y * w + x] = s;
+            const int* p = &pad[x];
+            Hr[x] = K[0] * p[0] + K[1] * p[1] + K[2] * p[2] + K[3] * p[3] + K[4] * p[4] + K[5] * p[5] + K[6] * p[6];
         }
-    for (int y = 0; y < h; y++)
+    }
+    for (int y = 0; y < h; y++) {
+        const int* r[7];
+        for (int i = -3; i <= 3; i++) r[i + 3] = &H[(size_t)reflect101(y + i, h) * w];
+        u8* D = dst + (size_t)y * dstride;
         for (int x = 0; x < w; x++) {
-            int s = 0;
-            for (int i = -3; i <= 3; i++) s += K[i + 3] * H[(size_t)reflect101(y + i, h) * w + x];
-            dst[(size_t)y * dstride + x] = (u8)((s + 32768) >> 16);
+            const int s = K[0] * r[0][x] + K[1] * r[1][x] + K[2] * r[2][x] + K[3] * r[3][x] + K[4] * r[4][x] + K[5] * r[5][x] + K[6] * r[6][x];
+            D[x] = (u8)((s + 32768) >> 16);
         }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
