@@ -133,7 +133,7 @@ def run_reference(args, rank, world):
         total_s += s
     v = per_step * args.steps / total_s
     sample = f"{per_step} of the 4096 frames per step, {threads} host threads, one extractor instance per thread"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -141,7 +141,17 @@ def run_reference(args, rank, world):
                    "frames_per_step": per_step, "note": "CPU oracle port of src/ORBextractor.cc (reference needs OpenCV/Boost to compile)"},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+def _emit(obj):
+    """Print the ONE JSON line on the real stdout (fd 1 is pointed at stderr while the bench runs so that library
+    chatter such as 'NCCL version ...' cannot pollute it)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -340,7 +350,7 @@ def main():
                "sample": f"first {n_done} of the {nF} frames ({s:.1f} s), one oracle extractor per thread, frames dealt round-robin"}
 
     if rank == 0:
-        print(json.dumps({
+        _emit({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
@@ -350,7 +360,7 @@ def main():
                        "parallelism": f"frame-sharded x{world}, no data-path collective"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "matching": matching,
-        }))
+        })
     if world > 1:
         dist.destroy_process_group()
 
