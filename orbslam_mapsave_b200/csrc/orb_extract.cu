@@ -949,61 +949,77 @@ __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
 }
 
 #define DESC_WARPS 8
-#define DESC_PW 11            // aligned words per staged patch row: covers kx-18 .. kx+18 for any alignment
+#define DESC_PW 11            // aligned words per staged blurred-patch row: covers kx-18 .. kx+18 for any alignment
+#define DESC_AW 9             // aligned words per staged disc row: covers kx-15 .. kx+15 for any alignment
+// grid = (ceil(max selCap / DESC_WARPS), nlevels, frames): blockIdx.y is the level, so there is no slot -> level search.
 __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                               const u8* __restrict__ blur, const uint2* __restrict__ sel,
                                                               const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
                                                               u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
                                                               int* __restrict__ status) {
     __shared__ __align__(16) float s_pat[32 * 36];                 // pattern as float (no I2F in the tap loop); row stride 36: conflict-free LDS.128
-    __shared__ u32 s_patch[DESC_WARPS][37][DESC_PW];
-    for (int i = threadIdx.x; i < 1024; i += 32 * DESC_WARPS) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, f = blockIdx.y;
-    const int slot = blockIdx.x * DESC_WARPS + warp;
-    if (slot >= P.selTotal) return;
-    int l = 0;
-    while (l + 1 < P.nlevels && slot >= P.lv[l + 1].selOff) l++;
-    const LevelPlan& L = P.lv[l];
-    const int idx = slot - L.selOff;
-    const int* sc = selCount + f * P.nlevels;
-    int before = 0, total = 0;
-    for (int i = 0; i < P.nlevels; i++) { const int c = sc[i]; if (i < l) before += c; total += c; }
-    if (slot == 0 && lane == 0) {
+    __shared__ u32 s_patch[DESC_WARPS][37][DESC_PW];               // blurred 37x37 neighbourhood
+    __shared__ u32 s_disc[DESC_WARPS][31][DESC_AW];                // unblurred 31x31 neighbourhood (IC_Angle)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l = blockIdx.y, f = blockIdx.z;
+    const int idx = blockIdx.x * DESC_WARPS + warp;
+    // per-level counts of this frame: lane i holds level i; prefix by shuffles (level-major output order, :1098-1106)
+    const int myc = lane < P.nlevels ? selCount[f * P.nlevels + lane] : 0;
+    int inc = myc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int before = __shfl_sync(0xffffffffu, inc - myc, l), cnt = __shfl_sync(0xffffffffu, myc, l);
+    if (blockIdx.x == 0 && l == 0 && warp == 0 && lane == 0) {
         nOut[f] = total;
         if (total > cap) atomicOr(status, ORB_DEV_OUT_OVERFLOW);
     }
-    if (idx >= sc[l]) return;
+    if (blockIdx.x * DESC_WARPS >= cnt) return;                    // whole CTA beyond this level's keypoints
+    for (int i = threadIdx.x; i < 1024; i += 32 * DESC_WARPS) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
+    __syncthreads();
     const int pos = before + idx;
-    if (pos >= cap) return;
-    const uint2 k = sel[(size_t)f * P.selTotal + slot];
+    if (idx >= cnt || pos >= cap) return;
+    const LevelPlan& L = P.lv[l];
+    const uint2 k = sel[(size_t)f * P.selTotal + L.selOff + idx];
     const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
-    const int pitch = L.pitch;
+    const int pitchW = L.pitch >> 2;
     const size_t lofs = (size_t)f * P.frameBytes + L.off;
 
-    // ---- stage the 37x37 blurred patch (rows ky-18..ky+18) as aligned words: 2 rows per load instruction
-    const int pxs = kx - 18 + ORBX_OX, wx0 = pxs >> 2, shift = pxs & 3;
+    // ---- stage both neighbourhoods as aligned words, all loads in flight before the first store
+    const int pxs = kx - 18 + ORBX_OX, shift = pxs & 3;            // (kx-15+OX) has the same alignment: 18-15 = 3 ... handled below
+    const int axs = kx - 15 + ORBX_OX, ashift = axs & 3;
     {
-        const int half = lane >> 4, wi = lane & 15;
-        const u32* bsrc = reinterpret_cast<const u32*>(blur + lofs + (size_t)(ky - 18 + ORBX_OY) * pitch) + wx0;
-        if (wi < DESC_PW)
-            for (int r = half; r < 37; r += 2) s_patch[warp][r][wi] = __ldg(bsrc + (size_t)r * (pitch >> 2) + wi);
+        const u32* bsrc = reinterpret_cast<const u32*>(blur + lofs) + (ky - 18 + ORBX_OY) * pitchW + (pxs >> 2);
+        const u32* asrc = reinterpret_cast<const u32*>(pyr + lofs) + (ky - 15 + ORBX_OY) * pitchW + (axs >> 2);
+        u32 vb[13], va[9];
+#pragma unroll
+        for (int j = 0; j < 13; j++) {
+            const int i = lane + 32 * j, r = i / DESC_PW, w = i - r * DESC_PW;
+            vb[j] = i < 37 * DESC_PW ? __ldg(bsrc + r * pitchW + w) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int i = lane + 32 * j, r = i / DESC_AW, w = i - r * DESC_AW;
+            va[j] = i < 31 * DESC_AW ? __ldg(asrc + r * pitchW + w) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 13; j++) { const int i = lane + 32 * j; if (i < 37 * DESC_PW) (&s_patch[warp][0][0])[i] = vb[j]; }
+#pragma unroll
+        for (int j = 0; j < 9; j++) { const int i = lane + 32 * j; if (i < 31 * DESC_AW) (&s_disc[warp][0][0])[i] = va[j]; }
     }
+    __syncwarp();
 
-    // ---- IC_Angle (ORBextractor.cc:76-103): lane = column u (-15..15), loop over the rows of the disc (coalesced)
+    // ---- IC_Angle (ORBextractor.cc:76-103): lane = column u (-15..15); the disc is symmetric (:461-468 makes umax its own
+    // transpose), so column u spans rows |v| <= umax[|u|]
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-        // the disc is symmetric (ORBextractor.cc:461-468 makes umax its own transpose): column u spans rows |v| <= umax[|u|]
         const int u = lane - 15, vlim = P.umax[u < 0 ? -u : u];
-        const u8* cen = pyr + lofs + (size_t)(ky + ORBX_OY) * pitch + kx + ORBX_OX + u;
+        const u8* cen = reinterpret_cast<const u8*>(&s_disc[warp][15][0]) + 15 + ashift + u;
         int colsum = 0;
 #pragma unroll
         for (int v = -15; v <= 15; v++) {
-            if ((v < 0 ? -v : v) <= vlim) {
-                const int I = cen[v * pitch];
-                colsum += I;
-                m01 += v * I;
-            }
+            const int I = ((v < 0 ? -v : v) <= vlim) ? (int)cen[v * (DESC_AW * 4)] : 0;
+            colsum += I;
+            m01 += v * I;
         }
         m10 = u * colsum;
     }
@@ -1018,7 +1034,6 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
     if (lane == 0) cs = (float)cos((double)ang);
     else if (lane == 1) cs = (float)sin((double)ang);
     const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
-    __syncwarp();
     const u8* center = reinterpret_cast<const u8*>(&s_patch[warp][18][0]) + 18 + shift;
     const float4* pat = reinterpret_cast<const float4*>(s_pat + lane * 36);
     u32 val = 0;
@@ -1437,7 +1452,9 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         ex->launches++;
     }
     if (stages & ORBX_STAGE_DESCRIBE) {
-        dim3 g(orb_div_up(P.selTotal, DESC_WARPS), nf);
+        int maxSel = 1;
+        for (int l = 0; l < nl; l++) maxSel = std::max(maxSel, P.lv[l].selCap);
+        dim3 g(orb_div_up(maxSel, DESC_WARPS), nl, nf);
         k_describe<<<g, 32 * DESC_WARPS, 0, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc, d_n, cap, ex->d_status);
         ex->launches++;
     }
