@@ -430,22 +430,18 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
         const int f = it / nCells, ci = it - f * nCells;
         const uint4 ce = __ldg(cells + ci);
         const u32 bar = b ? bar1 : bar0;
+        (void)bar1;
         mbar_expect_tx(bar, boxBytes);
         // TMA needs the box start 16-byte aligned in the innermost dimension: load from the aligned column, keep the lead
         tma_load_3d(smem_u32(wbase + b * P.fwTileBytes), maps + ((ce.y >> 16) & 0xFF), ((int)(ce.x & 0xFFFF) + ORBX_OX) & ~15,
                     (int)(ce.x >> 16) + ORBX_OY, f, bar);
     };
     if (lane == 0) issue(item, 0);
-    u32 ph0 = 0, ph1 = 0;
-    int buf = 0;
+    u32 ph0 = 0;
     const int t = P.minTh, hiT = 256 + t, loT = 256 - t;
     const u32 lt = (1u << lane) - 1;
 
-    for (; item < nItems; item += Wt, buf ^= 1) {
-        if (lane == 0 && item + Wt < nItems) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // our generic reads of that buffer are done (syncwarp below)
-            issue(item + Wt, buf ^ 1);
-        }
+    for (; item < nItems; item += Wt) {
         const int f = item / nCells, cidx = item - f * nCells;
         const uint4 ce = __ldg(cells + cidx);
         const int iniX = (int)(ce.x & 0xFFFF), iniY = (int)(ce.x >> 16);
@@ -453,9 +449,10 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
         const int dw = tw - 6, dh = th - 6;
         // score map: pixel (px, py) at byte (py + 1) * SP + px + 2; zero it while the tile is in flight
         for (int i = lane; i < (((dh + 2) * SP) >> 2); i += 32) reinterpret_cast<u32*>(score)[i] = 0;
-        if (buf) { mbar_wait(bar1, ph1); ph1 ^= 1; } else { mbar_wait(bar0, ph0); ph0 ^= 1; }
+        mbar_wait(bar0, ph0);
+        ph0 ^= 1;
         __syncwarp();
-        const u8* tile = wbase + buf * P.fwTileBytes;
+        const u8* tile = wbase;
 
         // ---- phase A (domain pixel 0 sits at tile (X0, 3); pairs are aligned to even tile x)
         const int X0 = ((iniX + ORBX_OX) & 15) + 3;
@@ -540,6 +537,11 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
             }
         }
         __syncwarp();
+        // the tile is no longer needed: fetch the next cell's tile now, it lands while NMS / emission / score clearing run
+        if (lane == 0 && item + Wt < nItems) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // order our generic reads before the async-proxy write
+            issue(item + Wt, 0);
+        }
 
         // ---- 3x3 NMS over the corners; survivors compacted in place again; then the threshold retry and emission
         int nKeep = 0, nIni = 0;
@@ -1257,7 +1259,7 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         const int boxW = (int)orb_align_up(maxCW + 6 + 15, 16), boxH = maxCH + 6;   // + up to 15 lead bytes (16-byte aligned box start)
         P.fwBoxW = boxW; P.fwBoxH = boxH;
         P.fwTileBytes = (int)orb_align_up((size_t)boxW * boxH, 128);
-        P.fwScoreOff = 2 * P.fwTileBytes;
+        P.fwScoreOff = P.fwTileBytes;                                 // one tile buffer: more warps per SM beat double buffering here
         P.fwPlistOff = P.fwScoreOff + (int)orb_align_up((size_t)P.scorePitch * P.scoreRows, 16);
         P.fwBarOff = P.fwPlistOff + (int)orb_align_up((size_t)(maxCW + 2) * maxCH * 2, 16);
         P.fwStride = (int)orb_align_up((size_t)P.fwBarOff + 16, 128);
