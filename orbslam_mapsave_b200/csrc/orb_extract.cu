@@ -461,14 +461,16 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
             const int off = X0 & 1, npr = (off + dw + 1) >> 1, ntask = npr * dh;
             const u32 inv = 0xFFFFFFFFu / (u32)npr + 1;
             const u8* cE = tile + 3 * BW + (X0 & ~1);
+            const u32 C1 = (u32)(0x8000 - (hiT + 1)) * 0x00010001u, C2 = (u32)(0x8000 + loT - 1) * 0x00010001u;
             for (int task0 = 0; task0 < ntask; task0 += 32) {
                 const int task = task0 + lane;
-                bool pass0 = false, pass1 = false;
-                int row = 0, px0 = 0;
+                u32 fl = 0;                                            // bit 15 / bit 31: first / second pixel of the pair passes
+                int ent = 0;
                 if (task < ntask) {
-                    row = npr == 1 ? task : (int)__umulhi((u32)task, inv);   // (inv overflows for npr == 1)
+                    const int row = npr == 1 ? task : (int)__umulhi((u32)task, inv);   // (inv overflows for npr == 1)
                     const int p = task - row * npr;
-                    px0 = 2 * p - off;
+                    const int px0 = 2 * p - off;
+                    ent = (row << 8) + px0;
                     const u8* pe = cE + row * BW + 2 * p;
 #define LD2(o) __byte_perm((u32) * reinterpret_cast<const u16*>(pe + (o)), 0, 0x4140)
                     const u32 vb = LD2(0) + 0x01000100u;
@@ -479,15 +481,14 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                     const u32 md = min3x2(__vmaxu2(d0, d8), __vmaxu2(d2, d10), __vmaxu2(d6, d14));    // dark arc possible iff > 256+t
                     const u32 mb = max3x2(__vminu2(d0, d8), __vminu2(d2, d10), __vminu2(d6, d14));    // bright arc possible iff < 256-t
                     // bit 15 of each half: md >= hiT+1  |  mb <= loT-1   (halves are 9-bit values: no carries between them)
-                    const u32 C1 = (u32)(0x8000 - (hiT + 1)) * 0x00010001u, C2 = (u32)(0x8000 + loT - 1) * 0x00010001u;
-                    const u32 fl = ((md + C1) | (C2 - mb)) & 0x80008000u;
-                    pass0 = (fl & 0x8000u) && px0 >= 0;
-                    pass1 = (fl & 0x80000000u) && px0 + 1 < dw;
+                    fl = ((md + C1) | (C2 - mb)) & 0x80008000u;
+                    if (px0 < 0) fl &= 0xFFFF0000u;                   // first pixel left of the domain
+                    if (px0 + 1 >= dw) fl &= 0x0000FFFFu;             // second pixel right of the domain
                 }
-                const u32 b0 = __ballot_sync(0xffffffffu, pass0), b1 = __ballot_sync(0xffffffffu, pass1);
+                const u32 b0 = __ballot_sync(0xffffffffu, fl & 0x8000u), b1 = __ballot_sync(0xffffffffu, fl & 0x80000000u);
                 const int n0 = __popc(b0);
-                if (pass0) plist[nl + __popc(b0 & lt)] = (u16)((row << 8) | px0);
-                if (pass1) plist[nl + n0 + __popc(b1 & lt)] = (u16)((row << 8) | (px0 + 1));
+                if (fl & 0x8000u) plist[nl + __popc(b0 & lt)] = (u16)ent;
+                if (fl & 0x80000000u) plist[nl + n0 + __popc(b1 & lt)] = (u16)(ent + 1);
                 nl += n0 + __popc(b1);
             }
         }
