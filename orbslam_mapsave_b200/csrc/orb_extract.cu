@@ -872,11 +872,13 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
 // =====================================================================================================
 #define BL_TW 128
 #define BL_TH 32
-// All levels in one launch: blockIdx.x walks the per-level tile lists (Plan::blurTileBase).  Horizontal pass: the 7 taps of
-// an output are two IDP4A over byte windows cut from three aligned words with funnel shifts (no byte unpacking);
-// results stay exact (<= 65280) and are kept as u32 x 4 in shared memory; vertical pass: 7 x LDS.128, symmetric taps folded.
+// All levels in one launch: blockIdx.x walks the per-level tile lists (Plan::blurTileBase).
+// Horizontal pass: the 7 taps of an output are two IDP4A over byte windows cut from three aligned words with funnel shifts (no
+// byte unpacking); a thread does two vertically adjacent rows and stores their exact results (<= 65280) packed as u16 pairs.
+// Vertical pass: with rows paired that way the 7 vertical taps of an output are four IDP2A (tap pairs (18,34)(48,56)(48,34)(18,0)
+// for even rows, (0,18)(34,48)(56,48)(34,18) for odd rows) on four LDS.128 shared by the two outputs of a thread.
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
-    __shared__ uint4 s_h[BL_TH + 6][BL_TW / 4];
+    __shared__ uint4 s_p[(BL_TH + 6) / 2][BL_TW / 4];                 // [row pair][4-column group]: h(row 2j) | h(row 2j+1) << 16
     int level = 0;
     while (level + 1 < P.nlevels && (int)blockIdx.x >= P.blurTileBase[level + 1]) level++;
     const LevelPlan& L = P.lv[level];
@@ -885,39 +887,48 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, co
     const int ty = t / tilesX, tx = t - ty * tilesX;
     const int x0 = tx * BL_TW, y0 = ty * BL_TH, f = blockIdx.y;
     const int tid = threadIdx.x;
-    const u8* src = pyr + (size_t)f * P.frameBytes + L.off;
-    const int wordsPerRow = L.pitch >> 2;
+    const int pitchW = L.pitch >> 2;
+    const u32* src = reinterpret_cast<const u32*>(pyr + (size_t)f * P.frameBytes + L.off) + (y0 - 3 + ORBX_OY) * pitchW + ((x0 + ORBX_OX) >> 2);
     const u32 K1 = 18u | (34u << 8) | (48u << 16) | (56u << 24);      // taps for x-3, x-2, x-1, x
     const u32 K2 = 48u | (34u << 8) | (18u << 16);                    // taps for x+1, x+2, x+3
-    const int rowsNeeded = min(BL_TH, L.h - y0) + 6;
-    for (int i = tid; i < rowsNeeded * (BL_TW / 4); i += 256) {
-        const int r = i >> 5, wx = i & 31;
-        const int by = y0 - 3 + r + ORBX_OY, bwx = ((x0 + ORBX_OX) >> 2) + wx;
-        uint4 h = make_uint4(0, 0, 0, 0);
-        if (bwx + 1 < wordsPerRow) {
-            const u32* rp = reinterpret_cast<const u32*>(src + (size_t)by * L.pitch) + bwx;
-            const u32 a = __ldg(rp - 1), b = __ldg(rp), c = __ldg(rp + 1);
-            h.x = __dp4a(__funnelshift_r(a, b, 8), K1, __dp4a(__funnelshift_r(b, c, 8), K2, 0u));
-            h.y = __dp4a(__funnelshift_r(a, b, 16), K1, __dp4a(__funnelshift_r(b, c, 16), K2, 0u));
-            h.z = __dp4a(__funnelshift_r(a, b, 24), K1, __dp4a(__funnelshift_r(b, c, 24), K2, 0u));
-            h.w = __dp4a(b, K1, __dp4a(c, K2, 0u));
-        }
-        s_h[r][wx] = h;
+    const int rows = min(BL_TH, L.h - y0);                            // output rows of this tile
+    const int pairsNeeded = (rows + 6 + 1) >> 1;
+    const int wcols = min(BL_TW / 4, (L.w - x0 + 3) >> 2);            // 4-column groups that hold image pixels
+    for (int i = tid; i < pairsNeeded * (BL_TW / 4); i += 256) {
+        const int j = i >> 5, wx = i & 31;
+        if (wx >= wcols) continue;
+        const u32* rp = src + (2 * j) * pitchW + wx;
+        const u32 a0 = __ldg(rp - 1), b0 = __ldg(rp), c0 = __ldg(rp + 1);
+        const u32 a1 = __ldg(rp + pitchW - 1), b1 = __ldg(rp + pitchW), c1 = __ldg(rp + pitchW + 1);
+        uint4 h;
+        h.x = __dp4a(__funnelshift_r(a0, b0, 8), K1, __dp4a(__funnelshift_r(b0, c0, 8), K2, 0u)) |
+              (__dp4a(__funnelshift_r(a1, b1, 8), K1, __dp4a(__funnelshift_r(b1, c1, 8), K2, 0u)) << 16);
+        h.y = __dp4a(__funnelshift_r(a0, b0, 16), K1, __dp4a(__funnelshift_r(b0, c0, 16), K2, 0u)) |
+              (__dp4a(__funnelshift_r(a1, b1, 16), K1, __dp4a(__funnelshift_r(b1, c1, 16), K2, 0u)) << 16);
+        h.z = __dp4a(__funnelshift_r(a0, b0, 24), K1, __dp4a(__funnelshift_r(b0, c0, 24), K2, 0u)) |
+              (__dp4a(__funnelshift_r(a1, b1, 24), K1, __dp4a(__funnelshift_r(b1, c1, 24), K2, 0u)) << 16);
+        h.w = __dp4a(b0, K1, __dp4a(c0, K2, 0u)) | (__dp4a(b1, K1, __dp4a(c1, K2, 0u)) << 16);
+        s_p[j][wx] = h;
     }
     __syncthreads();
-    u8* dst = blur + (size_t)f * P.frameBytes + L.off;
-    for (int i = tid; i < BL_TH * (BL_TW / 4); i += 256) {
-        const int r = i >> 5, wx = i & 31;
-        const int x = x0 + 4 * wx, y = y0 + r;
-        if (x >= L.w || y >= L.h) continue;
-        const uint4 h0 = s_h[r][wx], h1 = s_h[r + 1][wx], h2 = s_h[r + 2][wx], h3 = s_h[r + 3][wx];
-        const uint4 h4 = s_h[r + 4][wx], h5 = s_h[r + 5][wx], h6 = s_h[r + 6][wx];
-        const u32 v0 = 18u * (h0.x + h6.x) + 34u * (h1.x + h5.x) + 48u * (h2.x + h4.x) + 56u * h3.x + 32768u;
-        const u32 v1 = 18u * (h0.y + h6.y) + 34u * (h1.y + h5.y) + 48u * (h2.y + h4.y) + 56u * h3.y + 32768u;
-        const u32 v2 = 18u * (h0.z + h6.z) + 34u * (h1.z + h5.z) + 48u * (h2.z + h4.z) + 56u * h3.z + 32768u;
-        const u32 v3 = 18u * (h0.w + h6.w) + 34u * (h1.w + h5.w) + 48u * (h2.w + h4.w) + 56u * h3.w + 32768u;
-        const u32 o = (v0 >> 16) | ((v1 >> 16) << 8) | ((v2 >> 16) << 16) | ((v3 >> 16) << 24);
-        *reinterpret_cast<u32*>(dst + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = o;
+    u8* dst = blur + (size_t)f * P.frameBytes + L.off + (size_t)(y0 + ORBX_OY) * L.pitch + x0 + ORBX_OX;
+    // tap pairs as the two low bytes of the IDP2A weight operand
+    const u32 E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;          // even output row
+    const u32 O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);     // odd output row
+    for (int i = tid; i < (BL_TH / 2) * (BL_TW / 4); i += 256) {
+        const int j = i >> 5, wx = i & 31;                             // output rows 2j and 2j+1 use row pairs j .. j+3
+        if (wx >= wcols || 2 * j >= rows) continue;
+        const uint4 p0 = s_p[j][wx], p1 = s_p[j + 1][wx], p2 = s_p[j + 2][wx], p3 = s_p[j + 3][wx];
+#define VSUM(c, W0, W1, W2, W3) __dp2a_lo(p0.c, W0, __dp2a_lo(p1.c, W1, __dp2a_lo(p2.c, W2, __dp2a_lo(p3.c, W3, 32768u))))
+        const u32 e = (VSUM(x, E0, E1, E2, E3) >> 16) | ((VSUM(y, E0, E1, E2, E3) >> 16) << 8) |
+                      ((VSUM(z, E0, E1, E2, E3) >> 16) << 16) | ((VSUM(w, E0, E1, E2, E3) >> 16) << 24);
+        *reinterpret_cast<u32*>(dst + (size_t)(2 * j) * L.pitch + 4 * wx) = e;
+        if (2 * j + 1 < rows) {
+            const u32 o = (VSUM(x, O0, O1, O2, O3) >> 16) | ((VSUM(y, O0, O1, O2, O3) >> 16) << 8) |
+                          ((VSUM(z, O0, O1, O2, O3) >> 16) << 16) | ((VSUM(w, O0, O1, O2, O3) >> 16) << 24);
+            *reinterpret_cast<u32*>(dst + (size_t)(2 * j + 1) * L.pitch + 4 * wx) = o;
+        }
+#undef VSUM
     }
 }
 
