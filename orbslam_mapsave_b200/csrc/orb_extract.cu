@@ -92,6 +92,27 @@ __global__ void __launch_bounds__(256) k_level0(const __grid_constant__ Plan P, 
     *reinterpret_cast<u32*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
 }
 
+// 16 pixels per thread with 128-bit loads / stores when the frame width and base pointers are 16-byte aligned (VGA, 720p, 4K ...)
+__global__ void __launch_bounds__(256) k_level0_v16(const __grid_constant__ Plan P, const u8* __restrict__ images,
+                                                    const u8* __restrict__ masks, u8* __restrict__ pyr) {
+    const LevelPlan& L = P.lv[0];
+    const int x = (blockIdx.x * 64 + threadIdx.x) * 16, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
+    if (x >= L.w || y >= L.h) return;
+    const size_t fo = (size_t)f * P.width * P.height + (size_t)y * P.width + x;
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(images + fo));
+    if (masks) {
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(masks + fo));
+        // per byte: keep the pixel where the mask byte is non-zero (0x80 trick: (m | (m & 0x7f..) + 0x7f..) & 0x80.. marks non-zero bytes)
+        auto keep = [](u32 px, u32 mk) {
+            const u32 nz = ((mk & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | mk;       // bit 7 of each byte set iff that mask byte != 0
+            const u32 full = ((nz & 0x80808080u) >> 7) * 0xFFu;            // 0xFF in the bytes to keep
+            return px & full;
+        };
+        v.x = keep(v.x, m.x); v.y = keep(v.y, m.y); v.z = keep(v.z, m.z); v.w = keep(v.w, m.w);
+    }
+    *reinterpret_cast<uint4*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = v;
+}
+
 // Generic gather form (any scale factor): one thread = 4 adjacent ROI pixels, 4 byte gathers each.
 __global__ void __launch_bounds__(256) k_resize_generic(const __grid_constant__ Plan P, int level, u8* __restrict__ pyr,
                                                         const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab) {
@@ -1417,8 +1438,14 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     if (stages & ORBX_STAGE_PYRAMID) {
         {
             const LevelPlan& L = P.lv[0];
-            dim3 g(orb_div_up(L.w, 256), orb_div_up(L.h, 4), nf), b(64, 4);
-            k_level0<<<g, b, 0, st>>>(P, d_images, d_masks, ex->d_pyr);
+            const bool v16 = (L.w % 16 == 0) && ((uintptr_t)d_images % 16 == 0) && (!d_masks || (uintptr_t)d_masks % 16 == 0);
+            if (v16) {
+                dim3 g(orb_div_up(L.w, 1024), orb_div_up(L.h, 4), nf), b(64, 4);
+                k_level0_v16<<<g, b, 0, st>>>(P, d_images, d_masks, ex->d_pyr);
+            } else {
+                dim3 g(orb_div_up(L.w, 256), orb_div_up(L.h, 4), nf), b(64, 4);
+                k_level0<<<g, b, 0, st>>>(P, d_images, d_masks, ex->d_pyr);
+            }
             ex->launches++;
         }
         for (int l = 1; l < nl; l++) {
