@@ -173,3 +173,30 @@ def test_popc_peak_is_sane():
     v, clk = orb.popc_peak()
     print(f"POPC peak {v / 1e12:.3f} T/s at nominal {clk / 1e9:.3f} GHz -> {v / clk / 148:.2f} POPC/clk/SM")
     assert v > 1e11
+
+
+def test_config3_extract_then_match_consecutive_keyframes():
+    """BASELINE.json config 3: 1280x720, nFeatures=2000, 8 levels; top-2 + ratio matching between consecutive keyframes
+    (the second frame is a shifted, re-noised view of the same scene, so true matches exist).  GPU extraction + GPU matching
+    must reproduce the oracle's extraction + matching exactly."""
+    from orbslam_mapsave_b200.synth import synth
+    a = synth(1280, 720, 77)
+    rng = np.random.default_rng(5)
+    b = np.roll(a, (4, 7), axis=(0, 1))
+    b = np.clip(b.astype(np.int16) + rng.integers(-2, 3, b.shape), 0, 255).astype(np.uint8)
+    ex = orb.ORBextractor(2000, 1.2, 8, 20, 7, max_batch=2)
+    kp, desc, n = ex.extract_batch(np.stack([a, b]))
+    oex = orc.Extractor(2000, 1.2, 8, 20, 7)
+    (okp_a, od_a), (okp_b, od_b) = oex.extract(a), oex.extract(b)
+    assert n[0] == len(okp_a) and n[1] == len(okp_b)
+    da, db = desc[0, :n[0]], desc[1, :n[1]]
+    assert np.unpackbits(da ^ od_a).sum() <= 1e-4 * da.size * 8 and np.unpackbits(db ^ od_b).sum() <= 1e-4 * db.size * 8
+    bi, bd, sd = orb.ORBmatcher().hamming_top2(da, db)
+    obi, obd, osd = orc.hamming_top2(da, db)
+    assert np.array_equal(bi, obi) and np.array_equal(bd, obd) and np.array_equal(sd, osd)
+    good = (bd <= 50) & (bd.astype(np.float32) < np.float32(0.75) * sd.astype(np.float32))
+    # matched keypoints must agree with the known shift (x + 7, y + 4) at level-0 scale for the vast majority
+    ka, kb = kp[0, :n[0]][good], kp[1, :n[1]][bi[good]]
+    dx, dy = kb["x"] - ka["x"], kb["y"] - ka["y"]
+    ok = (np.abs(dx - 7) <= 2.5 * ka["size"] / 31) & (np.abs(dy - 4) <= 2.5 * ka["size"] / 31)
+    assert good.sum() > 300 and ok.mean() > 0.9, (int(good.sum()), float(ok.mean()))
