@@ -274,9 +274,11 @@ def main():
     dom_launches = {"pyramid": NLEVELS, "fast": 1, "octree": 1, "blur": 1, "describe": 1}[dom] * passes
     dom_launch_s = stage_s[dom] / dom_launches
     achieved = stage_bytes[dom] * nF / stage_s[dom] / 1e9
-    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast", "octree": "k_octree", "blur": "k_blur",
+    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast_tma", "octree": "k_octree", "blur": "k_blur",
                                            "describe": "k_describe"}[dom],
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1_final_all_kernels_ncu_full.md)
+                "traffic": ({"fast": 287.2e6, "describe": 561.1e6, "blur": 526.9e6, "octree": 15.7e6}.get(dom, 0) * args.chunk / 256) or None,
                 "peak_source": peak_src, "avg_launch_ms": dom_launch_s * 1e3, "algorithmic_bytes_per_frame": stage_bytes[dom],
                 "stage_ms_per_step": {k: v * 1e3 for k, v in stage_s.items()},
                 "step_hbm_frac": (B_FRAME * nF / (secs / args.steps) / 1e9) / hbm_peak,
