@@ -95,6 +95,9 @@ int orbx_check_status(orbx_extractor* ex);
  * bordered != 0 copies the (w+38)x(h+38) buffer with its REFLECT_101 border (src/ORBextractor.cc:1125-1132), else
  * the w x h image. */
 int orbx_get_pyramid_level(orbx_extractor* ex, int frame, int level, int bordered, uint8_t* dst, int dst_stride);
+/* All levels of frame `frame` in one call (one border launch, nlevels asynchronous copies, one synchronisation):
+ * dst[l] / dst_stride[l] as for orbx_get_pyramid_level.  This is what the C++ class uses to fill mvImagePyramid. */
+int orbx_get_pyramid(orbx_extractor* ex, int frame, int bordered, uint8_t* const* dst, const int* dst_stride);
 /* Parity/debug views of the last pass: the blurred level (src/ORBextractor.cc:1088-1089) and the FAST candidates of a
  * level in the reference's octree input order (:788-828).  *n_out receives the count (may exceed cap). */
 int orbx_get_blurred_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, int dst_stride);

@@ -24,7 +24,7 @@ TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
 SYMBOLS = [
     "orb_last_error", "orb_device_count",
     "orbx_create", "orbx_destroy", "orbx_tables", "orbx_level_size", "orbx_max_keypoints", "orbx_extract",
-    "orbx_extract_batch", "orbx_extract_batch_device", "orbx_check_status", "orbx_get_pyramid_level",
+    "orbx_extract_batch", "orbx_extract_batch_device", "orbx_check_status", "orbx_get_pyramid_level", "orbx_get_pyramid",
     "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device",
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
@@ -82,6 +82,8 @@ def lib():
     L.orbx_check_status.argtypes = [vp]
     L.orbx_get_pyramid_level.restype = i32
     L.orbx_get_pyramid_level.argtypes = [vp, i32, i32, i32, vp, i32]
+    L.orbx_get_pyramid.restype = i32
+    L.orbx_get_pyramid.argtypes = [vp, i32, i32, vp, vp]
     L.orbx_get_blurred_level.restype = i32
     L.orbx_get_blurred_level.argtypes = [vp, i32, i32, vp, i32]
     L.orbx_get_candidates.restype = i32

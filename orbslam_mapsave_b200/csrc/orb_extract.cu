@@ -1113,6 +1113,9 @@ struct orbx_extractor {
     orbx_keypoint* d_kp[2] = {nullptr, nullptr};
     int* d_n[2] = {nullptr, nullptr};
     int* h_n = nullptr;                    // pinned staging for the per-frame counts
+    int* h_status = nullptr;               // pinned mirror of the device status word
+    u8* h_stage = nullptr;                 // pinned staging for the latency path when the caller's buffers are pageable
+    size_t h_stage_cap = 0;
     size_t h_n_cap = 0;
     cudaStream_t sH2D = nullptr, sD2H = nullptr;
     cudaEvent_t evH2D[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evD2H[2] = {nullptr, nullptr};
@@ -1398,6 +1401,8 @@ extern "C" void orbx_destroy(orbx_extractor* ex) {
         if (ex->evD2H[i]) cudaEventDestroy(ex->evD2H[i]);
     }
     if (ex->h_n) cudaFreeHost(ex->h_n);
+    if (ex->h_status) cudaFreeHost(ex->h_status);
+    if (ex->h_stage) cudaFreeHost(ex->h_stage);
     if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
     if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
     cudaFree(ex->d_cand); cudaFree(ex->d_sel); cudaFree(ex->d_nodeOf); cudaFree(ex->d_candCount); cudaFree(ex->d_selCount);
@@ -1570,6 +1575,77 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
         ex->h_n_cap = n_frames;
     }
     const int ccap = std::min(cap, icap);             // keypoints copied back per frame (the rest of a row cannot be used)
+    if (!ex->h_status) ORB_CUDA_TRY(cudaMallocHost(&ex->h_status, sizeof(int)));
+    if (n_frames <= B) {
+        // ---- latency path (one device pass, e.g. the per-frame call of Frame::ExtractORB): a single stream, a single
+        // synchronisation; pageable caller buffers (cv::Mat, std::vector) go through one pinned staging block so that every copy
+        // is a true asynchronous DMA
+        cudaStream_t st = ex->stream;
+        auto pinned = [](const void* p) {
+            cudaPointerAttributes a;
+            if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+            return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+        };
+        const bool tight = (size_t)stride == (size_t)width && frame_stride == fpx;
+        const bool stageIn = !(tight && pinned(images)) && (size_t)n_frames * fpx <= (4u << 20);   // large frames: direct copy is cheaper
+        const bool stageOut = !(pinned(kp_out) && pinned(desc_out)) && (size_t)n_frames * icap <= 65536;
+        const size_t inBytes = (size_t)n_frames * fpx, kpBytes = (size_t)n_frames * icap * sizeof(orbx_keypoint), dBytes = (size_t)n_frames * icap * 32;
+        const size_t need = (stageIn ? orb_align_up(inBytes, 256) : 0) + (stageOut ? orb_align_up(kpBytes, 256) + dBytes : 0);
+        if (need > ex->h_stage_cap) {
+            if (ex->h_stage) ORB_CUDA_TRY(cudaFreeHost(ex->h_stage));
+            ex->h_stage = nullptr; ex->h_stage_cap = 0;
+            ORB_CUDA_TRY(cudaMallocHost(&ex->h_stage, need));
+            ex->h_stage_cap = need;
+        }
+        u8* hIn = ex->h_stage;
+        u8* hKp = ex->h_stage + (stageIn ? orb_align_up(inBytes, 256) : 0);
+        u8* hDesc = hKp + orb_align_up(kpBytes, 256);
+        if (stageIn) {
+            for (int f = 0; f < n_frames; f++)
+                for (int y = 0; y < height; y++)
+                    memcpy(hIn + f * fpx + (size_t)y * width, images + (size_t)f * frame_stride + (size_t)y * stride, width);
+            ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[0], hIn, inBytes, cudaMemcpyHostToDevice, st));
+        } else if (tight) {
+            ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[0], images, inBytes, cudaMemcpyHostToDevice, st));
+        } else {
+            for (int f = 0; f < n_frames; f++)
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in[0] + f * fpx, width, images + (size_t)f * frame_stride, stride, width, height,
+                                               cudaMemcpyHostToDevice, st));
+        }
+        if (masks)
+            for (int f = 0; f < n_frames; f++)
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_mask[0] + f * fpx, width, masks + (size_t)f * mask_frame_stride, mask_stride, width,
+                                               height, cudaMemcpyHostToDevice, st));
+        int rc = run_pass(ex, ex->d_in[0], masks ? ex->d_mask[0] : nullptr, n_frames, ex->d_kp[0], ex->d_desc[0], icap, ex->d_n[0],
+                          ORBX_STAGE_ALL, st);
+        if (rc != ORB_OK) return rc;
+        ORB_CUDA_TRY(cudaMemcpyAsync(ex->h_n, ex->d_n[0], n_frames * sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORB_CUDA_TRY(cudaMemcpyAsync(ex->h_status, ex->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (stageOut) {
+            ORB_CUDA_TRY(cudaMemcpyAsync(hKp, ex->d_kp[0], kpBytes, cudaMemcpyDeviceToHost, st));
+            ORB_CUDA_TRY(cudaMemcpyAsync(hDesc, ex->d_desc[0], dBytes, cudaMemcpyDeviceToHost, st));
+        } else {
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(kp_out, (size_t)cap * sizeof(orbx_keypoint), ex->d_kp[0], (size_t)icap * sizeof(orbx_keypoint),
+                                           (size_t)ccap * sizeof(orbx_keypoint), n_frames, cudaMemcpyDeviceToHost, st));
+            ORB_CUDA_TRY(cudaMemcpy2DAsync(desc_out, (size_t)cap * 32, ex->d_desc[0], (size_t)icap * 32, (size_t)ccap * 32, n_frames,
+                                           cudaMemcpyDeviceToHost, st));
+        }
+        ORB_CUDA_TRY(cudaStreamSynchronize(st));
+        const int sflags = *ex->h_status;
+        if (sflags) ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
+        ORB_REQUIRE(!(sflags & (ORB_DEV_CAND_OVERFLOW | ORB_DEV_NODE_OVERFLOW)), ORB_ERR_OVERFLOW,
+                    "FAST candidate buffer overflow (ORBX_CAND_PER_CELL=%d caps it; unset it to size for the worst case)", ex->candPerCell);
+        for (int f = 0; f < n_frames; f++) {
+            const int n = ex->h_n[f];
+            n_out[f] = n;
+            ORB_REQUIRE(n <= cap, ORB_ERR_CAPACITY, "frame %d has %d keypoints but cap is %d", f, n, cap);
+            if (stageOut && n > 0) {
+                memcpy(kp_out + (size_t)f * cap, hKp + (size_t)f * icap * sizeof(orbx_keypoint), (size_t)n * sizeof(orbx_keypoint));
+                memcpy(desc_out + (size_t)f * cap * 32, hDesc + (size_t)f * icap * 32, (size_t)n * 32);
+            }
+        }
+        return ORB_OK;
+    }
     int chunk = 0;
     for (int f0 = 0; f0 < n_frames; f0 += B, chunk++) {
         const int nf = std::min(B, n_frames - f0), sl = chunk & 1;
@@ -1648,6 +1724,43 @@ static int copy_level(orbx_extractor* ex, const u8* base, int frame, int level, 
 }
 extern "C" int orbx_get_pyramid_level(orbx_extractor* ex, int frame, int level, int bordered, uint8_t* dst, int dst_stride) {
     return copy_level(ex, ex ? ex->d_pyr : nullptr, frame, level, bordered, dst, dst_stride);
+}
+extern "C" int orbx_get_pyramid(orbx_extractor* ex, int frame, int bordered, uint8_t* const* dst, const int* dst_stride) {
+    ORB_REQUIRE(ex && dst && dst_stride && frame >= 0 && frame < ex->lastFrames, ORB_ERR_ARG, "bad frame");
+    std::lock_guard<std::mutex> lk(ex->mu);
+    ORB_CUDA_TRY(cudaSetDevice(ex->device));
+    const int nl = ex->nlevels, b = bordered ? 38 : 0;
+    if (bordered) {                  // full 19-px REFLECT_101 border of every level in one launch
+        dim3 g(8, nl, 1);
+        k_border<<<g, 256, 0, ex->stream>>>(ex->plan, ex->d_pyr, ORBX_EDGE, ORBX_EDGE, 0, frame);
+        ex->launches++;
+        ORB_CUDA_TRY(cudaGetLastError());
+    }
+    // device -> pinned staging (asynchronous DMA), one synchronisation, then plain row copies into the caller's (pageable) images
+    size_t total = 0;
+    for (int l = 0; l < nl; l++) total += orb_align_up((size_t)(ex->plan.lv[l].w + b) * (ex->plan.lv[l].h + b), 256);
+    if (total > ex->h_stage_cap) {
+        if (ex->h_stage) ORB_CUDA_TRY(cudaFreeHost(ex->h_stage));
+        ex->h_stage = nullptr; ex->h_stage_cap = 0;
+        ORB_CUDA_TRY(cudaMallocHost(&ex->h_stage, total));
+        ex->h_stage_cap = total;
+    }
+    size_t o = 0;
+    for (int l = 0; l < nl; l++) {
+        const LevelPlan& L = ex->plan.lv[l];
+        ORB_REQUIRE(dst[l] && dst_stride[l] >= L.w + b, ORB_ERR_ARG, "dst_stride too small");
+        const u8* src = ex->d_pyr + (size_t)frame * ex->plan.frameBytes + L.off + (bordered ? (size_t)(ORBX_OX - ORBX_EDGE) : (size_t)ORBX_OY * L.pitch + ORBX_OX);
+        ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->h_stage + o, L.w + b, src, L.pitch, L.w + b, L.h + b, cudaMemcpyDeviceToHost, ex->stream));
+        o += orb_align_up((size_t)(L.w + b) * (L.h + b), 256);
+    }
+    ORB_CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    o = 0;
+    for (int l = 0; l < nl; l++) {
+        const LevelPlan& L = ex->plan.lv[l];
+        for (int y = 0; y < L.h + b; y++) memcpy(dst[l] + (size_t)y * dst_stride[l], ex->h_stage + o + (size_t)y * (L.w + b), L.w + b);
+        o += orb_align_up((size_t)(L.w + b) * (L.h + b), 256);
+    }
+    return ORB_OK;
 }
 extern "C" int orbx_get_blurred_level(orbx_extractor* ex, int frame, int level, uint8_t* dst, int dst_stride) {
     return copy_level(ex, ex ? ex->d_blur : nullptr, frame, level, 0, dst, dst_stride);

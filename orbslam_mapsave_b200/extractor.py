@@ -108,7 +108,7 @@ class ORBextractor:
         capi.check(capi.lib().orbx_extract(self._h, capi._p(image), w, h, image.strides[0], capi._p(m),
                                            m.strides[0] if m is not None else 0, capi._p(kp), capi._p(desc), cap, C.byref(n)))
         if download_pyramid:
-            self.mvImagePyramid = [self.pyramid_level(0, l) for l in range(self.nlevels)]
+            self.mvImagePyramid = self.pyramid(0)
         return kp[:n.value].copy(), desc[:n.value].copy()
 
     def extract_batch(self, images, masks=None):
@@ -146,6 +146,15 @@ class ORBextractor:
         out = np.zeros((h + 38, w + 38) if bordered else (h, w), np.uint8)
         capi.check(capi.lib().orbx_get_pyramid_level(self._h, frame, level, int(bordered), capi._p(out), out.shape[1]))
         return out
+
+    def pyramid(self, frame, bordered=False):
+        """All levels of one frame with a single call (what the C++ class uses for mvImagePyramid)."""
+        b = 38 if bordered else 0
+        outs = [np.zeros((h + b, w + b), np.uint8) for (w, h) in (self.level_size(l) for l in range(self.nlevels))]
+        ptrs = (C.c_void_p * self.nlevels)(*[o.ctypes.data for o in outs])
+        strides = (C.c_int * self.nlevels)(*[o.shape[1] for o in outs])
+        capi.check(capi.lib().orbx_get_pyramid(self._h, frame, int(bordered), ptrs, strides))
+        return outs
 
     def blurred_level(self, frame, level):
         w, h = self.level_size(level)

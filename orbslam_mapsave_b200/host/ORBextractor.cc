@@ -68,17 +68,23 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::
 
     if (mbDownloadPyramid) {                                     // reference :1110-1135: ROI views inside (w+38)x(h+38) buffers
         mvImagePyramid.resize(nlevels);
+        std::vector<cv::Mat> whole(nlevels);
+        std::vector<uint8_t*> ptrs(nlevels);
+        std::vector<int> strides(nlevels), ws(nlevels), hs(nlevels);
         for (int l = 0; l < nlevels; l++) {
-            int w = 0, h = 0;
-            orbx_level_size(mHandle, l, &w, &h);
-            cv::Mat whole(h + 38, w + 38, CV_8U);
-            if (orbx_get_pyramid_level(mHandle, 0, l, 1, whole.data, (int)whole.step) != ORB_OK) break;
-#if defined(OPENCV_CORE_HPP) || defined(__OPENCV_CORE_HPP__)
-            mvImagePyramid[l] = whole(cv::Rect(19, 19, w, h));
-#else
-            mvImagePyramid[l] = whole.roi(19, 19, w, h);
-#endif
+            orbx_level_size(mHandle, l, &ws[l], &hs[l]);
+            whole[l] = cv::Mat(hs[l] + 38, ws[l] + 38, CV_8U);
+            ptrs[l] = whole[l].data;
+            strides[l] = (int)whole[l].step;
         }
+        if (orbx_get_pyramid(mHandle, 0, 1, ptrs.data(), strides.data()) == ORB_OK)
+            for (int l = 0; l < nlevels; l++) {
+#if defined(OPENCV_CORE_HPP) || defined(__OPENCV_CORE_HPP__)
+                mvImagePyramid[l] = whole[l](cv::Rect(19, 19, ws[l], hs[l]));
+#else
+                mvImagePyramid[l] = whole[l].roi(19, 19, ws[l], hs[l]);
+#endif
+            }
     }
 }
 
