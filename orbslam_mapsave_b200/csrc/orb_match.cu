@@ -97,6 +97,42 @@ __global__ void __launch_bounds__(T2_THREADS) k_top2(const u8* __restrict__ q, c
     }
 }
 
+// Latency form for ONE small problem (e.g. 2000 x 2000 between consecutive keyframes): the database is cut into `nslice` slices
+// so that the grid fills the GPU; each CTA keeps the packed top-2 keys of its slice, a second tiny kernel merges them.
+__global__ void __launch_bounds__(T2_THREADS) k_top2_slice(const u8* __restrict__ q, int nq, const u8* __restrict__ db, int nd,
+                                                           int slice_len, u32* __restrict__ part /*[nslice][2][nq]*/) {
+    __shared__ uint4 s_db[T2_DBT * 2];
+    const int tid = threadIdx.x, qi0 = blockIdx.x * T2_THREADS + tid, sl = blockIdx.y;
+    const int j_begin = sl * slice_len, j_end = min(nd, j_begin + slice_len);
+    u32 qr[1][8], best[1] = {KEY_NONE}, sec[1] = {KEY_NONE};
+    load_desc(q + (size_t)min(qi0, nq - 1) * 32, qr[0]);
+    for (int j0 = j_begin; j0 < j_end; j0 += T2_DBT) {
+        const int cnt = min(T2_DBT, j_end - j0);
+        __syncthreads();
+        for (int i = tid; i < cnt * 2; i += T2_THREADS) s_db[i] = __ldg(reinterpret_cast<const uint4*>(db + (size_t)j0 * 32) + i);
+        __syncthreads();
+        top2_scan_tile<1>(s_db, cnt, j0, qr, best, sec);
+    }
+    if (qi0 < nq) {
+        part[((size_t)sl * 2 + 0) * nq + qi0] = best[0];
+        part[((size_t)sl * 2 + 1) * nq + qi0] = sec[0];
+    }
+}
+__global__ void k_top2_merge(const u32* __restrict__ part, int nq, int nslice, int* __restrict__ best_idx, int* __restrict__ best_dist,
+                             int* __restrict__ second_dist) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    u32 best = KEY_NONE, sec = KEY_NONE;
+    for (int sl = 0; sl < nslice; sl++) {          // keys are unique (index in the low bits), so the packed top-2 merge is exact
+        const u32 b = part[((size_t)sl * 2 + 0) * nq + qi], s2 = part[((size_t)sl * 2 + 1) * nq + qi];
+        sec = min(min(sec, s2), max(best, b));
+        best = min(best, b);
+    }
+    best_idx[qi] = best == KEY_NONE ? -1 : (int)(best & KEY_IDX_MASK);
+    best_dist[qi] = key_dist(best);
+    second_dist[qi] = key_dist(sec);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // All-pairs keyframe matching (config 4): CTA = (query tile of keyframe q, database keyframe k).
 // count[q][k] += #queries passing  best <= th_low && best < ratio * second ; optional global nearest keyframe.
@@ -195,153 +231,161 @@ __global__ void k_three_maxima(const int* histo, int L, int* ind) {
     ind[0] = a; ind[1] = b; ind[2] = c;
 }
 
-// SearchByBoW, both overloads.  One CTA per call; one warp per shared vocabulary node (the greedy claim
-// `vpMapPointMatches[realIdxF]` / `vbMatched2[idx2]` only couples features of the same node, and a feature belongs to
-// exactly one node, so nodes are independent); inside a node the side-1 features are walked in order and the side-2
-// scan is spread over the lanes with a (distance, position) top-2 warp reduction.
+// SearchByBoW, both overloads.  Two launches per call: (1) one WARP per shared vocabulary node, spread over as many CTAs as
+// there are nodes / 4 (the greedy claim `vpMapPointMatches[realIdxF]` / `vbMatched2[idx2]` only couples features of the same
+// node, and a feature belongs to exactly one node, so nodes are independent); inside a node the side-1 features are walked in
+// order and the side-2 scan is spread over the lanes with a (distance, position) top-2 warp reduction; (2) one CTA applies the
+// rotation-histogram cull (ComputeThreeMaxima) and counts.
 //   KFKF = false: SearchByBoW(KF, Frame)  -> out[j in side 2] = idx1, accept best <= TH_LOW        (:231)
 //   KFKF = true : SearchByBoW(KF1, KF2)   -> out[i in side 1] = idx2, accept best <  TH_LOW, side-2 flag filter (:601)
+// Scratch (zeroed by the host before the launch): taken2[B.n], hist[HISTO_LENGTH], nmatch[1]; out[] preset to -1.
+#define SB_WARPS 4
 template <bool KFKF>
-__global__ void __launch_bounds__(256) k_search_bow(DevView A, DevView B, float nnratio, int checkOri, int* __restrict__ out,
-                                                    int* __restrict__ taken2, int* __restrict__ binOf, int* __restrict__ nmatches) {
-    __shared__ int s_hist[ORBM_HISTO_LENGTH];
-    __shared__ int s_n, s_ind[3];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
-    if (tid == 0) s_n = 0;
-    const int nOut = KFKF ? A.n : B.n;
-    for (int i = tid; i < nOut; i += blockDim.x) out[i] = -1;
-    for (int i = tid; i < B.n; i += blockDim.x) taken2[i] = 0;
-    __syncthreads();
-    for (int a = warp; a < A.nn; a += nwarps) {
-        const int b = find_node(B.ids, B.nn, A.ids[a]);
-        if (b < 0) continue;
-        const int o2 = B.off[b], c2 = B.off[b + 1] - o2;
-        for (int i1 = A.off[a]; i1 < A.off[a + 1]; i1++) {
-            const int idx1 = A.feat[i1];
-            if (!A.flag[idx1]) continue;
-            u32 d1[8];
-            load_desc(A.desc + (size_t)idx1 * 32, d1);
-            u32 best = KEY_NONE, sec = KEY_NONE;
-            for (int j = lane; j < c2; j += 32) {
-                const int idx2 = B.feat[o2 + j];
-                if (taken2[idx2]) continue;
-                if (KFKF && !B.flag[idx2]) continue;
-                u32 d2[8];
-                load_desc(B.desc + (size_t)idx2 * 32, d2);
-                const u32 key = ((u32)ham256(d1, d2) << KEY_SHIFT) | (u32)j;
-                sec = min(sec, max(best, key));
-                best = min(best, key);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const u32 ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, sec, o);
-                sec = min(min(sec, os), max(best, ob));
-                best = min(best, ob);
-            }
-            const int bd1 = key_dist(best), bd2 = key_dist(sec);
-            const bool th = KFKF ? (bd1 < ORBM_TH_LOW) : (bd1 <= ORBM_TH_LOW);
-            if (th && (float)bd1 < __fmul_rn(nnratio, (float)bd2)) {
-                const int idx2 = B.feat[o2 + (int)(best & KEY_IDX_MASK)];
-                if (lane == 0) {
-                    taken2[idx2] = 1;
-                    const int slot = KFKF ? idx1 : idx2;
-                    out[slot] = KFKF ? idx2 : idx1;
-                    if (checkOri) {
-                        const int bin = rot_bin(A.angle[idx1], B.angle[idx2]);
-                        binOf[slot] = bin;
-                        atomicAdd(&s_hist[bin], 1);
-                    }
-                    atomicAdd(&s_n, 1);
-                }
-            }
-            __syncwarp();
+__global__ void __launch_bounds__(32 * SB_WARPS) k_search_bow_nodes(DevView A, DevView B, float nnratio, int checkOri,
+                                                                    int* __restrict__ out, int* __restrict__ taken2,
+                                                                    int* __restrict__ binOf, int* __restrict__ hist,
+                                                                    int* __restrict__ nmatch) {
+    const int lane = threadIdx.x & 31, a = blockIdx.x * SB_WARPS + (threadIdx.x >> 5);
+    if (a >= A.nn) return;
+    const int b = find_node(B.ids, B.nn, A.ids[a]);
+    if (b < 0) return;
+    const int o2 = B.off[b], c2 = B.off[b + 1] - o2;
+    int nm = 0;
+    for (int i1 = A.off[a]; i1 < A.off[a + 1]; i1++) {
+        const int idx1 = A.feat[i1];
+        if (!A.flag[idx1]) continue;
+        u32 d1[8];
+        load_desc(A.desc + (size_t)idx1 * 32, d1);
+        u32 best = KEY_NONE, sec = KEY_NONE;
+        for (int j = lane; j < c2; j += 32) {
+            const int idx2 = B.feat[o2 + j];
+            if (taken2[idx2]) continue;
+            if (KFKF && !B.flag[idx2]) continue;
+            u32 d2[8];
+            load_desc(B.desc + (size_t)idx2 * 32, d2);
+            const u32 key = ((u32)ham256(d1, d2) << KEY_SHIFT) | (u32)j;
+            sec = min(sec, max(best, key));
+            best = min(best, key);
         }
-    }
-    __syncthreads();
-    if (checkOri) {
-        if (tid == 0) { int a, b, c; three_maxima_dev(s_hist, ORBM_HISTO_LENGTH, a, b, c); s_ind[0] = a; s_ind[1] = b; s_ind[2] = c; }
-        __syncthreads();
-        for (int i = tid; i < nOut; i += blockDim.x)
-            if (out[i] >= 0) {
-                const int bin = binOf[i];
-                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { out[i] = -1; atomicSub(&s_n, 1); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const u32 ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, sec, o);
+            sec = min(min(sec, os), max(best, ob));
+            best = min(best, ob);
+        }
+        const int bd1 = key_dist(best), bd2 = key_dist(sec);
+        const bool th = KFKF ? (bd1 < ORBM_TH_LOW) : (bd1 <= ORBM_TH_LOW);
+        if (th && (float)bd1 < __fmul_rn(nnratio, (float)bd2)) {
+            const int idx2 = B.feat[o2 + (int)(best & KEY_IDX_MASK)];
+            if (lane == 0) {
+                taken2[idx2] = 1;
+                const int slot = KFKF ? idx1 : idx2;
+                out[slot] = KFKF ? idx2 : idx1;
+                if (checkOri) {
+                    const int bin = rot_bin(A.angle[idx1], B.angle[idx2]);
+                    binOf[slot] = bin;
+                    atomicAdd(&hist[bin], 1);
+                }
+                nm++;
             }
-        __syncthreads();
+        }
+        __syncwarp();
     }
-    if (tid == 0) *nmatches = s_n;
+    if (lane == 0 && nm) atomicAdd(nmatch, nm);
+}
+
+__global__ void __launch_bounds__(256) k_search_bow_finish(int nOut, int checkOri, int* __restrict__ out, const int* __restrict__ binOf,
+                                                           const int* __restrict__ hist, int* __restrict__ nmatch) {
+    __shared__ int s_ind[3], s_drop;
+    const int tid = threadIdx.x;
+    if (!checkOri) return;
+    if (tid == 0) { int a, b, c; three_maxima_dev(hist, ORBM_HISTO_LENGTH, a, b, c); s_ind[0] = a; s_ind[1] = b; s_ind[2] = c; s_drop = 0; }
+    __syncthreads();
+    int drop = 0;
+    for (int i = tid; i < nOut; i += blockDim.x)
+        if (out[i] >= 0) {
+            const int bin = binOf[i];
+            if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { out[i] = -1; drop++; }
+        }
+    if (drop) atomicAdd(&s_drop, drop);
+    __syncthreads();
+    if (tid == 0) *nmatch -= s_drop;
 }
 
 // SearchForTriangulation.  No cross-query coupling (vbMatched2 is never set in the reference, :680,728), so one thread
 // per side-1 CSR slot walks its node's side-2 features serially, which keeps the reference's "last candidate wins a
-// tie" (`dist>bestDist` rejects, :741) and "bestDist only moves when the epipolar test passes" (:754-758).
+// tie" (`dist>bestDist` rejects, :741) and "bestDist only moves when the epipolar test passes" (:754-758).  Launch 1 spreads
+// the slots over the GPU; launch 2 (one CTA) applies the orientation cull and the ordered compaction (:818-823).
+// Scratch zeroed by the host: hist[HISTO_LENGTH], cnt[2]; m12[] preset to -1.
 struct TriParams { float F[9]; float ex, ey; int onlyStereo, checkOri; };
 
-__global__ void __launch_bounds__(256) k_search_tri(DevView A, DevView B, TriParams tp, const float* __restrict__ sf2,
-                                                    const float* __restrict__ sigma2, int* __restrict__ m12,
-                                                    int* __restrict__ pairs, int* __restrict__ npairs, int* __restrict__ nmatches) {
-    __shared__ int s_hist[ORBM_HISTO_LENGTH];
-    __shared__ int s_n, s_ind[3], s_wsum[34];
-    const int tid = threadIdx.x;
-    if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
-    if (tid == 0) s_n = 0;
-    for (int i = tid; i < A.n; i += blockDim.x) m12[i] = -1;
-    __syncthreads();
+__global__ void __launch_bounds__(128) k_search_tri_slots(DevView A, DevView B, TriParams tp, const float* __restrict__ sf2,
+                                                          const float* __restrict__ sigma2, int* __restrict__ m12,
+                                                          int* __restrict__ hist, int* __restrict__ cnt) {
     const int total1 = A.nn > 0 ? A.off[A.nn] : 0;
-    for (int p = tid; p < total1; p += blockDim.x) {
-        int lo = 0, hi = A.nn;                                   // node a with off[a] <= p < off[a+1]
-        while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (A.off[m] <= p) lo = m; else hi = m; }
-        const int b = find_node(B.ids, B.nn, A.ids[lo]);
-        if (b < 0) continue;
-        const int idx1 = A.feat[p];
-        if (A.flag[idx1]) continue;                              // already has a MapPoint (:706-708)
-        const bool st1 = A.uright[idx1] >= 0;
-        if (tp.onlyStereo && !st1) continue;
-        const float x1 = A.x[idx1], y1 = A.y[idx1];
-        u32 d1[8];
-        load_desc(A.desc + (size_t)idx1 * 32, d1);
-        // epipolar line l = x1' F12 (:143-145)
-        const float la = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[0]), __fmul_rn(y1, tp.F[3])), tp.F[6]);
-        const float lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[1]), __fmul_rn(y1, tp.F[4])), tp.F[7]);
-        const float lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[2]), __fmul_rn(y1, tp.F[5])), tp.F[8]);
-        const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
-        int bestDist = ORBM_TH_LOW, bestIdx2 = -1;
-        for (int i2 = B.off[b]; i2 < B.off[b + 1]; i2++) {
-            const int idx2 = B.feat[i2];
-            if (B.flag[idx2]) continue;
-            const bool st2 = B.uright[idx2] >= 0;
-            if (tp.onlyStereo && !st2) continue;
-            u32 d2[8];
-            load_desc(B.desc + (size_t)idx2 * 32, d2);
-            const int dist = ham256(d1, d2);
-            if (dist > ORBM_TH_LOW || dist > bestDist) continue;
-            const float x2 = B.x[idx2], y2 = B.y[idx2];
-            const int oc = B.octave[idx2];
-            if (!st1 && !st2) {
-                const float dx = __fsub_rn(tp.ex, x2), dy = __fsub_rn(tp.ey, y2);
-                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, sf2[oc])) continue;
-            }
-            if (den == 0) continue;
-            const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
-            const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
-            if ((double)dsqr < 3.84 * (double)sigma2[oc]) { bestIdx2 = idx2; bestDist = dist; }
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total1) return;
+    int lo = 0, hi = A.nn;                                       // node a with off[a] <= p < off[a+1]
+    while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (A.off[m] <= p) lo = m; else hi = m; }
+    const int b = find_node(B.ids, B.nn, A.ids[lo]);
+    if (b < 0) return;
+    const int idx1 = A.feat[p];
+    if (A.flag[idx1]) return;                                    // already has a MapPoint (:706-708)
+    const bool st1 = A.uright[idx1] >= 0;
+    if (tp.onlyStereo && !st1) return;
+    const float x1 = A.x[idx1], y1 = A.y[idx1];
+    u32 d1[8];
+    load_desc(A.desc + (size_t)idx1 * 32, d1);
+    // epipolar line l = x1' F12 (:143-145)
+    const float la = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[0]), __fmul_rn(y1, tp.F[3])), tp.F[6]);
+    const float lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[1]), __fmul_rn(y1, tp.F[4])), tp.F[7]);
+    const float lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, tp.F[2]), __fmul_rn(y1, tp.F[5])), tp.F[8]);
+    const float den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    int bestDist = ORBM_TH_LOW, bestIdx2 = -1;
+    for (int i2 = B.off[b]; i2 < B.off[b + 1]; i2++) {
+        const int idx2 = B.feat[i2];
+        if (B.flag[idx2]) continue;
+        const bool st2 = B.uright[idx2] >= 0;
+        if (tp.onlyStereo && !st2) continue;
+        u32 d2[8];
+        load_desc(B.desc + (size_t)idx2 * 32, d2);
+        const int dist = ham256(d1, d2);
+        if (dist > ORBM_TH_LOW || dist > bestDist) continue;
+        const float x2 = B.x[idx2], y2 = B.y[idx2];
+        const int oc = B.octave[idx2];
+        if (!st1 && !st2) {
+            const float dx = __fsub_rn(tp.ex, x2), dy = __fsub_rn(tp.ey, y2);
+            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.f, sf2[oc])) continue;
         }
-        if (bestIdx2 >= 0) {
-            m12[idx1] = bestIdx2;
-            atomicAdd(&s_n, 1);
-            if (tp.checkOri) atomicAdd(&s_hist[rot_bin(A.angle[idx1], B.angle[bestIdx2])], 1);
-        }
+        if (den == 0) continue;
+        const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, x2), __fmul_rn(lb, y2)), lc);
+        const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+        if ((double)dsqr < 3.84 * (double)sigma2[oc]) { bestIdx2 = idx2; bestDist = dist; }
     }
-    __syncthreads();
-    if (tp.checkOri) {
-        if (tid == 0) { int a, b, c; three_maxima_dev(s_hist, ORBM_HISTO_LENGTH, a, b, c); s_ind[0] = a; s_ind[1] = b; s_ind[2] = c; }
+    if (bestIdx2 >= 0) {
+        m12[idx1] = bestIdx2;
+        atomicAdd(&cnt[1], 1);
+        if (tp.checkOri) atomicAdd(&hist[rot_bin(A.angle[idx1], B.angle[bestIdx2])], 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_search_tri_finish(DevView A, DevView B, int checkOri, int* __restrict__ m12,
+                                                           const int* __restrict__ hist, int* __restrict__ pairs,
+                                                           int* __restrict__ cnt) {
+    __shared__ int s_ind[3], s_drop, s_wsum[34];
+    const int tid = threadIdx.x;
+    if (checkOri) {
+        if (tid == 0) { int a, b, c; three_maxima_dev(hist, ORBM_HISTO_LENGTH, a, b, c); s_ind[0] = a; s_ind[1] = b; s_ind[2] = c; s_drop = 0; }
         __syncthreads();
+        int drop = 0;
         for (int i = tid; i < A.n; i += blockDim.x)
             if (m12[i] >= 0) {
                 const int bin = rot_bin(A.angle[i], B.angle[m12[i]]);
-                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { m12[i] = -1; atomicSub(&s_n, 1); }
+                if (bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) { m12[i] = -1; drop++; }
             }
+        if (drop) atomicAdd(&s_drop, drop);
         __syncthreads();
+        if (tid == 0) cnt[1] -= s_drop;
     }
     // ordered compaction of (i, m12[i]) (:818-823): chunked block scan
     int base = 0;
@@ -367,7 +411,7 @@ __global__ void __launch_bounds__(256) k_search_tri(DevView A, DevView B, TriPar
         base += s_wsum[32];
         __syncthreads();
     }
-    if (tid == 0) { *npairs = base; *nmatches = s_n; }
+    if (tid == 0) cnt[0] = base;
 }
 
 // POPC issue-rate microbenchmark: 8 independent xor+popc chains per thread, register resident.
@@ -389,27 +433,36 @@ __global__ void k_popc_peak(u32* out, int iters) {
 // Host side
 // =====================================================================================================
 namespace {
-// Per-thread device scratch arena (grows; freed at thread exit is skipped on purpose: process-lifetime cache).
+// Per-thread device scratch arena (grows; process-lifetime cache) with a pinned host mirror.  Small calls (a SearchByBoW of
+// two 2000-feature keyframes is ~150 KB in ten arrays) are packed into the mirror and sent with ONE asynchronous copy, and
+// their results come back through the mirror with one synchronisation; large calls copy directly.
 struct Arena {
     int device = -1;
     u8* base = nullptr;
-    size_t cap = 0, used = 0;
+    u8* hbase = nullptr;
+    size_t cap = 0, used = 0, inEnd = 0;
+    bool staged = false;
     cudaStream_t stream = nullptr;
     int ensure(int dev, size_t bytes) {
         if (device != dev) {
             if (base) { cudaSetDevice(device); cudaFree(base); base = nullptr; cap = 0; }
+            if (hbase) { cudaFreeHost(hbase); hbase = nullptr; }
             if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
             device = dev;
         }
         ORB_CUDA_TRY(cudaSetDevice(dev));
         if (!stream) ORB_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        bytes += 64 * 256;                                   // per-array alignment slack
         if (bytes > cap) {
             if (base) ORB_CUDA_TRY(cudaFree(base));
-            base = nullptr;
+            if (hbase) ORB_CUDA_TRY(cudaFreeHost(hbase));
+            base = nullptr; hbase = nullptr;
             cap = orb_align_up(bytes + (bytes >> 2), 1 << 20);
             ORB_CUDA_TRY(cudaMalloc(&base, cap));
+            if (cap <= (8u << 20)) ORB_CUDA_TRY(cudaMallocHost(&hbase, cap));
         }
-        used = 0;
+        staged = hbase != nullptr && bytes <= (2u << 20);
+        used = 0; inEnd = 0;
         return ORB_OK;
     }
     template <typename T>
@@ -418,13 +471,43 @@ struct Arena {
         used += orb_align_up(count * sizeof(T), 256);
         return p;
     }
+    // send everything put() so far (staged mode); call once, after the last input and before the launch
+    int flush() {
+        if (staged && used > 0) ORB_CUDA_TRY(cudaMemcpyAsync(base, hbase, used, cudaMemcpyHostToDevice, stream));
+        inEnd = used;
+        return ORB_OK;
+    }
+    // bring `count` elements at device pointer d back to host pointer h; finish() completes the transfer
+    struct Pending { void* h; const u8* d; size_t bytes; };
+    std::vector<Pending> pend;
+    template <typename T>
+    int fetch(T* h, const T* d, size_t count) {
+        if (count == 0) return ORB_OK;
+        const u8* dp = reinterpret_cast<const u8*>(d);
+        if (staged) {
+            ORB_CUDA_TRY(cudaMemcpyAsync(hbase + (dp - base), dp, count * sizeof(T), cudaMemcpyDeviceToHost, stream));
+            pend.push_back({h, dp, count * sizeof(T)});
+        } else {
+            ORB_CUDA_TRY(cudaMemcpyAsync(h, dp, count * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        }
+        return ORB_OK;
+    }
+    int finish() {
+        ORB_CUDA_TRY(cudaStreamSynchronize(stream));
+        for (const Pending& p : pend) memcpy(p.h, hbase + (p.d - base), p.bytes);
+        pend.clear();
+        return ORB_OK;
+    }
 };
 thread_local Arena g_arena;
 
 template <typename T>
 int upload(Arena& A, const T* host, size_t count, const T** dev) {
     T* d = A.take<T>(std::max<size_t>(count, 1));
-    if (count) ORB_CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, A.stream));
+    if (count) {
+        if (A.staged) memcpy(A.hbase + (reinterpret_cast<u8*>(d) - A.base), host, count * sizeof(T));
+        else ORB_CUDA_TRY(cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, A.stream));
+    }
     *dev = d;
     return ORB_OK;
 }
@@ -447,12 +530,12 @@ extern "C" int orbm_descriptor_distance(const uint8_t* a, const uint8_t* b, int 
     const u8 *da, *db;
     if ((rc = upload(A, a, (size_t)n * 32, &da))) return rc;
     if ((rc = upload(A, b, (size_t)n * 32, &db))) return rc;
+    if ((rc = A.flush())) return rc;
     int* dd = A.take<int>(n);
     k_pair_distance<<<orb_div_up(n, 256), 256, 0, A.stream>>>(da, db, n, dd);
     ORB_CUDA_TRY(cudaGetLastError());
-    ORB_CUDA_TRY(cudaMemcpyAsync(dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
-    return ORB_OK;
+    if ((rc = A.fetch(dist, dd, (size_t)n))) return rc;
+    return A.finish();
 }
 
 static int launch_top2(const u8* d_q, const int* d_q_off, const int* d_q_cnt, const u8* d_db, const int* d_db_off,
@@ -492,7 +575,7 @@ extern "C" int orbm_hamming_top2(const uint8_t* q, int nq, const uint8_t* db, in
     if (rc) return rc;
     if (nq == 0) return ORB_OK;
     Arena& A = g_arena;
-    rc = A.ensure(device, pad((size_t)nq * 32) + pad((size_t)ndb * 32) + 3 * pad((size_t)nq * 4) + 4 * 256);
+    rc = A.ensure(device, pad((size_t)nq * 32) + pad((size_t)ndb * 32) + 3 * pad((size_t)nq * 4) + pad((size_t)32 * nq * 4) + 4 * 256);
     if (rc) return rc;
     const u8 *dq, *ddb;
     if ((rc = upload(A, q, (size_t)nq * 32, &dq))) return rc;
@@ -500,14 +583,27 @@ extern "C" int orbm_hamming_top2(const uint8_t* q, int nq, const uint8_t* db, in
     const int meta[4] = {0, nq, 0, ndb};
     const int* dmeta;
     if ((rc = upload(A, meta, 4, &dmeta))) return rc;
+    u32* u32part = nullptr;
+    if ((rc = A.flush())) return rc;
     int *bi = A.take<int>(nq), *bd = A.take<int>(nq), *sd = A.take<int>(nq);
-    rc = launch_top2(dq, dmeta, dmeta + 1, ddb, dmeta + 2, dmeta + 3, 1, nq, bi, bd, sd, A.stream);
-    if (rc) return rc;
-    ORB_CUDA_TRY(cudaMemcpyAsync(best_idx, bi, (size_t)nq * 4, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaMemcpyAsync(best_dist, bd, (size_t)nq * 4, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaMemcpyAsync(second_dist, sd, (size_t)nq * 4, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
-    return ORB_OK;
+    if ((long)nq * ndb <= (64L << 20)) u32part = A.take<u32>((size_t)16 * 2 * nq);      // latency form only for small problems
+    const int qtiles = orb_div_up(nq, T2_THREADS);
+    int nslice = std::min(16, std::max(1, 296 / qtiles));
+    int slice_len = (int)orb_align_up((size_t)orb_div_up(std::max(ndb, 1), nslice), 64);
+    nslice = orb_div_up(std::max(ndb, 1), slice_len);
+    if (nslice > 1 && u32part) {
+        dim3 g(qtiles, nslice);
+        k_top2_slice<<<g, T2_THREADS, 0, A.stream>>>(dq, nq, ddb, ndb, slice_len, u32part);
+        k_top2_merge<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(u32part, nq, nslice, bi, bd, sd);
+        ORB_CUDA_TRY(cudaGetLastError());
+    } else {
+        rc = launch_top2(dq, dmeta, dmeta + 1, ddb, dmeta + 2, dmeta + 3, 1, nq, bi, bd, sd, A.stream);
+        if (rc) return rc;
+    }
+    if ((rc = A.fetch(best_idx, bi, (size_t)nq))) return rc;
+    if ((rc = A.fetch(best_dist, bd, (size_t)nq))) return rc;
+    if ((rc = A.fetch(second_dist, sd, (size_t)nq))) return rc;
+    return A.finish();
 }
 
 extern "C" int orbm_allpairs_device(const uint8_t* d_desc, int n_kf, int per_kf, int q_begin, int q_end, int th_low, float ratio,
@@ -597,16 +693,23 @@ static int search_bow(const orbm_view* v1, const orbm_view* v2, float nnratio, i
     DevView d1, d2;
     if ((rc = upload_view(A, v1, false, &d1))) return rc;
     if ((rc = upload_view(A, v2, false, &d2))) return rc;
+    if ((rc = A.flush())) return rc;
     int* d_out = A.take<int>(std::max(nOut, 1));
     int* d_bin = A.take<int>(std::max(nOut, 1));
-    int* d_taken = A.take<int>(std::max(v2->n, 1));
-    int* d_nm = A.take<int>(1);
-    k_search_bow<KFKF><<<1, 256, 0, A.stream>>>(d1, d2, nnratio, checkOri, d_out, d_taken, d_bin, d_nm);
+    int* d_zero = A.take<int>((size_t)std::max(v2->n, 1) + ORBM_HISTO_LENGTH + 1);     // taken2 | hist | nmatch, one memset
+    int* d_taken = d_zero;
+    int* d_hist = d_zero + std::max(v2->n, 1);
+    int* d_nm = d_hist + ORBM_HISTO_LENGTH;
+    ORB_CUDA_TRY(cudaMemsetAsync(d_out, 0xFF, (size_t)std::max(nOut, 1) * 4, A.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_zero, 0, ((size_t)std::max(v2->n, 1) + ORBM_HISTO_LENGTH + 1) * 4, A.stream));
+    if (v1->fv.n_nodes > 0)
+        k_search_bow_nodes<KFKF><<<orb_div_up(v1->fv.n_nodes, SB_WARPS), 32 * SB_WARPS, 0, A.stream>>>(d1, d2, nnratio, checkOri, d_out,
+                                                                                                     d_taken, d_bin, d_hist, d_nm);
+    k_search_bow_finish<<<1, 256, 0, A.stream>>>(nOut, checkOri, d_out, d_bin, d_hist, d_nm);
     ORB_CUDA_TRY(cudaGetLastError());
-    if (nOut) ORB_CUDA_TRY(cudaMemcpyAsync(match, d_out, (size_t)nOut * 4, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaMemcpyAsync(n_matches, d_nm, 4, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
-    return ORB_OK;
+    if ((rc = A.fetch(match, d_out, (size_t)nOut))) return rc;
+    if ((rc = A.fetch(n_matches, d_nm, 1))) return rc;
+    return A.finish();
 }
 
 extern "C" int orbm_search_by_bow_kf_frame(const orbm_view* kf, const orbm_view* frame, float nnratio, int check_orientation,
@@ -636,22 +739,38 @@ extern "C" int orbm_search_for_triangulation(const orbm_view* kf1, const orbm_vi
     const float *d_sf, *d_s2;
     if ((rc = upload(A, scale_factors2, (size_t)n_levels2, &d_sf))) return rc;
     if ((rc = upload(A, level_sigma2_2, (size_t)n_levels2, &d_s2))) return rc;
+    if ((rc = A.flush())) return rc;
     int* d_m12 = A.take<int>(std::max(kf1->n, 1));
     int* d_pairs = A.take<int>(std::max(2 * kf1->n, 1));
-    int* d_cnt = A.take<int>(2);
+    int* d_cnt = A.take<int>(2 + ORBM_HISTO_LENGTH);          // cnt[2] | hist, one memset
+    int* d_hist = d_cnt + 2;
     TriParams tp;
     for (int i = 0; i < 9; i++) tp.F[i] = F12[i];
     tp.ex = ex; tp.ey = ey; tp.onlyStereo = only_stereo; tp.checkOri = check_orientation;
-    k_search_tri<<<1, 256, 0, A.stream>>>(d1, d2, tp, d_sf, d_s2, d_m12, d_pairs, d_cnt, d_cnt + 1);
+    ORB_CUDA_TRY(cudaMemsetAsync(d_m12, 0xFF, (size_t)std::max(kf1->n, 1) * 4, A.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (2 + ORBM_HISTO_LENGTH) * 4, A.stream));
+    {
+        const int total1 = kf1->fv.n_nodes > 0 ? kf1->fv.offsets[kf1->fv.n_nodes] : 0;
+        if (total1 > 0) k_search_tri_slots<<<orb_div_up(total1, 128), 128, 0, A.stream>>>(d1, d2, tp, d_sf, d_s2, d_m12, d_hist, d_cnt);
+    }
+    k_search_tri_finish<<<1, 256, 0, A.stream>>>(d1, d2, check_orientation, d_m12, d_hist, d_pairs, d_cnt);
     ORB_CUDA_TRY(cudaGetLastError());
     int cnt[2] = {0, 0};
-    ORB_CUDA_TRY(cudaMemcpyAsync(cnt, d_cnt, 8, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
-    *n_pairs = cnt[0]; *n_matches = cnt[1];
-    if (cnt[0]) {
-        ORB_CUDA_TRY(cudaMemcpyAsync(pairs_out, d_pairs, (size_t)cnt[0] * 8, cudaMemcpyDeviceToHost, A.stream));
-        ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
+    if (A.staged) {            // small call: bring counts and the whole pair buffer back with one synchronisation
+        std::vector<int> tmp(std::max(2 * kf1->n, 1));
+        if ((rc = A.fetch(cnt, d_cnt, 2))) return rc;
+        if ((rc = A.fetch(tmp.data(), d_pairs, (size_t)2 * kf1->n))) return rc;
+        if ((rc = A.finish())) return rc;
+        if (cnt[0]) memcpy(pairs_out, tmp.data(), (size_t)cnt[0] * 8);
+    } else {
+        if ((rc = A.fetch(cnt, d_cnt, 2))) return rc;
+        if ((rc = A.finish())) return rc;
+        if (cnt[0]) {
+            if ((rc = A.fetch(pairs_out, d_pairs, (size_t)cnt[0] * 2))) return rc;
+            if ((rc = A.finish())) return rc;
+        }
     }
+    *n_pairs = cnt[0]; *n_matches = cnt[1];
     return ORB_OK;
 }
 
@@ -663,12 +782,12 @@ extern "C" int orbm_three_maxima(const int* histo, int n_bins, int* ind, int dev
     if ((rc = A.ensure(device, pad((size_t)n_bins * 4) + 256))) return rc;
     const int* dh;
     if ((rc = upload(A, histo, (size_t)n_bins, &dh))) return rc;
+    if ((rc = A.flush())) return rc;
     int* di = A.take<int>(3);
     k_three_maxima<<<1, 1, 0, A.stream>>>(dh, n_bins, di);
     ORB_CUDA_TRY(cudaGetLastError());
-    ORB_CUDA_TRY(cudaMemcpyAsync(ind, di, 12, cudaMemcpyDeviceToHost, A.stream));
-    ORB_CUDA_TRY(cudaStreamSynchronize(A.stream));
-    return ORB_OK;
+    if ((rc = A.fetch(ind, di, 3))) return rc;
+    return A.finish();
 }
 
 extern "C" int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used) {
