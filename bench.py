@@ -99,6 +99,28 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Best effort: run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers (first touch)
+    are local to the GPU's PCIe root port.  Matters only when several ranks stream frames from host memory at once."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except (OSError, ValueError, AttributeError):
+        pass
+    return None
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -200,6 +222,7 @@ def main():
         return float(t.item())
 
     nF = args.frames
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None     # pinned staging memory local to this GPU's root port
     h_frames = torch.from_numpy(frames).pin_memory()
     d_frames = h_frames.cuda(non_blocking=True)
     ex = orb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, max_batch=args.chunk, device=local_rank)
@@ -359,7 +382,7 @@ def main():
             "config": {"workload": "C2: batch of 640x480 synthetic frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7",
                        "frames_per_gpu_per_step": nF, "unique_frames_per_gpu": min(args.unique, nF), "frames_per_device_pass": args.chunk,
                        "keypoints_per_frame": kp_per_frame, "l2": "inputs_exceed_l2 (1.26 GB of frames per step per GPU)",
-                       "parallelism": f"frame-sharded x{world}, no data-path collective"},
+                       "parallelism": f"frame-sharded x{world}, no data-path collective", "numa_node_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "matching": matching,
         })
