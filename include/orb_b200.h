@@ -188,6 +188,33 @@ int orbm_search_for_triangulation(const orbm_view* kf1, const orbm_view* kf2, co
  * searches above; this entry exposes it for tests.  ind[3]. */
 int orbm_three_maxima(const int* histo, int n_bins, int* ind, int device);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * ORB vocabulary: BoW assignment feeding the matcher (the first "next" row after the hot path)
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct orbv_vocabulary orbv_vocabulary;
+
+/* Build a vocabulary tree from flat node arrays, the state TemplatedVocabulary::loadFromTextFile / loadFromBinaryFile
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1351-1440, 1467-1512) leave in m_nodes: node 0 is the root; parent[i] < i
+ * for i >= 1 (children keep file order); descriptors n_nodes x 32 bytes (row 0 unused); weights[i] = Node::weight;
+ * is_leaf[i] != 0 marks words, numbered in node order like m_words.  scoring / weighting: DBoW2 ScoringType / WeightingType. */
+int orbv_create(orbv_vocabulary** out, int k, int L, int scoring, int weighting, int n_nodes, const int* parent,
+                const uint8_t* descriptors, const double* weights, const uint8_t* is_leaf, int device);
+/* Same from the two on-disk formats of the reference (text: ORBvoc.txt; binary: the fork's ORBvoc.bin, tools/bin_vocabulary.cc). */
+int orbv_load_text(orbv_vocabulary** out, const char* path, int device);
+int orbv_load_binary(orbv_vocabulary** out, const char* path, int device);
+/* Writes the fork's binary format (TemplatedVocabulary::saveToBinaryFile, :1515-1536). */
+int orbv_save_binary(const orbv_vocabulary* voc, const char* path);
+void orbv_destroy(orbv_vocabulary* voc);
+int orbv_info(const orbv_vocabulary* voc, int* k, int* L, int* n_nodes, int* n_words, int* scoring, int* weighting);
+
+/* Replaces TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup) (:1231-1272) for n descriptors:
+ * tree descent with FORB::distance (FORB.cpp:81-101), first child attaining the minimum wins; node_id = the node on the path
+ * at level L - levelsup (0 = root when that is <= 0).  Host pointers; any output may be NULL. */
+int orbv_transform(const orbv_vocabulary* voc, const uint8_t* desc, int n, int levelsup, int* word_id, double* weight, int* node_id);
+/* Device-resident form, asynchronous on `stream`. */
+int orbv_transform_device(const orbv_vocabulary* voc, const uint8_t* d_desc, int n, int levelsup, int* d_word_id, double* d_weight,
+                          int* d_node_id, void* stream);
+
 /* POPC issue-rate microbenchmark (defines the matching roofline): returns measured 32-bit POPC results
  * per second on `device` over a register-resident loop. */
 int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);

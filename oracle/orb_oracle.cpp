@@ -36,6 +36,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <list>
+#include <map>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -949,6 +950,66 @@ int orc_search_triangulation(const u8* desc1, int n1, const u8* hasmp1, const fl
     }
     *npairs_out = np;
     return nmatches;
+}
+
+
+// ---- DBoW2 vocabulary: TemplatedVocabulary::transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1140-1207, 1231-1272)
+// restated on flat node arrays (node 0 = root, parent[i] < i, children in node order).
+void orc_voc_transform(int n_nodes, const int* parent, const u8* ndesc, const double* nweight, const u8* is_leaf, int L,
+                       const u8* feat, int n, int levelsup, int* word_id, double* weight, int* node_id) {
+    std::vector<std::vector<int> > children(n_nodes);
+    std::vector<int> word(n_nodes, -1);
+    int nw = 0;
+    for (int i = 1; i < n_nodes; i++) { children[parent[i]].push_back(i); if (is_leaf[i]) word[i] = nw++; }
+    for (int f = 0; f < n; f++) {
+        const int nid_level = L - levelsup;
+        int nid = 0;                                            // root when nid_level <= 0
+        int final_id = 0, current_level = 0;
+        do {
+            ++current_level;
+            const std::vector<int>& nodes = children[final_id];
+            if (nodes.empty()) break;                            // (a one-node vocabulary: the reference would crash here)
+            final_id = nodes[0];
+            double best_d = (double)descriptor_distance(feat + (size_t)f * 32, ndesc + (size_t)final_id * 32);
+            for (size_t c = 1; c < nodes.size(); c++) {
+                const double d = (double)descriptor_distance(feat + (size_t)f * 32, ndesc + (size_t)nodes[c] * 32);
+                if (d < best_d) { best_d = d; final_id = nodes[c]; }
+            }
+            if (current_level == nid_level) nid = final_id;
+        } while (!children[final_id].empty());
+        word_id[f] = word[final_id]; weight[f] = nweight[final_id]; node_id[f] = nid;
+    }
+}
+// BowVector as transform(features, v, fv, levelsup) builds it: weighting 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY; scoring 0 L1_NORM, 1 L2_NORM,
+// 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT (mustNormalize: L1 for 0,2,3,4; L2 for 1; none for 5).  Returns the map size.
+int orc_voc_bow(int n, const int* word_id, const double* weight, int weighting, int scoring, int* out_word, double* out_value, int cap) {
+    std::map<unsigned, double> v;
+    const bool must = scoring != 5;
+    const bool l2 = scoring == 1;
+    for (int i = 0; i < n; i++) {
+        if (!(weight[i] > 0)) continue;
+        if (weighting == 0 || weighting == 1) {
+            std::map<unsigned, double>::iterator it = v.lower_bound((unsigned)word_id[i]);
+            if (it != v.end() && !(v.key_comp()((unsigned)word_id[i], it->first))) it->second += weight[i];
+            else v.insert(it, std::make_pair((unsigned)word_id[i], weight[i]));
+        } else {
+            std::map<unsigned, double>::iterator it = v.lower_bound((unsigned)word_id[i]);
+            if (it == v.end() || v.key_comp()((unsigned)word_id[i], it->first)) v.insert(it, std::make_pair((unsigned)word_id[i], weight[i]));
+        }
+    }
+    if ((weighting == 0 || weighting == 1) && !v.empty() && !must) {
+        const double nd = (double)v.size();
+        for (std::map<unsigned, double>::iterator it = v.begin(); it != v.end(); ++it) it->second /= nd;
+    }
+    if (must) {
+        double norm = 0.0;
+        if (!l2) for (std::map<unsigned, double>::iterator it = v.begin(); it != v.end(); ++it) norm += std::fabs(it->second);
+        else { for (std::map<unsigned, double>::iterator it = v.begin(); it != v.end(); ++it) norm += it->second * it->second; norm = std::sqrt(norm); }
+        if (norm > 0.0) for (std::map<unsigned, double>::iterator it = v.begin(); it != v.end(); ++it) it->second /= norm;
+    }
+    int k = 0;
+    for (std::map<unsigned, double>::iterator it = v.begin(); it != v.end() && k < cap; ++it, ++k) { out_word[k] = (int)it->first; out_value[k] = it->second; }
+    return (int)v.size();
 }
 
 }  // extern "C"

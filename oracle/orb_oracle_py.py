@@ -86,6 +86,10 @@ def lib():
         L.orc_search_triangulation.argtypes = ([vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp] +
                                                [vp, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp] +
                                                [vp, f32, f32, vp, vp, i32, i32, vp, vp])
+        L.orc_voc_transform.restype = None
+        L.orc_voc_transform.argtypes = [i32, vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp]
+        L.orc_voc_bow.restype = i32
+        L.orc_voc_bow.argtypes = [i32, vp, vp, i32, i32, vp, vp, i32]
         _lib = L
     return _lib
 
@@ -319,3 +323,25 @@ def search_triangulation(desc1, hasmp1, uright1, kx1, ky1, ang1, fv1,
         _p(desc2), len(desc2), _p(hasmp2), _p(uright2), _p(kx2), _p(ky2), _p(ang2), _p(oct2), fv2.n, _p(fv2.ids), _p(fv2.off), _p(fv2.feat),
         _p(F12), float(ex), float(ey), _p(sf2), _p(sigma2_2), int(only_stereo), int(check_ori), _p(pairs), C.byref(npairs))
     return n, pairs[:npairs.value].copy()
+
+
+# ------------------------------------------------------------------ vocabulary (DBoW2 transform)
+def voc_transform(parent, ndesc, nweight, is_leaf, L, feat, levelsup):
+    parent = np.ascontiguousarray(parent, np.int32)
+    ndesc, is_leaf, feat = _u8(ndesc), _u8(is_leaf), _u8(feat)
+    nweight = np.ascontiguousarray(nweight, np.float64)
+    n = len(feat)
+    w, nid = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    wt = np.zeros(n, np.float64)
+    lib().orc_voc_transform(len(parent), _p(parent), _p(ndesc), _p(nweight), _p(is_leaf), int(L), _p(feat), n, int(levelsup),
+                            _p(w), _p(wt), _p(nid))
+    return w, wt, nid
+
+
+def voc_bow(word_id, weight, weighting=0, scoring=0):
+    word_id = np.ascontiguousarray(word_id, np.int32)
+    weight = np.ascontiguousarray(weight, np.float64)
+    cap = len(word_id) + 1
+    ow, ov = np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+    k = lib().orc_voc_bow(len(word_id), _p(word_id), _p(weight), int(weighting), int(scoring), _p(ow), _p(ov), cap)
+    return ow[:k], ov[:k]

@@ -29,6 +29,8 @@ SYMBOLS = [
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
     "orbm_popc_peak",
+    "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
+    "orbv_transform_device",
 ]
 
 
@@ -111,6 +113,22 @@ def lib():
     L.orbm_three_maxima.argtypes = [vp, i32, vp, i32]
     L.orbm_popc_peak.restype = i32
     L.orbm_popc_peak.argtypes = [i32, vp, vp]
+    L.orbv_create.restype = i32
+    L.orbv_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, vp, i32]
+    L.orbv_load_text.restype = i32
+    L.orbv_load_text.argtypes = [C.POINTER(vp), C.c_char_p, i32]
+    L.orbv_load_binary.restype = i32
+    L.orbv_load_binary.argtypes = [C.POINTER(vp), C.c_char_p, i32]
+    L.orbv_save_binary.restype = i32
+    L.orbv_save_binary.argtypes = [vp, C.c_char_p]
+    L.orbv_destroy.restype = None
+    L.orbv_destroy.argtypes = [vp]
+    L.orbv_info.restype = i32
+    L.orbv_info.argtypes = [vp] * 7
+    L.orbv_transform.restype = i32
+    L.orbv_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.orbv_transform_device.restype = i32
+    L.orbv_transform_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     _lib = L
     return L
 

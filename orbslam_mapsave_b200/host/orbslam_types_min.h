@@ -12,8 +12,33 @@
 #include <vector>
 #include "cv_compat.h"
 
+#include <cmath>
 namespace DBoW2 {
 typedef unsigned int NodeId;
+typedef unsigned int WordId;
+typedef double WordValue;
+enum LNorm { L1, L2 };
+enum WeightingType { TF_IDF, TF, IDF, BINARY };
+enum ScoringType { L1_NORM, L2_NORM, CHI_SQUARE, KL, BHATTACHARYYA, DOT_PRODUCT };
+// Thirdparty/DBoW2/DBoW2/BowVector.{h,cpp}
+class BowVector : public std::map<WordId, WordValue> {
+public:
+    void addWeight(WordId id, WordValue v) {
+        iterator vit = this->lower_bound(id);
+        if (vit != this->end() && !(this->key_comp()(id, vit->first))) vit->second += v;
+        else this->insert(vit, value_type(id, v));
+    }
+    void addIfNotExist(WordId id, WordValue v) {
+        iterator vit = this->lower_bound(id);
+        if (vit == this->end() || (this->key_comp()(id, vit->first))) this->insert(vit, value_type(id, v));
+    }
+    void normalize(LNorm norm_type) {
+        double norm = 0.0;
+        if (norm_type == L1) { for (iterator it = begin(); it != end(); ++it) norm += std::fabs(it->second); }
+        else { for (iterator it = begin(); it != end(); ++it) norm += it->second * it->second; norm = std::sqrt(norm); }
+        if (norm > 0.0) for (iterator it = begin(); it != end(); ++it) it->second /= norm;
+    }
+};
 class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {
 public:
     void addFeature(NodeId id, unsigned int i_feature) { (*this)[id].push_back(i_feature); }

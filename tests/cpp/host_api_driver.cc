@@ -11,6 +11,7 @@
 
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
+#include "ORBVocabulary.h"
 
 using namespace ORB_SLAM2;
 
@@ -149,8 +150,37 @@ static int run_match(int argc, char** argv) {
     return ORBmatcher::LastStatus() == 0 ? 0 : 4;
 }
 
+// driver bow <voc.bin|voc.txt> <desc.raw> <levelsup> <out.bin>: Frame::ComputeBoW the way the reference does it
+static int run_bow(int argc, char** argv) {
+    if (argc < 6) return 2;
+    ORBVocabularyB200 voc;
+    const std::string path(argv[2]);
+    const bool ok = path.size() > 4 && path.substr(path.size() - 4) == ".txt" ? voc.loadFromTextFile(path) : voc.loadFromBinaryFile(path);
+    if (!ok) return 3;
+    std::vector<unsigned char> d = slurp(argv[3]);
+    const int n = (int)(d.size() / 32);
+    std::vector<cv::Mat> feats(n);
+    for (int i = 0; i < n; i++) feats[i] = cv::Mat(1, 32, CV_8U, &d[(size_t)i * 32]);    // Converter::toDescriptorVector
+    DBoW2::BowVector bow;
+    DBoW2::FeatureVector fv;
+    voc.transform(feats, bow, fv, atoi(argv[4]));
+    if (voc.LastStatus() != 0) return 4;
+    std::ofstream out(argv[5], std::ios::binary);
+    const int nb = (int)bow.size(), nn = (int)fv.size(), nw = (int)voc.size();
+    put(out, &nw, 1); put(out, &nb, 1);
+    for (DBoW2::BowVector::const_iterator it = bow.begin(); it != bow.end(); ++it) { const int w = (int)it->first; put(out, &w, 1); put(out, &it->second, 1); }
+    put(out, &nn, 1);
+    for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+        const int id = (int)it->first, c = (int)it->second.size();
+        put(out, &id, 1); put(out, &c, 1);
+        for (int j = 0; j < c; j++) { const int f = (int)it->second[j]; put(out, &f, 1); }
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
+    if (!strcmp(argv[1], "bow")) return run_bow(argc, argv);
     if (!strcmp(argv[1], "extract")) return run_extract(argc, argv);
     if (!strcmp(argv[1], "match")) return run_match(argc, argv);
     return 2;

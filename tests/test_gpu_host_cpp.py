@@ -140,3 +140,46 @@ def test_cpp_orbmatcher_matches_oracle(tmp_path, seed, ratio, ori, only_stereo):
     assert nm == on and np.array_equal(got, op)
     d, lo, hi, hl = take("<iiii")
     assert d == orc.descriptor_distance(desc[0][0], desc[1][0]) and (lo, hi, hl) == (50, 100, 30)
+
+
+def test_cpp_vocabulary_transform_matches_oracle(tmp_path):
+    """ORBVocabularyB200::transform(features, BowVector, FeatureVector, 4) == DBoW2 semantics (oracle), doubles bit-exact."""
+    import orbslam_mapsave_b200 as orb
+    from vocab_util import make_tree
+    from orbslam_mapsave_b200.synth import synth_descriptors
+    k, L = 10, 4
+    parent, desc, weight, is_leaf = make_tree(k, L, seed=7)
+    orb.ORBVocabulary.from_arrays(k, L, parent, desc, weight, is_leaf).saveToBinaryFile(tmp_path / "voc.bin")
+    feats = synth_descriptors(2000, 9, dup_of=desc[1:], dup_rate=0.7, max_flip=30)
+    (tmp_path / "desc.raw").write_bytes(feats.tobytes())
+    subprocess.check_call([_driver(), "bow", str(tmp_path / "voc.bin"), str(tmp_path / "desc.raw"), "4", str(tmp_path / "bow.bin")])
+    out = (tmp_path / "bow.bin").read_bytes()
+    nw, nb = struct.unpack_from("<ii", out, 0)
+    pos = 8
+    words, vals = [], []
+    for _ in range(nb):
+        w, v = struct.unpack_from("<id", out, pos)
+        pos += 12
+        words.append(w)
+        vals.append(v)
+    nn, = struct.unpack_from("<i", out, pos)
+    pos += 4
+    ids, lists = [], []
+    for _ in range(nn):
+        i, c = struct.unpack_from("<ii", out, pos)
+        pos += 8
+        lists.append(np.frombuffer(out, np.int32, c, pos))
+        pos += 4 * c
+        ids.append(i)
+    w32 = weight.astype(np.float32).astype(np.float64)           # the binary format stores float weights
+    ow, owt, onid = orc.voc_transform(parent, desc, w32, is_leaf, L, feats, 4)
+    bw, bv = orc.voc_bow(ow, owt, 0, 0)
+    assert nw == int(is_leaf.sum())
+    assert np.array_equal(np.array(words, np.int32), bw)
+    assert np.array_equal(np.array(vals, np.float64).view(np.uint64), bv.view(np.uint64))
+    keep = owt > 0
+    ofv = orc.FeatVec(onid[keep])
+    assert ids == ofv.ids.tolist()
+    idx = np.nonzero(keep)[0]
+    for j, lst in enumerate(lists):
+        assert np.array_equal(lst, idx[ofv.feat[ofv.off[j]:ofv.off[j + 1]]])
