@@ -366,6 +366,34 @@ def main():
             matching["cpu_baseline"] = {"value": len(qs) * per / s, "unit": "pairs/s", "cores": thr, "kind": "port",
                                         "sample": f"{len(qs)} queries x {per} descriptors, reference bit-hack popcount"}
 
+    # ---- "next" row of the scope table: BoW assignment (DBoW2 transform) feeding the matcher, ORBvoc-shaped synthetic tree
+    bow = None
+    if not args.no_match:
+        k, L = 10, 6
+        n_nodes = (k ** (L + 1) - 1) // (k - 1)
+        rng = np.random.default_rng(21)
+        parent = ((np.arange(n_nodes, dtype=np.int64) - 1) // k).astype(np.int32)
+        parent[0] = 0
+        ndesc = rng.integers(0, 256, (n_nodes, 32), dtype=np.uint8)
+        is_leaf = (np.arange(n_nodes) >= (k ** L - 1) // (k - 1)).astype(np.uint8)
+        weights = np.where(is_leaf == 1, rng.uniform(0.1, 9.0, n_nodes), 0.0)
+        voc = orb.ORBVocabulary.from_arrays(k, L, parent, ndesc, weights, is_leaf, device=local_rank)
+        nd = 1 << 21
+        d_feat = torch.randint(0, 256, (nd, 32), dtype=torch.uint8, device="cuda")
+        d_w = torch.zeros(nd, dtype=torch.int32, device="cuda")
+        d_nid = torch.zeros(nd, dtype=torch.int32, device="cuda")
+        d_wt = torch.zeros(nd, dtype=torch.float64, device="cuda")
+
+        def bstep():
+            capi.check(capi.lib().orbv_transform_device(voc.handle, capi._p(d_feat), nd, 4, capi._p(d_w), capi._p(d_wt), capi._p(d_nid), stream))
+        for _ in range(3):
+            bstep()
+        bsteps = max(3, min(args.steps, 10))
+        bsecs = timed(bstep, bsteps)
+        bow = {"metric": "BoW assignment descriptors/s (k=10, L=6 vocabulary, levelsup=4)", "value": world * nd * bsteps / bsecs,
+               "unit": "descriptors/s", "hamming_distances_per_s": world * nd * bsteps * k * L / bsecs,
+               "config": {"workload": f"{nd} random descriptors per GPU per step through a synthetic {n_nodes}-node tree (35 MB, L2-resident)"}}
+
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -384,7 +412,7 @@ def main():
                        "keypoints_per_frame": kp_per_frame, "l2": "inputs_exceed_l2 (1.26 GB of frames per step per GPU)",
                        "parallelism": f"frame-sharded x{world}, no data-path collective", "numa_node_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "matching": matching,
+            "matching": matching, "bow": bow,
         })
     if world > 1:
         dist.destroy_process_group()
