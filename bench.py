@@ -304,6 +304,13 @@ def main():
                 "traffic": ({"fast": 287.2e6, "describe": 561.1e6, "blur": 526.9e6, "octree": 15.7e6}.get(dom, 0) * args.chunk / 256) or None,
                 "peak_source": peak_src, "avg_launch_ms": dom_launch_s * 1e3, "algorithmic_bytes_per_frame": stage_bytes[dom],
                 "stage_ms_per_step": {k: v * 1e3 for k, v in stage_s.items()},
+                # what actually bounds it: warp-instruction issue.  536.9 M warp-instructions per 256-frame k_fast_tma launch (ncu,
+                # profiles/r1_final_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
+                "issue": ({"warp_inst_per_launch": 536.9e6 * args.chunk / 256,
+                           "achieved_ginst_s": 536.9e6 * args.chunk / 256 / dom_launch_s / 1e9,
+                           "peak_ginst_s": 148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                           "frac": 536.9e6 * args.chunk / 256 / dom_launch_s / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6)}
+                          if dom == "fast" else None),
                 "step_hbm_frac": (B_FRAME * nF / (secs / args.steps) / 1e9) / hbm_peak,
                 "note": "640x480 pyramids are L2-resident and this stage is integer-issue bound, not HBM bound (SURVEY.md §7)"}
 
