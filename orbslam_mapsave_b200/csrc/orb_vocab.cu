@@ -20,42 +20,61 @@ struct orbv_vocabulary {
     std::vector<u8> desc, leaf;
     std::vector<double> weight;
     // device tree: children of node i are childList[childOff[i] .. childOff[i+1])
-    int *d_childOff = nullptr, *d_childList = nullptr, *d_wordId = nullptr;
+    int2* d_nodeRec = nullptr;
+    bool contiguous = false;
+    int maxChildren = 0;
+    int *d_childList = nullptr, *d_wordId = nullptr;
     u8* d_desc = nullptr;
     double* d_weight = nullptr;
     cudaStream_t stream = nullptr;
 };
 
-__global__ void __launch_bounds__(256) k_bow_transform(const int* __restrict__ childOff, const int* __restrict__ childList,
+// node record: {first child, number of children} when the children of every node are consecutive node ids (true for every
+// vocabulary DBoW2 itself created or saved: HKmeansStep appends the k children of a node together), else an index into the
+// generic child list.  LPD lanes cooperate on one descriptor (LPD = 16 covers k <= 16 with two descriptors per warp).
+template <int LPD, bool CONTIG>
+__global__ void __launch_bounds__(256) k_bow_transform(const int2* __restrict__ nodeRec, const int* __restrict__ childList,
                                                        const u8* __restrict__ ndesc, const double* __restrict__ nweight,
                                                        const int* __restrict__ nword, const u8* __restrict__ desc, int n, int L,
                                                        int levelsup, int* __restrict__ word_id, double* __restrict__ weight,
                                                        int* __restrict__ node_id) {
-    const int lane = threadIdx.x & 31, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= n) return;
-    const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)i * 32);
+    const int sub = (threadIdx.x & 31) / LPD, sl = threadIdx.x & (LPD - 1);
+    const int i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / LPD) + sub;
+    const bool live = i < n;
+    const uint4* dp = reinterpret_cast<const uint4*>(desc + (size_t)(live ? i : 0) * 32);
     const uint4 a = __ldg(dp), b = __ldg(dp + 1);
     const int nid_level = L - levelsup;
     int cur = 0, level = 0, nid = 0;
-    for (;;) {
-        const int c0 = childOff[cur], nc = childOff[cur + 1] - c0;
-        if (nc == 0) break;                                            // isLeaf()
-        ++level;
+    bool done = !live;
+    while (__any_sync(0xffffffffu, !done)) {
         u32 best = 0xFFFFFFFFu;
-        for (int j = lane; j < nc; j += 32) {                          // k <= 32 in practice: one round
-            const int child = childList[c0 + j];
-            const uint4* cp = reinterpret_cast<const uint4*>(ndesc + (size_t)child * 32);
-            const uint4 x = __ldg(cp), y = __ldg(cp + 1);
-            const int d = __popc(a.x ^ x.x) + __popc(a.y ^ x.y) + __popc(a.z ^ x.z) + __popc(a.w ^ x.w) +
-                          __popc(b.x ^ y.x) + __popc(b.y ^ y.y) + __popc(b.z ^ y.z) + __popc(b.w ^ y.w);
-            best = min(best, ((u32)d << 20) | (u32)j);                 // strict `d < best_d` in child order == min over (d, order)
+        int c0 = 0;
+        if (!done) {
+            const int2 rec = __ldg(nodeRec + cur);
+            c0 = rec.x;
+            const int nc = rec.y;
+            if (nc == 0) done = true;                                  // isLeaf()
+            else {
+                for (int j = sl; j < nc; j += LPD) {
+                    const int child = CONTIG ? c0 + j : childList[c0 + j];
+                    const uint4* cp = reinterpret_cast<const uint4*>(ndesc + (size_t)child * 32);
+                    const uint4 x = __ldg(cp), y = __ldg(cp + 1);
+                    const int d = __popc(a.x ^ x.x) + __popc(a.y ^ x.y) + __popc(a.z ^ x.z) + __popc(a.w ^ x.w) +
+                                  __popc(b.x ^ y.x) + __popc(b.y ^ y.y) + __popc(b.z ^ y.z) + __popc(b.w ^ y.w);
+                    best = min(best, ((u32)d << 20) | (u32)j);         // strict `d < best_d` in child order == min over (d, order)
+                }
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-        cur = childList[c0 + (int)(best & 0xFFFFF)];
-        if (level == nid_level) nid = cur;
+        for (int o = LPD / 2; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (!done) {
+            ++level;
+            const int j = (int)(best & 0xFFFFF);
+            cur = CONTIG ? c0 + j : childList[c0 + j];
+            if (level == nid_level) nid = cur;
+        }
     }
-    if (lane == 0) {
+    if (live && sl == 0) {
         if (word_id) word_id[i] = nword[cur];
         if (weight) weight[i] = nweight[cur];
         if (node_id) node_id[i] = nid;
@@ -79,13 +98,27 @@ static int build_device(orbv_vocabulary* v) {
     // DBoW2 decides "leaf" by children.empty(); the file flag must agree or transform() would index m_words wrongly
     for (int i = 1; i < n; i++)
         ORB_REQUIRE((off[i + 1] == off[i]) == (v->leaf[i] != 0), ORB_ERR_ARG, "vocabulary node %d: leaf flag and child list disagree", i);
+    // children consecutive?  then a node record is {first child, count}; else {offset into the child list, count}
+    std::vector<int2> rec(n);
+    v->contiguous = true;
+    v->maxChildren = 0;
+    for (int i = 0; i < n; i++) {
+        const int c0 = off[i], nc = off[i + 1] - off[i];
+        v->maxChildren = std::max(v->maxChildren, nc);
+        for (int j = 1; j < nc; j++)
+            if (list[c0 + j] != list[c0] + j) v->contiguous = false;
+    }
+    for (int i = 0; i < n; i++) {
+        const int c0 = off[i], nc = off[i + 1] - off[i];
+        rec[i] = make_int2(nc == 0 ? 0 : (v->contiguous ? list[c0] : c0), nc);
+    }
     ORB_CUDA_TRY(cudaSetDevice(v->device));
-    ORB_CUDA_TRY(cudaMalloc(&v->d_childOff, (n + 1) * sizeof(int)));
+    ORB_CUDA_TRY(cudaMalloc(&v->d_nodeRec, n * sizeof(int2)));
     ORB_CUDA_TRY(cudaMalloc(&v->d_childList, list.size() * sizeof(int)));
     ORB_CUDA_TRY(cudaMalloc(&v->d_wordId, n * sizeof(int)));
     ORB_CUDA_TRY(cudaMalloc(&v->d_desc, (size_t)n * 32));
     ORB_CUDA_TRY(cudaMalloc(&v->d_weight, n * sizeof(double)));
-    ORB_CUDA_TRY(cudaMemcpy(v->d_childOff, off.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    ORB_CUDA_TRY(cudaMemcpy(v->d_nodeRec, rec.data(), n * sizeof(int2), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(v->d_childList, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(v->d_wordId, word.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     ORB_CUDA_TRY(cudaMemcpy(v->d_desc, v->desc.data(), (size_t)n * 32, cudaMemcpyHostToDevice));
@@ -97,7 +130,7 @@ static int build_device(orbv_vocabulary* v) {
 extern "C" void orbv_destroy(orbv_vocabulary* v) {
     if (!v) return;
     cudaSetDevice(v->device);
-    cudaFree(v->d_childOff); cudaFree(v->d_childList); cudaFree(v->d_wordId); cudaFree(v->d_desc); cudaFree(v->d_weight);
+    cudaFree(v->d_nodeRec); cudaFree(v->d_childList); cudaFree(v->d_wordId); cudaFree(v->d_desc); cudaFree(v->d_weight);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
 }
@@ -215,8 +248,13 @@ extern "C" int orbv_transform_device(const orbv_vocabulary* v, const uint8_t* d_
     ORB_REQUIRE(v && (d_desc || n == 0) && n >= 0, ORB_ERR_ARG, "bad arguments");
     if (n == 0) return ORB_OK;
     cudaStream_t st = stream ? (cudaStream_t)stream : v->stream;
-    k_bow_transform<<<orb_div_up(n, 8), 256, 0, st>>>(v->d_childOff, v->d_childList, v->d_desc, v->d_weight, v->d_wordId, d_desc, n, v->L,
-                                                      levelsup, d_word_id, d_weight, d_node_id);
+#define BOW_LAUNCH(LPD, CT)                                                                                                   \
+    k_bow_transform<LPD, CT><<<orb_div_up(n, 8 * (32 / LPD)), 256, 0, st>>>(v->d_nodeRec, v->d_childList, v->d_desc, v->d_weight, \
+                                                                             v->d_wordId, d_desc, n, v->L, levelsup, d_word_id,    \
+                                                                             d_weight, d_node_id)
+    if (v->maxChildren <= 16) { if (v->contiguous) BOW_LAUNCH(16, true); else BOW_LAUNCH(16, false); }
+    else { if (v->contiguous) BOW_LAUNCH(32, true); else BOW_LAUNCH(32, false); }
+#undef BOW_LAUNCH
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
 }

@@ -11,9 +11,11 @@ from vocab_util import make_tree
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("k,L,ragged,levelsup", [(10, 3, False, 1), (10, 4, False, 4), (10, 4, False, 2), (7, 5, True, 3), (20, 2, False, 0), (3, 6, True, 4)])
-def test_transform_matches_oracle(k, L, ragged, levelsup):
-    parent, desc, weight, is_leaf = make_tree(k, L, seed=k * 10 + L, ragged=ragged)
+@pytest.mark.parametrize("k,L,ragged,levelsup,interleave", [(10, 3, False, 1, False), (10, 4, False, 4, False), (10, 4, False, 2, True),
+                                                            (7, 5, True, 3, False), (20, 2, False, 0, False), (3, 6, True, 4, True),
+                                                            (18, 3, True, 1, True)])
+def test_transform_matches_oracle(k, L, ragged, levelsup, interleave):
+    parent, desc, weight, is_leaf = make_tree(k, L, seed=k * 10 + L, ragged=ragged, interleave=interleave)
     voc = orb.ORBVocabulary.from_arrays(k, L, parent, desc, weight, is_leaf)
     info = voc.info()
     assert info["n_nodes"] == len(parent) and info["n_words"] == int(is_leaf.sum())

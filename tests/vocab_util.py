@@ -2,7 +2,7 @@
 import numpy as np
 
 
-def make_tree(k, L, seed, ragged=False):
+def make_tree(k, L, seed, ragged=False, interleave=False):
     """Random vocabulary tree in the reference's node order (breadth-first like ORBvoc.txt is not required: any order with
     parent < child works).  Returns parent, desc, weight, is_leaf."""
     rng = np.random.default_rng(seed)
@@ -10,14 +10,22 @@ def make_tree(k, L, seed, ragged=False):
     frontier = [0]
     for lev in range(1, L + 1):
         nxt = []
+        plan = []
         for p in frontier:
             nch = k if not ragged else int(rng.integers(1, k + 1))
             if ragged and lev > 1 and rng.random() < 0.15:
                 continue                                       # an early leaf
-            for _ in range(nch):
-                parent.append(p)
-                level.append(lev)
-                nxt.append(len(parent) - 1)
+            plan.append([p, nch])
+        if interleave:                                         # siblings are NOT consecutive node ids (generic child-list path)
+            while any(c > 0 for _, c in plan):
+                for e in plan:
+                    if e[1] > 0:
+                        e[1] -= 1
+                        parent.append(e[0]); level.append(lev); nxt.append(len(parent) - 1)
+        else:
+            for p, nch in plan:
+                for _ in range(nch):
+                    parent.append(p); level.append(lev); nxt.append(len(parent) - 1)
         frontier = nxt
     n = len(parent)
     desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
