@@ -215,6 +215,13 @@ int orbv_transform(const orbv_vocabulary* voc, const uint8_t* desc, int n, int l
 int orbv_transform_device(const orbv_vocabulary* voc, const uint8_t* d_desc, int n, int levelsup, int* d_word_id, double* d_weight,
                           int* d_node_id, void* stream);
 
+/* Replaces the selection loop of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:483-548) for a batch
+ * of map points: set s holds descriptors [offsets[s], offsets[s+1]) of `desc` (the observations' descriptors in map order);
+ * best_idx[s] = index inside the set of the descriptor with the least median Hamming distance to the set
+ * (median = sorted row[int(0.5*(N-1))] incl. the zero self-distance, first index wins ties), -1 for an empty set.
+ * Sets of more than 1024 descriptors are rejected (ORB_ERR_ARG).  Host pointers. */
+int orbm_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_sets, int* best_idx, int device);
+
 /* POPC issue-rate microbenchmark (defines the matching roofline): returns measured 32-bit POPC results
  * per second on `device` over a register-resident loop. */
 int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);

@@ -1012,4 +1012,26 @@ int orc_voc_bow(int n, const int* word_id, const double* weight, int weighting, 
     return (int)v.size();
 }
 
+
+// MapPoint::ComputeDistinctiveDescriptors selection (src/MapPoint.cc:511-541) for one set of N descriptors
+int orc_distinctive(const u8* desc, int N) {
+    if (N <= 0) return -1;
+    std::vector<std::vector<float> > D(N, std::vector<float>(N, 0.f));
+    for (int i = 0; i < N; i++) {
+        D[i][i] = 0;
+        for (int j = i + 1; j < N; j++) {
+            const int dij = descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+            D[i][j] = (float)dij; D[j][i] = (float)dij;
+        }
+    }
+    int BestMedian = 0x7fffffff, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        std::vector<int> v(D[i].begin(), D[i].end());
+        std::sort(v.begin(), v.end());
+        const int median = v[(size_t)(0.5 * (N - 1))];
+        if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    return BestIdx;
+}
+
 }  // extern "C"

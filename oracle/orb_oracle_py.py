@@ -88,6 +88,8 @@ def lib():
                                                [vp, f32, f32, vp, vp, i32, i32, vp, vp])
         L.orc_voc_transform.restype = None
         L.orc_voc_transform.argtypes = [i32, vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, vp]
+        L.orc_distinctive.restype = i32
+        L.orc_distinctive.argtypes = [vp, i32]
         L.orc_voc_bow.restype = i32
         L.orc_voc_bow.argtypes = [i32, vp, vp, i32, i32, vp, vp, i32]
         _lib = L
@@ -345,3 +347,8 @@ def voc_bow(word_id, weight, weighting=0, scoring=0):
     ow, ov = np.zeros(cap, np.int32), np.zeros(cap, np.float64)
     k = lib().orc_voc_bow(len(word_id), _p(word_id), _p(weight), int(weighting), int(scoring), _p(ow), _p(ov), cap)
     return ow[:k], ov[:k]
+
+
+def distinctive(desc):
+    desc = _u8(desc).reshape(-1, 32)
+    return lib().orc_distinctive(_p(desc), len(desc))

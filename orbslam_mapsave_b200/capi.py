@@ -28,7 +28,7 @@ SYMBOLS = [
     "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device",
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
-    "orbm_popc_peak",
+    "orbm_popc_peak", "orbm_distinctive_descriptors",
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
     "orbv_transform_device",
 ]
@@ -113,6 +113,8 @@ def lib():
     L.orbm_three_maxima.argtypes = [vp, i32, vp, i32]
     L.orbm_popc_peak.restype = i32
     L.orbm_popc_peak.argtypes = [i32, vp, vp]
+    L.orbm_distinctive_descriptors.restype = i32
+    L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, i32]
     L.orbv_create.restype = i32
     L.orbv_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, vp, i32]
     L.orbv_load_text.restype = i32

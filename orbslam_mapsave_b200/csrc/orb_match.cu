@@ -414,6 +414,45 @@ __global__ void __launch_bounds__(256) k_search_tri_finish(DevView A, DevView B,
     if (tid == 0) cnt[0] = base;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:483-548), one warp per map point.  Row i of the N x N distance matrix is
+// produced by the lanes (descriptor i broadcast), kept in shared memory, and its median = the smallest value v with
+// #{d <= v} >= int(0.5*(N-1)) + 1, found by a 9-step binary search over v in [0, 256] with ballot counts.
+#define DD_WARPS 4
+#define DD_MAXN 1024
+__global__ void __launch_bounds__(32 * DD_WARPS) k_distinctive(const u8* __restrict__ desc, const int* __restrict__ offsets, int n_sets,
+                                                                int* __restrict__ best_idx) {
+    __shared__ u16 s_row[DD_WARPS][DD_MAXN];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, s = blockIdx.x * DD_WARPS + w;
+    if (s >= n_sets) return;
+    const int o = offsets[s], N = offsets[s + 1] - o;
+    if (N <= 0) { if (lane == 0) best_idx[s] = -1; return; }
+    const int m = (int)(0.5 * (N - 1));
+    int bestMedian = 0x7fffffff, bestIdx = 0;
+    for (int i = 0; i < N; i++) {
+        u32 di[8];
+        load_desc(desc + (size_t)(o + i) * 32, di);
+        for (int j = lane; j < N; j += 32) {
+            u32 dj[8];
+            load_desc(desc + (size_t)(o + j) * 32, dj);
+            s_row[w][j] = (u16)ham256(di, dj);
+        }
+        __syncwarp();
+        int lo = 0, hi = 256;                                            // smallest v with count(d <= v) >= m + 1
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int j0 = 0; j0 < N; j0 += 32) {
+                const int j = j0 + lane;
+                c += __popc(__ballot_sync(0xffffffffu, j < N && (int)s_row[w][j] <= mid));
+            }
+            if (c >= m + 1) hi = mid; else lo = mid + 1;
+        }
+        if (lo < bestMedian) { bestMedian = lo; bestIdx = i; }
+        __syncwarp();
+    }
+    if (lane == 0) best_idx[s] = bestIdx;
+}
+
 // POPC issue-rate microbenchmark: 8 independent xor+popc chains per thread, register resident.
 __global__ void k_popc_peak(u32* out, int iters) {
     u32 a[8], acc[8];
@@ -772,6 +811,30 @@ extern "C" int orbm_search_for_triangulation(const orbm_view* kf1, const orbm_vi
     }
     *n_pairs = cnt[0]; *n_matches = cnt[1];
     return ORB_OK;
+}
+
+extern "C" int orbm_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_sets, int* best_idx, int device) {
+    ORB_REQUIRE(offsets && best_idx && n_sets >= 0, ORB_ERR_ARG, "bad arguments");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n_sets == 0) return ORB_OK;
+    const int total = offsets[n_sets];
+    ORB_REQUIRE(total >= 0 && (desc || total == 0), ORB_ERR_ARG, "bad arguments");
+    for (int s2 = 0; s2 < n_sets; s2++)
+        ORB_REQUIRE(offsets[s2 + 1] >= offsets[s2] && offsets[s2 + 1] - offsets[s2] <= DD_MAXN, ORB_ERR_ARG,
+                    "set %d has %d descriptors (limit %d)", s2, offsets[s2 + 1] - offsets[s2], DD_MAXN);
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, pad((size_t)total * 32) + pad((size_t)(n_sets + 1) * 4) + pad((size_t)n_sets * 4)))) return rc;
+    const u8* dd;
+    const int* doff;
+    if ((rc = upload(A, desc, (size_t)total * 32, &dd))) return rc;
+    if ((rc = upload(A, offsets, (size_t)n_sets + 1, &doff))) return rc;
+    if ((rc = A.flush())) return rc;
+    int* dbest = A.take<int>(n_sets);
+    k_distinctive<<<orb_div_up(n_sets, DD_WARPS), 32 * DD_WARPS, 0, A.stream>>>(dd, doff, n_sets, dbest);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if ((rc = A.fetch(best_idx, dbest, (size_t)n_sets))) return rc;
+    return A.finish();
 }
 
 extern "C" int orbm_three_maxima(const int* histo, int n_bins, int* ind, int device) {

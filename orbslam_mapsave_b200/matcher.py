@@ -102,6 +102,16 @@ class ORBmatcher:
         return tuple(int(v) for v in ind)
 
 
+def distinctive_descriptors(desc, offsets, device=0):
+    """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (src/MapPoint.cc:483-548): index, inside each set
+    desc[offsets[s]:offsets[s+1]], of the descriptor with the least median distance to the set."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    out = np.zeros(max(len(offsets) - 1, 1), np.int32)
+    capi.check(capi.lib().orbm_distinctive_descriptors(capi._p(desc), capi._p(offsets), len(offsets) - 1, capi._p(out), device))
+    return out[:len(offsets) - 1]
+
+
 def popc_peak(device=0):
     v, clk = C.c_double(), C.c_double()
     capi.check(capi.lib().orbm_popc_peak(device, C.byref(v), C.byref(clk)))

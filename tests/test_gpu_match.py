@@ -200,3 +200,22 @@ def test_config3_extract_then_match_consecutive_keyframes():
     dx, dy = kb["x"] - ka["x"], kb["y"] - ka["y"]
     ok = (np.abs(dx - 7) <= 2.5 * ka["size"] / 31) & (np.abs(dy - 4) <= 2.5 * ka["size"] / 31)
     assert good.sum() > 300 and ok.mean() > 0.9, (int(good.sum()), float(ok.mean()))
+
+
+def test_distinctive_descriptors_vs_oracle():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:483-548) for a ragged batch of map points."""
+    rng = np.random.default_rng(8)
+    sizes = [1, 2, 3, 0, 5, 17, 32, 33, 64, 100, 257, 7, 2, 1000] + [int(v) for v in rng.integers(2, 40, 200)]
+    sets = []
+    for i, n in enumerate(sizes):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.stack([_flip(base, int(rng.integers(0, 60)), rng) for _ in range(n)]) if n else np.zeros((0, 32), np.uint8)
+        if n >= 4 and i % 3 == 0:
+            d[2] = d[1]                      # exact duplicates: ties in the medians, first index must win
+        sets.append(d)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    got = orb.distinctive_descriptors(np.concatenate(sets), offsets)
+    want = np.array([orc.distinctive(d) for d in sets], np.int32)
+    assert np.array_equal(got, want)
+    with pytest.raises(orb.OrbError):
+        orb.distinctive_descriptors(np.zeros((1025, 32), np.uint8), np.array([0, 1025], np.int32))
