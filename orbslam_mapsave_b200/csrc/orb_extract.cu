@@ -1332,7 +1332,8 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
             const int perSM = std::max(1, std::min(8, (int)((prop.sharedMemPerMultiprocessor - 4096) / (ex->fwSmem + 1024))));
             ex->fwGrid = prop.multiProcessorCount * perSM;
             static std::mutex amu2;
-            static size_t maxFw = 0;
+            static size_t maxFwDev[64] = {0};                         // the opt-in is per function AND per device
+            size_t& maxFw = maxFwDev[ex->device & 63];
             std::lock_guard<std::mutex> lk(amu2);
             if (ex->fwSmem > maxFw) {
                 ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, ORBX_FAST_SPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
@@ -1343,7 +1344,8 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     }
     {   // dynamic shared-memory opt-in is per function, shared by all handles: only ever raise it
         static std::mutex amu;
-        static size_t maxFast = 0, maxOct = 0;
+        static size_t maxFastDev[64] = {0}, maxOctDev[64] = {0};     // per function AND per device
+        size_t &maxFast = maxFastDev[ex->device & 63], &maxOct = maxOctDev[ex->device & 63];
         std::lock_guard<std::mutex> lk(amu);
         if (ex->fastSmem > maxFast) {
             ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
