@@ -364,7 +364,13 @@ def main():
                     "config": {"workload": f"all-pairs: {q1 - q0} query keyframes/GPU x {ndb} keyframes x {per} descriptors",
                                "collective": "all_gather(match-count table)" if world > 1 else "none"},
                     "roofline": {"bound": "popc", "achieved": pairs / msecs * 8 / 1e12, "peak": popc / 1e12 * world, "unit": "TPOPC/s",
-                                 "frac": pairs / msecs * 8 / (popc * world), "peak_source": "orbm_popc_peak microbenchmark, this run"}}
+                                 "frac": pairs / msecs * 8 / (popc * world), "peak_source": "orbm_popc_peak microbenchmark, this run",
+                                 "note": "achieved = ALGORITHMIC POPC (8 per pair, SURVEY 8d); the kernel EXECUTES 4 POPC + 18.5 ALU-pipe ops "
+                                         "per pair (carry-save compression of the XOR words), so frac > 1 is expected",
+                                 "executed": {"popc_per_pair": 4, "alu_ops_per_pair": 18.5,
+                                              "popc_pipe_frac": pairs / msecs * 4 / (popc * world),
+                                              "alu_pipe_frac": pairs / msecs * 18.5 / (148 * 64 * clk * world),
+                                              "alu_peak_source": "148 SMs x 64 lanes/clk (B300_MICROARCH: alu pipe rt_SMSP=2) x SM clock"}}}
         if rank == 0 and not args.no_cpu:
             from oracle import orb_oracle_py as orc
             thr = host_threads()
