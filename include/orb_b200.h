@@ -222,6 +222,68 @@ int orbv_transform_device(const orbv_vocabulary* voc, const uint8_t* d_desc, int
  * Sets of more than 1024 descriptors are rejected (ORB_ERR_ARG).  Host pointers. */
 int orbm_distinctive_descriptors(const uint8_t* desc, const int* offsets, int n_sets, int* best_idx, int device);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Projection / window searches (the first "next" row): the ORBmatcher searches that look for a descriptor
+ * inside a window of a Frame's / KeyFrame's feature grid (GetFeaturesInArea) instead of inside a vocabulary node.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* The side that is searched: the fields of Frame (include/Frame.h:98,141-197) / KeyFrame (include/KeyFrame.h:146-204) that
+ * GetFeaturesInArea (src/Frame.cc:445-498, src/KeyFrame.cc:1311-1350) and the candidate loops read.  mGrid is flattened to
+ * CSR: cell (ix, iy) = mGrid[ix][iy] has index ix*grid_rows + iy and holds cell_features[cell_offsets[c] .. cell_offsets[c+1])
+ * in push order (AssignFeaturesToGrid, src/Frame.cc:341-356, note PosInGrid ROUNDS, :500-510). */
+typedef struct orbm_grid_view {
+    int n;                          /* N */
+    const uint8_t* desc;            /* mDescriptors, n x 32 */
+    const float* x;                 /* mvKeysUn[i].pt.x */
+    const float* y;                 /* mvKeysUn[i].pt.y */
+    const int* octave;              /* mvKeysUn[i].octave */
+    const float* angle;             /* mvKeysUn[i].angle (NULL when the orientation check is off) */
+    const float* uright;            /* mvuRight[i] (NULL = monocular, no stereo gate) */
+    const uint8_t* blocked;         /* per feature, 1 = the candidate loop `continue`s on it from the start
+                                       (e.g. mvpMapPoints[i] && mvpMapPoints[i]->Observations() > 0); NULL = none */
+    int grid_cols, grid_rows;       /* FRAME_GRID_COLS x FRAME_GRID_ROWS (64 x 48) / mnGridCols x mnGridRows */
+    float min_x, min_y, max_x, max_y;   /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+    float inv_w, inv_h;             /* mfGridElementWidthInv, mfGridElementHeightInv */
+    const int* cell_offsets;        /* grid_cols*grid_rows + 1 */
+    const int* cell_features;
+    const float* scale_factors;     /* mvScaleFactors */
+    int n_levels;
+} orbm_grid_view;
+
+/* Replaces int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th)
+ * (src/ORBmatcher.cc:45-129; caller Tracking::SearchLocalPoints).  Per map point, as left by Frame::isInFrustum
+ * (src/Frame.cc:373-443): in_view = mbTrackInView && !isBad(); proj_x/proj_y/proj_xr = mTrackProjX/Y/XR;
+ * level = mnTrackScaleLevel; view_cos = mTrackViewCos; desc = GetDescriptor(); claims = Observations() > 0 (a feature
+ * given to such a point is skipped by later points, :87-89).
+ * owner[F.n] receives, per feature, the index of the LAST map point the reference stores in F.mvpMapPoints[idx], or -1 if
+ * the reference leaves that entry alone.  *n_matches = the reference's return value. */
+int orbm_search_by_projection_map(const orbm_grid_view* frame, int n_points, const uint8_t* in_view, const float* proj_x,
+                                  const float* proj_y, const float* proj_xr, const int* level, const float* view_cos,
+                                  const uint8_t* desc, const uint8_t* claims, float th, float nnratio,
+                                  int* owner, int* n_matches, int device);
+
+/* Replaces int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
+ * (src/ORBmatcher.cc:1331-1463; caller Tracking::TrackWithMotionModel, the per-frame tracking search).
+ * cur: CurrentFrame (blocked = mvpMapPoints[i] && Observations() > 0).  Tcw_cur / Tcw_last: rows 0..2 of mTcw, row-major
+ * 3x4 float.  Per LastFrame feature i (n_last of them): has_point = mvpMapPoints[i] && !mvbOutlier[i]; world = GetWorldPos()
+ * (3 floats); octave = LastFrame.mvKeys[i].octave; angle = LastFrame.mvKeysUn[i].angle; desc = the MAP POINT's
+ * GetDescriptor(); claims = Observations() > 0.
+ * owner[cur.n]: index i of the LastFrame feature whose point ends up in CurrentFrame.mvpMapPoints[idx]; -1 = entry left
+ * alone; -2 = entry set to NULL by the rotation-consistency cull (:1446-1458).  *n_matches = the return value. */
+int orbm_search_by_projection_frame(const orbm_grid_view* cur, const float* Tcw_cur, const float* Tcw_last,
+                                    float fx, float fy, float cx, float cy, float mbf, float mb,
+                                    int n_last, const uint8_t* has_point, const float* world, const int* octave,
+                                    const float* angle, const uint8_t* desc, const uint8_t* claims,
+                                    float th, int mono, int check_orientation, int* owner, int* n_matches, int device);
+
+/* Replaces int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+ * vector<int>& vnMatches12, int windowSize) (src/ORBmatcher.cc:408-523; monocular initialisation).
+ * f2: F2.  Per F1 feature (n1): desc1, octave1 = mvKeysUn[i].octave, angle1, prev_xy = vbPrevMatched (2 floats each, updated
+ * in place for matched features, :516-519).  matches12[n1] = vnMatches12.  *n_matches = the return value. */
+int orbm_search_for_initialization(const orbm_grid_view* f2, int n1, const uint8_t* desc1, const int* octave1,
+                                   const float* angle1, float* prev_xy, int window_size, float nnratio,
+                                   int check_orientation, int* matches12, int* n_matches, int device);
+
 /* POPC issue-rate microbenchmark (defines the matching roofline): returns measured 32-bit POPC results
  * per second on `device` over a register-resident loop. */
 int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cfloat>
 #include <cstdint>
@@ -1032,6 +1033,221 @@ int orc_distinctive(const u8* desc, int N) {
         if (median < BestMedian) { BestMedian = median; BestIdx = i; }
     }
     return BestIdx;
+}
+
+
+// ---- projection / window searches ----------------------------------------------------------------------------
+// The Frame/KeyFrame side that is searched, flat (include/Frame.h:98,141-197): same layout as orbm_grid_view of the product ABI.
+struct orc_grid_view {
+    int n;
+    const u8* desc; const float* x; const float* y; const int* octave; const float* angle; const float* uright; const u8* blocked;
+    int grid_cols, grid_rows;
+    float min_x, min_y, max_x, max_y, inv_w, inv_h;
+    const int* cell_offsets; const int* cell_features;
+    const float* scale_factors; int n_levels;
+};
+
+// Frame::AssignFeaturesToGrid + PosInGrid, src/Frame.cc:341-356, 500-510 (note: round, not floor).  cell index = ix*rows + iy.
+// Writes CSR (offsets[cols*rows+1], features[<= n]); returns the number of features placed.
+int orc_assign_features_to_grid(int n, const float* x, const float* y, int cols, int rows, float min_x, float min_y, float inv_w,
+                                float inv_h, int* offsets, int* features) {
+    std::vector<std::vector<int> > grid((size_t)cols * rows);
+    for (int i = 0; i < n; i++) {
+        const int posX = (int)std::round((x[i] - min_x) * inv_w);
+        const int posY = (int)std::round((y[i] - min_y) * inv_h);
+        if (posX < 0 || posX >= cols || posY < 0 || posY >= rows) continue;
+        grid[(size_t)posX * rows + posY].push_back(i);
+    }
+    int k = 0;
+    offsets[0] = 0;
+    for (size_t c = 0; c < grid.size(); c++) {
+        for (int i : grid[c]) features[k++] = i;
+        offsets[c + 1] = k;
+    }
+    return k;
+}
+
+// Frame::GetFeaturesInArea, src/Frame.cc:445-498 (KeyFrame::GetFeaturesInArea, src/KeyFrame.cc:1311-1350, is the same without
+// the level test: call with minLevel = maxLevel = -1).
+static void features_in_area(const orc_grid_view& F, float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) {
+    out.clear();
+    const int nMinCellX = std::max(0, (int)std::floor((x - F.min_x - r) * F.inv_w));
+    if (nMinCellX >= F.grid_cols) return;
+    const int nMaxCellX = std::min(F.grid_cols - 1, (int)std::ceil((x - F.min_x + r) * F.inv_w));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)std::floor((y - F.min_y - r) * F.inv_h));
+    if (nMinCellY >= F.grid_rows) return;
+    const int nMaxCellY = std::min(F.grid_rows - 1, (int)std::ceil((y - F.min_y + r) * F.inv_h));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const int c = ix * F.grid_rows + iy;
+            for (int j = F.cell_offsets[c]; j < F.cell_offsets[c + 1]; j++) {
+                const int idx = F.cell_features[j];
+                if (bCheckLevels) {
+                    if (F.octave[idx] < minLevel) continue;
+                    if (maxLevel >= 0)
+                        if (F.octave[idx] > maxLevel) continue;
+                }
+                const float distx = F.x[idx] - x;
+                const float disty = F.y[idx] - y;
+                if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+            }
+        }
+}
+
+// SearchByProjection(Frame&, const vector<MapPoint*>&, th), ORBmatcher.cc:45-129.  owner[F.n]: last map point stored per feature.
+int orc_search_projection_map(const orc_grid_view* Fp, int n_points, const u8* in_view, const float* proj_x, const float* proj_y,
+                              const float* proj_xr, const int* level, const float* view_cos, const u8* desc, const u8* claims,
+                              float th, float nnratio, int* owner) {
+    const orc_grid_view& F = *Fp;
+    for (int i = 0; i < F.n; i++) owner[i] = -1;
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < n_points; iMP++) {
+        if (!in_view[iMP]) continue;                                   // !mbTrackInView || isBad()
+        const int nPredictedLevel = level[iMP];
+        float r = view_cos[iMP] > 0.998 ? 2.5f : 4.0f;                 // RadiusByViewingCos, :131-137
+        if (bFactor) r *= th;
+        features_in_area(F, proj_x[iMP], proj_y[iMP], r * F.scale_factors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel, vIndices);
+        if (vIndices.empty()) continue;
+        const u8* MPdescriptor = desc + (size_t)iMP * 32;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            const bool hasObs = owner[idx] >= 0 ? claims[owner[idx]] != 0 : (F.blocked && F.blocked[idx]);
+            if (hasObs) continue;                                      // mvpMapPoints[idx] && Observations() > 0
+            if (F.uright && F.uright[idx] > 0) {
+                const float er = std::fabs(proj_xr[iMP] - F.uright[idx]);
+                if (er > r * F.scale_factors[nPredictedLevel]) continue;
+            }
+            const int dist = descriptor_distance(MPdescriptor, F.desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = F.octave[idx]; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = F.octave[idx]; bestDist2 = dist; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            owner[bestIdx] = iMP;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+// SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono), ORBmatcher.cc:1331-1463.
+// 3x3 * 3x1 + 3x1 products follow cv::gemm for small float matrices as observed with cv2 4.13: float32, left to right, no FMA
+// (tests/golden/make_golden.py pins this).  owner[cur.n]: LastFrame feature index, -1 untouched, -2 set to NULL by the cull.
+static inline void rt_apply(const float* T /*3x4*/, const float* p, float* out) {
+    for (int r = 0; r < 3; r++) out[r] = ((T[4 * r] * p[0] + T[4 * r + 1] * p[1]) + T[4 * r + 2] * p[2]) + T[4 * r + 3];
+}
+int orc_search_projection_frame(const orc_grid_view* Cp, const float* Tcw, const float* Tlw, float fx, float fy, float cx, float cy,
+                                float mbf, float mb, int n_last, const u8* has_point, const float* world, const int* octave,
+                                const float* angle, const u8* desc, const u8* claims, float th, int mono, int checkOri, int* owner) {
+    const orc_grid_view& CF = *Cp;
+    for (int i = 0; i < CF.n; i++) owner[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    // twc = -Rcw.t()*tcw ; tlc = Rlw*twc + tlw  (:1344-1352)
+    float twc[3], tlc[3];
+    for (int r = 0; r < 3; r++) twc[r] = -((Tcw[0 * 4 + r] * Tcw[3] + Tcw[1 * 4 + r] * Tcw[7]) + Tcw[2 * 4 + r] * Tcw[11]);
+    rt_apply(Tlw, twc, tlc);
+    const bool bForward = tlc[2] > mb && !mono;
+    const bool bBackward = -tlc[2] > mb && !mono;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < n_last; i++) {
+        if (!has_point[i]) continue;                                   // pMP && !mvbOutlier[i]
+        float x3Dc[3];
+        rt_apply(Tcw, world + 3 * (size_t)i, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = 1.0 / x3Dc[2];
+        if (invzc < 0) continue;
+        float u = fx * xc * invzc + cx;
+        float v = fy * yc * invzc + cy;
+        if (u < CF.min_x || u > CF.max_x) continue;
+        if (v < CF.min_y || v > CF.max_y) continue;
+        const int nLastOctave = octave[i];
+        float radius = th * CF.scale_factors[nLastOctave];
+        if (bForward) features_in_area(CF, u, v, radius, nLastOctave, -1, vIndices2);
+        else if (bBackward) features_in_area(CF, u, v, radius, 0, nLastOctave, vIndices2);
+        else features_in_area(CF, u, v, radius, nLastOctave - 1, nLastOctave + 1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const u8* dMP = desc + (size_t)i * 32;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const bool hasObs = owner[i2] >= 0 ? claims[owner[i2]] != 0 : (owner[i2] == -1 && CF.blocked && CF.blocked[i2]);
+            if (hasObs) continue;
+            if (CF.uright && CF.uright[i2] > 0) {
+                const float ur = u - mbf * invzc;
+                const float er = std::fabs(ur - CF.uright[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(dMP, CF.desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            owner[bestIdx2] = i;
+            nmatches++;
+            if (checkOri) rotHist[rot_bin(angle[i], CF.angle[bestIdx2])].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rotHist[i]) { owner[j] = -2; nmatches--; }
+    }
+    return nmatches;
+}
+
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize), ORBmatcher.cc:408-523.
+int orc_search_initialization(const orc_grid_view* F2p, int n1, const u8* desc1, const int* octave1, const float* angle1,
+                              float* prev_xy, int windowSize, float nnratio, int checkOri, int* vnMatches12) {
+    const orc_grid_view& F2 = *F2p;
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) vnMatches12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vMatchedDistance(F2.n, INT_MAX), vnMatches21(F2.n, -1);
+    std::vector<int> vIndices2;
+    for (int i1 = 0; i1 < n1; i1++) {
+        const int level1 = octave1[i1];
+        if (level1 > 0) continue;
+        features_in_area(F2, prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)windowSize, level1, level1, vIndices2);
+        if (vIndices2.empty()) continue;
+        const u8* d1 = desc1 + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = descriptor_distance(d1, F2.desc + (size_t)i2 * 32);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) { bestDist2 = dist; }
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                vnMatches12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (checkOri) rotHist[rot_bin(angle1[i1], F2.angle[bestIdx2])].push_back(i1);
+            }
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int idx1 : rotHist[i])
+                if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)
+        if (vnMatches12[i1] >= 0) { prev_xy[2 * i1] = F2.x[vnMatches12[i1]]; prev_xy[2 * i1 + 1] = F2.y[vnMatches12[i1]]; }
+    return nmatches;
 }
 
 }  // extern "C"

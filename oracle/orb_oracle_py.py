@@ -352,3 +352,86 @@ def voc_bow(word_id, weight, weighting=0, scoring=0):
 def distinctive(desc):
     desc = _u8(desc).reshape(-1, 32)
     return lib().orc_distinctive(_p(desc), len(desc))
+
+
+# ------------------------------------------------------------------ projection / window searches
+class GridViewC(C.Structure):
+    """orc_grid_view of orb_oracle.cpp (same layout as the product's orbm_grid_view)"""
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p), ("octave", C.c_void_p),
+                ("angle", C.c_void_p), ("uright", C.c_void_p), ("blocked", C.c_void_p), ("grid_cols", C.c_int), ("grid_rows", C.c_int),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("inv_w", C.c_float),
+                ("inv_h", C.c_float), ("cell_offsets", C.c_void_p), ("cell_features", C.c_void_p), ("scale_factors", C.c_void_p),
+                ("n_levels", C.c_int)]
+
+
+class Grid:
+    """A Frame as the window searches see it; the grid is built by the oracle's AssignFeaturesToGrid restatement."""
+
+    def __init__(self, desc, x, y, octave, scale_factors, bounds, angle=None, uright=None, blocked=None, grid_cols=64, grid_rows=48):
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        self.desc = _u8(desc).reshape(-1, 32)
+        self.n = len(self.desc)
+        self.x, self.y, self.angle, self.uright = f32(x), f32(y), f32(angle), f32(uright)
+        self.octave = np.ascontiguousarray(octave, np.int32)
+        self.blocked = None if blocked is None else _u8(blocked)
+        self.sf = f32(scale_factors)
+        self.bounds = tuple(np.float32(v) for v in bounds)
+        self.cols, self.rows = grid_cols, grid_rows
+        self.inv_w = np.float32(grid_cols) / np.float32(self.bounds[2] - self.bounds[0])
+        self.inv_h = np.float32(grid_rows) / np.float32(self.bounds[3] - self.bounds[1])
+        self.off = np.zeros(grid_cols * grid_rows + 1, np.int32)
+        self.feat = np.zeros(max(self.n, 1), np.int32)
+        f = lib().orc_assign_features_to_grid
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        f(self.n, _p(self.x), _p(self.y), grid_cols, grid_rows, self.bounds[0], self.bounds[1], self.inv_w, self.inv_h, _p(self.off), _p(self.feat))
+
+    def c(self):
+        return GridViewC(self.n, _p(self.desc), _p(self.x), _p(self.y), _p(self.octave), _p(self.angle), _p(self.uright), _p(self.blocked),
+                         self.cols, self.rows, self.bounds[0], self.bounds[1], self.bounds[2], self.bounds[3], self.inv_w, self.inv_h,
+                         _p(self.off), _p(self.feat), _p(self.sf), len(self.sf))
+
+
+def search_projection_map(grid, in_view, proj_x, proj_y, proj_xr, level, view_cos, desc, claims, th, nnratio):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    in_view, claims, desc = _u8(in_view), _u8(claims), _u8(desc).reshape(-1, 32)
+    proj_x, proj_y, proj_xr, view_cos = f32(proj_x), f32(proj_y), f32(proj_xr), f32(view_cos)
+    level = np.ascontiguousarray(level, np.int32)
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    f = lib().orc_search_projection_map
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(GridViewC), C.c_int] + [C.c_void_p] * 8 + [C.c_float, C.c_float, C.c_void_p]
+    g = grid.c()
+    n = f(C.byref(g), len(in_view), _p(in_view), _p(proj_x), _p(proj_y), _p(proj_xr), _p(level), _p(view_cos), _p(desc), _p(claims),
+          float(th), float(nnratio), _p(owner))
+    return n, owner[:grid.n]
+
+
+def search_projection_frame(grid, Tcw, Tlw, fx, fy, cx, cy, mbf, mb, has_point, world, octave, angle, desc, claims, th, mono, check_ori):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    has_point, claims, desc = _u8(has_point), _u8(claims), _u8(desc).reshape(-1, 32)
+    world, angle = f32(world).reshape(-1, 3), f32(angle)
+    octave = np.ascontiguousarray(octave, np.int32)
+    Tc, Tl = f32(Tcw).reshape(-1)[:12].copy(), f32(Tlw).reshape(-1)[:12].copy()
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    f = lib().orc_search_projection_frame
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(GridViewC), C.c_void_p, C.c_void_p] + [C.c_float] * 6 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]
+    g = grid.c()
+    n = f(C.byref(g), _p(Tc), _p(Tl), fx, fy, cx, cy, mbf, mb, len(has_point), _p(has_point), _p(world), _p(octave), _p(angle), _p(desc),
+          _p(claims), float(th), int(mono), int(check_ori), _p(owner))
+    return n, owner[:grid.n]
+
+
+def search_initialization(grid2, desc1, octave1, angle1, prev_matched, window_size, nnratio, check_ori):
+    desc1 = _u8(desc1).reshape(-1, 32)
+    octave1 = np.ascontiguousarray(octave1, np.int32)
+    angle1 = np.ascontiguousarray(angle1, np.float32)
+    assert prev_matched.dtype == np.float32 and prev_matched.flags.c_contiguous
+    m = np.zeros(max(len(desc1), 1), np.int32)
+    f = lib().orc_search_initialization
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(GridViewC), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    g = grid2.c()
+    n = f(C.byref(g), len(desc1), _p(desc1), _p(octave1), _p(angle1), _p(prev_matched), int(window_size), float(nnratio), int(check_ori), _p(m))
+    return n, m[:len(desc1)]

@@ -5,5 +5,6 @@ host/.  This Python package only binds the C ABI for tests and bench.py.
 """
 from .capi import OrbError, KP_DTYPE, LIB_PATH, lib, device_count   # noqa: F401
 from .extractor import ORBextractor                                  # noqa: F401
-from .matcher import ORBmatcher, FeatureVector, View, popc_peak, distinctive_descriptors      # noqa: F401
+from . import matcher                                                                    # noqa: F401
+from .matcher import ORBmatcher, FeatureVector, View, GridView, popc_peak, distinctive_descriptors      # noqa: F401
 from .vocabulary import ORBVocabulary                                  # noqa: F401

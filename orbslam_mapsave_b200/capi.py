@@ -29,6 +29,7 @@ SYMBOLS = [
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
     "orbm_popc_peak", "orbm_distinctive_descriptors",
+    "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_for_initialization",
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
     "orbv_transform_device",
 ]
@@ -47,6 +48,15 @@ class FeatVecC(C.Structure):
 class ViewC(C.Structure):
     _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("flag", C.c_void_p), ("angle", C.c_void_p), ("x", C.c_void_p),
                 ("y", C.c_void_p), ("octave", C.c_void_p), ("uright", C.c_void_p), ("fv", FeatVecC)]
+
+
+class GridViewC(C.Structure):
+    """orbm_grid_view of include/orb_b200.h"""
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p), ("octave", C.c_void_p),
+                ("angle", C.c_void_p), ("uright", C.c_void_p), ("blocked", C.c_void_p), ("grid_cols", C.c_int), ("grid_rows", C.c_int),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("inv_w", C.c_float),
+                ("inv_h", C.c_float), ("cell_offsets", C.c_void_p), ("cell_features", C.c_void_p), ("scale_factors", C.c_void_p),
+                ("n_levels", C.c_int)]
 
 
 _lib = None
@@ -115,6 +125,13 @@ def lib():
     L.orbm_popc_peak.argtypes = [i32, vp, vp]
     L.orbm_distinctive_descriptors.restype = i32
     L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, i32]
+    L.orbm_search_by_projection_map.restype = i32
+    L.orbm_search_by_projection_map.argtypes = [C.POINTER(GridViewC), i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, i32]
+    L.orbm_search_by_projection_frame.restype = i32
+    L.orbm_search_by_projection_frame.argtypes = [C.POINTER(GridViewC), vp, vp, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp, vp, vp,
+                                                  vp, f32, i32, i32, vp, vp, i32]
+    L.orbm_search_for_initialization.restype = i32
+    L.orbm_search_for_initialization.argtypes = [C.POINTER(GridViewC), i32, vp, vp, vp, vp, i32, f32, i32, vp, vp, i32]
     L.orbv_create.restype = i32
     L.orbv_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, vp, i32]
     L.orbv_load_text.restype = i32

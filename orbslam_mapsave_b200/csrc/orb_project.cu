@@ -1,0 +1,500 @@
+// orb_project.cu — B200 (sm_100a) implementation of the ORBmatcher searches that look inside a window of a Frame's /
+// KeyFrame's feature grid: SearchByProjection(Frame, MapPoints) src/ORBmatcher.cc:45-129,
+// SearchByProjection(CurrentFrame, LastFrame) :1331-1463, SearchForInitialization :408-523, on top of
+// Frame::GetFeaturesInArea src/Frame.cc:445-498.
+//
+// The reference walks its queries serially because an accepted match changes what later queries may take
+// (F.mvpMapPoints[idx] / vMatchedDistance[idx]).  Here every call is three launches:
+//   1. k_win_*        one thread per query: the function-specific part (projection, radius, level range, stereo gate) -> Win
+//   2. k_win_candidates  one warp per query: GetFeaturesInArea in the reference's order (cells ix-major, iy-minor, push order
+//                     inside a cell; lanes = cells, order-preserving write through a warp scan) + the Hamming distances
+//   3. k_win_resolve  one CTA: replays the serial claims as data-parallel ROUNDS.  In a round every unresolved query picks its
+//                     best (and second) candidate among those still available; a query is FINAL when no earlier unresolved
+//                     query could still take one of those two (minq[c] = lowest unresolved query that holds c with a distance
+//                     it could be accepted with).  The lowest unresolved query is always final, so the loop terminates, and
+//                     claims on one feature are finalised in query order, which is all the serial loop guarantees.
+// Integer / float32 work only; float expressions use explicit _rn operations (no FMA contraction), like the reference built
+// without -ffp-contract.
+#include "orb_match_common.cuh"
+
+#include <climits>
+
+#define WL_SHIFT 22                         // candidate entry = distance << 22 | feature index
+#define WL_IDX_MASK 0x3FFFFFu
+#define WIN_ACTIVE 1
+#define WIN_CLAIMS 2
+#define WIN_GATE 4
+
+enum { MODE_BEST = 0, MODE_TOP2_LEVEL = 1, MODE_INIT = 2 };
+
+struct DevGrid {
+    int n;
+    const u8* desc; const float* x; const float* y; const int* octave; const float* angle; const float* uright; const u8* blocked;
+    int cols, rows;
+    float min_x, min_y, max_x, max_y, inv_w, inv_h;
+    const int* cell_off; const int* cell_feat;
+    const float* sf; int n_levels;
+};
+struct __align__(16) Win { float u, v, r, ur, tol; int minL, maxL, flags; };
+
+// ---- 1. windows --------------------------------------------------------------------------------------------------------------
+// SearchByProjection(Frame, MapPoints): ORBmatcher.cc:50-66 (radius by viewing cosine, window r*scale, levels [l-1, l])
+__global__ void k_win_map(DevGrid G, int nq, const u8* __restrict__ in_view, const float* __restrict__ px, const float* __restrict__ py,
+                          const float* __restrict__ pxr, const int* __restrict__ level, const float* __restrict__ vcos,
+                          const u8* __restrict__ claims, float th, Win* __restrict__ win) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    Win w = {0.f, 0.f, 0.f, 0.f, 0.f, -1, -1, 0};
+    if (in_view[q]) {
+        const int l = level[q];
+        float r = ((double)vcos[q] > 0.998) ? 2.5f : 4.0f;
+        if ((double)th != 1.0) r = __fmul_rn(r, th);
+        w.u = px[q]; w.v = py[q];
+        w.r = __fmul_rn(r, G.sf[l]);
+        w.ur = pxr[q]; w.tol = w.r;
+        w.minL = l - 1; w.maxL = l;
+        w.flags = WIN_ACTIVE | (claims[q] ? WIN_CLAIMS : 0) | (G.uright ? WIN_GATE : 0);
+    }
+    win[q] = w;
+}
+
+// SearchByProjection(CurrentFrame, LastFrame): ORBmatcher.cc:1357-1396
+struct FrameProj { float T[12]; float fx, fy, cx, cy, mbf, th; int forward, backward; };
+__global__ void k_win_frame(DevGrid G, FrameProj P, int nq, const u8* __restrict__ has_point, const float* __restrict__ world,
+                            const int* __restrict__ octave, const u8* __restrict__ claims, Win* __restrict__ win) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    Win w = {0.f, 0.f, 0.f, 0.f, 0.f, -1, -1, 0};
+    if (has_point[q]) {
+        const float X = world[3 * q], Y = world[3 * q + 1], Z = world[3 * q + 2];
+        float c[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            c[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P.T[4 * r], X), __fmul_rn(P.T[4 * r + 1], Y)), __fmul_rn(P.T[4 * r + 2], Z)), P.T[4 * r + 3]);
+        const float invzc = (float)__ddiv_rn(1.0, (double)c[2]);
+        bool ok = !(invzc < 0);
+        const float u = __fadd_rn(__fmul_rn(__fmul_rn(P.fx, c[0]), invzc), P.cx);
+        const float v = __fadd_rn(__fmul_rn(__fmul_rn(P.fy, c[1]), invzc), P.cy);
+        if (u < G.min_x || u > G.max_x) ok = false;
+        if (v < G.min_y || v > G.max_y) ok = false;
+        if (ok) {
+            const int o = octave[q];
+            w.u = u; w.v = v;
+            w.r = __fmul_rn(P.th, G.sf[o]);
+            w.ur = __fsub_rn(u, __fmul_rn(P.mbf, invzc)); w.tol = w.r;
+            if (P.forward) { w.minL = o; w.maxL = -1; }
+            else if (P.backward) { w.minL = 0; w.maxL = o; }
+            else { w.minL = o - 1; w.maxL = o + 1; }
+            w.flags = WIN_ACTIVE | (claims[q] ? WIN_CLAIMS : 0) | (G.uright ? WIN_GATE : 0);
+        }
+    }
+    win[q] = w;
+}
+
+// SearchForInitialization: ORBmatcher.cc:422-430 (level-0 features only, window = windowSize around vbPrevMatched)
+__global__ void k_win_init(int nq, const int* __restrict__ octave1, const float* __restrict__ prev_xy, float window, Win* __restrict__ win) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    Win w = {0.f, 0.f, 0.f, 0.f, 0.f, -1, -1, 0};
+    const int l = octave1[q];
+    if (!(l > 0)) {
+        w.u = prev_xy[2 * q]; w.v = prev_xy[2 * q + 1]; w.r = window;
+        w.minL = l; w.maxL = l;
+        w.flags = WIN_ACTIVE | WIN_CLAIMS;
+    }
+    win[q] = w;
+}
+
+// ---- 2. candidates: Frame::GetFeaturesInArea (src/Frame.cc:445-498) + the static `continue`s of the candidate loops ------------
+__device__ __forceinline__ bool cand_pass(const DevGrid& G, const Win& w, bool checkLevels, int idx) {
+    if (G.blocked && G.blocked[idx]) return false;
+    if (checkLevels) {
+        const int o = G.octave[idx];
+        if (o < w.minL) return false;
+        if (w.maxL >= 0 && o > w.maxL) return false;
+    }
+    const float dx = __fsub_rn(G.x[idx], w.u), dy = __fsub_rn(G.y[idx], w.v);
+    if (!(fabsf(dx) < w.r && fabsf(dy) < w.r)) return false;
+    if (w.flags & WIN_GATE) {
+        const float ur = G.uright[idx];
+        if (ur > 0 && fabsf(__fsub_rn(w.ur, ur)) > w.tol) return false;
+    }
+    return true;
+}
+
+#define WC_WARPS 4
+__global__ void __launch_bounds__(32 * WC_WARPS) k_win_candidates(DevGrid G, const Win* __restrict__ win, const u8* __restrict__ qdesc,
+                                                                  int nq, int stride, int drop_above, u32* __restrict__ list,
+                                                                  int* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * WC_WARPS + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const Win w = win[q];
+    int total = 0;
+    if (w.flags & WIN_ACTIVE) {
+        const int minCX = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.u, G.min_x), w.r), G.inv_w)));
+        const int maxCX = min(G.cols - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.u, G.min_x), w.r), G.inv_w)));
+        const int minCY = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(w.v, G.min_y), w.r), G.inv_h)));
+        const int maxCY = min(G.rows - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(w.v, G.min_y), w.r), G.inv_h)));
+        if (minCX < G.cols && maxCX >= 0 && minCY < G.rows && maxCY >= 0 && maxCX >= minCX && maxCY >= minCY) {
+            const bool checkLevels = (w.minL > 0) || (w.maxL >= 0);
+            u32 qd[8];
+            load_desc(qdesc + (size_t)q * 32, qd);
+            const int ncy = maxCY - minCY + 1, T = (maxCX - minCX + 1) * ncy;
+            u32* out = list + (size_t)q * stride;
+            for (int t0 = 0; t0 < T; t0 += 32) {
+                const int t = t0 + lane;
+                int b = 0, e = 0;
+                if (t < T) {
+                    const int c = (minCX + t / ncy) * G.rows + (minCY + t % ncy);
+                    b = G.cell_off[c]; e = G.cell_off[c + 1];
+                }
+                // distances of this lane's cell; entries above drop_above can never be accepted (best-only modes)
+                int n = 0;
+                for (int j = b; j < e; j++) {
+                    const int idx = G.cell_feat[j];
+                    if (!cand_pass(G, w, checkLevels, idx)) continue;
+                    u32 d2[8];
+                    load_desc(G.desc + (size_t)idx * 32, d2);
+                    if (ham256(qd, d2) <= drop_above) n++;
+                }
+                int inc = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+                int p = total + inc - n;
+                for (int j = b; j < e && n > 0; j++) {
+                    const int idx = G.cell_feat[j];
+                    if (!cand_pass(G, w, checkLevels, idx)) continue;
+                    u32 d2[8];
+                    load_desc(G.desc + (size_t)idx * 32, d2);
+                    const int d = ham256(qd, d2);
+                    if (d <= drop_above) out[p++] = ((u32)d << WL_SHIFT) | (u32)idx;
+                }
+                total += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+    }
+    if (lane == 0) cnt[q] = total;
+}
+
+// ---- 3. resolution ------------------------------------------------------------------------------------------------------------
+// State per searched feature c, `thr[c]`:
+//   MODE_BEST / MODE_TOP2_LEVEL: the query that claimed c (INT_MAX = nobody); c is available to query q iff thr[c] > q, i.e. the
+//     test is relative to q's place in the serial order, so a claim finalised early by a LATER query never hides c from an
+//     earlier one (queries whose point has no observations take a feature without claiming it, ORBmatcher.cc:87-89).
+//   MODE_INIT: vMatchedDistance[c] (:448, 471); c is available at distance d iff d < thr[c].  Here the state is absolute, so a
+//     claim on c additionally waits for every earlier unresolved query that still holds c at any distance (minqa), which keeps
+//     "the state a query sees" equal to the state at its serial turn.
+// minq[c]  = lowest unresolved claiming query that holds c, available, with a distance it could be accepted with (d <= th_dist).
+struct ResolveParams { int nq, nt, stride, mode, th_dist, checkOri; float nnratio; };
+#define WR_THREADS 1024
+
+__global__ void __launch_bounds__(WR_THREADS) k_win_resolve(ResolveParams P, const u32* __restrict__ list, const int* __restrict__ cnt,
+                                                            const Win* __restrict__ win, const int* __restrict__ t_octave,
+                                                            const float* __restrict__ q_angle, const float* __restrict__ t_angle,
+                                                            int* __restrict__ thr, int* __restrict__ minq, int* __restrict__ minqa,
+                                                            int* __restrict__ state, int* __restrict__ dec, int* __restrict__ qbin,
+                                                            int* __restrict__ owner, int* __restrict__ match, int* __restrict__ out_cnt) {
+    __shared__ int s_unres, s_hist[ORBM_HISTO_LENGTH], s_nm, s_ind[3], s_rounds;
+    const int tid = threadIdx.x;
+    const bool init = P.mode == MODE_INIT, needSecond = P.mode != MODE_BEST;
+    for (int c = tid; c < P.nt; c += WR_THREADS) { thr[c] = init ? 257 : INT_MAX; owner[c] = -1; }
+    for (int q = tid; q < P.nq; q += WR_THREADS) { match[q] = -1; dec[q] = -1; state[q] = cnt[q] == 0 ? 2 : 0; }
+    if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
+    if (tid == 0) { s_nm = 0; s_rounds = 0; }
+    __syncthreads();
+    for (;;) {
+        if (tid == 0) s_unres = 0;
+        for (int c = tid; c < P.nt; c += WR_THREADS) { minq[c] = INT_MAX; if (init) minqa[c] = INT_MAX; }
+        __syncthreads();
+        for (int q = tid; q < P.nq; q += WR_THREADS) {
+            if (state[q] != 0 || !(win[q].flags & WIN_CLAIMS)) continue;
+            const u32* l = list + (size_t)q * P.stride;
+            const int n = cnt[q];
+            for (int k = 0; k < n; k++) {
+                const u32 e = l[k];
+                const int d = (int)(e >> WL_SHIFT), idx = (int)(e & WL_IDX_MASK);
+                if (!(init ? d < thr[idx] : thr[idx] > q)) continue;
+                if (init) atomicMin(&minqa[idx], q);
+                if (d <= P.th_dist) atomicMin(&minq[idx], q);
+            }
+        }
+        __syncthreads();
+        for (int q = tid; q < P.nq; q += WR_THREADS) {
+            if (state[q] != 0) continue;
+            const u32* l = list + (size_t)q * P.stride;
+            const int n = cnt[q];
+            u32 best = KEY_NONE, sec = KEY_NONE;                        // (distance << 22 | position): first in list order wins ties
+            for (int k = 0; k < n; k++) {
+                const u32 e = l[k];
+                const int d = (int)(e >> WL_SHIFT), idx = (int)(e & WL_IDX_MASK);
+                if (!(init ? d < thr[idx] : thr[idx] > q)) continue;
+                const u32 key = ((u32)d << WL_SHIFT) | (u32)k;
+                sec = min(sec, max(best, key));
+                best = min(best, key);
+            }
+            const int bidx = best == KEY_NONE ? -1 : (int)(l[best & WL_IDX_MASK] & WL_IDX_MASK);
+            const int sidx = sec == KEY_NONE ? -1 : (int)(l[sec & WL_IDX_MASK] & WL_IDX_MASK);
+            const int bd = best == KEY_NONE ? 256 : (int)(best >> WL_SHIFT);
+            bool accept = bidx >= 0 && bd <= P.th_dist;
+            if (accept && P.mode == MODE_TOP2_LEVEL) {                  // ORBmatcher.cc:117-121
+                const int sd = sec == KEY_NONE ? 256 : (int)(sec >> WL_SHIFT);
+                const int bl = t_octave[bidx], sl = sidx >= 0 ? t_octave[sidx] : -1;
+                if (bl == sl && (float)bd > __fmul_rn(P.nnratio, (float)sd)) accept = false;
+            } else if (accept && init) {                                // ORBmatcher.cc:461-463
+                const float sd = sec == KEY_NONE ? (float)INT_MAX : (float)(int)(sec >> WL_SHIFT);
+                if (!((float)bd < __fmul_rn(sd, P.nnratio))) accept = false;
+            }
+            bool fin = (bidx < 0 || minq[bidx] >= q) && (!needSecond || sidx < 0 || minq[sidx] >= q);
+            if (fin && init && accept && minqa[bidx] < q) fin = false;
+            if (!fin) { s_unres = 1; continue; }
+            dec[q] = accept ? ((bd << WL_SHIFT) | bidx) : -1;
+            state[q] = 1;
+        }
+        __syncthreads();
+        for (int q = tid; q < P.nq; q += WR_THREADS) {
+            if (state[q] != 1) continue;
+            state[q] = 2;
+            if (dec[q] < 0) continue;
+            const int bidx = dec[q] & WL_IDX_MASK, bd = dec[q] >> WL_SHIFT;
+            if (init) {                                                 // ORBmatcher.cc:465-473 (at most one claim per feature per round)
+                const int prev = owner[bidx];
+                if (prev >= 0) { match[prev] = -1; atomicSub(&s_nm, 1); }
+                owner[bidx] = q;
+                thr[bidx] = bd;
+            } else {
+                atomicMax(&owner[bidx], q);
+                if (win[q].flags & WIN_CLAIMS) atomicMin(&thr[bidx], q);
+            }
+            match[q] = bidx;
+            atomicAdd(&s_nm, 1);
+            if (P.checkOri) {
+                const int bin = rot_bin(q_angle[q], t_angle[bidx]);
+                qbin[q] = bin;
+                atomicAdd(&s_hist[bin], 1);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_rounds++;
+        if (!s_unres) break;
+        __syncthreads();
+    }
+    if (P.checkOri) {                                                   // rotation consistency (:1446-1458, :493-512)
+        if (tid == 0) { int a, b, c; three_maxima_dev(s_hist, ORBM_HISTO_LENGTH, a, b, c); s_ind[0] = a; s_ind[1] = b; s_ind[2] = c; }
+        __syncthreads();
+        for (int q = tid; q < P.nq; q += WR_THREADS) {
+            if (init ? match[q] < 0 : dec[q] < 0) continue;
+            const int bin = qbin[q];
+            if (bin == s_ind[0] || bin == s_ind[1] || bin == s_ind[2]) continue;
+            if (init) match[q] = -1;
+            else owner[dec[q] & WL_IDX_MASK] = -2;
+            atomicSub(&s_nm, 1);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { out_cnt[0] = s_nm; out_cnt[1] = s_rounds; }
+}
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+static int check_grid(const orbm_grid_view* g, bool needAngle) {
+    ORB_REQUIRE(g && g->n >= 0, ORB_ERR_ARG, "bad grid view");
+    ORB_REQUIRE(g->n <= (int)WL_IDX_MASK, ORB_ERR_ARG, "more than 4194303 features");
+    ORB_REQUIRE(g->n == 0 || (g->desc && g->x && g->y && g->octave), ORB_ERR_ARG, "grid view: desc/x/y/octave are required");
+    ORB_REQUIRE(!needAngle || g->n == 0 || g->angle, ORB_ERR_ARG, "grid view: angle is required for the orientation check");
+    ORB_REQUIRE(g->grid_cols > 0 && g->grid_rows > 0 && g->cell_offsets && (g->cell_features || g->n == 0), ORB_ERR_ARG, "grid view: bad grid");
+    const int nc = g->grid_cols * g->grid_rows;
+    ORB_REQUIRE(g->cell_offsets[0] == 0, ORB_ERR_ARG, "grid view: cell_offsets[0] != 0");
+    for (int c = 0; c < nc; c++) ORB_REQUIRE(g->cell_offsets[c] <= g->cell_offsets[c + 1], ORB_ERR_ARG, "grid view: offsets not monotone");
+    for (int i = 0; i < g->cell_offsets[nc]; i++)
+        ORB_REQUIRE(g->cell_features[i] >= 0 && g->cell_features[i] < g->n, ORB_ERR_ARG, "grid view: feature index out of range");
+    ORB_REQUIRE(g->n_levels > 0 && g->scale_factors, ORB_ERR_ARG, "grid view: scale_factors are required");
+    for (int i = 0; i < g->n; i++) ORB_REQUIRE(g->octave[i] >= 0 && g->octave[i] < g->n_levels, ORB_ERR_ARG, "grid view: octave out of range");
+    return ORB_OK;
+}
+static size_t grid_bytes(const orbm_grid_view* g) {
+    const size_t n = (size_t)g->n, nc = (size_t)g->grid_cols * g->grid_rows;
+    return pad(n * 32) + 5 * pad(n * 4) + pad(n) + pad((nc + 1) * 4) + pad((size_t)g->cell_offsets[nc] * 4) + pad((size_t)g->n_levels * 4);
+}
+static int upload_grid(Arena& A, const orbm_grid_view* g, DevGrid* d) {
+    int rc;
+    const size_t n = (size_t)g->n, nc = (size_t)g->grid_cols * g->grid_rows;
+    d->n = g->n; d->cols = g->grid_cols; d->rows = g->grid_rows;
+    d->min_x = g->min_x; d->min_y = g->min_y; d->max_x = g->max_x; d->max_y = g->max_y; d->inv_w = g->inv_w; d->inv_h = g->inv_h;
+    d->n_levels = g->n_levels;
+    d->angle = nullptr; d->uright = nullptr; d->blocked = nullptr;
+    if ((rc = upload(A, g->desc, n * 32, &d->desc))) return rc;
+    if ((rc = upload(A, g->x, n, &d->x))) return rc;
+    if ((rc = upload(A, g->y, n, &d->y))) return rc;
+    if ((rc = upload(A, g->octave, n, &d->octave))) return rc;
+    if (g->angle) { if ((rc = upload(A, g->angle, n, &d->angle))) return rc; }
+    if (g->uright) { if ((rc = upload(A, g->uright, n, &d->uright))) return rc; }
+    if (g->blocked) { if ((rc = upload(A, g->blocked, n, &d->blocked))) return rc; }
+    if ((rc = upload(A, g->cell_offsets, nc + 1, &d->cell_off))) return rc;
+    if ((rc = upload(A, g->cell_features, (size_t)g->cell_offsets[nc], &d->cell_feat))) return rc;
+    if ((rc = upload(A, g->scale_factors, (size_t)g->n_levels, &d->sf))) return rc;
+    return ORB_OK;
+}
+
+// outputs + scratch of one search, taken from the arena after the inputs have been flushed
+struct WinWork {
+    Win* win; int* owner; int* match; int* out_cnt;                    // (owner, match, out_cnt) stay inside the mirrored part
+    u32* list; int* cnt; int* thr; int* minq; int* minqa; int* state; int* dec; int* qbin;
+};
+static size_t work_small_bytes(int nq, int nt) { return pad((size_t)nt * 4) + pad((size_t)nq * 4) + pad(8); }
+static size_t work_scratch_bytes(int nq, int nt) {
+    return pad((size_t)nq * sizeof(Win)) + pad((size_t)nq * (size_t)std::max(nt, 1) * 4) + 4 * pad((size_t)nq * 4) + 3 * pad((size_t)nt * 4);
+}
+static void take_work(Arena& A, int nq, int nt, WinWork* w) {
+    w->owner = A.take<int>(std::max(nt, 1));
+    w->match = A.take<int>(std::max(nq, 1));
+    w->out_cnt = A.take<int>(2);
+    w->win = A.take<Win>(std::max(nq, 1));
+    w->list = A.take<u32>((size_t)std::max(nq, 1) * std::max(nt, 1));
+    w->cnt = A.take<int>(std::max(nq, 1));
+    w->state = A.take<int>(std::max(nq, 1));
+    w->dec = A.take<int>(std::max(nq, 1));
+    w->qbin = A.take<int>(std::max(nq, 1));
+    w->thr = A.take<int>(std::max(nt, 1));
+    w->minq = A.take<int>(std::max(nt, 1));
+    w->minqa = A.take<int>(std::max(nt, 1));
+}
+static int run_search(Arena& A, const DevGrid& G, const WinWork& w, const u8* d_qdesc, const float* d_qangle, int nq, int mode,
+                      int th_dist, float nnratio, int checkOri) {
+    const int stride = std::max(G.n, 1);
+    const int drop_above = mode == MODE_BEST ? th_dist : 256;
+    if (nq > 0) k_win_candidates<<<orb_div_up(nq, WC_WARPS), 32 * WC_WARPS, 0, A.stream>>>(G, w.win, d_qdesc, nq, stride, drop_above, w.list, w.cnt);
+    ResolveParams P;
+    P.nq = nq; P.nt = G.n; P.stride = stride; P.mode = mode; P.th_dist = th_dist; P.checkOri = checkOri; P.nnratio = nnratio;
+    k_win_resolve<<<1, WR_THREADS, 0, A.stream>>>(P, w.list, w.cnt, w.win, G.octave, d_qangle, G.angle, w.thr, w.minq, w.minqa, w.state, w.dec,
+                                                  w.qbin, w.owner, w.match, w.out_cnt);
+    ORB_CUDA_TRY(cudaGetLastError());
+    return ORB_OK;
+}
+
+extern "C" int orbm_search_by_projection_map(const orbm_grid_view* frame, int n_points, const uint8_t* in_view, const float* proj_x,
+                                             const float* proj_y, const float* proj_xr, const int* level, const float* view_cos,
+                                             const uint8_t* desc, const uint8_t* claims, float th, float nnratio, int* owner,
+                                             int* n_matches, int device) {
+    ORB_REQUIRE(owner && n_matches && n_points >= 0, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(n_points == 0 || (in_view && proj_x && proj_y && proj_xr && level && view_cos && desc && claims), ORB_ERR_ARG, "null map point array");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_grid(frame, false))) return rc;
+    for (int i = 0; i < n_points; i++)
+        ORB_REQUIRE(!in_view[i] || (level[i] >= 0 && level[i] < frame->n_levels), ORB_ERR_ARG, "predicted level out of range");
+    const int nq = n_points, nt = frame->n;
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, grid_bytes(frame) + 2 * pad(nq) + 4 * pad((size_t)nq * 4) + pad((size_t)nq * 4) + pad((size_t)nq * 32) +
+                                   work_small_bytes(nq, nt), work_scratch_bytes(nq, nt)))) return rc;
+    DevGrid G;
+    if ((rc = upload_grid(A, frame, &G))) return rc;
+    const u8 *d_inview, *d_claims, *d_desc;
+    const float *d_px, *d_py, *d_pxr, *d_vc;
+    const int* d_level;
+    if ((rc = upload(A, in_view, (size_t)nq, &d_inview))) return rc;
+    if ((rc = upload(A, claims, (size_t)nq, &d_claims))) return rc;
+    if ((rc = upload(A, proj_x, (size_t)nq, &d_px))) return rc;
+    if ((rc = upload(A, proj_y, (size_t)nq, &d_py))) return rc;
+    if ((rc = upload(A, proj_xr, (size_t)nq, &d_pxr))) return rc;
+    if ((rc = upload(A, view_cos, (size_t)nq, &d_vc))) return rc;
+    if ((rc = upload(A, level, (size_t)nq, &d_level))) return rc;
+    if ((rc = upload(A, desc, (size_t)nq * 32, &d_desc))) return rc;
+    if ((rc = A.flush())) return rc;
+    WinWork w;
+    take_work(A, nq, nt, &w);
+    if (nq > 0) k_win_map<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(G, nq, d_inview, d_px, d_py, d_pxr, d_level, d_vc, d_claims, th, w.win);
+    if ((rc = run_search(A, G, w, d_desc, nullptr, nq, MODE_TOP2_LEVEL, ORBM_TH_HIGH, nnratio, 0))) return rc;
+    int cnt[2] = {0, 0};
+    if ((rc = A.fetch(owner, w.owner, (size_t)nt))) return rc;
+    if ((rc = A.fetch(cnt, w.out_cnt, 2))) return rc;
+    if ((rc = A.finish())) return rc;
+    *n_matches = cnt[0];
+    return ORB_OK;
+}
+
+extern "C" int orbm_search_by_projection_frame(const orbm_grid_view* cur, const float* Tcw_cur, const float* Tcw_last, float fx, float fy,
+                                               float cx, float cy, float mbf, float mb, int n_last, const uint8_t* has_point,
+                                               const float* world, const int* octave, const float* angle, const uint8_t* desc,
+                                               const uint8_t* claims, float th, int mono, int check_orientation, int* owner,
+                                               int* n_matches, int device) {
+    ORB_REQUIRE(owner && n_matches && n_last >= 0 && Tcw_cur && Tcw_last, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(n_last == 0 || (has_point && world && octave && desc && claims && (angle || !check_orientation)), ORB_ERR_ARG, "null LastFrame array");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_grid(cur, check_orientation != 0))) return rc;
+    for (int i = 0; i < n_last; i++)
+        ORB_REQUIRE(!has_point[i] || (octave[i] >= 0 && octave[i] < cur->n_levels), ORB_ERR_ARG, "LastFrame octave out of range");
+    // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw (src/ORBmatcher.cc:1344-1355); float32, left to right (cv::gemm on 3x3 floats)
+    FrameProj P;
+    for (int i = 0; i < 12; i++) P.T[i] = Tcw_cur[i];
+    float twc[3];
+    for (int r = 0; r < 3; r++) twc[r] = -((Tcw_cur[r] * Tcw_cur[3] + Tcw_cur[4 + r] * Tcw_cur[7]) + Tcw_cur[8 + r] * Tcw_cur[11]);
+    const float tlcz = ((Tcw_last[8] * twc[0] + Tcw_last[9] * twc[1]) + Tcw_last[10] * twc[2]) + Tcw_last[11];
+    P.forward = (tlcz > mb && !mono) ? 1 : 0;
+    P.backward = (-tlcz > mb && !mono) ? 1 : 0;
+    P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy; P.mbf = mbf; P.th = th;
+    const int nq = n_last, nt = cur->n;
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, grid_bytes(cur) + 2 * pad(nq) + pad((size_t)nq * 12) + 2 * pad((size_t)nq * 4) + pad((size_t)nq * 32) +
+                                   work_small_bytes(nq, nt), work_scratch_bytes(nq, nt)))) return rc;
+    DevGrid G;
+    if ((rc = upload_grid(A, cur, &G))) return rc;
+    const u8 *d_has, *d_claims, *d_desc;
+    const float *d_world, *d_angle = nullptr;
+    const int* d_oct;
+    if ((rc = upload(A, has_point, (size_t)nq, &d_has))) return rc;
+    if ((rc = upload(A, claims, (size_t)nq, &d_claims))) return rc;
+    if ((rc = upload(A, world, (size_t)nq * 3, &d_world))) return rc;
+    if ((rc = upload(A, octave, (size_t)nq, &d_oct))) return rc;
+    if (check_orientation) { if ((rc = upload(A, angle, (size_t)nq, &d_angle))) return rc; }
+    if ((rc = upload(A, desc, (size_t)nq * 32, &d_desc))) return rc;
+    if ((rc = A.flush())) return rc;
+    WinWork w;
+    take_work(A, nq, nt, &w);
+    if (nq > 0) k_win_frame<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(G, P, nq, d_has, d_world, d_oct, d_claims, w.win);
+    if ((rc = run_search(A, G, w, d_desc, d_angle, nq, MODE_BEST, ORBM_TH_HIGH, 0.f, check_orientation))) return rc;
+    int cnt[2] = {0, 0};
+    if ((rc = A.fetch(owner, w.owner, (size_t)nt))) return rc;
+    if ((rc = A.fetch(cnt, w.out_cnt, 2))) return rc;
+    if ((rc = A.finish())) return rc;
+    *n_matches = cnt[0];
+    return ORB_OK;
+}
+
+extern "C" int orbm_search_for_initialization(const orbm_grid_view* f2, int n1, const uint8_t* desc1, const int* octave1,
+                                              const float* angle1, float* prev_xy, int window_size, float nnratio,
+                                              int check_orientation, int* matches12, int* n_matches, int device) {
+    ORB_REQUIRE(matches12 && n_matches && n1 >= 0, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(n1 == 0 || (desc1 && octave1 && prev_xy && (angle1 || !check_orientation)), ORB_ERR_ARG, "null F1 array");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_grid(f2, check_orientation != 0))) return rc;
+    const int nq = n1, nt = f2->n;
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, grid_bytes(f2) + pad((size_t)nq * 8) + 2 * pad((size_t)nq * 4) + pad((size_t)nq * 32) + work_small_bytes(nq, nt),
+                       work_scratch_bytes(nq, nt)))) return rc;
+    DevGrid G;
+    if ((rc = upload_grid(A, f2, &G))) return rc;
+    G.uright = nullptr; G.blocked = nullptr;                            // no stereo gate / no pre-claimed features in this search
+    const u8* d_desc;
+    const float *d_prev, *d_angle = nullptr;
+    const int* d_oct;
+    if ((rc = upload(A, octave1, (size_t)nq, &d_oct))) return rc;
+    if ((rc = upload(A, (const float*)prev_xy, (size_t)nq * 2, &d_prev))) return rc;
+    if (check_orientation) { if ((rc = upload(A, angle1, (size_t)nq, &d_angle))) return rc; }
+    if ((rc = upload(A, desc1, (size_t)nq * 32, &d_desc))) return rc;
+    if ((rc = A.flush())) return rc;
+    WinWork w;
+    take_work(A, nq, nt, &w);
+    if (nq > 0) k_win_init<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(nq, d_oct, d_prev, (float)window_size, w.win);
+    if ((rc = run_search(A, G, w, d_desc, d_angle, nq, MODE_INIT, ORBM_TH_LOW, nnratio, check_orientation))) return rc;
+    int cnt[2] = {0, 0};
+    if ((rc = A.fetch(matches12, w.match, (size_t)nq))) return rc;
+    if ((rc = A.fetch(cnt, w.out_cnt, 2))) return rc;
+    if ((rc = A.finish())) return rc;
+    for (int i = 0; i < nq; i++)                                        // vbPrevMatched update, src/ORBmatcher.cc:516-519
+        if (matches12[i] >= 0) { prev_xy[2 * i] = f2->x[matches12[i]]; prev_xy[2 * i + 1] = f2->y[matches12[i]]; }
+    *n_matches = cnt[0];
+    return ORB_OK;
+}

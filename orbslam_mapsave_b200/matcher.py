@@ -43,6 +43,45 @@ class View:
                           capi._p(self.octave), capi._p(self.uright), self.fv.c())
 
 
+class GridView:
+    """The Frame / KeyFrame fields the window searches read (include/Frame.h:98,141-197): undistorted keypoints, descriptors,
+    mvuRight, the image bounds and the feature grid mGrid flattened to CSR (cell = ix * rows + iy, push order inside a cell)."""
+
+    def __init__(self, desc, x, y, octave, scale_factors, bounds, angle=None, uright=None, blocked=None, grid_cols=64, grid_rows=48):
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.n = len(self.desc)
+        self.x, self.y, self.angle, self.uright = f32(x), f32(y), f32(angle), f32(uright)
+        self.octave = np.ascontiguousarray(octave, np.int32)
+        self.blocked = None if blocked is None else np.ascontiguousarray(blocked, np.uint8)
+        self.scale_factors = f32(scale_factors)
+        self.min_x, self.min_y, self.max_x, self.max_y = (np.float32(v) for v in bounds)
+        self.grid_cols, self.grid_rows = int(grid_cols), int(grid_rows)
+        # mfGridElementWidthInv / HeightInv (src/Frame.cc:101-102): float(cols) / float(maxX - minX)
+        self.inv_w = np.float32(self.grid_cols) / np.float32(self.max_x - self.min_x)
+        self.inv_h = np.float32(self.grid_rows) / np.float32(self.max_y - self.min_y)
+        self._assign_features_to_grid()
+
+    def _assign_features_to_grid(self):
+        """Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:341-356, 500-510): cell = round((pt - min) * inv)."""
+        cround = lambda v: np.where(v >= 0, np.floor(v.astype(np.float64) + 0.5), -np.floor(-v.astype(np.float64) + 0.5)).astype(np.int64)
+        px = cround((self.x - self.min_x) * self.inv_w)
+        py = cround((self.y - self.min_y) * self.inv_h)
+        ok = (px >= 0) & (px < self.grid_cols) & (py >= 0) & (py < self.grid_rows)
+        cell = px[ok] * self.grid_rows + py[ok]
+        idx = np.nonzero(ok)[0]
+        order = np.argsort(cell, kind="stable")
+        counts = np.bincount(cell, minlength=self.grid_cols * self.grid_rows)
+        self.cell_offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self.cell_features = np.ascontiguousarray(idx[order], np.int32)
+
+    def c(self):
+        p = capi._p
+        return capi.GridViewC(self.n, p(self.desc), p(self.x), p(self.y), p(self.octave), p(self.angle), p(self.uright), p(self.blocked),
+                              self.grid_cols, self.grid_rows, self.min_x, self.min_y, self.max_x, self.max_y, self.inv_w, self.inv_h,
+                              p(self.cell_offsets), p(self.cell_features), p(self.scale_factors), len(self.scale_factors))
+
+
 class ORBmatcher:
     TH_HIGH, TH_LOW, HISTO_LENGTH = capi.TH_HIGH, capi.TH_LOW, capi.HISTO_LENGTH     # src/ORBmatcher.cc:37-39
 
@@ -93,6 +132,57 @@ class ORBmatcher:
                                                             capi._p(s2), len(sf2), int(bOnlyStereo), int(self.mbCheckOrientation),
                                                             capi._p(pairs), C.byref(npairs), C.byref(nm), self.device))
         return nm.value, pairs[:npairs.value].copy()
+
+    def SearchByProjectionMapPoints(self, frame, in_view, proj_x, proj_y, proj_xr, level, view_cos, desc, claims, th=1.0):
+        """SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:45-129).  Arrays per map point as left by
+        Frame::isInFrustum.  Returns (nmatches, owner[F.N]): the map point stored in F.mvpMapPoints[idx], -1 = untouched."""
+        u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        in_view, claims, desc = u8(in_view), u8(claims), u8(desc).reshape(-1, 32)
+        proj_x, proj_y, proj_xr, view_cos = f32(proj_x), f32(proj_y), f32(proj_xr), f32(view_cos)
+        level = np.ascontiguousarray(level, np.int32)
+        g = frame.c()
+        owner = np.zeros(max(frame.n, 1), np.int32)
+        n = C.c_int()
+        capi.check(capi.lib().orbm_search_by_projection_map(C.byref(g), len(in_view), capi._p(in_view), capi._p(proj_x), capi._p(proj_y),
+                                                            capi._p(proj_xr), capi._p(level), capi._p(view_cos), capi._p(desc),
+                                                            capi._p(claims), float(th), self.mfNNratio, capi._p(owner), C.byref(n),
+                                                            self.device))
+        return n.value, owner[:frame.n]
+
+    def SearchByProjectionFrame(self, cur, Tcw_cur, Tcw_last, fx, fy, cx, cy, mbf, mb, has_point, world, octave, angle, desc, claims,
+                                th, bMono):
+        """SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (src/ORBmatcher.cc:1331-1463).
+        Returns (nmatches, owner[cur.N]): LastFrame feature index, -1 = untouched, -2 = set to NULL by the rotation cull."""
+        u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        has_point, claims, desc = u8(has_point), u8(claims), u8(desc).reshape(-1, 32)
+        world, angle = f32(world).reshape(-1, 3), f32(angle)
+        octave = np.ascontiguousarray(octave, np.int32)
+        Tc, Tl = f32(Tcw_cur).reshape(-1)[:12].copy(), f32(Tcw_last).reshape(-1)[:12].copy()
+        g = cur.c()
+        owner = np.zeros(max(cur.n, 1), np.int32)
+        n = C.c_int()
+        capi.check(capi.lib().orbm_search_by_projection_frame(C.byref(g), capi._p(Tc), capi._p(Tl), fx, fy, cx, cy, mbf, mb, len(has_point),
+                                                              capi._p(has_point), capi._p(world), capi._p(octave), capi._p(angle),
+                                                              capi._p(desc), capi._p(claims), float(th), int(bMono),
+                                                              int(self.mbCheckOrientation), capi._p(owner), C.byref(n), self.device))
+        return n.value, owner[:cur.n]
+
+    def SearchForInitialization(self, f2, desc1, octave1, angle1, prev_matched, windowSize=10):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:408-523).
+        prev_matched: (n1, 2) float32, updated in place.  Returns (nmatches, vnMatches12)."""
+        desc1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32)
+        octave1 = np.ascontiguousarray(octave1, np.int32)
+        angle1 = np.ascontiguousarray(angle1, np.float32)
+        assert prev_matched.dtype == np.float32 and prev_matched.flags.c_contiguous and prev_matched.shape == (len(desc1), 2)
+        g = f2.c()
+        m = np.zeros(max(len(desc1), 1), np.int32)
+        n = C.c_int()
+        capi.check(capi.lib().orbm_search_for_initialization(C.byref(g), len(desc1), capi._p(desc1), capi._p(octave1), capi._p(angle1),
+                                                             capi._p(prev_matched), int(windowSize), self.mfNNratio,
+                                                             int(self.mbCheckOrientation), capi._p(m), C.byref(n), self.device))
+        return n.value, m[:len(desc1)]
 
     @staticmethod
     def ComputeThreeMaxima(histo, device=0):
