@@ -13,6 +13,7 @@
 //                     query could still take one of those two (minq[c] = lowest unresolved query that holds c with a distance
 //                     it could be accepted with).  The lowest unresolved query is always final, so the loop terminates, and
 //                     claims on one feature are finalised in query order, which is all the serial loop guarantees.
+//                     Typical calls need 2-6 rounds.
 // Integer / float32 work only; float expressions use explicit _rn operations (no FMA contraction), like the reference built
 // without -ffp-contract.
 #include "orb_match_common.cuh"
@@ -177,63 +178,90 @@ __global__ void __launch_bounds__(32 * WC_WARPS) k_win_candidates(DevGrid G, con
 }
 
 // ---- 3. resolution ------------------------------------------------------------------------------------------------------------
-// State per searched feature c, `thr[c]`:
-//   MODE_BEST / MODE_TOP2_LEVEL: the query that claimed c (INT_MAX = nobody); c is available to query q iff thr[c] > q, i.e. the
-//     test is relative to q's place in the serial order, so a claim finalised early by a LATER query never hides c from an
-//     earlier one (queries whose point has no observations take a feature without claiming it, ORBmatcher.cc:87-89).
-//   MODE_INIT: vMatchedDistance[c] (:448, 471); c is available at distance d iff d < thr[c].  Here the state is absolute, so a
-//     claim on c additionally waits for every earlier unresolved query that still holds c at any distance (minqa), which keeps
-//     "the state a query sees" equal to the state at its serial turn.
-// minq[c]  = lowest unresolved claiming query that holds c, available, with a distance it could be accepted with (d <= th_dist).
+// State per searched feature c:
+//   claimq[c] = the first query that claimed c (INT_MAX = nobody).  MODE_BEST / MODE_TOP2_LEVEL: c is available to query q iff
+//     claimq[c] > q, i.e. the test is relative to q's place in the serial order, so a claim finalised early by a LATER query
+//     never hides c from an earlier one (queries whose point has no observations take a feature without claiming it,
+//     ORBmatcher.cc:87-89).
+//   MODE_INIT: thr[c] = vMatchedDistance[c] (:448, 471); an entry (d, c) is available iff d < thr[c].  Every claim carries a
+//     distance <= TH_LOW, so for an entry with d > TH_LOW that is the same as "nobody before q has claimed c" = claimq[c] > q
+//     (relative again), and for d <= TH_LOW the absolute thr[c] is exact because a later claim on c waits (minq) for every
+//     earlier unresolved query that holds c with such a distance.
+// minq[c] = lowest unresolved claiming query that holds c, available, with a distance it could be accepted with (d <= th_dist).
+// g lanes per query (g = 1..32 by mean list length), lanes over the candidate list.
 struct ResolveParams { int nq, nt, stride, mode, th_dist, checkOri; float nnratio; };
 #define WR_THREADS 1024
+#define WR_WARPS (WR_THREADS / 32)
+
+__device__ __forceinline__ bool entry_avail(bool init, int th_dist, int d, int idx, int q, const int* thr, const int* claimq) {
+    return (init && d <= th_dist) ? d < thr[idx] : claimq[idx] > q;
+}
 
 __global__ void __launch_bounds__(WR_THREADS) k_win_resolve(ResolveParams P, const u32* __restrict__ list, const int* __restrict__ cnt,
                                                             const Win* __restrict__ win, const int* __restrict__ t_octave,
                                                             const float* __restrict__ q_angle, const float* __restrict__ t_angle,
-                                                            int* __restrict__ thr, int* __restrict__ minq, int* __restrict__ minqa,
+                                                            int* __restrict__ thr, int* __restrict__ minq, int* __restrict__ claimq,
                                                             int* __restrict__ state, int* __restrict__ dec, int* __restrict__ qbin,
                                                             int* __restrict__ owner, int* __restrict__ match, int* __restrict__ out_cnt) {
-    __shared__ int s_unres, s_hist[ORBM_HISTO_LENGTH], s_nm, s_ind[3], s_rounds;
+    __shared__ int s_unres, s_hist[ORBM_HISTO_LENGTH], s_nm, s_ind[3], s_rounds, s_entries, s_active;
     const int tid = threadIdx.x;
     const bool init = P.mode == MODE_INIT, needSecond = P.mode != MODE_BEST;
-    for (int c = tid; c < P.nt; c += WR_THREADS) { thr[c] = init ? 257 : INT_MAX; owner[c] = -1; }
-    for (int q = tid; q < P.nq; q += WR_THREADS) { match[q] = -1; dec[q] = -1; state[q] = cnt[q] == 0 ? 2 : 0; }
     if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
-    if (tid == 0) { s_nm = 0; s_rounds = 0; }
+    if (tid == 0) { s_nm = 0; s_rounds = 0; s_entries = 0; s_active = 0; }
     __syncthreads();
+    for (int c = tid; c < P.nt; c += WR_THREADS) { thr[c] = 257; claimq[c] = INT_MAX; owner[c] = -1; }
+    {
+        int e = 0, a = 0;
+        for (int q = tid; q < P.nq; q += WR_THREADS) {
+            match[q] = -1; dec[q] = -1; state[q] = cnt[q] == 0 ? 2 : 0;
+            e += cnt[q]; a += cnt[q] != 0;
+        }
+        if (a) { atomicAdd(&s_entries, e); atomicAdd(&s_active, a); }
+    }
+    __syncthreads();
+    // lanes per query: a power of two near (mean list length / 4), so short lists keep many queries in flight
+    int g = 1;
+    while (g < 32 && (long)g * 4 * max(s_active, 1) < (long)s_entries) g <<= 1;
+    const int sub = tid & (g - 1), qpw = 32 / g, q_first = (tid >> 5) * qpw + ((tid & 31) / g), q_step = WR_WARPS * qpw;
     for (;;) {
         if (tid == 0) s_unres = 0;
-        for (int c = tid; c < P.nt; c += WR_THREADS) { minq[c] = INT_MAX; if (init) minqa[c] = INT_MAX; }
+        for (int c = tid; c < P.nt; c += WR_THREADS) minq[c] = INT_MAX;
         __syncthreads();
-        for (int q = tid; q < P.nq; q += WR_THREADS) {
+        for (int q = q_first; q < P.nq; q += q_step) {
             if (state[q] != 0 || !(win[q].flags & WIN_CLAIMS)) continue;
             const u32* l = list + (size_t)q * P.stride;
             const int n = cnt[q];
-            for (int k = 0; k < n; k++) {
+            for (int k = sub; k < n; k += g) {
                 const u32 e = l[k];
                 const int d = (int)(e >> WL_SHIFT), idx = (int)(e & WL_IDX_MASK);
-                if (!(init ? d < thr[idx] : thr[idx] > q)) continue;
-                if (init) atomicMin(&minqa[idx], q);
-                if (d <= P.th_dist) atomicMin(&minq[idx], q);
+                if (d <= P.th_dist && entry_avail(init, P.th_dist, d, idx, q, thr, claimq)) atomicMin(&minq[idx], q);
             }
         }
         __syncthreads();
-        for (int q = tid; q < P.nq; q += WR_THREADS) {
-            if (state[q] != 0) continue;
-            const u32* l = list + (size_t)q * P.stride;
-            const int n = cnt[q];
+        for (int q0 = (tid >> 5) * qpw; q0 < P.nq; q0 += q_step) {      // warp-uniform trip count: shuffles below use the full mask
+            const int q = q0 + ((tid & 31) / g);
+            const bool live = q < P.nq && state[q] == 0;
+            const u32* l = list + (size_t)(live ? q : 0) * P.stride;
+            const int n = live ? cnt[q] : 0;
             u32 best = KEY_NONE, sec = KEY_NONE;                        // (distance << 22 | position): first in list order wins ties
-            for (int k = 0; k < n; k++) {
+            for (int k = sub; k < n; k += g) {
                 const u32 e = l[k];
                 const int d = (int)(e >> WL_SHIFT), idx = (int)(e & WL_IDX_MASK);
-                if (!(init ? d < thr[idx] : thr[idx] > q)) continue;
+                if (!entry_avail(init, P.th_dist, d, idx, q, thr, claimq)) continue;
                 const u32 key = ((u32)d << WL_SHIFT) | (u32)k;
                 sec = min(sec, max(best, key));
                 best = min(best, key);
             }
+            for (int o = g >> 1; o > 0; o >>= 1) {
+                const u32 ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, sec, o);
+                sec = min(min(sec, os), max(best, ob));
+                best = min(best, ob);
+            }
+            if (!live || sub != 0) continue;
             const int bidx = best == KEY_NONE ? -1 : (int)(l[best & WL_IDX_MASK] & WL_IDX_MASK);
             const int sidx = sec == KEY_NONE ? -1 : (int)(l[sec & WL_IDX_MASK] & WL_IDX_MASK);
+            const bool fin = (bidx < 0 || minq[bidx] >= q) && (!needSecond || sidx < 0 || minq[sidx] >= q);
+            if (!fin) { s_unres = 1; continue; }
             const int bd = best == KEY_NONE ? 256 : (int)(best >> WL_SHIFT);
             bool accept = bidx >= 0 && bd <= P.th_dist;
             if (accept && P.mode == MODE_TOP2_LEVEL) {                  // ORBmatcher.cc:117-121
@@ -244,9 +272,6 @@ __global__ void __launch_bounds__(WR_THREADS) k_win_resolve(ResolveParams P, con
                 const float sd = sec == KEY_NONE ? (float)INT_MAX : (float)(int)(sec >> WL_SHIFT);
                 if (!((float)bd < __fmul_rn(sd, P.nnratio))) accept = false;
             }
-            bool fin = (bidx < 0 || minq[bidx] >= q) && (!needSecond || sidx < 0 || minq[sidx] >= q);
-            if (fin && init && accept && minqa[bidx] < q) fin = false;
-            if (!fin) { s_unres = 1; continue; }
             dec[q] = accept ? ((bd << WL_SHIFT) | bidx) : -1;
             state[q] = 1;
         }
@@ -261,9 +286,10 @@ __global__ void __launch_bounds__(WR_THREADS) k_win_resolve(ResolveParams P, con
                 if (prev >= 0) { match[prev] = -1; atomicSub(&s_nm, 1); }
                 owner[bidx] = q;
                 thr[bidx] = bd;
+                atomicMin(&claimq[bidx], q);
             } else {
                 atomicMax(&owner[bidx], q);
-                if (win[q].flags & WIN_CLAIMS) atomicMin(&thr[bidx], q);
+                if (win[q].flags & WIN_CLAIMS) atomicMin(&claimq[bidx], q);
             }
             match[q] = bidx;
             atomicAdd(&s_nm, 1);
@@ -339,7 +365,7 @@ static int upload_grid(Arena& A, const orbm_grid_view* g, DevGrid* d) {
 // outputs + scratch of one search, taken from the arena after the inputs have been flushed
 struct WinWork {
     Win* win; int* owner; int* match; int* out_cnt;                    // (owner, match, out_cnt) stay inside the mirrored part
-    u32* list; int* cnt; int* thr; int* minq; int* minqa; int* state; int* dec; int* qbin;
+    u32* list; int* cnt; int* thr; int* minq; int* claimq; int* state; int* dec; int* qbin;
 };
 static size_t work_small_bytes(int nq, int nt) { return pad((size_t)nt * 4) + pad((size_t)nq * 4) + pad(8); }
 static size_t work_scratch_bytes(int nq, int nt) {
@@ -357,7 +383,7 @@ static void take_work(Arena& A, int nq, int nt, WinWork* w) {
     w->qbin = A.take<int>(std::max(nq, 1));
     w->thr = A.take<int>(std::max(nt, 1));
     w->minq = A.take<int>(std::max(nt, 1));
-    w->minqa = A.take<int>(std::max(nt, 1));
+    w->claimq = A.take<int>(std::max(nt, 1));
 }
 static int run_search(Arena& A, const DevGrid& G, const WinWork& w, const u8* d_qdesc, const float* d_qangle, int nq, int mode,
                       int th_dist, float nnratio, int checkOri) {
@@ -366,7 +392,7 @@ static int run_search(Arena& A, const DevGrid& G, const WinWork& w, const u8* d_
     if (nq > 0) k_win_candidates<<<orb_div_up(nq, WC_WARPS), 32 * WC_WARPS, 0, A.stream>>>(G, w.win, d_qdesc, nq, stride, drop_above, w.list, w.cnt);
     ResolveParams P;
     P.nq = nq; P.nt = G.n; P.stride = stride; P.mode = mode; P.th_dist = th_dist; P.checkOri = checkOri; P.nnratio = nnratio;
-    k_win_resolve<<<1, WR_THREADS, 0, A.stream>>>(P, w.list, w.cnt, w.win, G.octave, d_qangle, G.angle, w.thr, w.minq, w.minqa, w.state, w.dec,
+    k_win_resolve<<<1, WR_THREADS, 0, A.stream>>>(P, w.list, w.cnt, w.win, G.octave, d_qangle, G.angle, w.thr, w.minq, w.claimq, w.state, w.dec,
                                                   w.qbin, w.owner, w.match, w.out_cnt);
     ORB_CUDA_TRY(cudaGetLastError());
     return ORB_OK;
