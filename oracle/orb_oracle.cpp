@@ -1141,6 +1141,12 @@ int orc_search_projection_map(const orc_grid_view* Fp, int n_points, const u8* i
 static inline void rt_apply(const float* T /*3x4*/, const float* p, float* out) {
     for (int r = 0; r < 3; r++) out[r] = ((T[4 * r] * p[0] + T[4 * r + 1] * p[1]) + T[4 * r + 2] * p[2]) + T[4 * r + 3];
 }
+// exposed for the golden test: out = T[:, :3] * p + T[:, 3] ; outT = -T[:, :3]^T * T[:, 3]
+void orc_rt_apply(const float* T, const float* p, float* out) { rt_apply(T, p, out); }
+void orc_minus_rt_t(const float* T, float* out) {
+    for (int r = 0; r < 3; r++)
+        out[r] = (float)(-(((double)T[0 * 4 + r] * T[3] + (double)T[1 * 4 + r] * T[7]) + (double)T[2 * 4 + r] * T[11]));
+}
 int orc_search_projection_frame(const orc_grid_view* Cp, const float* Tcw, const float* Tlw, float fx, float fy, float cx, float cy,
                                 float mbf, float mb, int n_last, const u8* has_point, const float* world, const int* octave,
                                 const float* angle, const u8* desc, const u8* claims, float th, int mono, int checkOri, int* owner) {
@@ -1150,7 +1156,9 @@ int orc_search_projection_frame(const orc_grid_view* Cp, const float* Tcw, const
     std::vector<int> rotHist[HISTO_LENGTH];
     // twc = -Rcw.t()*tcw ; tlc = Rlw*twc + tlw  (:1344-1352)
     float twc[3], tlc[3];
-    for (int r = 0; r < 3; r++) twc[r] = -((Tcw[0 * 4 + r] * Tcw[3] + Tcw[1 * 4 + r] * Tcw[7]) + Tcw[2 * 4 + r] * Tcw[11]);
+    // (the transposed product takes cv::gemm's general path, which accumulates float inputs in double; pinned by prim_gemm3.npz)
+    for (int r = 0; r < 3; r++)
+        twc[r] = (float)(-(((double)Tcw[0 * 4 + r] * Tcw[3] + (double)Tcw[1 * 4 + r] * Tcw[7]) + (double)Tcw[2 * 4 + r] * Tcw[11]));
     rt_apply(Tlw, twc, tlc);
     const bool bForward = tlc[2] > mb && !mono;
     const bool bBackward = -tlc[2] > mb && !mono;

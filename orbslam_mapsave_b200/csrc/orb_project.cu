@@ -451,11 +451,12 @@ extern "C" int orbm_search_by_projection_frame(const orbm_grid_view* cur, const 
     if ((rc = check_grid(cur, check_orientation != 0))) return rc;
     for (int i = 0; i < n_last; i++)
         ORB_REQUIRE(!has_point[i] || (octave[i] >= 0 && octave[i] < cur->n_levels), ORB_ERR_ARG, "LastFrame octave out of range");
-    // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw (src/ORBmatcher.cc:1344-1355); float32, left to right (cv::gemm on 3x3 floats)
+    // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw (src/ORBmatcher.cc:1344-1355); A*x+b: float32, left to right (cv::gemm on 3x3 floats)
     FrameProj P;
     for (int i = 0; i < 12; i++) P.T[i] = Tcw_cur[i];
     float twc[3];
-    for (int r = 0; r < 3; r++) twc[r] = -((Tcw_cur[r] * Tcw_cur[3] + Tcw_cur[4 + r] * Tcw_cur[7]) + Tcw_cur[8 + r] * Tcw_cur[11]);
+    for (int r = 0; r < 3; r++)           // transposed product: cv::gemm's general path accumulates in double
+        twc[r] = (float)(-(((double)Tcw_cur[r] * Tcw_cur[3] + (double)Tcw_cur[4 + r] * Tcw_cur[7]) + (double)Tcw_cur[8 + r] * Tcw_cur[11]));
     const float tlcz = ((Tcw_last[8] * twc[0] + Tcw_last[9] * twc[1]) + Tcw_last[10] * twc[2]) + Tcw_last[11];
     P.forward = (tlcz > mb && !mono) ? 1 : 0;
     P.backward = (-tlcz > mb && !mono) ? 1 : 0;

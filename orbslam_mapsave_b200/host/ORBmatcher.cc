@@ -134,14 +134,15 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
 
 int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
                                        std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
-    // Epipole in the second image (ORBmatcher.cc:667-673).  cv::Mat float products accumulate in double (cv::gemm), then round.
+    // Epipole in the second image (ORBmatcher.cc:667-673).  `R2w*Cw+t2w` is one cv::gemm(A, B, 1, C, 1) on 3x3 / 3x1 floats:
+    // float32, left to right (cv2 4.13, tests/golden/prim_gemm3.npz).
     cv::Mat Cw = pKF1->GetCameraCenter();
     cv::Mat R2w = pKF2->GetRotation();
     cv::Mat t2w = pKF2->GetTranslation();
     float C2[3];
     for (int i = 0; i < 3; i++)
-        C2[i] = (float)((double)R2w.at<float>(i, 0) * Cw.at<float>(0) + (double)R2w.at<float>(i, 1) * Cw.at<float>(1) +
-                        (double)R2w.at<float>(i, 2) * Cw.at<float>(2) + (double)t2w.at<float>(i));
+        C2[i] = ((R2w.at<float>(i, 0) * Cw.at<float>(0) + R2w.at<float>(i, 1) * Cw.at<float>(1)) + R2w.at<float>(i, 2) * Cw.at<float>(2)) +
+                t2w.at<float>(i);
     const float invz = 1.0f / C2[2];
     const float ex = pKF2->fx * C2[0] * invz + pKF2->cx;
     const float ey = pKF2->fy * C2[1] * invz + pKF2->cy;
@@ -161,6 +162,136 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     if (g_status != ORB_OK) return 0;
     vMatchedPairs.reserve(npairs);
     for (int i = 0; i < npairs; i++) vMatchedPairs.push_back(std::make_pair((size_t)pairs[2 * i], (size_t)pairs[2 * i + 1]));
+    return nmatches;
+}
+
+
+// ---- window searches ------------------------------------------------------------------------------------------
+namespace {
+// flat copy of the Frame fields GetFeaturesInArea and the candidate loops read (src/Frame.cc:445-498)
+struct GridSide {
+    std::vector<unsigned char> desc, blocked;
+    std::vector<float> x, y, angle, uright;
+    std::vector<int> octave, off, feat;
+    orbm_grid_view view;
+};
+void snapshot_frame_grid(const Frame& F, bool blockObserved, GridSide& g) {
+    const int n = F.N;
+    g.desc.resize((size_t)n * 32);
+    g.x.resize(n); g.y.resize(n); g.angle.resize(n); g.octave.resize(n); g.uright.resize(n); g.blocked.assign(n, 0);
+    for (int i = 0; i < n; i++) {
+        std::memcpy(&g.desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+        const cv::KeyPoint& kp = F.mvKeysUn[i];
+        g.x[i] = kp.pt.x; g.y[i] = kp.pt.y; g.angle[i] = kp.angle; g.octave[i] = kp.octave;
+        g.uright[i] = F.mvuRight.empty() ? -1.0f : F.mvuRight[i];
+        if (blockObserved && F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0) g.blocked[i] = 1;   // ORBmatcher.cc:87-89
+    }
+    g.off.assign(1, 0); g.feat.clear();
+    for (int ix = 0; ix < FRAME_GRID_COLS; ix++)
+        for (int iy = 0; iy < FRAME_GRID_ROWS; iy++) {
+            const std::vector<std::size_t>& cell = F.mGrid[ix][iy];
+            for (size_t k = 0; k < cell.size(); k++) g.feat.push_back((int)cell[k]);
+            g.off.push_back((int)g.feat.size());
+        }
+    std::memset(&g.view, 0, sizeof(g.view));
+    g.view.n = n;
+    g.view.desc = g.desc.data(); g.view.x = g.x.data(); g.view.y = g.y.data(); g.view.octave = g.octave.data();
+    g.view.angle = g.angle.data(); g.view.uright = g.uright.data(); g.view.blocked = g.blocked.data();
+    g.view.grid_cols = FRAME_GRID_COLS; g.view.grid_rows = FRAME_GRID_ROWS;
+    g.view.min_x = F.mnMinX; g.view.min_y = F.mnMinY; g.view.max_x = F.mnMaxX; g.view.max_y = F.mnMaxY;
+    g.view.inv_w = F.mfGridElementWidthInv; g.view.inv_h = F.mfGridElementHeightInv;
+    g.view.cell_offsets = g.off.data(); g.view.cell_features = g.feat.data();
+    g.view.scale_factors = F.mvScaleFactors.data(); g.view.n_levels = (int)F.mvScaleFactors.size();
+}
+}  // namespace
+
+int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    GridSide g;
+    snapshot_frame_grid(F, true, g);
+    const int np = (int)vpMapPoints.size();
+    std::vector<unsigned char> in_view(np), claims(np), desc((size_t)np * 32);
+    std::vector<float> px(np), py(np), pxr(np), vc(np);
+    std::vector<int> level(np);
+    for (int i = 0; i < np; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        in_view[i] = (pMP->mbTrackInView && !pMP->isBad()) ? 1 : 0;                      // ORBmatcher.cc:53-58
+        if (!in_view[i]) continue;
+        px[i] = pMP->mTrackProjX; py[i] = pMP->mTrackProjY; pxr[i] = pMP->mTrackProjXR;
+        level[i] = pMP->mnTrackScaleLevel; vc[i] = pMP->mTrackViewCos;
+        claims[i] = pMP->Observations() > 0 ? 1 : 0;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    std::vector<int> owner(F.N > 0 ? F.N : 1, -1);
+    int nmatches = 0;
+    report(orbm_search_by_projection_map(&g.view, np, in_view.data(), px.data(), py.data(), pxr.data(), level.data(), vc.data(),
+                                         desc.data(), claims.data(), th, mfNNratio, owner.data(), &nmatches, g_device));
+    if (g_status != ORB_OK) return 0;
+    for (int j = 0; j < F.N; j++)
+        if (owner[j] >= 0) F.mvpMapPoints[j] = vpMapPoints[owner[j]];
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+    GridSide g;
+    snapshot_frame_grid(CurrentFrame, true, g);
+    float Tc[12], Tl[12];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) { Tc[4 * r + c] = CurrentFrame.mTcw.at<float>(r, c); Tl[4 * r + c] = LastFrame.mTcw.at<float>(r, c); }
+    const int nl = LastFrame.N;
+    std::vector<unsigned char> has(nl, 0), claims(nl, 0), desc((size_t)nl * 32);
+    std::vector<float> world((size_t)nl * 3), angle(nl);
+    std::vector<int> octave(nl);
+    for (int i = 0; i < nl; i++) {
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;                                   // ORBmatcher.cc:1359-1363
+        has[i] = 1;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        for (int k = 0; k < 3; k++) world[3 * (size_t)i + k] = x3Dw.at<float>(k);
+        octave[i] = LastFrame.mvKeys[i].octave;
+        angle[i] = LastFrame.mvKeysUn[i].angle;
+        claims[i] = pMP->Observations() > 0 ? 1 : 0;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&desc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    std::vector<int> owner(CurrentFrame.N > 0 ? CurrentFrame.N : 1, -1);
+    int nmatches = 0;
+    report(orbm_search_by_projection_frame(&g.view, Tc, Tl, CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy,
+                                           CurrentFrame.mbf, CurrentFrame.mb, nl, has.data(), world.data(), octave.data(), angle.data(),
+                                           desc.data(), claims.data(), th, bMono ? 1 : 0, mbCheckOrientation ? 1 : 0, owner.data(),
+                                           &nmatches, g_device));
+    if (g_status != ORB_OK) return 0;
+    for (int j = 0; j < CurrentFrame.N; j++) {
+        if (owner[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[owner[j]];
+        else if (owner[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL);   // rotation cull, :1452-1456
+    }
+    return nmatches;
+}
+
+int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                        int windowSize) {
+    GridSide g;
+    snapshot_frame_grid(F2, false, g);
+    g.view.uright = NULL; g.view.blocked = NULL;
+    const int n1 = (int)F1.mvKeysUn.size();
+    vnMatches12 = std::vector<int>(n1, -1);
+    std::vector<unsigned char> desc((size_t)n1 * 32);
+    std::vector<int> octave(n1);
+    std::vector<float> angle(n1), prev((size_t)2 * n1);
+    for (int i = 0; i < n1; i++) {
+        std::memcpy(&desc[(size_t)i * 32], F1.mDescriptors.ptr(i), 32);
+        octave[i] = F1.mvKeysUn[i].octave; angle[i] = F1.mvKeysUn[i].angle;
+        prev[2 * (size_t)i] = vbPrevMatched[i].x; prev[2 * (size_t)i + 1] = vbPrevMatched[i].y;
+    }
+    std::vector<int> m12(n1 > 0 ? n1 : 1, -1);
+    int nmatches = 0;
+    report(orbm_search_for_initialization(&g.view, n1, desc.data(), octave.data(), angle.data(), prev.data(), windowSize, mfNNratio,
+                                          mbCheckOrientation ? 1 : 0, m12.data(), &nmatches, g_device));
+    if (g_status != ORB_OK) return 0;
+    for (int i = 0; i < n1; i++) {
+        vnMatches12[i] = m12[i];
+        vbPrevMatched[i] = cv::Point2f(prev[2 * (size_t)i], prev[2 * (size_t)i + 1]);
+    }
     return nmatches;
 }
 

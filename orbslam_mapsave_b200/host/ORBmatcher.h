@@ -1,7 +1,8 @@
 // ORBmatcher.h — drop-in for the hot-path members of the reference's include/ORBmatcher.h:37-101:
-// DescriptorDistance, both SearchByBoW overloads, SearchForTriangulation (+ the constants).  Same signatures; bodies marshal
-// to the C ABI of include/orb_b200.h.  The projection / fuse / Sim3 searches of the reference class are outside this path
-//  and stay in the reference's own ORBmatcher.cc — see INTEGRATION.md.
+// DescriptorDistance, both SearchByBoW overloads, SearchForTriangulation (+ the constants), and — first "next" row of
+// SURVEY.md §8f — the window searches SearchByProjection(Frame, MapPoints), SearchByProjection(CurrentFrame, LastFrame) and
+// SearchForInitialization.  Same signatures; bodies marshal to the C ABI of include/orb_b200.h.  The relocalisation / loop /
+// fuse / Sim3 searches of the reference class stay in the reference's own ORBmatcher.cc — see INTEGRATION.md.
 #ifndef ORB_B200_ORBMATCHER_H
 #define ORB_B200_ORBMATCHER_H
 
@@ -22,6 +23,16 @@ public:
     // Brute force constrained to ORB that belong to the same vocabulary node (reference :65-66)
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
+
+    // Search matches between Frame keypoints and projected MapPoints. Returns number of matches.  Used to track the local map
+    // (Tracking) (reference :48, src/ORBmatcher.cc:45-129)
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3);
+    // Project MapPoints tracked in last frame into the current frame and search matches.  Used to track from previous frame
+    // (Tracking) (reference :52, src/ORBmatcher.cc:1331-1463)
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    // Matching for the Map Initialization (only used in the monocular case) (reference :69, src/ORBmatcher.cc:408-523)
+    int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                int windowSize = 10);
 
     // Matching to triangulate new MapPoints. Check Epipolar Constraint. (reference :72-73)
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,

@@ -50,9 +50,21 @@ namespace ORB_SLAM2 {
 class MapPoint {
 public:
     bool isBad() { return mbBad; }
+    int Observations() { return nObs; }                                // include/MapPoint.h:64
+    cv::Mat GetDescriptor() { return mDescriptor.clone(); }            // :87
+    cv::Mat GetWorldPos() { return mWorldPos.clone(); }                // :58
+    // variables used by the tracking, written by Frame::isInFrustum (include/MapPoint.h:106-111)
+    float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0;
+    bool mbTrackInView = false;
+    int mnTrackScaleLevel = 0;
+    float mTrackViewCos = 0;
     bool mbBad = false;
+    int nObs = 0;
+    cv::Mat mDescriptor, mWorldPos;                                    // 1x32 CV_8U, 3x1 CV_32F
 };
 
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
 class Frame {
 public:
     int N = 0;
@@ -61,6 +73,13 @@ public:
     DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
     std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
+    cv::Mat mTcw;                                                      // 4x4 CV_32F
+    float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
+    std::vector<float> mvScaleFactors;
+    float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;              // static members in the reference (include/Frame.h:192-195)
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;       // static in the reference (:168-169)
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];  // :170
 };
 
 class KeyFrame {

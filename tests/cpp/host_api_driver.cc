@@ -2,6 +2,7 @@
 // Frame / LocalMapping code does, on inputs written by tests/test_gpu_host_cpp.py; writes results back as raw binaries.
 //   driver extract <in.raw> <w> <h> <nfeat> <scale> <nlevels> <ini> <min> <out_prefix> [mask.raw]
 //   driver match   <in.bin> <out.bin>
+//   driver project <in.bin> <out.bin>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -178,10 +179,141 @@ static int run_bow(int argc, char** argv) {
     return 0;
 }
 
+
+// driver project <in.bin> <out.bin>: the window searches the way Tracking calls them (SearchLocalPoints, TrackWithMotionModel,
+// MonocularInitialization).  The Frame is assembled like Frame::Frame does: AssignFeaturesToGrid with PosInGrid's round().
+#include <cmath>
+static void build_frame(Reader& r, Frame& F) {
+    const int n = r.get<int>();
+    F.N = n;
+    std::vector<unsigned char> desc = r.arr<unsigned char>((size_t)n * 32);
+    F.mDescriptors = cv::Mat(n, 32, CV_8U);
+    for (int i = 0; i < n; i++) memcpy(F.mDescriptors.ptr(i), &desc[(size_t)i * 32], 32);
+    std::vector<float> x = r.arr<float>(n), y = r.arr<float>(n), ang = r.arr<float>(n), ur = r.arr<float>(n);
+    std::vector<int> oct = r.arr<int>(n);
+    std::vector<float> b = r.arr<float>(4);
+    const int nlev = r.get<int>();
+    F.mvScaleFactors = r.arr<float>(nlev);
+    F.mnMinX = b[0]; F.mnMinY = b[1]; F.mnMaxX = b[2]; F.mnMaxY = b[3];
+    F.mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (F.mnMaxX - F.mnMinX);
+    F.mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (F.mnMaxY - F.mnMinY);
+    F.mvKeysUn.resize(n); F.mvKeys.resize(n); F.mvuRight = ur;
+    F.mvpMapPoints.assign(n, (MapPoint*)NULL);
+    F.mvbOutlier.assign(n, false);
+    for (int i = 0; i < n; i++) {
+        F.mvKeysUn[i] = cv::KeyPoint(x[i], y[i], 31, ang[i], 10, oct[i]);
+        F.mvKeys[i] = F.mvKeysUn[i];
+        const int px = (int)round((x[i] - F.mnMinX) * F.mfGridElementWidthInv), py = (int)round((y[i] - F.mnMinY) * F.mfGridElementHeightInv);
+        if (px < 0 || px >= FRAME_GRID_COLS || py < 0 || py >= FRAME_GRID_ROWS) continue;
+        F.mGrid[px][py].push_back(i);
+    }
+}
+static cv::Mat mat_from(const std::vector<float>& v, int rows, int cols) {
+    cv::Mat m(rows, cols, CV_32F);
+    for (int i = 0; i < rows * cols; i++) m.at<float>(i / cols, i % cols) = v[i];
+    return m;
+}
+static int run_project(int argc, char** argv) {
+    if (argc < 4) return 2;
+    Reader r; r.buf = slurp(argv[2]);
+    std::ofstream out(argv[3], std::ios::binary);
+    const float ratio = r.get<float>();
+    const int ori = r.get<int>();
+    ORBmatcher m(ratio, ori != 0);
+    {   // SearchByProjection(F, vpMapPoints, th)
+        Frame* F = new Frame();
+        build_frame(r, *F);
+        std::vector<unsigned char> blocked = r.arr<unsigned char>(F->N);
+        std::vector<MapPoint> own(F->N);                 // pre-existing points of the frame: observed ones block their feature
+        for (int i = 0; i < F->N; i++) { own[i].nObs = blocked[i] ? 2 : 0; F->mvpMapPoints[i] = (i % 3 == 0 || blocked[i]) ? &own[i] : NULL; }
+        const int np = r.get<int>();
+        const float th = r.get<float>();
+        std::vector<unsigned char> in_view = r.arr<unsigned char>(np), claims = r.arr<unsigned char>(np), d = r.arr<unsigned char>((size_t)np * 32);
+        std::vector<float> px = r.arr<float>(np), py = r.arr<float>(np), pxr = r.arr<float>(np), vc = r.arr<float>(np);
+        std::vector<int> lvl = r.arr<int>(np);
+        std::vector<MapPoint> pool(np);
+        std::vector<MapPoint*> vp(np);
+        for (int i = 0; i < np; i++) {
+            pool[i].mbTrackInView = in_view[i] != 0; pool[i].mTrackProjX = px[i]; pool[i].mTrackProjY = py[i]; pool[i].mTrackProjXR = pxr[i];
+            pool[i].mnTrackScaleLevel = lvl[i]; pool[i].mTrackViewCos = vc[i]; pool[i].nObs = claims[i] ? 3 : 0;
+            pool[i].mDescriptor = cv::Mat(1, 32, CV_8U); memcpy(pool[i].mDescriptor.ptr(0), &d[(size_t)i * 32], 32);
+            vp[i] = &pool[i];
+        }
+        const int n = m.SearchByProjection(*F, vp, th);
+        put(out, &n, 1);
+        std::vector<int> owner(F->N, -1);
+        for (int j = 0; j < F->N; j++)
+            if (F->mvpMapPoints[j] && np && F->mvpMapPoints[j] >= &pool[0] && F->mvpMapPoints[j] <= &pool[np - 1]) owner[j] = (int)(F->mvpMapPoints[j] - &pool[0]);
+        put(out, owner.data(), owner.size());
+        delete F;
+    }
+    {   // SearchByProjection(CurrentFrame, LastFrame, th, bMono)
+        Frame* C = new Frame(); Frame* L = new Frame();
+        build_frame(r, *C);
+        std::vector<unsigned char> blocked = r.arr<unsigned char>(C->N);
+        std::vector<MapPoint> own(C->N);
+        for (int i = 0; i < C->N; i++) { own[i].nObs = blocked[i] ? 2 : 0; C->mvpMapPoints[i] = (i % 3 == 0 || blocked[i]) ? &own[i] : NULL; }
+        C->mTcw = mat_from(r.arr<float>(16), 4, 4); L->mTcw = mat_from(r.arr<float>(16), 4, 4);
+        std::vector<float> K = r.arr<float>(6);
+        C->fx = K[0]; C->fy = K[1]; C->cx = K[2]; C->cy = K[3]; C->mbf = K[4]; C->mb = K[5];
+        const float th = r.get<float>();
+        const int mono = r.get<int>(), nl = r.get<int>();
+        std::vector<unsigned char> has = r.arr<unsigned char>(nl), claims = r.arr<unsigned char>(nl), d = r.arr<unsigned char>((size_t)nl * 32);
+        std::vector<float> world = r.arr<float>((size_t)nl * 3), ang = r.arr<float>(nl);
+        std::vector<int> oct = r.arr<int>(nl);
+        L->N = nl; L->mvKeys.resize(nl); L->mvKeysUn.resize(nl); L->mvpMapPoints.assign(nl, (MapPoint*)NULL); L->mvbOutlier.assign(nl, false);
+        std::vector<MapPoint> pool(nl);
+        for (int i = 0; i < nl; i++) {
+            L->mvKeys[i] = cv::KeyPoint(0, 0, 31, ang[i], 10, oct[i]); L->mvKeysUn[i] = L->mvKeys[i];
+            pool[i].nObs = claims[i] ? 3 : 0;
+            pool[i].mDescriptor = cv::Mat(1, 32, CV_8U); memcpy(pool[i].mDescriptor.ptr(0), &d[(size_t)i * 32], 32);
+            pool[i].mWorldPos = cv::Mat(3, 1, CV_32F);
+            for (int k = 0; k < 3; k++) pool[i].mWorldPos.at<float>(k) = world[3 * (size_t)i + k];
+            if (has[i]) L->mvpMapPoints[i] = &pool[i];
+            else if (i % 2) { L->mvpMapPoints[i] = &pool[i]; L->mvbOutlier[i] = true; }      // outliers are skipped like missing points
+        }
+        const int n = m.SearchByProjection(*C, *L, th, mono != 0);
+        put(out, &n, 1);
+        std::vector<int> owner(C->N, -1);
+        for (int j = 0; j < C->N; j++) {
+            MapPoint* p = C->mvpMapPoints[j];
+            if (p && nl && p >= &pool[0] && p <= &pool[nl - 1]) owner[j] = (int)(p - &pool[0]);
+            else if (!p && (j % 3 == 0 || blocked[j])) owner[j] = -2;                        // a pre-existing point was set to NULL
+        }
+        put(out, owner.data(), owner.size());
+        delete C; delete L;
+    }
+    {   // SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+        Frame* F2 = new Frame(); Frame* F1 = new Frame();
+        build_frame(r, *F2);
+        const int n1 = r.get<int>(), window = r.get<int>();
+        std::vector<unsigned char> d = r.arr<unsigned char>((size_t)n1 * 32);
+        std::vector<int> oct = r.arr<int>(n1);
+        std::vector<float> ang = r.arr<float>(n1), prev = r.arr<float>((size_t)n1 * 2);
+        F1->N = n1; F1->mvKeysUn.resize(n1);
+        F1->mDescriptors = cv::Mat(n1, 32, CV_8U);
+        std::vector<cv::Point2f> vbPrev(n1);
+        for (int i = 0; i < n1; i++) {
+            memcpy(F1->mDescriptors.ptr(i), &d[(size_t)i * 32], 32);
+            F1->mvKeysUn[i] = cv::KeyPoint(prev[2 * i], prev[2 * i + 1], 31, ang[i], 10, oct[i]);
+            vbPrev[i] = cv::Point2f(prev[2 * i], prev[2 * i + 1]);
+        }
+        std::vector<int> m12(3, 7);
+        const int n = m.SearchForInitialization(*F1, *F2, vbPrev, m12, window);
+        put(out, &n, 1);
+        const int sz = (int)m12.size(); put(out, &sz, 1);
+        put(out, m12.data(), m12.size());
+        for (int i = 0; i < n1; i++) { const float p[2] = {vbPrev[i].x, vbPrev[i].y}; put(out, p, 2); }
+        delete F1; delete F2;
+    }
+    return ORBmatcher::LastStatus() == 0 ? 0 : 4;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     if (!strcmp(argv[1], "bow")) return run_bow(argc, argv);
     if (!strcmp(argv[1], "extract")) return run_extract(argc, argv);
     if (!strcmp(argv[1], "match")) return run_match(argc, argv);
+    if (!strcmp(argv[1], "project")) return run_project(argc, argv);
     return 2;
 }

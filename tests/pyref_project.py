@@ -129,7 +129,7 @@ def search_projection_frame(cf, lf, mbf, mb, th, mono, check_ori):
     owner = [-1] * cf.n
     n = 0
     hist = [[] for _ in range(HISTO_LENGTH)]
-    twc = [F(-F(F(F(Tcw[0, r] * Tcw[0, 3]) + F(Tcw[1, r] * Tcw[1, 3])) + F(Tcw[2, r] * Tcw[2, 3]))) for r in range(3)]
+    twc = [F(-((float(Tcw[0, r]) * float(Tcw[0, 3]) + float(Tcw[1, r]) * float(Tcw[1, 3])) + float(Tcw[2, r]) * float(Tcw[2, 3]))) for r in range(3)]
     tlc = _rt(Tlw, twc)
     fwd = bool(tlc[2] > F(mb)) and not mono
     bwd = bool(F(-tlc[2]) > F(mb)) and not mono

@@ -127,9 +127,8 @@ def test_cpp_orbmatcher_matches_oracle(tmp_path, seed, ratio, ori, only_stereo):
     got = np.frombuffer(out, np.int32, sz, pos); pos += 4 * sz
     on, om = orc.search_bow_kf_kf(desc[0], good[0], ang[0], fv[0], desc[1], good[1], ang[1], fv[1], np.float32(ratio), ori)
     assert nm == on and np.array_equal(got, om)
-    # SearchForTriangulation: epipole as the class computes it (double accumulation like cv::gemm, then float)
-    C2 = np.array([np.float32(float(R[i, 0]) * float(Ow[0]) + float(R[i, 1]) * float(Ow[1]) + float(R[i, 2]) * float(Ow[2]) + float(t[i]))
-                   for i in range(3)], np.float32)
+    # SearchForTriangulation: epipole as the class computes it (cv::gemm on 3x3 floats: float32, left to right; prim_gemm3.npz)
+    C2 = (((R[:, 0] * Ow[0] + R[:, 1] * Ow[1]) + R[:, 2] * Ow[2]) + t).astype(np.float32)
     invz = np.float32(1.0) / C2[2]
     ex = K[0] * C2[0] * invz + K[2]
     ey = K[1] * C2[1] * invz + K[3]
@@ -183,3 +182,70 @@ def test_cpp_vocabulary_transform_matches_oracle(tmp_path):
     idx = np.nonzero(keep)[0]
     for j, lst in enumerate(lists):
         assert np.array_equal(lst, idx[ofv.feat[ofv.off[j]:ofv.off[j + 1]]])
+
+
+@pytest.mark.parametrize("seed,mono,ori", [(0, False, 1), (1, True, 1), (2, False, 0)])
+def test_cpp_window_searches_match_oracle(tmp_path, seed, mono, ori):
+    """ORBmatcher::SearchByProjection(F, MapPoints) / (CurrentFrame, LastFrame) / SearchForInitialization through the C++ class,
+    on Frames assembled like Frame::Frame does (AssignFeaturesToGrid), against the oracle."""
+    import proj_util as pu
+    rng = np.random.default_rng(100 + seed)
+    ratio = 0.8
+
+    def frame_blob(fa):
+        ur = fa["uright"] if fa["uright"] is not None else np.full(len(fa["x"]), -1, np.float32)
+        return (struct.pack("<i", len(fa["x"])) + fa["desc"].tobytes() + fa["x"].tobytes() + fa["y"].tobytes() + fa["angle"].tobytes() +
+                ur.astype(np.float32).tobytes() + fa["octave"].tobytes() + np.array(fa["bounds"], np.float32).tobytes() +
+                struct.pack("<i", 8) + pu.SCALE.tobytes())
+
+    blob = struct.pack("<fi", ratio, ori)
+    # A: local map points
+    n = 1500
+    faA = pu.frame_arrays(n, rng, stereo=not mono, cluster=seed == 2)
+    blockedA = (rng.random(n) < 0.15).astype(np.uint8)
+    mp = pu.map_points_for(faA, 2000, rng)
+    th = 3.0
+    blob += frame_blob(faA) + blockedA.tobytes() + struct.pack("<if", 2000, th)
+    blob += mp["in_view"].tobytes() + mp["claims"].tobytes() + mp["desc"].tobytes()
+    blob += mp["proj_x"].tobytes() + mp["proj_y"].tobytes() + mp["proj_xr"].tobytes() + mp["view_cos"].tobytes() + mp["level"].tobytes()
+    # B: last frame
+    faB = pu.frame_arrays(n, rng, stereo=not mono)
+    blockedB = (rng.random(n) < 0.1).astype(np.uint8)
+    lf = pu.last_frame_for(faB, 1800, rng, tz=0.3 if seed == 2 else 0.0)
+    mbf, mb, thB = 40.0, np.float32(40.0) / np.float32(lf["fx"]), 15.0 if mono else 7.0
+    T4 = lambda T: np.concatenate([T, np.array([[0, 0, 0, 1]], np.float32)], 0).astype(np.float32)
+    blob += frame_blob(faB) + blockedB.tobytes() + T4(lf["Tcw"]).tobytes() + T4(lf["Tlw"]).tobytes()
+    blob += np.array([lf["fx"], lf["fy"], lf["cx"], lf["cy"], mbf, mb], np.float32).tobytes() + struct.pack("<fii", thB, int(mono), 1800)
+    blob += lf["has_point"].tobytes() + lf["claims"].tobytes() + lf["desc"].tobytes() + lf["world"].tobytes() + lf["angle"].tobytes() + lf["octave"].tobytes()
+    # C: initialisation
+    faC = pu.frame_arrays(n, rng, stereo=False)
+    faC["octave"][rng.random(n) < 0.5] = 0
+    f1 = pu.init_frame1_for(faC, 1600, rng)
+    blob += frame_blob(faC) + struct.pack("<ii", 1600, 100) + f1["desc1"].tobytes() + f1["octave1"].tobytes() + f1["angle1"].tobytes() + f1["prev"].tobytes()
+    (tmp_path / "in.bin").write_bytes(blob)
+    subprocess.check_call([_driver(), "project", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = (tmp_path / "out.bin").read_bytes()
+    pos = 0
+    # A
+    (nm,) = struct.unpack_from("<i", out, pos); pos += 4
+    got = np.frombuffer(out, np.int32, n, pos); pos += 4 * n
+    ogA = orc.Grid(faA["desc"], faA["x"], faA["y"], faA["octave"], pu.SCALE, faA["bounds"], angle=faA["angle"], uright=faA["uright"], blocked=blockedA)
+    on, oo = orc.search_projection_map(ogA, th=th, nnratio=ratio, **mp)
+    assert nm == on and np.array_equal(got, oo) and on > 100
+    # B
+    (nm,) = struct.unpack_from("<i", out, pos); pos += 4
+    got = np.frombuffer(out, np.int32, n, pos); pos += 4 * n
+    ogB = orc.Grid(faB["desc"], faB["x"], faB["y"], faB["octave"], pu.SCALE, faB["bounds"], angle=faB["angle"], uright=faB["uright"], blocked=blockedB)
+    on, oo = orc.search_projection_frame(ogB, lf["Tcw"], lf["Tlw"], lf["fx"], lf["fy"], lf["cx"], lf["cy"], mbf, mb, lf["has_point"], lf["world"],
+                                         lf["octave"], lf["angle"], lf["desc"], lf["claims"], thB, mono, ori)
+    had_point = (np.arange(n) % 3 == 0) | (blockedB != 0)
+    want = np.where((oo == -2) & ~had_point, -1, oo)        # NULLing an entry that held nothing is invisible to the caller
+    assert nm == on and np.array_equal(got, want) and (oo >= 0).sum() > 100
+    # C
+    nm, sz = struct.unpack_from("<ii", out, pos); pos += 8
+    got = np.frombuffer(out, np.int32, sz, pos); pos += 4 * sz
+    gprev = np.frombuffer(out, np.float32, 2 * 1600, pos).reshape(-1, 2)
+    ogC = orc.Grid(faC["desc"], faC["x"], faC["y"], faC["octave"], pu.SCALE, faC["bounds"], angle=faC["angle"])
+    oprev = f1["prev"].copy()
+    on, om = orc.search_initialization(ogC, f1["desc1"], f1["octave1"], f1["angle1"], oprev, 100, ratio, ori)
+    assert nm == on and sz == 1600 and np.array_equal(got, om) and np.array_equal(gprev, oprev) and on > 50

@@ -97,3 +97,22 @@ def test_full_extractor_matches_cv2_chain(path):
     for f in ("x", "y", "size", "response", "octave", "class_id", "angle"):
         assert np.array_equal(kp[f], want[f]), f
     assert np.array_equal(desc, g["desc"])
+
+
+def test_small_gemm_matches_cv2(golden_dir):
+    """`Rcw*x3Dw+tcw` (src/ORBmatcher.cc:1365) = cv::gemm(A, B, 1, C, 1): float32 left to right for 3x3 floats;
+    `-Rcw.t()*tcw` (:1347) takes the general path with double accumulation (tests/golden/make_golden_gemm.py)."""
+    import ctypes as C
+    g = np.load(os.path.join(golden_dir, "prim_gemm3.npz"))
+    L = orc.lib()
+    L.orc_rt_apply.argtypes = [C.c_void_p] * 3
+    L.orc_minus_rt_t.argtypes = [C.c_void_p] * 2
+    R, x, t = g["R"], g["x"], g["t"]
+    out = np.zeros(3, np.float32)
+    for i in range(len(R)):
+        T = np.ascontiguousarray(np.concatenate([R[i], t[i][:, None]], 1), np.float32)
+        L.orc_rt_apply(T.ctypes.data, x[i].ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, g["out"][i]), i
+        T2 = np.ascontiguousarray(np.concatenate([R[i], x[i][:, None]], 1), np.float32)
+        L.orc_minus_rt_t(T2.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, g["outT"][i]), i
