@@ -284,6 +284,17 @@ int orbm_search_for_initialization(const orbm_grid_view* f2, int n1, const uint8
                                    const float* angle1, float* prev_xy, int window_size, float nnratio,
                                    int check_orientation, int* matches12, int* n_matches, int device);
 
+/* The shared core of the two remaining SearchByProjection overloads — (Frame& CurrentFrame, KeyFrame*, sAlreadyFound, th,
+ * ORBdist) src/ORBmatcher.cc:1465-1602 (relocalisation) and (KeyFrame*, Scw, vpPoints, vpMatched, th) :293-406 (loop closing):
+ * per query an explicit window (u, v, r) with the level bounds given to GetFeaturesInArea (:1536 / the test at :380-381), the
+ * nearest descriptor among features that are neither `target->blocked` nor taken by an earlier query (first wins ties),
+ * accepted when its distance <= th_dist; an accepted match blocks its feature.  The per-point projection (Rcw*x+tcw, the depth
+ * and viewing-angle tests, MapPoint::PredictScale) is done by the C++ class where the MapPoint objects live.
+ * owner[target->n]: query index; -1 = entry left alone; -2 = set to NULL by the rotation cull (:1583-1599).  */
+int orbm_search_windows(const orbm_grid_view* target, int nq, const uint8_t* active, const float* u, const float* v,
+                        const float* r, const int* min_level, const int* max_level, const uint8_t* desc, const float* angle,
+                        int th_dist, int check_orientation, int* owner, int* n_matches, int device);
+
 /* POPC issue-rate microbenchmark (defines the matching roofline): returns measured 32-bit POPC results
  * per second on `device` over a register-resident loop. */
 int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);

@@ -1258,4 +1258,138 @@ int orc_search_initialization(const orc_grid_view* F2p, int n1, const u8* desc1,
     return nmatches;
 }
 
+
+// ---- the shared core of the remaining projection searches: explicit windows, best candidate, every accepted match blocks ------
+// per query: active, (u, v, r), GetFeaturesInArea level bounds; candidates with F.blocked are skipped (:1548-1549 / :375-376).
+// owner[F.n]: query index, -1 untouched, -2 set to NULL by the rotation cull (only with checkOri).
+int orc_search_windows(const orc_grid_view* Fp, int nq, const u8* active, const float* u, const float* v, const float* r,
+                       const int* min_level, const int* max_level, const u8* desc, const float* angle, int th_dist, int checkOri,
+                       int* owner) {
+    const orc_grid_view& F = *Fp;
+    for (int i = 0; i < F.n; i++) owner[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH], cand;
+    for (int q = 0; q < nq; q++) {
+        if (!active[q]) continue;
+        features_in_area(F, u[q], v[q], r[q], min_level[q], max_level[q], cand);
+        if (cand.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : cand) {
+            if ((F.blocked && F.blocked[i2]) || owner[i2] >= 0) continue;
+            const int dist = descriptor_distance(desc + (size_t)q * 32, F.desc + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= th_dist) {
+            owner[bestIdx2] = q;
+            nmatches++;
+            if (checkOri) rotHist[rot_bin(angle[q], F.angle[bestIdx2])].push_back(bestIdx2);
+        }
+    }
+    if (checkOri) {
+        int sizes[HISTO_LENGTH], ind1 = -1, ind2 = -1, ind3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sizes[i] = (int)rotHist[i].size();
+        three_maxima(sizes, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int j : rotHist[i]) { owner[j] = -2; nmatches--; }
+    }
+    return nmatches;
+}
+
+// MapPoint::PredictScale, src/MapPoint.cc:633-642: ceil(log(mfMaxDistance / dist) / logScaleFactor), float log (std::log(float)).
+// This fork does not clamp the result, and then indexes mvScaleFactors with it (undefined behaviour outside [0, nlevels));
+// oracle and product clamp to the valid range, as upstream ORB-SLAM2 does since 2017.
+static int predict_scale(float mfMaxDistance, float currentDist, float logScaleFactor, int nlevels) {
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = (int)std::ceil(std::log(ratio) / logScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= nlevels) nScale = nlevels - 1;
+    return nScale;
+}
+static inline float norm3(const float* p) {          // cv::norm(3x1 CV_32F): double accumulation, sqrt, then -> float (prim_gemm3.npz)
+    return (float)std::sqrt((double)p[0] * p[0] + (double)p[1] * p[1] + (double)p[2] * p[2]);
+}
+static inline void minus_rt_t(const float* T, float* out) {
+    for (int r = 0; r < 3; r++)
+        out[r] = (float)(-(((double)T[0 * 4 + r] * T[3] + (double)T[1 * 4 + r] * T[7]) + (double)T[2 * 4 + r] * T[11]));
+}
+
+// SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist), ORBmatcher.cc:1465-1602.
+// valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP); CF.blocked = CurrentFrame.mvpMapPoints[i2] != NULL (:1548-1549).
+int orc_search_projection_kf(const orc_grid_view* Cp, const float* Tcw, float fx, float fy, float cx, float cy, float logScaleFactor,
+                             int n_kf, const u8* valid, const float* world, const float* mf_max, const float* mf_min,
+                             const float* angle, const u8* desc, float th, int ORBdist, int checkOri, int* owner) {
+    const orc_grid_view& CF = *Cp;
+    std::vector<u8> active(n_kf, 0);
+    std::vector<float> u(n_kf, 0.f), v(n_kf, 0.f), rad(n_kf, 0.f);
+    std::vector<int> minL(n_kf, -1), maxL(n_kf, -1);
+    float Ow[3];
+    minus_rt_t(Tcw, Ow);
+    for (int i = 0; i < n_kf; i++) {
+        if (!valid[i]) continue;
+        float x3Dc[3];
+        const float* x3Dw = world + 3 * (size_t)i;
+        rt_apply(Tcw, x3Dw, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = 1.0 / x3Dc[2];
+        const float uu = fx * xc * invzc + cx;
+        const float vv = fy * yc * invzc + cy;
+        if (uu < CF.min_x || uu > CF.max_x) continue;
+        if (vv < CF.min_y || vv > CF.max_y) continue;
+        const float PO[3] = {x3Dw[0] - Ow[0], x3Dw[1] - Ow[1], x3Dw[2] - Ow[2]};
+        const float dist3D = norm3(PO);
+        const float maxDistance = 1.2f * mf_max[i], minDistance = 0.8f * mf_min[i];
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = predict_scale(mf_max[i], dist3D, logScaleFactor, CF.n_levels);
+        active[i] = 1; u[i] = uu; v[i] = vv;
+        rad[i] = th * CF.scale_factors[nPredictedLevel];
+        minL[i] = nPredictedLevel - 1; maxL[i] = nPredictedLevel + 1;
+    }
+    return orc_search_windows(Cp, n_kf, active.data(), u.data(), v.data(), rad.data(), minL.data(), maxL.data(), desc, angle, ORBdist,
+                              checkOri, owner);
+}
+
+// SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th),
+// ORBmatcher.cc:293-406.  Scw: rows 0..2 of the 4x4 similarity.  valid[i] = !isBad() && !spAlreadyFound.count(pMP);
+// KF.blocked = vpMatched[idx] != NULL.  Conventions for the cv::Mat expressions that cannot be pinned from Python:
+// row.dot(row) and PO.dot(Pn) accumulate in double (cv::Mat::dot); sRcw/scw and col/scw multiply by (float)(1.0/scw).
+int orc_search_projection_sim3(const orc_grid_view* Kp, const float* Scw, float fx, float fy, float cx, float cy, float logScaleFactor,
+                               int n_pts, const u8* valid, const float* world, const float* mf_max, const float* mf_min,
+                               const float* normal, const u8* desc, int th, int* owner) {
+    const orc_grid_view& KF = *Kp;
+    const float scw = (float)std::sqrt((double)Scw[0] * Scw[0] + (double)Scw[1] * Scw[1] + (double)Scw[2] * Scw[2]);
+    const float inv = (float)(1.0 / (double)scw);
+    float T[12];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[4 * r + c] = Scw[4 * r + c] * inv;
+    float Ow[3];
+    minus_rt_t(T, Ow);
+    std::vector<u8> active(n_pts, 0);
+    std::vector<float> u(n_pts, 0.f), v(n_pts, 0.f), rad(n_pts, 0.f);
+    std::vector<int> minL(n_pts, -1), maxL(n_pts, -1);
+    for (int i = 0; i < n_pts; i++) {
+        if (!valid[i]) continue;
+        const float* p3Dw = world + 3 * (size_t)i;
+        float p3Dc[3];
+        rt_apply(T, p3Dw, p3Dc);
+        if (p3Dc[2] < 0.0) continue;
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float uu = fx * x + cx, vv = fy * y + cy;
+        if (!(uu >= KF.min_x && uu < KF.max_x && vv >= KF.min_y && vv < KF.max_y)) continue;       // KeyFrame::IsInImage
+        const float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        const float dist = norm3(PO);
+        const float maxDistance = 1.2f * mf_max[i], minDistance = 0.8f * mf_min[i];
+        if (dist < minDistance || dist > maxDistance) continue;
+        const float* Pn = normal + 3 * (size_t)i;
+        const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
+        if (dot < 0.5 * dist) continue;
+        const int nPredictedLevel = predict_scale(mf_max[i], dist, logScaleFactor, KF.n_levels);
+        active[i] = 1; u[i] = uu; v[i] = vv;
+        rad[i] = th * KF.scale_factors[nPredictedLevel];
+        minL[i] = nPredictedLevel - 1; maxL[i] = nPredictedLevel;
+    }
+    return orc_search_windows(Kp, n_pts, active.data(), u.data(), v.data(), rad.data(), minL.data(), maxL.data(), desc, nullptr, TH_LOW, 0, owner);
+}
+
 }  // extern "C"

@@ -435,3 +435,49 @@ def search_initialization(grid2, desc1, octave1, angle1, prev_matched, window_si
     g = grid2.c()
     n = f(C.byref(g), len(desc1), _p(desc1), _p(octave1), _p(angle1), _p(prev_matched), int(window_size), float(nnratio), int(check_ori), _p(m))
     return n, m[:len(desc1)]
+
+
+def search_windows(grid, active, u, v, r, min_level, max_level, desc, angle, th_dist, check_ori):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    active, desc = _u8(active), _u8(desc).reshape(-1, 32)
+    u, v, r, min_level, max_level = f32(u), f32(v), f32(r), i32(min_level), i32(max_level)
+    angle = f32(angle) if angle is not None else None
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    f = lib().orc_search_windows
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(GridViewC), C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p]
+    g = grid.c()
+    n = f(C.byref(g), len(active), _p(active), _p(u), _p(v), _p(r), _p(min_level), _p(max_level), _p(desc), _p(angle), int(th_dist),
+          int(check_ori), _p(owner))
+    return n, owner[:grid.n]
+
+
+def search_projection_kf(grid, Tcw, fx, fy, cx, cy, log_sf, valid, world, mf_max, mf_min, angle, desc, th, orb_dist, check_ori):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    valid, desc = _u8(valid), _u8(desc).reshape(-1, 32)
+    world, mf_max, mf_min, angle = f32(world).reshape(-1, 3), f32(mf_max), f32(mf_min), f32(angle)
+    T = f32(Tcw).reshape(-1)[:12].copy()
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    f = lib().orc_search_projection_kf
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(GridViewC), C.c_void_p] + [C.c_float] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]
+    g = grid.c()
+    n = f(C.byref(g), _p(T), fx, fy, cx, cy, log_sf, len(valid), _p(valid), _p(world), _p(mf_max), _p(mf_min), _p(angle), _p(desc),
+          float(th), int(orb_dist), int(check_ori), _p(owner))
+    return n, owner[:grid.n]
+
+
+def search_projection_sim3(grid, Scw, fx, fy, cx, cy, log_sf, valid, world, mf_max, mf_min, normal, desc, th):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    valid, desc = _u8(valid), _u8(desc).reshape(-1, 32)
+    world, normal, mf_max, mf_min = f32(world).reshape(-1, 3), f32(normal).reshape(-1, 3), f32(mf_max), f32(mf_min)
+    S = f32(Scw).reshape(-1)[:12].copy()
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    f = lib().orc_search_projection_sim3
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(GridViewC), C.c_void_p] + [C.c_float] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    g = grid.c()
+    n = f(C.byref(g), _p(S), fx, fy, cx, cy, log_sf, len(valid), _p(valid), _p(world), _p(mf_max), _p(mf_min), _p(normal), _p(desc),
+          int(th), _p(owner))
+    return n, owner[:grid.n]

@@ -106,6 +106,16 @@ __global__ void k_win_init(int nq, const int* __restrict__ octave1, const float*
     win[q] = w;
 }
 
+// Explicit windows (the shared core of the relocalisation / loop-closing projection searches): every accepted match claims.
+__global__ void k_win_explicit(int nq, const u8* __restrict__ active, const float* __restrict__ u, const float* __restrict__ v,
+                               const float* __restrict__ r, const int* __restrict__ minL, const int* __restrict__ maxL, Win* __restrict__ win) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    Win w = {0.f, 0.f, 0.f, 0.f, 0.f, -1, -1, 0};
+    if (active[q]) { w.u = u[q]; w.v = v[q]; w.r = r[q]; w.minL = minL[q]; w.maxL = maxL[q]; w.flags = WIN_ACTIVE | WIN_CLAIMS; }
+    win[q] = w;
+}
+
 // ---- 2. candidates: Frame::GetFeaturesInArea (src/Frame.cc:445-498) + the static `continue`s of the candidate loops ------------
 __device__ __forceinline__ bool cand_pass(const DevGrid& G, const Win& w, bool checkLevels, int idx) {
     if (G.blocked && G.blocked[idx]) return false;
@@ -522,6 +532,45 @@ extern "C" int orbm_search_for_initialization(const orbm_grid_view* f2, int n1, 
     if ((rc = A.finish())) return rc;
     for (int i = 0; i < nq; i++)                                        // vbPrevMatched update, src/ORBmatcher.cc:516-519
         if (matches12[i] >= 0) { prev_xy[2 * i] = f2->x[matches12[i]]; prev_xy[2 * i + 1] = f2->y[matches12[i]]; }
+    *n_matches = cnt[0];
+    return ORB_OK;
+}
+
+extern "C" int orbm_search_windows(const orbm_grid_view* target, int nq, const uint8_t* active, const float* u, const float* v,
+                                   const float* r, const int* min_level, const int* max_level, const uint8_t* desc, const float* angle,
+                                   int th_dist, int check_orientation, int* owner, int* n_matches, int device) {
+    ORB_REQUIRE(owner && n_matches && nq >= 0 && th_dist >= 0 && th_dist <= 256, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(nq == 0 || (active && u && v && r && min_level && max_level && desc && (angle || !check_orientation)), ORB_ERR_ARG, "null query array");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_grid(target, check_orientation != 0))) return rc;
+    const int nt = target->n;
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, grid_bytes(target) + pad(nq) + 6 * pad((size_t)nq * 4) + pad((size_t)nq * 32) + work_small_bytes(nq, nt),
+                       work_scratch_bytes(nq, nt)))) return rc;
+    DevGrid G;
+    if ((rc = upload_grid(A, target, &G))) return rc;
+    G.uright = nullptr;                                                 // no stereo gate in these searches
+    const u8 *d_active, *d_desc;
+    const float *d_u, *d_v, *d_r, *d_angle = nullptr;
+    const int *d_minL, *d_maxL;
+    if ((rc = upload(A, active, (size_t)nq, &d_active))) return rc;
+    if ((rc = upload(A, u, (size_t)nq, &d_u))) return rc;
+    if ((rc = upload(A, v, (size_t)nq, &d_v))) return rc;
+    if ((rc = upload(A, r, (size_t)nq, &d_r))) return rc;
+    if ((rc = upload(A, min_level, (size_t)nq, &d_minL))) return rc;
+    if ((rc = upload(A, max_level, (size_t)nq, &d_maxL))) return rc;
+    if (check_orientation) { if ((rc = upload(A, angle, (size_t)nq, &d_angle))) return rc; }
+    if ((rc = upload(A, desc, (size_t)nq * 32, &d_desc))) return rc;
+    if ((rc = A.flush())) return rc;
+    WinWork w;
+    take_work(A, nq, nt, &w);
+    if (nq > 0) k_win_explicit<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(nq, d_active, d_u, d_v, d_r, d_minL, d_maxL, w.win);
+    if ((rc = run_search(A, G, w, d_desc, d_angle, nq, MODE_BEST, th_dist, 0.f, check_orientation))) return rc;
+    int cnt[2] = {0, 0};
+    if ((rc = A.fetch(owner, w.owner, (size_t)nt))) return rc;
+    if ((rc = A.fetch(cnt, w.out_cnt, 2))) return rc;
+    if ((rc = A.finish())) return rc;
     *n_matches = cnt[0];
     return ORB_OK;
 }

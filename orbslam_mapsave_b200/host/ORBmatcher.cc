@@ -3,6 +3,7 @@
 // Replaces src/ORBmatcher.cc:159-291, 525-658, 660-826, 1650-1666 of the reference.
 #include "ORBmatcher.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -292,6 +293,159 @@ int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Po
         vnMatches12[i] = m12[i];
         vbPrevMatched[i] = cv::Point2f(prev[2 * (size_t)i], prev[2 * (size_t)i + 1]);
     }
+    return nmatches;
+}
+
+
+// ---- relocalisation / loop-closing projection searches: the per-point projection runs here (where the MapPoint objects live),
+// the window search, Hamming distances and the serial claim order on the GPU (orbm_search_windows) --------------------------------
+namespace {
+// cv::gemm(A, x, 1, b, 1) on 3x3 / 3x1 floats: float32, left to right; transposed products and cv::norm / Mat::dot accumulate in
+// double (cv2 4.13, tests/golden/prim_gemm3.npz)
+inline void rt_apply(const float* T, const float* p, float* out) {
+    for (int r = 0; r < 3; r++) out[r] = ((T[4 * r] * p[0] + T[4 * r + 1] * p[1]) + T[4 * r + 2] * p[2]) + T[4 * r + 3];
+}
+inline void minus_rt_t(const float* T, float* out) {
+    for (int r = 0; r < 3; r++) out[r] = (float)(-(((double)T[r] * T[3] + (double)T[4 + r] * T[7]) + (double)T[8 + r] * T[11]));
+}
+inline float norm3(const float* p) { return (float)std::sqrt((double)p[0] * p[0] + (double)p[1] * p[1] + (double)p[2] * p[2]); }
+inline int clamp_level(int l, int n) { return l < 0 ? 0 : (l >= n ? n - 1 : l); }   // the fork indexes mvScaleFactors unclamped (UB)
+
+struct Windows {
+    std::vector<unsigned char> active, desc;
+    std::vector<float> u, v, r, angle;
+    std::vector<int> minL, maxL;
+    explicit Windows(int n) : active(n, 0), desc((size_t)n * 32), u(n), v(n), r(n), angle(n), minL(n, -1), maxL(n, -1) {}
+};
+}  // namespace
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th,
+                                   const int ORBdist) {
+    GridSide g;
+    snapshot_frame_grid(CurrentFrame, false, g);
+    for (int i = 0; i < CurrentFrame.N; i++) g.blocked[i] = CurrentFrame.mvpMapPoints[i] ? 1 : 0;          // ORBmatcher.cc:1548-1549
+    float T[12], Ow[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[4 * r + c] = CurrentFrame.mTcw.at<float>(r, c);
+    minus_rt_t(T, Ow);                                                                                      // :1471
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    const int n = (int)vpMPs.size(), nlev = (int)CurrentFrame.mvScaleFactors.size();
+    Windows w(n);
+    for (int i = 0; i < n; i++) {
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || sAlreadyFound.count(pMP)) continue;
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        const float X[3] = {x3Dw.at<float>(0), x3Dw.at<float>(1), x3Dw.at<float>(2)};
+        float x3Dc[3];
+        rt_apply(T, X, x3Dc);
+        const float xc = x3Dc[0], yc = x3Dc[1];
+        const float invzc = 1.0 / x3Dc[2];
+        const float u = CurrentFrame.fx * xc * invzc + CurrentFrame.cx;
+        const float v = CurrentFrame.fy * yc * invzc + CurrentFrame.cy;
+        if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+        if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+        const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+        float dist3D = norm3(PO);
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = clamp_level(pMP->PredictScale(dist3D, CurrentFrame.mfLogScaleFactor), nlev);
+        w.active[i] = 1; w.u[i] = u; w.v[i] = v;
+        w.r[i] = th * CurrentFrame.mvScaleFactors[nPredictedLevel];
+        w.minL[i] = nPredictedLevel - 1; w.maxL[i] = nPredictedLevel + 1;
+        w.angle[i] = pKF->mvKeysUn[i].angle;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&w.desc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    std::vector<int> owner(CurrentFrame.N > 0 ? CurrentFrame.N : 1, -1);
+    int nmatches = 0;
+    report(orbm_search_windows(&g.view, n, w.active.data(), w.u.data(), w.v.data(), w.r.data(), w.minL.data(), w.maxL.data(),
+                               w.desc.data(), w.angle.data(), ORBdist, mbCheckOrientation ? 1 : 0, owner.data(), &nmatches, g_device));
+    if (g_status != ORB_OK) return 0;
+    for (int j = 0; j < CurrentFrame.N; j++) {
+        if (owner[j] >= 0) CurrentFrame.mvpMapPoints[j] = vpMPs[owner[j]];
+        else if (owner[j] == -2) CurrentFrame.mvpMapPoints[j] = NULL;
+    }
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched,
+                                   int th) {
+    const float &fx = pKF->fx, &fy = pKF->fy, &cx = pKF->cx, &cy = pKF->cy;
+    // Decompose Scw (ORBmatcher.cc:301-306): scw = sqrt(row0 . row0) (Mat::dot: double), Rcw = sRcw / scw, tcw = Scw.col(3) / scw
+    const float s0 = Scw.at<float>(0, 0), s1 = Scw.at<float>(0, 1), s2 = Scw.at<float>(0, 2);
+    const float scw = (float)std::sqrt((double)s0 * s0 + (double)s1 * s1 + (double)s2 * s2);
+    const float inv = (float)(1.0 / (double)scw);
+    float T[12], Ow[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[4 * r + c] = Scw.at<float>(r, c) * inv;
+    minus_rt_t(T, Ow);
+    // the KeyFrame side: mGrid is not public, but it is Frame::AssignFeaturesToGrid of mvKeysUn (src/KeyFrame.cc:48-53), rebuilt here
+    const int n = pKF->N;
+    GridSide g;
+    g.desc.resize((size_t)n * 32);
+    g.x.resize(n); g.y.resize(n); g.angle.resize(n); g.octave.resize(n); g.blocked.assign(n, 0);
+    std::vector<std::vector<int> > grid((size_t)pKF->mnGridCols * pKF->mnGridRows);
+    for (int i = 0; i < n; i++) {
+        std::memcpy(&g.desc[(size_t)i * 32], pKF->mDescriptors.ptr(i), 32);
+        const cv::KeyPoint& kp = pKF->mvKeysUn[i];
+        g.x[i] = kp.pt.x; g.y[i] = kp.pt.y; g.angle[i] = kp.angle; g.octave[i] = kp.octave;
+        g.blocked[i] = vpMatched[i] ? 1 : 0;                                                                 // :375-376
+        const int posX = (int)round((kp.pt.x - pKF->mnMinX) * pKF->mfGridElementWidthInv);
+        const int posY = (int)round((kp.pt.y - pKF->mnMinY) * pKF->mfGridElementHeightInv);
+        if (posX < 0 || posX >= pKF->mnGridCols || posY < 0 || posY >= pKF->mnGridRows) continue;
+        grid[(size_t)posX * pKF->mnGridRows + posY].push_back(i);
+    }
+    g.off.assign(1, 0);
+    for (size_t c = 0; c < grid.size(); c++) { g.feat.insert(g.feat.end(), grid[c].begin(), grid[c].end()); g.off.push_back((int)g.feat.size()); }
+    std::memset(&g.view, 0, sizeof(g.view));
+    g.view.n = n; g.view.desc = g.desc.data(); g.view.x = g.x.data(); g.view.y = g.y.data(); g.view.octave = g.octave.data();
+    g.view.angle = g.angle.data(); g.view.blocked = g.blocked.data();
+    g.view.grid_cols = pKF->mnGridCols; g.view.grid_rows = pKF->mnGridRows;
+    g.view.min_x = (float)pKF->mnMinX; g.view.min_y = (float)pKF->mnMinY; g.view.max_x = (float)pKF->mnMaxX; g.view.max_y = (float)pKF->mnMaxY;
+    g.view.inv_w = pKF->mfGridElementWidthInv; g.view.inv_h = pKF->mfGridElementHeightInv;
+    g.view.cell_offsets = g.off.data(); g.view.cell_features = g.feat.data();
+    g.view.scale_factors = pKF->mvScaleFactors.data(); g.view.n_levels = (int)pKF->mvScaleFactors.size();
+
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+    const int np = (int)vpPoints.size(), nlev = (int)pKF->mvScaleFactors.size();
+    Windows w(np);
+    for (int iMP = 0; iMP < np; iMP++) {
+        MapPoint* pMP = vpPoints[iMP];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float X[3] = {p3Dw.at<float>(0), p3Dw.at<float>(1), p3Dw.at<float>(2)};
+        float p3Dc[3];
+        rt_apply(T, X, p3Dc);
+        if (p3Dc[2] < 0.0) continue;
+        const float invz = 1 / p3Dc[2];
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!pKF->IsInImage(u, v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+        const float dist = norm3(PO);
+        if (dist < minDistance || dist > maxDistance) continue;
+        const cv::Mat Pn = pMP->GetNormal();
+        const double dot = (double)PO[0] * Pn.at<float>(0) + (double)PO[1] * Pn.at<float>(1) + (double)PO[2] * Pn.at<float>(2);
+        if (dot < 0.5 * dist) continue;
+        const int nPredictedLevel = clamp_level(pMP->PredictScale(dist, pKF->mfLogScaleFactor), nlev);
+        w.active[iMP] = 1; w.u[iMP] = u; w.v[iMP] = v;
+        w.r[iMP] = th * pKF->mvScaleFactors[nPredictedLevel];
+        w.minL[iMP] = nPredictedLevel - 1; w.maxL[iMP] = nPredictedLevel;                                   // :380-381
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&w.desc[(size_t)iMP * 32], d.ptr(0), 32);
+    }
+    std::vector<int> owner(n > 0 ? n : 1, -1);
+    int nmatches = 0;
+    report(orbm_search_windows(&g.view, np, w.active.data(), w.u.data(), w.v.data(), w.r.data(), w.minL.data(), w.maxL.data(),
+                               w.desc.data(), NULL, TH_LOW, 0, owner.data(), &nmatches, g_device));
+    if (g_status != ORB_OK) return 0;
+    for (int j = 0; j < n; j++)
+        if (owner[j] >= 0) vpMatched[j] = vpPoints[owner[j]];
     return nmatches;
 }
 

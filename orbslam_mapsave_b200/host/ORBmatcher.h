@@ -1,11 +1,12 @@
 // ORBmatcher.h — drop-in for the hot-path members of the reference's include/ORBmatcher.h:37-101:
 // DescriptorDistance, both SearchByBoW overloads, SearchForTriangulation (+ the constants), and — first "next" row of
 // SURVEY.md §8f — the window searches SearchByProjection(Frame, MapPoints), SearchByProjection(CurrentFrame, LastFrame) and
-// SearchForInitialization.  Same signatures; bodies marshal to the C ABI of include/orb_b200.h.  The relocalisation / loop /
-// fuse / Sim3 searches of the reference class stay in the reference's own ORBmatcher.cc — see INTEGRATION.md.
+// SearchForInitialization and the two projection searches of relocalisation / loop closing.  Same signatures; bodies marshal
+// to the C ABI of include/orb_b200.h.  Fuse (x2) and SearchBySim3 stay in the reference's own ORBmatcher.cc — see INTEGRATION.md.
 #ifndef ORB_B200_ORBMATCHER_H
 #define ORB_B200_ORBMATCHER_H
 
+#include <set>
 #include <utility>
 #include <vector>
 #include "cv_compat.h"
@@ -30,6 +31,12 @@ public:
     // Project MapPoints tracked in last frame into the current frame and search matches.  Used to track from previous frame
     // (Tracking) (reference :52, src/ORBmatcher.cc:1331-1463)
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    // Project MapPoints seen in KeyFrame into the Frame and search matches.  Used in relocalisation (Tracking)
+    // (reference :56, src/ORBmatcher.cc:1465-1602)
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
+    // Project MapPoints using a Similarity Transformation and search matches.  Used in loop detection (Loop Closing)
+    // (reference :60, src/ORBmatcher.cc:293-406)
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th);
     // Matching for the Map Initialization (only used in the monocular case) (reference :69, src/ORBmatcher.cc:408-523)
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
                                 int windowSize = 10);

@@ -9,6 +9,7 @@
 #include "MapPoint.h"
 #else
 #include <map>
+#include <set>
 #include <vector>
 #include "cv_compat.h"
 
@@ -58,9 +59,17 @@ public:
     bool mbTrackInView = false;
     int mnTrackScaleLevel = 0;
     float mTrackViewCos = 0;
+    cv::Mat GetNormal() { return mNormalVector.clone(); }              // :60
+    float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }  // src/MapPoint.cc:621-631
+    float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }
+    int PredictScale(const float& currentDist, const float& logScaleFactor) {   // src/MapPoint.cc:633-642 (this fork: no clamp)
+        const float ratio = mfMaxDistance / currentDist;
+        return (int)std::ceil(std::log(ratio) / logScaleFactor);
+    }
     bool mbBad = false;
     int nObs = 0;
-    cv::Mat mDescriptor, mWorldPos;                                    // 1x32 CV_8U, 3x1 CV_32F
+    float mfMinDistance = 0, mfMaxDistance = 0;
+    cv::Mat mDescriptor, mWorldPos, mNormalVector;                     // 1x32 CV_8U, 3x1 CV_32F, 3x1 CV_32F
 };
 
 #define FRAME_GRID_ROWS 48
@@ -77,6 +86,7 @@ public:
     cv::Mat mTcw;                                                      // 4x4 CV_32F
     float fx = 0, fy = 0, cx = 0, cy = 0, mbf = 0, mb = 0;
     std::vector<float> mvScaleFactors;
+    float mfLogScaleFactor = 0;
     float mnMinX = 0, mnMaxX = 0, mnMinY = 0, mnMaxY = 0;              // static members in the reference (include/Frame.h:192-195)
     float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;       // static in the reference (:168-169)
     std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];  // :170
@@ -91,6 +101,11 @@ public:
     cv::Mat mDescriptors;
     DBoW2::FeatureVector mFeatVec;
     std::vector<float> mvScaleFactors, mvLevelSigma2;
+    float mfLogScaleFactor = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;                // include/KeyFrame.h:196-199 (ints here, floats in Frame)
+    int mnGridCols = 64, mnGridRows = 48;                              // :152-155
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    bool IsInImage(const float& x, const float& y) const { return (x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY); }
     std::vector<MapPoint*> mvpMapPoints;
     cv::Mat Ow, Rcw, tcw;                               // 3x1, 3x3, 3x1 CV_32F
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }

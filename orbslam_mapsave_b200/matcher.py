@@ -184,6 +184,23 @@ class ORBmatcher:
                                                              int(self.mbCheckOrientation), capi._p(m), C.byref(n), self.device))
         return n.value, m[:len(desc1)]
 
+    def SearchWindows(self, target, active, u, v, r, min_level, max_level, desc, angle=None, th_dist=capi.TH_HIGH):
+        """Core of SearchByProjection(Frame, KeyFrame, ...) / (KeyFrame, Scw, ...) (src/ORBmatcher.cc:1465-1602, 293-406) on
+        explicit windows.  Returns (nmatches, owner[target.N]) with -1 = untouched, -2 = culled to NULL."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        active, desc = np.ascontiguousarray(active, np.uint8), np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        u, v, r, min_level, max_level = f32(u), f32(v), f32(r), i32(min_level), i32(max_level)
+        ori = self.mbCheckOrientation and angle is not None
+        angle = f32(angle) if ori else None
+        g = target.c()
+        owner = np.zeros(max(target.n, 1), np.int32)
+        n = C.c_int()
+        capi.check(capi.lib().orbm_search_windows(C.byref(g), len(active), capi._p(active), capi._p(u), capi._p(v), capi._p(r),
+                                                  capi._p(min_level), capi._p(max_level), capi._p(desc), capi._p(angle), int(th_dist),
+                                                  int(ori), capi._p(owner), C.byref(n), self.device))
+        return n.value, owner[:target.n]
+
     @staticmethod
     def ComputeThreeMaxima(histo, device=0):
         histo = np.ascontiguousarray(histo, np.int32)

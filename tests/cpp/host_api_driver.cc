@@ -3,6 +3,7 @@
 //   driver extract <in.raw> <w> <h> <nfeat> <scale> <nlevels> <ini> <min> <out_prefix> [mask.raw]
 //   driver match   <in.bin> <out.bin>
 //   driver project <in.bin> <out.bin>
+//   driver project2 <in.bin> <out.bin>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -309,11 +310,99 @@ static int run_project(int argc, char** argv) {
     return ORBmatcher::LastStatus() == 0 ? 0 : 4;
 }
 
+// driver project2 <in.bin> <out.bin>: the relocalisation and loop-closing projection searches (Tracking::Relocalization,
+// LoopClosing::ComputeSim3).  Point states: 0 = NULL entry, 1 = good, 2 = bad, 3 = already found.
+static void fill_point(MapPoint& p, const float* world, float mfmax, float mfmin, const float* normal, const unsigned char* d) {
+    p.mWorldPos = cv::Mat(3, 1, CV_32F); p.mNormalVector = cv::Mat(3, 1, CV_32F);
+    for (int k = 0; k < 3; k++) { p.mWorldPos.at<float>(k) = world[k]; p.mNormalVector.at<float>(k) = normal[k]; }
+    p.mfMaxDistance = mfmax; p.mfMinDistance = mfmin;
+    p.mDescriptor = cv::Mat(1, 32, CV_8U); memcpy(p.mDescriptor.ptr(0), d, 32);
+}
+static int run_project2(int argc, char** argv) {
+    if (argc < 4) return 2;
+    Reader r; r.buf = slurp(argv[2]);
+    std::ofstream out(argv[3], std::ios::binary);
+    const int ori = r.get<int>();
+    ORBmatcher m(0.9f, ori != 0);
+    {   // SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist)
+        Frame* C = new Frame();
+        build_frame(r, *C);
+        std::vector<unsigned char> blocked = r.arr<unsigned char>(C->N);
+        std::vector<MapPoint> own(C->N);
+        for (int i = 0; i < C->N; i++) C->mvpMapPoints[i] = blocked[i] ? &own[i] : NULL;
+        C->mTcw = mat_from(r.arr<float>(16), 4, 4);
+        std::vector<float> K = r.arr<float>(5);
+        C->fx = K[0]; C->fy = K[1]; C->cx = K[2]; C->cy = K[3]; C->mfLogScaleFactor = K[4];
+        const float th = r.get<float>();
+        const int orbdist = r.get<int>(), n = r.get<int>();
+        std::vector<unsigned char> state = r.arr<unsigned char>(n), d = r.arr<unsigned char>((size_t)n * 32);
+        std::vector<float> world = r.arr<float>((size_t)n * 3), normal = r.arr<float>((size_t)n * 3), mfmax = r.arr<float>(n), mfmin = r.arr<float>(n), ang = r.arr<float>(n);
+        KeyFrame kf; kf.N = n; kf.mvKeysUn.resize(n); kf.mvpMapPoints.assign(n, (MapPoint*)NULL);
+        std::vector<MapPoint> pool(n);
+        std::set<MapPoint*> found;
+        for (int i = 0; i < n; i++) {
+            kf.mvKeysUn[i] = cv::KeyPoint(0, 0, 31, ang[i], 10, 0);
+            fill_point(pool[i], &world[3 * (size_t)i], mfmax[i], mfmin[i], &normal[3 * (size_t)i], &d[(size_t)i * 32]);
+            pool[i].mbBad = state[i] == 2;
+            if (state[i]) kf.mvpMapPoints[i] = &pool[i];
+            if (state[i] == 3) found.insert(&pool[i]);
+        }
+        const int nm = m.SearchByProjection(*C, &kf, found, th, orbdist);
+        put(out, &nm, 1);
+        std::vector<int> owner(C->N, -1);
+        for (int j = 0; j < C->N; j++) {
+            MapPoint* p = C->mvpMapPoints[j];
+            if (p && n && p >= &pool[0] && p <= &pool[n - 1]) owner[j] = (int)(p - &pool[0]);
+        }
+        put(out, owner.data(), owner.size());
+        delete C;
+    }
+    {   // SearchByProjection(pKF, Scw, vpPoints, vpMatched, th)
+        Frame* F = new Frame();
+        build_frame(r, *F);
+        KeyFrame kf;
+        kf.N = F->N; kf.mDescriptors = F->mDescriptors; kf.mvKeysUn = F->mvKeysUn; kf.mvScaleFactors = F->mvScaleFactors;
+        kf.mnMinX = (int)F->mnMinX; kf.mnMinY = (int)F->mnMinY; kf.mnMaxX = (int)F->mnMaxX; kf.mnMaxY = (int)F->mnMaxY;
+        kf.mfGridElementWidthInv = F->mfGridElementWidthInv; kf.mfGridElementHeightInv = F->mfGridElementHeightInv;
+        std::vector<unsigned char> blocked = r.arr<unsigned char>(kf.N);
+        cv::Mat Scw = mat_from(r.arr<float>(16), 4, 4);
+        std::vector<float> K = r.arr<float>(5);
+        kf.fx = K[0]; kf.fy = K[1]; kf.cx = K[2]; kf.cy = K[3]; kf.mfLogScaleFactor = K[4];
+        const int th = r.get<int>(), n = r.get<int>();
+        std::vector<unsigned char> state = r.arr<unsigned char>(n), d = r.arr<unsigned char>((size_t)n * 32);
+        std::vector<float> world = r.arr<float>((size_t)n * 3), normal = r.arr<float>((size_t)n * 3), mfmax = r.arr<float>(n), mfmin = r.arr<float>(n);
+        std::vector<MapPoint> pool(n), dummy(kf.N);
+        std::vector<MapPoint*> vpPoints(n), vpMatched(kf.N, (MapPoint*)NULL);
+        std::vector<int> foundIdx;
+        for (int i = 0; i < n; i++) {
+            fill_point(pool[i], &world[3 * (size_t)i], mfmax[i], mfmin[i], &normal[3 * (size_t)i], &d[(size_t)i * 32]);
+            pool[i].mbBad = state[i] == 2 || state[i] == 0;             // vpPoints holds no NULLs in the reference; 0 -> bad here
+            vpPoints[i] = &pool[i];
+            if (state[i] == 3) foundIdx.push_back(i);
+        }
+        size_t k = 0;
+        for (int j = 0; j < kf.N; j++)
+            if (blocked[j]) { vpMatched[j] = k < foundIdx.size() ? &pool[foundIdx[k]] : &dummy[j]; k++; }
+        if (k < foundIdx.size()) return 6;                               // the generator guarantees enough blocked features
+        const int nm = m.SearchByProjection(&kf, Scw, vpPoints, vpMatched, th);
+        put(out, &nm, 1);
+        std::vector<int> owner(kf.N, -1);
+        for (int j = 0; j < kf.N; j++) {
+            MapPoint* p = vpMatched[j];
+            if (!blocked[j] && p && n && p >= &pool[0] && p <= &pool[n - 1]) owner[j] = (int)(p - &pool[0]);
+        }
+        put(out, owner.data(), owner.size());
+        delete F;
+    }
+    return ORBmatcher::LastStatus() == 0 ? 0 : 4;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     if (!strcmp(argv[1], "bow")) return run_bow(argc, argv);
     if (!strcmp(argv[1], "extract")) return run_extract(argc, argv);
     if (!strcmp(argv[1], "match")) return run_match(argc, argv);
     if (!strcmp(argv[1], "project")) return run_project(argc, argv);
+    if (!strcmp(argv[1], "project2")) return run_project2(argc, argv);
     return 2;
 }

@@ -115,3 +115,39 @@ def init_frame1_for(fa2, n1, rng, shift=(4.0, -3.0)):
     angle1 = ((fa2["angle"][tgt] + rng.choice([0.0, 0.0, 0.0, 90.0], n1) + rng.normal(0, 3, n1)) % 360).astype(np.float32)
     prev = np.ascontiguousarray(np.stack([x1, y1], 1), np.float32)
     return dict(desc1=desc1, octave1=octave1, angle1=angle1, prev=prev)
+
+
+def kf_points_for(fa, n_pts, rng, fx=520.0, fy=520.0, cx=320.0, cy=240.0, sim_scale=1.0):
+    """Map points seen from a pose (Tcw, optionally a similarity s*[R|t]) that project near features of `fa`, with the
+    scale-invariance distances MapPoint::UpdateNormalAndDepth would give them (so PredictScale lands near the feature's octave)."""
+    n = len(fa["x"])
+    R = rot_small(rng, 3.0).astype(np.float32)
+    t = np.array([rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1), rng.uniform(-0.1, 0.1)], np.float32)
+    T = np.concatenate([R, t[:, None]], 1).astype(np.float32)
+    S = (T * np.float32(sim_scale)).astype(np.float32)
+    Tn = (S.astype(np.float64) / np.sqrt((S[0, :3].astype(np.float64) ** 2).sum()))           # what the search decomposes back
+    tgt = rng.integers(0, n, n_pts)
+    dup = rng.random(n_pts) < 0.3
+    tgt[dup] = tgt[rng.integers(0, n_pts, dup.sum())]
+    z = rng.uniform(1.0, 8.0, n_pts)
+    u = fa["x"][tgt].astype(np.float64) + rng.normal(0, 2.0, n_pts)
+    v = fa["y"][tgt].astype(np.float64) + rng.normal(0, 2.0, n_pts)
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    pc[rng.random(n_pts) < 0.03, 2] *= -1
+    world = ((pc - Tn[:, 3]) @ Tn[:, :3]).astype(np.float32)
+    Ow = -Tn[:, :3].T @ Tn[:, 3]
+    PO = world.astype(np.float64) - Ow
+    dist = np.linalg.norm(PO, axis=1)
+    lvl = np.clip(fa["octave"][tgt] + rng.integers(-1, 2, n_pts), 0, 7)
+    mf_max = (dist * SCALE[lvl].astype(np.float64) * rng.uniform(0.85, 1.0, n_pts)).astype(np.float32)
+    far = rng.random(n_pts) < 0.05
+    mf_max[far] *= np.float32(0.3)                                     # outside the scale-invariance range
+    mf_min = (mf_max / SCALE[7]).astype(np.float32)
+    normal = PO / dist[:, None]
+    side = rng.random(n_pts) < 0.1
+    normal[side] = np.roll(normal[side], 1, axis=1) * np.array([1, -1, 1])            # oblique views (viewing-angle test)
+    desc = np.stack([flip(fa["desc"][tt], int(rng.choice([0, 3, 10, 30, 49, 50, 51, 95, 100, 101, 128])), rng) for tt in tgt])
+    angle = ((fa["angle"][tgt] + rng.choice([0.0, 0.0, 0.0, 45.0, 200.0], n_pts) + rng.normal(0, 3, n_pts)) % 360).astype(np.float32)
+    state = rng.choice(np.array([0, 1, 1, 1, 1, 1, 2, 3], np.uint8), n_pts)       # 0 none, 1 good, 2 bad, 3 already found
+    return dict(T=T, S=S, fx=fx, fy=fy, cx=cx, cy=cy, world=world, mf_max=mf_max, mf_min=mf_min, normal=normal.astype(np.float32),
+                desc=desc, angle=angle, state=state)

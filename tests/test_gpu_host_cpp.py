@@ -249,3 +249,54 @@ def test_cpp_window_searches_match_oracle(tmp_path, seed, mono, ori):
     oprev = f1["prev"].copy()
     on, om = orc.search_initialization(ogC, f1["desc1"], f1["octave1"], f1["angle1"], oprev, 100, ratio, ori)
     assert nm == on and sz == 1600 and np.array_equal(got, om) and np.array_equal(gprev, oprev) and on > 50
+
+
+@pytest.mark.parametrize("seed,ori,scale", [(0, 1, 1.0), (1, 0, 2.5)])
+def test_cpp_relocalisation_and_loop_projection_match_oracle(tmp_path, seed, ori, scale):
+    """SearchByProjection(CurrentFrame, KeyFrame, sAlreadyFound, th, ORBdist) and SearchByProjection(KeyFrame, Scw, vpPoints,
+    vpMatched, th) through the C++ class (projection on the host, window search on the GPU) against the oracle."""
+    import proj_util as pu
+    rng = np.random.default_rng(200 + seed)
+    n, npts = 1500, 1800
+    log_sf = float(np.log(np.float32(1.2)))
+
+    def frame_blob(fa):
+        ur = np.full(len(fa["x"]), -1, np.float32)
+        return (struct.pack("<i", len(fa["x"])) + fa["desc"].tobytes() + fa["x"].tobytes() + fa["y"].tobytes() + fa["angle"].tobytes() +
+                ur.tobytes() + fa["octave"].tobytes() + np.array(fa["bounds"], np.float32).tobytes() + struct.pack("<i", 8) + pu.SCALE.tobytes())
+
+    T4 = lambda T: np.concatenate([T, np.array([[0, 0, 0, 1]], np.float32)], 0).astype(np.float32)
+    blob = struct.pack("<i", ori)
+    # relocalisation
+    faD = pu.frame_arrays(n, rng, stereo=False, cluster=seed == 1)
+    blockedD = (rng.random(n) < 0.2).astype(np.uint8)
+    kp = pu.kf_points_for(faD, npts, rng)
+    thD, orbdist = 10.0, 100 if seed == 0 else 64
+    K = np.array([kp["fx"], kp["fy"], kp["cx"], kp["cy"], log_sf], np.float32)
+    blob += frame_blob(faD) + blockedD.tobytes() + T4(kp["T"]).tobytes() + K.tobytes() + struct.pack("<fii", thD, orbdist, npts)
+    blob += kp["state"].tobytes() + kp["desc"].tobytes() + kp["world"].tobytes() + kp["normal"].tobytes() + kp["mf_max"].tobytes() + kp["mf_min"].tobytes() + kp["angle"].tobytes()
+    # loop closing
+    faE = pu.frame_arrays(n, rng, stereo=False)
+    faE["x"] = np.clip(faE["x"], 0, 639.5).astype(np.float32)
+    blockedE = (rng.random(n) < 0.3).astype(np.uint8)
+    kq = pu.kf_points_for(faE, npts, rng, sim_scale=scale)
+    thE = 10
+    blob += frame_blob(faE) + blockedE.tobytes() + T4(kq["S"]).tobytes() + K.tobytes() + struct.pack("<ii", thE, npts)
+    blob += kq["state"].tobytes() + kq["desc"].tobytes() + kq["world"].tobytes() + kq["normal"].tobytes() + kq["mf_max"].tobytes() + kq["mf_min"].tobytes()
+    (tmp_path / "in.bin").write_bytes(blob)
+    subprocess.check_call([_driver(), "project2", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = (tmp_path / "out.bin").read_bytes()
+    pos = 0
+    (nm,) = struct.unpack_from("<i", out, pos); pos += 4
+    got = np.frombuffer(out, np.int32, n, pos); pos += 4 * n
+    og = orc.Grid(faD["desc"], faD["x"], faD["y"], faD["octave"], pu.SCALE, faD["bounds"], angle=faD["angle"], blocked=blockedD)
+    on, oo = orc.search_projection_kf(og, kp["T"], kp["fx"], kp["fy"], kp["cx"], kp["cy"], np.float32(log_sf), kp["state"] == 1, kp["world"],
+                                      kp["mf_max"], kp["mf_min"], kp["angle"], kp["desc"], thD, orbdist, ori)
+    want = np.where(oo == -2, -1, oo)            # a culled entry held nothing before: NULL again
+    assert nm == on and np.array_equal(got, want) and (oo >= 0).sum() > 100
+    (nm,) = struct.unpack_from("<i", out, pos); pos += 4
+    got = np.frombuffer(out, np.int32, n, pos); pos += 4 * n
+    og = orc.Grid(faE["desc"], faE["x"], faE["y"], faE["octave"], pu.SCALE, faE["bounds"], angle=faE["angle"], blocked=blockedE)
+    on, oo = orc.search_projection_sim3(og, kq["S"], kq["fx"], kq["fy"], kq["cx"], kq["cy"], np.float32(log_sf), kq["state"] == 1, kq["world"],
+                                        kq["mf_max"], kq["mf_min"], kq["normal"], kq["desc"], thE)
+    assert nm == on and np.array_equal(got, oo) and on > 100

@@ -90,3 +90,31 @@ def test_window_search_rejects_bad_arguments():
     mp["in_view"][:] = 1
     with pytest.raises(orb.OrbError):
         orb.ORBmatcher().SearchByProjectionMapPoints(g, **mp)
+
+
+@pytest.mark.parametrize("n,nq,seed,cluster,ori,th", [(2000, 2500, 60, False, True, 100), (2000, 2500, 61, True, True, 100),
+                                                      (3000, 1500, 62, True, False, 50), (400, 0, 63, False, True, 50)])
+def test_search_windows_core(n, nq, seed, cluster, ori, th):
+    """orbm_search_windows: explicit windows, best candidate, every accepted match blocks (the core of the relocalisation and
+    loop-closing SearchByProjection overloads)."""
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n, rng, stereo=False, cluster=cluster)
+    blocked = (rng.random(n) < 0.2).astype(np.uint8)
+    g, og = pu.make_grids(fa, blocked, orb, orc)
+    tgt = rng.integers(0, n, nq)
+    dup = rng.random(nq) < 0.4
+    if nq:
+        tgt[dup] = tgt[rng.integers(0, nq, dup.sum())]
+    desc = np.stack([pu.flip(fa["desc"][t], int(rng.choice([0, 5, 30, 49, 50, 51, 99, 100, 101])), rng) for t in tgt]) if nq else np.zeros((0, 32), np.uint8)
+    u = (fa["x"][tgt] + rng.normal(0, 2, nq)).astype(np.float32)
+    v = (fa["y"][tgt] + rng.normal(0, 2, nq)).astype(np.float32)
+    lvl = fa["octave"][tgt] + rng.integers(-1, 2, nq)
+    r = (rng.choice([7.0, 15.0, 40.0], nq) * np.float32(1.2) ** np.clip(lvl, 0, 7)).astype(np.float32)
+    active = (rng.random(nq) < 0.9).astype(np.uint8)
+    angle = ((fa["angle"][tgt] + rng.choice([0.0, 0.0, 120.0], nq)) % 360).astype(np.float32)
+    args = (active, u, v, r, lvl - 1, lvl + rng.integers(0, 2, nq), desc)
+    want_n, want = orc.search_windows(og, *args, angle, th, ori)
+    got_n, got = orb.ORBmatcher(0.9, ori).SearchWindows(g, *args, angle=angle, th_dist=th)
+    assert got_n == want_n and np.array_equal(got, want)
+    if nq:
+        assert (want >= 0).sum() > 200
