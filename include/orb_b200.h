@@ -112,6 +112,17 @@ int orbx_run_stages_device(orbx_extractor* ex, const uint8_t* d_images, int n_fr
                            orbx_keypoint* d_kp_out, uint8_t* d_desc_out, int cap, int* d_n_out, int stage_mask,
                            void* stream);
 
+/* Replaces void Frame::ComputeStereoMatches() (src/Frame.cc:584-756), the only reader of mvImagePyramid: row-band
+ * candidates among the right keypoints, descriptor distance < TH_HIGH, 11x11 SAD over shifts -5..+5 on the pyramid level of
+ * the left keypoint, parabola fit, disparity / depth, and the final cut at 1.5*1.4*median SAD.  The pyramids are the
+ * device-resident ones of the LAST pass of the two handles (frame_left / frame_right inside those passes), so a stereo
+ * front-end never downloads them.  kp_left / kp_right: mvKeys / mvKeysRight; u_right / depth: mvuRight / mvDepth (n_left each,
+ * -1 where no match).  Host pointers; blocks until done. */
+int orbx_stereo_matches(orbx_extractor* left, orbx_extractor* right, int frame_left, int frame_right,
+                        const orbx_keypoint* kp_left, const uint8_t* desc_left, int n_left,
+                        const orbx_keypoint* kp_right, const uint8_t* desc_right, int n_right,
+                        float mbf, float mb, float* u_right, float* depth);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * ORBmatcher
  * ---------------------------------------------------------------------------------------------------------------- */

@@ -1392,4 +1392,109 @@ int orc_search_projection_sim3(const orc_grid_view* Kp, const float* Scw, float 
     return orc_search_windows(Kp, n_pts, active.data(), u.data(), v.data(), rad.data(), minL.data(), maxL.data(), desc, nullptr, TH_LOW, 0, owner);
 }
 
+
+// ---- Frame::ComputeStereoMatches, src/Frame.cc:584-756 -------------------------------------------------------------
+// pyrL / pyrR: the border-less levels of the two extractors' mvImagePyramid (contiguous, stride = w[l]).  kpL = mvKeys, kpR =
+// mvKeysRight.  Out: mvuRight, mvDepth (n_left each).  Two undefined behaviours of the reference are given a definition here
+// (and identically in the product): rows outside [0, nRows) are not entered in the row table (:604-612 would write out of
+// bounds), and an empty vDistIdx skips the median cut (:738-739 would read element 0 of an empty vector).
+void orc_stereo_matches(int nlevels, const u8* const* pyrL, const u8* const* pyrR, const int* w, const int* h,
+                        const float* scaleFactors, const float* invScaleFactors,
+                        const orc_kp* kpL, const u8* descL, int N, const orc_kp* kpR, const u8* descR, int Nr,
+                        float mbf, float mb, float* mvuRight, float* mvDepth) {
+    (void)nlevels;
+    for (int i = 0; i < N; i++) { mvuRight[i] = -1.0f; mvDepth[i] = -1.0f; }
+    const int nRows = h[0];
+    std::vector<std::vector<size_t> > vRowIndices(nRows, std::vector<size_t>());
+    for (int iR = 0; iR < Nr; iR++) {
+        const float kpY = kpR[iR].y;
+        const float r = 2.0f * scaleFactors[kpR[iR].octave];
+        const int maxr = (int)std::ceil(kpY + r);
+        const int minr = (int)std::floor(kpY - r);
+        for (int yi = minr; yi <= maxr; yi++)
+            if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);
+    }
+    const float minZ = mb;
+    const float minD = -3;
+    const float maxD = mbf / minZ;
+    std::vector<std::pair<int, int> > vDistIdx;
+    for (int iL = 0; iL < N; iL++) {
+        const orc_kp& kpL_ = kpL[iL];
+        const int levelL = kpL_.octave;
+        const float vL = kpL_.y, uL = kpL_.x;
+        if (!(vL >= 0 && (size_t)vL < (size_t)nRows)) continue;
+        const std::vector<size_t>& vCandidates = vRowIndices[(size_t)vL];
+        if (vCandidates.empty()) continue;
+        const float minU = uL - maxD;
+        const float maxU = uL - minD;
+        if (maxU < 0) continue;
+        int bestDist = TH_HIGH;
+        size_t bestIdxR = 0;
+        const u8* dL = descL + (size_t)iL * 32;
+        for (size_t iC = 0; iC < vCandidates.size(); iC++) {
+            const size_t iR = vCandidates[iC];
+            if (kpR[iR].octave < levelL - 1 || kpR[iR].octave > levelL + 1) continue;
+            const float uR = kpR[iR].x;
+            if (uR >= minU && uR <= maxU) {
+                const int dist = descriptor_distance(dL, descR + iR * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+            }
+        }
+        if (bestDist < TH_HIGH) {
+            const float uR0 = kpR[bestIdxR].x;
+            const float scaleFactor = invScaleFactors[levelL];
+            const float scaleduL = std::round(kpL_.x * scaleFactor);
+            const float scaledvL = std::round(kpL_.y * scaleFactor);
+            const float scaleduR0 = std::round(uR0 * scaleFactor);
+            const int wd = 5;
+            const u8* IL = pyrL[levelL];
+            const u8* IRimg = pyrR[levelL];
+            const int cols = w[levelL];
+            const int r0 = (int)(scaledvL - wd), c0 = (int)(scaleduL - wd);
+            const float ILc = (float)IL[(size_t)(r0 + wd) * cols + c0 + wd];
+            int bestDistS = INT_MAX, bestincR = 0;
+            const int L = 5;
+            float vDists[2 * 5 + 1];
+            const float iniu = scaleduR0 + L - wd;
+            const float endu = scaleduR0 + L + wd + 1;
+            if (iniu < 0 || endu >= cols) continue;
+            // (third definition of reference UB / cv::Mat range assertions: windows leaving the level image are skipped)
+            if (r0 < 0 || r0 + 2 * wd + 1 > h[levelL] || c0 < 0 || c0 + 2 * wd + 1 > cols || (int)scaleduR0 - L - wd < 0) continue;
+            for (int incR = -L; incR <= +L; incR++) {
+                const int cr = (int)(scaleduR0 + incR - wd);
+                const float IRc = (float)IRimg[(size_t)(r0 + wd) * cols + cr + wd];
+                float dist = 0;                                     // cv::norm(IL, IR, NORM_L1): integer-valued terms, exact in float
+                for (int y = 0; y < 2 * wd + 1; y++)
+                    for (int x = 0; x < 2 * wd + 1; x++)
+                        dist += std::fabs(((float)IL[(size_t)(r0 + y) * cols + c0 + x] - ILc) - ((float)IRimg[(size_t)(r0 + y) * cols + cr + x] - IRc));
+                if (dist < bestDistS) { bestDistS = dist; bestincR = incR; }
+                vDists[L + incR] = dist;
+            }
+            if (bestincR == -L || bestincR == L) continue;
+            const float dist1 = vDists[L + bestincR - 1];
+            const float dist2 = vDists[L + bestincR];
+            const float dist3 = vDists[L + bestincR + 1];
+            const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+            if (deltaR < -1 || deltaR > 1) continue;
+            float bestuR = scaleFactors[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+            float disparity = (uL - bestuR);
+            if (disparity >= 0 && disparity < maxD) {
+                if (disparity <= 0) { disparity = 0.01; bestuR = uL - 0.01; }
+                mvDepth[iL] = mbf / disparity;
+                mvuRight[iL] = bestuR;
+                vDistIdx.push_back(std::pair<int, int>(bestDistS, iL));
+            }
+        }
+    }
+    if (vDistIdx.empty()) return;
+    std::sort(vDistIdx.begin(), vDistIdx.end());
+    const float median = vDistIdx[vDistIdx.size() / 2].first;
+    const float thDist = 1.5f * 1.4f * median;
+    for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+        if (vDistIdx[i].first < thDist) break;
+        mvuRight[vDistIdx[i].second] = -1;
+        mvDepth[vDistIdx[i].second] = -1;
+    }
+}
+
 }  // extern "C"

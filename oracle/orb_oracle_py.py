@@ -481,3 +481,27 @@ def search_projection_sim3(grid, Scw, fx, fy, cx, cy, log_sf, valid, world, mf_m
     n = f(C.byref(g), _p(S), fx, fy, cx, cy, log_sf, len(valid), _p(valid), _p(world), _p(mf_max), _p(mf_min), _p(normal), _p(desc),
           int(th), _p(owner))
     return n, owner[:grid.n]
+
+
+def stereo_matches(levels_left, levels_right, scale_factors, inv_scale_factors, kp_left, desc_left, kp_right, desc_right, mbf, mb):
+    """Frame::ComputeStereoMatches restatement; levels_*: lists of border-less pyramid levels (uint8 arrays)."""
+    nl = len(levels_left)
+    L = [np.ascontiguousarray(a, np.uint8) for a in levels_left]
+    R = [np.ascontiguousarray(a, np.uint8) for a in levels_right]
+    assert all(a.shape == b.shape for a, b in zip(L, R))
+    pl = (C.c_void_p * nl)(*[a.ctypes.data for a in L])
+    pr = (C.c_void_p * nl)(*[a.ctypes.data for a in R])
+    w = np.array([a.shape[1] for a in L], np.int32)
+    h = np.array([a.shape[0] for a in L], np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    isf = np.ascontiguousarray(inv_scale_factors, np.float32)
+    kl, kr = np.ascontiguousarray(kp_left, KP_DTYPE), np.ascontiguousarray(kp_right, KP_DTYPE)
+    dl, dr = _u8(desc_left).reshape(-1, 32), _u8(desc_right).reshape(-1, 32)
+    u = np.zeros(max(len(kl), 1), np.float32)
+    d = np.zeros(max(len(kl), 1), np.float32)
+    f = lib().orc_stereo_matches
+    f.restype = None
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    f(nl, pl, pr, _p(w), _p(h), _p(sf), _p(isf), _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), float(mbf), float(mb), _p(u), _p(d))
+    return u[:len(kl)], d[:len(kl)]

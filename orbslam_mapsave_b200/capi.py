@@ -25,7 +25,7 @@ SYMBOLS = [
     "orb_last_error", "orb_device_count",
     "orbx_create", "orbx_destroy", "orbx_tables", "orbx_level_size", "orbx_max_keypoints", "orbx_extract",
     "orbx_extract_batch", "orbx_extract_batch_device", "orbx_check_status", "orbx_get_pyramid_level", "orbx_get_pyramid",
-    "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device",
+    "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device", "orbx_stereo_matches",
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
     "orbm_popc_peak", "orbm_distinctive_descriptors",
@@ -104,6 +104,8 @@ def lib():
     L.orbx_launch_count.argtypes = [vp]
     L.orbx_run_stages_device.restype = i32
     L.orbx_run_stages_device.argtypes = [vp, vp, i32, vp, vp, vp, i32, vp, i32, vp]
+    L.orbx_stereo_matches.restype = i32
+    L.orbx_stereo_matches.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp, i32, f32, f32, vp, vp]
     L.orbm_descriptor_distance.restype = i32
     L.orbm_descriptor_distance.argtypes = [vp, vp, i32, vp, i32]
     L.orbm_hamming_top2.restype = i32

@@ -1787,3 +1787,215 @@ extern "C" int orbx_get_candidates(orbx_extractor* ex, int frame, int level, orb
     for (int i = 0; i < n && i < cap; i++) { out[i].x = k[i].x & 0xFFFF; out[i].y = k[i].x >> 16; out[i].response = k[i].y >> 24; }
     return ORB_OK;
 }
+
+// =====================================================================================================
+// Frame::ComputeStereoMatches (src/Frame.cc:584-756) on the device-resident pyramids of two extractor handles —
+// the only consumer of the public mvImagePyramid, so a stereo front-end no longer downloads the pyramids at all.
+// One warp per left keypoint, no cross-keypoint dependency until the final median cut:
+//   1. candidates = right keypoints whose row band [floor(y-r), ceil(y+r)], r = 2*scale[octave], holds row int(vL) (:599-612;
+//      the reference's row table lists them in ascending index, so the packed (distance, index) minimum is its "first wins"),
+//      octave within +-1, uR in [uL - mbf/mb, uL + 3]; best descriptor distance < TH_HIGH (:644-668);
+//   2. 11x11 SAD of the centre-subtracted patches at the keypoint's pyramid level for the 11 shifts -5..+5 (:680-715): integer
+//      arithmetic (the reference's float L1 norm of integer-valued differences is exact);
+//   3. parabola fit, disparity test, depth (:717-747), float32 with explicit _rn operations;
+//   4. k_stereo_median: median of the accepted SADs (rank size/2) by a 17-step counting search, cut at 1.5f*1.4f*median (:750-765).
+struct StereoParams {
+    const u8* pyrL; const u8* pyrR;
+    const orbx_keypoint* kpL; const orbx_keypoint* kpR; const u8* descL; const u8* descR;
+    int nL, nR, nRows;
+    float mbf, maxD;
+    float sf[ORBX_MAX_LEVELS], isf[ORBX_MAX_LEVELS];
+};
+#define ST_WARPS 8
+__global__ void __launch_bounds__(32 * ST_WARPS) k_stereo_prepare(StereoParams S, int4* __restrict__ rinfo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.nR) return;
+    const orbx_keypoint k = S.kpR[i];
+    const float r = __fmul_rn(2.0f, S.sf[k.octave]);
+    int4 v;
+    v.x = max((int)floorf(__fsub_rn(k.y, r)), 0);                    // rows outside [0, nRows) are not entered in the table
+    v.y = min((int)ceilf(__fadd_rn(k.y, r)), S.nRows - 1);
+    v.z = k.octave;
+    v.w = __float_as_int(k.x);
+    rinfo[i] = v;
+}
+
+__global__ void __launch_bounds__(32 * ST_WARPS) k_stereo(const __grid_constant__ Plan P, StereoParams S, const int4* __restrict__ rinfo,
+                                                          float* __restrict__ uRight, float* __restrict__ depth, int* __restrict__ sad) {
+    const int lane = threadIdx.x & 31, iL = blockIdx.x * ST_WARPS + (threadIdx.x >> 5);
+    if (iL >= S.nL) return;
+    const orbx_keypoint kL = S.kpL[iL];
+    const int levelL = kL.octave;
+    const float uL = kL.x, vL = kL.y;
+    float outU = -1.0f, outD = -1.0f;
+    int outS = -1;
+    const float minU = __fsub_rn(uL, S.maxD), maxU = __fsub_rn(uL, -3.0f);
+    const bool rowOk = vL >= 0 && (int)vL < S.nRows;
+    if (rowOk && !(maxU < 0)) {
+        const int row = (int)vL;
+        u32 dl[8];
+        {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(S.descL + (size_t)iL * 32)), hi = __ldg(reinterpret_cast<const uint4*>(S.descL + (size_t)iL * 32) + 1);
+            dl[0] = lo.x; dl[1] = lo.y; dl[2] = lo.z; dl[3] = lo.w; dl[4] = hi.x; dl[5] = hi.y; dl[6] = hi.z; dl[7] = hi.w;
+        }
+        u32 best = ((u32)100 << 22);                                  // TH_HIGH, strict '<' (:646, 661)
+        for (int j = lane; j < S.nR; j += 32) {
+            const int4 ri = __ldg(&rinfo[j]);
+            if (row < ri.x || row > ri.y) continue;
+            if (ri.z < levelL - 1 || ri.z > levelL + 1) continue;
+            const float uR = __int_as_float(ri.w);
+            if (!(uR >= minU && uR <= maxU)) continue;
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(S.descR + (size_t)j * 32)), hi = __ldg(reinterpret_cast<const uint4*>(S.descR + (size_t)j * 32) + 1);
+            const int d = __popc(dl[0] ^ lo.x) + __popc(dl[1] ^ lo.y) + __popc(dl[2] ^ lo.z) + __popc(dl[3] ^ lo.w) +
+                          __popc(dl[4] ^ hi.x) + __popc(dl[5] ^ hi.y) + __popc(dl[6] ^ hi.z) + __popc(dl[7] ^ hi.w);
+            best = min(best, ((u32)d << 22) | (u32)j);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if ((best >> 22) < 100u) {
+            const int bestIdxR = (int)(best & 0x3FFFFFu);
+            const float uR0 = S.kpR[bestIdxR].x;
+            const float scaleFactor = S.isf[levelL];
+            const float scaleduL = roundf(__fmul_rn(kL.x, scaleFactor));
+            const float scaledvL = roundf(__fmul_rn(kL.y, scaleFactor));
+            const float scaleduR0 = roundf(__fmul_rn(uR0, scaleFactor));
+            const LevelPlan& Lp = P.lv[levelL];
+            const float iniu = __fadd_rn(scaleduR0, 0.0f), endu = __fadd_rn(scaleduR0, 11.0f);      // +L-w, +L+w+1
+            // the reference only tests the right window (:697-699); windows that leave the level image (impossible for the
+            // extractor's own keypoints, which stay 19 level-pixels away from the border) are skipped instead of being read
+            const int r0 = (int)scaledvL - 5, c0 = (int)scaleduL - 5, cr0 = (int)scaleduR0 - 10;
+            const bool inside = r0 >= 0 && r0 + 11 <= Lp.h && c0 >= 0 && c0 + 11 <= Lp.w;
+            if (!(iniu < 0 || endu >= (float)Lp.w) && inside && cr0 >= 0) {
+                const u8* bl = S.pyrL + Lp.off + (size_t)ORBX_OY * Lp.pitch + ORBX_OX;
+                const u8* br = S.pyrR + Lp.off + (size_t)ORBX_OY * Lp.pitch + ORBX_OX;
+                const int ILc = bl[(size_t)(r0 + 5) * Lp.pitch + c0 + 5];
+                int acc[11];
+#pragma unroll
+                for (int k = 0; k < 11; k++) acc[k] = 0;
+                for (int p = lane; p < 121; p += 32) {
+                    const int y = p / 11, x = p - y * 11;
+                    const int a = (int)bl[(size_t)(r0 + y) * Lp.pitch + c0 + x] - ILc;
+                    const u8* rr = br + (size_t)(r0 + y) * Lp.pitch + cr0 + x;
+                    const u8* rc = br + (size_t)(r0 + 5) * Lp.pitch + cr0 + 5;
+#pragma unroll
+                    for (int k = 0; k < 11; k++) acc[k] += abs(a - ((int)rr[k] - (int)rc[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < 11; k++)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                int bestS = 0x7fffffff, bestinc = 0;
+#pragma unroll
+                for (int k = 0; k < 11; k++)
+                    if (acc[k] < bestS) { bestS = acc[k]; bestinc = k - 5; }
+                if (bestinc != -5 && bestinc != 5) {
+                    float dist1 = 0.f, dist2 = 0.f, dist3 = 0.f;
+#pragma unroll
+                    for (int k = 1; k < 10; k++)
+                        if (k - 5 == bestinc) { dist1 = (float)acc[k - 1]; dist2 = (float)acc[k]; dist3 = (float)acc[k + 1]; }
+                    const float den = __fmul_rn(2.0f, __fsub_rn(__fadd_rn(dist1, dist3), __fmul_rn(2.0f, dist2)));
+                    const float deltaR = __fdiv_rn(__fsub_rn(dist1, dist3), den);
+                    if (!(deltaR < -1 || deltaR > 1)) {
+                        float bestuR = __fmul_rn(S.sf[levelL], __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+                        float disparity = __fsub_rn(uL, bestuR);
+                        if (disparity >= 0 && disparity < S.maxD) {
+                            if (disparity <= 0) { disparity = 0.01f; bestuR = (float)((double)uL - 0.01); }
+                            outD = __fdiv_rn(S.mbf, disparity);
+                            outU = bestuR;
+                            outS = bestS;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { uRight[iL] = outU; depth[iL] = outD; sad[iL] = outS; }
+}
+
+__global__ void __launch_bounds__(1024) k_stereo_median(int n, const int* __restrict__ sad, float* __restrict__ uRight, float* __restrict__ depth) {
+    __shared__ int s_cnt, s_valid;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_valid = 0;
+    __syncthreads();
+    int c = 0;
+    for (int i = tid; i < n; i += blockDim.x) c += sad[i] >= 0;
+    if (c) atomicAdd(&s_valid, c);
+    __syncthreads();
+    const int nv = s_valid;
+    if (nv == 0) return;
+    const int rank = nv / 2;                                         // vDistIdx[size/2] of the ascending sort
+    int lo = 0, hi = 1 << 17;                                        // smallest v with #{sad <= v} >= rank + 1  (SAD <= 121*510)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        __syncthreads();
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        c = 0;
+        for (int i = tid; i < n; i += blockDim.x) { const int v = sad[i]; c += (v >= 0 && v <= mid); }
+        if (c) atomicAdd(&s_cnt, c);
+        __syncthreads();
+        if (s_cnt >= rank + 1) hi = mid; else lo = mid + 1;
+    }
+    const float thDist = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)lo);
+    for (int i = tid; i < n; i += blockDim.x)
+        if (sad[i] >= 0 && !((float)sad[i] < thDist)) { uRight[i] = -1.0f; depth[i] = -1.0f; }
+}
+
+extern "C" int orbx_stereo_matches(orbx_extractor* left, orbx_extractor* right, int frame_left, int frame_right,
+                                   const orbx_keypoint* kp_left, const uint8_t* desc_left, int n_left,
+                                   const orbx_keypoint* kp_right, const uint8_t* desc_right, int n_right,
+                                   float mbf, float mb, float* u_right, float* depth) {
+    ORB_REQUIRE(left && right && n_left >= 0 && n_right >= 0, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(n_left == 0 || (kp_left && desc_left && u_right && depth), ORB_ERR_ARG, "null left array");
+    ORB_REQUIRE(n_right == 0 || (kp_right && desc_right), ORB_ERR_ARG, "null right array");
+    ORB_REQUIRE(left->device == right->device && left->nlevels == right->nlevels && left->plan.width == right->plan.width &&
+                left->plan.height == right->plan.height && left->scaleFactor == right->scaleFactor, ORB_ERR_ARG,
+                "the two extractors must share device, image size, level count and scale factor");
+    ORB_REQUIRE(frame_left >= 0 && frame_left < left->lastFrames && frame_right >= 0 && frame_right < right->lastFrames, ORB_ERR_ARG,
+                "no pyramid for that frame: run the extraction first");
+    ORB_REQUIRE(n_right <= 0x3FFFFF, ORB_ERR_ARG, "too many right keypoints");
+    for (int i = 0; i < n_left; i++) ORB_REQUIRE(kp_left[i].octave >= 0 && kp_left[i].octave < left->nlevels, ORB_ERR_ARG, "left octave out of range");
+    for (int i = 0; i < n_right; i++) ORB_REQUIRE(kp_right[i].octave >= 0 && kp_right[i].octave < right->nlevels, ORB_ERR_ARG, "right octave out of range");
+    if (n_left == 0) return ORB_OK;
+    ORB_CUDA_TRY(cudaSetDevice(left->device));
+    std::lock_guard<std::mutex> lk(left->mu);
+    cudaStream_t st = left->stream;
+    // scratch: one allocation per call sized by the keypoint counts (a few hundred KB)
+    const size_t bL = (size_t)n_left * sizeof(orbx_keypoint), bR = (size_t)std::max(n_right, 1) * sizeof(orbx_keypoint);
+    const size_t offKL = 0, offKR = orb_align_up(offKL + bL, 256), offDL = orb_align_up(offKR + bR, 256),
+                 offDR = orb_align_up(offDL + (size_t)n_left * 32, 256), offRI = orb_align_up(offDR + (size_t)std::max(n_right, 1) * 32, 256),
+                 offU = orb_align_up(offRI + (size_t)std::max(n_right, 1) * 16, 256), offD = orb_align_up(offU + (size_t)n_left * 4, 256),
+                 offS = orb_align_up(offD + (size_t)n_left * 4, 256), total = orb_align_up(offS + (size_t)n_left * 4, 256);
+    u8* d = nullptr;
+    ORB_CUDA_TRY(cudaMallocAsync(&d, total, st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(d + offKL, kp_left, bL, cudaMemcpyHostToDevice, st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(d + offDL, desc_left, (size_t)n_left * 32, cudaMemcpyHostToDevice, st));
+    if (n_right) {
+        ORB_CUDA_TRY(cudaMemcpyAsync(d + offKR, kp_right, (size_t)n_right * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, st));
+        ORB_CUDA_TRY(cudaMemcpyAsync(d + offDR, desc_right, (size_t)n_right * 32, cudaMemcpyHostToDevice, st));
+    }
+    // the right handle's last pass must be complete before its pyramid is read on the left handle's stream
+    ORB_CUDA_TRY(cudaStreamSynchronize(right->stream));
+    StereoParams S;
+    S.pyrL = left->d_pyr + (size_t)frame_left * left->plan.frameBytes;
+    S.pyrR = right->d_pyr + (size_t)frame_right * right->plan.frameBytes;
+    S.kpL = reinterpret_cast<const orbx_keypoint*>(d + offKL); S.kpR = reinterpret_cast<const orbx_keypoint*>(d + offKR);
+    S.descL = d + offDL; S.descR = d + offDR;
+    S.nL = n_left; S.nR = n_right; S.nRows = left->plan.lv[0].h;
+    S.mbf = mbf; S.maxD = mbf / mb;
+    for (int l = 0; l < left->nlevels; l++) { S.sf[l] = left->sf[l]; S.isf[l] = left->isf[l]; }
+    int4* rinfo = reinterpret_cast<int4*>(d + offRI);
+    float* dU = reinterpret_cast<float*>(d + offU);
+    float* dD = reinterpret_cast<float*>(d + offD);
+    int* dS = reinterpret_cast<int*>(d + offS);
+    if (n_right) k_stereo_prepare<<<orb_div_up(n_right, 32 * ST_WARPS), 32 * ST_WARPS, 0, st>>>(S, rinfo);
+    k_stereo<<<orb_div_up(n_left, ST_WARPS), 32 * ST_WARPS, 0, st>>>(left->plan, S, rinfo, dU, dD, dS);
+    k_stereo_median<<<1, 1024, 0, st>>>(n_left, dS, dU, dD);
+    left->launches += 3;
+    ORB_CUDA_TRY(cudaGetLastError());
+    ORB_CUDA_TRY(cudaMemcpyAsync(u_right, dU, (size_t)n_left * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA_TRY(cudaMemcpyAsync(depth, dD, (size_t)n_left * 4, cudaMemcpyDeviceToHost, st));
+    ORB_CUDA_TRY(cudaFreeAsync(d, st));
+    ORB_CUDA_TRY(cudaStreamSynchronize(st));
+    return ORB_OK;
+}

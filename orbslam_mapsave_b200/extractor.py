@@ -134,6 +134,20 @@ class ORBextractor:
                                                      capi._p(d_desc), cap, capi._p(d_n), stages,
                                                      C.c_void_p(stream) if stream else None))
 
+    def ComputeStereoMatches(self, right, kp_left, desc_left, kp_right, desc_right, mbf, mb, frame_left=0, frame_right=0):
+        """Frame::ComputeStereoMatches (src/Frame.cc:584-756) on the device-resident pyramids of this (left) extractor and
+        `right`, after both have extracted their image.  Returns (mvuRight, mvDepth)."""
+        kp_left = np.ascontiguousarray(kp_left, capi.KP_DTYPE)
+        kp_right = np.ascontiguousarray(kp_right, capi.KP_DTYPE)
+        desc_left = np.ascontiguousarray(desc_left, np.uint8).reshape(-1, 32)
+        desc_right = np.ascontiguousarray(desc_right, np.uint8).reshape(-1, 32)
+        u = np.zeros(max(len(kp_left), 1), np.float32)
+        d = np.zeros(max(len(kp_left), 1), np.float32)
+        capi.check(capi.lib().orbx_stereo_matches(self._h, right._h, frame_left, frame_right, capi._p(kp_left), capi._p(desc_left),
+                                                  len(kp_left), capi._p(kp_right), capi._p(desc_right), len(kp_right), float(mbf), float(mb),
+                                                  capi._p(u), capi._p(d)))
+        return u[:len(kp_left)], d[:len(kp_left)]
+
     def check_status(self):
         capi.check(capi.lib().orbx_check_status(self._h))
 

@@ -88,4 +88,22 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::
     }
 }
 
+
+void ORBextractor::ComputeStereoMatches(ORBextractor* left, ORBextractor* right, const std::vector<cv::KeyPoint>& mvKeys,
+                                        const cv::Mat& mDescriptors, const std::vector<cv::KeyPoint>& mvKeysRight,
+                                        const cv::Mat& mDescriptorsRight, float mbf, float mb, std::vector<float>& mvuRight,
+                                        std::vector<float>& mvDepth) {
+    const int N = (int)mvKeys.size(), Nr = (int)mvKeysRight.size();
+    mvuRight = std::vector<float>(N, -1.0f);                                              // src/Frame.cc:586-587
+    mvDepth = std::vector<float>(N, -1.0f);
+    if (N == 0 || !left->mHandle || !right->mHandle) return;
+    std::vector<unsigned char> dl((size_t)N * 32), dr((size_t)(Nr > 0 ? Nr : 1) * 32);
+    for (int i = 0; i < N; i++) std::memcpy(&dl[(size_t)i * 32], mDescriptors.ptr(i), 32);
+    for (int i = 0; i < Nr; i++) std::memcpy(&dr[(size_t)i * 32], mDescriptorsRight.ptr(i), 32);
+    left->mLastStatus = orbx_stereo_matches(left->mHandle, right->mHandle, 0, 0, reinterpret_cast<const orbx_keypoint*>(mvKeys.data()),
+                                            dl.data(), N, reinterpret_cast<const orbx_keypoint*>(mvKeysRight.data()), dr.data(), Nr,
+                                            mbf, mb, mvuRight.data(), mvDepth.data());
+    if (left->mLastStatus != ORB_OK) std::fprintf(stderr, "ORBextractor::ComputeStereoMatches: %s\n", orb_last_error());
+}
+
 }  // namespace ORB_SLAM2

@@ -38,6 +38,13 @@ public:
     void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }   // mvImagePyramid costs 8 device->host copies per frame;
                                                                     // only Frame::ComputeStereoMatches reads it
     int LastStatus() const { return mLastStatus; }             // orb_status of the last call (the reference API has no error channel)
+    // The body of Frame::ComputeStereoMatches (src/Frame.cc:584-756) on the device-resident pyramids of the two extractors'
+    // last operator() calls: fills mvuRight / mvDepth exactly like the reference.  With this, a stereo Frame can call
+    // SetPyramidDownload(false) on both extractors (nothing else reads mvImagePyramid).
+    static void ComputeStereoMatches(ORBextractor* left, ORBextractor* right, const std::vector<cv::KeyPoint>& mvKeys,
+                                     const cv::Mat& mDescriptors, const std::vector<cv::KeyPoint>& mvKeysRight,
+                                     const cv::Mat& mDescriptorsRight, float mbf, float mb, std::vector<float>& mvuRight,
+                                     std::vector<float>& mvDepth);
 
 protected:
     void Plan(int width, int height);

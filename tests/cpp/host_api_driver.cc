@@ -397,6 +397,29 @@ static int run_project2(int argc, char** argv) {
     return ORBmatcher::LastStatus() == 0 ? 0 : 4;
 }
 
+// driver stereo <left.raw> <right.raw> <w> <h> <nfeat> <nlevels> <mbf> <mb> <out.bin>: the stereo Frame constructor's path
+// (two extractors, then ComputeStereoMatches) without ever downloading a pyramid
+static int run_stereo(int argc, char** argv) {
+    if (argc < 11) return 2;
+    const int w = atoi(argv[4]), h = atoi(argv[5]);
+    std::vector<unsigned char> l = slurp(argv[2]), r = slurp(argv[3]);
+    if ((int)l.size() != w * h || (int)r.size() != w * h) return 3;
+    ORBextractor exL(atoi(argv[6]), 1.2f, atoi(argv[7]), 20, 7), exR(atoi(argv[6]), 1.2f, atoi(argv[7]), 20, 7);
+    exL.SetPyramidDownload(false); exR.SetPyramidDownload(false);
+    cv::Mat imL(h, w, CV_8U, l.data()), imR(h, w, CV_8U, r.data()), nomask;
+    std::vector<cv::KeyPoint> kL, kR;
+    cv::Mat dL, dR;
+    exL(imL, nomask, kL, dL);
+    exR(imR, nomask, kR, dR);
+    std::vector<float> uR(2, 5.f), depth;
+    ORBextractor::ComputeStereoMatches(&exL, &exR, kL, dL, kR, dR, (float)atof(argv[8]), (float)atof(argv[9]), uR, depth);
+    if (exL.LastStatus() != 0) return 4;
+    std::ofstream out(argv[10], std::ios::binary);
+    const int n = (int)uR.size();
+    put(out, &n, 1); put(out, uR.data(), uR.size()); put(out, depth.data(), depth.size());
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     if (!strcmp(argv[1], "bow")) return run_bow(argc, argv);
@@ -404,5 +427,6 @@ int main(int argc, char** argv) {
     if (!strcmp(argv[1], "match")) return run_match(argc, argv);
     if (!strcmp(argv[1], "project")) return run_project(argc, argv);
     if (!strcmp(argv[1], "project2")) return run_project2(argc, argv);
+    if (!strcmp(argv[1], "stereo")) return run_stereo(argc, argv);
     return 2;
 }

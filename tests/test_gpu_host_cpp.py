@@ -300,3 +300,27 @@ def test_cpp_relocalisation_and_loop_projection_match_oracle(tmp_path, seed, ori
     on, oo = orc.search_projection_sim3(og, kq["S"], kq["fx"], kq["fy"], kq["cx"], kq["cy"], np.float32(log_sf), kq["state"] == 1, kq["world"],
                                         kq["mf_max"], kq["mf_min"], kq["normal"], kq["desc"], thE)
     assert nm == on and np.array_equal(got, oo) and on > 100
+
+
+def test_cpp_stereo_matches_oracle(tmp_path):
+    """Two C++ ORBextractors + ORBextractor::ComputeStereoMatches (the stereo Frame constructor's path, src/Frame.cc:78-95) with
+    the pyramid download switched off, against the oracle's ComputeStereoMatches on the oracle's pyramids."""
+    from test_gpu_stereo import _stereo_pair
+    left, right = _stereo_pair(640, 480, 7)
+    (tmp_path / "l.raw").write_bytes(left.tobytes())
+    (tmp_path / "r.raw").write_bytes(right.tobytes())
+    mbf, mb = 40.0, np.float32(40.0) / np.float32(500.0)
+    subprocess.check_call([_driver(), "stereo", str(tmp_path / "l.raw"), str(tmp_path / "r.raw"), "640", "480", "1000", "8", repr(mbf),
+                           repr(float(mb)), str(tmp_path / "out.bin")])
+    out = (tmp_path / "out.bin").read_bytes()
+    (n,) = struct.unpack_from("<i", out, 0)
+    got_u = np.frombuffer(out, np.float32, n, 4)
+    got_d = np.frombuffer(out, np.float32, n, 4 + 4 * n)
+    oL, oR = orc.Extractor(1000, 1.2, 8, 20, 7), orc.Extractor(1000, 1.2, 8, 20, 7)
+    okL, odL = oL.extract(left)
+    okR, odR = oR.extract(right)
+    t = oL.tables()
+    want_u, want_d = orc.stereo_matches([oL.level(l) for l in range(8)], [oR.level(l) for l in range(8)], t["scale"], t["inv_scale"],
+                                        okL, odL, okR, odR, mbf, float(mb))
+    assert n == len(okL) and np.array_equal(got_u.view(np.uint32), want_u.view(np.uint32))
+    assert np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32)) and (want_u >= 0).sum() > 200
