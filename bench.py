@@ -407,6 +407,61 @@ def main():
                "unit": "descriptors/s", "hamming_distances_per_s": world * nd * bsteps * k * L / bsecs,
                "config": {"workload": f"{nd} random descriptors per GPU per step through a synthetic {n_nodes}-node tree (35 MB, L2-resident)"}}
 
+    # ---- "next" rows: the tracker's window searches and the stereo matcher, single-call latency through the C ABI from host
+    # arrays (rank 0, N=1 only: they are per-frame latency paths, "replicas only" under multi-GPU)
+    tracking = None
+    if rank == 0 and world == 1 and not args.no_match:
+        import time as _t
+        rng = np.random.default_rng(5)
+        n = 2000
+        sc = (1.2 ** np.arange(8)).astype(np.float32)
+        pz = 1.0 / sc.astype(np.float64)
+        fx_, fy_, cx_, cy_ = 520.0, 520.0, 320.0, 240.0
+        x = rng.uniform(0, 640, n).astype(np.float32)
+        y = rng.uniform(0, 480, n).astype(np.float32)
+        octv = rng.choice(8, n, p=pz / pz.sum()).astype(np.int32)
+        ang = rng.uniform(0, 360, n).astype(np.float32)
+        dsc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        ur = np.where(rng.random(n) < 0.7, x - 20, -1).astype(np.float32)
+        grid = orb.GridView(dsc, x, y, octv, sc, (0.0, 0.0, 640.0, 480.0), angle=ang, uright=ur, blocked=np.zeros(n, np.uint8))
+        Tcw = np.concatenate([np.eye(3, dtype=np.float32), np.zeros((3, 1), np.float32)], 1)
+        z = rng.uniform(1, 8, n)
+        world_pts = np.stack([(x + rng.normal(0, 2, n) - cx_) / fx_ * z, (y + rng.normal(0, 2, n) - cy_) / fy_ * z, z], 1).astype(np.float32)
+        flips = (rng.random((n, 32, 8)) < 0.05)
+        mdesc = dsc ^ np.packbits(flips, axis=2).reshape(n, 32)
+        args_f = (Tcw, Tcw, fx_, fy_, cx_, cy_, 40.0, 40.0 / fx_, np.ones(n, np.uint8), world_pts, octv, ang, mdesc, np.ones(n, np.uint8), 7.0, False)
+        m = orb.ORBmatcher(0.9, True, device=local_rank)
+
+        def lat(f, reps=30):
+            f()
+            t0 = _t.perf_counter()
+            for _ in range(reps):
+                r = f()
+            return (_t.perf_counter() - t0) / reps, r
+        t_gpu, (nm, _) = lat(lambda: m.SearchByProjectionFrame(grid, *args_f))
+        tracking = {"search_by_projection_last_frame": {"ms_per_call": 1e3 * t_gpu, "features": n, "matches": int(nm),
+                                                        "note": "C ABI from pageable host arrays: upload + 3 kernels + download"}}
+        left = frames[0]
+        right = np.roll(left, -12, axis=1)
+        exL, exR = orb.ORBextractor(1000, 1.2, 8, 20, 7, device=local_rank), orb.ORBextractor(1000, 1.2, 8, 20, 7, device=local_rank)
+        kL, dL = exL(left, download_pyramid=False)
+        kR, dR = exR(right, download_pyramid=False)
+        t_st, (u_r, _) = lat(lambda: exL.ComputeStereoMatches(exR, kL, dL, kR, dR, 40.0, 0.08))
+        tracking["compute_stereo_matches"] = {"ms_per_call": 1e3 * t_st, "left_keypoints": int(len(kL)), "matched": int((u_r >= 0).sum()),
+                                              "note": "640x480, on the device-resident pyramids of two extractor handles"}
+        if not args.no_cpu:
+            from oracle import orb_oracle_py as orc
+            og = orc.Grid(dsc, x, y, octv, sc, (0.0, 0.0, 640.0, 480.0), angle=ang, uright=ur, blocked=np.zeros(n, np.uint8))
+            t_cpu, _ = lat(lambda: orc.search_projection_frame(og, *args_f, True), 5)
+            tracking["search_by_projection_last_frame"]["cpu_port_ms_per_call"] = 1e3 * t_cpu
+            oL, oR = orc.Extractor(1000, 1.2, 8, 20, 7), orc.Extractor(1000, 1.2, 8, 20, 7)
+            okL, odL = oL.extract(left)
+            okR, odR = oR.extract(right)
+            tb = oL.tables()
+            lv = ([oL.level(l) for l in range(8)], [oR.level(l) for l in range(8)])
+            t_cpu, _ = lat(lambda: orc.stereo_matches(lv[0], lv[1], tb["scale"], tb["inv_scale"], okL, odL, okR, odR, 40.0, 0.08), 5)
+            tracking["compute_stereo_matches"]["cpu_port_ms_per_call"] = 1e3 * t_cpu
+
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -425,7 +480,7 @@ def main():
                        "keypoints_per_frame": kp_per_frame, "l2": "inputs_exceed_l2 (1.26 GB of frames per step per GPU)",
                        "parallelism": f"frame-sharded x{world}, no data-path collective", "numa_node_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "matching": matching, "bow": bow,
+            "matching": matching, "bow": bow, "tracking": tracking,
         })
     if world > 1:
         dist.destroy_process_group()

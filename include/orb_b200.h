@@ -306,6 +306,16 @@ int orbm_search_windows(const orbm_grid_view* target, int nq, const uint8_t* act
                         const float* r, const int* min_level, const int* max_level, const uint8_t* desc, const float* angle,
                         int th_dist, int check_orientation, int* owner, int* n_matches, int device);
 
+/* Independent form of the window search, for the searches in which a match does not change what later queries may take:
+ * SearchBySim3 (src/ORBmatcher.cc:1105-1329, both directions) and the candidate loops of Fuse (:828-972) and Fuse with a
+ * similarity (:974-1103).  best_idx[q] = the feature in q's window (levels as above) with the smallest descriptor distance
+ * (first wins ties) if that distance <= th_dist, else -1.  With ur / inv_level_sigma2 (both or neither) every candidate first
+ * passes Fuse's reprojection gate (:913-944): e2 * inv_level_sigma2[octave] <= 7.8 with e2 = ex^2+ey^2+(ur-uright)^2 when the
+ * feature has uright >= 0, else <= 5.99 with e2 = ex^2+ey^2.  target->blocked is ignored. */
+int orbm_search_windows_best(const orbm_grid_view* target, int nq, const uint8_t* active, const float* u, const float* v,
+                             const float* r, const int* min_level, const int* max_level, const uint8_t* desc, const float* ur,
+                             const float* inv_level_sigma2, int th_dist, int* best_idx, int device);
+
 /* POPC issue-rate microbenchmark (defines the matching roofline): returns measured 32-bit POPC results
  * per second on `device` over a register-resident loop. */
 int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);

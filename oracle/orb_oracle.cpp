@@ -1497,4 +1497,122 @@ void orc_stereo_matches(int nlevels, const u8* const* pyrL, const u8* const* pyr
     }
 }
 
+
+// ---- independent window search: the candidate loops of SearchBySim3 (ORBmatcher.cc:1178-1213, 1258-1293) and Fuse (:899-950,
+// 1054-1081).  With ur / inv_sigma2 the chi-square reprojection gate of Fuse (:913-944) applies per candidate.
+void orc_search_windows_best(const orc_grid_view* Fp, int nq, const u8* active, const float* u, const float* v, const float* r,
+                             const int* min_level, const int* max_level, const u8* desc, const float* ur, const float* inv_sigma2,
+                             int th_dist, int* best_idx) {
+    const orc_grid_view& F = *Fp;
+    std::vector<int> cand;
+    for (int q = 0; q < nq; q++) {
+        best_idx[q] = -1;
+        if (!active[q]) continue;
+        features_in_area(F, u[q], v[q], r[q], min_level[q], max_level[q], cand);
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            if (inv_sigma2) {
+                const int kpLevel = F.octave[idx];
+                const float kpx = F.x[idx], kpy = F.y[idx];
+                const float kpr = F.uright ? F.uright[idx] : -1.0f;
+                const float ex = u[q] - kpx, ey = v[q] - kpy;
+                if (kpr >= 0) {
+                    const float er = ur[q] - kpr;
+                    const float e2 = ex * ex + ey * ey + er * er;
+                    if (e2 * inv_sigma2[kpLevel] > 7.8) continue;
+                } else {
+                    const float e2 = ex * ex + ey * ey;
+                    if (e2 * inv_sigma2[kpLevel] > 5.99) continue;
+                }
+            }
+            const int dist = descriptor_distance(desc + (size_t)q * 32, F.desc + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestDist <= th_dist) best_idx[q] = bestIdx;
+    }
+}
+
+
+// ---- Fuse (ORBmatcher.cc:828-972) and Fuse with a similarity (:974-1103): projection + candidate loop for every point that passes
+// the entry test; best_idx[i] = bestIdx when bestDist <= TH_LOW, else -1.  The map updates (:952-971, 1083-1099) are host
+// bookkeeping on MapPoint / KeyFrame objects and are replayed by the tests from these indices.
+//   variant 0: T = [Rcw|tcw], Ow = GetCameraCenter(), invz = 1/z, chi-square gate with bf / inv_sigma2
+//   variant 1: T = rows of Scw (decomposed here, :983-987), invz = 1.0/z, no gate
+void orc_fuse_search(const orc_grid_view* Kp, int variant, const float* Tin, const float* Ow_in, float fx, float fy, float cx, float cy,
+                     float bf, float logScaleFactor, int n, const u8* skip, const float* world, const float* mf_max, const float* mf_min,
+                     const float* normal, const u8* desc, float th, const float* inv_sigma2, int* best_idx) {
+    const orc_grid_view& KF = *Kp;
+    float T[12], Ow[3];
+    if (variant == 0) {
+        for (int i = 0; i < 12; i++) T[i] = Tin[i];
+        for (int i = 0; i < 3; i++) Ow[i] = Ow_in[i];
+    } else {
+        const float scw = (float)std::sqrt((double)Tin[0] * Tin[0] + (double)Tin[1] * Tin[1] + (double)Tin[2] * Tin[2]);
+        const float inv = (float)(1.0 / (double)scw);
+        for (int i = 0; i < 12; i++) T[i] = Tin[i] * inv;
+        minus_rt_t(T, Ow);
+    }
+    std::vector<u8> active(n, 0);
+    std::vector<float> u(n, 0.f), v(n, 0.f), rad(n, 0.f), ur(n, 0.f);
+    std::vector<int> minL(n, -1), maxL(n, -1);
+    for (int i = 0; i < n; i++) {
+        if (skip[i]) continue;
+        const float* p3Dw = world + 3 * (size_t)i;
+        float p3Dc[3];
+        rt_apply(T, p3Dw, p3Dc);
+        if (p3Dc[2] < 0.0f) continue;
+        float invz;
+        if (variant == 0) invz = 1 / p3Dc[2]; else invz = 1.0 / p3Dc[2];
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float uu = fx * x + cx, vv = fy * y + cy;
+        if (!(uu >= KF.min_x && uu < KF.max_x && vv >= KF.min_y && vv < KF.max_y)) continue;
+        ur[i] = uu - bf * invz;
+        const float maxDistance = 1.2f * mf_max[i], minDistance = 0.8f * mf_min[i];
+        const float PO[3] = {p3Dw[0] - Ow[0], p3Dw[1] - Ow[1], p3Dw[2] - Ow[2]};
+        const float dist3D = norm3(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float* Pn = normal + 3 * (size_t)i;
+        const double dot = (double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2];
+        if (dot < 0.5 * dist3D) continue;
+        const int nPredictedLevel = predict_scale(mf_max[i], dist3D, logScaleFactor, KF.n_levels);
+        active[i] = 1; u[i] = uu; v[i] = vv;
+        rad[i] = th * KF.scale_factors[nPredictedLevel];
+        minL[i] = nPredictedLevel - 1; maxL[i] = nPredictedLevel;
+    }
+    orc_search_windows_best(Kp, n, active.data(), u.data(), v.data(), rad.data(), minL.data(), maxL.data(), desc,
+                            variant == 0 ? ur.data() : nullptr, variant == 0 ? inv_sigma2 : nullptr, TH_LOW, best_idx);
+}
+
+// One direction of SearchBySim3 (ORBmatcher.cc:1150-1219 / 1222-1299): points seen from camera `from` (Rfw, tfw) moved into camera
+// `to` by [sR|t], searched in `to`'s features.  valid[i] = pMP && !vbAlreadyMatched[i] && !isBad().
+void orc_sim3_direction(const orc_grid_view* Tp, const float* Rfw, const float* tfw, const float* sR, const float* t, float fx, float fy,
+                        float cx, float cy, float logScaleFactor, int n, const u8* valid, const float* world, const float* mf_max,
+                        const float* mf_min, const u8* desc, float th, int* vnMatch) {
+    const orc_grid_view& KF = *Tp;
+    float T1[12], T2[12];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) { T1[4 * r + c] = Rfw[3 * r + c]; T2[4 * r + c] = sR[3 * r + c]; } T1[4 * r + 3] = tfw[r]; T2[4 * r + 3] = t[r]; }
+    std::vector<u8> active(n, 0);
+    std::vector<float> u(n, 0.f), v(n, 0.f), rad(n, 0.f);
+    std::vector<int> minL(n, -1), maxL(n, -1);
+    for (int i = 0; i < n; i++) {
+        if (!valid[i]) continue;
+        float c1[3], c2[3];
+        rt_apply(T1, world + 3 * (size_t)i, c1);
+        rt_apply(T2, c1, c2);
+        if (c2[2] < 0.0) continue;
+        const float invz = 1.0 / c2[2];
+        const float x = c2[0] * invz, y = c2[1] * invz;
+        const float uu = fx * x + cx, vv = fy * y + cy;
+        if (!(uu >= KF.min_x && uu < KF.max_x && vv >= KF.min_y && vv < KF.max_y)) continue;
+        const float maxDistance = 1.2f * mf_max[i], minDistance = 0.8f * mf_min[i];
+        const float dist3D = norm3(c2);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = predict_scale(mf_max[i], dist3D, logScaleFactor, KF.n_levels);
+        active[i] = 1; u[i] = uu; v[i] = vv;
+        rad[i] = th * KF.scale_factors[nPredictedLevel];
+        minL[i] = nPredictedLevel - 1; maxL[i] = nPredictedLevel;
+    }
+    orc_search_windows_best(Tp, n, active.data(), u.data(), v.data(), rad.data(), minL.data(), maxL.data(), desc, nullptr, nullptr, TH_HIGH, vnMatch);
+}
+
 }  // extern "C"

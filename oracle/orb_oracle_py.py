@@ -505,3 +505,47 @@ def stereo_matches(levels_left, levels_right, scale_factors, inv_scale_factors, 
                   C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     f(nl, pl, pr, _p(w), _p(h), _p(sf), _p(isf), _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), float(mbf), float(mb), _p(u), _p(d))
     return u[:len(kl)], d[:len(kl)]
+
+
+def search_windows_best(grid, active, u, v, r, min_level, max_level, desc, ur, inv_sigma2, th_dist):
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    active, desc = _u8(active), _u8(desc).reshape(-1, 32)
+    u, v, r, ur, inv_sigma2, min_level, max_level = f32(u), f32(v), f32(r), f32(ur), f32(inv_sigma2), i32(min_level), i32(max_level)
+    best = np.zeros(max(len(active), 1), np.int32)
+    f = lib().orc_search_windows_best
+    f.restype = None
+    f.argtypes = [C.POINTER(GridViewC), C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_void_p]
+    g = grid.c()
+    f(C.byref(g), len(active), _p(active), _p(u), _p(v), _p(r), _p(min_level), _p(max_level), _p(desc), _p(ur), _p(inv_sigma2), int(th_dist), _p(best))
+    return best[:len(active)]
+
+
+def fuse_search(grid, variant, T, Ow, fx, fy, cx, cy, bf, log_sf, skip, world, mf_max, mf_min, normal, desc, th, inv_sigma2):
+    f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    skip, desc = _u8(skip), _u8(desc).reshape(-1, 32)
+    world, normal, mf_max, mf_min, inv_sigma2 = f32(world).reshape(-1, 3), f32(normal).reshape(-1, 3), f32(mf_max), f32(mf_min), f32(inv_sigma2)
+    Tf, Owf = f32(T).reshape(-1)[:12].copy(), f32(Ow if Ow is not None else np.zeros(3))
+    best = np.zeros(max(len(skip), 1), np.int32)
+    f = lib().orc_fuse_search
+    f.restype = None
+    f.argtypes = [C.POINTER(GridViewC), C.c_int, C.c_void_p, C.c_void_p] + [C.c_float] * 6 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_void_p, C.c_void_p]
+    g = grid.c()
+    f(C.byref(g), int(variant), _p(Tf), _p(Owf), fx, fy, cx, cy, bf, log_sf, len(skip), _p(skip), _p(world), _p(mf_max), _p(mf_min),
+      _p(normal), _p(desc), float(th), _p(inv_sigma2), _p(best))
+    return best[:len(skip)]
+
+
+def sim3_direction(grid_to, Rfw, tfw, sR, t, fx, fy, cx, cy, log_sf, valid, world, mf_max, mf_min, desc, th):
+    f32 = lambda a: np.ascontiguousarray(a, np.float32)
+    valid, desc = _u8(valid), _u8(desc).reshape(-1, 32)
+    world, mf_max, mf_min = f32(world).reshape(-1, 3), f32(mf_max), f32(mf_min)
+    Rfw, tfw, sR, t = f32(Rfw).reshape(9), f32(tfw).reshape(3), f32(sR).reshape(9), f32(t).reshape(3)
+    out = np.zeros(max(len(valid), 1), np.int32)
+    f = lib().orc_sim3_direction
+    f.restype = None
+    f.argtypes = [C.POINTER(GridViewC)] + [C.c_void_p] * 4 + [C.c_float] * 5 + [C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_void_p]
+    g = grid_to.c()
+    f(C.byref(g), _p(Rfw), _p(tfw), _p(sR), _p(t), fx, fy, cx, cy, log_sf, len(valid), _p(valid), _p(world), _p(mf_max), _p(mf_min), _p(desc),
+      float(th), _p(out))
+    return out[:len(valid)]

@@ -29,7 +29,7 @@ SYMBOLS = [
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
     "orbm_popc_peak", "orbm_distinctive_descriptors",
-    "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_for_initialization", "orbm_search_windows",
+    "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_for_initialization", "orbm_search_windows", "orbm_search_windows_best",
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
     "orbv_transform_device",
 ]
@@ -136,6 +136,8 @@ def lib():
     L.orbm_search_for_initialization.argtypes = [C.POINTER(GridViewC), i32, vp, vp, vp, vp, i32, f32, i32, vp, vp, i32]
     L.orbm_search_windows.restype = i32
     L.orbm_search_windows.argtypes = [C.POINTER(GridViewC), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32]
+    L.orbm_search_windows_best.restype = i32
+    L.orbm_search_windows_best.argtypes = [C.POINTER(GridViewC), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32]
     L.orbv_create.restype = i32
     L.orbv_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, vp, i32]
     L.orbv_load_text.restype = i32

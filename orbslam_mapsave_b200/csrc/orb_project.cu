@@ -25,6 +25,7 @@
 #define WIN_ACTIVE 1
 #define WIN_CLAIMS 2
 #define WIN_GATE 4
+#define WIN_CHI2 8                          // Fuse: per-candidate reprojection-error gate (src/ORBmatcher.cc:913-944)
 
 enum { MODE_BEST = 0, MODE_TOP2_LEVEL = 1, MODE_INIT = 2 };
 
@@ -35,6 +36,7 @@ struct DevGrid {
     float min_x, min_y, max_x, max_y, inv_w, inv_h;
     const int* cell_off; const int* cell_feat;
     const float* sf; int n_levels;
+    const float* inv_sigma2;                // mvInvLevelSigma2 (Fuse only)
 };
 struct __align__(16) Win { float u, v, r, ur, tol; int minL, maxL, flags; };
 
@@ -108,11 +110,15 @@ __global__ void k_win_init(int nq, const int* __restrict__ octave1, const float*
 
 // Explicit windows (the shared core of the relocalisation / loop-closing projection searches): every accepted match claims.
 __global__ void k_win_explicit(int nq, const u8* __restrict__ active, const float* __restrict__ u, const float* __restrict__ v,
-                               const float* __restrict__ r, const int* __restrict__ minL, const int* __restrict__ maxL, Win* __restrict__ win) {
+                               const float* __restrict__ r, const int* __restrict__ minL, const int* __restrict__ maxL,
+                               const float* __restrict__ ur, int flags, Win* __restrict__ win) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     Win w = {0.f, 0.f, 0.f, 0.f, 0.f, -1, -1, 0};
-    if (active[q]) { w.u = u[q]; w.v = v[q]; w.r = r[q]; w.minL = minL[q]; w.maxL = maxL[q]; w.flags = WIN_ACTIVE | WIN_CLAIMS; }
+    if (active[q]) {
+        w.u = u[q]; w.v = v[q]; w.r = r[q]; w.minL = minL[q]; w.maxL = maxL[q]; w.flags = WIN_ACTIVE | flags;
+        if (ur) w.ur = ur[q];
+    }
     win[q] = w;
 }
 
@@ -129,6 +135,19 @@ __device__ __forceinline__ bool cand_pass(const DevGrid& G, const Win& w, bool c
     if (w.flags & WIN_GATE) {
         const float ur = G.uright[idx];
         if (ur > 0 && fabsf(__fsub_rn(w.ur, ur)) > w.tol) return false;
+    }
+    if (w.flags & WIN_CHI2) {                                           // chi-square gate on the reprojection error, 2 or 3 dof
+        const float ex = __fsub_rn(w.u, G.x[idx]), ey = __fsub_rn(w.v, G.y[idx]);
+        const float kpr = G.uright ? G.uright[idx] : -1.0f;
+        const float is2 = G.inv_sigma2[G.octave[idx]];
+        if (kpr >= 0) {
+            const float er = __fsub_rn(w.ur, kpr);
+            const float e2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(er, er));
+            if ((double)__fmul_rn(e2, is2) > 7.8) return false;
+        } else {
+            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            if ((double)__fmul_rn(e2, is2) > 5.99) return false;
+        }
     }
     return true;
 }
@@ -358,7 +377,7 @@ static int upload_grid(Arena& A, const orbm_grid_view* g, DevGrid* d) {
     d->n = g->n; d->cols = g->grid_cols; d->rows = g->grid_rows;
     d->min_x = g->min_x; d->min_y = g->min_y; d->max_x = g->max_x; d->max_y = g->max_y; d->inv_w = g->inv_w; d->inv_h = g->inv_h;
     d->n_levels = g->n_levels;
-    d->angle = nullptr; d->uright = nullptr; d->blocked = nullptr;
+    d->angle = nullptr; d->uright = nullptr; d->blocked = nullptr; d->inv_sigma2 = nullptr;
     if ((rc = upload(A, g->desc, n * 32, &d->desc))) return rc;
     if ((rc = upload(A, g->x, n, &d->x))) return rc;
     if ((rc = upload(A, g->y, n, &d->y))) return rc;
@@ -565,7 +584,7 @@ extern "C" int orbm_search_windows(const orbm_grid_view* target, int nq, const u
     if ((rc = A.flush())) return rc;
     WinWork w;
     take_work(A, nq, nt, &w);
-    if (nq > 0) k_win_explicit<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(nq, d_active, d_u, d_v, d_r, d_minL, d_maxL, w.win);
+    if (nq > 0) k_win_explicit<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(nq, d_active, d_u, d_v, d_r, d_minL, d_maxL, nullptr, WIN_CLAIMS, w.win);
     if ((rc = run_search(A, G, w, d_desc, d_angle, nq, MODE_BEST, th_dist, 0.f, check_orientation))) return rc;
     int cnt[2] = {0, 0};
     if ((rc = A.fetch(owner, w.owner, (size_t)nt))) return rc;
@@ -573,4 +592,46 @@ extern "C" int orbm_search_windows(const orbm_grid_view* target, int nq, const u
     if ((rc = A.finish())) return rc;
     *n_matches = cnt[0];
     return ORB_OK;
+}
+
+extern "C" int orbm_search_windows_best(const orbm_grid_view* target, int nq, const uint8_t* active, const float* u, const float* v,
+                                        const float* r, const int* min_level, const int* max_level, const uint8_t* desc, const float* ur,
+                                        const float* inv_level_sigma2, int th_dist, int* best_idx, int device) {
+    ORB_REQUIRE(best_idx && nq >= 0 && th_dist >= 0 && th_dist <= 256, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(nq == 0 || (active && u && v && r && min_level && max_level && desc), ORB_ERR_ARG, "null query array");
+    ORB_REQUIRE((ur == nullptr) == (inv_level_sigma2 == nullptr), ORB_ERR_ARG, "ur and inv_level_sigma2 go together");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_grid(target, false))) return rc;
+    if (nq == 0) return ORB_OK;
+    const int nt = target->n;
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, grid_bytes(target) + pad(nq) + 7 * pad((size_t)nq * 4) + pad((size_t)nq * 32) + pad((size_t)target->n_levels * 4) +
+                                   work_small_bytes(nq, nt), work_scratch_bytes(nq, nt)))) return rc;
+    DevGrid G;
+    if ((rc = upload_grid(A, target, &G))) return rc;
+    G.blocked = nullptr;                                                // nothing is pre-claimed and nothing claims in these searches
+    const u8 *d_active, *d_desc;
+    const float *d_u, *d_v, *d_r, *d_ur = nullptr;
+    const int *d_minL, *d_maxL;
+    if ((rc = upload(A, active, (size_t)nq, &d_active))) return rc;
+    if ((rc = upload(A, u, (size_t)nq, &d_u))) return rc;
+    if ((rc = upload(A, v, (size_t)nq, &d_v))) return rc;
+    if ((rc = upload(A, r, (size_t)nq, &d_r))) return rc;
+    if ((rc = upload(A, min_level, (size_t)nq, &d_minL))) return rc;
+    if ((rc = upload(A, max_level, (size_t)nq, &d_maxL))) return rc;
+    if (ur) {
+        if ((rc = upload(A, ur, (size_t)nq, &d_ur))) return rc;
+        if ((rc = upload(A, inv_level_sigma2, (size_t)target->n_levels, &G.inv_sigma2))) return rc;
+    } else {
+        G.uright = nullptr;
+    }
+    if ((rc = upload(A, desc, (size_t)nq * 32, &d_desc))) return rc;
+    if ((rc = A.flush())) return rc;
+    WinWork w;
+    take_work(A, nq, nt, &w);
+    k_win_explicit<<<orb_div_up(nq, 256), 256, 0, A.stream>>>(nq, d_active, d_u, d_v, d_r, d_minL, d_maxL, d_ur, ur ? WIN_CHI2 : 0, w.win);
+    if ((rc = run_search(A, G, w, d_desc, nullptr, nq, MODE_BEST, th_dist, 0.f, 0))) return rc;
+    if ((rc = A.fetch(best_idx, w.match, (size_t)nq))) return rc;
+    return A.finish();
 }

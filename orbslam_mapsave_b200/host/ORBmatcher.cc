@@ -311,6 +311,34 @@ inline void minus_rt_t(const float* T, float* out) {
 inline float norm3(const float* p) { return (float)std::sqrt((double)p[0] * p[0] + (double)p[1] * p[1] + (double)p[2] * p[2]); }
 inline int clamp_level(int l, int n) { return l < 0 ? 0 : (l >= n ? n - 1 : l); }   // the fork indexes mvScaleFactors unclamped (UB)
 
+// the KeyFrame side: mGrid is not public, but it is Frame::AssignFeaturesToGrid of mvKeysUn (src/KeyFrame.cc:48-53), rebuilt here
+void snapshot_keyframe_grid(KeyFrame* pKF, GridSide& g) {
+    const int n = pKF->N;
+    g.desc.resize((size_t)n * 32);
+    g.x.resize(n); g.y.resize(n); g.angle.resize(n); g.octave.resize(n); g.uright.resize(n); g.blocked.assign(n, 0);
+    std::vector<std::vector<int> > grid((size_t)pKF->mnGridCols * pKF->mnGridRows);
+    for (int i = 0; i < n; i++) {
+        std::memcpy(&g.desc[(size_t)i * 32], pKF->mDescriptors.ptr(i), 32);
+        const cv::KeyPoint& kp = pKF->mvKeysUn[i];
+        g.x[i] = kp.pt.x; g.y[i] = kp.pt.y; g.angle[i] = kp.angle; g.octave[i] = kp.octave;
+        g.uright[i] = pKF->mvuRight.empty() ? -1.0f : pKF->mvuRight[i];
+        const int posX = (int)round((kp.pt.x - pKF->mnMinX) * pKF->mfGridElementWidthInv);
+        const int posY = (int)round((kp.pt.y - pKF->mnMinY) * pKF->mfGridElementHeightInv);
+        if (posX < 0 || posX >= pKF->mnGridCols || posY < 0 || posY >= pKF->mnGridRows) continue;
+        grid[(size_t)posX * pKF->mnGridRows + posY].push_back(i);
+    }
+    g.off.assign(1, 0); g.feat.clear();
+    for (size_t c = 0; c < grid.size(); c++) { g.feat.insert(g.feat.end(), grid[c].begin(), grid[c].end()); g.off.push_back((int)g.feat.size()); }
+    std::memset(&g.view, 0, sizeof(g.view));
+    g.view.n = n; g.view.desc = g.desc.data(); g.view.x = g.x.data(); g.view.y = g.y.data(); g.view.octave = g.octave.data();
+    g.view.angle = g.angle.data(); g.view.uright = g.uright.data(); g.view.blocked = g.blocked.data();
+    g.view.grid_cols = pKF->mnGridCols; g.view.grid_rows = pKF->mnGridRows;
+    g.view.min_x = (float)pKF->mnMinX; g.view.min_y = (float)pKF->mnMinY; g.view.max_x = (float)pKF->mnMaxX; g.view.max_y = (float)pKF->mnMaxY;
+    g.view.inv_w = pKF->mfGridElementWidthInv; g.view.inv_h = pKF->mfGridElementHeightInv;
+    g.view.cell_offsets = g.off.data(); g.view.cell_features = g.feat.data();
+    g.view.scale_factors = pKF->mvScaleFactors.data(); g.view.n_levels = (int)pKF->mvScaleFactors.size();
+}
+
 struct Windows {
     std::vector<unsigned char> active, desc;
     std::vector<float> u, v, r, angle;
@@ -381,32 +409,10 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 4; c++) T[4 * r + c] = Scw.at<float>(r, c) * inv;
     minus_rt_t(T, Ow);
-    // the KeyFrame side: mGrid is not public, but it is Frame::AssignFeaturesToGrid of mvKeysUn (src/KeyFrame.cc:48-53), rebuilt here
     const int n = pKF->N;
     GridSide g;
-    g.desc.resize((size_t)n * 32);
-    g.x.resize(n); g.y.resize(n); g.angle.resize(n); g.octave.resize(n); g.blocked.assign(n, 0);
-    std::vector<std::vector<int> > grid((size_t)pKF->mnGridCols * pKF->mnGridRows);
-    for (int i = 0; i < n; i++) {
-        std::memcpy(&g.desc[(size_t)i * 32], pKF->mDescriptors.ptr(i), 32);
-        const cv::KeyPoint& kp = pKF->mvKeysUn[i];
-        g.x[i] = kp.pt.x; g.y[i] = kp.pt.y; g.angle[i] = kp.angle; g.octave[i] = kp.octave;
-        g.blocked[i] = vpMatched[i] ? 1 : 0;                                                                 // :375-376
-        const int posX = (int)round((kp.pt.x - pKF->mnMinX) * pKF->mfGridElementWidthInv);
-        const int posY = (int)round((kp.pt.y - pKF->mnMinY) * pKF->mfGridElementHeightInv);
-        if (posX < 0 || posX >= pKF->mnGridCols || posY < 0 || posY >= pKF->mnGridRows) continue;
-        grid[(size_t)posX * pKF->mnGridRows + posY].push_back(i);
-    }
-    g.off.assign(1, 0);
-    for (size_t c = 0; c < grid.size(); c++) { g.feat.insert(g.feat.end(), grid[c].begin(), grid[c].end()); g.off.push_back((int)g.feat.size()); }
-    std::memset(&g.view, 0, sizeof(g.view));
-    g.view.n = n; g.view.desc = g.desc.data(); g.view.x = g.x.data(); g.view.y = g.y.data(); g.view.octave = g.octave.data();
-    g.view.angle = g.angle.data(); g.view.blocked = g.blocked.data();
-    g.view.grid_cols = pKF->mnGridCols; g.view.grid_rows = pKF->mnGridRows;
-    g.view.min_x = (float)pKF->mnMinX; g.view.min_y = (float)pKF->mnMinY; g.view.max_x = (float)pKF->mnMaxX; g.view.max_y = (float)pKF->mnMaxY;
-    g.view.inv_w = pKF->mfGridElementWidthInv; g.view.inv_h = pKF->mfGridElementHeightInv;
-    g.view.cell_offsets = g.off.data(); g.view.cell_features = g.feat.data();
-    g.view.scale_factors = pKF->mvScaleFactors.data(); g.view.n_levels = (int)pKF->mvScaleFactors.size();
+    snapshot_keyframe_grid(pKF, g);
+    for (int i = 0; i < n; i++) g.blocked[i] = vpMatched[i] ? 1 : 0;                                          // :375-376
 
     std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
     spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
@@ -447,6 +453,218 @@ int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector
     for (int j = 0; j < n; j++)
         if (owner[j] >= 0) vpMatched[j] = vpPoints[owner[j]];
     return nmatches;
+}
+
+
+// ---- SearchBySim3 and Fuse: the candidate loops do not depend on earlier iterations, so all points are searched at once on the
+// device (orbm_search_windows_best) and the reference's bookkeeping / map updates run afterwards on the host, in order -------------
+namespace {
+// scale a 3x3 by a scalar the way `s*R` / `(1.0/s)*R.t()` do: cv::Mat::convertTo scales CV_32F data by (float)alpha
+// (cv2 4.13, probed through cv2.normalize; same convention as sRcw/scw above)
+inline float scaled(float v, double alpha) { return v * (float)alpha; }
+
+// one direction of SearchBySim3 (ORBmatcher.cc:1150-1219 / 1222-1299): points of `from` into `to`
+void sim3_direction(KeyFrame* to, const std::vector<MapPoint*>& pts, const std::vector<bool>& already, const float* Rfw, const float* tfw,
+                    const float* sR, const float* t, float th, std::vector<int>& vnMatch, int device, int* status) {
+    const int n = (int)pts.size(), nlev = (int)to->mvScaleFactors.size();
+    Windows w(n);
+    for (int i = 0; i < n; i++) {
+        MapPoint* pMP = pts[i];
+        if (!pMP || already[i]) continue;
+        if (pMP->isBad()) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float X[3] = {p3Dw.at<float>(0), p3Dw.at<float>(1), p3Dw.at<float>(2)};
+        float T1[12], T2[12], c1[3], c2[3];
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) { T1[4 * r + c] = Rfw[3 * r + c]; T2[4 * r + c] = sR[3 * r + c]; } T1[4 * r + 3] = tfw[r]; T2[4 * r + 3] = t[r]; }
+        rt_apply(T1, X, c1);
+        rt_apply(T2, c1, c2);
+        if (c2[2] < 0.0) continue;
+        const float invz = 1.0 / c2[2];
+        const float x = c2[0] * invz, y = c2[1] * invz;
+        const float u = to->fx * x + to->cx, v = to->fy * y + to->cy;
+        if (!to->IsInImage(u, v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        const float dist3D = norm3(c2);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = clamp_level(pMP->PredictScale(dist3D, to->mfLogScaleFactor), nlev);
+        w.active[i] = 1; w.u[i] = u; w.v[i] = v;
+        w.r[i] = th * to->mvScaleFactors[nPredictedLevel];
+        w.minL[i] = nPredictedLevel - 1; w.maxL[i] = nPredictedLevel;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&w.desc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    GridSide g;
+    snapshot_keyframe_grid(to, g);
+    vnMatch.assign(n > 0 ? n : 1, -1);
+    *status = orbm_search_windows_best(&g.view, n, w.active.data(), w.u.data(), w.v.data(), w.r.data(), w.minL.data(), w.maxL.data(),
+                                       w.desc.data(), NULL, NULL, ORBM_TH_HIGH, vnMatch.data(), device);
+    vnMatch.resize(n);
+}
+}  // namespace
+
+int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                             const cv::Mat& t12, const float th) {
+    cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    // sR12 = s12*R12 ; sR21 = (1.0/s12)*R12.t() ; t21 = -sR21*t12 (:1123-1126)
+    float r1w[9], r2w[9], T1w[3], T2w[3], sR12[9], sR21[9], T12[3], T21[3];
+    for (int r = 0; r < 3; r++) {
+        T1w[r] = t1w.at<float>(r); T2w[r] = t2w.at<float>(r); T12[r] = t12.at<float>(r);
+        for (int c = 0; c < 3; c++) {
+            r1w[3 * r + c] = R1w.at<float>(r, c); r2w[3 * r + c] = R2w.at<float>(r, c);
+            sR12[3 * r + c] = scaled(R12.at<float>(r, c), (double)s12);
+            sR21[3 * r + c] = scaled(R12.at<float>(c, r), 1.0 / s12);
+        }
+    }
+    for (int r = 0; r < 3; r++) T21[r] = -((sR21[3 * r] * T12[0] + sR21[3 * r + 1] * T12[1]) + sR21[3 * r + 2] * T12[2]);
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size();
+    const std::vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N2 = (int)vpMapPoints2.size();
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {
+        MapPoint* pMP = vpMatches12[i];
+        if (pMP) {
+            vbAlreadyMatched1[i] = true;
+            int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+    }
+    std::vector<int> vnMatch1, vnMatch2;
+    int st = ORB_OK;
+    sim3_direction(pKF2, vpMapPoints1, vbAlreadyMatched1, r1w, T1w, sR21, T21, th, vnMatch1, g_device, &st);
+    report(st);
+    if (st != ORB_OK) return 0;
+    sim3_direction(pKF1, vpMapPoints2, vbAlreadyMatched2, r2w, T2w, sR12, T12, th, vnMatch2, g_device, &st);
+    report(st);
+    if (st != ORB_OK) return 0;
+    int nFound = 0;                                                    // check agreement (:1301-1326)
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0) {
+            const int idx1 = vnMatch2[idx2];
+            if (idx1 == i1) { vpMatches12[i1] = vpMapPoints2[idx2]; nFound++; }
+        }
+    }
+    return nFound;
+}
+
+namespace {
+// the projection part shared by both Fuse overloads (:846-893, 1012-1051); T = [Rcw|tcw] row-major 3x4
+void fuse_windows(KeyFrame* pKF, const float* T, const float* Ow, const std::vector<MapPoint*>& pts, const std::vector<unsigned char>& skip,
+                  float th, bool stereoGate, Windows& w, std::vector<float>& ur) {
+    const int n = (int)pts.size(), nlev = (int)pKF->mvScaleFactors.size();
+    ur.assign(n > 0 ? n : 1, 0.f);
+    for (int i = 0; i < n; i++) {
+        MapPoint* pMP = pts[i];
+        if (!pMP || skip[i]) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float X[3] = {p3Dw.at<float>(0), p3Dw.at<float>(1), p3Dw.at<float>(2)};
+        float p3Dc[3];
+        rt_apply(T, X, p3Dc);
+        if (p3Dc[2] < 0.0f) continue;
+        const float invz = stereoGate ? 1 / p3Dc[2] : (float)(1.0 / p3Dc[2]);       // `1/z` (:855) vs `1.0/z` (:1023)
+        const float x = p3Dc[0] * invz, y = p3Dc[1] * invz;
+        const float u = pKF->fx * x + pKF->cx, v = pKF->fy * y + pKF->cy;
+        if (!pKF->IsInImage(u, v)) continue;
+        ur[i] = u - pKF->mbf * invz;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        const float PO[3] = {X[0] - Ow[0], X[1] - Ow[1], X[2] - Ow[2]};
+        const float dist3D = norm3(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const cv::Mat Pn = pMP->GetNormal();
+        const double dot = (double)PO[0] * Pn.at<float>(0) + (double)PO[1] * Pn.at<float>(1) + (double)PO[2] * Pn.at<float>(2);
+        if (dot < 0.5 * dist3D) continue;
+        const int nPredictedLevel = clamp_level(pMP->PredictScale(dist3D, pKF->mfLogScaleFactor), nlev);
+        w.active[i] = 1; w.u[i] = u; w.v[i] = v;
+        w.r[i] = th * pKF->mvScaleFactors[nPredictedLevel];
+        w.minL[i] = nPredictedLevel - 1; w.maxL[i] = nPredictedLevel;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&w.desc[(size_t)i * 32], d.ptr(0), 32);
+    }
+}
+}  // namespace
+
+// Precondition inherited from the callers (LocalMapping::SearchInNeighbors de-duplicates with mnFuseCandidateForKF,
+// LoopClosing::SearchAndFuse passes a set): a MapPoint appears once in vpMapPoints, so the state snapshotted before the device
+// search (position, descriptor, normal) is the state the reference would read at that point's turn; isBad() / IsInKeyFrame(),
+// which earlier replacements do change, are re-evaluated at the point's turn below.
+int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Owm = pKF->GetCameraCenter();
+    float T[12], Ow[3];
+    for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T[4 * r + c] = Rcw.at<float>(r, c); T[4 * r + 3] = tcw.at<float>(r); Ow[r] = Owm.at<float>(r); }
+    const int nMPs = (int)vpMapPoints.size();
+    std::vector<unsigned char> skip(nMPs > 0 ? nMPs : 1, 0);
+    for (int i = 0; i < nMPs; i++) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (pMP && (pMP->isBad() || pMP->IsInKeyFrame(pKF))) skip[i] = 1;           // both only ever turn true during Fuse
+    }
+    Windows w(nMPs);
+    std::vector<float> ur;
+    fuse_windows(pKF, T, Ow, vpMapPoints, skip, th, true, w, ur);
+    GridSide g;
+    snapshot_keyframe_grid(pKF, g);
+    std::vector<int> best(nMPs > 0 ? nMPs : 1, -1);
+    report(orbm_search_windows_best(&g.view, nMPs, w.active.data(), w.u.data(), w.v.data(), w.r.data(), w.minL.data(), w.maxL.data(),
+                                    w.desc.data(), ur.data(), pKF->mvInvLevelSigma2.data(), TH_LOW, best.data(), g_device));
+    if (g_status != ORB_OK) return 0;
+    int nFused = 0;
+    for (int i = 0; i < nMPs; i++) {                                                 // :952-971, in the reference's order
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+        if (best[i] < 0) continue;
+        const int bestIdx = best[i];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx);
+            pKF->AddMapPoint(pMP, bestIdx);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint) {
+    const float s0 = Scw.at<float>(0, 0), s1 = Scw.at<float>(0, 1), s2 = Scw.at<float>(0, 2);
+    const float scw = (float)std::sqrt((double)s0 * s0 + (double)s1 * s1 + (double)s2 * s2);       // :983-987
+    const float inv = (float)(1.0 / (double)scw);
+    float T[12], Ow[3];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[4 * r + c] = Scw.at<float>(r, c) * inv;
+    minus_rt_t(T, Ow);
+    const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();
+    const int nPoints = (int)vpPoints.size();
+    std::vector<unsigned char> skip(nPoints > 0 ? nPoints : 1, 0);
+    for (int i = 0; i < nPoints; i++)
+        if (vpPoints[i]->isBad() || spAlreadyFound.count(vpPoints[i])) skip[i] = 1;               // :1002-1003 (this overload mutates neither)
+    Windows w(nPoints);
+    std::vector<float> ur;
+    fuse_windows(pKF, T, Ow, vpPoints, skip, th, false, w, ur);
+    GridSide g;
+    snapshot_keyframe_grid(pKF, g);
+    std::vector<int> best(nPoints > 0 ? nPoints : 1, -1);
+    report(orbm_search_windows_best(&g.view, nPoints, w.active.data(), w.u.data(), w.v.data(), w.r.data(), w.minL.data(), w.maxL.data(),
+                                    w.desc.data(), NULL, NULL, TH_LOW, best.data(), g_device));
+    if (g_status != ORB_OK) return 0;
+    int nFused = 0;
+    for (int iMP = 0; iMP < nPoints; iMP++) {                                        // :1083-1099
+        if (best[iMP] < 0) continue;
+        MapPoint* pMP = vpPoints[iMP];
+        MapPoint* pMPinKF = pKF->GetMapPoint(best[iMP]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[iMP] = pMPinKF;
+        } else {
+            pMP->AddObservation(pKF, best[iMP]);
+            pKF->AddMapPoint(pMP, best[iMP]);
+        }
+        nFused++;
+    }
+    return nFused;
 }
 
 }  // namespace ORB_SLAM2

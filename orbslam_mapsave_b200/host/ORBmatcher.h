@@ -1,8 +1,8 @@
 // ORBmatcher.h — drop-in for the hot-path members of the reference's include/ORBmatcher.h:37-101:
 // DescriptorDistance, both SearchByBoW overloads, SearchForTriangulation (+ the constants), and — first "next" row of
 // SURVEY.md §8f — the window searches SearchByProjection(Frame, MapPoints), SearchByProjection(CurrentFrame, LastFrame) and
-// SearchForInitialization and the two projection searches of relocalisation / loop closing.  Same signatures; bodies marshal
-// to the C ABI of include/orb_b200.h.  Fuse (x2) and SearchBySim3 stay in the reference's own ORBmatcher.cc — see INTEGRATION.md.
+// SearchForInitialization, the two projection searches of relocalisation / loop closing, SearchBySim3 and Fuse x2.  Same signatures; bodies marshal
+// to the C ABI of include/orb_b200.h.  SearchBySim3 and Fuse (x2) search on the device and apply their map updates on the host.
 #ifndef ORB_B200_ORBMATCHER_H
 #define ORB_B200_ORBMATCHER_H
 
@@ -37,6 +37,14 @@ public:
     // Project MapPoints using a Similarity Transformation and search matches.  Used in loop detection (Loop Closing)
     // (reference :60, src/ORBmatcher.cc:293-406)
     int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th);
+    // Search matches between MapPoints seen in KF1 and KF2 transforming by a Sim3 [s12*R12|t12]
+    // (reference :77, src/ORBmatcher.cc:1105-1329)
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                     const cv::Mat& t12, const float th);
+    // Project MapPoints into KeyFrame and search for duplicated MapPoints (reference :80, src/ORBmatcher.cc:828-972)
+    int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th = 3.0);
+    // Project MapPoints into KeyFrame using a given Sim3 and search for duplicated MapPoints (reference :83, :974-1103)
+    int Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint);
     // Matching for the Map Initialization (only used in the monocular case) (reference :69, src/ORBmatcher.cc:408-523)
     int SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
                                 int windowSize = 10);

@@ -48,6 +48,7 @@ public:
 
 namespace ORB_SLAM2 {
 
+class KeyFrame;
 class MapPoint {
 public:
     bool isBad() { return mbBad; }
@@ -66,6 +67,12 @@ public:
         const float ratio = mfMaxDistance / currentDist;
         return (int)std::ceil(std::log(ratio) / logScaleFactor);
     }
+    // observations (include/MapPoint.h:61-70; bodies after KeyFrame below, as in src/MapPoint.cc:93-116, 226-283)
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }
+    int GetIndexInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) ? (int)mObservations[pKF] : -1; }
+    inline void AddObservation(KeyFrame* pKF, size_t idx);
+    inline void Replace(MapPoint* pMP);
+    std::map<KeyFrame*, size_t> mObservations;
     bool mbBad = false;
     int nObs = 0;
     float mfMinDistance = 0, mfMaxDistance = 0;
@@ -110,10 +117,38 @@ public:
     cv::Mat Ow, Rcw, tcw;                               // 3x1, 3x3, 3x1 CV_32F
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }                   // src/KeyFrame.cc:620-624
+    void ReplaceMapPointMatch(const size_t& idx, MapPoint* pMP) { mvpMapPoints[idx] = pMP; }          // :640-643
+    void EraseMapPointMatch(const size_t& idx) { mvpMapPoints[idx] = static_cast<MapPoint*>(NULL); }  // :626-630
+    std::set<MapPoint*> GetMapPoints() {                                                              // :645-659
+        std::set<MapPoint*> s;
+        for (size_t i = 0; i < mvpMapPoints.size(); i++)
+            if (mvpMapPoints[i] && !mvpMapPoints[i]->isBad()) s.insert(mvpMapPoints[i]);
+        return s;
+    }
+    std::vector<float> mvInvLevelSigma2;
+    float mbf = 0;
     cv::Mat GetCameraCenter() { return Ow.clone(); }
     cv::Mat GetRotation() { return Rcw.clone(); }
     cv::Mat GetTranslation() { return tcw.clone(); }
 };
+
+inline void MapPoint::AddObservation(KeyFrame* pKF, size_t idx) {
+    if (mObservations.count(pKF)) return;
+    mObservations[pKF] = idx;
+    if (pKF->mvuRight[idx] >= 0) nObs += 2; else nObs++;
+}
+inline void MapPoint::Replace(MapPoint* pMP) {
+    if (pMP == this) return;
+    std::map<KeyFrame*, size_t> obs = mObservations;
+    mObservations.clear();
+    mbBad = true;
+    for (std::map<KeyFrame*, size_t>::iterator mit = obs.begin(); mit != obs.end(); ++mit) {
+        KeyFrame* pKF = mit->first;
+        if (!pMP->IsInKeyFrame(pKF)) { pKF->ReplaceMapPointMatch(mit->second, pMP); pMP->AddObservation(pKF, mit->second); }
+        else pKF->EraseMapPointMatch(mit->second);
+    }
+}
 
 }  // namespace ORB_SLAM2
 #endif

@@ -201,6 +201,20 @@ class ORBmatcher:
                                                   int(ori), capi._p(owner), C.byref(n), self.device))
         return n.value, owner[:target.n]
 
+    def SearchWindowsBest(self, target, active, u, v, r, min_level, max_level, desc, ur=None, inv_level_sigma2=None, th_dist=capi.TH_LOW):
+        """Independent window search (SearchBySim3 / the candidate loops of Fuse, src/ORBmatcher.cc:828-1329): per query the
+        nearest feature in its window, -1 if none within th_dist; with ur + inv_level_sigma2 Fuse's chi-square gate applies."""
+        f32 = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        active, desc = np.ascontiguousarray(active, np.uint8), np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        u, v, r, ur, is2, min_level, max_level = f32(u), f32(v), f32(r), f32(ur), f32(inv_level_sigma2), i32(min_level), i32(max_level)
+        g = target.c()
+        best = np.zeros(max(len(active), 1), np.int32)
+        capi.check(capi.lib().orbm_search_windows_best(C.byref(g), len(active), capi._p(active), capi._p(u), capi._p(v), capi._p(r),
+                                                       capi._p(min_level), capi._p(max_level), capi._p(desc), capi._p(ur), capi._p(is2),
+                                                       int(th_dist), capi._p(best), self.device))
+        return best[:len(active)]
+
     @staticmethod
     def ComputeThreeMaxima(histo, device=0):
         histo = np.ascontiguousarray(histo, np.int32)

@@ -420,6 +420,108 @@ static int run_stereo(int argc, char** argv) {
     return 0;
 }
 
+// driver fuse <in.bin> <out.bin>: Fuse (LocalMapping::SearchInNeighbors), Fuse with a similarity (LoopClosing::SearchAndFuse) and
+// SearchBySim3 (LoopClosing::ComputeSim3) on stand-in KeyFrame / MapPoint objects; the final object graph is written back.
+static void build_keyframe(Reader& r, KeyFrame& kf) {
+    Frame* F = new Frame();
+    build_frame(r, *F);
+    kf.N = F->N; kf.mDescriptors = F->mDescriptors; kf.mvKeysUn = F->mvKeysUn; kf.mvKeys = F->mvKeys; kf.mvuRight = F->mvuRight;
+    kf.mvScaleFactors = F->mvScaleFactors;
+    kf.mnMinX = (int)F->mnMinX; kf.mnMinY = (int)F->mnMinY; kf.mnMaxX = (int)F->mnMaxX; kf.mnMaxY = (int)F->mnMaxY;
+    kf.mfGridElementWidthInv = F->mfGridElementWidthInv; kf.mfGridElementHeightInv = F->mfGridElementHeightInv;
+    kf.mvpMapPoints.assign(kf.N, (MapPoint*)NULL);
+    std::vector<float> K = r.arr<float>(6);
+    kf.fx = K[0]; kf.fy = K[1]; kf.cx = K[2]; kf.cy = K[3]; kf.mbf = K[4]; kf.mfLogScaleFactor = K[5];
+    kf.mvInvLevelSigma2 = r.arr<float>(kf.mvScaleFactors.size());
+    std::vector<float> T = r.arr<float>(12), Ow = r.arr<float>(3);
+    kf.Rcw = cv::Mat(3, 3, CV_32F); kf.tcw = cv::Mat(3, 1, CV_32F); kf.Ow = cv::Mat(3, 1, CV_32F);
+    for (int i = 0; i < 3; i++) { kf.tcw.at<float>(i) = T[4 * i + 3]; kf.Ow.at<float>(i) = Ow[i]; for (int j = 0; j < 3; j++) kf.Rcw.at<float>(i, j) = T[4 * i + j]; }
+    delete F;
+}
+struct PointSet {
+    std::vector<MapPoint> pool;
+    std::vector<unsigned char> state;
+    void load(Reader& r) {
+        const int n = r.get<int>();
+        state = r.arr<unsigned char>(n);
+        std::vector<int> nobs = r.arr<int>(n);
+        std::vector<unsigned char> d = r.arr<unsigned char>((size_t)n * 32);
+        std::vector<float> world = r.arr<float>((size_t)n * 3), normal = r.arr<float>((size_t)n * 3), mfmax = r.arr<float>(n), mfmin = r.arr<float>(n);
+        pool.resize(n);
+        for (int i = 0; i < n; i++) {
+            fill_point(pool[i], &world[3 * (size_t)i], mfmax[i], mfmin[i], &normal[3 * (size_t)i], &d[(size_t)i * 32]);
+            pool[i].mbBad = state[i] == 2; pool[i].nObs = nobs[i];
+        }
+    }
+};
+static int encode(MapPoint* p, PointSet& kfp, PointSet& cand) {
+    if (!p) return -1;
+    if (!kfp.pool.empty() && p >= &kfp.pool[0] && p <= &kfp.pool.back()) return (int)(p - &kfp.pool[0]);
+    if (!cand.pool.empty() && p >= &cand.pool[0] && p <= &cand.pool.back()) return 100000 + (int)(p - &cand.pool[0]);
+    return -2;
+}
+static void attach_kf_points(KeyFrame& kf, PointSet& kfp) {           // state 1/2: the KeyFrame observes the point at that feature
+    for (int j = 0; j < kf.N; j++)
+        if (kfp.state[j]) { kf.mvpMapPoints[j] = &kfp.pool[j]; kfp.pool[j].mObservations[&kf] = j; }
+}
+static void dump_state(std::ofstream& out, KeyFrame& kf, PointSet& kfp, PointSet& cand) {
+    std::vector<int> ptr(kf.N);
+    for (int j = 0; j < kf.N; j++) ptr[j] = encode(kf.mvpMapPoints[j], kfp, cand);
+    put(out, ptr.data(), ptr.size());
+    for (PointSet* ps : {&kfp, &cand})
+        for (size_t i = 0; i < ps->pool.size(); i++) { const int v[2] = {ps->pool[i].mbBad ? 1 : 0, ps->pool[i].nObs}; put(out, v, 2); }
+}
+static int run_fuse(int argc, char** argv) {
+    if (argc < 4) return 2;
+    Reader r; r.buf = slurp(argv[2]);
+    std::ofstream out(argv[3], std::ios::binary);
+    ORBmatcher m(0.8f, true);
+    for (int variant = 0; variant < 2; variant++) {
+        KeyFrame kf;
+        build_keyframe(r, kf);
+        PointSet kfp, cand;
+        kfp.load(r); cand.load(r);
+        attach_kf_points(kf, kfp);
+        const float th = r.get<float>();
+        std::vector<int> inKfAt = r.arr<int>(cand.pool.size());       // state 3: the candidate already sits in the KeyFrame at this feature
+        std::vector<MapPoint*> vp(cand.pool.size());
+        for (size_t i = 0; i < cand.pool.size(); i++) {
+            vp[i] = (variant == 0 && cand.state[i] == 0) ? NULL : &cand.pool[i];
+            if (cand.state[i] == 3) { cand.pool[i].mObservations[&kf] = inKfAt[i]; kf.mvpMapPoints[inKfAt[i]] = &cand.pool[i]; }
+        }
+        int n;
+        if (variant == 0) n = m.Fuse(&kf, vp, th);
+        else {
+            cv::Mat Scw = mat_from(r.arr<float>(16), 4, 4);
+            std::vector<MapPoint*> rep(vp.size(), (MapPoint*)NULL);
+            n = m.Fuse(&kf, Scw, vp, th, rep);
+            std::vector<int> e(rep.size());
+            for (size_t i = 0; i < rep.size(); i++) e[i] = encode(rep[i], kfp, cand);
+            put(out, e.data(), e.size());
+        }
+        put(out, &n, 1);
+        dump_state(out, kf, kfp, cand);
+    }
+    {   // SearchBySim3
+        KeyFrame kf1, kf2;
+        build_keyframe(r, kf1); build_keyframe(r, kf2);
+        PointSet p1, p2;
+        p1.load(r); p2.load(r);
+        attach_kf_points(kf1, p1); attach_kf_points(kf2, p2);
+        const float s12 = r.get<float>(), th = r.get<float>();
+        cv::Mat R12 = mat_from(r.arr<float>(9), 3, 3), t12 = mat_from(r.arr<float>(3), 3, 1);
+        std::vector<int> pre = r.arr<int>(kf1.N);                      // vpMatches12 on entry: index of a KF2 feature's point, or -1
+        std::vector<MapPoint*> vpMatches12(kf1.N, (MapPoint*)NULL);
+        for (int i = 0; i < kf1.N; i++) if (pre[i] >= 0) vpMatches12[i] = &p2.pool[pre[i]];
+        const int n = m.SearchBySim3(&kf1, &kf2, vpMatches12, s12, R12, t12, th);
+        put(out, &n, 1);
+        std::vector<int> e(kf1.N);
+        for (int i = 0; i < kf1.N; i++) e[i] = vpMatches12[i] ? (int)(vpMatches12[i] - &p2.pool[0]) : -1;
+        put(out, e.data(), e.size());
+    }
+    return ORBmatcher::LastStatus() == 0 ? 0 : 4;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
     if (!strcmp(argv[1], "bow")) return run_bow(argc, argv);
@@ -428,5 +530,6 @@ int main(int argc, char** argv) {
     if (!strcmp(argv[1], "project")) return run_project(argc, argv);
     if (!strcmp(argv[1], "project2")) return run_project2(argc, argv);
     if (!strcmp(argv[1], "stereo")) return run_stereo(argc, argv);
+    if (!strcmp(argv[1], "fuse")) return run_fuse(argc, argv);
     return 2;
 }

@@ -151,3 +151,34 @@ def kf_points_for(fa, n_pts, rng, fx=520.0, fy=520.0, cx=320.0, cy=240.0, sim_sc
     state = rng.choice(np.array([0, 1, 1, 1, 1, 1, 2, 3], np.uint8), n_pts)       # 0 none, 1 good, 2 bad, 3 already found
     return dict(T=T, S=S, fx=fx, fy=fy, cx=cx, cy=cy, world=world, mf_max=mf_max, mf_min=mf_min, normal=normal.astype(np.float32),
                 desc=desc, angle=angle, state=state)
+
+
+def points_for_transform(fa, n_pts, rng, A, b, dist_from_camera, fx=520.0, fy=520.0, cx=320.0, cy=240.0, tgt=None):
+    """World points P with A @ P + b landing (through K) near features of `fa`; scale-invariance distances consistent with the
+    distance the search will measure (|A P + b| for SearchBySim3, |P - Ow| otherwise)."""
+    n = len(fa["x"])
+    if tgt is None:
+        tgt = rng.integers(0, n, n_pts)
+    z = rng.uniform(1.0, 8.0, n_pts)
+    u = fa["x"][tgt].astype(np.float64) + rng.normal(0, 1.5, n_pts)
+    v = fa["y"][tgt].astype(np.float64) + rng.normal(0, 1.5, n_pts)
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    pc[rng.random(n_pts) < 0.03, 2] *= -1
+    world = np.linalg.solve(A.astype(np.float64), (pc - b.astype(np.float64)).T).T.astype(np.float32)
+    if dist_from_camera:
+        dist = np.linalg.norm(pc, axis=1)
+        PO = pc
+    else:
+        sc = np.sqrt((A[0].astype(np.float64) ** 2).sum())
+        Rn, tn = A.astype(np.float64) / sc, b.astype(np.float64) / sc
+        PO = world.astype(np.float64) - (-Rn.T @ tn)
+        dist = np.linalg.norm(PO, axis=1)
+    lvl = np.clip(fa["octave"][tgt] + rng.integers(0, 2, n_pts), 0, 7)
+    mf_max = (dist * SCALE[lvl].astype(np.float64) * rng.uniform(0.88, 1.0, n_pts)).astype(np.float32)
+    mf_max[rng.random(n_pts) < 0.05] *= np.float32(0.3)
+    mf_min = (mf_max / SCALE[7]).astype(np.float32)
+    normal = (PO / np.maximum(dist, 1e-9)[:, None])
+    side = rng.random(n_pts) < 0.1
+    normal[side] = np.roll(normal[side], 1, axis=1) * np.array([1, -1, 1])
+    desc = np.stack([flip(fa["desc"][tt], int(rng.choice([0, 3, 10, 30, 49, 50, 51, 95, 100, 101, 128])), rng) for tt in tgt])
+    return dict(world=world, mf_max=mf_max, mf_min=mf_min, normal=normal.astype(np.float32), desc=desc, tgt=tgt)

@@ -324,3 +324,181 @@ def test_cpp_stereo_matches_oracle(tmp_path):
                                         okL, odL, okR, odR, mbf, float(mb))
     assert n == len(okL) and np.array_equal(got_u.view(np.uint32), want_u.view(np.uint32))
     assert np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32)) and (want_u >= 0).sum() > 200
+
+
+class _Pt:
+    def __init__(self, bad, nobs):
+        self.bad, self.nobs, self.obs = bool(bad), int(nobs), {}
+
+
+def _emulate_fuse(variant, uright, kf_ptr, kfp, cand, cand_state, best):
+    """The bookkeeping of Fuse (src/ORBmatcher.cc:952-971 / 1083-1099) and MapPoint::Replace / AddObservation
+    (src/MapPoint.cc:93-116, 226-283) replayed in Python from the oracle's per-point search result."""
+    def add_obs(p, idx):
+        if "kf" in p.obs:
+            return
+        p.obs["kf"] = idx
+        p.nobs += 2 if uright[idx] >= 0 else 1
+
+    def replace(this, other):
+        if this is other:
+            return
+        obs, this.obs, this.bad = this.obs, {}, True
+        for _, idx in obs.items():
+            if "kf" not in other.obs:
+                kf_ptr[idx] = other
+                add_obs(other, idx)
+            else:
+                kf_ptr[idx] = None
+    n, rep = 0, [None] * len(cand)
+    for i, p in enumerate(cand):
+        if variant == 0:
+            if cand_state[i] == 0 or p.bad or "kf" in p.obs:
+                continue
+        if best[i] < 0:
+            continue
+        inkf = kf_ptr[best[i]]
+        if inkf is not None:
+            if not inkf.bad:
+                if variant == 0:
+                    if inkf.nobs > p.nobs:
+                        replace(p, inkf)
+                    else:
+                        replace(inkf, p)
+                else:
+                    rep[i] = inkf
+        else:
+            add_obs(p, best[i])
+            kf_ptr[best[i]] = p
+        n += 1
+    return n, rep
+
+
+def test_cpp_fuse_and_sim3_match_oracle(tmp_path):
+    """ORBmatcher::Fuse (both overloads) and SearchBySim3 through the C++ class: candidate loops on the GPU
+    (orbm_search_windows_best), map updates on the host, against the oracle's searches + a Python replay of the bookkeeping."""
+    import proj_util as pu
+    rng = np.random.default_rng(300)
+    n, npts = 1200, 1500
+    log_sf = float(np.log(np.float32(1.2)))
+    K = np.array([520.0, 520.0, 320.0, 240.0, 40.0, log_sf], np.float32)
+    is2 = (1.0 / (pu.SCALE * pu.SCALE)).astype(np.float32)
+
+    def frame_blob(fa):
+        return (struct.pack("<i", len(fa["x"])) + fa["desc"].tobytes() + fa["x"].tobytes() + fa["y"].tobytes() + fa["angle"].tobytes() +
+                fa["uright"].astype(np.float32).tobytes() + fa["octave"].tobytes() + np.array(fa["bounds"], np.float32).tobytes() + struct.pack("<i", 8) + pu.SCALE.tobytes())
+
+    def kf_blob(fa, T, Ow):
+        return frame_blob(fa) + K.tobytes() + is2.tobytes() + np.ascontiguousarray(T, np.float32).tobytes() + np.ascontiguousarray(Ow, np.float32).tobytes()
+
+    def pts_blob(state, nobs, P):
+        return (struct.pack("<i", len(state)) + state.tobytes() + nobs.astype(np.int32).tobytes() + P["desc"].tobytes() + P["world"].tobytes() +
+                P["normal"].tobytes() + P["mf_max"].tobytes() + P["mf_min"].tobytes())
+
+    def frame(seed_cluster=False):
+        fa = pu.frame_arrays(n, rng, stereo=True, cluster=seed_cluster)
+        fa["x"] = np.clip(fa["x"], 0, 639.5).astype(np.float32)
+        fa["y"] = np.clip(fa["y"], 0, 479.5).astype(np.float32)
+        return fa
+
+    def pose(deg=3.0):
+        R = pu.rot_small(rng, deg).astype(np.float32)
+        t = rng.uniform(-0.1, 0.1, 3).astype(np.float32)
+        return R, t
+
+    blob, expect = b"", []
+    for variant in (0, 1):
+        fa = frame(variant == 1)
+        R, t = pose()
+        T = np.concatenate([R, t[:, None]], 1).astype(np.float32)
+        Ow = (-(R.astype(np.float64).T @ t.astype(np.float64))).astype(np.float32)
+        scale = 1.0 if variant == 0 else 1.7
+        A, b = (T[:, :3] * np.float32(scale)).astype(np.float32), (T[:, 3] * np.float32(scale)).astype(np.float32)
+        S = np.concatenate([A, b[:, None]], 1).astype(np.float32)
+        kstate = rng.choice(np.array([0, 0, 1, 1, 2], np.uint8), n)
+        knobs = rng.integers(1, 6, n)
+        kP = pu.points_for_transform(fa, n, rng, A, b, False)
+        P = pu.points_for_transform(fa, npts, rng, A, b, False)
+        cstate = rng.choice(np.array([0, 1, 1, 1, 1, 2, 3], np.uint8), npts) if variant == 0 else rng.choice(np.array([1, 1, 1, 1, 2, 3], np.uint8), npts)
+        cnobs = rng.integers(0, 6, npts)
+        free = np.nonzero(kstate == 0)[0]
+        in_at = np.full(npts, -1, np.int32)
+        three = np.nonzero(cstate == 3)[0]
+        in_at[three] = rng.choice(free, len(three), replace=False)
+        th = 3.0 if variant == 0 else 4.0
+        blob += kf_blob(fa, T, Ow) + pts_blob(kstate, knobs, kP) + pts_blob(cstate, cnobs, P) + struct.pack("<f", th) + in_at.tobytes()
+        if variant == 1:
+            blob += np.concatenate([S, np.array([[0, 0, 0, 1]], np.float32)], 0).astype(np.float32).tobytes()
+        og = orc.Grid(fa["desc"], fa["x"], fa["y"], fa["octave"], pu.SCALE, fa["bounds"], angle=fa["angle"], uright=fa["uright"])
+        skip = (cstate != 1).astype(np.uint8)
+        best = orc.fuse_search(og, variant, T if variant == 0 else S, Ow if variant == 0 else None, K[0], K[1], K[2], K[3], K[4], np.float32(log_sf),
+                               skip, P["world"], P["mf_max"], P["mf_min"], P["normal"], P["desc"], th, is2)
+        kfp = [_Pt(kstate[j] == 2, knobs[j]) for j in range(n)]
+        cand = [_Pt(cstate[i] == 2, cnobs[i]) for i in range(npts)]
+        kf_ptr = [None] * n
+        for j in range(n):
+            if kstate[j]:
+                kf_ptr[j] = kfp[j]
+                kfp[j].obs["kf"] = j
+        for i in three:
+            cand[i].obs["kf"] = int(in_at[i])
+            kf_ptr[in_at[i]] = cand[i]
+        nf, rep = _emulate_fuse(variant, fa["uright"], kf_ptr, kfp, cand, cstate, best)
+        enc = lambda p: -1 if p is None else (kfp.index(p) if p in kfp else 100000 + cand.index(p))
+        expect.append((nf, [enc(p) for p in rep], [enc(p) for p in kf_ptr], [(int(p.bad), p.nobs) for p in kfp + cand], int((best >= 0).sum())))
+    # SearchBySim3
+    fa1, fa2 = frame(), frame()
+    (Ra, ta), (Rb, tb) = pose(), pose()
+    s12 = np.float32(1.15)
+    R12 = (Ra.astype(np.float64) @ Rb.astype(np.float64).T).astype(np.float32)
+    t12 = (ta.astype(np.float64) - float(s12) * (R12.astype(np.float64) @ tb.astype(np.float64))).astype(np.float32)
+    # the class's own arithmetic for sR12, sR21, t21 (float scaling like cv::Mat::convertTo, float32 left-to-right products)
+    sR12 = (R12 * s12).astype(np.float32)
+    sR21 = (R12.T * np.float32(1.0 / float(s12))).astype(np.float32)
+    t21 = (-((sR21[:, 0] * t12[0] + sR21[:, 1] * t12[1]) + sR21[:, 2] * t12[2])).astype(np.float32)
+    perm = rng.permutation(n)                                  # KF1 feature i <-> KF2 feature perm[i], with a few broken pairs
+    inv = np.argsort(perm)
+    broken = rng.random(n) < 0.15
+    tgt2 = np.where(broken, rng.integers(0, n, n), inv)
+    P1 = pu.points_for_transform(fa2, n, rng, (Rb / s12).astype(np.float32), tb, True, tgt=perm)   # KF1's points land on KF2's features
+    P2 = pu.points_for_transform(fa1, n, rng, (Ra * s12).astype(np.float32), ta, True, tgt=tgt2)
+    st1 = rng.choice(np.array([0, 1, 1, 1, 2], np.uint8), n)
+    st2 = rng.choice(np.array([0, 1, 1, 1, 2], np.uint8), n)
+    pre = np.where((rng.random(n) < 0.1) & (st1 == 1), rng.integers(0, n, n), -1).astype(np.int32)
+    pre[(pre >= 0) & (st2[np.maximum(pre, 0)] == 0)] = -1
+    Tz = lambda R, t: np.concatenate([R, t[:, None]], 1).astype(np.float32)
+    th3 = 7.5
+    blob += kf_blob(fa1, Tz(Ra, ta), np.zeros(3)) + kf_blob(fa2, Tz(Rb, tb), np.zeros(3))
+    blob += pts_blob(st1, np.ones(n), P1) + pts_blob(st2, np.ones(n), P2) + struct.pack("<ff", float(s12), th3) + R12.tobytes() + t12.tobytes() + pre.tobytes()
+    og1 = orc.Grid(fa1["desc"], fa1["x"], fa1["y"], fa1["octave"], pu.SCALE, fa1["bounds"], angle=fa1["angle"], uright=fa1["uright"])
+    og2 = orc.Grid(fa2["desc"], fa2["x"], fa2["y"], fa2["octave"], pu.SCALE, fa2["bounds"], angle=fa2["angle"], uright=fa2["uright"])
+    already1 = pre >= 0
+    already2 = np.zeros(n, bool)
+    already2[pre[pre >= 0]] = True
+    m1 = orc.sim3_direction(og2, Ra, ta, sR21, t21, K[0], K[1], K[2], K[3], np.float32(log_sf), (st1 == 1) & ~already1, P1["world"], P1["mf_max"],
+                            P1["mf_min"], P1["desc"], th3)
+    m2 = orc.sim3_direction(og1, Rb, tb, sR12, t12, K[0], K[1], K[2], K[3], np.float32(log_sf), (st2 == 1) & ~already2, P2["world"], P2["mf_max"],
+                            P2["mf_min"], P2["desc"], th3)
+    want12 = pre.copy()
+    nfound = 0
+    for i1 in range(n):
+        if m1[i1] >= 0 and m2[m1[i1]] == i1:
+            want12[i1] = m1[i1]
+            nfound += 1
+    (tmp_path / "in.bin").write_bytes(blob)
+    subprocess.check_call([_driver(), "fuse", str(tmp_path / "in.bin"), str(tmp_path / "out.bin")])
+    out = (tmp_path / "out.bin").read_bytes()
+    pos = 0
+    for variant in (0, 1):
+        nf, rep, kfptr, pts, nbest = expect[variant]
+        if variant == 1:
+            got = np.frombuffer(out, np.int32, npts, pos); pos += 4 * npts
+            assert np.array_equal(got, np.array(rep, np.int32))
+        (gn,) = struct.unpack_from("<i", out, pos); pos += 4
+        got = np.frombuffer(out, np.int32, n, pos); pos += 4 * n
+        assert gn == nf and np.array_equal(got, np.array(kfptr, np.int32)) and nf > 100, (variant, gn, nf, nbest)
+        got = np.frombuffer(out, np.int32, 2 * (n + npts), pos).reshape(-1, 2); pos += 8 * (n + npts)
+        assert np.array_equal(got, np.array(pts, np.int32))
+    (gn,) = struct.unpack_from("<i", out, pos); pos += 4
+    got = np.frombuffer(out, np.int32, n, pos)
+    assert gn == nfound and np.array_equal(got, want12) and nfound > 50, (gn, nfound)

@@ -118,3 +118,27 @@ def test_search_windows_core(n, nq, seed, cluster, ori, th):
     assert got_n == want_n and np.array_equal(got, want)
     if nq:
         assert (want >= 0).sum() > 200
+
+
+@pytest.mark.parametrize("n,nq,seed,cluster,chi2,th", [(2000, 2500, 70, False, False, 100), (2000, 2500, 71, True, True, 50),
+                                                       (3000, 1500, 72, False, True, 50), (10, 0, 73, False, False, 50)])
+def test_search_windows_best(n, nq, seed, cluster, chi2, th):
+    """orbm_search_windows_best: the independent candidate loops of SearchBySim3 / Fuse, with and without Fuse's chi-square gate."""
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n, rng, stereo=True, cluster=cluster)
+    g, og = pu.make_grids(fa, None, orb, orc)
+    tgt = rng.integers(0, n, nq)
+    desc = np.stack([pu.flip(fa["desc"][t], int(rng.choice([0, 5, 30, 49, 50, 51, 99, 100, 101])), rng) for t in tgt]) if nq else np.zeros((0, 32), np.uint8)
+    u = (fa["x"][tgt] + rng.normal(0, 1.5, nq)).astype(np.float32)
+    v = (fa["y"][tgt] + rng.normal(0, 1.5, nq)).astype(np.float32)
+    lvl = fa["octave"][tgt] + rng.integers(0, 2, nq)
+    r = (rng.choice([3.0, 4.0, 7.5], nq) * np.float32(1.2) ** np.clip(lvl, 0, 7)).astype(np.float32)
+    active = (rng.random(nq) < 0.9).astype(np.uint8)
+    ur = (np.where(fa["uright"][tgt] >= 0, fa["uright"][tgt], u - 10) + rng.normal(0, 1.5, nq)).astype(np.float32) if chi2 else None
+    is2 = (1.0 / (pu.SCALE * pu.SCALE)).astype(np.float32) if chi2 else None
+    args = (active, u, v, r, lvl - 1, lvl, desc, ur, is2)
+    want = orc.search_windows_best(og, *args, th)
+    got = orb.ORBmatcher().SearchWindowsBest(g, *args, th_dist=th)
+    assert np.array_equal(got, want)
+    if nq:
+        assert (want >= 0).sum() > 200
