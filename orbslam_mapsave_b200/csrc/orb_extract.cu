@@ -1134,6 +1134,8 @@ struct orbx_extractor {
     bool fastConst = false;
     long long launches = 0;
     int lastFrames = 0;
+    u8* d_stereo = nullptr;                // scratch of orbx_stereo_matches
+    size_t stereoCap = 0;
     std::mutex mu;
 };
 
@@ -1395,7 +1397,7 @@ extern "C" int orbx_create(orbx_extractor** out, int nfeatures, float scale_fact
 extern "C" void orbx_destroy(orbx_extractor* ex) {
     if (!ex) return;
     cudaSetDevice(ex->device);
-    cudaFree(ex->d_pyr); cudaFree(ex->d_blur);
+    cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_stereo);
     for (int i = 0; i < 2; i++) {
         cudaFree(ex->d_in[i]); cudaFree(ex->d_mask[i]); cudaFree(ex->d_desc[i]); cudaFree(ex->d_kp[i]); cudaFree(ex->d_n[i]);
         if (ex->evH2D[i]) cudaEventDestroy(ex->evH2D[i]);
@@ -1966,8 +1968,13 @@ extern "C" int orbx_stereo_matches(orbx_extractor* left, orbx_extractor* right, 
                  offDR = orb_align_up(offDL + (size_t)n_left * 32, 256), offRI = orb_align_up(offDR + (size_t)std::max(n_right, 1) * 32, 256),
                  offU = orb_align_up(offRI + (size_t)std::max(n_right, 1) * 16, 256), offD = orb_align_up(offU + (size_t)n_left * 4, 256),
                  offS = orb_align_up(offD + (size_t)n_left * 4, 256), total = orb_align_up(offS + (size_t)n_left * 4, 256);
-    u8* d = nullptr;
-    ORB_CUDA_TRY(cudaMallocAsync(&d, total, st));
+    if (total > left->stereoCap) {                                   // grow-only scratch kept in the handle
+        if (left->d_stereo) ORB_CUDA_TRY(cudaFree(left->d_stereo));
+        left->d_stereo = nullptr;
+        left->stereoCap = orb_align_up(total + (total >> 1), 1 << 16);
+        ORB_CUDA_TRY(cudaMalloc(&left->d_stereo, left->stereoCap));
+    }
+    u8* d = left->d_stereo;
     ORB_CUDA_TRY(cudaMemcpyAsync(d + offKL, kp_left, bL, cudaMemcpyHostToDevice, st));
     ORB_CUDA_TRY(cudaMemcpyAsync(d + offDL, desc_left, (size_t)n_left * 32, cudaMemcpyHostToDevice, st));
     if (n_right) {
@@ -1995,7 +2002,6 @@ extern "C" int orbx_stereo_matches(orbx_extractor* left, orbx_extractor* right, 
     ORB_CUDA_TRY(cudaGetLastError());
     ORB_CUDA_TRY(cudaMemcpyAsync(u_right, dU, (size_t)n_left * 4, cudaMemcpyDeviceToHost, st));
     ORB_CUDA_TRY(cudaMemcpyAsync(depth, dD, (size_t)n_left * 4, cudaMemcpyDeviceToHost, st));
-    ORB_CUDA_TRY(cudaFreeAsync(d, st));
     ORB_CUDA_TRY(cudaStreamSynchronize(st));
     return ORB_OK;
 }
