@@ -46,12 +46,14 @@ __global__ void __launch_bounds__(256) k_bow_transform(const int2* __restrict__ 
     const int nid_level = L - levelsup;
     int cur = 0, level = 0, nid = 0;
     bool done = !live;
+    // The record of the current node travels with the descent: every lane loads its child's record together with the child's
+    // descriptor (two independent loads), and the winner's record is shuffled out, so a level costs ONE dependent L2 round trip.
+    int2 rec = done ? make_int2(0, 0) : __ldg(nodeRec + 0);
     while (__any_sync(0xffffffffu, !done)) {
         u32 best = 0xFFFFFFFFu;
-        int c0 = 0;
+        const int c0 = rec.x;
+        int2 crec = make_int2(0, 0);
         if (!done) {
-            const int2 rec = __ldg(nodeRec + cur);
-            c0 = rec.x;
             const int nc = rec.y;
             if (nc == 0) done = true;                                  // isLeaf()
             else {
@@ -59,18 +61,27 @@ __global__ void __launch_bounds__(256) k_bow_transform(const int2* __restrict__ 
                     const int child = CONTIG ? c0 + j : childList[c0 + j];
                     const uint4* cp = reinterpret_cast<const uint4*>(ndesc + (size_t)child * 32);
                     const uint4 x = __ldg(cp), y = __ldg(cp + 1);
+                    const int2 r = __ldg(nodeRec + child);
                     const int d = __popc(a.x ^ x.x) + __popc(a.y ^ x.y) + __popc(a.z ^ x.z) + __popc(a.w ^ x.w) +
                                   __popc(b.x ^ y.x) + __popc(b.y ^ y.y) + __popc(b.z ^ y.z) + __popc(b.w ^ y.w);
-                    best = min(best, ((u32)d << 20) | (u32)j);         // strict `d < best_d` in child order == min over (d, order)
+                    const u32 key = ((u32)d << 20) | (u32)j;           // strict `d < best_d` in child order == min over (d, order)
+                    if (key < best) { best = key; crec = r; }
                 }
             }
         }
+        const u32 mine = best;
 #pragma unroll
         for (int o = LPD / 2; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+        // the lane that holds the winning key publishes the winner's record (keys are unique inside a group: the order is part of them)
+        const u32 grp = (LPD == 32) ? 0xFFFFFFFFu : (((1u << LPD) - 1u) << (sub * LPD));
+        const u32 who = __ballot_sync(0xffffffffu, !done && mine == best) & grp;
+        const int src = who ? (__ffs(who) - 1) : (int)(threadIdx.x & 31);
+        const int rx = __shfl_sync(0xffffffffu, crec.x, src), ry = __shfl_sync(0xffffffffu, crec.y, src);
         if (!done) {
             ++level;
             const int j = (int)(best & 0xFFFFF);
             cur = CONTIG ? c0 + j : childList[c0 + j];
+            rec = make_int2(rx, ry);
             if (level == nid_level) nid = cur;
         }
     }
