@@ -331,6 +331,32 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": world * nF * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(nF * W * H),
            "d2h_bytes_per_step": int(h_n.sum()) * 60 + nF * 4, "ms_per_step": 1e3 * e2e_s / args.steps}
+    # the floor the platform sets for e2e: the same bytes moved with no compute at all (all ranks at once, same pinned buffers).
+    # At N=1 the copies hide behind the kernels; with 8 ranks streaming 1.26 GB per step each the host side becomes the limit.
+    d_stage = torch.empty((args.chunk, H, W), dtype=torch.uint8, device="cuda")
+    d_kp_s = torch.empty((args.chunk, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc_s = torch.empty((args.chunk, cap, 32), dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def copy_step():
+        for c0 in range(0, nF, args.chunk):
+            c1 = min(nF, c0 + args.chunk)
+            with torch.cuda.stream(s_in):
+                d_stage[: c1 - c0].copy_(h_frames[c0:c1], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_kp[c0:c1].copy_(d_kp_s[: c1 - c0], non_blocking=True)
+                h_desc[c0:c1].copy_(d_desc_s[: c1 - c0], non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+    copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(3, args.steps // 4)):
+        copy_step()
+    barrier()
+    copy_s = max_over_ranks(time.perf_counter() - t0) / max(3, args.steps // 4)
+    e2e["copy_only_ms_per_step"] = 1e3 * copy_s
+    e2e["copy_only_h2d_gbs_per_gpu"] = nF * W * H / copy_s / 1e9
 
     # ---- secondary metric: Hamming matches/s (all-pairs keyframe matching, sharded by query keyframe)
     matching = None
