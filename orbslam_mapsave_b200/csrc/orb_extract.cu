@@ -982,113 +982,170 @@ __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
 #define DESC_WARPS 8
 #define DESC_PW 11            // aligned words per staged blurred-patch row: covers kx-18 .. kx+18 for any alignment
 #define DESC_AW 9             // aligned words per staged disc row: covers kx-15 .. kx+15 for any alignment
-// grid = (ceil(max selCap / DESC_WARPS), nlevels, frames): blockIdx.y is the level, so there is no slot -> level search.
+#define DESC_PATCH_WORDS (37 * DESC_PW)
+#define DESC_DISC_WORDS (31 * DESC_AW)
+#define DESC_BUF_WORDS (DESC_PATCH_WORDS + DESC_DISC_WORDS)
+#define DESC_SMEM_BYTES (32 * 36 * 4 + 2 * DESC_WARPS * DESC_BUF_WORDS * 4)
+// Persistent warps over the work items (frame, slot): slot r of a frame is position r of the per-frame selection buffer
+// (level l owns [selOff[l], selOff[l] + selCap[l])), so the selection entry and the per-level counts of an item are two
+// INDEPENDENT loads whose addresses follow from the item number alone.  Software pipeline per warp:
+//   item i+2: those two loads are issued;   item i+1: its two neighbourhoods are copied to shared memory with cp.async (no
+//   registers, no waiting);   item i: orientation + descriptor from the other shared-memory buffer.
+struct DescItem { uint2 k; int cntv; };
+__device__ __forceinline__ void cp_async4(u32 dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                               const u8* __restrict__ blur, const uint2* __restrict__ sel,
                                                               const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
                                                               u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
-                                                              int* __restrict__ status) {
-    __shared__ __align__(16) float s_pat[32 * 36];                 // pattern as float (no I2F in the tap loop); row stride 36: conflict-free LDS.128
-    __shared__ u32 s_patch[DESC_WARPS][37][DESC_PW];               // blurred 37x37 neighbourhood
-    __shared__ u32 s_disc[DESC_WARPS][31][DESC_AW];                // unblurred 31x31 neighbourhood (IC_Angle)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l = blockIdx.y, f = blockIdx.z;
-    const int idx = blockIdx.x * DESC_WARPS + warp;
-    // per-level counts of this frame: lane i holds level i; prefix by shuffles (level-major output order, :1098-1106)
-    const int myc = lane < P.nlevels ? selCount[f * P.nlevels + lane] : 0;
-    int inc = myc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    const int total = __shfl_sync(0xffffffffu, inc, 31);
-    const int before = __shfl_sync(0xffffffffu, inc - myc, l), cnt = __shfl_sync(0xffffffffu, myc, l);
-    if (blockIdx.x == 0 && l == 0 && warp == 0 && lane == 0) {
-        nOut[f] = total;
-        if (total > cap) atomicOr(status, ORB_DEV_OUT_OVERFLOW);
-    }
-    if (blockIdx.x * DESC_WARPS >= cnt) return;                    // whole CTA beyond this level's keypoints
+                                                              int* __restrict__ status, int nf) {
+    extern __shared__ __align__(16) u8 smem_desc[];
+    float* s_pat = reinterpret_cast<float*>(smem_desc);            // pattern as float (no I2F in the tap loop); row stride 36: conflict-free LDS.128
+    u32* s_buf = reinterpret_cast<u32*>(smem_desc + 32 * 36 * 4);  // [2][DESC_WARPS][DESC_BUF_WORDS]: blurred 37x37 + unblurred 31x31 neighbourhoods
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 1024; i += 32 * DESC_WARPS) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
     __syncthreads();
-    const int pos = before + idx;
-    if (idx >= cnt || pos >= cap) return;
-    const LevelPlan& L = P.lv[l];
-    const uint2 k = sel[(size_t)f * P.selTotal + L.selOff + idx];
-    const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
-    const int pitchW = L.pitch >> 2;
-    const size_t lofs = (size_t)f * P.frameBytes + L.off;
+    const int nItems = nf * P.selTotal, GW = gridDim.x * DESC_WARPS;
+    int item = blockIdx.x * DESC_WARPS + warp;
 
-    // ---- stage both neighbourhoods as aligned words, all loads in flight before the first store
-    const int pxs = kx - 18 + ORBX_OX, shift = pxs & 3;            // (kx-15+OX) has the same alignment: 18-15 = 3 ... handled below
-    const int axs = kx - 15 + ORBX_OX, ashift = axs & 3;
-    {
+    auto load_item = [&](int it) {                                 // stage A: two independent loads
+        DescItem d;
+        d.k = make_uint2(0u, 0u); d.cntv = 0;
+        if (it < nItems) {
+            const int f = it / P.selTotal;
+            d.k = __ldg(sel + it);
+            d.cntv = lane < P.nlevels ? __ldg(selCount + f * P.nlevels + lane) : 0;
+        }
+        return d;
+    };
+    // resolves (level, index in level, output position) of an item; returns false for empty slots
+    auto resolve = [&](int it, const DescItem& d, int& f, int& l, int& pos, int& total) {
+        if (it >= nItems) return false;
+        f = it / P.selTotal;
+        const int r = it - f * P.selTotal;
+        l = 0;
+#pragma unroll 1
+        for (int j = 1; j < P.nlevels; j++) l += (r >= P.lv[j].selOff) ? 1 : 0;
+        const int idx = r - P.lv[l].selOff;
+        int inc = d.cntv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        total = __shfl_sync(0xffffffffu, inc, 31);
+        const int before = __shfl_sync(0xffffffffu, inc - d.cntv, l), cnt = __shfl_sync(0xffffffffu, d.cntv, l);
+        pos = before + idx;
+        if (r == 0 && lane == 0) {                                 // slot 0 of every frame reports the frame's keypoint count
+            nOut[f] = total;
+            if (total > cap) atomicOr(status, ORB_DEV_OUT_OVERFLOW);
+        }
+        return idx < cnt && pos < cap;
+    };
+    auto stage = [&](int buf, int f, int l, const uint2 k) {       // stage B: cp.async both neighbourhoods as aligned words
+        const LevelPlan& L = P.lv[l];
+        const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
+        const int pitchW = L.pitch >> 2;
+        const size_t lofs = (size_t)f * P.frameBytes + L.off;
+        const int pxs = kx - 18 + ORBX_OX, axs = kx - 15 + ORBX_OX;
         const u32* bsrc = reinterpret_cast<const u32*>(blur + lofs) + (ky - 18 + ORBX_OY) * pitchW + (pxs >> 2);
         const u32* asrc = reinterpret_cast<const u32*>(pyr + lofs) + (ky - 15 + ORBX_OY) * pitchW + (axs >> 2);
-        u32 vb[13], va[9];
+        const u32 dst = smem_u32(s_buf + (size_t)(buf * DESC_WARPS + warp) * DESC_BUF_WORDS);
 #pragma unroll
         for (int j = 0; j < 13; j++) {
             const int i = lane + 32 * j, r = i / DESC_PW, w = i - r * DESC_PW;
-            vb[j] = i < 37 * DESC_PW ? __ldg(bsrc + r * pitchW + w) : 0u;
+            if (i < DESC_PATCH_WORDS) cp_async4(dst + 4 * i, bsrc + r * pitchW + w);
         }
 #pragma unroll
         for (int j = 0; j < 9; j++) {
             const int i = lane + 32 * j, r = i / DESC_AW, w = i - r * DESC_AW;
-            va[j] = i < 31 * DESC_AW ? __ldg(asrc + r * pitchW + w) : 0u;
+            if (i < DESC_DISC_WORDS) cp_async4(dst + 4 * (DESC_PATCH_WORDS + i), asrc + r * pitchW + w);
         }
-#pragma unroll
-        for (int j = 0; j < 13; j++) { const int i = lane + 32 * j; if (i < 37 * DESC_PW) (&s_patch[warp][0][0])[i] = vb[j]; }
-#pragma unroll
-        for (int j = 0; j < 9; j++) { const int i = lane + 32 * j; if (i < 31 * DESC_AW) (&s_disc[warp][0][0])[i] = va[j]; }
-    }
-    __syncwarp();
+    };
 
-    // ---- IC_Angle (ORBextractor.cc:76-103): lane = column u (-15..15); the disc is symmetric (:461-468 makes umax its own
-    // transpose), so column u spans rows |v| <= umax[|u|]
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - 15, vlim = P.umax[u < 0 ? -u : u];
-        const u8* cen = reinterpret_cast<const u8*>(&s_disc[warp][15][0]) + 15 + ashift + u;
-        int colsum = 0;
+    // prologue
+    DescItem d0 = load_item(item), d1 = load_item(item + GW);
+    int f0 = 0, l0 = 0, pos0 = 0, tot0 = 0;
+    bool ok0 = resolve(item, d0, f0, l0, pos0, tot0);
+    if (ok0) stage(0, f0, l0, d0.k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int buf = 0;
+    for (; item < nItems; item += GW) {
+        // stage A for item+2 (consumed two iterations from now), stage B for item+1
+        const DescItem d2 = load_item(item + 2 * GW);
+        int f1 = 0, l1 = 0, pos1 = 0, tot1 = 0;
+        const bool ok1 = resolve(item + GW, d1, f1, l1, pos1, tot1);
+        if (ok1) stage(buf ^ 1, f1, l1, d1.k);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");       // the copies of the CURRENT item have landed
+        __syncwarp();
+        if (ok0) {
+            const int l = l0, f = f0, pos = pos0;
+            const uint2 k = d0.k;
+            const LevelPlan& L = P.lv[l];
+            const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
+            const int shift = (kx - 18 + ORBX_OX) & 3, ashift = (kx - 15 + ORBX_OX) & 3;
+            const u32* patch = s_buf + (size_t)(buf * DESC_WARPS + warp) * DESC_BUF_WORDS;
+            const u32* disc = patch + DESC_PATCH_WORDS;
+
+            // ---- IC_Angle (ORBextractor.cc:76-103): lane = column u (-15..15); the disc is symmetric (:461-468 makes umax its own
+            // transpose), so column u spans rows |v| <= umax[|u|]
+            int m10 = 0, m01 = 0;
+            if (lane < 31) {
+                const int u = lane - 15, vlim = P.umax[u < 0 ? -u : u];
+                const u8* cen = reinterpret_cast<const u8*>(disc + 15 * DESC_AW) + 15 + ashift + u;
+                int colsum = 0;
 #pragma unroll
-        for (int v = -15; v <= 15; v++) {
-            const int I = ((v < 0 ? -v : v) <= vlim) ? (int)cen[v * (DESC_AW * 4)] : 0;
-            colsum += I;
-            m01 += v * I;
+                for (int v = -15; v <= 15; v++) {
+                    const int I = ((v < 0 ? -v : v) <= vlim) ? (int)cen[v * (DESC_AW * 4)] : 0;
+                    colsum += I;
+                    m01 += v * I;
+                }
+                m10 = u * colsum;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+            const float angle = dev_fast_atan2((float)m01, (float)m10);
+
+            // ---- computeOrbDescriptor (ORBextractor.cc:107-146); cos for lane 0, sin for lane 1 (double, then rounded to float)
+            const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+            const float ang = __fmul_rn(angle, factorPI);
+            float cs = 0.f;
+            if (lane < 2) {                                         // one non-divergent sincos for both (shared range reduction)
+                double sd, cd;
+                sincos((double)ang, &sd, &cd);
+                cs = (float)(lane == 0 ? cd : sd);
+            }
+            const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
+            const u8* center = reinterpret_cast<const u8*>(patch + 18 * DESC_PW) + 18 + shift;
+            const float4* pat = reinterpret_cast<const float4*>(s_pat + lane * 36);
+            u32 val = 0;
+            // round-half-even without the XU pipe: x + 1.5*2^23 leaves rint(x) in the low mantissa bits (|x| < 2^22), == cvRound
+            const float MAGIC = 12582912.f;
+            const int MAGIC_I = 0x4B400000;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 pp = pat[j];                               // x0, y0, x1, y1
+                const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)), MAGIC)) - MAGIC_I;
+                const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)), MAGIC)) - MAGIC_I;
+                const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.z, b), __fmul_rn(pp.w, a)), MAGIC)) - MAGIC_I;
+                const int q1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.z, a), __fmul_rn(pp.w, b)), MAGIC)) - MAGIC_I;
+                const int t0 = center[r0 * (DESC_PW * 4) + q0], t1 = center[r1 * (DESC_PW * 4) + q1];
+                val |= (u32)(t0 < t1) << j;
+            }
+            descOut[((size_t)f * cap + pos) * 32 + lane] = (u8)val;
+            if (lane == 0) {
+                orbx_keypoint kp;
+                kp.x = (float)kx; kp.y = (float)ky;
+                if (l != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // :1098-1104
+                kp.size = L.kpSize; kp.angle = angle; kp.response = (float)k.y; kp.octave = l; kp.class_id = -1;
+                kpOut[(size_t)f * cap + pos] = kp;
+            }
         }
-        m10 = u * colsum;
+        __syncwarp();                                              // everyone is done with buffer `buf` before it is refilled
+        d0 = d1; d1 = d2;
+        ok0 = ok1; f0 = f1; l0 = l1; pos0 = pos1;
+        buf ^= 1;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-    const float angle = dev_fast_atan2((float)m01, (float)m10);
-
-    // ---- computeOrbDescriptor (ORBextractor.cc:107-146); cos on lane 0, sin on lane 1 (double, then rounded to float)
-    const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
-    const float ang = __fmul_rn(angle, factorPI);
-    float cs = 0.f;
-    if (lane == 0) cs = (float)cos((double)ang);
-    else if (lane == 1) cs = (float)sin((double)ang);
-    const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
-    const u8* center = reinterpret_cast<const u8*>(&s_patch[warp][18][0]) + 18 + shift;
-    const float4* pat = reinterpret_cast<const float4*>(s_pat + lane * 36);
-    u32 val = 0;
-    // round-half-even without the XU pipe: x + 1.5*2^23 leaves rint(x) in the low mantissa bits (|x| < 2^22), == cvRound
-    const float MAGIC = 12582912.f;
-    const int MAGIC_I = 0x4B400000;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const float4 pp = pat[j];                                   // x0, y0, x1, y1
-        const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)), MAGIC)) - MAGIC_I;
-        const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)), MAGIC)) - MAGIC_I;
-        const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.z, b), __fmul_rn(pp.w, a)), MAGIC)) - MAGIC_I;
-        const int q1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.z, a), __fmul_rn(pp.w, b)), MAGIC)) - MAGIC_I;
-        const int t0 = center[r0 * (DESC_PW * 4) + q0], t1 = center[r1 * (DESC_PW * 4) + q1];
-        val |= (u32)(t0 < t1) << j;
-    }
-    descOut[((size_t)f * cap + pos) * 32 + lane] = (u8)val;
-    if (lane == 0) {
-        orbx_keypoint kp;
-        kp.x = (float)kx; kp.y = (float)ky;
-        if (l != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // :1098-1104
-        kp.size = L.kpSize; kp.angle = angle; kp.response = (float)k.y; kp.octave = l; kp.class_id = -1;
-        kpOut[(size_t)f * cap + pos] = kp;
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // =====================================================================================================
@@ -1126,7 +1183,7 @@ struct orbx_extractor {
     CUtensorMap* d_maps = nullptr;         // one TMA descriptor per pyramid level (k_fast_tma)
     bool useTma = false;
     size_t fwSmem = 0;
-    int fwGrid = 0;
+    int fwGrid = 0, descGrid = 0;
     uint4* d_cells = nullptr;              // valid FAST cells: {iniX | iniY<<16, tw | th<<8 | level<<16, cell id, 0}
     int nCells = 0;
     int capInternal = 0;
@@ -1344,6 +1401,19 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
             }
         }
     }
+    {   // k_describe: persistent grid, DESC_SMEM_BYTES of dynamic shared memory per CTA
+        cudaDeviceProp prop;
+        ORB_CUDA_TRY(cudaGetDeviceProperties(&prop, ex->device));
+        const int perSM = std::max(1, std::min(8, (int)((prop.sharedMemPerMultiprocessor - 2048) / (DESC_SMEM_BYTES + 1024))));
+        ex->descGrid = prop.multiProcessorCount * perSM;
+        static std::mutex amu3;
+        static bool descOptIn[64] = {false};
+        std::lock_guard<std::mutex> lk(amu3);
+        if (!descOptIn[ex->device & 63]) {
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES));
+            descOptIn[ex->device & 63] = true;
+        }
+    }
     {   // dynamic shared-memory opt-in is per function, shared by all handles: only ever raise it
         static std::mutex amu;
         static size_t maxFastDev[64] = {0}, maxOctDev[64] = {0};     // per function AND per device
@@ -1498,10 +1568,10 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         ex->launches++;
     }
     if (stages & ORBX_STAGE_DESCRIBE) {
-        int maxSel = 1;
-        for (int l = 0; l < nl; l++) maxSel = std::max(maxSel, P.lv[l].selCap);
-        dim3 g(orb_div_up(maxSel, DESC_WARPS), nl, nf);
-        k_describe<<<g, 32 * DESC_WARPS, 0, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc, d_n, cap, ex->d_status);
+        const int items = nf * P.selTotal;
+        const int grid = std::min(ex->descGrid, orb_div_up(items, DESC_WARPS));
+        k_describe<<<grid, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc, d_n, cap,
+                                                                  ex->d_status, nf);
         ex->launches++;
     }
     ORB_CUDA_TRY(cudaGetLastError());
