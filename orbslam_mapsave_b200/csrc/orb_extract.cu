@@ -144,11 +144,13 @@ __global__ void __launch_bounds__(256) k_resize_generic(const __grid_constant__ 
 // the two horizontal taps of a pixel are cut out with a funnel shift and combined with their 11-bit coefficients by one
 // IDP2A (p0*c0 + p1*c1), the vertical pass is the reference's exact (>>4, *b, >>16, +2, >>2) sequence.
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, int level, u8* __restrict__ pyr,
-                                                const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab) {
+                                                const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab, u32 wqInv) {
     const LevelPlan& L = P.lv[level];
     const LevelPlan& S = P.lv[level - 1];
-    const int x = (blockIdx.x * 64 + threadIdx.x) * 4, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
-    if (x >= L.w || y >= L.h) return;
+    // flat index over (row, group of 4 pixels): no idle lanes at the right edge of a level (widths are not multiples of 128)
+    const u32 wq = (u32)(L.w + 3) >> 2, idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= wq * (u32)L.h) return;
+    const int y = (int)__umulhi(idx, wqInv), x = (int)(idx - (u32)y * wq) * 4, f = blockIdx.y;
     u8* frame = pyr + (size_t)f * P.frameBytes;
     const u8* src = frame + S.off + (size_t)ORBX_OY * S.pitch + ORBX_OX;
     const ResizeTap ty = ytab[L.ytabOff + y];
@@ -895,7 +897,7 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
 // Vertical pass: with rows paired that way the 7 vertical taps of an output are four IDP2A (tap pairs (18,34)(48,56)(48,34)(18,0)
 // for even rows, (0,18)(34,48)(56,48)(34,18) for odd rows) on four LDS.128 shared by the two outputs of a thread.
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, const u8* __restrict__ pyr, u8* __restrict__ blur) {
-    __shared__ uint4 s_p[(BL_TH + 6) / 2][BL_TW / 4];                 // [row pair][4-column group]: h(row 2j) | h(row 2j+1) << 16
+    __shared__ uint4 s_p[(BL_TH + 6) / 2][BL_TW / 4 + 1];             // [row pair][4-column group]: h(row 2j) | h(row 2j+1) << 16 (+1: rows start on different banks)
     int level = 0;
     while (level + 1 < P.nlevels && (int)blockIdx.x >= P.blurTileBase[level + 1]) level++;
     const LevelPlan& L = P.lv[level];
@@ -911,9 +913,11 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, co
     const int rows = min(BL_TH, L.h - y0);                            // output rows of this tile
     const int pairsNeeded = (rows + 6 + 1) >> 1;
     const int wcols = min(BL_TW / 4, (L.w - x0 + 3) >> 2);            // 4-column groups that hold image pixels
-    for (int i = tid; i < pairsNeeded * (BL_TW / 4); i += 256) {
-        const int j = i >> 5, wx = i & 31;
-        if (wx >= wcols) continue;
+    // work items are (row pair, column group) over the groups that hold image pixels only: edge tiles of a level (widths are not
+    // multiples of 128) keep every lane busy.  j = i / wcols by multiplication (exact for i < 2048).
+    const u32 winv = (65536u + (u32)wcols - 1u) / (u32)wcols;
+    for (int i = tid; i < pairsNeeded * wcols; i += 256) {
+        const int j = (int)(((u32)i * winv) >> 16), wx = i - j * wcols;
         const u32* rp = src + (2 * j) * pitchW + wx;
         const u32 a0 = __ldg(rp - 1), b0 = __ldg(rp), c0 = __ldg(rp + 1);
         const u32 a1 = __ldg(rp + pitchW - 1), b1 = __ldg(rp + pitchW), c1 = __ldg(rp + pitchW + 1);
@@ -932,9 +936,8 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, co
     // tap pairs as the two low bytes of the IDP2A weight operand
     const u32 E0 = 18u | (34u << 8), E1 = 48u | (56u << 8), E2 = 48u | (34u << 8), E3 = 18u;          // even output row
     const u32 O0 = 18u << 8, O1 = 34u | (48u << 8), O2 = 56u | (48u << 8), O3 = 34u | (18u << 8);     // odd output row
-    for (int i = tid; i < (BL_TH / 2) * (BL_TW / 4); i += 256) {
-        const int j = i >> 5, wx = i & 31;                             // output rows 2j and 2j+1 use row pairs j .. j+3
-        if (wx >= wcols || 2 * j >= rows) continue;
+    for (int i = tid; i < ((rows + 1) >> 1) * wcols; i += 256) {
+        const int j = (int)(((u32)i * winv) >> 16), wx = i - j * wcols;   // output rows 2j and 2j+1 use row pairs j .. j+3
         const uint4 p0 = s_p[j][wx], p1 = s_p[j + 1][wx], p2 = s_p[j + 2][wx], p3 = s_p[j + 3][wx];
 #define VSUM(c, W0, W1, W2, W3) __dp2a_lo(p0.c, W0, __dp2a_lo(p1.c, W1, __dp2a_lo(p2.c, W2, __dp2a_lo(p3.c, W3, 32768u))))
         const u32 e = (VSUM(x, E0, E1, E2, E3) >> 16) | ((VSUM(y, E0, E1, E2, E3) >> 16) << 8) |
@@ -1526,7 +1529,12 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         for (int l = 1; l < nl; l++) {
             const LevelPlan& L = P.lv[l];
             dim3 g(orb_div_up(L.w, 256), orb_div_up(L.h, 4), nf), b(64, 4);
-            if (L.fastResize) k_resize<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
+            // y = idx / wq as umulhi(idx, 2^32 / wq + 1) is exact while idx * wq < 2^32 (true up to ~6000 x 6000 levels)
+            if (L.fastResize && (unsigned long long)((L.w + 3) >> 2) * ((L.w + 3) >> 2) * L.h < (1ull << 32)) {
+                const u32 wq = (u32)(L.w + 3) >> 2;
+                dim3 gf(orb_div_up((int)wq * L.h, 256), nf);
+                k_resize<<<gf, 256, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab, 0xFFFFFFFFu / wq + 1);
+            }
             else k_resize_generic<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
             ex->launches++;
         }
