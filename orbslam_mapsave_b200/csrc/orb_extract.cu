@@ -890,7 +890,7 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
 // level in the same geometry.  Tile 128x32 outputs per CTA; separable through shared memory.
 // =====================================================================================================
 #define BL_TW 128
-#define BL_TH 32
+#define BL_TH 128
 // All levels in one launch: blockIdx.x walks the per-level tile lists (Plan::blurTileBase).
 // Horizontal pass: the 7 taps of an output are two IDP4A over byte windows cut from three aligned words with funnel shifts (no
 // byte unpacking); a thread does two vertically adjacent rows and stores their exact results (<= 65280) packed as u16 pairs.
