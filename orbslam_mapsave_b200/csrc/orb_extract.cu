@@ -1566,7 +1566,10 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     }
     if (stages & ORBX_STAGE_OCTREE) {
         dim3 g(nl, nf);
-        k_octree<<<g, ORBX_OCT_THREADS, ex->octSmem, st>>>(P, ex->d_cand, ex->d_candCount, ex->d_nodeOf, ex->d_sel,
+        // a (level, frame) CTA at VGA size holds ~1400 candidates at most: in a batch pass (plenty of CTAs) 128 threads keep the many
+        // barrier-separated passes short (0.37 vs 0.63 us/frame); large images and single-frame latency calls want the full 512
+        const int octT = (P.width * P.height <= 500000 && nf >= 16) ? 128 : ORBX_OCT_THREADS;
+        k_octree<<<g, octT, ex->octSmem, st>>>(P, ex->d_cand, ex->d_candCount, ex->d_nodeOf, ex->d_sel,
                                                            ex->d_selCount, ex->d_status);
         ex->launches++;
     }
