@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constan
 // mbarrier), so the load of the next cell overlaps the work on the current one and costs no per-thread instructions.
 // Nothing inside a cell needs a CTA barrier or a shared atomic: compaction is ballot + popc on a warp-uniform counter.
 // ---------------------------------------------------------------------------------------------------
-#define ORBX_FW_WARPS 4
+#define ORBX_FW_WARPS 8
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u32 bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -429,7 +429,7 @@ template <int BOXW, int SPP>
 __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_constant__ Plan P, const CUtensorMap* __restrict__ maps,
                                                                   const uint4* __restrict__ cells, int nCells, int nf,
                                                                   uint2* __restrict__ cand, int* __restrict__ candCount,
-                                                                  int* __restrict__ status) {
+                                                                  int* __restrict__ status, int* __restrict__ workCounter) {
     extern __shared__ __align__(128) u8 smem_fw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int BW = BOXW > 0 ? BOXW : P.fwBoxW, SP = SPP > 0 ? SPP : P.scorePitch;
@@ -462,8 +462,13 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
     if (lane == 0) issue(item, 0);
     u32 ph0 = 0;
     const u32 lt = (1u << lane) - 1;
+    // Cells differ in cost (texture, the minThFAST retry), so after its first, statically assigned cell a warp takes its work
+    // from a global counter; the id of the next cell is fetched one cell ahead so that its TMA load can be issued early.
+    int nextItem = 0;
+    if (lane == 0) nextItem = Wt + atomicAdd(workCounter, 1);
+    nextItem = __shfl_sync(0xffffffffu, nextItem, 0);
 
-    for (; item < nItems; item += Wt) {
+    for (; item < nItems;) {
         const int f = item / nCells, cidx = item - f * nCells;
         const uint4 ce = __ldg(cells + cidx);
         const int iniX = (int)(ce.x & 0xFFFF), iniY = (int)(ce.x >> 16);
@@ -592,10 +597,13 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
         }
         __syncwarp();
         // the tile is no longer needed: fetch the next cell's tile now, it lands while emission / score clearing run
-        if (lane == 0 && item + Wt < nItems) {
+        item = nextItem;                                              // (f, l, c, iniX ... of the cell in hand are locals)
+        if (lane == 0 && item < nItems) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // order our generic reads before the async-proxy write
-            issue(item + Wt, 0);
+            issue(item, 0);
+            nextItem = Wt + atomicAdd(workCounter, 1);
         }
+        nextItem = __shfl_sync(0xffffffffu, nextItem, 0);
         if (nKeep) {                                                  // every survivor of the pass that produced them is emitted (score >= T)
             const LevelPlan& L = P.lv[l];
             int base = 0;
@@ -1181,7 +1189,7 @@ struct orbx_extractor {
     cudaEvent_t evH2D[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evD2H[2] = {nullptr, nullptr};
     uint2 *d_cand = nullptr, *d_sel = nullptr;
     u32* d_nodeOf = nullptr;
-    int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr;
+    int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr, *d_workCounter = nullptr;
     ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
     CUtensorMap* d_maps = nullptr;         // one TMA descriptor per pyramid level (k_fast_tma)
     bool useTma = false;
@@ -1338,6 +1346,7 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     ORB_CUDA_TRY(cudaMalloc(&ex->d_nodeOf, (size_t)B * P.candTotal * sizeof(u32)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_sel, (size_t)B * P.selTotal * sizeof(uint2)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_candCount, (size_t)B * nl * sizeof(int)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_workCounter, sizeof(int)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_selCount, (size_t)B * nl * sizeof(int)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_status, sizeof(int)));
     ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
@@ -1482,7 +1491,7 @@ extern "C" void orbx_destroy(orbx_extractor* ex) {
     if (ex->h_stage) cudaFreeHost(ex->h_stage);
     if (ex->sH2D) cudaStreamDestroy(ex->sH2D);
     if (ex->sD2H) cudaStreamDestroy(ex->sD2H);
-    cudaFree(ex->d_cand); cudaFree(ex->d_sel); cudaFree(ex->d_nodeOf); cudaFree(ex->d_candCount); cudaFree(ex->d_selCount);
+    cudaFree(ex->d_cand); cudaFree(ex->d_sel); cudaFree(ex->d_nodeOf); cudaFree(ex->d_candCount); cudaFree(ex->d_workCounter); cudaFree(ex->d_selCount);
     cudaFree(ex->d_status); cudaFree(ex->d_xtab); cudaFree(ex->d_ytab); cudaFree(ex->d_cells); cudaFree(ex->d_maps);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
@@ -1546,16 +1555,17 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     }
     if (stages & ORBX_STAGE_FAST) {
         ORB_CUDA_TRY(cudaMemsetAsync(ex->d_candCount, 0, (size_t)nf * nl * sizeof(int), st));
+        ORB_CUDA_TRY(cudaMemsetAsync(ex->d_workCounter, 0, sizeof(int), st));
         dim3 g(ex->nCells, nf);
         if (ex->nCells > 0 && ex->useTma) {
             const int items = ex->nCells * nf;
             const int grid = std::min(ex->fwGrid, orb_div_up(items, ORBX_FW_WARPS));
             if (P.fwBoxW == 64 && ex->fastConst)
                 k_fast_tma<64, ORBX_FAST_SPP><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
-                                                                                          ex->d_candCount, ex->d_status);
+                                                                                          ex->d_candCount, ex->d_status, ex->d_workCounter);
             else
                 k_fast_tma<0, 0><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
-                                                                             ex->d_candCount, ex->d_status);
+                                                                             ex->d_candCount, ex->d_status, ex->d_workCounter);
         } else if (ex->nCells > 0) {
             if (ex->fastConst)
                 k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_cells, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
