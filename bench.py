@@ -184,7 +184,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--unique", type=int, default=4096, help="distinct synthetic frames per GPU (others repeat them)")
-    ap.add_argument("--chunk", type=int, default=256, help="frames per device pass (workspace size)")
+    ap.add_argument("--chunk", type=int, default=512, help="frames per device pass of the device-resident measurement (workspace size)")
+    ap.add_argument("--e2e-chunk", type=int, default=256, help="frames per pipelined chunk of the host-buffer (e2e) path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-match", action="store_true", help="skip the matching sub-benchmark")
     ap.add_argument("--match-q", type=int, default=32, help="query keyframes per GPU in the matching sub-benchmark")
@@ -300,16 +301,16 @@ def main():
     roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast_tma", "octree": "k_octree", "blur": "k_blur",
                                            "describe": "k_describe"}[dom],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1_final_all_kernels_ncu_full.md)
-                "traffic": ({"fast": 287.2e6, "describe": 561.1e6, "blur": 526.9e6, "octree": 15.7e6}.get(dom, 0) * args.chunk / 256) or None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1m_all_kernels_ncu_full.md)
+                "traffic": ({"fast": 285.9e6, "describe": 601.6e6, "blur": 524.8e6, "octree": 16.0e6}.get(dom, 0) * args.chunk / 256) or None,
                 "peak_source": peak_src, "avg_launch_ms": dom_launch_s * 1e3, "algorithmic_bytes_per_frame": stage_bytes[dom],
                 "stage_ms_per_step": {k: v * 1e3 for k, v in stage_s.items()},
-                # what actually bounds it: warp-instruction issue.  536.9 M warp-instructions per 256-frame k_fast_tma launch (ncu,
-                # profiles/r1_final_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
-                "issue": ({"warp_inst_per_launch": 536.9e6 * args.chunk / 256,
-                           "achieved_ginst_s": 536.9e6 * args.chunk / 256 / dom_launch_s / 1e9,
+                # what actually bounds it: warp-instruction issue.  540.3 M warp-instructions per 256-frame k_fast_tma launch (ncu,
+                # profiles/r1m_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
+                "issue": ({"warp_inst_per_launch": 540.3e6 * args.chunk / 256,
+                           "achieved_ginst_s": 540.3e6 * args.chunk / 256 / dom_launch_s / 1e9,
                            "peak_ginst_s": 148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                           "frac": 536.9e6 * args.chunk / 256 / dom_launch_s / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6)}
+                           "frac": 540.3e6 * args.chunk / 256 / dom_launch_s / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6)}
                           if dom == "fast" else None),
                 "step_hbm_frac": (B_FRAME * nF / (secs / args.steps) / 1e9) / hbm_peak,
                 "note": "640x480 pyramids are L2-resident and this stage is integer-issue bound, not HBM bound (SURVEY.md §7)"}
@@ -319,8 +320,12 @@ def main():
     h_desc = torch.zeros((nF, cap, 32), dtype=torch.uint8).pin_memory()
     h_n = np.zeros(nF, np.int32)
 
+    # the host-buffer path pipelines H2D / compute / D2H in chunks of its own handle's pass size (smaller chunks start earlier)
+    ex2 = ex if args.e2e_chunk == args.chunk else orb.ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, max_batch=args.e2e_chunk,
+                                                                     device=local_rank)
+
     def e2e_step():
-        capi.check(capi.lib().orbx_extract_batch(ex.handle, capi._p(h_frames), nF, W, H, W, W * H, None, 0, 0,
+        capi.check(capi.lib().orbx_extract_batch(ex2.handle, capi._p(h_frames), nF, W, H, W, W * H, None, 0, 0,
                                                  capi._p(h_kp), capi._p(h_desc), cap, capi._p(h_n)))
     e2e_step()
     barrier()
@@ -333,14 +338,14 @@ def main():
            "d2h_bytes_per_step": int(h_n.sum()) * 60 + nF * 4, "ms_per_step": 1e3 * e2e_s / args.steps}
     # the floor the platform sets for e2e: the same bytes moved with no compute at all (all ranks at once, same pinned buffers).
     # At N=1 the copies hide behind the kernels; with 8 ranks streaming 1.26 GB per step each the host side becomes the limit.
-    d_stage = torch.empty((args.chunk, H, W), dtype=torch.uint8, device="cuda")
-    d_kp_s = torch.empty((args.chunk, cap, 7), dtype=torch.float32, device="cuda")
-    d_desc_s = torch.empty((args.chunk, cap, 32), dtype=torch.uint8, device="cuda")
+    d_stage = torch.empty((args.e2e_chunk, H, W), dtype=torch.uint8, device="cuda")
+    d_kp_s = torch.empty((args.e2e_chunk, cap, 7), dtype=torch.float32, device="cuda")
+    d_desc_s = torch.empty((args.e2e_chunk, cap, 32), dtype=torch.uint8, device="cuda")
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
     def copy_step():
-        for c0 in range(0, nF, args.chunk):
-            c1 = min(nF, c0 + args.chunk)
+        for c0 in range(0, nF, args.e2e_chunk):
+            c1 = min(nF, c0 + args.e2e_chunk)
             with torch.cuda.stream(s_in):
                 d_stage[: c1 - c0].copy_(h_frames[c0:c1], non_blocking=True)
             with torch.cuda.stream(s_out):
@@ -502,7 +507,7 @@ def main():
             "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "C2: batch of 640x480 synthetic frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7",
-                       "frames_per_gpu_per_step": nF, "unique_frames_per_gpu": min(args.unique, nF), "frames_per_device_pass": args.chunk,
+                       "frames_per_gpu_per_step": nF, "unique_frames_per_gpu": min(args.unique, nF), "frames_per_device_pass": args.chunk, "frames_per_e2e_chunk": args.e2e_chunk,
                        "keypoints_per_frame": kp_per_frame, "l2": "inputs_exceed_l2 (1.26 GB of frames per step per GPU)",
                        "parallelism": f"frame-sharded x{world}, no data-path collective", "numa_node_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
