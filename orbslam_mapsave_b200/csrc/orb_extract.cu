@@ -165,17 +165,19 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, 
     const u32* r1p = reinterpret_cast<const u32*>(src + (size_t)sy1 * S.pitch + base);
     const u32 a0 = r0p[0], a1 = r0p[1], a2 = r0p[2];
     const u32 b0 = r1p[0], b1 = r1p[1], b2 = r1p[2];
+    // the 8 source bytes starting at the first output's tap, per row; output k then picks its two taps (bytes d, d+1 with
+    // d = sx[k] - sx[0] <= 6, checked on the host) with one PRMT whose selector is d | (d+1) << 4
+    const int sh0 = (sx[0] - base) * 8;
+    const u32 alo = __funnelshift_r(a0, a1, sh0), ahi = __funnelshift_r(a1, a2, sh0);
+    const u32 blo = __funnelshift_r(b0, b1, sh0), bhi = __funnelshift_r(b1, b2, sh0);
     u32 out = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int i = sx[k] - base, sh = (i & 3) * 8;
-        const bool w0 = i < 4, w1 = i < 8;
-        const u32 pa = __funnelshift_r(w0 ? a0 : (w1 ? a1 : a2), w0 ? a1 : a2, sh);
-        const u32 pb = __funnelshift_r(w0 ? b0 : (w1 ? b1 : b2), w0 ? b1 : b2, sh);
-        const int r0 = (int)__dp2a_lo(cf[k], pa, 0u);
-        const int r1 = (int)__dp2a_lo(cf[k], pb, 0u);
-        int v = (((ty.c0 * (r0 >> 4)) >> 16) + ((ty.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
+        const u32 sel = (u32)(sx[k] - sx[0]) * 0x11u + 0x10u;
+        const int r0 = (int)__dp2a_lo(cf[k], __byte_perm(alo, ahi, sel), 0u);
+        const int r1 = (int)__dp2a_lo(cf[k], __byte_perm(blo, bhi, sel), 0u);
+        // <= 255 by construction (non-negative coefficients summing to 2048 per axis): cv::resize's saturate_cast is a no-op here
+        const int v = (((ty.c0 * (r0 >> 4)) >> 16) + ((ty.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
         out |= (u32)v << (8 * k);
     }
     *reinterpret_cast<u32*>(frame + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
@@ -1311,12 +1313,19 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         if (l > 0) {
             build_resize_taps(P.lv[l - 1].w, L.w, true, xt);
             build_resize_taps(P.lv[l - 1].h, L.h, false, yt);
-            // fast form needs: each group of 4 outputs reads source bytes within [s0 & ~3, (s0 & ~3) + 11]
+            // fast form needs: the taps of each group of 4 outputs lie within the 8 source bytes that start at the first one's tap,
+            // and every coefficient is in [0, 2048] (no saturation possible)
             L.fastResize = 1;
             for (int x = 0; x < L.w; x += 4) {
-                const int s0 = xt[L.xtabOff + x].s & ~3;
-                for (int k = 0; k < 4 && x + k < L.w; k++)
-                    if (xt[L.xtabOff + x + k].s + 1 - s0 > 11 || xt[L.xtabOff + x + k].s < s0) L.fastResize = 0;
+                const int s0 = xt[L.xtabOff + x].s;
+                for (int k = 0; k < 4 && x + k < L.w; k++) {
+                    const ResizeTap& t = xt[L.xtabOff + x + k];
+                    if (t.s < s0 || t.s + 1 - s0 > 7 || s0 < 0 || t.c0 < 0 || t.c1 < 0 || t.c0 + t.c1 != 2048) L.fastResize = 0;
+                }
+            }
+            for (int y = 0; y < L.h; y++) {
+                const ResizeTap& t = yt[L.ytabOff + y];
+                if (t.c0 < 0 || t.c1 < 0 || t.c0 + t.c1 != 2048) L.fastResize = 0;
             }
             while (xt.size() % 4) xt.push_back(xt.back());           // pad so a thread can always load 4 taps
         }
