@@ -140,47 +140,64 @@ __global__ void __launch_bounds__(256) k_resize_generic(const __grid_constant__ 
     *reinterpret_cast<u32*>(frame + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
 }
 
-// Fast form for scale factors <= 2: the 4 outputs of a thread read source bytes inside 3 aligned words per source row,
-// the two horizontal taps of a pixel are cut out with a funnel shift and combined with their 11-bit coefficients by one
-// IDP2A (p0*c0 + p1*c1), the vertical pass is the reference's exact (>>4, *b, >>16, +2, >>2) sequence.
+// Fast form for scale factors <= 2.  A thread produces 4 adjacent pixels of TWO consecutive output rows: the tap tables, the
+// PRMT selectors and all address arithmetic are shared by the two rows, and so is the horizontal pass of the source row the
+// two outputs have in common (for a 1.2 pyramid the second output row starts where the first one ends 5 times out of 6).
+// Horizontal pass of a source row: 3 aligned words -> the 8 bytes starting at the first output's tap (two funnel shifts);
+// output k picks its two taps (bytes d, d+1 with d = sx[k] - sx[0] <= 6, checked on the host) with one PRMT and combines them
+// with their 11-bit coefficients by one IDP2A.  Vertical pass: the reference's exact (>>4, *b, >>16, +2, >>2) sequence.
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, int level, u8* __restrict__ pyr,
                                                 const ResizeTap* __restrict__ xtab, const ResizeTap* __restrict__ ytab, u32 wqInv) {
     const LevelPlan& L = P.lv[level];
     const LevelPlan& S = P.lv[level - 1];
-    // flat index over (row, group of 4 pixels): no idle lanes at the right edge of a level (widths are not multiples of 128)
+    // flat index over (row pair, group of 4 pixels): no idle lanes at the right edge of a level (widths are not multiples of 128)
     const u32 wq = (u32)(L.w + 3) >> 2, idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= wq * (u32)L.h) return;
-    const int y = (int)__umulhi(idx, wqInv), x = (int)(idx - (u32)y * wq) * 4, f = blockIdx.y;
+    if (idx >= wq * (u32)((L.h + 1) >> 1)) return;
+    const int yp = (int)__umulhi(idx, wqInv), x = (int)(idx - (u32)yp * wq) * 4, y = 2 * yp, f = blockIdx.y;
+    const bool two = y + 1 < L.h;
     u8* frame = pyr + (size_t)f * P.frameBytes;
     const u8* src = frame + S.off + (size_t)ORBX_OY * S.pitch + ORBX_OX;
-    const ResizeTap ty = ytab[L.ytabOff + y];
-    const int sy0 = min(max(ty.s, 0), S.h - 1), sy1 = min(max(ty.s + 1, 0), S.h - 1);
+    const ResizeTap ty0 = ytab[L.ytabOff + y], ty1 = ytab[L.ytabOff + (two ? y + 1 : y)];
+    const int sA0 = min(max(ty0.s, 0), S.h - 1), sA1 = min(max(ty0.s + 1, 0), S.h - 1);
+    const int sB0 = min(max(ty1.s, 0), S.h - 1), sB1 = min(max(ty1.s + 1, 0), S.h - 1);
     // x taps of the 4 outputs: xtab rows are padded to a multiple of 4 entries, so two 16-byte loads
     const uint4* tp = reinterpret_cast<const uint4*>(xtab + L.xtabOff + x);
     const uint4 t01 = __ldg(tp), t23 = __ldg(tp + 1);
-    const int sx[4] = {(int)t01.x, (int)t01.z, (int)t23.x, (int)t23.z};
+    const int sx0 = (int)t01.x;
     const u32 cf[4] = {t01.y, t01.w, t23.y, t23.w};
-    const int base = sx[0] & ~3;
-    const u32* r0p = reinterpret_cast<const u32*>(src + (size_t)sy0 * S.pitch + base);
-    const u32* r1p = reinterpret_cast<const u32*>(src + (size_t)sy1 * S.pitch + base);
-    const u32 a0 = r0p[0], a1 = r0p[1], a2 = r0p[2];
-    const u32 b0 = r1p[0], b1 = r1p[1], b2 = r1p[2];
-    // the 8 source bytes starting at the first output's tap, per row; output k then picks its two taps (bytes d, d+1 with
-    // d = sx[k] - sx[0] <= 6, checked on the host) with one PRMT whose selector is d | (d+1) << 4
-    const int sh0 = (sx[0] - base) * 8;
-    const u32 alo = __funnelshift_r(a0, a1, sh0), ahi = __funnelshift_r(a1, a2, sh0);
-    const u32 blo = __funnelshift_r(b0, b1, sh0), bhi = __funnelshift_r(b1, b2, sh0);
-    u32 out = 0;
+    const u32 sel[4] = {0x10u, (u32)((int)t01.z - sx0) * 0x11u + 0x10u, (u32)((int)t23.x - sx0) * 0x11u + 0x10u,
+                        (u32)((int)t23.z - sx0) * 0x11u + 0x10u};
+    const int base = sx0 & ~3, sh0 = (sx0 - base) * 8;
+    const u8* col = src + base;
+    auto hpass = [&](int sy, int (&h)[4]) {                          // h[k] = (p0*c0 + p1*c1) >> 4 for the 4 outputs, source row sy
+        const u32* rp = reinterpret_cast<const u32*>(col + (size_t)sy * S.pitch);
+        const u32 w0 = rp[0], w1 = rp[1], w2 = rp[2];
+        const u32 lo = __funnelshift_r(w0, w1, sh0), hi = __funnelshift_r(w1, w2, sh0);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const u32 sel = (u32)(sx[k] - sx[0]) * 0x11u + 0x10u;
-        const int r0 = (int)__dp2a_lo(cf[k], __byte_perm(alo, ahi, sel), 0u);
-        const int r1 = (int)__dp2a_lo(cf[k], __byte_perm(blo, bhi, sel), 0u);
-        // <= 255 by construction (non-negative coefficients summing to 2048 per axis): cv::resize's saturate_cast is a no-op here
-        const int v = (((ty.c0 * (r0 >> 4)) >> 16) + ((ty.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        out |= (u32)v << (8 * k);
+        for (int k = 0; k < 4; k++) h[k] = (int)__dp2a_lo(cf[k], __byte_perm(lo, hi, sel[k]), 0u) >> 4;
+    };
+    auto vpass = [&](const ResizeTap& t, const int (&h0)[4], const int (&h1)[4]) {
+        u32 out = 0;                                                 // <= 255 by construction (coefficients >= 0 summing to 2048 per axis)
+#pragma unroll
+        for (int k = 0; k < 4; k++) out |= (u32)((((t.c0 * h0[k]) >> 16) + ((t.c1 * h1[k]) >> 16) + 2) >> 2) << (8 * k);
+        return out;
+    };
+    int hA0[4], hA1[4], hB0[4], hB1[4];
+    hpass(sA0, hA0);
+    hpass(sA1, hA1);
+    u8* dst = frame + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX;
+    *reinterpret_cast<u32*>(dst) = vpass(ty0, hA0, hA1);
+    if (two) {
+        if (sB0 == sA1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) hB0[k] = hA1[k];
+        } else hpass(sB0, hB0);
+        if (sB1 == sA1) {                                            // (only at the clamped bottom rows)
+#pragma unroll
+            for (int k = 0; k < 4; k++) hB1[k] = hA1[k];
+        } else hpass(sB1, hB1);
+        *reinterpret_cast<u32*>(dst + L.pitch) = vpass(ty1, hB0, hB1);
     }
-    *reinterpret_cast<u32*>(frame + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
 }
 
 // REFLECT_101 border of every level (copyMakeBorder, ORBextractor.cc:1125-1132): `bw` columns left/right and `bh` rows
@@ -1550,7 +1567,7 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
             // y = idx / wq as umulhi(idx, 2^32 / wq + 1) is exact while idx * wq < 2^32 (true up to ~6000 x 6000 levels)
             if (L.fastResize && (unsigned long long)((L.w + 3) >> 2) * ((L.w + 3) >> 2) * L.h < (1ull << 32)) {
                 const u32 wq = (u32)(L.w + 3) >> 2;
-                dim3 gf(orb_div_up((int)wq * L.h, 256), nf);
+                dim3 gf(orb_div_up((int)wq * ((L.h + 1) >> 1), 256), nf);
                 k_resize<<<gf, 256, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab, 0xFFFFFFFFu / wq + 1);
             }
             else k_resize_generic<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
