@@ -301,12 +301,12 @@ def main():
     roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast_tma", "octree": "k_octree", "blur": "k_blur",
                                            "describe": "k_describe"}[dom],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1m_all_kernels_ncu_full.md)
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1n_all_kernels_ncu_full.md)
                 "traffic": ({"fast": 285.9e6, "describe": 601.6e6, "blur": 524.8e6, "octree": 16.0e6}.get(dom, 0) * args.chunk / 256) or None,
                 "peak_source": peak_src, "avg_launch_ms": dom_launch_s * 1e3, "algorithmic_bytes_per_frame": stage_bytes[dom],
                 "stage_ms_per_step": {k: v * 1e3 for k, v in stage_s.items()},
                 # what actually bounds it: warp-instruction issue.  540.3 M warp-instructions per 256-frame k_fast_tma launch (ncu,
-                # profiles/r1m_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
+                # profiles/r1n_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
                 "issue": ({"warp_inst_per_launch": 540.3e6 * args.chunk / 256,
                            "achieved_ginst_s": 540.3e6 * args.chunk / 256 / dom_launch_s / 1e9,
                            "peak_ginst_s": 148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
