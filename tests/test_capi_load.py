@@ -34,6 +34,17 @@ def test_no_cpu_fallback_without_gpu():
         orb.ORBmatcher().hamming_top2(np.zeros((4, 32), np.uint8), np.zeros((4, 32), np.uint8))
     with pytest.raises(orb.OrbError):
         orb.ORBmatcher.DescriptorDistance(np.zeros(32, np.uint8), np.zeros(32, np.uint8))
+    # the widened rows fail the same way: window searches, vocabulary
+    n = 8
+    g = orb.GridView(np.zeros((n, 32), np.uint8), np.linspace(10, 600, n), np.linspace(10, 400, n), np.zeros(n, np.int32),
+                     np.ones(8, np.float32), (0.0, 0.0, 640.0, 480.0), angle=np.zeros(n, np.float32))
+    assert g.cell_offsets[-1] == n and len(g.cell_offsets) == 64 * 48 + 1            # host-side grid build needs no GPU
+    with pytest.raises(orb.OrbError):
+        orb.ORBmatcher().SearchForInitialization(g, np.zeros((n, 32), np.uint8), np.zeros(n, np.int32), np.zeros(n, np.float32),
+                                                 np.zeros((n, 2), np.float32), 100)
+    with pytest.raises(orb.OrbError):
+        orb.ORBmatcher().SearchWindowsBest(g, np.ones(n, np.uint8), np.zeros(n), np.zeros(n), np.ones(n), np.zeros(n, np.int32),
+                                           np.zeros(n, np.int32), np.zeros((n, 32), np.uint8))
 
 
 def test_product_never_imports_oracle():
