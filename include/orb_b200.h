@@ -320,6 +320,86 @@ int orbm_search_windows_best(const orbm_grid_view* target, int nq, const uint8_t
  * per second on `device` over a register-resident loop. */
 int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Map archive: the fork's System::SaveMap / LoadMap file (src/System.cc:552-574) as a source of real keyframe
+ * descriptor sets for the matcher.  Host-only: parses / writes the Boost binary archive (`no_header`, `oa << mpMap`) whose
+ * field order is Map::save/load (src/Map.cc:31-134), MapPoint::save/load (src/MapPoint.cc:59-213), KeyFrame::save/load
+ * (src/KeyFrame.cc:86-510) and the cv::Mat / cv::KeyPoint serializers of include/MapPoint.h:198-247.  The byte framing is
+ * documented in orbslam_mapsave_b200/csrc/orb_map.cpp.  Boost is absent from this image: layout parity is unpinned.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct orbmap_archive orbmap_archive;
+
+typedef struct orbmap_info {
+    int32_t n_mappoints, n_keyframes, n_origins;     /* mspMapPoints, mspKeyFrames, mvpKeyFrameOrigins */
+    uint32_t test_data;                              /* 0xdeadbeef when the load sequence matched (src/Map.cc:127-131) */
+    uint64_t max_kf_id;                              /* mnMaxKFid */
+    int64_t total_features;                          /* sum of mDescriptors.rows over the keyframes */
+    int64_t total_observations;                      /* sum of mObservations sizes over the map points */
+    int64_t trailing_bytes;                          /* bytes Map::load leaves unread (Map::save's second map-point block) */
+} orbmap_info;
+
+typedef struct orbmap_keyframe_info {
+    uint64_t id, frame_id, next_id, parent_id;       /* mnId, mnFrameId, KeyFrame::nNextId, mpParent->mnId */
+    double timestamp;
+    int32_t n;                                       /* N */
+    int32_t n_keys, n_keys_un, n_uright, n_depth;    /* vector sizes as stored */
+    int32_t desc_rows, desc_cols;                    /* mDescriptors: rows x bytes per row (32) */
+    int32_t n_mappoint_slots;                        /* mvpMapPoints.size() */
+    int32_t n_levels, n_scale_factors;               /* mnScaleLevels, mvScaleFactors.size() */
+    int32_t grid_cols, grid_rows, min_x, min_y, max_x, max_y;
+    int32_t n_connected, n_ordered, n_children, n_loop_edges;
+    int32_t has_parent, is_bad, not_erase, to_be_erased, first_connection;
+    float scale_factor, log_scale_factor, fx, fy, cx, cy, invfx, invfy, bf, b, th_depth, grid_inv_w, grid_inv_h, half_baseline;
+} orbmap_keyframe_info;
+
+/* Replaces System::LoadMap (src/System.cc:552-563) as far as the data goes: every field of the archive is kept. */
+int orbmap_load(orbmap_archive** out, const char* path);
+/* Replaces System::SaveMap (src/System.cc:565-574): writes the archive back, byte-identical for a loaded file. */
+int orbmap_save(const orbmap_archive* ar, const char* path);
+int orbmap_create(orbmap_archive** out);             /* an empty map to fill with orbmap_add_* */
+void orbmap_destroy(orbmap_archive* ar);
+int orbmap_get_info(const orbmap_archive* ar, orbmap_info* info);
+/* group 0 = mspKeyFrames, 1 = mvpKeyFrameOrigins (stored as full KeyFrame records, src/Map.cc:52-56); i = position in the file */
+int orbmap_keyframe_get_info(const orbmap_archive* ar, int group, int i, orbmap_keyframe_info* info);
+/* Copies of the per-feature arrays; any pointer may be NULL.  keys / keys_un: n_keys / n_keys_un records (`size` is 0: the
+ * fork's cv::KeyPoint serializer never stores it); desc: desc_rows x 32; mappoint_ids[n_mappoint_slots]: mnId or -1;
+ * scale_factors / level_sigma2 / inv_level_sigma2: n_scale_factors floats; Tcw: 16 floats; K: 9 floats. */
+int orbmap_keyframe_arrays(const orbmap_archive* ar, int group, int i, orbx_keypoint* keys, orbx_keypoint* keys_un, float* uright,
+                           float* depth, uint8_t* desc, int64_t* mappoint_ids, float* scale_factors, float* level_sigma2,
+                           float* inv_level_sigma2, float* Tcw, float* K);
+/* Covisibility / spanning-tree ids (-1 = entry stored without an id). */
+int orbmap_keyframe_links(const orbmap_archive* ar, int group, int i, int64_t* connected_ids, int32_t* connected_weights,
+                          int64_t* ordered_ids, int32_t* ordered_weights, int64_t* children_ids, int64_t* loop_edge_ids);
+/* mGrid as the CSR that orbm_grid_view takes (cells column-major like mGrid[col][row]); with both arrays NULL only the
+ * counts are returned. */
+int orbmap_keyframe_grid(const orbmap_archive* ar, int group, int i, int32_t* cell_offsets, int32_t* cell_features, int capacity,
+                         int32_t* n_cells, int32_t* n_entries);
+/* All map points in file order; any pointer may be NULL.  world_pos / normal: 3 floats each; desc: 32 bytes each;
+ * ref_kf: mnId or -1; obs_offsets[n_mappoints + 1]: CSR offsets into orbmap_observations' arrays. */
+int orbmap_mappoints(const orbmap_archive* ar, uint64_t* ids, float* world_pos, float* normal, uint8_t* desc, int64_t* ref_kf,
+                     uint8_t* bad, int32_t* n_obs, int32_t* visible, int32_t* found, float* min_dist, float* max_dist,
+                     int32_t* obs_offsets);
+int orbmap_observations(const orbmap_archive* ar, int64_t* kf_ids, int64_t* feature_idx);
+/* The gather loop of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:495-510) for every map point: the observed
+ * keyframe rows back to back (capacity in descriptors), offsets[n_mappoints + 1]; the input of orbm_distinctive_descriptors.
+ * With desc == NULL only the offsets / total are produced. */
+int orbmap_observed_descriptors(const orbmap_archive* ar, uint8_t* desc, int32_t* offsets, int64_t capacity, int64_t* n_total);
+/* Building a map from flat arrays (what Map::save would be fed from a live Map). */
+int orbmap_add_mappoint(orbmap_archive* ar, uint64_t id, int64_t first_kf_id, const float* world_pos, const float* normal,
+                        const uint8_t* desc, int64_t ref_kf_id, int n_obs, const int64_t* obs_kf_ids, const int64_t* obs_feature_idx,
+                        int visible, int found, float min_dist, float max_dist);
+/* Uses of `info`: id, frame_id, timestamp, n, n_levels, scale_factor, log_scale_factor, intrinsics, bounds, grid size (0 = 64 x 48),
+ * has_parent / parent_id and the flags.  Twc / Ow / Cw follow KeyFrame::SetPose (src/KeyFrame.cc:792-806), mGrid follows
+ * Frame::AssignFeaturesToGrid (src/Frame.cc:341-356). */
+int orbmap_add_keyframe(orbmap_archive* ar, const orbmap_keyframe_info* info, const orbx_keypoint* keys, const orbx_keypoint* keys_un,
+                        const float* uright, const float* depth, const uint8_t* desc, const int64_t* mappoint_ids,
+                        const float* scale_factors, const float* level_sigma2, const float* inv_level_sigma2, const float* Tcw,
+                        const float* K);
+int orbmap_set_keyframe_links(orbmap_archive* ar, int i, int n_connected, const int64_t* connected_ids, const int32_t* connected_weights,
+                              int n_ordered, const int64_t* ordered_ids, const int32_t* ordered_weights, int n_children,
+                              const int64_t* children_ids, int n_loop_edges, const int64_t* loop_edge_ids);
+int orbmap_add_origin(orbmap_archive* ar, int keyframe_index);
+
 #ifdef __cplusplus
 }
 #endif

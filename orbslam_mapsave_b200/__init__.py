@@ -8,3 +8,4 @@ from .extractor import ORBextractor                                  # noqa: F40
 from . import matcher                                                                    # noqa: F401
 from .matcher import ORBmatcher, FeatureVector, View, GridView, popc_peak, distinctive_descriptors      # noqa: F401
 from .vocabulary import ORBVocabulary                                  # noqa: F401
+from .map_archive import MapArchive                                   # noqa: F401

@@ -32,6 +32,9 @@ SYMBOLS = [
     "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_for_initialization", "orbm_search_windows", "orbm_search_windows_best",
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
     "orbv_transform_device",
+    "orbmap_load", "orbmap_save", "orbmap_create", "orbmap_destroy", "orbmap_get_info", "orbmap_keyframe_get_info",
+    "orbmap_keyframe_arrays", "orbmap_keyframe_links", "orbmap_keyframe_grid", "orbmap_mappoints", "orbmap_observations",
+    "orbmap_observed_descriptors", "orbmap_add_mappoint", "orbmap_add_keyframe", "orbmap_set_keyframe_links", "orbmap_add_origin",
 ]
 
 
@@ -57,6 +60,24 @@ class GridViewC(C.Structure):
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("inv_w", C.c_float),
                 ("inv_h", C.c_float), ("cell_offsets", C.c_void_p), ("cell_features", C.c_void_p), ("scale_factors", C.c_void_p),
                 ("n_levels", C.c_int)]
+
+
+class MapInfoC(C.Structure):
+    """orbmap_info of include/orb_b200.h"""
+    _fields_ = [("n_mappoints", C.c_int32), ("n_keyframes", C.c_int32), ("n_origins", C.c_int32), ("test_data", C.c_uint32),
+                ("max_kf_id", C.c_uint64), ("total_features", C.c_int64), ("total_observations", C.c_int64),
+                ("trailing_bytes", C.c_int64)]
+
+
+class MapKeyFrameInfoC(C.Structure):
+    """orbmap_keyframe_info of include/orb_b200.h"""
+    _fields_ = ([(n, C.c_uint64) for n in ("id", "frame_id", "next_id", "parent_id")] + [("timestamp", C.c_double)] +
+                [(n, C.c_int32) for n in ("n", "n_keys", "n_keys_un", "n_uright", "n_depth", "desc_rows", "desc_cols",
+                                          "n_mappoint_slots", "n_levels", "n_scale_factors", "grid_cols", "grid_rows", "min_x", "min_y",
+                                          "max_x", "max_y", "n_connected", "n_ordered", "n_children", "n_loop_edges", "has_parent",
+                                          "is_bad", "not_erase", "to_be_erased", "first_connection")] +
+                [(n, C.c_float) for n in ("scale_factor", "log_scale_factor", "fx", "fy", "cx", "cy", "invfx", "invfy", "bf", "b",
+                                          "th_depth", "grid_inv_w", "grid_inv_h", "half_baseline")])
 
 
 _lib = None
@@ -154,6 +175,39 @@ def lib():
     L.orbv_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.orbv_transform_device.restype = i32
     L.orbv_transform_device.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
+    i64, u64 = C.c_int64, C.c_uint64
+    L.orbmap_load.restype = i32
+    L.orbmap_load.argtypes = [C.POINTER(vp), C.c_char_p]
+    L.orbmap_save.restype = i32
+    L.orbmap_save.argtypes = [vp, C.c_char_p]
+    L.orbmap_create.restype = i32
+    L.orbmap_create.argtypes = [C.POINTER(vp)]
+    L.orbmap_destroy.restype = None
+    L.orbmap_destroy.argtypes = [vp]
+    L.orbmap_get_info.restype = i32
+    L.orbmap_get_info.argtypes = [vp, C.POINTER(MapInfoC)]
+    L.orbmap_keyframe_get_info.restype = i32
+    L.orbmap_keyframe_get_info.argtypes = [vp, i32, i32, C.POINTER(MapKeyFrameInfoC)]
+    L.orbmap_keyframe_arrays.restype = i32
+    L.orbmap_keyframe_arrays.argtypes = [vp, i32, i32] + [vp] * 11
+    L.orbmap_keyframe_links.restype = i32
+    L.orbmap_keyframe_links.argtypes = [vp, i32, i32] + [vp] * 6
+    L.orbmap_keyframe_grid.restype = i32
+    L.orbmap_keyframe_grid.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp]
+    L.orbmap_mappoints.restype = i32
+    L.orbmap_mappoints.argtypes = [vp] * 13
+    L.orbmap_observations.restype = i32
+    L.orbmap_observations.argtypes = [vp, vp, vp]
+    L.orbmap_observed_descriptors.restype = i32
+    L.orbmap_observed_descriptors.argtypes = [vp, vp, vp, i64, vp]
+    L.orbmap_add_mappoint.restype = i32
+    L.orbmap_add_mappoint.argtypes = [vp, u64, i64, vp, vp, vp, i64, i32, vp, vp, i32, i32, f32, f32]
+    L.orbmap_add_keyframe.restype = i32
+    L.orbmap_add_keyframe.argtypes = [vp, C.POINTER(MapKeyFrameInfoC)] + [vp] * 11
+    L.orbmap_set_keyframe_links.restype = i32
+    L.orbmap_set_keyframe_links.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, i32, vp, i32, vp]
+    L.orbmap_add_origin.restype = i32
+    L.orbmap_add_origin.argtypes = [vp, i32]
     _lib = L
     return L
 

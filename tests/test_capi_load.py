@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_header_symbol():
     hdr = open(os.path.join(ROOT, "include", "orb_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(orb[xmv]?_[a-z0-9_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(orb(?:[xmv]|map)?_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
     L = orb.lib()
     for s in declared:
