@@ -1767,9 +1767,27 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
         }
         return ORB_OK;
     }
-    int chunk = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += B, chunk++) {
-        const int nf = std::min(B, n_frames - f0), sl = chunk & 1;
+    // Chunk schedule.  The pipeline's fill (H2D of the first chunk, nothing to compute yet) and drain (compute + D2H of the last
+    // chunk, nothing left to copy in) are pure overhead, and both are proportional to the size of the chunk at that end; the
+    // steady state wants large chunks (fewer, fuller launches).  So the call ramps up 32, 64, ... < B frames, runs chunks of B,
+    // and ramps down again.  ORBX_E2E_RAMP=0 restores equal chunks (A/B measurements).
+    std::vector<int> sizes;
+    {
+        static const bool ramp = [] { const char* e = getenv("ORBX_E2E_RAMP"); return !(e && e[0] == '0'); }();
+        std::vector<int> head;
+        int hsum = 0;
+        if (ramp)
+            for (int c = 32; c < B && n_frames - 2 * (hsum + c) >= B; c *= 2) { head.push_back(c); hsum += c; }
+        int mid = n_frames - 2 * hsum;
+        sizes = head;
+        for (; mid > 0; mid -= B) sizes.push_back(std::min(B, mid));
+        if (!head.empty() && sizes.back() < B && sizes.size() > head.size() + 1)          // keep the ragged chunk away from the tail
+            std::swap(sizes.back(), sizes[head.size()]);
+        sizes.insert(sizes.end(), head.rbegin(), head.rend());
+    }
+    int chunk = 0, f0 = 0;
+    for (size_t ci = 0; ci < sizes.size(); f0 += sizes[ci], ci++, chunk++) {
+        const int nf = sizes[ci], sl = chunk & 1;
         // ---- H2D (slot's input buffer is free once the compute of chunk-2 has finished)
         if (chunk >= 2) ORB_CUDA_TRY(cudaStreamWaitEvent(ex->sH2D, ex->evComp[sl], 0));
         if ((size_t)stride == (size_t)width && frame_stride == fpx) {

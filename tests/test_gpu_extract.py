@@ -137,6 +137,24 @@ def test_batch_matches_single_and_oracle():
     print(f"angle float mismatches: {nang}, descriptor bit mismatches: {nbits} over {int(n.sum())} keypoints")
 
 
+def test_ramped_chunk_schedule_matches_single_calls():
+    """orbx_extract_batch over many passes uses a ramped chunk schedule (32, 8, 64, 64, 32 frames here) to shorten the pipeline's
+    fill and drain; every frame must come back in its own slot, identical to a single-frame call."""
+    base = [synth(640, 480, s) for s in range(40, 50)]
+    frames = np.stack([np.roll(base[i % 10], 3 * (i // 10), axis=1) for i in range(200)])
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=64)
+    kp, desc, n = ex.extract_batch(frames)
+    one = orb.ORBextractor(1000, 1.2, 8, 20, 7)
+    for f in range(len(frames)):
+        k1, d1 = one(frames[f])
+        assert n[f] == len(k1), f
+        assert np.array_equal(kp[f, :n[f]].view(np.uint32), k1.view(np.uint32).reshape(-1)) or \
+            np.array_equal(kp[f, :n[f]].tobytes(), k1.tobytes()), f
+        assert np.array_equal(desc[f, :n[f]], d1), f
+    okp, odesc = orc.Extractor(1000, 1.2, 8, 20, 7).extract(frames[137])
+    _compare(kp[137, :n[137]], desc[137, :n[137]], okp, odesc)
+
+
 def test_device_resident_batch_idempotent():
     import torch
     frames = torch.from_numpy(np.stack([synth(640, 480, s) for s in range(30, 34)])).cuda()
