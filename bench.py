@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--unique", type=int, default=4096, help="distinct synthetic frames per GPU (others repeat them)")
     ap.add_argument("--chunk", type=int, default=512, help="frames per device pass of the device-resident measurement (workspace size)")
-    ap.add_argument("--e2e-chunk", type=int, default=256, help="frames per pipelined chunk of the host-buffer (e2e) path")
+    ap.add_argument("--e2e-chunk", type=int, default=128, help="frames per pipelined chunk of the host-buffer (e2e) path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-match", action="store_true", help="skip the matching sub-benchmark")
     ap.add_argument("--match-q", type=int, default=32, help="query keyframes per GPU in the matching sub-benchmark")

@@ -1186,6 +1186,10 @@ static inline int h_cvRoundD(double v) { return (int)nearbyint(v); }
 static inline int h_cvFloor(double v) { int i = (int)v; return i - (i > v); }
 static inline int h_cvCeil(double v) { int i = (int)v; return i + (i < v); }
 
+// staging slots of the pipelined host-buffer path (orbx_extract_batch): with H2D time ~ compute time two slots run the copy and
+// compute streams in lock-step (each waits for the other's previous chunk), so any jitter stalls both; four let the copies run ahead
+#define ORBX_MAX_SLOTS 6
+#define ORBX_MAX_HELPERS 3
 struct orbx_extractor {
     int nfeatures, nlevels, iniTh, minTh, device, maxBatch, candPerCell;
     double scaleFactor;
@@ -1196,16 +1200,16 @@ struct orbx_extractor {
     // device workspace
     u8 *d_pyr = nullptr, *d_blur = nullptr;
     // host-buffer path: two staging slots so that H2D(chunk i+1), compute(chunk i) and D2H(chunk i-1) overlap
-    u8 *d_in[2] = {nullptr, nullptr}, *d_mask[2] = {nullptr, nullptr}, *d_desc[2] = {nullptr, nullptr};
-    orbx_keypoint* d_kp[2] = {nullptr, nullptr};
-    int* d_n[2] = {nullptr, nullptr};
+    u8 *d_in[ORBX_MAX_SLOTS] = {}, *d_mask[ORBX_MAX_SLOTS] = {}, *d_desc[ORBX_MAX_SLOTS] = {};
+    orbx_keypoint* d_kp[ORBX_MAX_SLOTS] = {};
+    int* d_n[ORBX_MAX_SLOTS] = {};
     int* h_n = nullptr;                    // pinned staging for the per-frame counts
     int* h_status = nullptr;               // pinned mirror of the device status word
     u8* h_stage = nullptr;                 // pinned staging for the latency path when the caller's buffers are pageable
     size_t h_stage_cap = 0;
     size_t h_n_cap = 0;
     cudaStream_t sH2D = nullptr, sD2H = nullptr;
-    cudaEvent_t evH2D[2] = {nullptr, nullptr}, evComp[2] = {nullptr, nullptr}, evD2H[2] = {nullptr, nullptr};
+    cudaEvent_t evH2D[ORBX_MAX_SLOTS] = {}, evComp[ORBX_MAX_SLOTS] = {}, evD2H[ORBX_MAX_SLOTS] = {};
     uint2 *d_cand = nullptr, *d_sel = nullptr;
     u32* d_nodeOf = nullptr;
     int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr, *d_workCounter = nullptr;
@@ -1224,6 +1228,10 @@ struct orbx_extractor {
     u8* d_stereo = nullptr;                // scratch of orbx_stereo_matches
     size_t stereoCap = 0;
     std::mutex mu;
+    // orbx_extract_batch over several passes: helper handles (own stream and workspace each) take chunks in turn, so that the
+    // launch gaps and kernel tails of one pass (13 dependent kernels, ~0.1 ms per pass) are filled by another pass's work
+    orbx_extractor* helpers[ORBX_MAX_HELPERS] = {};
+    int nHelpers = 0;
 };
 
 static void build_resize_taps(int ssize, int dsize, bool clampX, std::vector<ResizeTap>& out) {
@@ -1504,9 +1512,10 @@ extern "C" int orbx_create(orbx_extractor** out, int nfeatures, float scale_fact
 
 extern "C" void orbx_destroy(orbx_extractor* ex) {
     if (!ex) return;
+    for (int i = 0; i < ORBX_MAX_HELPERS; i++) if (ex->helpers[i]) { orbx_destroy(ex->helpers[i]); ex->helpers[i] = nullptr; }
     cudaSetDevice(ex->device);
     cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_stereo);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < ORBX_MAX_SLOTS; i++) {
         cudaFree(ex->d_in[i]); cudaFree(ex->d_mask[i]); cudaFree(ex->d_desc[i]); cudaFree(ex->d_kp[i]); cudaFree(ex->d_n[i]);
         if (ex->evH2D[i]) cudaEventDestroy(ex->evH2D[i]);
         if (ex->evComp[i]) cudaEventDestroy(ex->evComp[i]);
@@ -1541,7 +1550,12 @@ extern "C" int orbx_level_size(const orbx_extractor* ex, int level, int* w, int*
     return ORB_OK;
 }
 extern "C" int orbx_max_keypoints(const orbx_extractor* ex) { return ex ? ex->capInternal : 0; }
-extern "C" long long orbx_launch_count(const orbx_extractor* ex) { return ex ? ex->launches : 0; }
+extern "C" long long orbx_launch_count(const orbx_extractor* ex) {
+    if (!ex) return 0;
+    long long n = ex->launches;
+    for (int i = 0; i < ORBX_MAX_HELPERS; i++) if (ex->helpers[i]) n += ex->helpers[i]->launches;
+    return n;
+}
 
 // One device pass over nf <= maxBatch frames.
 static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, int nf, orbx_keypoint* d_kp, u8* d_desc,
@@ -1672,7 +1686,9 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
     const size_t fpx = (size_t)width * height;
     std::lock_guard<std::mutex> lk(ex->mu);
     ORB_CUDA_TRY(cudaSetDevice(ex->device));
-    const int nslots = n_frames > B ? 2 : 1;
+    static const int maxSlots = [] { const char* e = getenv("ORBX_E2E_SLOTS"); const int v = e ? atoi(e) : ORBX_MAX_SLOTS;
+                                     return std::max(2, std::min(ORBX_MAX_SLOTS, v)); }();      // must exceed the number of compute streams
+    const int nslots = n_frames > B ? maxSlots : 1;
     for (int i = 0; i < nslots; i++) {
         if (!ex->d_in[i]) {
             ORB_CUDA_TRY(cudaMalloc(&ex->d_in[i], (size_t)B * fpx));
@@ -1696,6 +1712,17 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
         ex->h_n_cap = n_frames;
     }
     const int ccap = std::min(cap, icap);             // keypoints copied back per frame (the rest of a row cannot be used)
+    if (nslots > 1) {
+        static const int nStreams = [] { const char* e = getenv("ORBX_E2E_STREAMS"); const int v = e ? atoi(e) : 2;
+                                         return std::max(1, std::min(1 + ORBX_MAX_HELPERS, v)); }();
+        for (int i = 0; i < nStreams - 1; i++)
+            if (!ex->helpers[i]) {
+                int rc = orbx_create(&ex->helpers[i], ex->nfeatures, (float)ex->scaleFactor, ex->nlevels, ex->iniTh, ex->minTh, width, height,
+                                     B, ex->device);
+                if (rc != ORB_OK) return rc;
+            }
+        ex->nHelpers = nStreams - 1;
+    }
     if (!ex->h_status) ORB_CUDA_TRY(cudaMallocHost(&ex->h_status, sizeof(int)));
     if (n_frames <= B) {
         // ---- latency path (one device pass, e.g. the per-frame call of Frame::ExtractORB): a single stream, a single
@@ -1767,29 +1794,38 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
         }
         return ORB_OK;
     }
-    // Chunk schedule.  The pipeline's fill (H2D of the first chunk, nothing to compute yet) and drain (compute + D2H of the last
-    // chunk, nothing left to copy in) are pure overhead, and both are proportional to the size of the chunk at that end; the
-    // steady state wants large chunks (fewer, fuller launches).  So the call ramps up 32, 64, ... < B frames, runs chunks of B,
-    // and ramps down again.  ORBX_E2E_RAMP=0 restores equal chunks (A/B measurements).
+    // Chunk schedule.  Measured with ORBX_E2E_TRACE (tools/e2e_trace.py): the compute stream is the busy one (a pass costs about
+    // 0.18 ms + 5.7 us per 640x480 frame, the copy 5.6 us per frame), so the step is  fill + sum of passes + drain  with
+    // fill = H2D of the first chunk and drain = D2H of the last one.  Few large passes minimise the sum; a small first and last
+    // chunk (64 frames) minimise fill and drain.  ORBX_E2E_RAMP=0 restores equal chunks (A/B measurements).
     std::vector<int> sizes;
     {
         static const bool ramp = [] { const char* e = getenv("ORBX_E2E_RAMP"); return !(e && e[0] == '0'); }();
-        std::vector<int> head;
-        int hsum = 0;
-        if (ramp)
-            for (int c = 32; c < B && n_frames - 2 * (hsum + c) >= B; c *= 2) { head.push_back(c); hsum += c; }
-        int mid = n_frames - 2 * hsum;
-        sizes = head;
-        for (; mid > 0; mid -= B) sizes.push_back(std::min(B, mid));
-        if (!head.empty() && sizes.back() < B && sizes.size() > head.size() + 1)          // keep the ragged chunk away from the tail
-            std::swap(sizes.back(), sizes[head.size()]);
-        sizes.insert(sizes.end(), head.rbegin(), head.rend());
+        const int edge = (ramp && B > 64 && n_frames >= 2 * B) ? 64 : 0;
+        if (edge) sizes.push_back(edge);
+        for (int mid = n_frames - 2 * edge; mid > 0; mid -= B) sizes.push_back(std::min(B, mid));
+        if (edge) sizes.push_back(edge);
     }
+    // ORBX_E2E_TRACE=1: per-chunk device timeline of the three streams on stderr (a profiling aid, not used by the product path)
+    static const bool trace = [] { const char* e = getenv("ORBX_E2E_TRACE"); return e && e[0] == '1'; }();
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tev.push_back(e);
+    };
     int chunk = 0, f0 = 0;
     for (size_t ci = 0; ci < sizes.size(); f0 += sizes[ci], ci++, chunk++) {
-        const int nf = sizes[ci], sl = chunk & 1;
-        // ---- H2D (slot's input buffer is free once the compute of chunk-2 has finished)
-        if (chunk >= 2) ORB_CUDA_TRY(cudaStreamWaitEvent(ex->sH2D, ex->evComp[sl], 0));
+        const int nf = sizes[ci], sl = chunk % nslots;
+        // the handle (stream + workspace) computing this chunk; the last chunk is always ex's own, so that the views of the last pass
+        // (orbx_get_pyramid*, orbx_stereo_matches) keep their meaning
+        const int hsel = (int)((sizes.size() - 1 - ci) % (size_t)(ex->nHelpers + 1));
+        orbx_extractor* cx = hsel ? ex->helpers[hsel - 1] : ex;
+        // ---- H2D (slot's input buffer is free once the compute of chunk-nslots has finished)
+        if (chunk >= nslots) ORB_CUDA_TRY(cudaStreamWaitEvent(ex->sH2D, ex->evComp[sl], 0));
+        mark(ex->sH2D);
         if ((size_t)stride == (size_t)width && frame_stride == fpx) {
             ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[sl], images + (size_t)f0 * frame_stride, (size_t)nf * fpx, cudaMemcpyHostToDevice, ex->sH2D));
         } else {
@@ -1801,29 +1837,50 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
             for (int f = 0; f < nf; f++)
                 ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_mask[sl] + f * fpx, width, masks + (size_t)(f0 + f) * mask_frame_stride, mask_stride,
                                                width, height, cudaMemcpyHostToDevice, ex->sH2D));
+        mark(ex->sH2D);
         ORB_CUDA_TRY(cudaEventRecord(ex->evH2D[sl], ex->sH2D));
-        // ---- compute (slot's output buffers are free once the D2H of chunk-2 has finished)
-        ORB_CUDA_TRY(cudaStreamWaitEvent(ex->stream, ex->evH2D[sl], 0));
-        if (chunk >= 2) ORB_CUDA_TRY(cudaStreamWaitEvent(ex->stream, ex->evD2H[sl], 0));
-        int rc = run_pass(ex, ex->d_in[sl], masks ? ex->d_mask[sl] : nullptr, nf, ex->d_kp[sl], ex->d_desc[sl], icap, ex->d_n[sl],
-                          ORBX_STAGE_ALL, ex->stream);
+        // ---- compute (slot's output buffers are free once the D2H of chunk-nslots has finished)
+        ORB_CUDA_TRY(cudaStreamWaitEvent(cx->stream, ex->evH2D[sl], 0));
+        if (chunk >= nslots) ORB_CUDA_TRY(cudaStreamWaitEvent(cx->stream, ex->evD2H[sl], 0));
+        mark(cx->stream);
+        int rc = run_pass(cx, ex->d_in[sl], masks ? ex->d_mask[sl] : nullptr, nf, ex->d_kp[sl], ex->d_desc[sl], icap, ex->d_n[sl],
+                          ORBX_STAGE_ALL, cx->stream);
         if (rc != ORB_OK) return rc;
-        ORB_CUDA_TRY(cudaEventRecord(ex->evComp[sl], ex->stream));
+        mark(cx->stream);
+        ORB_CUDA_TRY(cudaEventRecord(ex->evComp[sl], cx->stream));
         // ---- D2H: counts, then the padded keypoint / descriptor rows in one 2-D copy each
         ORB_CUDA_TRY(cudaStreamWaitEvent(ex->sD2H, ex->evComp[sl], 0));
+        mark(ex->sD2H);
         ORB_CUDA_TRY(cudaMemcpyAsync(ex->h_n + f0, ex->d_n[sl], nf * sizeof(int), cudaMemcpyDeviceToHost, ex->sD2H));
         ORB_CUDA_TRY(cudaMemcpy2DAsync(kp_out + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_keypoint), ex->d_kp[sl],
                                        (size_t)icap * sizeof(orbx_keypoint), (size_t)ccap * sizeof(orbx_keypoint), nf,
                                        cudaMemcpyDeviceToHost, ex->sD2H));
         ORB_CUDA_TRY(cudaMemcpy2DAsync(desc_out + (size_t)f0 * cap * 32, (size_t)cap * 32, ex->d_desc[sl], (size_t)icap * 32,
                                        (size_t)ccap * 32, nf, cudaMemcpyDeviceToHost, ex->sD2H));
+        mark(ex->sD2H);
         ORB_CUDA_TRY(cudaEventRecord(ex->evD2H[sl], ex->sD2H));
     }
     ORB_CUDA_TRY(cudaStreamSynchronize(ex->sD2H));
     ORB_CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    for (int i = 0; i < ex->nHelpers; i++) ORB_CUDA_TRY(cudaStreamSynchronize(ex->helpers[i]->stream));
+    if (trace) {
+        fprintf(stderr, "chunk frames   h2d[start end]   compute[start end]   d2h[start end]  (ms since the first copy started)\n");
+        for (size_t c = 0; c < sizes.size(); c++) {
+            float t[6];
+            for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], tev[0], tev[6 * c + k]);
+            fprintf(stderr, "%3zu %5d   %7.3f %7.3f   %7.3f %7.3f   %7.3f %7.3f\n", c, sizes[c], t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     int s = 0;
     ORB_CUDA_TRY(cudaMemcpy(&s, ex->d_status, sizeof(int), cudaMemcpyDeviceToHost));
     if (s) ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
+    for (int i = 0; i < ex->nHelpers; i++) {
+        int s2 = 0;
+        ORB_CUDA_TRY(cudaMemcpy(&s2, ex->helpers[i]->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+        if (s2) ORB_CUDA_TRY(cudaMemset(ex->helpers[i]->d_status, 0, sizeof(int)));
+        s |= s2;
+    }
     ORB_REQUIRE(!(s & (ORB_DEV_CAND_OVERFLOW | ORB_DEV_NODE_OVERFLOW)), ORB_ERR_OVERFLOW,
                 "FAST candidate buffer overflow (ORBX_CAND_PER_CELL=%d caps it; unset it to size for the worst case)", ex->candPerCell);
     for (int f = 0; f < n_frames; f++) {

@@ -138,11 +138,11 @@ def test_batch_matches_single_and_oracle():
 
 
 def test_ramped_chunk_schedule_matches_single_calls():
-    """orbx_extract_batch over many passes uses a ramped chunk schedule (32, 8, 64, 64, 32 frames here) to shorten the pipeline's
-    fill and drain; every frame must come back in its own slot, identical to a single-frame call."""
+    """orbx_extract_batch over many passes uses small first / last chunks (64, 128, 128, 16, 64 frames here) to shorten the
+    pipeline's fill and drain, over four staging slots; every frame must come back in its own slot, identical to a single-frame call."""
     base = [synth(640, 480, s) for s in range(40, 50)]
-    frames = np.stack([np.roll(base[i % 10], 3 * (i // 10), axis=1) for i in range(200)])
-    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=64)
+    frames = np.stack([np.roll(base[i % 10], 3 * (i // 10), axis=1) for i in range(400)])
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=128)
     kp, desc, n = ex.extract_batch(frames)
     one = orb.ORBextractor(1000, 1.2, 8, 20, 7)
     for f in range(len(frames)):
