@@ -1648,6 +1648,8 @@ extern "C" int orbx_run_stages_device(orbx_extractor* ex, const uint8_t* d_image
     ORB_CUDA_TRY(cudaSetDevice(ex->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ex->stream;
     const size_t fpx = (size_t)ex->plan.width * ex->plan.height;
+    // (Alternating the passes between two handles on forked streams was measured and is slower here: 167 k vs 170 k frames/s —
+    // two concurrent passes double the working set; profiles/README.md.)
     for (int f0 = 0; f0 < n_frames; f0 += ex->maxBatch) {
         const int nf = std::min(ex->maxBatch, n_frames - f0);
         int rc = run_pass(ex, d_images + f0 * fpx, d_masks ? d_masks + f0 * fpx : nullptr, nf, d_kp_out + (size_t)f0 * cap,
@@ -1668,6 +1670,13 @@ extern "C" int orbx_check_status(orbx_extractor* ex) {
     ORB_CUDA_TRY(cudaSetDevice(ex->device));
     ORB_CUDA_TRY(cudaMemcpy(&s, ex->d_status, sizeof(int), cudaMemcpyDeviceToHost));
     if (s) ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
+    for (int i = 0; i < ORBX_MAX_HELPERS; i++)
+        if (ex->helpers[i]) {
+            int s2 = 0;
+            ORB_CUDA_TRY(cudaMemcpy(&s2, ex->helpers[i]->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+            if (s2) ORB_CUDA_TRY(cudaMemset(ex->helpers[i]->d_status, 0, sizeof(int)));
+            s |= s2;
+        }
     ORB_REQUIRE(!(s & (ORB_DEV_CAND_OVERFLOW | ORB_DEV_NODE_OVERFLOW)), ORB_ERR_OVERFLOW,
                 "FAST candidate buffer overflow (ORBX_CAND_PER_CELL=%d caps it; unset it to size for the worst case)", ex->candPerCell);
     ORB_REQUIRE(!(s & ORB_DEV_OUT_OVERFLOW), ORB_ERR_CAPACITY, "keypoint output capacity too small (need orbx_max_keypoints())");

@@ -155,6 +155,34 @@ def test_ramped_chunk_schedule_matches_single_calls():
     _compare(kp[137, :n[137]], desc[137, :n[137]], okp, odesc)
 
 
+def test_device_resident_multi_pass_matches_single_calls():
+    """orbx_extract_batch_device over more frames than the workspace holds runs several passes; results must land in the right
+    rows and equal single-frame calls, and later work on the caller's stream must see them."""
+    import torch
+    base = [synth(640, 480, s) for s in range(60, 65)]
+    host = np.stack([np.roll(base[i % 5], 2 * (i // 5), axis=0) for i in range(22)])
+    frames = torch.from_numpy(host).cuda()
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=4)            # 22 frames: 6 passes, the last one ragged
+    ex._plan(640, 480)
+    cap = ex.max_keypoints()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        kp = torch.zeros((22, cap, 7), dtype=torch.float32, device="cuda")
+        desc = torch.zeros((22, cap, 32), dtype=torch.uint8, device="cuda")
+        n = torch.zeros(22, dtype=torch.int32, device="cuda")
+        ex.extract_batch_device(frames, kp, desc, n, cap, stream=st.cuda_stream)
+        n2 = n.clone()                                                 # ordered after the passes on the same stream
+    st.synchronize()
+    ex.check_status()
+    kp, desc, n = kp.cpu().numpy(), desc.cpu().numpy(), n2.cpu().numpy()
+    one = orb.ORBextractor(1000, 1.2, 8, 20, 7)
+    for f in range(22):
+        k1, d1 = one(host[f])
+        assert n[f] == len(k1) and n[f] > 900, f
+        assert kp[f, :n[f]].tobytes() == k1.tobytes(), f
+        assert np.array_equal(desc[f, :n[f]], d1), f
+
+
 def test_device_resident_batch_idempotent():
     import torch
     frames = torch.from_numpy(np.stack([synth(640, 480, s) for s in range(30, 34)])).cuda()
