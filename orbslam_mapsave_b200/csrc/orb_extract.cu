@@ -1016,6 +1016,17 @@ __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
 #define DESC_DISC_WORDS (31 * DESC_AW)
 #define DESC_BUF_WORDS (DESC_PATCH_WORDS + DESC_DISC_WORDS)
 #define DESC_SMEM_BYTES (32 * 36 * 4 + 2 * DESC_WARPS * DESC_BUF_WORDS * 4)
+// TMA staging (k_describe<true>): the two neighbourhoods of a keypoint are two boxes of the per-level tensor maps, dropped into
+// shared memory by one elected lane (no per-lane address arithmetic).  A box has to start at a 16-byte aligned pixel column (an
+// unaligned start raises "illegal instruction" on sm_100a), so boxes are 64 / 48 bytes wide and start at the aligned column at or
+// before the neighbourhood's first pixel; buffers are 128-byte aligned.
+#define DESC_TMA_PW 64                    // 15 + 37 <= 64
+#define DESC_TMA_AW 48                    // 15 + 31 <= 48
+#define DESC_TMA_PATCH_BYTES 2432         // 37 x 64 = 2368, rounded up to 128
+#define DESC_TMA_DISC_BYTES 1536          // 31 x 48 = 1488
+#define DESC_TMA_BUF_BYTES (DESC_TMA_PATCH_BYTES + DESC_TMA_DISC_BYTES)
+#define DESC_TMA_TX_BYTES (37 * DESC_TMA_PW + 31 * DESC_TMA_AW)
+#define DESC_TMA_SMEM_BYTES (32 * 36 * 4 + 2 * DESC_WARPS * DESC_TMA_BUF_BYTES + 2 * DESC_WARPS * 8)
 // Persistent warps over the work items (frame, slot): slot r of a frame is position r of the per-frame selection buffer
 // (level l owns [selOff[l], selOff[l] + selCap[l])), so the selection entry and the per-level counts of an item are two
 // INDEPENDENT loads whose addresses follow from the item number alone.  Software pipeline per warp:
@@ -1025,15 +1036,30 @@ struct DescItem { uint2 k; int cntv; };
 __device__ __forceinline__ void cp_async4(u32 dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+template <bool TMA>
 __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                               const u8* __restrict__ blur, const uint2* __restrict__ sel,
                                                               const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
                                                               u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
-                                                              int* __restrict__ status, int nf) {
-    extern __shared__ __align__(16) u8 smem_desc[];
+                                                              int* __restrict__ status, int nf, const CUtensorMap* __restrict__ maps) {
+    extern __shared__ __align__(128) u8 smem_desc[];
     float* s_pat = reinterpret_cast<float*>(smem_desc);            // pattern as float (no I2F in the tap loop); row stride 36: conflict-free LDS.128
-    u32* s_buf = reinterpret_cast<u32*>(smem_desc + 32 * 36 * 4);  // [2][DESC_WARPS][DESC_BUF_WORDS]: blurred 37x37 + unblurred 31x31 neighbourhoods
+    u32* s_buf = reinterpret_cast<u32*>(smem_desc + 32 * 36 * 4);  // [2][DESC_WARPS][buffer]: blurred 37x37 + unblurred 31x31 neighbourhoods
+    constexpr int BUF_WORDS = TMA ? DESC_TMA_BUF_BYTES / 4 : DESC_BUF_WORDS;
+    constexpr int PATCH_WORDS = TMA ? DESC_TMA_PATCH_BYTES / 4 : DESC_PATCH_WORDS;
+    constexpr int PWB = TMA ? DESC_TMA_PW : DESC_PW * 4, AWB = TMA ? DESC_TMA_AW : DESC_AW * 4;   // row pitches in bytes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // TMA: one mbarrier per (warp, buffer), completed by the two box loads of an item
+    const u32 bars = smem_u32(smem_desc + 32 * 36 * 4 + 2 * DESC_WARPS * DESC_TMA_BUF_BYTES) + (u32)warp * 16;
+    u32 phases = 0;                                               // bit b: parity of buffer b's barrier
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(bars, 1);
+            mbar_init(bars + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (int i = threadIdx.x; i < 1024; i += 32 * DESC_WARPS) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
     __syncthreads();
     const int nItems = nf * P.selTotal, GW = gridDim.x * DESC_WARPS;
@@ -1070,15 +1096,26 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
         }
         return idx < cnt && pos < cap;
     };
-    auto stage = [&](int buf, int f, int l, const uint2 k) {       // stage B: cp.async both neighbourhoods as aligned words
+    auto stage = [&](int buf, int f, int l, const uint2 k) {       // stage B: both neighbourhoods to shared memory, asynchronously
         const LevelPlan& L = P.lv[l];
         const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
+        if (TMA) {
+            if (lane == 0) {
+                const u32 bar = bars + 8 * buf;
+                const u32 dst = smem_u32(s_buf + (size_t)(buf * DESC_WARPS + warp) * BUF_WORDS);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // our generic reads of this buffer precede the async write
+                mbar_expect_tx(bar, DESC_TMA_TX_BYTES);
+                tma_load_3d(dst, maps + P.nlevels + l, (kx - 18 + ORBX_OX) & ~15, ky - 18 + ORBX_OY, f, bar);
+                tma_load_3d(dst + DESC_TMA_PATCH_BYTES, maps + 2 * P.nlevels + l, (kx - 15 + ORBX_OX) & ~15, ky - 15 + ORBX_OY, f, bar);
+            }
+            return;
+        }
         const int pitchW = L.pitch >> 2;
         const size_t lofs = (size_t)f * P.frameBytes + L.off;
         const int pxs = kx - 18 + ORBX_OX, axs = kx - 15 + ORBX_OX;
         const u32* bsrc = reinterpret_cast<const u32*>(blur + lofs) + (ky - 18 + ORBX_OY) * pitchW + (pxs >> 2);
         const u32* asrc = reinterpret_cast<const u32*>(pyr + lofs) + (ky - 15 + ORBX_OY) * pitchW + (axs >> 2);
-        const u32 dst = smem_u32(s_buf + (size_t)(buf * DESC_WARPS + warp) * DESC_BUF_WORDS);
+        const u32 dst = smem_u32(s_buf + (size_t)(buf * DESC_WARPS + warp) * BUF_WORDS);
 #pragma unroll
         for (int j = 0; j < 13; j++) {
             const int i = lane + 32 * j, r = i / DESC_PW, w = i - r * DESC_PW;
@@ -1096,7 +1133,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
     int f0 = 0, l0 = 0, pos0 = 0, tot0 = 0;
     bool ok0 = resolve(item, d0, f0, l0, pos0, tot0);
     if (ok0) stage(0, f0, l0, d0.k);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");
     int buf = 0;
     for (; item < nItems; item += GW) {
         // stage A for item+2 (consumed two iterations from now), stage B for item+1
@@ -1104,28 +1141,32 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
         int f1 = 0, l1 = 0, pos1 = 0, tot1 = 0;
         const bool ok1 = resolve(item + GW, d1, f1, l1, pos1, tot1);
         if (ok1) stage(buf ^ 1, f1, l1, d1.k);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");       // the copies of the CURRENT item have landed
+        if (TMA) {
+            if (ok0) { mbar_wait(bars + 8 * buf, (phases >> buf) & 1u); phases ^= 1u << buf; }
+        } else {
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");   // the copies of the CURRENT item have landed
+        }
         __syncwarp();
         if (ok0) {
             const int l = l0, f = f0, pos = pos0;
             const uint2 k = d0.k;
             const LevelPlan& L = P.lv[l];
             const int kx = (int)(k.x & 0xFFFF), ky = (int)(k.x >> 16);
-            const int shift = (kx - 18 + ORBX_OX) & 3, ashift = (kx - 15 + ORBX_OX) & 3;
-            const u32* patch = s_buf + (size_t)(buf * DESC_WARPS + warp) * DESC_BUF_WORDS;
-            const u32* disc = patch + DESC_PATCH_WORDS;
+            const int shift = (kx - 18 + ORBX_OX) & (TMA ? 15 : 3), ashift = (kx - 15 + ORBX_OX) & (TMA ? 15 : 3);
+            const u32* patch = s_buf + (size_t)(buf * DESC_WARPS + warp) * BUF_WORDS;
+            const u32* disc = patch + PATCH_WORDS;
 
             // ---- IC_Angle (ORBextractor.cc:76-103): lane = column u (-15..15); the disc is symmetric (:461-468 makes umax its own
             // transpose), so column u spans rows |v| <= umax[|u|]
             int m10 = 0, m01 = 0;
             if (lane < 31) {
                 const int u = lane - 15, vlim = P.umax[u < 0 ? -u : u];
-                const u8* cen = reinterpret_cast<const u8*>(disc + 15 * DESC_AW) + 15 + ashift + u;
+                const u8* cen = reinterpret_cast<const u8*>(disc) + 15 * AWB + 15 + ashift + u;
                 int colsum = 0;
 #pragma unroll
                 for (int v = -15; v <= 15; v++) {
-                    const int I = ((v < 0 ? -v : v) <= vlim) ? (int)cen[v * (DESC_AW * 4)] : 0;
+                    const int I = ((v < 0 ? -v : v) <= vlim) ? (int)cen[v * AWB] : 0;
                     colsum += I;
                     m01 += v * I;
                 }
@@ -1145,7 +1186,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
                 cs = (float)(lane == 0 ? cd : sd);
             }
             const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
-            const u8* center = reinterpret_cast<const u8*>(patch + 18 * DESC_PW) + 18 + shift;
+            const u8* center = reinterpret_cast<const u8*>(patch) + 18 * PWB + 18 + shift;
             const float4* pat = reinterpret_cast<const float4*>(s_pat + lane * 36);
             u32 val = 0;
             // round-half-even without the XU pipe: x + 1.5*2^23 leaves rint(x) in the low mantissa bits (|x| < 2^22), == cvRound
@@ -1158,7 +1199,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
                 const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)), MAGIC)) - MAGIC_I;
                 const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.z, b), __fmul_rn(pp.w, a)), MAGIC)) - MAGIC_I;
                 const int q1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.z, a), __fmul_rn(pp.w, b)), MAGIC)) - MAGIC_I;
-                const int t0 = center[r0 * (DESC_PW * 4) + q0], t1 = center[r1 * (DESC_PW * 4) + q1];
+                const int t0 = center[r0 * PWB + q0], t1 = center[r1 * PWB + q1];
                 val |= (u32)(t0 < t1) << j;
             }
             descOut[((size_t)f * cap + pos) * 32 + lane] = (u8)val;
@@ -1175,7 +1216,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
         ok0 = ok1; f0 = f1; l0 = l1; pos0 = pos1;
         buf ^= 1;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!TMA) asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // =====================================================================================================
@@ -1215,7 +1256,7 @@ struct orbx_extractor {
     int *d_candCount = nullptr, *d_selCount = nullptr, *d_status = nullptr, *d_workCounter = nullptr;
     ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
     CUtensorMap* d_maps = nullptr;         // one TMA descriptor per pyramid level (k_fast_tma)
-    bool useTma = false;
+    bool useTma = false, descTma = false;
     size_t fwSmem = 0;
     int fwGrid = 0, descGrid = 0;
     uint4* d_cells = nullptr;              // valid FAST cells: {iniX | iniY<<16, tw | th<<8 | level<<16, cell id, 0}
@@ -1412,21 +1453,30 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
             cudaDriverEntryPointQueryResult qres;
             if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
                 qres == cudaDriverEntryPointSuccess) {
-                std::vector<CUtensorMap> maps(nl);
+                // maps [0, nl): FAST cell tiles of the pyramid; [nl, 2nl): 64 x 37 boxes of the blurred pyramid and [2nl, 3nl): 48 x 31
+                // boxes of the pyramid, the two neighbourhoods k_describe<true> stages per keypoint
+                std::vector<CUtensorMap> maps(3 * nl);
                 bool ok = true;
                 for (int l = 0; l < nl && ok; l++) {
                     const LevelPlan& L = P.lv[l];
                     cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.brows, (cuuint64_t)ex->maxBatch};
                     cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)P.frameBytes};
                     cuuint32_t box[3] = {(cuuint32_t)boxW, (cuuint32_t)boxH, 1};
+                    cuuint32_t boxP[3] = {DESC_TMA_PW, 37, 1}, boxA[3] = {DESC_TMA_AW, 31, 1};
                     cuuint32_t estr[3] = {1, 1, 1};
                     ok = ((EncodeFn)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_pyr + L.off, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                         ((EncodeFn)fn)(&maps[nl + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_blur + L.off, dims, strides, boxP, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                         ((EncodeFn)fn)(&maps[2 * nl + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ex->d_pyr + L.off, dims, strides, boxA, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
                 }
                 if (ok) {
-                    ORB_CUDA_TRY(cudaMalloc(&ex->d_maps, nl * sizeof(CUtensorMap)));
-                    ORB_CUDA_TRY(cudaMemcpy(ex->d_maps, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+                    ORB_CUDA_TRY(cudaMalloc(&ex->d_maps, 3 * nl * sizeof(CUtensorMap)));
+                    ORB_CUDA_TRY(cudaMemcpy(ex->d_maps, maps.data(), 3 * nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
                     ex->useTma = true;
                 }
             } else cudaGetLastError();
@@ -1450,13 +1500,17 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     {   // k_describe: persistent grid, DESC_SMEM_BYTES of dynamic shared memory per CTA
         cudaDeviceProp prop;
         ORB_CUDA_TRY(cudaGetDeviceProperties(&prop, ex->device));
-        const int perSM = std::max(1, std::min(8, (int)((prop.sharedMemPerMultiprocessor - 2048) / (DESC_SMEM_BYTES + 1024))));
+        static const bool wantDescTma = [] { const char* e = getenv("ORBX_DESC_TMA"); return !(e && atoi(e) == 0); }();
+        ex->descTma = ex->useTma && wantDescTma;
+        const int descSmem = ex->descTma ? DESC_TMA_SMEM_BYTES : DESC_SMEM_BYTES;
+        const int perSM = std::max(1, std::min(8, (int)((prop.sharedMemPerMultiprocessor - 2048) / (descSmem + 1024))));
         ex->descGrid = prop.multiProcessorCount * perSM;
         static std::mutex amu3;
         static bool descOptIn[64] = {false};
         std::lock_guard<std::mutex> lk(amu3);
         if (!descOptIn[ex->device & 63]) {
-            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES));
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES));
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_TMA_SMEM_BYTES));
             descOptIn[ex->device & 63] = true;
         }
     }
@@ -1631,8 +1685,12 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     if (stages & ORBX_STAGE_DESCRIBE) {
         const int items = nf * P.selTotal;
         const int grid = std::min(ex->descGrid, orb_div_up(items, DESC_WARPS));
-        k_describe<<<grid, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc, d_n, cap,
-                                                                  ex->d_status, nf);
+        if (ex->descTma)
+            k_describe<true><<<grid, 32 * DESC_WARPS, DESC_TMA_SMEM_BYTES, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
+                                                                                d_n, cap, ex->d_status, nf, ex->d_maps);
+        else
+            k_describe<false><<<grid, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
+                                                                             d_n, cap, ex->d_status, nf, nullptr);
         ex->launches++;
     }
     ORB_CUDA_TRY(cudaGetLastError());
