@@ -338,8 +338,13 @@ def make_chain():
         ("small_320x240_seed5", dict(W=320, H=240, seed=5, nfeatures=500, scaleFactor=1.2, nlevels=6, iniTh=20, minTh=7, mask=False)),
         ("mask_400x300_seed9", dict(W=400, H=300, seed=9, nfeatures=600, scaleFactor=1.2, nlevels=7, iniTh=20, minTh=7, mask=True)),
         ("rgbd_424x240_seed11", dict(W=424, H=240, seed=11, nfeatures=300, scaleFactor=1.5, nlevels=3, iniTh=15, minTh=3, mask=False)),
+        # BASELINE config 3 geometry: 16:9, so DistributeOctTree starts from nIni = round(1280/720) = 2 root nodes (:542-562)
+        ("c3_1280x720_seed3", dict(W=1280, H=720, seed=3, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniTh=20, minTh=7, mask=False)),
     ]
+    only = set(sys.argv[2:]) if len(sys.argv) > 2 and sys.argv[1] == "chain" else None
     for name, c in cases:
+        if only is not None and name not in only:
+            continue
         img = synth(c["W"], c["H"], c["seed"])
         mask = None
         if c["mask"]:
@@ -357,5 +362,7 @@ def make_chain():
 
 
 if __name__ == "__main__":
-    make_primitives()
+    # `python make_golden.py` regenerates everything; `python make_golden.py chain <name>...` only the named chain cases
+    if not (len(sys.argv) > 1 and sys.argv[1] == "chain"):
+        make_primitives()
     make_chain()
