@@ -1032,7 +1032,7 @@ __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
 // INDEPENDENT loads whose addresses follow from the item number alone.  Software pipeline per warp:
 //   item i+2: those two loads are issued;   item i+1: its two neighbourhoods are copied to shared memory with cp.async (no
 //   registers, no waiting);   item i: orientation + descriptor from the other shared-memory buffer.
-struct DescItem { uint2 k; int cntv; };
+struct DescItem { uint2 k; int cntv, f, r; bool valid; };
 __device__ __forceinline__ void cp_async4(u32 dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -1065,30 +1065,30 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
     const int nItems = nf * P.selTotal, GW = gridDim.x * DESC_WARPS;
     int item = blockIdx.x * DESC_WARPS + warp;
 
-    auto load_item = [&](int it) {                                 // stage A: two independent loads
+    // the item stream of this warp: it, it + GW, ...; (frame, slot) advance incrementally (no division per item)
+    const int stepF = GW / P.selTotal, stepR = GW - stepF * P.selTotal;
+    int ldIt = item, ldF = item / P.selTotal, ldR = item - ldF * P.selTotal;
+    auto load_next = [&]() {                                       // stage A: two independent loads
         DescItem d;
-        d.k = make_uint2(0u, 0u); d.cntv = 0;
-        if (it < nItems) {
-            const int f = it / P.selTotal;
-            d.k = __ldg(sel + it);
-            d.cntv = lane < P.nlevels ? __ldg(selCount + f * P.nlevels + lane) : 0;
+        d.k = make_uint2(0u, 0u); d.cntv = 0; d.f = ldF; d.r = ldR; d.valid = ldIt < nItems;
+        if (d.valid) {
+            d.k = __ldg(sel + ldIt);
+            d.cntv = lane < P.nlevels ? __ldg(selCount + ldF * P.nlevels + lane) : 0;
         }
+        ldIt += GW; ldF += stepF; ldR += stepR;
+        if (ldR >= P.selTotal) { ldR -= P.selTotal; ldF++; }
         return d;
     };
     // resolves (level, index in level, output position) of an item; returns false for empty slots
-    auto resolve = [&](int it, const DescItem& d, int& f, int& l, int& pos, int& total) {
-        if (it >= nItems) return false;
-        f = it / P.selTotal;
-        const int r = it - f * P.selTotal;
-        l = 0;
-#pragma unroll 1
-        for (int j = 1; j < P.nlevels; j++) l += (r >= P.lv[j].selOff) ? 1 : 0;
+    auto resolve = [&](const DescItem& d, int& f, int& l, int& pos, int& total) {
+        if (!d.valid) return false;
+        f = d.f;
+        const int r = d.r;
+        // level = number of levels 1.. whose first slot is <= r (lanes compare in parallel); counts: two warp reductions
+        l = __popc(__ballot_sync(0xffffffffu, lane >= 1 && lane < P.nlevels && r >= P.lv[lane & (ORBX_MAX_LEVELS - 1)].selOff));
         const int idx = r - P.lv[l].selOff;
-        int inc = d.cntv;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-        total = __shfl_sync(0xffffffffu, inc, 31);
-        const int before = __shfl_sync(0xffffffffu, inc - d.cntv, l), cnt = __shfl_sync(0xffffffffu, d.cntv, l);
+        total = __reduce_add_sync(0xffffffffu, d.cntv);
+        const int before = __reduce_add_sync(0xffffffffu, lane < l ? d.cntv : 0), cnt = __shfl_sync(0xffffffffu, d.cntv, l);
         pos = before + idx;
         if (r == 0 && lane == 0) {                                 // slot 0 of every frame reports the frame's keypoint count
             nOut[f] = total;
@@ -1129,17 +1129,17 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
     };
 
     // prologue
-    DescItem d0 = load_item(item), d1 = load_item(item + GW);
+    DescItem d0 = load_next(), d1 = load_next();
     int f0 = 0, l0 = 0, pos0 = 0, tot0 = 0;
-    bool ok0 = resolve(item, d0, f0, l0, pos0, tot0);
+    bool ok0 = resolve(d0, f0, l0, pos0, tot0);
     if (ok0) stage(0, f0, l0, d0.k);
     if (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");
     int buf = 0;
     for (; item < nItems; item += GW) {
         // stage A for item+2 (consumed two iterations from now), stage B for item+1
-        const DescItem d2 = load_item(item + 2 * GW);
+        const DescItem d2 = load_next();
         int f1 = 0, l1 = 0, pos1 = 0, tot1 = 0;
-        const bool ok1 = resolve(item + GW, d1, f1, l1, pos1, tot1);
+        const bool ok1 = resolve(d1, f1, l1, pos1, tot1);
         if (ok1) stage(buf ^ 1, f1, l1, d1.k);
         if (TMA) {
             if (ok0) { mbar_wait(bars + 8 * buf, (phases >> buf) & 1u); phases ^= 1u << buf; }
@@ -1162,11 +1162,14 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
             int m10 = 0, m01 = 0;
             if (lane < 31) {
                 const int u = lane - 15, vlim = P.umax[u < 0 ? -u : u];
-                const u8* cen = reinterpret_cast<const u8*>(disc) + 15 * AWB + 15 + ashift + u;
+                // explicit shared-space loads from a 32-bit address: with generic pointers the compiler rebuilt a shared::cluster window
+                // address (S2R SR_CgaCtaId + LEA) for every one of the 31 predicated loads of the TMA variant
+                const u32 cen = smem_u32(disc) + 15 * AWB + 15 + ashift + u;
                 int colsum = 0;
 #pragma unroll
                 for (int v = -15; v <= 15; v++) {
-                    const int I = ((v < 0 ? -v : v) <= vlim) ? (int)cen[v * AWB] : 0;
+                    int I = 0;
+                    if ((v < 0 ? -v : v) <= vlim) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(I) : "r"(cen + v * AWB));
                     colsum += I;
                     m01 += v * I;
                 }
