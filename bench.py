@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=4096, help="frames per GPU per step")
     ap.add_argument("--unique", type=int, default=4096, help="distinct synthetic frames per GPU (others repeat them)")
-    ap.add_argument("--chunk", type=int, default=512, help="frames per device pass of the device-resident measurement (workspace size)")
+    ap.add_argument("--chunk", type=int, default=1024, help="frames per device pass of the device-resident measurement (workspace size)")
     ap.add_argument("--e2e-chunk", type=int, default=128, help="frames per pipelined chunk of the host-buffer (e2e) path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-match", action="store_true", help="skip the matching sub-benchmark")
@@ -301,12 +301,12 @@ def main():
     roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast_tma", "octree": "k_octree", "blur": "k_blur",
                                            "describe": "k_describe"}[dom],
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1n_all_kernels_ncu_full.md)
-                "traffic": ({"fast": 285.9e6, "describe": 601.6e6, "blur": 524.8e6, "octree": 16.0e6}.get(dom, 0) * args.chunk / 256) or None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1q_all_kernels_ncu_full.md)
+                "traffic": ({"fast": 285.5e6, "describe": 581.7e6, "blur": 523.2e6, "octree": 15.9e6}.get(dom, 0) * args.chunk / 256) or None,
                 "peak_source": peak_src, "avg_launch_ms": dom_launch_s * 1e3, "algorithmic_bytes_per_frame": stage_bytes[dom],
                 "stage_ms_per_step": {k: v * 1e3 for k, v in stage_s.items()},
                 # what actually bounds it: warp-instruction issue.  540.3 M warp-instructions per 256-frame k_fast_tma launch (ncu,
-                # profiles/r1n_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
+                # profiles/r1q_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
                 "issue": ({"warp_inst_per_launch": 540.3e6 * args.chunk / 256,
                            "achieved_ginst_s": 540.3e6 * args.chunk / 256 / dom_launch_s / 1e9,
                            "peak_ginst_s": 148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
