@@ -340,6 +340,10 @@ def make_chain():
         ("rgbd_424x240_seed11", dict(W=424, H=240, seed=11, nfeatures=300, scaleFactor=1.5, nlevels=3, iniTh=15, minTh=3, mask=False)),
         # BASELINE config 3 geometry: 16:9, so DistributeOctTree starts from nIni = round(1280/720) = 2 root nodes (:542-562)
         ("c3_1280x720_seed3", dict(W=1280, H=720, seed=3, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniTh=20, minTh=7, mask=False)),
+        # BASELINE config 5 (4K, 8000 features, 12 levels).  The 8 MB image is not stored: the tests regenerate it with
+        # synth(W, H, seed) and check its CRC against the one recorded here.
+        ("c5_3840x2160_seed1", dict(W=3840, H=2160, seed=1, nfeatures=8000, scaleFactor=1.2, nlevels=12, iniTh=20, minTh=7, mask=False,
+                                    store_image=False)),
     ]
     only = set(sys.argv[2:]) if len(sys.argv) > 2 and sys.argv[1] == "chain" else None
     for name, c in cases:
@@ -355,9 +359,11 @@ def make_chain():
         lvl_sum = np.array([int(p.astype(np.int64).sum()) for p in st["pyr"]], np.int64)
         blur_sum = np.array([int(b.astype(np.int64).sum()) if b is not None else -1 for b in st["blurred"]], np.int64)
         params = np.array([c["W"], c["H"], c["seed"], c["nfeatures"], c["nlevels"], c["iniTh"], c["minTh"], int(c["mask"])], np.int32)
+        import zlib
+        extra = dict(image=img) if c.get("store_image", True) else dict(image_crc=np.uint32(zlib.crc32(img.tobytes())))
         np.savez_compressed(os.path.join(HERE, f"chain_{name}.npz"), params=params, scaleFactor=np.float32(c["scaleFactor"]),
-                            image=img, kp=kp, desc=desc, cand_counts=cand_counts, level_sums=lvl_sum, blur_sums=blur_sum,
-                            quota=np.array(st["quota"], np.int32), last_level=st["pyr"][-1])
+                            kp=kp, desc=desc, cand_counts=cand_counts, level_sums=lvl_sum, blur_sums=blur_sum,
+                            quota=np.array(st["quota"], np.int32), last_level=st["pyr"][-1], **extra)
         print(name, len(kp), cand_counts.tolist())
 
 
