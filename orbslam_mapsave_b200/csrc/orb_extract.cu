@@ -168,9 +168,10 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ Plan P, 
     const u32 sel[4] = {0x10u, (u32)((int)t01.z - sx0) * 0x11u + 0x10u, (u32)((int)t23.x - sx0) * 0x11u + 0x10u,
                         (u32)((int)t23.z - sx0) * 0x11u + 0x10u};
     const int base = sx0 & ~3, sh0 = (sx0 - base) * 8;
-    const u8* col = src + base;
     auto hpass = [&](int sy, int (&h)[4]) {                          // h[k] = (p0*c0 + p1*c1) >> 4 for the 4 outputs, source row sy
-        const u32* rp = reinterpret_cast<const u32*>(col + (size_t)sy * S.pitch);
+        // one 32-bit offset and one 64-bit add per source row; the three words are immediates off that address (the compiler
+        // otherwise keeps three 64-bit column bases and adds the frame pointer per load: 9 instead of 3 address instructions per row)
+        const u32* rp = reinterpret_cast<const u32*>(src + (u32)(sy * S.pitch + base));
         const u32 w0 = rp[0], w1 = rp[1], w2 = rp[2];
         const u32 lo = __funnelshift_r(w0, w1, sh0), hi = __funnelshift_r(w1, w2, sh0);
 #pragma unroll
