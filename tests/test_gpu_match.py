@@ -219,3 +219,14 @@ def test_distinctive_descriptors_vs_oracle():
     assert np.array_equal(got, want)
     with pytest.raises(orb.OrbError):
         orb.distinctive_descriptors(np.zeros((1025, 32), np.uint8), np.array([0, 1025], np.int32))
+
+
+def test_distances_and_top2_match_cv2_golden():
+    """The device path against real-OpenCV Hamming distances (tests/golden/prim_hamming.npz: cv2.norm / BFMatcher.knnMatch)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "prim_hamming.npz"))
+    assert np.array_equal(orb.ORBmatcher.DescriptorDistance(g["a"], g["b"]), g["dist"])
+    bi, b1, b2 = orb.ORBmatcher().hamming_top2(g["q"], g["db"])
+    assert np.array_equal(b1, g["best"]) and np.array_equal(b2, g["second"])
+    uniq = g["best"] < g["second"]
+    assert np.array_equal(bi[uniq], g["best_idx"][uniq])

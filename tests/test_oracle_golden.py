@@ -127,3 +127,15 @@ def test_small_gemm_matches_cv2(golden_dir):
         T2 = np.ascontiguousarray(np.concatenate([R[i], x[i][:, None]], 1), np.float32)
         L.orc_minus_rt_t(T2.ctypes.data, out.ctypes.data)
         assert np.array_equal(out, g["outT"][i]), i
+
+
+def test_descriptor_distance_and_top2_match_cv2(golden_dir):
+    """ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1650-1666, the bit-twiddling popcount) == cv2.norm(NORM_HAMMING), and the
+    oracle's top-2 distances == cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) (tests/golden/make_golden_hamming.py, cv2 4.13)."""
+    g = np.load(os.path.join(golden_dir, "prim_hamming.npz"))
+    got = np.array([orc.descriptor_distance(x, y) for x, y in zip(g["a"], g["b"])], np.int32)
+    assert np.array_equal(got, g["dist"])
+    bi, b1, b2 = orc.hamming_top2(g["q"], g["db"])
+    assert np.array_equal(b1, g["best"]) and np.array_equal(b2, g["second"])
+    uniq = g["best"] < g["second"]
+    assert np.array_equal(bi[uniq], g["best_idx"][uniq])
