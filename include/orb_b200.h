@@ -77,7 +77,12 @@ int orbx_extract(orbx_extractor* ex, const uint8_t* image, int width, int height
 
 /* Batch form (not in the reference: N frames per call for throughput).  Frames are `frame_stride` bytes apart, rows
  * `stride` bytes; masks (or NULL) laid out likewise with mask_frame_stride/mask_stride.  kp_out[n_frames*cap],
- * desc_out[n_frames*cap*32], n_out[n_frames].  Host pointers; blocks until done. */
+ * desc_out[n_frames*cap*32], n_out[n_frames].  Host pointers (pinned memory makes the copies true DMA); blocks until done.
+ * More than max_batch frames are pipelined in chunks of max_batch (first and last chunk 64 frames): copy-in, compute and copy-out
+ * run on separate streams over six device staging slots, and a helper handle (a second workspace of the same size, created on
+ * first use and owned by `ex`) computes every other chunk.  The "last pass" views (orbx_get_pyramid*, orbx_stereo_matches) refer to
+ * the final chunk.  Environment switches for measurements: ORBX_E2E_STREAMS (1..4), ORBX_E2E_SLOTS, ORBX_E2E_RAMP=0,
+ * ORBX_E2E_TRACE=1 (per-chunk device timeline on stderr). */
 int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int n_frames, int width, int height, int stride,
                        size_t frame_stride, const uint8_t* masks, int mask_stride, size_t mask_frame_stride,
                        orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
