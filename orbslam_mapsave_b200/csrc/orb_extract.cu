@@ -58,7 +58,6 @@ struct Plan {
     int totalCells, candTotal, selTotal, maxNodes, sortN;
     int tilePitch, tileRows, scorePitch, scoreRows;   // FAST shared-memory tile geometry (max over levels)
     int fwBoxW, fwBoxH, fwTileBytes, fwScoreOff, fwPlistOff, fwBarOff, fwStride;   // k_fast_tma per-warp shared-memory layout
-    int fwPlistCap;                                                              // entries (u16) of the per-warp list buffer
     int width, height;
     unsigned long long frameBytes;
     int umax[16];
@@ -513,7 +512,7 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
             const int t = pass ? P.minTh : P.iniTh;
             T = t;
             // ---- phase A
-            int nl = 0, np = 0;
+            int nl = 0;
             {
                 const int hiT = 256 + t, loT = 256 - t;
                 const u8* cE = tile + 3 * BW + (X0 & ~1);
@@ -526,7 +525,7 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                         const int row = npr == 1 ? task : (int)__umulhi((u32)task, inv);   // (inv overflows for npr == 1)
                         const int p = task - row * npr;
                         const int px0 = 2 * p - off;
-                        ent = (row << 8) | (px0 & 0xFF);
+                        ent = (row << 8) + px0;
                         const u8* pe = cE + row * BW + 2 * p;
 #define LD2(o) __byte_perm((u32) * reinterpret_cast<const u16*>(pe + (o)), 0, 0x4140)
                         const u32 vb = LD2(0) + 0x01000100u;
@@ -541,31 +540,13 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                         if (px0 < 0) fl &= 0xFFFF0000u;               // first pixel left of the domain
                         if (px0 + 1 >= dw) fl &= 0x0000FFFFu;         // second pixel right of the domain
                     }
-                    // ~95 % of the pairs fail: compact PAIRS (one ballot, one store) here and expand the few survivors to pixels below,
-                    // instead of a two-ballot pixel compaction in every iteration.  Pair entry: px0 (8 bits, two's complement: -1
-                    // when the first pixel lies left of the domain) | row << 8 (6 bits) | first passes << 14 | second passes << 15.
-                    const u32 any = __ballot_sync(0xffffffffu, fl != 0u);
-                    if (fl) plist[np + __popc(any & lt)] = (u16)((ent & 0x3FFF) | ((fl & 0x8000u) >> 1) | (fl >> 16));
-                    np += __popc(any);
+                    const u32 b0 = __ballot_sync(0xffffffffu, fl & 0x8000u), b1 = __ballot_sync(0xffffffffu, fl & 0x80000000u);
+                    const int n0 = __popc(b0);
+                    if (fl & 0x8000u) plist[nl + __popc(b0 & lt)] = (u16)ent;
+                    if (fl & 0x80000000u) plist[nl + n0 + __popc(b1 & lt)] = (u16)(ent + 1);
+                    nl += n0 + __popc(b1);
                 }
             }
-            __syncwarp();
-            // ---- expansion of the pair entries [0, np) into pixel entries, BACKWARDS into the top of the buffer: after the chunk that
-            // starts at e0 the pixels occupy [top, cap) with cap - top <= 2 (np - e0) and 2 np <= cap, so top >= 2 e0: the unread pair
-            // entries [0, e0) are never overwritten.  Phase B reads the pixel list from plist + lb.
-            int lb = P.fwPlistCap;
-            for (int e0 = (np - 1) & ~31; np > 0 && e0 >= 0; e0 -= 32) {
-                const int e = e0 + lane;
-                const u32 pe = e < np ? (u32)plist[e] : 0u;
-                __syncwarp();
-                const u32 b0 = __ballot_sync(0xffffffffu, pe & 0x4000u), b1 = __ballot_sync(0xffffffffu, pe & 0x8000u);
-                const int n0 = __popc(b0);
-                lb -= n0 + __popc(b1);
-                const int first = (int)(pe & 0x3F00u) + (int)(signed char)(pe & 0xFFu);        // (row << 8) + px0
-                if (pe & 0x4000u) plist[lb + __popc(b0 & lt)] = (u16)first;
-                if (pe & 0x8000u) plist[lb + n0 + __popc(b1 & lt)] = (u16)(first + 1);
-            }
-            nl = P.fwPlistCap - lb;
             __syncwarp();
 
             // ---- phase B: exact score of the listed pixels, ONE pixel per lane with d = v - ring in the low half and -d in the
@@ -579,7 +560,7 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                     const int e = e0 + lane;
                     int ent = 0, sc = 0;
                     if (e < nl) {
-                        ent = plist[lb + e];
+                        ent = plist[e];
                         const u8* q = t8 + (ent >> 8) * BW + (ent & 0xFF);
                         const u32 v = q[0];
                         const u32 K = (256u + v) | ((256u - v) << 16);
@@ -1463,8 +1444,7 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         P.fwTileBytes = (int)orb_align_up((size_t)boxW * boxH, 128);
         P.fwScoreOff = P.fwTileBytes;                                 // one tile buffer: more warps per SM beat double buffering here
         P.fwPlistOff = P.fwScoreOff + (int)orb_align_up((size_t)P.scorePitch * P.scoreRows, 16);
-        P.fwPlistCap = (maxCW + 2) * maxCH;                          // >= 2 x (pixel pairs of a cell) and > its pixels
-        P.fwBarOff = P.fwPlistOff + (int)orb_align_up((size_t)P.fwPlistCap * 2, 16);
+        P.fwBarOff = P.fwPlistOff + (int)orb_align_up((size_t)(maxCW + 2) * maxCH * 2, 16);
         P.fwStride = (int)orb_align_up((size_t)P.fwBarOff + 16, 128);
         ex->fwSmem = (size_t)P.fwStride * ORBX_FW_WARPS;
         ex->useTma = false;
