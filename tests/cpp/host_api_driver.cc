@@ -14,6 +14,7 @@
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
 #include "ORBVocabulary.h"
+#include "MapArchive.h"
 
 using namespace ORB_SLAM2;
 
@@ -522,8 +523,52 @@ static int run_fuse(int argc, char** argv) {
     return ORBmatcher::LastStatus() == 0 ? 0 : 4;
 }
 
+// maparchive <in.bin> <out.bin> <dump.txt>: loads a saved map through ORB_SLAM2::MapArchiveB200 (host-only, no GPU needed), writes
+// it back, and dumps what the class hands out as text for the Python test to compare with the logical map the file was made from.
+static int run_maparchive(int argc, char** argv) {
+    if (argc < 5) return 2;
+    ORB_SLAM2::MapArchiveB200 ar;
+    if (!ar.Load(argv[2])) { fprintf(stderr, "load failed: %s\n", ar.LastError().c_str()); return 3; }
+    if (!ar.Save(argv[3])) { fprintf(stderr, "save failed: %s\n", ar.LastError().c_str()); return 4; }
+    FILE* f = fopen(argv[4], "w");
+    if (!f) return 5;
+    fprintf(f, "map %lu %lu %lu %d\n", ar.KeyFramesInMap(), ar.MapPointsInMap(), ar.GetMaxKFid(), (int)ar.LoadValidated());
+    for (size_t i = 0; i < ar.KeyFramesInMap(); i++) {
+        ORB_SLAM2::MapArchiveB200::KeyFrameData k;
+        if (!ar.GetKeyFrame(i, k)) { fclose(f); return 6; }
+        unsigned long long dsum = 0;
+        for (int r = 0; r < k.mDescriptors.rows; r++)
+            for (int c = 0; c < k.mDescriptors.cols; c++) dsum = dsum * 1000003ull + k.mDescriptors.ptr(r)[c];
+        long mpsum = 0;
+        for (long v : k.mvpMapPointIds) mpsum = mpsum * 31 + v;
+        double kx = 0;
+        for (const cv::KeyPoint& p : k.mvKeysUn) kx += (double)p.pt.x + 2.0 * (double)p.pt.y + (double)p.angle + p.octave;
+        fprintf(f, "kf %lu %lu %d %d %llu %ld %.6f %.9g %.9g %d %zu %zu %zu %zu %zu\n", k.mnId, k.mnFrameId, k.N, k.mDescriptors.rows, dsum, mpsum, kx,
+                (double)k.Tcw.at<float>(1, 3), (double)k.mK.at<float>(0, 2), (int)k.hasParent, k.mConnectedKeyFrameWeights.size(),
+                k.mvpOrderedConnectedKeyFrames.size(), k.mspChildrens.size(), k.mspLoopEdges.size(), k.gridFeatures.size());
+    }
+    std::vector<ORB_SLAM2::MapArchiveB200::MapPointData> mps = ar.GetAllMapPoints();
+    for (const auto& p : mps) {
+        unsigned long long dsum = 0;
+        for (int c = 0; c < 32; c++) dsum = dsum * 1000003ull + p.mDescriptor.ptr()[c];
+        long osum = 0;
+        for (const auto& o : p.mObservations) osum = osum * 31 + o.first * 7 + o.second;
+        fprintf(f, "mp %lu %llu %ld %zu %ld %.9g\n", p.mnId, dsum, p.refKFId, p.mObservations.size(), osum, (double)p.mWorldPos.at<float>(2));
+    }
+    cv::Mat obs;
+    std::vector<int> off;
+    if (!ar.ObservedDescriptors(obs, off)) { fclose(f); return 7; }
+    unsigned long long osum = 0;
+    for (int r = 0; r < obs.rows; r++)
+        for (int c = 0; c < 32; c++) osum = osum * 1000003ull + obs.ptr(r)[c];
+    fprintf(f, "observed %d %llu %d\n", obs.rows, osum, off.empty() ? 0 : off.back());
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) return 2;
+    if (!strcmp(argv[1], "maparchive")) return run_maparchive(argc, argv);
     if (!strcmp(argv[1], "bow")) return run_bow(argc, argv);
     if (!strcmp(argv[1], "extract")) return run_extract(argc, argv);
     if (!strcmp(argv[1], "match")) return run_match(argc, argv);

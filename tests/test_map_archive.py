@@ -160,3 +160,59 @@ def _write(tmp_path, name, data):
     p = tmp_path / name
     p.write_bytes(data)
     return p
+
+
+def test_cpp_map_archive_class(tmp_path):
+    """ORB_SLAM2::MapArchiveB200 (orbslam_mapsave_b200/host/MapArchive.h) through the C++ driver: counts, per-keyframe and
+    per-map-point contents (as order-sensitive checksums) and the observation gather equal the logical map; Save() reproduces
+    the file.  Host-only: runs without a GPU."""
+    import subprocess
+    drv = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "host_api_driver")
+    if not os.path.exists(drv):
+        pytest.skip("host_api_driver not built")
+    m = make_random_map(21, n_kf=4, n_feat=70, n_mp=35)
+    blob = serialize_map(m)
+    src, out, dump = tmp_path / "in.bin", tmp_path / "out.bin", tmp_path / "dump.txt"
+    src.write_bytes(blob)
+    subprocess.check_call([drv, "maparchive", str(src), str(out), str(dump)])
+    assert out.read_bytes() == blob
+    lines = dump.read_text().split("\n")
+    M = (1 << 64) - 1
+
+    def dsum(a):
+        s = 0
+        for v in np.asarray(a, np.uint8).reshape(-1):
+            s = (s * 1000003 + int(v)) & M
+        return s
+
+    def lsum(vals):
+        s = 0
+        for v in vals:
+            s = s * 31 + v
+            s = ((s + (1 << 63)) & M) - (1 << 63)          # C long wrap-around
+        return s
+
+    assert lines[0] == f"map {len(m['keyframes'])} {len(m['mappoints'])} {m['max_kf_id']} 1"
+    kfl = [ln.split() for ln in lines if ln.startswith("kf ")]
+    assert len(kfl) == len(m["keyframes"])
+    for got, k in zip(kfl, m["keyframes"]):
+        assert [int(got[1]), int(got[2]), int(got[3]), int(got[4])] == [k["id"], k["frame_id"], k["n"], k["n"]]
+        assert int(got[5]) == dsum(k["desc"])
+        assert int(got[6]) == lsum([-1 if v < 0 else v for v in k["mappoint_ids"]])
+        kx = sum(float(q["x"]) + 2.0 * float(q["y"]) + float(q["angle"]) + q["octave"] for q in k["keys_un"])
+        assert abs(float(got[7]) - kx) <= 1e-6 * max(1.0, abs(kx))
+        assert np.float32(float(got[8])) == k["Tcw"][1, 3] and np.float32(float(got[9])) == k["K"][0, 2]
+        assert int(got[10]) == int(k["parent"] is not None)
+        assert [int(v) for v in got[11:16]] == [len(k["connected"]), len(k["ordered_ids"]), len(k["children"]), len(k["loop_edges"]),
+                                                sum(len(c) for col in k["grid"] for c in col)]
+    mpl = [ln.split() for ln in lines if ln.startswith("mp ")]
+    assert len(mpl) == len(m["mappoints"])
+    for got, p in zip(mpl, m["mappoints"]):
+        assert int(got[1]) == p["id"] and int(got[2]) == dsum(p["desc"])
+        assert int(got[3]) == (-1 if p["ref_kf"] is None else p["ref_kf"]) and int(got[4]) == len(p["obs"])
+        assert int(got[5]) == lsum([(-1 * 7 + -1) if kf < 0 else kf * 7 + idx for kf, idx in p["obs"]])
+        assert np.float32(float(got[6])) == p["world_pos"][2, 0]
+    by_id = {k["id"]: k for k in m["keyframes"]}
+    rows = [by_id[kf]["desc"][idx] for p in m["mappoints"] for kf, idx in p["obs"] if kf >= 0]
+    obs = [ln.split() for ln in lines if ln.startswith("observed ")][0]
+    assert int(obs[1]) == len(rows) == int(obs[3]) and int(obs[2]) == dsum(np.stack(rows))
