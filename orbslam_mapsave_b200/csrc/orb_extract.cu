@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                         if (px0 + 1 >= dw) fl &= 0x0000FFFFu;         // second pixel right of the domain
                     }
                     const u32 b0 = __ballot_sync(0xffffffffu, fl & 0x8000u), b1 = __ballot_sync(0xffffffffu, fl & 0x80000000u);
+                    if ((b0 | b1) == 0u) continue;                     // warp-uniform: flat neighbourhoods leave nothing to compact
                     const int n0 = __popc(b0);
                     if (fl & 0x8000u) plist[nl + __popc(b0 & lt)] = (u16)ent;
                     if (fl & 0x80000000u) plist[nl + n0 + __popc(b1 & lt)] = (u16)(ent + 1);
