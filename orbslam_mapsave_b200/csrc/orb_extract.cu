@@ -445,7 +445,9 @@ __device__ __forceinline__ void tma_load_3d(u32 dst, const CUtensorMap* map, int
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
-template <int BOXW, int SPP>
+// PAIR4 (experimental, off by default, ORBX_FAST_PAIR4=1; NOT yet validated on a GPU — DESIGN.md §9): the quick test also looks at
+// the fourth opposite ring pair (4,12), evaluated only in warp-iterations in which some lane passed the three-pair test.
+template <int BOXW, int SPP, bool PAIR4 = false>
 __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_constant__ Plan P, const CUtensorMap* __restrict__ maps,
                                                                   const uint4* __restrict__ cells, int nCells, int nf,
                                                                   uint2* __restrict__ cand, int* __restrict__ candCount,
@@ -521,6 +523,8 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                     const int task = task0 + lane;
                     u32 fl = 0;                                        // bit 15 / bit 31: first / second pixel of the pair passes
                     int ent = 0;
+                    u32 vb4 = 0, md4 = 0, mb4 = 0;                     // (PAIR4 only)
+                    const u8* pe4 = tile;
                     if (task < ntask) {
                         const int row = npr == 1 ? task : (int)__umulhi((u32)task, inv);   // (inv overflows for npr == 1)
                         const int p = task - row * npr;
@@ -539,6 +543,16 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                         fl = ((md + C1) | (C2 - mb)) & 0x80008000u;
                         if (px0 < 0) fl &= 0xFFFF0000u;               // first pixel left of the domain
                         if (px0 + 1 >= dw) fl &= 0x0000FFFFu;         // second pixel right of the domain
+                        if (PAIR4) { vb4 = vb; md4 = md; mb4 = mb; pe4 = pe; }
+                    }
+                    if (PAIR4 && __any_sync(0xffffffffu, fl != 0u) && task < ntask) {
+                        // ring pixels 4 and 12 are (x + 3, y) and (x - 3, y): odd byte offsets, so each u16x2 is cut from two aligned
+                        // 16-bit loads (bytes 1 of the first and 0 of the second: selector 0x3421)
+#define LDU(o) ((u32) * reinterpret_cast<const u16*>(pe4 + (o)))
+                        const u32 d4 = vb4 - __byte_perm(LDU(2), LDU(4), 0x3421), d12 = vb4 - __byte_perm(LDU(-4), LDU(-2), 0x3421);
+#undef LDU
+                        const u32 md2 = __vminu2(md4, __vmaxu2(d4, d12)), mb2 = __vmaxu2(mb4, __vminu2(d4, d12));
+                        fl &= ((md2 + C1) | (C2 - mb2)) & 0x80008000u;
                     }
                     const u32 b0 = __ballot_sync(0xffffffffu, fl & 0x8000u), b1 = __ballot_sync(0xffffffffu, fl & 0x80000000u);
                     if ((b0 | b1) == 0u) continue;                     // warp-uniform: flat neighbourhoods leave nothing to compact
@@ -1498,6 +1512,7 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
             std::lock_guard<std::mutex> lk(amu2);
             if (ex->fwSmem > maxFw) {
                 ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, ORBX_FAST_SPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
+                ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, ORBX_FAST_SPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
                 ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
                 maxFw = ex->fwSmem;
             }
@@ -1660,7 +1675,11 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         if (ex->nCells > 0 && ex->useTma) {
             const int items = ex->nCells * nf;
             const int grid = std::min(ex->fwGrid, orb_div_up(items, ORBX_FW_WARPS));
-            if (P.fwBoxW == 64 && ex->fastConst)
+            static const bool pair4 = [] { const char* e = getenv("ORBX_FAST_PAIR4"); return e && e[0] == '1'; }();
+            if (P.fwBoxW == 64 && ex->fastConst && pair4)
+                k_fast_tma<64, ORBX_FAST_SPP, true><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
+                                                                                                ex->d_candCount, ex->d_status, ex->d_workCounter);
+            else if (P.fwBoxW == 64 && ex->fastConst)
                 k_fast_tma<64, ORBX_FAST_SPP><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
                                                                                           ex->d_candCount, ex->d_status, ex->d_workCounter);
             else
