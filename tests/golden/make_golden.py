@@ -340,6 +340,9 @@ def make_chain():
         ("rgbd_424x240_seed11", dict(W=424, H=240, seed=11, nfeatures=300, scaleFactor=1.5, nlevels=3, iniTh=15, minTh=3, mask=False)),
         # BASELINE config 3 geometry: 16:9, so DistributeOctTree starts from nIni = round(1280/720) = 2 root nodes (:542-562)
         ("c3_1280x720_seed3", dict(W=1280, H=720, seed=3, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniTh=20, minTh=7, mask=False)),
+        # the values the fork ships in Examples/ORB_RGB640x480.yaml (2000 features, iniThFAST 32); image regenerated from the seed
+        ("fork_yaml_640x480_seed2", dict(W=640, H=480, seed=2, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniTh=32, minTh=7, mask=False,
+                                         store_image=False)),
         # BASELINE config 5 (4K, 8000 features, 12 levels).  The 8 MB image is not stored: the tests regenerate it with
         # synth(W, H, seed) and check its CRC against the one recorded here.
         ("c5_3840x2160_seed1", dict(W=3840, H=2160, seed=1, nfeatures=8000, scaleFactor=1.2, nlevels=12, iniTh=20, minTh=7, mask=False,
