@@ -11,8 +11,9 @@ A "step" = ORB extraction (pyramid -> FAST cells -> octree -> blur -> orientatio
   matching   secondary metric of BASELINE.json: Hamming top-2 + ratio pairs/s (all-pairs keyframe matching, sharded by
              query keyframe, NCCL all-gather of the per-rank match tables when N>1) against the measured POPC peak
 
-`--impl reference` times the reference's CPU implementation of the path (the oracle port: the reference itself cannot be
-compiled here) on all host threads, on a bounded sample of the same workload per step.
+`--impl reference` times the reference's own CPU implementation of the path — oracle/_ref: src/ORBextractor.cc compiled unmodified
+over a stand-in for the OpenCV API slice it uses; the oracle port when oracle/_ref has not been built — on all host
+threads, on a bounded sample of the same workload per step.
 """
 import argparse
 import json
@@ -128,16 +129,52 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def _ref_available():
+    try:
+        from oracle import ref_py
+        return ref_py.available()
+    except Exception:
+        return False
+
+
+def ref_extract_mt(frames, threads):
+    """The reference's own ORBextractor (oracle/_ref: src/ORBextractor.cc compiled unmodified over the OpenCV stand-in) on `threads`
+    host threads, one extractor instance per thread, frames dealt round-robin; ctypes releases the GIL in the call.  Returns seconds."""
+    from oracle import ref_py
+    exs = [ref_py.RefExtractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH) for _ in range(threads)]
+
+    def work(t):
+        for i in range(t, len(frames), threads):
+            exs[t].extract(frames[i])
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    return time.perf_counter() - t0
+
+
+REF_NOTE = ("the reference's own src/ORBextractor.cc compiled unmodified (oracle/_ref); the image has no OpenCV C++, so cv::FAST / resize / "
+            "GaussianBlur / copyMakeBorder / fastAtan2 behind it are the oracle's scalar restatements (bit-exact against cv2 4.13), slower than "
+            "an optimised OpenCV build")
+
+
 def cpu_extract_sample(frames, threads, budget_s):
-    """Oracle extraction on `threads` host threads over a bounded sample; returns (frames/s, n_frames, seconds)."""
-    from oracle import orb_oracle_py as orc
-    chunk = max(threads * 4, 8)
+    """CPU extraction on `threads` host threads over a bounded sample; returns (frames/s, n_frames, seconds, kind)."""
+    use_ref = _ref_available()
+    chunk = max(threads * 16, 64) if use_ref else max(threads * 4, 8)      # (python threads: amortise their start-up)
     done, secs = 0, 0.0
+    from oracle import orb_oracle_py as orc
     while secs < budget_s and done + chunk <= len(frames):
-        s, _ = orc.extract_batch_mt(frames[done:done + chunk], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+        if use_ref:
+            s = ref_extract_mt(frames[done:done + chunk], threads)
+        else:
+            s, _ = orc.extract_batch_mt(frames[done:done + chunk], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
         secs += s
         done += chunk
-    return done / secs, done, secs
+    return done / secs, done, secs, ("reference" if use_ref else "port")
 
 
 def run_reference(args, rank, world):
@@ -146,13 +183,19 @@ def run_reference(args, rank, world):
     threads = host_threads()
     frames = make_frames(max(threads * 8, 64), 0, 4096)
     per_step = len(frames)
+    use_ref = _ref_available()
     from oracle import orb_oracle_py as orc
+
+    def one(fr):
+        if use_ref:
+            return ref_extract_mt(fr, threads)
+        return orc.extract_batch_mt(fr, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)[0]
+
     for _ in range(args.warmup):
-        orc.extract_batch_mt(frames[:threads], NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
+        one(frames[:threads])
     total_s = 0.0
     for _ in range(args.steps):
-        s, _ = orc.extract_batch_mt(frames, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, threads)
-        total_s += s
+        total_s += one(frames)
     v = per_step * args.steps / total_s
     sample = f"{per_step} of the 4096 frames per step, {threads} host threads, one extractor instance per thread"
     _emit({
@@ -160,8 +203,9 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "C2: batch of 640x480 synthetic frames, nFeatures=1000, 8 levels, scale 1.2, FAST 20/7",
-                   "frames_per_step": per_step, "note": "CPU oracle port of src/ORBextractor.cc (reference needs OpenCV/Boost to compile)"},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+                   "frames_per_step": per_step,
+                   "note": REF_NOTE if use_ref else "CPU oracle port of src/ORBextractor.cc (oracle/_ref has not been built)"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "reference" if use_ref else "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -497,9 +541,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         thr = host_threads()
-        v, n_done, s = cpu_extract_sample(frames, thr, 12.0)
-        cpu = {"value": v, "unit": "frames/s", "cores": thr, "kind": "port",
-               "sample": f"first {n_done} of the {nF} frames ({s:.1f} s), one oracle extractor per thread, frames dealt round-robin"}
+        v, n_done, s, kind = cpu_extract_sample(frames, thr, 12.0)
+        cpu = {"value": v, "unit": "frames/s", "cores": thr, "kind": kind,
+               "sample": f"first {n_done} of the {nF} frames ({s:.1f} s), one extractor instance per thread, frames dealt round-robin",
+               "note": REF_NOTE if kind == "reference" else "CPU oracle port of src/ORBextractor.cc (oracle/_ref has not been built)"}
 
     if rank == 0:
         _emit({
