@@ -13,11 +13,13 @@
 // library, and only as the checker / reported CPU baseline.  The product (orbslam_mapsave_b200/csrc) never
 // links, loads or calls it.
 //
-// PARITY PINNING: the reference ships no tests, golden vectors or fixtures for this path
-// and cannot be compiled here (needs OpenCV/Boost/DBoW2 C++ headers that are absent) => "parity unpinned" by
-// the reference itself.  What IS pinned: every OpenCV primitive below is checked bit-for-bit against cv2 4.13.0
-// golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py), and the full extractor is checked
-// against an independent Python chain of the real cv2 primitives (same script).
+// PARITY PINNING.  Extractor: oracle/_ref is the reference's own src/ORBextractor.cc compiled unmodified over ref_shim/cvshim.hpp
+// (OpenCV API stand-in whose image primitives are the functions of this file); run on a monotonic heap it equals this oracle's
+// output bit for bit on all golden configurations (tests/test_reference_ref.py).  Matcher: the reference ships no tests, golden
+// vectors or fixtures and src/ORBmatcher.cc cannot be compiled here (Boost/DBoW2/Eigen headers absent)
+// => "parity unpinned" by the reference itself for the matcher functions.  Also pinned: every OpenCV primitive below bit-for-bit
+// against cv2 4.13.0 golden vectors (tests/golden/*.npz, made by tests/golden/make_golden*.py), and the full extractor against an
+// independent Python chain of the real cv2 primitives (same script).
 //
 // Known, documented deviations from "whatever binary the reference authors ran":
 //   * DistributeOctTree sorts (size, node pointer) pairs (ORBextractor.cc:683); pointer order is allocator
