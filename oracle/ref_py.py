@@ -80,3 +80,91 @@ def extract_monotonic_heap(img, nfeatures, scale_factor, nlevels, ini_th, min_th
     kp = np.frombuffer(raw[4:4 + 28 * n], np.float32).reshape(n, 7).copy()
     desc = np.frombuffer(raw[4 + 28 * n:4 + 60 * n], np.uint8).reshape(n, 32).copy()
     return kp, desc
+
+
+# ---- matcher: the reference's own src/ORBmatcher.cc (oracle/_ref/libref_orbmatcher.so) --------------------------------------
+MLIB = os.path.join(_HERE, "_ref", "libref_orbmatcher.so")
+
+
+def matcher_available():
+    return os.path.exists(MLIB)
+
+
+class _Side(C.Structure):
+    _fields_ = [("n", C.c_int), ("desc", C.c_void_p), ("flag", C.c_void_p), ("angle", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p),
+                ("octave", C.c_void_p), ("uright", C.c_void_p), ("n_nodes", C.c_int), ("node_ids", C.c_void_p), ("off", C.c_void_p),
+                ("feat", C.c_void_p)]
+
+
+_mlib = None
+
+
+def mlib():
+    global _mlib
+    if _mlib is None:
+        L = C.CDLL(MLIB)
+        L.refm_descriptor_distance.restype = C.c_int
+        L.refm_descriptor_distance.argtypes = [C.c_void_p, C.c_void_p]
+        L.refm_three_maxima.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.refm_search_bow_kf_frame.restype = C.c_int
+        L.refm_search_bow_kf_frame.argtypes = [C.POINTER(_Side), C.POINTER(_Side), C.c_float, C.c_int, C.c_void_p]
+        L.refm_search_bow_kf_kf.restype = C.c_int
+        L.refm_search_bow_kf_kf.argtypes = [C.POINTER(_Side), C.POINTER(_Side), C.c_float, C.c_int, C.c_void_p]
+        L.refm_search_triangulation.restype = C.c_int
+        L.refm_search_triangulation.argtypes = [C.POINTER(_Side), C.POINTER(_Side), C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int]
+        _mlib = L
+    return _mlib
+
+
+def _side(desc, fv, angle, flag=None, x=None, y=None, octave=None, uright=None):
+    """fv: an object with .ids / .off / .feat int32 arrays (oracle.orb_oracle_py.FeatVec).  Returns (struct, keep-alive list)."""
+    keep = [np.ascontiguousarray(desc, np.uint8).reshape(-1, 32), np.ascontiguousarray(angle, np.float32)]
+    p = lambda a: a.ctypes.data if a is not None else None
+    opt = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+    flag, x, y, octave, uright = opt(flag, np.uint8), opt(x, np.float32), opt(y, np.float32), opt(octave, np.int32), opt(uright, np.float32)
+    ids, off, feat = (np.ascontiguousarray(a, np.int32) for a in (fv.ids, fv.off, fv.feat))
+    keep += [flag, x, y, octave, uright, ids, off, feat]
+    s = _Side(len(keep[0]), p(keep[0]), p(flag), p(keep[1]), p(x), p(y), p(octave), p(uright), len(ids), p(ids), p(off), p(feat))
+    return s, keep
+
+
+def ref_descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return mlib().refm_descriptor_distance(a.ctypes.data, b.ctypes.data)
+
+
+def ref_three_maxima(counts):
+    c = np.ascontiguousarray(counts, np.int32)
+    out = np.zeros(3, np.int32)
+    mlib().refm_three_maxima(c.ctypes.data, len(c), out.ctypes.data)
+    return tuple(int(v) for v in out)
+
+
+def ref_search_bow_kf_f(desc1, valid1, angle1, fv1, desc2, angle2, fv2, nnratio, check_ori):
+    s1, k1 = _side(desc1, fv1, angle1, flag=valid1)
+    s2, k2 = _side(desc2, fv2, angle2)
+    m = np.zeros(max(len(k2[0]), 1), np.int32)
+    n = mlib().refm_search_bow_kf_frame(C.byref(s1), C.byref(s2), float(nnratio), int(check_ori), m.ctypes.data)
+    return n, m[:len(k2[0])]
+
+
+def ref_search_bow_kf_kf(desc1, valid1, angle1, fv1, desc2, valid2, angle2, fv2, nnratio, check_ori):
+    s1, k1 = _side(desc1, fv1, angle1, flag=valid1)
+    s2, k2 = _side(desc2, fv2, angle2, flag=valid2)
+    m = np.zeros(max(len(k1[0]), 1), np.int32)
+    n = mlib().refm_search_bow_kf_kf(C.byref(s1), C.byref(s2), float(nnratio), int(check_ori), m.ctypes.data)
+    return n, m[:len(k1[0])]
+
+
+def ref_search_triangulation(desc1, hasmp1, uright1, kx1, ky1, ang1, fv1, desc2, hasmp2, uright2, kx2, ky2, ang2, oct2, fv2,
+                             F12, ex, ey, sf2, sigma2_2, only_stereo, check_ori, nnratio=0.6):
+    s1, k1 = _side(desc1, fv1, ang1, flag=hasmp1, x=kx1, y=ky1, octave=np.zeros(len(desc1), np.int32), uright=uright1)
+    s2, k2 = _side(desc2, fv2, ang2, flag=hasmp2, x=kx2, y=ky2, octave=oct2, uright=uright2)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf2, sg = np.ascontiguousarray(sf2, np.float32), np.ascontiguousarray(sigma2_2, np.float32)
+    cap = max(len(k1[0]), 1)
+    pairs = np.zeros((cap, 2), np.int32)
+    n = mlib().refm_search_triangulation(C.byref(s1), C.byref(s2), F.ctypes.data, float(ex), float(ey), sf2.ctypes.data, sg.ctypes.data,
+                                         len(sf2), int(only_stereo), float(nnratio), int(check_ori), pairs.ctypes.data, cap)
+    return n, pairs[:n].copy()

@@ -1,0 +1,193 @@
+// ref_matcher_driver.cpp — TEST INFRASTRUCTURE.  C entry points around the reference's own ORB_SLAM2::ORBmatcher
+// (/root/reference/src/ORBmatcher.cc compiled unmodified; KeyFrame / Frame / MapPoint are the plain-data stand-ins of
+// ref_types.hpp, DBoW2::FeatureVector is the reference's own).  Pinned through these: DescriptorDistance, SearchByBoW x2,
+// SearchForTriangulation (+ CheckDistEpipolarLine), ComputeThreeMaxima.
+#include <vector>
+#include <ORBmatcher.h>      // the shadow next to this file first (angle brackets: via -I, so that its #include_next works)
+
+namespace ORB_SLAM2 {
+
+// members of the stand-ins that the reference defines in translation units which cannot be compiled here
+void MapPoint::AddObservation(KeyFrame* pKF, size_t idx) {                 // src/MapPoint.cc:93-104
+    if (mObservations.count(pKF)) return;
+    mObservations[pKF] = idx;
+    if (pKF->mvuRight[idx] >= 0) nObs += 2; else nObs++;
+}
+void MapPoint::Replace(MapPoint* pMP) {                                     // src/MapPoint.cc:247-283 (without the map bookkeeping)
+    if (pMP == this) return;
+    std::map<KeyFrame*, size_t> obs = mObservations;
+    mObservations.clear();
+    mbBad = true;
+    for (std::map<KeyFrame*, size_t>::iterator mit = obs.begin(); mit != obs.end(); ++mit) {
+        KeyFrame* pKF = mit->first;
+        if (!pMP->IsInKeyFrame(pKF)) { pKF->ReplaceMapPointMatch(mit->second, pMP); pMP->AddObservation(pKF, mit->second); }
+        else pKF->EraseMapPointMatch(mit->second);
+    }
+}
+std::vector<size_t> Frame::GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel, const int maxLevel) const {
+    std::vector<size_t> vIndices;                                           // src/Frame.cc:445-498
+    const int nMinCellX = std::max(0, (int)floor((x - mnMinX - r) * mfGridElementWidthInv));
+    if (nMinCellX >= FRAME_GRID_COLS) return vIndices;
+    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)ceil((x - mnMinX + r) * mfGridElementWidthInv));
+    if (nMaxCellX < 0) return vIndices;
+    const int nMinCellY = std::max(0, (int)floor((y - mnMinY - r) * mfGridElementHeightInv));
+    if (nMinCellY >= FRAME_GRID_ROWS) return vIndices;
+    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)ceil((y - mnMinY + r) * mfGridElementHeightInv));
+    if (nMaxCellY < 0) return vIndices;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const std::vector<size_t>& vCell = mGrid[ix][iy];
+            for (size_t j = 0; j < vCell.size(); j++) {
+                const cv::KeyPoint& kpUn = mvKeysUn[vCell[j]];
+                if (bCheckLevels) {
+                    if (kpUn.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kpUn.octave > maxLevel) continue;
+                }
+                const float distx = kpUn.pt.x - x, disty = kpUn.pt.y - y;
+                if (fabs(distx) < r && fabs(disty) < r) vIndices.push_back(vCell[j]);
+            }
+        }
+    return vIndices;
+}
+std::vector<size_t> KeyFrame::GetFeaturesInArea(const float& x, const float& y, const float& r) const {
+    std::vector<size_t> vIndices;                                           // src/KeyFrame.cc:1311-1350
+    const int nMinCellX = std::max(0, (int)floor((x - mnMinX - r) * mfGridElementWidthInv));
+    if (nMinCellX >= mnGridCols) return vIndices;
+    const int nMaxCellX = std::min((int)mnGridCols - 1, (int)ceil((x - mnMinX + r) * mfGridElementWidthInv));
+    if (nMaxCellX < 0) return vIndices;
+    const int nMinCellY = std::max(0, (int)floor((y - mnMinY - r) * mfGridElementHeightInv));
+    if (nMinCellY >= mnGridRows) return vIndices;
+    const int nMaxCellY = std::min((int)mnGridRows - 1, (int)ceil((y - mnMinY + r) * mfGridElementHeightInv));
+    if (nMaxCellY < 0) return vIndices;
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const std::vector<size_t>& vCell = mGrid[ix][iy];
+            for (size_t j = 0; j < vCell.size(); j++) {
+                const cv::KeyPoint& kpUn = mvKeysUn[vCell[j]];
+                const float distx = kpUn.pt.x - x, disty = kpUn.pt.y - y;
+                if (fabs(distx) < r && fabs(disty) < r) vIndices.push_back(vCell[j]);
+            }
+        }
+    return vIndices;
+}
+
+struct MatcherAccess : public ORBmatcher {                                  // ComputeThreeMaxima is protected
+    MatcherAccess(float r, bool o) : ORBmatcher(r, o) {}
+    using ORBmatcher::ComputeThreeMaxima;
+};
+
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+extern "C" {
+
+struct refm_side {
+    int n;
+    const unsigned char* desc;      // n x 32
+    const unsigned char* flag;      // n: the feature holds a good MapPoint (may be NULL = none)
+    const float *angle, *x, *y;     // keypoint angle / undistorted position (x, y may be NULL)
+    const int* octave;              // may be NULL
+    const float* uright;            // may be NULL (= -1)
+    int n_nodes;
+    const int *node_ids, *off, *feat;
+};
+
+}
+
+namespace {
+
+template <class T> void fill_common(T& k, const refm_side& s, std::vector<MapPoint>& pool) {
+    k.N = s.n;
+    k.mDescriptors.create(s.n > 0 ? s.n : 1, 32, CV_8U);
+    k.mDescriptors.rows = s.n;
+    k.mvKeysUn.resize(s.n);
+    k.mvKeys.resize(s.n);
+    k.mvuRight.assign(s.n, -1.f);
+    k.mvpMapPoints.assign(s.n, static_cast<MapPoint*>(NULL));
+    pool.resize(s.n);
+    for (int i = 0; i < s.n; i++) {
+        memcpy(k.mDescriptors.ptr(i), s.desc + 32 * (size_t)i, 32);
+        cv::KeyPoint kp(s.x ? s.x[i] : 0.f, s.y ? s.y[i] : 0.f, 31.f, s.angle ? s.angle[i] : 0.f, 0.f, s.octave ? s.octave[i] : 0, -1);
+        k.mvKeysUn[i] = kp;
+        k.mvKeys[i] = kp;
+        if (s.uright) k.mvuRight[i] = s.uright[i];
+        if (s.flag && s.flag[i]) k.mvpMapPoints[i] = &pool[i];
+    }
+    for (int a = 0; a < s.n_nodes; a++)
+        for (int e = s.off[a]; e < s.off[a + 1]; e++) k.mFeatVec[(DBoW2::NodeId)s.node_ids[a]].push_back((unsigned int)s.feat[e]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int refm_descriptor_distance(const unsigned char* a, const unsigned char* b) {
+    cv::Mat A(1, 32, CV_8U, (void*)a), B(1, 32, CV_8U, (void*)b);
+    return ORBmatcher::DescriptorDistance(A, B);
+}
+
+void refm_three_maxima(const int* counts, int L, int* out3) {
+    std::vector<std::vector<int> > histo(L);
+    for (int i = 0; i < L; i++) histo[i].assign(counts[i], 0);
+    MatcherAccess m(0.6f, true);
+    int i1 = -1, i2 = -1, i3 = -1;
+    m.ComputeThreeMaxima(histo.data(), L, i1, i2, i3);
+    out3[0] = i1; out3[1] = i2; out3[2] = i3;
+}
+
+int refm_search_bow_kf_frame(const refm_side* kf, const refm_side* fr, float nnratio, int check_ori, int* m21) {
+    KeyFrame K;
+    Frame F;
+    std::vector<MapPoint> p1, p2;
+    fill_common(K, *kf, p1);
+    fill_common(F, *fr, p2);
+    std::fill(F.mvpMapPoints.begin(), F.mvpMapPoints.end(), static_cast<MapPoint*>(NULL));
+    ORBmatcher m(nnratio, check_ori != 0);
+    std::vector<MapPoint*> out;
+    const int n = m.SearchByBoW(&K, F, out);
+    for (int j = 0; j < fr->n; j++) m21[j] = out[j] ? (int)(out[j] - p1.data()) : -1;
+    return n;
+}
+
+int refm_search_bow_kf_kf(const refm_side* k1, const refm_side* k2, float nnratio, int check_ori, int* m12) {
+    KeyFrame A, B;
+    std::vector<MapPoint> p1, p2;
+    fill_common(A, *k1, p1);
+    fill_common(B, *k2, p2);
+    ORBmatcher m(nnratio, check_ori != 0);
+    std::vector<MapPoint*> out;
+    const int n = m.SearchByBoW(&A, &B, out);
+    for (int i = 0; i < k1->n; i++) m12[i] = out[i] ? (int)(out[i] - p2.data()) : -1;
+    return n;
+}
+
+int refm_search_triangulation(const refm_side* k1, const refm_side* k2, const float* F12, float ex, float ey, const float* sf2,
+                              const float* sigma2_2, int nlev, int only_stereo, float nnratio, int check_ori, int* pairs, int cap) {
+    KeyFrame A, B;
+    std::vector<MapPoint> p1, p2;
+    fill_common(A, *k1, p1);
+    fill_common(B, *k2, p2);
+    // epipole (:667-673): C2 = R2w * Cw + t2w with R2w = I, t2w = 0, Cw = (ex, ey, 1) and unit intrinsics gives exactly (ex, ey)
+    A.Ow.create(3, 1, CV_32F);
+    A.Ow.at<float>(0) = ex; A.Ow.at<float>(1) = ey; A.Ow.at<float>(2) = 1.f;
+    B.Rcw.create(3, 3, CV_32F);
+    B.tcw.create(3, 1, CV_32F);
+    for (int r = 0; r < 3; r++) {
+        B.tcw.at<float>(r) = 0.f;
+        for (int c = 0; c < 3; c++) B.Rcw.at<float>(r, c) = r == c ? 1.f : 0.f;
+    }
+    B.fx = B.fy = 1.f; B.cx = B.cy = 0.f;
+    B.mvScaleFactors.assign(sf2, sf2 + nlev);
+    B.mvLevelSigma2.assign(sigma2_2, sigma2_2 + nlev);
+    cv::Mat F(3, 3, CV_32F);
+    for (int i = 0; i < 9; i++) F.at<float>(i / 3, i % 3) = F12[i];
+    ORBmatcher m(nnratio, check_ori != 0);
+    std::vector<std::pair<size_t, size_t> > out;
+    const int n = m.SearchForTriangulation(&A, &B, F, out, only_stereo != 0);
+    for (size_t i = 0; i < out.size() && (int)i < cap; i++) { pairs[2 * i] = (int)out[i].first; pairs[2 * i + 1] = (int)out[i].second; }
+    return n >= 0 ? (int)out.size() : n;
+}
+
+}  // extern "C"

@@ -53,6 +53,20 @@ public:
     Mat rowRange(int a, int b) const { Mat m = *this; m.rows = b - a; m.data = data + (size_t)a * step; return m; }
     Mat colRange(int a, int b) const { Mat m = *this; m.cols = b - a; m.data = data + (size_t)a * elemSize(); return m; }
     Mat roi(int x, int y, int w, int h) const { return rowRange(y, y + h).colRange(x, x + w); }
+    Mat col(int c) const { return colRange(c, c + 1); }
+    Mat t() const {                                       // transposed copy (CV_32F or CV_8U)
+        Mat m(cols, rows, type_);
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++)
+                std::memcpy(m.data + (size_t)c * m.step + (size_t)r * elemSize(), data + (size_t)r * step + (size_t)c * elemSize(), elemSize());
+        return m;
+    }
+    double dot(const Mat& o) const {                      // CV_32F, accumulated in double like cv::Mat::dot
+        double s = 0;
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < cols; c++) s += (double)at<float>(r, c) * (double)o.at<float>(r, c);
+        return s;
+    }
     Mat clone() const {
         Mat m(rows, cols, type_);
         for (int r = 0; r < rows; r++) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * elemSize());

@@ -54,3 +54,65 @@ def test_reference_with_stock_heap_differs_only_by_the_pointer_tie_break(seed):
     common = set(ref) & set(ora)
     assert len(common) >= 0.97 * len(ora) and abs(len(ref) - len(ora)) <= 16
     assert all(ref[k] == ora[k] for k in common)
+
+
+# ---- matcher: the reference's own src/ORBmatcher.cc (compiled unmodified over plain-data stand-ins for KeyFrame / Frame / MapPoint)
+matcher = pytest.mark.skipif(not ref_py.matcher_available(), reason="oracle/_ref/libref_orbmatcher.so not built")
+
+
+def _scene(*a, **k):
+    import test_gpu_match as tgm            # the scene generator of the GPU parity tests (planted matches, TH_LOW edges, ties, claims)
+    return tgm._scene(*a, **k)
+
+
+@matcher
+@pytest.mark.parametrize("n1,n2,seed", [(300, 280, 0), (2000, 2000, 1), (1000, 40, 2), (50, 900, 3), (0, 10, 4), (10, 0, 5)])
+@pytest.mark.parametrize("ratio,ori", [(0.7, True), (0.75, True), (0.6, False), (1.0, True)])
+def test_reference_search_by_bow_kf_frame_equals_oracle(n1, n2, seed, ratio, ori):
+    s = _scene(n1, n2, seed)
+    f1, f2 = orc.FeatVec(s["node1"]), orc.FeatVec(s["node2"])
+    on, om = orc.search_bow_kf_f(s["d1"], s["flag1"], s["ang1"], f1, s["d2"], s["ang2"], f2, ratio, ori)
+    rn, rm = ref_py.ref_search_bow_kf_f(s["d1"], s["flag1"], s["ang1"], f1, s["d2"], s["ang2"], f2, ratio, ori)
+    assert rn == on and np.array_equal(rm, om)
+
+
+@matcher
+@pytest.mark.parametrize("n1,n2,seed", [(300, 280, 10), (2000, 2000, 11), (700, 64, 12), (0, 0, 13)])
+@pytest.mark.parametrize("ratio,ori", [(0.75, True), (0.6, False)])
+def test_reference_search_by_bow_kf_kf_equals_oracle(n1, n2, seed, ratio, ori):
+    s = _scene(n1, n2, seed)
+    f1, f2 = orc.FeatVec(s["node1"]), orc.FeatVec(s["node2"])
+    on, om = orc.search_bow_kf_kf(s["d1"], s["flag1"], s["ang1"], f1, s["d2"], s["flag2"], s["ang2"], f2, ratio, ori)
+    rn, rm = ref_py.ref_search_bow_kf_kf(s["d1"], s["flag1"], s["ang1"], f1, s["d2"], s["flag2"], s["ang2"], f2, ratio, ori)
+    assert rn == on and np.array_equal(rm, om)
+
+
+@matcher
+@pytest.mark.parametrize("n1,n2,seed", [(300, 280, 20), (2000, 2000, 21), (64, 900, 22), (5, 0, 23)])
+@pytest.mark.parametrize("only_stereo,ori", [(False, False), (True, False), (False, True)])
+def test_reference_search_for_triangulation_equals_oracle(n1, n2, seed, only_stereo, ori):
+    s = _scene(n1, n2, seed, tri=True)
+    rng = np.random.default_rng(seed)
+    F12 = (rng.normal(0, 1, (3, 3)) * np.array([[1e-6, 1e-5, 1e-3], [1e-5, 1e-6, 1e-3], [1e-3, 1e-3, 1e-1]])).astype(np.float32)
+    sf2 = (1.2 ** np.arange(8)).astype(np.float32)
+    sig2 = (sf2 * sf2 * 5000).astype(np.float32)
+    args = (s["d1"], s["flag1"], s["ur1"], s["x1"], s["y1"], s["ang1"], orc.FeatVec(s["node1"]),
+            s["d2"], s["flag2"], s["ur2"], s["x2"], s["y2"], s["ang2"], s["oct2"], orc.FeatVec(s["node2"]),
+            F12, 320.0, 240.0, sf2, sig2, only_stereo, ori)
+    on, op = orc.search_triangulation(*args)
+    rn, rp = ref_py.ref_search_triangulation(*args)
+    assert len(rp) == len(op) and np.array_equal(rp, op)
+    if n1 >= 2000 and not only_stereo:
+        assert len(op) >= 10
+
+
+@matcher
+def test_reference_descriptor_distance_and_three_maxima_equal_oracle():
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+        assert ref_py.ref_descriptor_distance(a, b) == orc.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
+    cases = [rng.integers(0, 50, 30) for _ in range(100)] + [np.zeros(30, int), np.full(30, 4), np.eye(30, dtype=int)[7] * 9,
+                                                             np.array([100, 9, 10, 11] + [0] * 26)]
+    for h in cases:
+        assert ref_py.ref_three_maxima(h) == tuple(orc.three_maxima(h))
