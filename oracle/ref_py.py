@@ -168,3 +168,56 @@ def ref_search_triangulation(desc1, hasmp1, uright1, kx1, ky1, ang1, fv1, desc2,
     n = mlib().refm_search_triangulation(C.byref(s1), C.byref(s2), F.ctypes.data, float(ex), float(ey), sf2.ctypes.data, sg.ctypes.data,
                                          len(sf2), int(only_stereo), float(nnratio), int(check_ori), pairs.ctypes.data, cap)
     return n, pairs[:n].copy()
+
+
+# ---- window searches of the tracker through the reference's own code (grid: an oracle.orb_oracle_py.Grid; same struct layout) ----
+def _wlib():
+    L = mlib()
+    if not getattr(L, "_win_ready", False):
+        vp, f32, i32 = C.c_void_p, C.c_float, C.c_int
+        L.refm_search_projection_map.restype = i32
+        L.refm_search_projection_map.argtypes = [vp, i32] + [vp] * 8 + [f32, f32, vp]
+        L.refm_search_projection_frame.restype = i32
+        L.refm_search_projection_frame.argtypes = [vp, vp, vp] + [f32] * 6 + [i32] + [vp] * 6 + [f32, i32, i32, f32, vp]
+        L.refm_search_initialization.restype = i32
+        L.refm_search_initialization.argtypes = [vp, i32, vp, vp, vp, vp, i32, f32, i32, vp]
+        L._win_ready = True
+    return L
+
+
+def _a(x, t):
+    return np.ascontiguousarray(x, t)
+
+
+def ref_search_projection_map(grid, in_view, proj_x, proj_y, proj_xr, level, view_cos, desc, claims, th, nnratio):
+    g = grid.c()
+    iv, cl, d = _a(in_view, np.uint8), _a(claims, np.uint8), _a(desc, np.uint8).reshape(-1, 32)
+    px, py, pr, vc, lv = _a(proj_x, np.float32), _a(proj_y, np.float32), _a(proj_xr, np.float32), _a(view_cos, np.float32), _a(level, np.int32)
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    n = _wlib().refm_search_projection_map(C.addressof(g), len(iv), iv.ctypes.data, px.ctypes.data, py.ctypes.data, pr.ctypes.data,
+                                           lv.ctypes.data, vc.ctypes.data, d.ctypes.data, cl.ctypes.data, float(th), float(nnratio),
+                                           owner.ctypes.data)
+    return n, owner[:grid.n]
+
+
+def ref_search_projection_frame(grid, Tcw, Tlw, fx, fy, cx, cy, mbf, mb, has_point, world, octave, angle, desc, claims, th, mono, check_ori,
+                                nnratio=0.9):
+    g = grid.c()
+    hp, cl, d = _a(has_point, np.uint8), _a(claims, np.uint8), _a(desc, np.uint8).reshape(-1, 32)
+    w, an, oc = _a(world, np.float32).reshape(-1, 3), _a(angle, np.float32), _a(octave, np.int32)
+    Tc, Tl = _a(Tcw, np.float32).reshape(-1)[:12].copy(), _a(Tlw, np.float32).reshape(-1)[:12].copy()
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    n = _wlib().refm_search_projection_frame(C.addressof(g), Tc.ctypes.data, Tl.ctypes.data, fx, fy, cx, cy, mbf, mb, len(hp), hp.ctypes.data,
+                                             w.ctypes.data, oc.ctypes.data, an.ctypes.data, d.ctypes.data, cl.ctypes.data, float(th),
+                                             int(mono), int(check_ori), float(nnratio), owner.ctypes.data)
+    return n, owner[:grid.n]
+
+
+def ref_search_initialization(grid2, desc1, octave1, angle1, prev_matched, window_size, nnratio, check_ori):
+    g = grid2.c()
+    d, oc, an = _a(desc1, np.uint8).reshape(-1, 32), _a(octave1, np.int32), _a(angle1, np.float32)
+    assert prev_matched.dtype == np.float32 and prev_matched.flags.c_contiguous
+    m = np.zeros(max(len(d), 1), np.int32)
+    n = _wlib().refm_search_initialization(C.addressof(g), len(d), d.ctypes.data, oc.ctypes.data, an.ctypes.data, prev_matched.ctypes.data,
+                                           int(window_size), float(nnratio), int(check_ori), m.ctypes.data)
+    return n, m[:len(d)]

@@ -3,9 +3,8 @@
 // `A*B + C` is ONE cv::gemm call that multiplies and adds in float32, left to right (characterised against cv2 4.13 in
 // tests/golden/prim_gemm3.npz); that is the only product the PINNED functions use (SearchForTriangulation's epipole, :667-673).
 // `M / s` and `s * M` scale by (float)(1.0 / s) resp. (float)s (convertTo); dot() and norm() accumulate in double.
-// NOT reproduced: `-R.t()*t` is evaluated here as a plain float product of a materialised transpose, whereas cv::gemm takes its
-// general (double-accumulating) path for a transposed operand — so the window searches / Fuse / SearchBySim3 of this build, which
-// use it, are compiled but NOT used as a numerical reference (their oracle restatements carry the pinned rule).
+// `-R.t()*t` (the only product without `+ C`) follows gemm's general path: double accumulation (same golden file).  The similarity
+// scalings of SearchBySim3 / Fuse(Scw) (`M / s`, `s * M.t()`) are written as convertTo does them but are not exercised by the tests.
 #pragma once
 #define ORB_B200_FORCE_CV_SHIM 1
 #include <cassert>
@@ -25,9 +24,22 @@ inline Mat gemm_small(const Mat& A, const Mat& B, const Mat* C) {
         }
     return out;
 }
-struct MatProd {                                          // A * B, evaluated when it meets `+ C` (one gemm) or a Mat
+// A * B WITHOUT `+ C`: the only such products in src/ORBmatcher.cc are `-R.t()*t` (:306, :993, :1344, :1481), which cv::gemm runs on
+// its general path (transposed operand): products accumulated in DOUBLE, rounded once.  The negation of the materialised transpose is
+// exact, so (-R^T)*t accumulated in double equals gemm(R, t, alpha = -1, GEMM_1_T).
+inline Mat gemm_general(const Mat& A, const Mat& B) {
+    Mat out(A.rows, B.cols, CV_32F);
+    for (int r = 0; r < A.rows; r++)
+        for (int c = 0; c < B.cols; c++) {
+            double acc = (double)A.at<float>(r, 0) * (double)B.at<float>(0, c);
+            for (int k = 1; k < A.cols; k++) acc = acc + (double)A.at<float>(r, k) * (double)B.at<float>(k, c);
+            out.at<float>(r, c) = (float)acc;
+        }
+    return out;
+}
+struct MatProd {                                          // A * B, evaluated when it meets `+ C` (one small gemm) or a Mat
     Mat a, b;
-    operator Mat() const { return gemm_small(a, b, nullptr); }
+    operator Mat() const { return gemm_general(a, b); }
 };
 inline MatProd operator*(const Mat& a, const Mat& b) { MatProd p = {a, b}; return p; }
 inline Mat operator+(const MatProd& p, const Mat& c) { return gemm_small(p.a, p.b, &c); }

@@ -190,4 +190,146 @@ int refm_search_triangulation(const refm_side* k1, const refm_side* k2, const fl
     return n >= 0 ? (int)out.size() : n;
 }
 
+// ---- window searches of the tracker: Frame stand-ins filled from the oracle's grid view (same struct layout) ----
+struct refm_grid {
+    int n;
+    const unsigned char* desc;
+    const float *x, *y;
+    const int* octave;
+    const float *angle, *uright;
+    const unsigned char* blocked;       // the feature already holds a MapPoint with Observations() > 0
+    int grid_cols, grid_rows;
+    float min_x, min_y, max_x, max_y, inv_w, inv_h;
+    const int *cell_offsets, *cell_features;    // CSR of mGrid, cell = ix * grid_rows + iy, entries in push order
+    const float* scale_factors;
+    int n_levels;
+};
+
+static void fill_frame(Frame& F, const refm_grid& g, std::vector<MapPoint>& holders) {
+    F.N = g.n;
+    F.mDescriptors.create(g.n > 0 ? g.n : 1, 32, CV_8U);
+    F.mDescriptors.rows = g.n;
+    F.mvKeysUn.resize(g.n);
+    F.mvuRight.assign(g.n, -1.f);
+    F.mvpMapPoints.assign(g.n, static_cast<MapPoint*>(NULL));
+    F.mvbOutlier.assign(g.n, false);
+    holders.resize(g.n);
+    for (int i = 0; i < g.n; i++) {
+        memcpy(F.mDescriptors.ptr(i), g.desc + 32 * (size_t)i, 32);
+        F.mvKeysUn[i] = cv::KeyPoint(g.x[i], g.y[i], 31.f, g.angle ? g.angle[i] : 0.f, 0.f, g.octave[i], -1);
+        if (g.uright) F.mvuRight[i] = g.uright[i];
+        if (g.blocked && g.blocked[i]) { holders[i].nObs = 1; F.mvpMapPoints[i] = &holders[i]; }
+    }
+    F.mvKeys = F.mvKeysUn;
+    F.mvScaleFactors.assign(g.scale_factors, g.scale_factors + g.n_levels);
+    F.mnScaleLevels = g.n_levels;
+    F.mnMinX = g.min_x; F.mnMinY = g.min_y; F.mnMaxX = g.max_x; F.mnMaxY = g.max_y;
+    F.mfGridElementWidthInv = g.inv_w; F.mfGridElementHeightInv = g.inv_h;
+    assert(g.grid_cols == FRAME_GRID_COLS && g.grid_rows == FRAME_GRID_ROWS);
+    for (int ix = 0; ix < FRAME_GRID_COLS; ix++)
+        for (int iy = 0; iy < FRAME_GRID_ROWS; iy++) {
+            const int c = ix * FRAME_GRID_ROWS + iy;
+            for (int e = g.cell_offsets[c]; e < g.cell_offsets[c + 1]; e++) F.mGrid[ix][iy].push_back((size_t)g.cell_features[e]);
+        }
+}
+
+static void owners_out(const Frame& F, const std::vector<MapPoint>& pool, int* owner) {
+    for (int i = 0; i < F.N; i++) {
+        const MapPoint* p = F.mvpMapPoints[i];
+        owner[i] = (p && !pool.empty() && p >= pool.data() && p < pool.data() + pool.size()) ? (int)(p - pool.data()) : -1;
+    }
+}
+
+// SearchByProjection(Frame&, const vector<MapPoint*>&, th)  (:45-129)
+int refm_search_projection_map(const refm_grid* g, int npts, const unsigned char* in_view, const float* proj_x, const float* proj_y,
+                               const float* proj_xr, const int* level, const float* view_cos, const unsigned char* desc,
+                               const unsigned char* claims, float th, float nnratio, int* owner) {
+    Frame F;
+    std::vector<MapPoint> holders, pool(npts);
+    fill_frame(F, *g, holders);
+    std::vector<MapPoint*> pts(npts);
+    for (int i = 0; i < npts; i++) {
+        MapPoint& p = pool[i];
+        p.mbTrackInView = in_view[i] != 0;
+        p.mTrackProjX = proj_x[i]; p.mTrackProjY = proj_y[i]; p.mTrackProjXR = proj_xr[i];
+        p.mnTrackScaleLevel = level[i]; p.mTrackViewCos = view_cos[i];
+        p.nObs = claims[i] ? 1 : 0;
+        p.mDescriptor.create(1, 32, CV_8U);
+        memcpy(p.mDescriptor.ptr(), desc + 32 * (size_t)i, 32);
+        pts[i] = &p;
+    }
+    ORBmatcher m(nnratio, true);
+    const int n = m.SearchByProjection(F, pts, th);
+    owners_out(F, pool, owner);
+    return n;
+}
+
+// SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)  (:1331-1463); owner: -1 also for entries the rotation
+// cull set back to NULL
+int refm_search_projection_frame(const refm_grid* g, const float* Tcw, const float* Tlw, float fx, float fy, float cx, float cy, float mbf,
+                                 float mb, int n_last, const unsigned char* has_point, const float* world, const int* octave,
+                                 const float* angle, const unsigned char* desc, const unsigned char* claims, float th, int mono,
+                                 int check_ori, float nnratio, int* owner) {
+    Frame C, L;
+    std::vector<MapPoint> holders, pool(n_last);
+    fill_frame(C, *g, holders);
+    auto pose = [](Frame& F, const float* T) {
+        F.mTcw.create(4, 4, CV_32F);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) F.mTcw.at<float>(r, c) = T[4 * r + c];
+        F.mTcw.at<float>(3, 0) = F.mTcw.at<float>(3, 1) = F.mTcw.at<float>(3, 2) = 0.f;
+        F.mTcw.at<float>(3, 3) = 1.f;
+    };
+    pose(C, Tcw);
+    pose(L, Tlw);
+    C.fx = fx; C.fy = fy; C.cx = cx; C.cy = cy; C.mbf = mbf; C.mb = mb;
+    L.N = n_last;
+    L.mvKeys.resize(n_last);
+    L.mvKeysUn.resize(n_last);
+    L.mvpMapPoints.assign(n_last, static_cast<MapPoint*>(NULL));
+    L.mvbOutlier.assign(n_last, false);
+    for (int i = 0; i < n_last; i++) {
+        L.mvKeys[i] = L.mvKeysUn[i] = cv::KeyPoint(0.f, 0.f, 31.f, angle[i], 0.f, octave[i], -1);
+        if (!has_point[i]) continue;
+        MapPoint& p = pool[i];
+        p.nObs = claims[i] ? 1 : 0;
+        p.mWorldPos.create(3, 1, CV_32F);
+        for (int c = 0; c < 3; c++) p.mWorldPos.at<float>(c) = world[3 * (size_t)i + c];
+        p.mDescriptor.create(1, 32, CV_8U);
+        memcpy(p.mDescriptor.ptr(), desc + 32 * (size_t)i, 32);
+        L.mvpMapPoints[i] = &p;
+    }
+    ORBmatcher m(nnratio, check_ori != 0);
+    const int n = m.SearchByProjection(C, L, th, mono != 0);
+    owners_out(C, pool, owner);
+    return n;
+}
+
+// SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  (:408-523); prev_matched: n1 x 2 floats, updated in place
+int refm_search_initialization(const refm_grid* g2, int n1, const unsigned char* desc1, const int* octave1, const float* angle1,
+                               float* prev_matched, int window_size, float nnratio, int check_ori, int* m12) {
+    Frame F1, F2;
+    std::vector<MapPoint> holders;
+    fill_frame(F2, *g2, holders);
+    F1.N = n1;
+    F1.mvKeysUn.resize(n1);
+    F1.mDescriptors.create(n1 > 0 ? n1 : 1, 32, CV_8U);
+    F1.mDescriptors.rows = n1;
+    std::vector<cv::Point2f> prev(n1);
+    for (int i = 0; i < n1; i++) {
+        F1.mvKeysUn[i] = cv::KeyPoint(prev_matched[2 * i], prev_matched[2 * i + 1], 31.f, angle1[i], 0.f, octave1[i], -1);
+        memcpy(F1.mDescriptors.ptr(i), desc1 + 32 * (size_t)i, 32);
+        prev[i] = cv::Point2f(prev_matched[2 * i], prev_matched[2 * i + 1]);
+    }
+    ORBmatcher m(nnratio, check_ori != 0);
+    std::vector<int> out;
+    const int n = m.SearchForInitialization(F1, F2, prev, out, window_size);
+    for (int i = 0; i < n1; i++) {
+        m12[i] = out[i];
+        prev_matched[2 * i] = prev[i].x;
+        prev_matched[2 * i + 1] = prev[i].y;
+    }
+    return n;
+}
+
 }  // extern "C"

@@ -116,3 +116,61 @@ def test_reference_descriptor_distance_and_three_maxima_equal_oracle():
                                                              np.array([100, 9, 10, 11] + [0] * 26)]
     for h in cases:
         assert ref_py.ref_three_maxima(h) == tuple(orc.three_maxima(h))
+
+
+# ---- the tracker's window searches through the reference's own code (Frame::GetFeaturesInArea is a stand-in restated from
+# src/Frame.cc:445-498: that translation unit cannot be compiled here)
+def _grid(fa, blocked):
+    import proj_util as pu
+    return orc.Grid(fa["desc"], fa["x"], fa["y"], fa["octave"], pu.SCALE, fa["bounds"], angle=fa["angle"], uright=fa["uright"], blocked=blocked)
+
+
+@matcher
+@pytest.mark.parametrize("n,npts,seed,cluster,stereo,th", [
+    (2000, 3000, 10, False, True, 1.0), (2000, 3000, 11, True, True, 3.0), (1500, 800, 12, False, False, 5.0),
+    (300, 4000, 13, True, True, 3.0), (1, 5, 14, False, True, 1.0), (50, 0, 15, False, True, 1.0), (8000, 9000, 16, False, True, 3.0)])
+def test_reference_search_by_projection_map_points_equals_oracle(n, npts, seed, cluster, stereo, th):
+    import proj_util as pu
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n, rng, stereo=stereo, cluster=cluster)
+    og = _grid(fa, (rng.random(n) < 0.15).astype(np.uint8))
+    mp = pu.map_points_for(fa, npts, rng)
+    wn, want = orc.search_projection_map(og, th=th, nnratio=0.8, **mp)
+    rn, got = ref_py.ref_search_projection_map(og, th=th, nnratio=0.8, **mp)
+    assert rn == wn and np.array_equal(got, want)
+
+
+@matcher
+@pytest.mark.parametrize("n,nlast,seed,mono,tz,ori,cluster", [
+    (2000, 2000, 30, True, 0.0, True, False), (2000, 2000, 31, False, 0.5, True, False), (2000, 2000, 32, False, -0.5, True, True),
+    (1200, 3000, 33, False, 0.0, False, True), (2000, 0, 34, True, 0.0, True, False), (3, 10, 35, False, 0.0, True, False),
+    (8000, 8000, 36, False, 0.0, True, False)])
+def test_reference_search_by_projection_last_frame_equals_oracle(n, nlast, seed, mono, tz, ori, cluster):
+    import proj_util as pu
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n, rng, stereo=not mono, cluster=cluster)
+    og = _grid(fa, (rng.random(n) < 0.1).astype(np.uint8))
+    lf = pu.last_frame_for(fa, nlast, rng, tz=tz)
+    mbf, mb, th = 40.0, 40.0 / lf["fx"], 15.0 if mono else 7.0
+    args = (lf["Tcw"], lf["Tlw"], lf["fx"], lf["fy"], lf["cx"], lf["cy"], mbf, mb, lf["has_point"], lf["world"], lf["octave"], lf["angle"],
+            lf["desc"], lf["claims"], th, mono)
+    wn, want = orc.search_projection_frame(og, *args, ori)
+    rn, got = ref_py.ref_search_projection_frame(og, *args, ori)
+    # the reference sets culled entries back to NULL; the oracle marks them -2
+    assert rn == wn and np.array_equal(got, np.where(want == -2, -1, want))
+
+
+@matcher
+@pytest.mark.parametrize("n2,n1,seed,window,ori", [(2000, 2000, 40, 100, True), (2000, 2000, 41, 10, True), (1000, 3000, 42, 50, False),
+                                                   (2000, 0, 43, 100, True), (2, 9, 44, 100, True), (6000, 6000, 45, 100, True)])
+def test_reference_search_for_initialization_equals_oracle(n2, n1, seed, window, ori):
+    import proj_util as pu
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n2, rng, stereo=False)
+    fa["octave"][rng.random(n2) < 0.5] = 0
+    og = _grid(fa, None)
+    f1 = pu.init_frame1_for(fa, n1, rng)
+    prev_o, prev_r = f1["prev"].copy(), f1["prev"].copy()
+    wn, want = orc.search_initialization(og, f1["desc1"], f1["octave1"], f1["angle1"], prev_o, window, 0.9, ori)
+    rn, got = ref_py.ref_search_initialization(og, f1["desc1"], f1["octave1"], f1["angle1"], prev_r, window, 0.9, ori)
+    assert rn == wn and np.array_equal(got, want) and np.array_equal(prev_r, prev_o)
