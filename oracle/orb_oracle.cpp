@@ -18,8 +18,8 @@
 // output bit for bit on all golden configurations (tests/test_reference_ref.py).  Matcher: oracle/_ref/libref_orbmatcher.so is the
 // reference's own src/ORBmatcher.cc compiled unmodified over plain-data stand-ins for KeyFrame / Frame / MapPoint; its
 // DescriptorDistance, SearchByBoW x2, SearchForTriangulation, ComputeThreeMaxima, SearchByProjection(Frame, MapPoints),
-// SearchByProjection(Frame, LastFrame) and SearchForInitialization equal this oracle on every scene of the GPU parity tests.  The
-// relocalisation / loop-closing projections, Fuse x2, SearchBySim3 and ComputeStereoMatches restatements remain "parity unpinned" by
+// SearchByProjection(Frame, LastFrame), SearchForInitialization and the relocalisation / loop-closing projections equal this oracle on
+// the scenes of the GPU parity tests.  The Fuse x2, SearchBySim3 and ComputeStereoMatches restatements remain "parity unpinned" by
 // the reference itself (the reference ships no tests or golden vectors).  Also pinned: every OpenCV primitive below bit-for-bit
 // against cv2 4.13.0 golden vectors (tests/golden/*.npz, made by tests/golden/make_golden*.py), and the full extractor against an
 // independent Python chain of the real cv2 primitives (same script).

@@ -221,3 +221,32 @@ def ref_search_initialization(grid2, desc1, octave1, angle1, prev_matched, windo
     n = _wlib().refm_search_initialization(C.addressof(g), len(d), d.ctypes.data, oc.ctypes.data, an.ctypes.data, prev_matched.ctypes.data,
                                            int(window_size), float(nnratio), int(check_ori), m.ctypes.data)
     return n, m[:len(d)]
+
+
+def ref_search_projection_kf(grid, Tcw, fx, fy, cx, cy, log_sf, state, world, mf_max, mf_min, angle, desc, th, orb_dist, check_ori):
+    """state: 0 none / 1 good / 2 bad / 3 already found (uint8), per keyframe feature."""
+    L = mlib()
+    L.refm_search_projection_kf.restype = C.c_int
+    L.refm_search_projection_kf.argtypes = [C.c_void_p, C.c_void_p] + [C.c_float] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_int, C.c_int, C.c_void_p]
+    g = grid.c()
+    st, d = _a(state, np.uint8), _a(desc, np.uint8).reshape(-1, 32)
+    w, mx, mn, an = _a(world, np.float32).reshape(-1, 3), _a(mf_max, np.float32), _a(mf_min, np.float32), _a(angle, np.float32)
+    T = _a(Tcw, np.float32).reshape(-1)[:12].copy()
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    n = L.refm_search_projection_kf(C.addressof(g), T.ctypes.data, fx, fy, cx, cy, log_sf, len(st), st.ctypes.data, w.ctypes.data, mx.ctypes.data,
+                                    mn.ctypes.data, an.ctypes.data, d.ctypes.data, float(th), int(orb_dist), int(check_ori), owner.ctypes.data)
+    return n, owner[:grid.n]
+
+
+def ref_search_projection_sim3(grid, Scw, fx, fy, cx, cy, log_sf, state, world, mf_max, mf_min, normal, desc, th):
+    L = mlib()
+    L.refm_search_projection_sim3.restype = C.c_int
+    L.refm_search_projection_sim3.argtypes = [C.c_void_p, C.c_void_p] + [C.c_float] * 5 + [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    g = grid.c()
+    st, d = _a(state, np.uint8), _a(desc, np.uint8).reshape(-1, 32)
+    w, nr, mx, mn = _a(world, np.float32).reshape(-1, 3), _a(normal, np.float32).reshape(-1, 3), _a(mf_max, np.float32), _a(mf_min, np.float32)
+    S = _a(Scw, np.float32).reshape(-1)[:12].copy()
+    owner = np.zeros(max(grid.n, 1), np.int32)
+    n = L.refm_search_projection_sim3(C.addressof(g), S.ctypes.data, fx, fy, cx, cy, log_sf, len(st), st.ctypes.data, w.ctypes.data, mx.ctypes.data,
+                                      mn.ctypes.data, nr.ctypes.data, d.ctypes.data, int(th), owner.ctypes.data)
+    return n, owner[:grid.n]

@@ -332,4 +332,103 @@ int refm_search_initialization(const refm_grid* g2, int n1, const unsigned char*
     return n;
 }
 
+static void fill_points(std::vector<MapPoint>& pool, int npts, const unsigned char* state, const float* world, const float* normal,
+                        const float* mf_max, const float* mf_min, const unsigned char* desc) {
+    pool.resize(npts);
+    for (int i = 0; i < npts; i++) {
+        MapPoint& p = pool[i];
+        p.mbBad = state[i] == 2;
+        p.nObs = 1;
+        p.mfMaxDistance = mf_max[i];
+        p.mfMinDistance = mf_min[i];
+        p.mWorldPos.create(3, 1, CV_32F);
+        p.mNormalVector.create(3, 1, CV_32F);
+        for (int c = 0; c < 3; c++) {
+            p.mWorldPos.at<float>(c) = world[3 * (size_t)i + c];
+            p.mNormalVector.at<float>(c) = normal ? normal[3 * (size_t)i + c] : 0.f;
+        }
+        p.mDescriptor.create(1, 32, CV_8U);
+        memcpy(p.mDescriptor.ptr(), desc + 32 * (size_t)i, 32);
+    }
+}
+
+// SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)  (:1465-1602, relocalisation)
+// state[i]: 0 = the keyframe feature holds no MapPoint, 1 = good, 2 = bad, 3 = already found
+int refm_search_projection_kf(const refm_grid* g, const float* Tcw, float fx, float fy, float cx, float cy, float log_sf, int npts,
+                              const unsigned char* state, const float* world, const float* mf_max, const float* mf_min, const float* angle,
+                              const unsigned char* desc, float th, int orb_dist, int check_ori, int* owner) {
+    Frame C;
+    std::vector<MapPoint> holders, pool;
+    fill_frame(C, *g, holders);
+    C.mTcw.create(4, 4, CV_32F);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) C.mTcw.at<float>(r, c) = Tcw[4 * r + c];
+    C.mTcw.at<float>(3, 0) = C.mTcw.at<float>(3, 1) = C.mTcw.at<float>(3, 2) = 0.f;
+    C.mTcw.at<float>(3, 3) = 1.f;
+    C.fx = fx; C.fy = fy; C.cx = cx; C.cy = cy; C.mfLogScaleFactor = log_sf;
+    fill_points(pool, npts, state, world, nullptr, mf_max, mf_min, desc);
+    KeyFrame K;
+    K.N = npts;
+    K.mvKeysUn.resize(npts);
+    K.mvpMapPoints.assign(npts, static_cast<MapPoint*>(NULL));
+    std::set<MapPoint*> found;
+    for (int i = 0; i < npts; i++) {
+        K.mvKeysUn[i] = cv::KeyPoint(0.f, 0.f, 31.f, angle[i], 0.f, 0, -1);
+        if (state[i] != 0) K.mvpMapPoints[i] = &pool[i];
+        if (state[i] == 3) found.insert(&pool[i]);
+    }
+    ORBmatcher m(0.9f, check_ori != 0);
+    const int n = m.SearchByProjection(C, &K, found, th, orb_dist);
+    owners_out(C, pool, owner);
+    return n;
+}
+
+// SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th)  (:293-406, loop
+// closing); points whose state is not 1 are handed over as bad (skipped either way)
+int refm_search_projection_sim3(const refm_grid* g, const float* Scw, float fx, float fy, float cx, float cy, float log_sf, int npts,
+                                const unsigned char* state, const float* world, const float* mf_max, const float* mf_min, const float* normal,
+                                const unsigned char* desc, int th, int* owner) {
+    KeyFrame K;
+    std::vector<MapPoint> holders(g->n), pool;
+    K.N = g->n;
+    K.fx = fx; K.fy = fy; K.cx = cx; K.cy = cy; K.mfLogScaleFactor = log_sf;
+    K.mvKeysUn.resize(g->n);
+    K.mDescriptors.create(g->n > 0 ? g->n : 1, 32, CV_8U);
+    K.mDescriptors.rows = g->n;
+    std::vector<MapPoint*> matched(g->n, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < g->n; i++) {
+        memcpy(K.mDescriptors.ptr(i), g->desc + 32 * (size_t)i, 32);
+        K.mvKeysUn[i] = cv::KeyPoint(g->x[i], g->y[i], 31.f, g->angle ? g->angle[i] : 0.f, 0.f, g->octave[i], -1);
+        if (g->blocked && g->blocked[i]) matched[i] = &holders[i];
+    }
+    K.mvScaleFactors.assign(g->scale_factors, g->scale_factors + g->n_levels);
+    K.mnMinX = (int)g->min_x; K.mnMinY = (int)g->min_y; K.mnMaxX = (int)g->max_x; K.mnMaxY = (int)g->max_y;
+    K.mnGridCols = g->grid_cols; K.mnGridRows = g->grid_rows;
+    K.mfGridElementWidthInv = g->inv_w; K.mfGridElementHeightInv = g->inv_h;
+    K.mGrid.assign(g->grid_cols, std::vector<std::vector<size_t> >(g->grid_rows));
+    for (int ix = 0; ix < g->grid_cols; ix++)
+        for (int iy = 0; iy < g->grid_rows; iy++) {
+            const int c = ix * g->grid_rows + iy;
+            for (int e = g->cell_offsets[c]; e < g->cell_offsets[c + 1]; e++) K.mGrid[ix][iy].push_back((size_t)g->cell_features[e]);
+        }
+    fill_points(pool, npts, state, world, normal, mf_max, mf_min, desc);
+    std::vector<MapPoint*> pts(npts);
+    for (int i = 0; i < npts; i++) {
+        if (state[i] != 1) pool[i].mbBad = true;
+        pts[i] = &pool[i];
+    }
+    cv::Mat S(4, 4, CV_32F);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) S.at<float>(r, c) = Scw[4 * r + c];
+    S.at<float>(3, 0) = S.at<float>(3, 1) = S.at<float>(3, 2) = 0.f;
+    S.at<float>(3, 3) = 1.f;
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchByProjection(&K, S, pts, matched, th);
+    for (int i = 0; i < g->n; i++) {
+        const MapPoint* p = matched[i];
+        owner[i] = (p && !pool.empty() && p >= pool.data() && p < pool.data() + pool.size()) ? (int)(p - pool.data()) : -1;
+    }
+    return n;
+}
+
 }  // extern "C"

@@ -174,3 +174,55 @@ def test_reference_search_for_initialization_equals_oracle(n2, n1, seed, window,
     wn, want = orc.search_initialization(og, f1["desc1"], f1["octave1"], f1["angle1"], prev_o, window, 0.9, ori)
     rn, got = ref_py.ref_search_initialization(og, f1["desc1"], f1["octave1"], f1["angle1"], prev_r, window, 0.9, ori)
     assert rn == wn and np.array_equal(got, want) and np.array_equal(prev_r, prev_o)
+
+
+def _drop_predict_scale_ub(kp, Tn):
+    """This fork's MapPoint::PredictScale is unclamped and its result indexes mvScaleFactors (src/MapPoint.cc:633-642): out-of-range
+    levels are undefined behaviour in the reference and clamped in the oracle / product.  Points that would get there are taken out
+    of the scene for both sides (margin 1e-3 of a level)."""
+    R, t = Tn[:, :3].astype(np.float64), Tn[:, 3].astype(np.float64)
+    dist = np.linalg.norm(kp["world"].astype(np.float64) - (-R.T @ t), axis=1)
+    lv = np.log(kp["mf_max"].astype(np.float64) / dist) / np.log(1.2)
+    st = kp["state"].copy()
+    st[~((lv > -0.999) & (lv < 6.999))] = 0
+    return st
+
+
+LOG_SF = np.float32(np.log(np.float32(1.2)))
+
+
+@matcher
+@pytest.mark.parametrize("n,npts,seed,ori,orbdist,cluster", [(2000, 2500, 70, True, 100, False), (2000, 2500, 71, False, 64, True),
+                                                            (500, 3000, 72, True, 100, True), (4000, 4000, 73, True, 64, False)])
+def test_reference_relocalisation_projection_equals_oracle(n, npts, seed, ori, orbdist, cluster):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1465-1602."""
+    import proj_util as pu
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n, rng, stereo=False, cluster=cluster)
+    og = _grid(fa, (rng.random(n) < 0.2).astype(np.uint8))
+    kp = pu.kf_points_for(fa, npts, rng)
+    st = _drop_predict_scale_ub(kp, kp["T"])
+    a = (kp["T"], kp["fx"], kp["fy"], kp["cx"], kp["cy"], LOG_SF)
+    b = (kp["world"], kp["mf_max"], kp["mf_min"], kp["angle"], kp["desc"], 10.0, orbdist, ori)
+    on, oo = orc.search_projection_kf(og, *a, st == 1, *b)
+    rn, ro = ref_py.ref_search_projection_kf(og, *a, st, *b)
+    assert rn == on and on > 100 and np.array_equal(ro, np.where(oo == -2, -1, oo))
+
+
+@matcher
+@pytest.mark.parametrize("n,npts,seed,scale", [(2000, 2500, 80, 1.0), (2000, 2500, 81, 2.5), (600, 3000, 82, 0.4), (4000, 4000, 83, 1.7)])
+def test_reference_loop_closing_projection_equals_oracle(n, npts, seed, scale):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:293-406, with a similarity of scale `scale`."""
+    import proj_util as pu
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n, rng, stereo=False)
+    fa["x"] = np.clip(fa["x"], 0, 639.5).astype(np.float32)
+    og = _grid(fa, (rng.random(n) < 0.3).astype(np.uint8))
+    kq = pu.kf_points_for(fa, npts, rng, sim_scale=scale)
+    S = kq["S"].astype(np.float64)
+    st = _drop_predict_scale_ub(kq, S / np.sqrt((S[0, :3] ** 2).sum()))
+    a = (kq["S"], kq["fx"], kq["fy"], kq["cx"], kq["cy"], LOG_SF)
+    b = (kq["world"], kq["mf_max"], kq["mf_min"], kq["normal"], kq["desc"], 10)
+    on, oo = orc.search_projection_sim3(og, *a, st == 1, *b)
+    rn, ro = ref_py.ref_search_projection_sim3(og, *a, st, *b)
+    assert rn == on and on > 100 and np.array_equal(ro, oo)
