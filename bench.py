@@ -234,6 +234,12 @@ def main():
     ap.add_argument("--no-match", action="store_true", help="skip the matching sub-benchmark")
     ap.add_argument("--match-q", type=int, default=32, help="query keyframes per GPU in the matching sub-benchmark")
     ap.add_argument("--match-db", type=int, default=512, help="database keyframes in the matching sub-benchmark")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C5 blocks (`configs` key; N=1 only)")
+    ap.add_argument("--only-config", default=None, choices=["C1", "C3", "C5"],
+                    help="measure just this BASELINE configuration and print its block (profiling aid: ncu runs, A/B)")
+    ap.add_argument("--c3-frames", type=int, default=256)
+    ap.add_argument("--c5-frames", type=int, default=32)
+    ap.add_argument("--c5-batch", type=int, default=16, help="4K frames per device pass")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,6 +249,15 @@ def main():
         return
 
     # synthetic frames first (fork pool) — before CUDA is touched
+    import bench_configs as bc
+    want_cfg = (world == 1 and not args.no_configs) or args.only_config
+    c3_frames = c5_frames = None
+    if want_cfg and args.only_config in (None, "C3"):
+        c3_frames = bc.moving_window_frames(1280, 720, args.c3_frames, 16, 100000)
+    if want_cfg and args.only_config in (None, "C5"):
+        c5_frames = bc.make_frames(3840, 2160, args.c5_frames, 8, 200000)
+    if args.only_config:
+        args.frames = 64
     frames = make_frames(args.frames, rank * args.frames, args.unique)
 
     import torch
@@ -265,6 +280,37 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def measure_configs(stream, popc):
+        """BASELINE configs C1 / C3 / C5 (bench_configs.py), N=1."""
+        peaks_ = {}
+        try:
+            peaks_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm = float(peaks_.get("hbm_gbs", 6650.0))
+        out = {"hbm_peak_source": "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks_ else "fallback (B200_PROFILING.md)"}
+        if args.only_config in (None, "C1"):
+            ref_ms = None if args.no_cpu else bc.reference_ms_per_frame(frames[0])
+            out["C1"] = bc.c1_latency(torch, orb, capi, local_rank, frames[0], ref_ms=ref_ms)
+        if c3_frames is not None:
+            blk, ctx = bc.batch_config("C3", torch, orb, capi, local_rank, hbm, c3_frames, len(c3_frames), 128, min(args.steps, 5), stream)
+            blk["matching"] = bc.consecutive_keyframe_matching(torch, capi, ctx, min(args.steps, 5), stream, popc)
+            out["C3"] = blk
+            del ctx
+        if c5_frames is not None:
+            blk, ctx = bc.batch_config("C5", torch, orb, capi, local_rank, hbm, c5_frames, 8, args.c5_batch, min(args.steps, 5), stream)
+            out["C5"] = blk
+            del ctx
+        torch.cuda.empty_cache()
+        return out
+
+    if args.only_config:
+        tstream = torch.cuda.Stream(device=local_rank)
+        torch.cuda.set_stream(tstream)
+        popc, _ = orb.popc_peak(local_rank)
+        _emit(measure_configs(tstream.cuda_stream, popc))
+        return
 
     nF = args.frames
     numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None     # pinned staging memory local to this GPU's root port
@@ -537,6 +583,12 @@ def main():
             t_cpu, _ = lat(lambda: orc.stereo_matches(lv[0], lv[1], tb["scale"], tb["inv_scale"], okL, odL, okR, odR, 40.0, 0.08), 5)
             tracking["compute_stereo_matches"]["cpu_port_ms_per_call"] = 1e3 * t_cpu
 
+    # ---- the other BASELINE configurations (C1 latency, C3 extract + consecutive-keyframe matching, C5 4K stress), N=1 only
+    configs = None
+    if rank == 0 and want_cfg:
+        popc_c, _ = orb.popc_peak(local_rank)
+        configs = measure_configs(stream, popc_c)
+
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -556,7 +608,7 @@ def main():
                        "keypoints_per_frame": kp_per_frame, "l2": "inputs_exceed_l2 (1.26 GB of frames per step per GPU)",
                        "parallelism": f"frame-sharded x{world}, no data-path collective", "numa_node_rank0": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "matching": matching, "bow": bow, "tracking": tracking,
+            "matching": matching, "bow": bow, "tracking": tracking, "configs": configs,
         })
     if world > 1:
         dist.destroy_process_group()

@@ -39,7 +39,8 @@ extern "C" int orb_device_count(void) {
 #define ORBX_MINB 16          // minBorder = EDGE_THRESHOLD-3 (ORBextractor.cc:772)
 #define ORBX_FAST_THREADS 128
 #define ORBX_FAST_LOCAL_CAP 1024
-#define ORBX_OCT_THREADS 512
+#define ORBX_OCT_THREADS 1024
+#define OCT_U 4
 
 struct LevelPlan {
     int w, h, pitch, brows;
@@ -57,7 +58,7 @@ struct Plan {
     int nlevels, iniTh, minTh;
     int totalCells, candTotal, selTotal, maxNodes, sortN;
     int tilePitch, tileRows, scorePitch, scoreRows;   // FAST shared-memory tile geometry (max over levels)
-    int fwBoxW, fwBoxH, fwTileBytes, fwScoreOff, fwPlistOff, fwBarOff, fwStride;   // k_fast_tma per-warp shared-memory layout
+    int fwBoxW, fwBoxH, fwTileBytes, fwScoreOff, fwPlistOff, fwGlistOff, fwBarOff, fwStride;   // k_fast_tma per-warp shared-memory layout
     int width, height;
     unsigned long long frameBytes;
     int umax[16];
@@ -445,9 +446,24 @@ __device__ __forceinline__ void tma_load_3d(u32 dst, const CUtensorMap* map, int
                  ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
 }
 
-// PAIR4 (experimental, off by default, ORBX_FAST_PAIR4=1; NOT yet validated on a GPU — DESIGN.md §9): the quick test also looks at
-// the fourth opposite ring pair (4,12), evaluated only in warp-iterations in which some lane passed the three-pair test.
-template <int BOXW, int SPP, bool PAIR4 = false>
+// explicit shared-space accesses from a 32-bit shared address (generic pointers make the compiler rebuild the shared::cluster window
+// base inside the loop); OFF is an immediate
+template <int OFF> __device__ __forceinline__ u32 lds32i(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ void sts32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(u32 addr, u32 v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory"); }
+
+// Phase A (the quick test) works on FOUR horizontally adjacent pixels per lane, one byte each: the tile is read as aligned 32-bit
+// words, |v - ring| of the four pixels is ONE VABSDIFF4, and "differs by more than t" is the carry into bit 7 of
+// ((d & 0x7f) + (127 - t)) | d  (exact for t <= 127; larger thresholds are tested at 127, which is still a necessary condition).
+// A FAST-9 corner needs, for each of the 4 opposite ring pairs (0,8) (2,10) (4,12) (6,14), at least one member that differs from the
+// centre by more than t (any 9 contiguous ring pixels contain one member of every opposite pair).  On the synthetic frames this
+// sign-agnostic 4-pair test passes 13.4 % of the pixels at t = 20 (the signed 3-pair u16x2 test it replaces passed 20.1 % at twice
+// the instructions per pixel; FAST-9 corners are 5.6 %): tools/fast_filter_rates.py.
+template <int BOXW, int SPP>
 __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_constant__ Plan P, const CUtensorMap* __restrict__ maps,
                                                                   const uint4* __restrict__ cells, int nCells, int nf,
                                                                   uint2* __restrict__ cand, int* __restrict__ candCount,
@@ -505,61 +521,88 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
 
         // Like the reference (ORBextractor.cc:807-815) the cell is first searched at iniThFAST and only if that leaves no keypoint
         // at minThFAST.  NMS among corners >= ini is unaffected by weaker neighbours (they can never block a stronger pixel), so the
-        // ini pass is exact on its own, and it lets the cheap phase-A test reject ~80 % of the pixels instead of ~70 %.
-        const int X0 = ((iniX + ORBX_OX) & 15) + 3;                  // domain pixel 0 sits at tile (X0, 3); pairs are aligned to even tile x
-        const int off = X0 & 1, npr = (off + dw + 1) >> 1, ntask = npr * dh;
-        const u32 inv = 0xFFFFFFFFu / (u32)npr + 1;
+        // ini pass is exact on its own, and it lets the cheap phase-A test reject ~87 % of the pixels instead of ~77 %.
+        const int X0 = ((iniX + ORBX_OX) & 15) + 3;                  // domain pixel 0 sits at tile (X0, 3)
+        // 4-pixel groups aligned to tile words: group g of a row covers tile x [g0 + 4g, g0 + 4g + 4), i.e. domain px [4g - offq, ...)
+        const int g0 = X0 & ~3, offq = X0 - g0, ng = (offq + dw + 3) >> 2, ntask = ng * dh;
+        const u32 tileS = smem_u32(wbase), plS = smem_u32(plist), glS = smem_u32(wbase + P.fwGlistOff);
+        const u32 inv = 0xFFFFFFFFu / (u32)ng + 1;
         int nKeep = 0, T = P.iniTh;
         for (int pass = 0; pass < 2; pass++) {
             const int t = pass ? P.minTh : P.iniTh;
             T = t;
             // ---- phase A
-            int nl = 0;
+            int nl = 0, ngl = 0;
             {
-                const int hiT = 256 + t, loT = 256 - t;
-                const u8* cE = tile + 3 * BW + (X0 & ~1);
-                const u32 C1 = (u32)(0x8000 - (hiT + 1)) * 0x00010001u, C2 = (u32)(0x8000 + loT - 1) * 0x00010001u;
+                // no `& 0x7f` before the add: a byte with d >= 129 + t carries into its left neighbour, whose test then reads
+                // d >= t instead of d > t — weaker, hence still a necessary condition (its own bit 7 comes from `| d`)
+                const u32 Kt = (u32)(127 - min(t, 127)) * 0x01010101u;
+                const u32 cE = tileS + 3 * BW + g0;
                 for (int task0 = 0; task0 < ntask; task0 += 32) {
                     const int task = task0 + lane;
-                    u32 fl = 0;                                        // bit 15 / bit 31: first / second pixel of the pair passes
+                    u32 fl = 0;                                        // bit 7 of byte i: pixel i of the group passes
                     int ent = 0;
-                    u32 vb4 = 0, md4 = 0, mb4 = 0;                     // (PAIR4 only)
-                    const u8* pe4 = tile;
                     if (task < ntask) {
-                        const int row = npr == 1 ? task : (int)__umulhi((u32)task, inv);   // (inv overflows for npr == 1)
-                        const int p = task - row * npr;
-                        const int px0 = 2 * p - off;
-                        ent = (row << 8) + px0;
-                        const u8* pe = cE + row * BW + 2 * p;
-#define LD2(o) __byte_perm((u32) * reinterpret_cast<const u16*>(pe + (o)), 0, 0x4140)
-                        const u32 vb = LD2(0) + 0x01000100u;
-                        const u32 d0 = vb - LD2(3 * BW), d8 = vb - LD2(-3 * BW);
-                        const u32 d2 = vb - LD2(2 * BW + 2), d10 = vb - LD2(-2 * BW - 2);
-                        const u32 d6 = vb - LD2(-2 * BW + 2), d14 = vb - LD2(2 * BW - 2);
-#undef LD2
-                        const u32 md = min3x2(__vmaxu2(d0, d8), __vmaxu2(d2, d10), __vmaxu2(d6, d14));    // dark arc possible iff > 256+t
-                        const u32 mb = max3x2(__vminu2(d0, d8), __vminu2(d2, d10), __vminu2(d6, d14));    // bright arc possible iff < 256-t
-                        // bit 15 of each half: md >= hiT+1  |  mb <= loT-1   (halves are 9-bit values: no carries between them)
-                        fl = ((md + C1) | (C2 - mb)) & 0x80008000u;
-                        if (px0 < 0) fl &= 0xFFFF0000u;               // first pixel left of the domain
-                        if (px0 + 1 >= dw) fl &= 0x0000FFFFu;         // second pixel right of the domain
-                        if (PAIR4) { vb4 = vb; md4 = md; mb4 = mb; pe4 = pe; }
+                        const int row = ng == 1 ? task : (int)__umulhi((u32)task, inv);   // (inv overflows for ng == 1)
+                        const int g = task - row * ng;
+                        const int lo = 4 * g - offq;                  // domain px of the group's first pixel (-3 .. dw-1)
+                        ent = (row << 8) + lo;
+                        const u32 pw = cE + (u32)(row * BW + 4 * g);
+                        u32 cl, cc, cr, ul, uc, ur, dl, dc, dr, r0, r8;
+                        if (BOXW > 0) {                               // compile-time pitch: one address register, immediate offsets
+                            cl = lds32i<-4>(pw); cc = lds32i<0>(pw); cr = lds32i<4>(pw);
+                            ul = lds32i<2 * BOXW - 4>(pw); uc = lds32i<2 * BOXW>(pw); ur = lds32i<2 * BOXW + 4>(pw);
+                            dl = lds32i<-2 * BOXW - 4>(pw); dc = lds32i<-2 * BOXW>(pw); dr = lds32i<-2 * BOXW + 4>(pw);
+                            r0 = lds32i<3 * BOXW>(pw); r8 = lds32i<-3 * BOXW>(pw);
+                        } else {
+                            const u32 pu = pw + 2 * BW, pd = pw - 2 * BW;
+                            cl = lds32i<-4>(pw); cc = lds32i<0>(pw); cr = lds32i<4>(pw);
+                            ul = lds32i<-4>(pu); uc = lds32i<0>(pu); ur = lds32i<4>(pu);
+                            dl = lds32i<-4>(pd); dc = lds32i<0>(pd); dr = lds32i<4>(pd);
+                            r0 = lds32i<0>(pw + 3 * BW); r8 = lds32i<0>(pw - 3 * BW);
+                        }
+                        const u32 r4 = __byte_perm(cc, cr, 0x6543), r12 = __byte_perm(cl, cc, 0x4321);
+                        const u32 r2 = __byte_perm(uc, ur, 0x5432), r14 = __byte_perm(ul, uc, 0x5432);
+                        const u32 r6 = __byte_perm(dc, dr, 0x5432), r10 = __byte_perm(dl, dc, 0x5432);
+#define FAR(r, dv) const u32 dv = __vabsdiffu4(cc, r), dv##x = dv + Kt
+                        FAR(r0, a0); FAR(r8, a8); FAR(r2, a2); FAR(r10, a10); FAR(r4, a4); FAR(r12, a12); FAR(r6, a6); FAR(r14, a14);
+#undef FAR
+                        // pair (k, k+8) has a far member: bit 7 of (x_k | d_k | x_k8 | d_k8); all four pairs: AND
+                        const u32 p0 = a0x | a0 | a8x, p1 = a2x | a2 | a10x, p2 = a4x | a4 | a12x, p3 = a6x | a6 | a14x;
+                        u32 m = 0x80808080u;                          // pixels of the group that lie inside the domain
+                        if (g == 0) m = 0x80808080u << (8 * offq);
+                        if (g == ng - 1) m &= 0x80808080u >> (8 * (4 * ng - offq - dw));
+                        fl = (p0 | a8) & (p1 | a10) & (p2 | a12) & (p3 | a14) & m;
                     }
-                    if (PAIR4 && __any_sync(0xffffffffu, fl != 0u) && task < ntask) {
-                        // ring pixels 4 and 12 are (x + 3, y) and (x - 3, y): odd byte offsets, so each u16x2 is cut from two aligned
-                        // 16-bit loads (bytes 1 of the first and 0 of the second: selector 0x3421)
-#define LDU(o) ((u32) * reinterpret_cast<const u16*>(pe4 + (o)))
-                        const u32 d4 = vb4 - __byte_perm(LDU(2), LDU(4), 0x3421), d12 = vb4 - __byte_perm(LDU(-4), LDU(-2), 0x3421);
-#undef LDU
-                        const u32 md2 = __vminu2(md4, __vmaxu2(d4, d12)), mb2 = __vmaxu2(mb4, __vminu2(d4, d12));
-                        fl &= ((md2 + C1) | (C2 - mb2)) & 0x80008000u;
+                    // compaction at GROUP level (one ballot per iteration): entry = row << 8 | (lo + 4) with the pass flags left in
+                    // bits 7 / 15 / 23 / 31 (lo + 4 <= 67 and row <= 63 keep those bits free); expanded to pixels below
+                    const u32 bg = __ballot_sync(0xffffffffu, fl != 0u);
+                    if (bg == 0u) continue;                            // warp-uniform: flat neighbourhoods leave nothing to compact
+                    if (fl) sts32(glS + 4 * (u32)(ngl + __popc(bg & lt)), (u32)(ent + 4) | fl);
+                    ngl += __popc(bg);
+                }
+                __syncwarp();
+                // ---- expand the passing groups into the pixel list (order is irrelevant: every entry carries its coordinates)
+                for (int e0 = 0; e0 < ngl; e0 += 32) {
+                    const int e = e0 + lane;
+                    const u32 ge = e < ngl ? lds32i<0>(glS + 4 * (u32)e) : 0u;
+                    const u32 fb = ge & 0x80808080u;
+                    int pos = __popc(fb), tot;
+                    // exclusive prefix sum of the per-lane pixel counts: SHFL.UP delivers the in-range predicate with the value
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int v;
+                        asm volatile("{\n\t.reg .pred p;\n\tshfl.sync.up.b32 %0|p, %1, %2, 0, 0xffffffff;\n\t@p add.s32 %1, %1, %0;\n\t}"
+                                     : "=r"(v), "+r"(pos) : "r"(o));
                     }
-                    const u32 b0 = __ballot_sync(0xffffffffu, fl & 0x8000u), b1 = __ballot_sync(0xffffffffu, fl & 0x80000000u);
-                    if ((b0 | b1) == 0u) continue;                     // warp-uniform: flat neighbourhoods leave nothing to compact
-                    const int n0 = __popc(b0);
-                    if (fl & 0x8000u) plist[nl + __popc(b0 & lt)] = (u16)ent;
-                    if (fl & 0x80000000u) plist[nl + n0 + __popc(b1 & lt)] = (u16)(ent + 1);
-                    nl += n0 + __popc(b1);
+                    tot = __shfl_sync(0xffffffffu, pos, 31);
+                    pos = nl + pos - __popc(fb);
+                    const u32 px0 = (ge & 0x3F7Fu) - 4u;               // row << 8 | lo  (as the u16 the list holds)
+                    if (fb & 0x80u) { sts16(plS + 2 * (u32)pos, px0); pos++; }
+                    if (fb & 0x8000u) { sts16(plS + 2 * (u32)pos, px0 + 1); pos++; }
+                    if (fb & 0x800000u) { sts16(plS + 2 * (u32)pos, px0 + 2); pos++; }
+                    if ((int)fb < 0) sts16(plS + 2 * (u32)pos, px0 + 3);
+                    nl += tot;
                 }
             }
             __syncwarp();
@@ -754,12 +797,22 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
     const int bw = L.maxBX - ORBX_MINB, bh = L.maxBY - ORBX_MINB;
     for (int i = tid; i < nIni; i += T) S.cntB[i] = 0;
     __syncthreads();
-    for (int k = tid; k < n; k += T) {
-        const int xr = (int)(keys[k].x & 0xFFFF) - ORBX_MINB;
-        int r = (int)__fdiv_rn((float)xr, L.hX);
-        r = min(max(r, 0), nIni - 1);
-        nof[k] = (u32)r;
-        atomicAdd(&S.cntB[r], 1);
+    // Key loops: keys and node labels live in global memory (L2), so every loop issues the loads of OCT_U keys per thread before it
+    // touches any of them — one memory round trip per OCT_U keys instead of one (two, where the key was loaded after its label) per key.
+    for (int k0 = tid; k0 < n; k0 += OCT_U * T) {
+        u32 kx[OCT_U];
+#pragma unroll
+        for (int u = 0; u < OCT_U; u++) { const int k = k0 + u * T; kx[u] = k < n ? keys[k].x : 0u; }
+#pragma unroll
+        for (int u = 0; u < OCT_U; u++) {
+            const int k = k0 + u * T;
+            if (k >= n) break;
+            const int xr = (int)(kx[u] & 0xFFFF) - ORBX_MINB;
+            int r = (int)__fdiv_rn((float)xr, L.hX);
+            r = min(max(r, 0), nIni - 1);
+            nof[k] = (u32)r;
+            atomicAdd(&S.cntB[r], 1);
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -775,7 +828,13 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
     }
     __syncthreads();
     int size = s_cut;
-    for (int k = tid; k < n; k += T) nof[k] = (u32)s_rootMap[nof[k]];
+    for (int k0 = tid; k0 < n; k0 += OCT_U * T) {
+        u32 v[OCT_U];
+#pragma unroll
+        for (int u = 0; u < OCT_U; u++) { const int k = k0 + u * T; v[u] = k < n ? nof[k] : 0u; }
+#pragma unroll
+        for (int u = 0; u < OCT_U; u++) { const int k = k0 + u * T; if (k < n) nof[k] = (u32)s_rootMap[v[u]]; }
+    }
     __syncthreads();
     (void)bw;
 
@@ -788,16 +847,27 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
         for (int i = tid; i < 4 * size; i += T) S.cc[i] = 0;
         if (tid == 0) { s_nToExpand = 0; s_cut = 0x7fffffff; }
         __syncthreads();
-        for (int k = tid; k < n; k += T) {
-            const int nd = (int)(nof[k] & 0xFFFF);
-            if (cnt[nd] > 1) {
-                const uint2 key = keys[k];
-                const int x = (int)(key.x & 0xFFFF) - ORBX_MINB, y = (int)(key.x >> 16) - ORBX_MINB;
-                const int4 b = box[nd];
-                const int mx = b.x + ((b.y - b.x + 1) >> 1), my = b.z + ((b.w - b.z + 1) >> 1);
-                const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);
-                atomicAdd(&S.cc[nd * 4 + q], 1);
-                nof[k] = (u32)nd | ((u32)q << 16);
+        for (int k0 = tid; k0 < n; k0 += OCT_U * T) {
+            u32 v[OCT_U], kx[OCT_U];
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) {
+                const int k = k0 + u * T;
+                v[u] = k < n ? nof[k] : 0u;
+                kx[u] = k < n ? keys[k].x : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) {
+                const int k = k0 + u * T;
+                if (k >= n) break;
+                const int nd = (int)(v[u] & 0xFFFF);
+                if (cnt[nd] > 1) {
+                    const int x = (int)(kx[u] & 0xFFFF) - ORBX_MINB, y = (int)(kx[u] >> 16) - ORBX_MINB;
+                    const int4 b = box[nd];
+                    const int mx = b.x + ((b.y - b.x + 1) >> 1), my = b.z + ((b.w - b.z + 1) >> 1);
+                    const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+                    atomicAdd(&S.cc[nd * 4 + q], 1);
+                    nof[k] = (u32)nd | ((u32)q << 16);
+                }
             }
         }
         __syncthreads();
@@ -857,10 +927,16 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
             // recompute the child counts the scan scratch overwrote
             for (int i = tid; i < 4 * size; i += T) S.cc[i] = 0;
             __syncthreads();
-            for (int k = tid; k < n; k += T) {
-                const u32 v = nof[k];
-                const int nd = (int)(v & 0xFFFF);
-                if (cnt[nd] > 1) atomicAdd(&S.cc[nd * 4 + (int)((v >> 16) & 3)], 1);
+            for (int k0 = tid; k0 < n; k0 += OCT_U * T) {
+                u32 v[OCT_U];
+#pragma unroll
+                for (int u = 0; u < OCT_U; u++) { const int k = k0 + u * T; v[u] = k < n ? nof[k] : 0u; }
+#pragma unroll
+                for (int u = 0; u < OCT_U; u++) {
+                    if (k0 + u * T >= n) break;
+                    const int nd = (int)(v[u] & 0xFFFF);
+                    if (cnt[nd] > 1) atomicAdd(&S.cc[nd * 4 + (int)((v[u] >> 16) & 3)], 1);
+                }
             }
             __syncthreads();
         }
@@ -894,10 +970,17 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
             }
         }
         __syncthreads();
-        for (int k = tid; k < n; k += T) {
-            const u32 v = nof[k];
-            const int nd = (int)(v & 0xFFFF);
-            nof[k] = (u32)(S.div[nd] ? S.cc[nd * 4 + (int)((v >> 16) & 3)] : S.aux2[nd]);
+        for (int k0 = tid; k0 < n; k0 += OCT_U * T) {
+            u32 v[OCT_U];
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) { const int k = k0 + u * T; v[u] = k < n ? nof[k] : 0u; }
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) {
+                const int k = k0 + u * T;
+                if (k >= n) break;
+                const int nd = (int)(v[u] & 0xFFFF);
+                nof[k] = (u32)(S.div[nd] ? S.cc[nd * 4 + (int)((v[u] >> 16) & 3)] : S.aux2[nd]);
+            }
         }
         const int nToExpand = s_nToExpand;
         __syncthreads();
@@ -911,11 +994,23 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
     u64* best = (u64*)S.cc;
     for (int i = tid; i < size; i += T) best[i] = 0ull;
     __syncthreads();
-    for (int k = tid; k < n; k += T) {
-        const uint2 key = keys[k];
-        const u64 order = ((u64)(key.y & 0xFFFFFFu) << 32) | ((u64)(key.x >> 16) << 16) | (u64)(key.x & 0xFFFF);
-        const u64 v = ((u64)(key.y >> 24) << 56) | (0x00FFFFFFFFFFFFFFull - order);
-        atomicMax(&best[nof[k] & 0xFFFF], v);
+    for (int k0 = tid; k0 < n; k0 += OCT_U * T) {
+        u32 nd[OCT_U];
+        uint2 ky[OCT_U];
+#pragma unroll
+        for (int u = 0; u < OCT_U; u++) {
+            const int k = k0 + u * T;
+            nd[u] = k < n ? nof[k] : 0u;
+            ky[u] = k < n ? keys[k] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < OCT_U; u++) {
+            if (k0 + u * T >= n) break;
+            const uint2 key = ky[u];
+            const u64 order = ((u64)(key.y & 0xFFFFFFu) << 32) | ((u64)(key.x >> 16) << 16) | (u64)(key.x & 0xFFFF);
+            const u64 v = ((u64)(key.y >> 24) << 56) | (0x00FFFFFFFFFFFFFFull - order);
+            atomicMax(&best[nd[u] & 0xFFFF], v);
+        }
     }
     __syncthreads();
     for (int i = tid; i < size; i += T) {
@@ -1459,7 +1554,8 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         P.fwTileBytes = (int)orb_align_up((size_t)boxW * boxH, 128);
         P.fwScoreOff = P.fwTileBytes;                                 // one tile buffer: more warps per SM beat double buffering here
         P.fwPlistOff = P.fwScoreOff + (int)orb_align_up((size_t)P.scorePitch * P.scoreRows, 16);
-        P.fwBarOff = P.fwPlistOff + (int)orb_align_up((size_t)(maxCW + 2) * maxCH * 2, 16);
+        P.fwGlistOff = P.fwPlistOff + (int)orb_align_up((size_t)(maxCW + 2) * maxCH * 2, 16);      // <= (3 + maxCW + 3) / 4 groups per row
+        P.fwBarOff = P.fwGlistOff + (int)orb_align_up((size_t)((maxCW + 9) / 4) * maxCH * 4, 16);
         P.fwStride = (int)orb_align_up((size_t)P.fwBarOff + 16, 128);
         ex->fwSmem = (size_t)P.fwStride * ORBX_FW_WARPS;
         ex->useTma = false;
@@ -1512,7 +1608,6 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
             std::lock_guard<std::mutex> lk(amu2);
             if (ex->fwSmem > maxFw) {
                 ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, ORBX_FAST_SPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
-                ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, ORBX_FAST_SPP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
                 ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
                 maxFw = ex->fwSmem;
             }
@@ -1675,11 +1770,7 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         if (ex->nCells > 0 && ex->useTma) {
             const int items = ex->nCells * nf;
             const int grid = std::min(ex->fwGrid, orb_div_up(items, ORBX_FW_WARPS));
-            static const bool pair4 = [] { const char* e = getenv("ORBX_FAST_PAIR4"); return e && e[0] == '1'; }();
-            if (P.fwBoxW == 64 && ex->fastConst && pair4)
-                k_fast_tma<64, ORBX_FAST_SPP, true><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
-                                                                                                ex->d_candCount, ex->d_status, ex->d_workCounter);
-            else if (P.fwBoxW == 64 && ex->fastConst)
+            if (P.fwBoxW == 64 && ex->fastConst)
                 k_fast_tma<64, ORBX_FAST_SPP><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
                                                                                           ex->d_candCount, ex->d_status, ex->d_workCounter);
             else
@@ -1697,7 +1788,8 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         dim3 g(nl, nf);
         // a (level, frame) CTA at VGA size holds ~1400 candidates at most: in a batch pass (plenty of CTAs) 128 threads keep the many
         // barrier-separated passes short (0.37 vs 0.63 us/frame); large images and single-frame latency calls want the full 512
-        const int octT = (P.width * P.height <= 500000 && nf >= 16) ? 128 : ORBX_OCT_THREADS;
+        // (1024 threads for large images: a 4K level 0 holds ~100 k candidates and the key loops are pure memory latency)
+        const int octT = (P.width * P.height <= 500000 && nf >= 16) ? 128 : (P.width * P.height <= 500000 ? 512 : ORBX_OCT_THREADS);
         k_octree<<<g, octT, ex->octSmem, st>>>(P, ex->d_cand, ex->d_candCount, ex->d_nodeOf, ex->d_sel,
                                                            ex->d_selCount, ex->d_status);
         ex->launches++;
