@@ -250,3 +250,78 @@ def ref_search_projection_sim3(grid, Scw, fx, fy, cx, cy, log_sf, state, world, 
     n = L.refm_search_projection_sim3(C.addressof(g), S.ctypes.data, fx, fy, cx, cy, log_sf, len(st), st.ctypes.data, w.ctypes.data, mx.ctypes.data,
                                       mn.ctypes.data, nr.ctypes.data, d.ctypes.data, int(th), owner.ctypes.data)
     return n, owner[:grid.n]
+
+
+# ---- DBoW2: the reference's own Thirdparty/DBoW2 vocabulary (oracle/_ref/libref_dbow2.so) --------------------------------------
+VLIB = os.path.join(_HERE, "_ref", "libref_dbow2.so")
+
+
+def dbow2_available():
+    return os.path.exists(VLIB)
+
+
+_vlib = None
+
+
+def vlib():
+    global _vlib
+    if _vlib is None:
+        L = C.CDLL(VLIB)
+        vp, i32 = C.c_void_p, C.c_int
+        L.refv_load.restype = vp
+        L.refv_load.argtypes = [C.c_char_p, i32]
+        L.refv_destroy.argtypes = [vp]
+        L.refv_save_binary.argtypes = [vp, C.c_char_p]
+        L.refv_save_text.argtypes = [vp, C.c_char_p]
+        L.refv_info.argtypes = [vp] * 5
+        L.refv_transform_raw.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+        L.refv_transform.restype = i32
+        L.refv_transform.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+        _vlib = L
+    return _vlib
+
+
+class RefVocabulary:
+    """ORB_SLAM2::ORBVocabulary (TemplatedVocabulary<FORB::TDescriptor, FORB>) of the reference, loaded from one of its two on-disk
+    formats by its own loaders."""
+
+    def __init__(self, path, binary=False):
+        self._h = vlib().refv_load(str(path).encode(), int(binary))
+        if not self._h:
+            raise ValueError(f"the reference's loader rejected {path}")
+
+    def __del__(self):
+        try:
+            vlib().refv_destroy(self._h)
+        except Exception:
+            pass
+
+    def info(self):
+        v = [C.c_int() for _ in range(4)]
+        vlib().refv_info(self._h, *[C.byref(x) for x in v])
+        return dict(zip(("k", "L", "n_nodes", "n_words"), (x.value for x in v)))
+
+    def save_binary(self, path):
+        vlib().refv_save_binary(self._h, str(path).encode())
+
+    def save_text(self, path):
+        vlib().refv_save_text(self._h, str(path).encode())
+
+    def transform_raw(self, desc, levelsup):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        w, nid, wt = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.float64)
+        vlib().refv_transform_raw(self._h, d.ctypes.data, n, int(levelsup), w.ctypes.data, wt.ctypes.data, nid.ctypes.data)
+        return w, wt, nid
+
+    def transform(self, desc, levelsup):
+        """(BowVector word ids, values), (FeatureVector node ids, CSR offsets, feature indices)."""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        bid, bval = np.zeros(n + 1, np.int32), np.zeros(n + 1, np.float64)
+        fnode, foff, ffeat = np.zeros(n + 1, np.int32), np.zeros(n + 2, np.int32), np.zeros(n + 1, np.int32)
+        nn = C.c_int()
+        nb = vlib().refv_transform(self._h, d.ctypes.data, n, int(levelsup), bid.ctypes.data, bval.ctypes.data, fnode.ctypes.data,
+                                   foff.ctypes.data, ffeat.ctypes.data, C.byref(nn))
+        k = nn.value
+        return (bid[:nb], bval[:nb]), (fnode[:k], foff[:k + 1], ffeat[:foff[k]])

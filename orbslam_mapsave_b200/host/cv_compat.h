@@ -44,6 +44,7 @@ public:
         buf_ = std::shared_ptr<std::vector<unsigned char>>(new std::vector<unsigned char>((size_t)r * step));
         data = buf_->data();
     }
+    static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }   // create() value-initialises the storage
     void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     int type() const { return type_; }

@@ -46,3 +46,15 @@ def make_tree(k, L, seed, ragged=False, interleave=False):
     weight = np.where(is_leaf == 1, rng.uniform(0.0, 9.0, n), 0.0)
     weight[(is_leaf == 1) & (rng.random(n) < 0.05)] = 0.0       # stopped words
     return np.array(parent, np.int32), desc, weight, is_leaf
+
+
+def write_text(path, k, L, parent, desc, weight, is_leaf, scoring=0, weighting=0, trailing_newline=False):
+    """The layout TemplatedVocabulary::saveToTextFile writes (ORBvoc.txt, Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1443-1464).
+    By default WITHOUT the final newline: the reference's loader (`while(!f.eof()) getline`, :1393) turns the empty last line of a file
+    that ends in a newline into one more child of the root whose descriptor is whatever cv::Mat::create left in memory
+    (uninitialised) — undefined in the reference; the product skips blank lines."""
+    lines = [f"{k} {L} {scoring} {weighting}"]
+    for i in range(1, len(parent)):
+        lines.append(f"{parent[i]} {int(is_leaf[i])} " + " ".join(str(int(b)) for b in desc[i]) + f" {float(weight[i])!r}")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + ("\n" if trailing_newline else ""))
