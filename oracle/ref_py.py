@@ -325,3 +325,54 @@ class RefVocabulary:
                                    foff.ctypes.data, ffeat.ctypes.data, C.byref(nn))
         k = nn.value
         return (bid[:nb], bval[:nb]), (fnode[:k], foff[:k + 1], ffeat[:foff[k]])
+
+
+# ---- Fuse x2 / SearchBySim3 through the reference's own src/ORBmatcher.cc (object graph built from flat arrays) ------------------
+class _Points(C.Structure):
+    _fields_ = [("n", C.c_int), ("state", C.c_void_p), ("nobs", C.c_void_p), ("desc", C.c_void_p), ("world", C.c_void_p),
+                ("normal", C.c_void_p), ("mf_max", C.c_void_p), ("mf_min", C.c_void_p)]
+
+
+def _points(state, nobs, P):
+    keep = [_a(state, np.uint8), _a(nobs, np.int32), _a(P["desc"], np.uint8).reshape(-1, 32), _a(P["world"], np.float32).reshape(-1, 3),
+            _a(P["normal"], np.float32).reshape(-1, 3), _a(P["mf_max"], np.float32), _a(P["mf_min"], np.float32)]
+    return _Points(len(keep[0]), *[k.ctypes.data for k in keep]), keep
+
+
+def ref_fuse(variant, grid, K6, inv_sigma2, T, Ow, Scw, kf_state, kf_nobs, kfP, cand_state, cand_nobs, candP, in_at, th):
+    """ORBmatcher::Fuse (variant 0: src/ORBmatcher.cc:828-972; variant 1, with a similarity: :974-1103).  Returns
+    (nFused, keyframe feature -> point, (isBad, Observations) per point [keyframe's points, then the candidates], vpReplacePoint)."""
+    L = mlib()
+    L.refm_fuse.restype = C.c_int
+    L.refm_fuse.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.POINTER(_Points), C.POINTER(_Points), C.c_void_p, C.c_float] + [C.c_void_p] * 3
+    g = grid.c()
+    kp, k1 = _points(kf_state, kf_nobs, kfP)
+    cp, k2 = _points(cand_state, cand_nobs, candP)
+    K6, is2 = _a(K6, np.float32), _a(inv_sigma2, np.float32)
+    Tm = _a(T, np.float32).reshape(-1)[:12].copy()
+    Owm = _a(Ow if Ow is not None else np.zeros(3), np.float32)
+    Sm = _a(Scw if Scw is not None else np.eye(4), np.float32).reshape(-1).copy()
+    ia = _a(in_at, np.int32)
+    n, npts = grid.n, len(ia)
+    kf_ptr, pts, rep = np.zeros(max(n, 1), np.int32), np.zeros((n + npts, 2), np.int32), np.full(max(npts, 1), -1, np.int32)
+    nf = L.refm_fuse(int(variant), C.addressof(g), K6.ctypes.data, is2.ctypes.data, Tm.ctypes.data, Owm.ctypes.data, Sm.ctypes.data,
+                     C.byref(kp), C.byref(cp), ia.ctypes.data, float(th), kf_ptr.ctypes.data, pts.ctypes.data, rep.ctypes.data)
+    return nf, kf_ptr[:n], pts, rep[:npts]
+
+
+def ref_search_by_sim3(grid1, grid2, K6, T1, T2, st1, P1, st2, P2, s12, R12, t12, th, pre12):
+    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:1105-1329): (nFound, vpMatches12 as KF2 feature indices)."""
+    L = mlib()
+    L.refm_search_by_sim3.restype = C.c_int
+    L.refm_search_by_sim3.argtypes = [C.c_void_p] * 5 + [C.POINTER(_Points), C.POINTER(_Points), C.c_float, C.c_void_p, C.c_void_p, C.c_float,
+                                                          C.c_void_p, C.c_void_p]
+    g1, g2 = grid1.c(), grid2.c()
+    p1, k1 = _points(st1, np.ones(len(st1)), P1)
+    p2, k2 = _points(st2, np.ones(len(st2)), P2)
+    K6 = _a(K6, np.float32)
+    T1m, T2m = _a(T1, np.float32).reshape(-1)[:12].copy(), _a(T2, np.float32).reshape(-1)[:12].copy()
+    R, t, pre = _a(R12, np.float32).reshape(9).copy(), _a(t12, np.float32).reshape(3).copy(), _a(pre12, np.int32)
+    out = np.zeros(max(grid1.n, 1), np.int32)
+    n = L.refm_search_by_sim3(C.addressof(g1), C.addressof(g2), K6.ctypes.data, T1m.ctypes.data, T2m.ctypes.data, C.byref(p1), C.byref(p2),
+                              float(s12), R.ctypes.data, t.ctypes.data, float(th), pre.ctypes.data, out.ctypes.data)
+    return n, out[:grid1.n]

@@ -431,4 +431,126 @@ int refm_search_projection_sim3(const refm_grid* g, const float* Scw, float fx, 
     return n;
 }
 
+// ---- Fuse x2 and SearchBySim3 (src/ORBmatcher.cc:828-972, 974-1103, 1105-1329): the KeyFrame stand-in filled from the grid view, the
+// MapPoint object graph from flat arrays.  Point state: 0 = no point (NULL), 1 = good, 2 = bad, 3 = (candidates only) already observed by
+// the keyframe at feature in_at[i].  Results are reported as the graph the reference leaves behind.
+static void fill_keyframe(KeyFrame& K, const refm_grid& g, const float* K6, const float* inv_sigma2, const float* T /*3x4*/, const float* Ow) {
+    K.N = g.n;
+    K.fx = K6[0]; K.fy = K6[1]; K.cx = K6[2]; K.cy = K6[3]; K.mbf = K6[4]; K.mfLogScaleFactor = K6[5];
+    K.mvKeysUn.resize(g.n);
+    K.mvuRight.assign(g.n, -1.f);
+    K.mDescriptors.create(g.n > 0 ? g.n : 1, 32, CV_8U);
+    K.mDescriptors.rows = g.n;
+    K.mvpMapPoints.assign(g.n, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < g.n; i++) {
+        memcpy(K.mDescriptors.ptr(i), g.desc + 32 * (size_t)i, 32);
+        K.mvKeysUn[i] = cv::KeyPoint(g.x[i], g.y[i], 31.f, g.angle ? g.angle[i] : 0.f, 0.f, g.octave[i], -1);
+        if (g.uright) K.mvuRight[i] = g.uright[i];
+    }
+    K.mvKeys = K.mvKeysUn;
+    K.mnScaleLevels = g.n_levels;
+    K.mvScaleFactors.assign(g.scale_factors, g.scale_factors + g.n_levels);
+    if (inv_sigma2) K.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + g.n_levels);
+    K.mnMinX = (int)g.min_x; K.mnMinY = (int)g.min_y; K.mnMaxX = (int)g.max_x; K.mnMaxY = (int)g.max_y;
+    K.mnGridCols = g.grid_cols; K.mnGridRows = g.grid_rows;
+    K.mfGridElementWidthInv = g.inv_w; K.mfGridElementHeightInv = g.inv_h;
+    K.mGrid.assign(g.grid_cols, std::vector<std::vector<size_t> >(g.grid_rows));
+    for (int ix = 0; ix < g.grid_cols; ix++)
+        for (int iy = 0; iy < g.grid_rows; iy++) {
+            const int c = ix * g.grid_rows + iy;
+            for (int e = g.cell_offsets[c]; e < g.cell_offsets[c + 1]; e++) K.mGrid[ix][iy].push_back((size_t)g.cell_features[e]);
+        }
+    if (T) {
+        K.Rcw.create(3, 3, CV_32F);
+        K.tcw.create(3, 1, CV_32F);
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 3; c++) K.Rcw.at<float>(r, c) = T[4 * r + c];
+            K.tcw.at<float>(r) = T[4 * r + 3];
+        }
+    }
+    if (Ow) {
+        K.Ow.create(3, 1, CV_32F);
+        for (int r = 0; r < 3; r++) K.Ow.at<float>(r) = Ow[r];
+    }
+}
+
+struct refm_points {
+    int n;
+    const unsigned char* state;
+    const int* nobs;
+    const unsigned char* desc;
+    const float *world, *normal, *mf_max, *mf_min;
+};
+
+static void fill_pool(std::vector<MapPoint>& pool, const refm_points& p, long unsigned int id0) {
+    fill_points(pool, p.n, p.state, p.world, p.normal, p.mf_max, p.mf_min, p.desc);
+    for (int i = 0; i < p.n; i++) { pool[i].nObs = p.nobs ? p.nobs[i] : 1; pool[i].mnId = id0 + i; }
+}
+
+static int encode_point(const MapPoint* p, const std::vector<MapPoint>& kfp, const std::vector<MapPoint>& cand) {
+    if (!p) return -1;
+    if (!kfp.empty() && p >= kfp.data() && p < kfp.data() + kfp.size()) return (int)(p - kfp.data());
+    if (!cand.empty() && p >= cand.data() && p < cand.data() + cand.size()) return 100000 + (int)(p - cand.data());
+    return -2;
+}
+
+// variant 0: Fuse(pKF, vpMapPoints, th); variant 1: Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) with Scw 4x4 row-major.
+// kf_ptr_out[g->n]: which point every keyframe feature holds afterwards (index into the keyframe's pool, 100000 + candidate index, -1);
+// pts_out[(g->n + cand->n) x 2]: isBad, Observations of every point; replace_out[cand->n] (variant 1): vpReplacePoint.
+int refm_fuse(int variant, const refm_grid* g, const float* K6, const float* inv_sigma2, const float* T, const float* Ow, const float* Scw,
+              const refm_points* kfpts, const refm_points* cand, const int* in_at, float th, int* kf_ptr_out, int* pts_out, int* replace_out) {
+    KeyFrame K;
+    fill_keyframe(K, *g, K6, inv_sigma2, T, Ow);
+    std::vector<MapPoint> kfp, cp;
+    fill_pool(kfp, *kfpts, 0);
+    fill_pool(cp, *cand, 1000000);
+    for (int j = 0; j < g->n; j++)
+        if (kfpts->state[j]) { K.mvpMapPoints[j] = &kfp[j]; kfp[j].mObservations[&K] = (size_t)j; }
+    std::vector<MapPoint*> pts(cand->n, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < cand->n; i++) {
+        if (cand->state[i] == 0) continue;
+        pts[i] = &cp[i];
+        if (cand->state[i] == 3) { cp[i].mObservations[&K] = (size_t)in_at[i]; K.mvpMapPoints[in_at[i]] = &cp[i]; }
+    }
+    ORBmatcher m(0.8f, true);
+    int n;
+    if (variant == 0) n = m.Fuse(&K, pts, th);
+    else {
+        cv::Mat S(4, 4, CV_32F);
+        for (int i = 0; i < 16; i++) S.at<float>(i / 4, i % 4) = Scw[i];
+        std::vector<MapPoint*> rep(cand->n, static_cast<MapPoint*>(NULL));
+        n = m.Fuse(&K, S, pts, th, rep);
+        for (int i = 0; i < cand->n; i++) replace_out[i] = encode_point(rep[i], kfp, cp);
+    }
+    for (int j = 0; j < g->n; j++) kf_ptr_out[j] = encode_point(K.mvpMapPoints[j], kfp, cp);
+    for (int j = 0; j < g->n; j++) { pts_out[2 * j] = kfp[j].isBad(); pts_out[2 * j + 1] = kfp[j].Observations(); }
+    for (int i = 0; i < cand->n; i++) { pts_out[2 * (g->n + i)] = cp[i].isBad(); pts_out[2 * (g->n + i) + 1] = cp[i].Observations(); }
+    return n;
+}
+
+// SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  (:1105-1329).  pre12[n1]: index of the KF2 feature whose point vpMatches12[i]
+// holds on entry (-1 = NULL); matches12_out[n1]: the same view of vpMatches12 afterwards.
+int refm_search_by_sim3(const refm_grid* g1, const refm_grid* g2, const float* K6, const float* T1, const float* T2, const refm_points* p1,
+                        const refm_points* p2, float s12, const float* R12, const float* t12, float th, const int* pre12, int* matches12_out) {
+    KeyFrame A, B;
+    fill_keyframe(A, *g1, K6, nullptr, T1, nullptr);
+    fill_keyframe(B, *g2, K6, nullptr, T2, nullptr);
+    std::vector<MapPoint> a, b, none;
+    fill_pool(a, *p1, 0);
+    fill_pool(b, *p2, 1000000);
+    for (int i = 0; i < g1->n; i++) if (p1->state[i]) { A.mvpMapPoints[i] = &a[i]; a[i].mObservations[&A] = (size_t)i; }
+    for (int i = 0; i < g2->n; i++) if (p2->state[i]) { B.mvpMapPoints[i] = &b[i]; b[i].mObservations[&B] = (size_t)i; }
+    std::vector<MapPoint*> m12(g1->n, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < g1->n; i++) if (pre12[i] >= 0) m12[i] = &b[pre12[i]];
+    cv::Mat R(3, 3, CV_32F), t(3, 1, CV_32F);
+    for (int r = 0; r < 3; r++) { t.at<float>(r) = t12[r]; for (int c = 0; c < 3; c++) R.at<float>(r, c) = R12[3 * r + c]; }
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchBySim3(&A, &B, m12, s12, R, t, th);
+    for (int i = 0; i < g1->n; i++) {
+        const MapPoint* p = m12[i];
+        matches12_out[i] = (p && p >= b.data() && p < b.data() + b.size()) ? (int)(p - b.data()) : -1;
+    }
+    return n;
+}
+
 }  // extern "C"

@@ -287,3 +287,127 @@ def test_reference_dbow2_binary_format_round_trip(tmp_path):
     got = voc2.transform_raw(feats, 2)
     want = orc.voc_transform(parent, desc, weight.astype(np.float32).astype(np.float64), is_leaf, L, feats, 2)
     assert all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+# ---- Fuse x2 and SearchBySim3 through the reference's own code: the oracle's candidate searches (+ a replay of the reference's map
+# bookkeeping from the per-point result) against the object graph the reference itself leaves behind
+def _level_ok(dist, mf_max):
+    """Points whose PredictScale leaves [0, 8) index mvScaleFactors out of range in this fork (undefined; clamped in oracle / product)."""
+    lv = np.log(mf_max.astype(np.float64) / np.maximum(dist, 1e-12)) / np.log(1.2)
+    return (lv > -0.999) & (lv < 6.999)
+
+
+@matcher
+@pytest.mark.parametrize("variant,seed,n,npts,cluster", [(0, 300, 1200, 1500, False), (1, 301, 1200, 1500, True), (0, 302, 400, 3000, True),
+                                                         (1, 303, 3000, 800, False), (0, 304, 2000, 40, False)])
+def test_reference_fuse_equals_oracle_search_plus_bookkeeping(variant, seed, n, npts, cluster):
+    import proj_util as pu
+    from test_gpu_host_cpp import _Pt, _emulate_fuse
+    rng = np.random.default_rng(seed)
+    log_sf = float(np.log(np.float32(1.2)))
+    K = np.array([520.0, 520.0, 320.0, 240.0, 40.0, log_sf], np.float32)
+    is2 = (1.0 / (pu.SCALE * pu.SCALE)).astype(np.float32)
+    fa = pu.frame_arrays(n, rng, stereo=True, cluster=cluster)
+    fa["x"] = np.clip(fa["x"], 0, 639.5).astype(np.float32)
+    fa["y"] = np.clip(fa["y"], 0, 479.5).astype(np.float32)
+    R = pu.rot_small(rng, 3.0).astype(np.float32)
+    t = rng.uniform(-0.1, 0.1, 3).astype(np.float32)
+    T = np.concatenate([R, t[:, None]], 1).astype(np.float32)
+    Ow = (-(R.astype(np.float64).T @ t.astype(np.float64))).astype(np.float32)
+    scale = 1.0 if variant == 0 else 1.7
+    A, b = (T[:, :3] * np.float32(scale)).astype(np.float32), (T[:, 3] * np.float32(scale)).astype(np.float32)
+    S = np.concatenate([np.concatenate([A, b[:, None]], 1), np.array([[0, 0, 0, 1]], np.float32)], 0).astype(np.float32)
+    kstate = rng.choice(np.array([0, 0, 1, 1, 2], np.uint8), n)
+    knobs = rng.integers(1, 6, n)
+    kP = pu.points_for_transform(fa, n, rng, A, b, False)
+    P = pu.points_for_transform(fa, npts, rng, A, b, False)
+    cstate = (rng.choice(np.array([0, 1, 1, 1, 1, 2, 3], np.uint8), npts) if variant == 0 else
+              rng.choice(np.array([1, 1, 1, 1, 2, 3], np.uint8), npts))
+    dist = np.linalg.norm(P["world"].astype(np.float64) - Ow.astype(np.float64), axis=1) if npts else np.zeros(0)
+    cstate[(cstate == 1) & ~_level_ok(dist, P["mf_max"])] = 2
+    cnobs = rng.integers(0, 6, npts)
+    free = np.nonzero(kstate == 0)[0]
+    in_at = np.full(npts, -1, np.int32)
+    three = np.nonzero(cstate == 3)[0][:len(free)]
+    cstate[np.setdiff1d(np.nonzero(cstate == 3)[0], three)] = 2
+    in_at[three] = rng.choice(free, len(three), replace=False)
+    th = 3.0 if variant == 0 else 4.0
+    og = orc.Grid(fa["desc"], fa["x"], fa["y"], fa["octave"], pu.SCALE, fa["bounds"], angle=fa["angle"], uright=fa["uright"])
+    skip = (cstate != 1).astype(np.uint8)
+    best = orc.fuse_search(og, variant, T if variant == 0 else S[:3], Ow if variant == 0 else None, K[0], K[1], K[2], K[3], K[4],
+                           np.float32(log_sf), skip, P["world"], P["mf_max"], P["mf_min"], P["normal"], P["desc"], th, is2)
+    kfp = [_Pt(kstate[j] == 2, knobs[j]) for j in range(n)]
+    cand = [_Pt(cstate[i] == 2, cnobs[i]) for i in range(npts)]
+    kf_ptr = [None] * n
+    for j in range(n):
+        if kstate[j]:
+            kf_ptr[j] = kfp[j]
+            kfp[j].obs["kf"] = j
+    for i in three:
+        cand[i].obs["kf"] = int(in_at[i])
+        kf_ptr[in_at[i]] = cand[i]
+    nf, rep = _emulate_fuse(variant, fa["uright"], kf_ptr, kfp, cand, cstate, best)
+    idx = {id(p): j for j, p in enumerate(kfp)}
+    idx.update({id(p): 100000 + i for i, p in enumerate(cand)})
+    enc = lambda p: -1 if p is None else idx[id(p)]
+    rn, rkf, rpts, rrep = ref_py.ref_fuse(variant, og, K, is2, T, Ow, S, kstate, knobs, kP, cstate, cnobs, P, in_at, th)
+    assert rn == nf and (npts < 100 or nf > 50)
+    assert np.array_equal(rkf, np.array([enc(p) for p in kf_ptr], np.int32))
+    assert np.array_equal(rpts, np.array([(int(p.bad), p.nobs) for p in kfp + cand], np.int32).reshape(-1, 2))
+    if variant == 1:
+        assert np.array_equal(rrep, np.array([enc(p) for p in rep], np.int32))
+
+
+@matcher
+@pytest.mark.parametrize("seed,n,s12,th", [(310, 1200, 1.15, 7.5), (311, 2500, 0.8, 7.5), (312, 300, 1.6, 10.0)])
+def test_reference_search_by_sim3_equals_oracle(seed, n, s12, th):
+    import proj_util as pu
+    rng = np.random.default_rng(seed)
+    log_sf = float(np.log(np.float32(1.2)))
+    K = np.array([520.0, 520.0, 320.0, 240.0, 40.0, log_sf], np.float32)
+
+    def frame():
+        fa = pu.frame_arrays(n, rng, stereo=True)
+        fa["x"] = np.clip(fa["x"], 0, 639.5).astype(np.float32)
+        fa["y"] = np.clip(fa["y"], 0, 479.5).astype(np.float32)
+        return fa
+    fa1, fa2 = frame(), frame()
+    Ra, ta = pu.rot_small(rng, 3.0).astype(np.float32), rng.uniform(-0.1, 0.1, 3).astype(np.float32)
+    Rb, tb = pu.rot_small(rng, 3.0).astype(np.float32), rng.uniform(-0.1, 0.1, 3).astype(np.float32)
+    s12 = np.float32(s12)
+    R12 = (Ra.astype(np.float64) @ Rb.astype(np.float64).T).astype(np.float32)
+    t12 = (ta.astype(np.float64) - float(s12) * (R12.astype(np.float64) @ tb.astype(np.float64))).astype(np.float32)
+    # the reference's own arithmetic for sR12, sR21, t21 (:1121-1123): float scaling like cv::Mat::convertTo, `-sR21*t12` accumulated in double
+    sR12 = (R12 * s12).astype(np.float32)
+    sR21 = (R12.T * np.float32(1.0 / float(s12))).astype(np.float32)
+    t21 = (-(sR21.astype(np.float64) @ t12.astype(np.float64))).astype(np.float32)
+    perm = rng.permutation(n)
+    inv = np.argsort(perm)
+    tgt2 = np.where(rng.random(n) < 0.15, rng.integers(0, n, n), inv)
+    P1 = pu.points_for_transform(fa2, n, rng, (Rb / s12).astype(np.float32), tb, True, tgt=perm)
+    P2 = pu.points_for_transform(fa1, n, rng, (Ra * s12).astype(np.float32), ta, True, tgt=tgt2)
+    st1 = rng.choice(np.array([0, 1, 1, 1, 2], np.uint8), n)
+    st2 = rng.choice(np.array([0, 1, 1, 1, 2], np.uint8), n)
+    c1 = (sR21.astype(np.float64) @ (Ra.astype(np.float64) @ P1["world"].astype(np.float64).T + ta.astype(np.float64)[:, None])).T + t21.astype(np.float64)
+    c2 = (sR12.astype(np.float64) @ (Rb.astype(np.float64) @ P2["world"].astype(np.float64).T + tb.astype(np.float64)[:, None])).T + t12.astype(np.float64)
+    st1[(st1 == 1) & ~_level_ok(np.linalg.norm(c1, axis=1), P1["mf_max"])] = 2
+    st2[(st2 == 1) & ~_level_ok(np.linalg.norm(c2, axis=1), P2["mf_max"])] = 2
+    pre = np.where((rng.random(n) < 0.1) & (st1 == 1), rng.integers(0, n, n), -1).astype(np.int32)
+    pre[(pre >= 0) & (st2[np.maximum(pre, 0)] == 0)] = -1
+    og1 = orc.Grid(fa1["desc"], fa1["x"], fa1["y"], fa1["octave"], pu.SCALE, fa1["bounds"], angle=fa1["angle"], uright=fa1["uright"])
+    og2 = orc.Grid(fa2["desc"], fa2["x"], fa2["y"], fa2["octave"], pu.SCALE, fa2["bounds"], angle=fa2["angle"], uright=fa2["uright"])
+    already1 = pre >= 0
+    already2 = np.zeros(n, bool)
+    already2[pre[pre >= 0]] = True
+    m1 = orc.sim3_direction(og2, Ra, ta, sR21, t21, K[0], K[1], K[2], K[3], np.float32(log_sf), (st1 == 1) & ~already1, P1["world"], P1["mf_max"],
+                            P1["mf_min"], P1["desc"], th)
+    m2 = orc.sim3_direction(og1, Rb, tb, sR12, t12, K[0], K[1], K[2], K[3], np.float32(log_sf), (st2 == 1) & ~already2, P2["world"], P2["mf_max"],
+                            P2["mf_min"], P2["desc"], th)
+    want12, nfound = pre.copy(), 0
+    for i1 in range(n):
+        if m1[i1] >= 0 and m2[m1[i1]] == i1:
+            want12[i1] = m1[i1]
+            nfound += 1
+    Tz = lambda R, t: np.concatenate([R, t[:, None]], 1).astype(np.float32)
+    rn, r12 = ref_py.ref_search_by_sim3(og1, og2, K, Tz(Ra, ta), Tz(Rb, tb), st1, P1, st2, P2, s12, R12, t12, th, pre)
+    assert rn == nfound and nfound > 20 and np.array_equal(r12, want12)
