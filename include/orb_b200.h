@@ -330,7 +330,7 @@ int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used
  * descriptor sets for the matcher.  Host-only: parses / writes the Boost binary archive (`no_header`, `oa << mpMap`) whose
  * field order is Map::save/load (src/Map.cc:31-134), MapPoint::save/load (src/MapPoint.cc:59-213), KeyFrame::save/load
  * (src/KeyFrame.cc:86-510) and the cv::Mat / cv::KeyPoint serializers of include/MapPoint.h:198-247.  The byte framing is
- * documented in orbslam_mapsave_b200/csrc/orb_map.cpp.  Boost is absent from this image: layout parity is unpinned.
+ * documented in orbslam_mapsave_b200/csrc/orb_map.cpp.  Boost is absent from this image: the class-info framing is restated from Boost's documentation (unpinned); the field sequence of MapPoint is pinned to the reference's own MapPoint::save (orbmap_mappoint_record).
  * ---------------------------------------------------------------------------------------------------------------- */
 typedef struct orbmap_archive orbmap_archive;
 
@@ -385,6 +385,10 @@ int orbmap_mappoints(const orbmap_archive* ar, uint64_t* ids, float* world_pos, 
                      uint8_t* bad, int32_t* n_obs, int32_t* visible, int32_t* found, float* min_dist, float* max_dist,
                      int32_t* obs_offsets);
 int orbmap_observations(const orbmap_archive* ar, int64_t* kf_ids, int64_t* feature_idx);
+/* The fields of map point i exactly as MapPoint::save (src/MapPoint.cc:58-140) hands them to the archive — raw little-endian values in
+ * call order, WITHOUT Boost's class-info framing.  tests compare it with a recording of the reference's own MapPoint::save.
+ * out may be NULL (size query). */
+int orbmap_mappoint_record(const orbmap_archive* ar, int i, uint8_t* out, int64_t capacity, int64_t* n_bytes);
 /* The gather loop of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:495-510) for every map point: the observed
  * keyframe rows back to back (capacity in descriptors), offsets[n_mappoints + 1]; the input of orbm_distinctive_descriptors.
  * With desc == NULL only the offsets / total are produced. */

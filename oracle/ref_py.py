@@ -376,3 +376,45 @@ def ref_search_by_sim3(grid1, grid2, K6, T1, T2, st1, P1, st2, P2, s12, R12, t12
     n = L.refm_search_by_sim3(C.addressof(g1), C.addressof(g2), K6.ctypes.data, T1m.ctypes.data, T2m.ctypes.data, C.byref(p1), C.byref(p2),
                               float(s12), R.ctypes.data, t.ctypes.data, float(th), pre.ctypes.data, out.ctypes.data)
     return n, out[:grid1.n]
+
+
+# ---- MapPoint: the reference's own src/MapPoint.cc (oracle/_ref/libref_mappoint.so) ------------------------------------------
+PLIB = os.path.join(_HERE, "_ref", "libref_mappoint.so")
+
+
+def mappoint_available():
+    return os.path.exists(PLIB) and os.path.exists(MLIB)
+
+
+_plib = None
+
+
+def plib():
+    global _plib
+    if _plib is None:
+        L = C.CDLL(PLIB)
+        L.refp_distinctive.restype = C.c_int
+        L.refp_distinctive.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.refp_save_fields.restype = C.c_int
+        L.refp_save_fields.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        _plib = L
+    return _plib
+
+
+def ref_distinctive(desc, kf_bad=None, point_bad=False):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:483-548) on a point observed once by each of len(desc) keyframes.
+    Returns (index of the chosen observation or -1 when mDescriptor is left alone, mDescriptor)."""
+    d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    bad = None if kf_bad is None else np.ascontiguousarray(kf_bad, np.uint8)
+    out = np.zeros(32, np.uint8)
+    i = plib().refp_distinctive(d.ctypes.data, bad.ctypes.data if bad is not None else None, len(d), int(point_bad), out.ctypes.data)
+    return i, out
+
+
+def ref_mappoint_save_fields(n_obs, has_ref=True, track=False):
+    """(raw bytes, field tags) MapPoint::save (src/MapPoint.cc:58-140) hands to the archive, in call order."""
+    buf = np.zeros(1 << 16, np.uint8)
+    f = C.create_string_buffer(1 << 14)
+    n = plib().refp_save_fields(int(n_obs), int(has_ref), int(track), buf.ctypes.data, len(buf), f, len(f))
+    assert n >= 0
+    return buf[:n].tobytes(), f.value.decode().strip(";").split(";")

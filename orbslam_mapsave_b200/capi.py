@@ -33,7 +33,7 @@ SYMBOLS = [
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
     "orbv_transform_device",
     "orbmap_load", "orbmap_save", "orbmap_create", "orbmap_destroy", "orbmap_get_info", "orbmap_keyframe_get_info",
-    "orbmap_keyframe_arrays", "orbmap_keyframe_links", "orbmap_keyframe_grid", "orbmap_mappoints", "orbmap_observations",
+    "orbmap_keyframe_arrays", "orbmap_keyframe_links", "orbmap_keyframe_grid", "orbmap_mappoints", "orbmap_observations", "orbmap_mappoint_record",
     "orbmap_observed_descriptors", "orbmap_add_mappoint", "orbmap_add_keyframe", "orbmap_set_keyframe_links", "orbmap_add_origin",
 ]
 
@@ -198,6 +198,8 @@ def lib():
     L.orbmap_mappoints.argtypes = [vp] * 13
     L.orbmap_observations.restype = i32
     L.orbmap_observations.argtypes = [vp, vp, vp]
+    L.orbmap_mappoint_record.restype = i32
+    L.orbmap_mappoint_record.argtypes = [vp, i32, vp, i64, vp]
     L.orbmap_observed_descriptors.restype = i32
     L.orbmap_observed_descriptors.argtypes = [vp, vp, vp, i64, vp]
     L.orbmap_add_mappoint.restype = i32

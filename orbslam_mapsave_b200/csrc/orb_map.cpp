@@ -17,7 +17,8 @@
 //     under Boost's default `track_selectively` these classes are untracked (tracking byte 0, no object ids).  A set
 //     tracking byte is still honoured (object_id per object, id == running count means "new object");
 //   * std::vector<arithmetic> = collection_size_type (uint64) + the raw elements (array optimisation of binary
-//     archives); any other std::vector = collection_size_type + item_version_type (uint32) + the items.
+//     archives) and NO class preamble (BOOST_SERIALIZATION_COLLECTION_TRAITS makes them `object_serializable`); any other
+//     std::vector = [first time: tracking + version] + collection_size_type + item_version_type (uint32) + the items.
 // What follows that framing is the field order of Map::load (src/Map.cc:76-134), MapPoint::load (src/MapPoint.cc:142-213),
 // KeyFrame::load (src/KeyFrame.cc:308-510), the free cv::Mat save/load and the cv::KeyPoint serialize of
 // include/MapPoint.h:198-247 (which stores `response` twice and never `size`).
@@ -41,10 +42,9 @@ void orb_set_error(const char* fmt, ...);
 
 namespace {
 
-enum ClassId { C_MAP, C_MAPPOINT, C_KEYFRAME, C_MAT, C_KEYPOINT, C_VEC_KEYPOINT, C_VEC_FLOAT, C_VEC_INT, C_VEC_SIZE, C_VEC_VEC_SIZE,
-               C_VEC_VEC_VEC_SIZE, C_COUNT };
-const char* kClassName[C_COUNT] = {"Map", "MapPoint", "KeyFrame", "cv::Mat", "cv::KeyPoint", "vector<KeyPoint>", "vector<float>",
-                                   "vector<int>", "vector<size_t>", "vector<vector<size_t>>", "vector<vector<vector<size_t>>>"};
+enum ClassId { C_MAP, C_MAPPOINT, C_KEYFRAME, C_MAT, C_KEYPOINT, C_VEC_KEYPOINT, C_VEC_VEC_SIZE, C_VEC_VEC_VEC_SIZE, C_COUNT };
+const char* kClassName[C_COUNT] = {"Map", "MapPoint", "KeyFrame", "cv::Mat", "cv::KeyPoint", "vector<KeyPoint>", "vector<vector<size_t>>",
+                                   "vector<vector<vector<size_t>>>"};
 
 struct ClassState {
     bool seen = false, tracked = false;
@@ -138,6 +138,7 @@ struct MapRec {
     std::vector<KeyFrameRec> keyframes, origins;
     uint64_t max_kf_id = 0;
     uint32_t test_data = 0xdeadbeefu;    // src/Map.cc:22
+    bool tracked[C_COUNT] = {};          // tracking flag per class as read from the file (kept so that a save reproduces it)
     int64_t trailing_bytes = 0;          // what Map::load leaves unread (Map::save appends the map points a second time, :68-73)
     std::map<uint64_t, int> kf_index;    // mnId -> index into keyframes
 };
@@ -184,6 +185,9 @@ struct Writer {
     static constexpr bool reading = false;
     std::vector<uint8_t> out;
     ClassState cls[C_COUNT];
+    bool tracked_in[C_COUNT] = {};   // per-class tracking flags of the file this map was loaded from (all false for a built map)
+    bool framing = true;             // false: field payload only (orbmap_mappoint_record)
+    uint32_t n_objects = 1;          // object ids handed out so far (the Map itself is object 0)
     void raw(const void* src, size_t n) {
         const uint8_t* s = (const uint8_t*)src;
         out.insert(out.end(), s, s + n);
@@ -194,13 +198,19 @@ struct Writer {
         raw(&b, 1);
     }
     bool begin_object(ClassId c) {
+        if (!framing) return true;
         ClassState& s = cls[c];
         if (!s.seen) {
-            bool t = false;      // by-value classes are untracked in the fork (no pointer serialisation of them anywhere)
-            uint32_t ver = 0;
+            bool t = tracked_in[c];  // by-value classes are untracked in the fork (no pointer serialisation of them anywhere); a loaded
+            uint32_t ver = 0;        // file's own flags are written back as they were read
             boolean(t);
             prim(ver);
             s.seen = true;
+            s.tracked = t;
+        }
+        if (s.tracked) {             // every by-value object of a tracked class is a new object
+            uint32_t oid = n_objects++;
+            prim(oid);
         }
         return true;
     }
@@ -241,8 +251,10 @@ template <class Ar> uint64_t io_count(Ar& ar, uint64_t n) {
     return n;
 }
 
-template <class Ar, class T> void io_pod_vector(Ar& ar, ClassId c, std::vector<T>& v) {      // array-optimised std::vector
-    if (!ar.begin_object(c)) throw std::runtime_error("map archive: back-referenced vector");
+// std::vector of an arithmetic type: Boost's serialization/vector.hpp ends with BOOST_SERIALIZATION_COLLECTION_TRAITS(std::vector), which
+// gives vector<bool ... double> the implementation level `object_serializable` — no tracking byte, no version is ever written for
+// them — and binary archives store the elements as one raw array.
+template <class Ar, class T> void io_pod_vector(Ar& ar, std::vector<T>& v) {
     uint64_t n = io_count(ar, v.size());
     if (Ar::reading) {
         if (n * sizeof(T) > ar.remaining()) throw std::runtime_error("map archive truncated inside a vector");
@@ -359,16 +371,16 @@ template <class Ar> void io(Ar& ar, KeyFrameRec& k) {       // src/KeyFrame.cc:3
     ar.prim(k.n);
     io_obj_vector(ar, C_VEC_KEYPOINT, k.keys, [&](KeyPoint& p) { io(ar, p); });
     io_obj_vector(ar, C_VEC_KEYPOINT, k.keys_un, [&](KeyPoint& p) { io(ar, p); });
-    io_pod_vector(ar, C_VEC_FLOAT, k.uright);
-    io_pod_vector(ar, C_VEC_FLOAT, k.depth);
+    io_pod_vector(ar, k.uright);
+    io_pod_vector(ar, k.depth);
     io(ar, k.desc);
     io(ar, k.tcp);
     ar.prim(k.n_levels);
     ar.prim(k.scale_factor);
     ar.prim(k.log_scale_factor);
-    io_pod_vector(ar, C_VEC_FLOAT, k.scale_factors);
-    io_pod_vector(ar, C_VEC_FLOAT, k.level_sigma2);
-    io_pod_vector(ar, C_VEC_FLOAT, k.inv_level_sigma2);
+    io_pod_vector(ar, k.scale_factors);
+    io_pod_vector(ar, k.level_sigma2);
+    io_pod_vector(ar, k.inv_level_sigma2);
     ar.prim(k.min_x);
     ar.prim(k.min_y);
     ar.prim(k.max_x);
@@ -380,7 +392,7 @@ template <class Ar> void io(Ar& ar, KeyFrameRec& k) {       // src/KeyFrame.cc:3
     io(ar, k.Cw);
     io_idrefs(ar, k.mappoints);
     io_obj_vector(ar, C_VEC_VEC_VEC_SIZE, k.grid, [&](std::vector<std::vector<uint64_t>>& col) {
-        io_obj_vector(ar, C_VEC_VEC_SIZE, col, [&](std::vector<uint64_t>& cell) { io_pod_vector(ar, C_VEC_SIZE, cell); });
+        io_obj_vector(ar, C_VEC_VEC_SIZE, col, [&](std::vector<uint64_t>& cell) { io_pod_vector(ar, cell); });
     });
     int32_t nc = io_nitems(ar, k.connected.size());
     if (Ar::reading) k.connected.resize(nc);
@@ -392,7 +404,7 @@ template <class Ar> void io(Ar& ar, KeyFrameRec& k) {       // src/KeyFrame.cc:3
         }
     }
     io_idrefs(ar, k.ordered);
-    io_pod_vector(ar, C_VEC_INT, k.ordered_weights);
+    io_pod_vector(ar, k.ordered_weights);
     ar.boolean(k.first_connection);
     ar.boolean(k.parent.valid);
     if (k.parent.valid) ar.prim(k.parent.id);
@@ -433,6 +445,7 @@ void read_map(Reader& ar, MapRec& m) {
     ar.prim(m.max_kf_id);
     ar.prim(m.test_data);
     m.trailing_bytes = (int64_t)ar.remaining();
+    for (int c = 0; c < C_COUNT; ++c) m.tracked[c] = ar.cls[c].tracked;
 }
 
 // Map::save, src/Map.cc:31-74 (incl. the second copy of the map points that load never reads).
@@ -440,6 +453,7 @@ void write_map(Writer& ar, MapRec& m) {
     int16_t class_id = 0;
     bool tracked = true;          // a class saved through a pointer is tracked
     uint32_t version = 0, oid = 0;
+    for (int c = 0; c < C_COUNT; ++c) ar.tracked_in[c] = m.tracked[c];
     ar.prim(class_id);
     ar.boolean(tracked);
     ar.prim(version);
@@ -670,9 +684,12 @@ int orbmap_keyframe_arrays(const orbmap_archive* ar, int group, int i, orbx_keyp
     if (mappoint_ids)
         for (size_t j = 0; j < k->mappoints.size(); ++j) mappoint_ids[j] = k->mappoints[j].valid ? (int64_t)k->mappoints[j].id : -1;
     if (scale_factors && !k->scale_factors.empty()) memcpy(scale_factors, k->scale_factors.data(), k->scale_factors.size() * 4);
-    if (level_sigma2 && !k->level_sigma2.empty()) memcpy(level_sigma2, k->level_sigma2.data(), k->level_sigma2.size() * 4);
-    if (inv_level_sigma2 && !k->inv_level_sigma2.empty())
-        memcpy(inv_level_sigma2, k->inv_level_sigma2.data(), k->inv_level_sigma2.size() * 4);
+    // the three scale tables are independent vectors in the file; the caller sizes all of them from n_scale_factors
+    const size_t nsf = k->scale_factors.size();
+    if (level_sigma2)
+        for (size_t j = 0; j < nsf; ++j) level_sigma2[j] = j < k->level_sigma2.size() ? k->level_sigma2[j] : 0.f;
+    if (inv_level_sigma2)
+        for (size_t j = 0; j < nsf; ++j) inv_level_sigma2[j] = j < k->inv_level_sigma2.size() ? k->inv_level_sigma2[j] : 0.f;
     if (Tcw) copy_mat_f32(k->Tcw, Tcw, 16);
     if (K) copy_mat_f32(k->K, K, 9);
     return ORB_OK;
@@ -694,8 +711,8 @@ int orbmap_keyframe_links(const orbmap_archive* ar, int group, int i, int64_t* c
             for (size_t j = 0; j < v.size(); ++j) dst[j] = v[j].valid ? (int64_t)v[j].id : -1;
     };
     refs(k->ordered, ordered_ids);
-    if (ordered_weights && !k->ordered_weights.empty())
-        memcpy(ordered_weights, k->ordered_weights.data(), k->ordered_weights.size() * 4);
+    if (ordered_weights)         // mvOrderedWeights is a vector of its own in the file; the caller sizes it from n_ordered
+        for (size_t j = 0; j < k->ordered.size(); ++j) ordered_weights[j] = j < k->ordered_weights.size() ? k->ordered_weights[j] : 0;
     refs(k->children, children_ids);
     refs(k->loop_edges, loop_edge_ids);
     return ORB_OK;
@@ -786,6 +803,26 @@ int orbmap_observations(const orbmap_archive* ar, int64_t* kf_ids, int64_t* feat
 /* The gather loop of MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:495-510) for every map point of the archive:
  * observations in the stored order (= std::map<KeyFrame*, size_t> order at save time), skipping invalid entries, keyframes
  * that are not in the map, bad keyframes and out-of-range rows. */
+int orbmap_mappoint_record(const orbmap_archive* ar, int i, uint8_t* out, int64_t capacity, int64_t* n_bytes) {
+    if (!ar || i < 0 || (size_t)i >= ar->map.mappoints.size() || !n_bytes) {
+        orb_set_error("orbmap_mappoint_record: bad archive / index");
+        return ORB_ERR_ARG;
+    }
+    Writer w;
+    w.framing = false;
+    MapPointRec rec = ar->map.mappoints[i];
+    io(w, rec);
+    *n_bytes = (int64_t)w.out.size();
+    if (out) {
+        if ((int64_t)w.out.size() > capacity) {
+            orb_set_error("orbmap_mappoint_record: capacity %lld too small", (long long)capacity);
+            return ORB_ERR_CAPACITY;
+        }
+        memcpy(out, w.out.data(), w.out.size());
+    }
+    return ORB_OK;
+}
+
 int orbmap_observed_descriptors(const orbmap_archive* ar, uint8_t* desc, int32_t* offsets, int64_t capacity, int64_t* n_total) {
     if (!ar) {
         orb_set_error("orbmap_observed_descriptors: null archive");

@@ -48,7 +48,7 @@ public:
     void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     int type() const { return type_; }
-    size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
+    size_t elemSize() const { return (!data && rows == 0 && cols == 0) ? 0 : (type_ == CV_32F ? 4 : 1); }   // 0 for an empty Mat, like cv::Mat
     bool isContinuous() const { return step == (size_t)cols * elemSize(); }
     Mat row(int r) const { Mat m = *this; m.rows = 1; m.data = data + (size_t)r * step; return m; }
     Mat rowRange(int a, int b) const { Mat m = *this; m.rows = b - a; m.data = data + (size_t)a * step; return m; }
@@ -73,6 +73,7 @@ public:
         for (int r = 0; r < rows; r++) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * elemSize());
         return m;
     }
+    void copyTo(Mat& dst) const { dst = clone(); }
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     unsigned char* ptr(int r = 0) { return data + (size_t)r * step; }

@@ -65,13 +65,12 @@ class _Stream:
             self.f32(k["x"]), self.f32(k["y"])
 
     def vec_f32(self, v):
-        self.cls("vector<float>")
+        # no class preamble: vectors of arithmetic types are `object_serializable` (BOOST_SERIALIZATION_COLLECTION_TRAITS)
         v = np.ascontiguousarray(v, np.float32)
         self.u64(len(v))
         self.b += v.tobytes()
 
     def vec_i32(self, v):
-        self.cls("vector<int>")
         v = np.ascontiguousarray(v, np.int32)
         self.u64(len(v))
         self.b += v.tobytes()
@@ -83,7 +82,6 @@ class _Stream:
             self.cls("vector<vector<size_t>>")
             self.u64(len(col)), self.u32(0)
             for cell in col:
-                self.cls("vector<size_t>")
                 self.u64(len(cell))
                 self.b += np.ascontiguousarray(cell, np.uint64).tobytes()
 

@@ -411,3 +411,71 @@ def test_reference_search_by_sim3_equals_oracle(seed, n, s12, th):
     Tz = lambda R, t: np.concatenate([R, t[:, None]], 1).astype(np.float32)
     rn, r12 = ref_py.ref_search_by_sim3(og1, og2, K, Tz(Ra, ta), Tz(Rb, tb), st1, P1, st2, P2, s12, R12, t12, th, pre)
     assert rn == nfound and nfound > 20 and np.array_equal(r12, want12)
+
+
+# ---- MapPoint: the reference's own src/MapPoint.cc + include/MapPoint.h compiled unmodified (stand-ins for KeyFrame / Frame / Map,
+# recording stand-ins for Boost's archives; ORBmatcher::DescriptorDistance forwarded to the reference's own in libref_orbmatcher.so)
+mappoint = pytest.mark.skipif(not ref_py.mappoint_available(), reason="oracle/_ref/libref_mappoint.so not built")
+
+
+@mappoint
+def test_reference_compute_distinctive_descriptors_equals_oracle():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:483-548): least median Hamming distance to the other observations,
+    median = sorted row[int(0.5 * (N - 1))], first index wins ties, observations in bad keyframes left out — the oracle's choice on
+    the ragged sets of tests/test_gpu_match.py::test_distinctive_descriptors_vs_oracle (sizes 1 / 2 / 32 / 33 / 257 / 1000, duplicates)."""
+    from orbslam_mapsave_b200.synth import synth_descriptors
+    rng = np.random.default_rng(17)
+    sizes = [1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 64, 100, 257, 1000] + [int(v) for v in rng.integers(1, 40, 120)]
+    for k, n in enumerate(sizes):
+        base = synth_descriptors(1, 1000 + k)
+        d = synth_descriptors(n, 2000 + k, dup_of=base, dup_rate=0.8, max_flip=60)
+        if k % 5 == 0 and n > 3:
+            d[n // 2] = d[0]                                   # exact duplicates: equal medians, first index wins
+            d[n - 1] = d[1]
+        bad = (rng.random(n) < (0.3 if k % 3 == 0 else 0.0)).astype(np.uint8)
+        good = np.nonzero(bad == 0)[0]
+        ri, rdesc = ref_py.ref_distinctive(d, bad)
+        if len(good) == 0:
+            assert ri == -1
+            continue
+        oi = orc.distinctive(d[good])
+        assert np.array_equal(rdesc, d[good][oi]), (k, n, ri, oi)
+    assert ref_py.ref_distinctive(synth_descriptors(5, 1), point_bad=True)[0] == -1        # a bad point keeps its descriptor (:491-492)
+
+
+@mappoint
+def test_reference_mappoint_save_field_sequence_matches_the_archive_layout():
+    """The order and width of what MapPoint::save (src/MapPoint.cc:58-140) hands to the archive, recorded from the reference's own
+    code, equals the field list the map-archive reader / writer (orbslam_mapsave_b200/csrc/orb_map.cpp) is built on — stated here
+    as the tag sequence.  (This pins field order and widths, not Boost's class-info framing.)"""
+    mat = lambda nbytes: ["Mat{", "i4", "i4", "u8", "u8", f"a{nbytes}", "}"]
+    for n_obs, has_ref in [(0, True), (3, True), (5, False)]:
+        raw, tags = ref_py.ref_mappoint_save_fields(n_obs, has_ref)
+        want = (["u8", "u8", "i8", "i8", "i4", "f4", "f4", "f4", "b1", "i4", "f4"] + ["u8"] * 7 + mat(0) + ["u8"] + mat(12) + ["u4"] +
+                ["b1", "u8", "u8"] * n_obs + mat(12) + mat(32 if n_obs else 0) + (["b1", "u8"] if has_ref else ["b1"]) +
+                ["i4", "i4", "b1", "f4", "f4"])
+        assert tags == want, (n_obs, has_ref, tags)
+        # spot values: mnId = 41 (nNextId before construction), nNextId = 42 afterwards, mnFirstKFid = mnFirstFrame = 100
+        assert np.frombuffer(raw[:32], np.int64).tolist() == [41, 42, 100, 100]
+        rawt, tagst = ref_py.ref_mappoint_save_fields(n_obs, has_ref, track=True)
+        assert tagst == tags and np.frombuffer(rawt[36:48], np.float32).tolist() == [11.0, 12.0, 13.0]
+        if n_obs == 0:
+            continue                       # (the builder always stores a 1 x 32 descriptor; a point without observations has none)
+        # the same logical point through the product's map builder: its framing-free record equals the reference's bytes
+        import ctypes as C
+        from orbslam_mapsave_b200 import capi
+        L = capi.lib()
+        h = C.c_void_p()
+        capi.check(L.orbmap_create(C.byref(h)))
+        # MapPoint::nNextId is a static every record carries: 42 here, so a point with id 41 must be the newest in the map
+        desc = np.frombuffer(raw, np.uint8)[-(32 + (9 if has_ref else 1) + 17):][:32].copy()
+        kf_ids = np.array([100 + 7 * i for i in range(n_obs)], np.int64)
+        feat = np.array([i % 4 for i in range(n_obs)], np.int64)
+        pos, nrm = np.array([1.5, -2.25, 8.0], np.float32), np.zeros(3, np.float32)
+        capi.check(L.orbmap_add_mappoint(h, 41, 100, capi._p(pos), capi._p(nrm), capi._p(desc), 100 if has_ref else -1, n_obs, capi._p(kf_ids),
+                                         capi._p(feat), 1, 1, 0.0, 0.0))
+        nb = C.c_int64()
+        buf = np.zeros(4096, np.uint8)
+        capi.check(L.orbmap_mappoint_record(h, 0, capi._p(buf), len(buf), C.byref(nb)))
+        L.orbmap_destroy(h)
+        assert buf[:nb.value].tobytes() == raw
