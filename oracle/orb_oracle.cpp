@@ -1620,4 +1620,13 @@ void orc_sim3_direction(const orc_grid_view* Tp, const float* Rfw, const float* 
     orc_search_windows_best(Tp, n, active.data(), u.data(), v.data(), rad.data(), minL.data(), maxL.data(), desc, nullptr, nullptr, TH_HIGH, vnMatch);
 }
 
+// Frame::GetFeaturesInArea on its own (the candidate list every window search starts from), for the comparison with the reference's
+// own src/Frame.cc: returns the number of indices, out[0..cap) receives them in the reference's order.
+int orc_features_in_area(const orc_grid_view* F, float x, float y, float r, int min_level, int max_level, int* out, int cap) {
+    std::vector<int> v;
+    features_in_area(*F, x, y, r, min_level, max_level, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = v[i];
+    return (int)v.size();
+}
+
 }  // extern "C"

@@ -549,3 +549,14 @@ def sim3_direction(grid_to, Rfw, tfw, sR, t, fx, fy, cx, cy, log_sf, valid, worl
     f(C.byref(g), _p(Rfw), _p(tfw), _p(sR), _p(t), fx, fy, cx, cy, log_sf, len(valid), _p(valid), _p(world), _p(mf_max), _p(mf_min), _p(desc),
       float(th), _p(out))
     return out[:len(valid)]
+
+
+def features_in_area(grid, x, y, r, min_level=-1, max_level=-1):
+    """Frame::GetFeaturesInArea restatement on its own (src/Frame.cc:445-498)."""
+    out = np.zeros(max(grid.n, 1), np.int32)
+    f = lib().orc_features_in_area
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(GridViewC), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    g = grid.c()
+    n = f(C.byref(g), float(x), float(y), float(r), int(min_level), int(max_level), _p(out), len(out))
+    return out[:n].copy()

@@ -418,3 +418,52 @@ def ref_mappoint_save_fields(n_obs, has_ref=True, track=False):
     n = plib().refp_save_fields(int(n_obs), int(has_ref), int(track), buf.ctypes.data, len(buf), f, len(f))
     assert n >= 0
     return buf[:n].tobytes(), f.value.decode().strip(";").split(";")
+
+
+# ---- Frame: the reference's own src/Frame.cc (oracle/_ref/libref_frame.so) --------------------------------------------------
+FLIB = os.path.join(_HERE, "_ref", "libref_frame.so")
+
+
+def frame_available():
+    return os.path.exists(FLIB) and os.path.exists(MLIB)
+
+
+def ref_stereo_matches(levels_left, levels_right, scale_factors, inv_scale_factors, kp_left, desc_left, kp_right, desc_right, mbf, mb):
+    """Frame::ComputeStereoMatches (src/Frame.cc:584-756) of the reference on border-less pyramid levels; same arguments as the oracle's
+    stereo_matches.  Returns (mvuRight, mvDepth)."""
+    from .orb_oracle_py import KP_DTYPE
+    L = C.CDLL(FLIB)
+    nl = len(levels_left)
+    Ls = [np.ascontiguousarray(a, np.uint8) for a in levels_left]
+    Rs = [np.ascontiguousarray(a, np.uint8) for a in levels_right]
+    pl = (C.c_void_p * nl)(*[a.ctypes.data for a in Ls])
+    pr = (C.c_void_p * nl)(*[a.ctypes.data for a in Rs])
+    w = np.array([a.shape[1] for a in Ls], np.int32)
+    h = np.array([a.shape[0] for a in Ls], np.int32)
+    sf, isf = _a(scale_factors, np.float32), _a(inv_scale_factors, np.float32)
+    kl, kr = np.ascontiguousarray(kp_left, KP_DTYPE), np.ascontiguousarray(kp_right, KP_DTYPE)
+    dl, dr = _a(desc_left, np.uint8).reshape(-1, 32), _a(desc_right, np.uint8).reshape(-1, 32)
+    u, d = np.zeros(max(len(kl), 1), np.float32), np.zeros(max(len(kl), 1), np.float32)
+    f = L.reff_stereo_matches
+    f.restype = None
+    f.argtypes = [C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    f(nl, pl, pr, w.ctypes.data, h.ctypes.data, sf.ctypes.data, isf.ctypes.data, kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data,
+      dr.ctypes.data, len(kr), float(mbf), float(mb), u.ctypes.data, d.ctypes.data)
+    return u[:len(kl)], d[:len(kl)]
+
+
+def ref_grid_and_areas(x, y, octave, bounds, queries, levels):
+    """Frame::AssignFeaturesToGrid + Frame::GetFeaturesInArea of the reference: (cell_offsets, cell_features, per-query index lists)."""
+    L = C.CDLL(FLIB)
+    x, y, oc, b = _a(x, np.float32), _a(y, np.float32), _a(octave, np.int32), _a(bounds, np.float32)
+    q, ql = _a(queries, np.float32).reshape(-1, 3), _a(levels, np.int32).reshape(-1, 2)
+    n, nq = len(x), len(q)
+    off, feat = np.zeros(64 * 48 + 1, np.int32), np.zeros(max(n, 1), np.int32)
+    cap = max(n, 1) * max(nq, 1)
+    qoff, qidx = np.zeros(nq + 1, np.int32), np.zeros(cap, np.int32)
+    f = L.reff_grid_and_areas
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+    e = f(n, x.ctypes.data, y.ctypes.data, oc.ctypes.data, b.ctypes.data, off.ctypes.data, feat.ctypes.data, nq, q.ctypes.data, ql.ctypes.data,
+          qoff.ctypes.data, qidx.ctypes.data, cap)
+    return off, feat[:e], [qidx[qoff[k]:qoff[k + 1]].copy() for k in range(nq)]

@@ -74,6 +74,22 @@ public:
         return m;
     }
     void copyTo(Mat& dst) const { dst = clone(); }
+    Mat reshape(int /*cn*/) const { return *this; }          // channels are not represented in this single-channel stand-in
+    static Mat ones(int r, int c, int type) {
+        Mat m(r, c, type);
+        for (int y = 0; y < r; y++)
+            for (int x = 0; x < c; x++) { if (type == CV_32F) m.at<float>(y, x) = 1.f; else m.at<unsigned char>(y, x) = 1; }
+        return m;
+    }
+    void convertTo(Mat& dst, int rtype) const {           // CV_8U -> CV_32F (exact) or a same-type copy; dst may be *this (a view is left alone)
+        Mat out(rows, cols, rtype);
+        for (int y = 0; y < rows; y++)
+            for (int x = 0; x < cols; x++) {
+                const float v = type_ == CV_32F ? at<float>(y, x) : (float)at<unsigned char>(y, x);
+                if (rtype == CV_32F) out.at<float>(y, x) = v; else out.at<unsigned char>(y, x) = (unsigned char)v;
+            }
+        dst = out;
+    }
     template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
     template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
     unsigned char* ptr(int r = 0) { return data + (size_t)r * step; }

@@ -479,3 +479,52 @@ def test_reference_mappoint_save_field_sequence_matches_the_archive_layout():
         capi.check(L.orbmap_mappoint_record(h, 0, capi._p(buf), len(buf), C.byref(nb)))
         L.orbmap_destroy(h)
         assert buf[:nb.value].tobytes() == raw
+
+
+# ---- Frame::ComputeStereoMatches: the reference's own src/Frame.cc compiled unmodified (the extractors it reads are stand-ins holding
+# the pyramids; DescriptorDistance is the reference's own)
+frame = pytest.mark.skipif(not ref_py.frame_available(), reason="oracle/_ref/libref_frame.so not built")
+
+
+@frame
+@pytest.mark.parametrize("W,H,nf,nl,seed,mbf", [(640, 480, 1000, 8, 0, 40.0), (752, 480, 1200, 8, 1, 47.9), (1280, 720, 2000, 8, 2, 386.0),
+                                              (424, 240, 600, 6, 3, 20.0)])
+def test_reference_compute_stereo_matches_equals_oracle(W, H, nf, nl, seed, mbf):
+    """mvuRight / mvDepth of the reference's Frame::ComputeStereoMatches (src/Frame.cc:584-756) equal the oracle's bit for bit on the
+    stereo pairs of tests/test_gpu_stereo.py (keypoints of the extractor stay >= 19 px inside every level, so none of the reference's
+    unchecked accesses — row table, 11x11 windows — leaves the image)."""
+    from test_gpu_stereo import _stereo_pair
+    left, right = _stereo_pair(W, H, seed)
+    oL, oR = orc.Extractor(nf, 1.2, nl, 20, 7), orc.Extractor(nf, 1.2, nl, 20, 7)
+    okL, odL = oL.extract(left)
+    okR, odR = oR.extract(right)
+    t = oL.tables()
+    mb = mbf / 500.0
+    lv = ([oL.level(l) for l in range(nl)], [oR.level(l) for l in range(nl)])
+    want_u, want_d = orc.stereo_matches(lv[0], lv[1], t["scale"], t["inv_scale"], okL, odL, okR, odR, mbf, mb)
+    got_u, got_d = ref_py.ref_stereo_matches(lv[0], lv[1], t["scale"], t["inv_scale"], okL, odL, okR, odR, mbf, mb)
+    assert (want_u >= 0).sum() > len(okL) // 4
+    assert np.array_equal(got_u.view(np.uint32), want_u.view(np.uint32)) and np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))
+
+
+@frame
+@pytest.mark.parametrize("n,seed,cluster", [(2000, 50, False), (6000, 51, True), (3, 52, False)])
+def test_reference_feature_grid_and_features_in_area_equal_oracle(n, seed, cluster):
+    """Frame::AssignFeaturesToGrid / PosInGrid (src/Frame.cc:341-356, 500-510: `round`) and Frame::GetFeaturesInArea (:445-498) of the
+    reference's own Frame.cc: the grid equals the CSR the oracle / product are handed, and the candidate lists (order included) equal the
+    oracle's restatement that every window search starts from."""
+    import proj_util as pu
+    rng = np.random.default_rng(seed)
+    fa = pu.frame_arrays(n, rng, stereo=False, cluster=cluster)
+    og = orc.Grid(fa["desc"], fa["x"], fa["y"], fa["octave"], pu.SCALE, fa["bounds"], angle=fa["angle"])
+    nq = 300
+    q = np.stack([rng.uniform(-30, 670, nq), rng.uniform(-30, 510, nq), rng.choice([1.0, 3.0, 7.5, 15.0, 40.0, 100.0], nq)], 1).astype(np.float32)
+    lev = np.stack([rng.integers(-1, 6, nq), rng.integers(-1, 8, nq)], 1).astype(np.int32)
+    off, feat, lists = ref_py.ref_grid_and_areas(fa["x"], fa["y"], fa["octave"], fa["bounds"], q, lev)
+    assert np.array_equal(off, og.off) and np.array_equal(feat, og.feat[:len(feat)]) and len(feat) == og.off[-1]
+    total = 0
+    for k in range(nq):
+        want = orc.features_in_area(og, q[k, 0], q[k, 1], q[k, 2], lev[k, 0], lev[k, 1])
+        assert np.array_equal(lists[k], want), k
+        total += len(want)
+    assert n < 100 or total > 1000
