@@ -453,6 +453,12 @@ template <int OFF> __device__ __forceinline__ u32 lds32i(u32 addr) {
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
     return v;
 }
+template <int OFF> __device__ __forceinline__ u32 lds8i(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ void sts8(u32 addr, u32 v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts16(u32 addr, u32 v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory"); }
 
@@ -467,7 +473,8 @@ template <int BOXW, int SPP>
 __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_constant__ Plan P, const CUtensorMap* __restrict__ maps,
                                                                   const uint4* __restrict__ cells, int nCells, int nf,
                                                                   uint2* __restrict__ cand, int* __restrict__ candCount,
-                                                                  int* __restrict__ status, int* __restrict__ workCounter) {
+                                                                  int* __restrict__ status, int* __restrict__ workCounter,
+                                                                  unsigned long long cellsInv40) {
     extern __shared__ __align__(128) u8 smem_fw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int BW = BOXW > 0 ? BOXW : P.fwBoxW, SP = SPP > 0 ? SPP : P.scorePitch;
@@ -487,19 +494,25 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    auto issue = [&](int it, int b) {          // lane 0 only
-        const int f = it / nCells, ci = it - f * nCells;
-        const uint4 ce = __ldg(cells + ci);
-        const u32 bar = b ? bar1 : bar0;
-        (void)bar1;
-        mbar_expect_tx(bar, boxBytes);
-        // TMA needs the box start 16-byte aligned in the innermost dimension: load from the aligned column, keep the lead
-        tma_load_3d(smem_u32(wbase + b * P.fwTileBytes), maps + ((ce.y >> 16) & 0xFF), ((int)(ce.x & 0xFFFF) + ORBX_OX) & ~15,
-                    (int)(ce.x >> 16) + ORBX_OY, f, bar);
+    // item -> (frame, cell): one 64-bit multiply by ceil(2^40 / nCells) (exact while item * nCells < 2^40) instead of an integer division
+    auto split = [&](int it, int& f, int& ci) {
+        f = (int)(((unsigned long long)(u32)it * cellsInv40) >> 40);
+        ci = it - f * nCells;
     };
-    if (lane == 0) issue(item, 0);
+    auto issue = [&](int f, int ci) {          // lane 0 only
+        const uint4 ce = __ldg(cells + ci);
+        mbar_expect_tx(bar0, boxBytes);
+        // TMA needs the box start 16-byte aligned in the innermost dimension: load from the aligned column, keep the lead
+        tma_load_3d(smem_u32(wbase), maps + ((ce.y >> 16) & 0xFF), ((int)(ce.x & 0xFFFF) + ORBX_OX) & ~15, (int)(ce.x >> 16) + ORBX_OY, f, bar0);
+    };
+    int f, cidx;
+    split(item, f, cidx);
+    if (lane == 0) issue(f, cidx);
     u32 ph0 = 0;
     const u32 lt = (1u << lane) - 1;
+    // the score map (pixel (px, py) at byte (py + 1) * SP + px + 2) is zeroed once; every cell clears the entries it wrote
+    for (int i = lane; i < ((P.scoreRows * SP) >> 2); i += 32) reinterpret_cast<u32*>(score)[i] = 0;
+    const u32 scoreS = smem_u32(score);
     // Cells differ in cost (texture, the minThFAST retry), so after its first, statically assigned cell a warp takes its work
     // from a global counter; the id of the next cell is fetched one cell ahead so that its TMA load can be issued early.
     int nextItem = 0;
@@ -507,13 +520,10 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
     nextItem = __shfl_sync(0xffffffffu, nextItem, 0);
 
     for (; item < nItems;) {
-        const int f = item / nCells, cidx = item - f * nCells;
         const uint4 ce = __ldg(cells + cidx);
         const int iniX = (int)(ce.x & 0xFFFF), iniY = (int)(ce.x >> 16);
         const int tw = (int)(ce.y & 0xFF), th = (int)((ce.y >> 8) & 0xFF), l = (int)((ce.y >> 16) & 0xFF), c = (int)ce.z;
         const int dw = tw - 6, dh = th - 6;
-        // score map: pixel (px, py) at byte (py + 1) * SP + px + 2; zero it while the tile is in flight
-        for (int i = lane; i < (((dh + 2) * SP) >> 2); i += 32) reinterpret_cast<u32*>(score)[i] = 0;
         mbar_wait(bar0, ph0);
         ph0 ^= 1;
         __syncwarp();
@@ -526,8 +536,8 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
         // 4-pixel groups aligned to tile words: group g of a row covers tile x [g0 + 4g, g0 + 4g + 4), i.e. domain px [4g - offq, ...)
         const int g0 = X0 & ~3, offq = X0 - g0, ng = (offq + dw + 3) >> 2, ntask = ng * dh;
         const u32 tileS = smem_u32(wbase), plS = smem_u32(plist), glS = smem_u32(wbase + P.fwGlistOff);
-        const u32 inv = 0xFFFFFFFFu / (u32)ng + 1;
-        int nKeep = 0, T = P.iniTh;
+        const u32 inv = ce.w;                                         // 2^32 / ng + 1, from the host
+        int nKeep = 0, nc = 0, T = P.iniTh;
         for (int pass = 0; pass < 2; pass++) {
             const int t = pass ? P.minTh : P.iniTh;
             T = t;
@@ -611,7 +621,7 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
             // high half of every register (x = K + ring * 0xFFFF, K = (256 + v) | (256 - v) << 16), so that
             //   A = max over arcs of min9(d)   and   B = max over arcs of min9(-d)
             // come out of one min3/max3 sequence (40 VIMNMX3.U16x2 per pixel).  Corners are compacted in place at the list front.
-            int nc = 0;
+            nc = 0;
             {
                 const u8* t8 = tile + 3 * BW + X0;
                 for (int e0 = 0; e0 < nl; e0 += 32) {
@@ -652,7 +662,8 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
             }
             __syncwarp();
 
-            // ---- 3x3 NMS over the corners; survivors compacted in place again
+            // ---- 3x3 NMS over the corners, branch-free (8 neighbours -> one maximum -> one compare); the survivors go to the group
+            // list's buffer (free by now) so that plist[0, nc) keeps the corners for the clean-up of the score map
             nKeep = 0;
             for (int e0 = 0; e0 < nc; e0 += 32) {
                 const int e = e0 + lane;
@@ -660,14 +671,22 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                 int ent = 0;
                 if (e < nc) {
                     ent = plist[e];
-                    const u8* sp = score + ((ent >> 8) + 1) * SP + (ent & 0xFF) + 2;
-                    const int s = sp[0];
-                    keep = s > sp[-1] && s > sp[1] && s > sp[-SP - 1] && s > sp[-SP] && s > sp[-SP + 1] &&
-                           s > sp[SP - 1] && s > sp[SP] && s > sp[SP + 1];
+                    const u32 sp = scoreS + (u32)(((ent >> 8) + 1) * SP + (ent & 0xFF) + 2);
+                    u32 s, n0, n1, n2, n3, n4, n5, n6, n7;
+                    if (SPP > 0) {
+                        s = lds8i<0>(sp); n0 = lds8i<-1>(sp); n1 = lds8i<1>(sp);
+                        n2 = lds8i<-SPP - 1>(sp); n3 = lds8i<-SPP>(sp); n4 = lds8i<-SPP + 1>(sp);
+                        n5 = lds8i<SPP - 1>(sp); n6 = lds8i<SPP>(sp); n7 = lds8i<SPP + 1>(sp);
+                    } else {
+                        const u32 su = sp - SP, sd = sp + SP;
+                        s = lds8i<0>(sp); n0 = lds8i<-1>(sp); n1 = lds8i<1>(sp);
+                        n2 = lds8i<-1>(su); n3 = lds8i<0>(su); n4 = lds8i<1>(su);
+                        n5 = lds8i<-1>(sd); n6 = lds8i<0>(sd); n7 = lds8i<1>(sd);
+                    }
+                    keep = s > __vimax3_u32(__vimax3_u32(n0, n1, n2), __vimax3_u32(n3, n4, n5), max(n6, n7));
                 }
-                __syncwarp();
                 const u32 bk = __ballot_sync(0xffffffffu, keep);
-                if (keep) plist[nKeep + __popc(bk & lt)] = (u16)ent;
+                if (keep) sts16(glS + 2 * (u32)(nKeep + __popc(bk & lt)), (u32)ent);
                 nKeep += __popc(bk);
             }
             if (nKeep > 0 || P.minTh >= P.iniTh) break;               // :811 `if(vKeysCell.empty())` -> retry at minThFAST
@@ -675,28 +694,40 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
         }
         __syncwarp();
         // the tile is no longer needed: fetch the next cell's tile now, it lands while emission / score clearing run
-        item = nextItem;                                              // (f, l, c, iniX ... of the cell in hand are locals)
-        if (lane == 0 && item < nItems) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // order our generic reads before the async-proxy write
-            issue(item, 0);
-            nextItem = Wt + atomicAdd(workCounter, 1);
+        const int fCur = f;                                           // (l, c, iniX ... of the cell in hand are locals)
+        item = nextItem;
+        if (item < nItems) {
+            split(item, f, cidx);
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // order our generic reads before the async-proxy write
+                issue(f, cidx);
+                nextItem = Wt + atomicAdd(workCounter, 1);
+            }
         }
         nextItem = __shfl_sync(0xffffffffu, nextItem, 0);
         if (nKeep) {                                                  // every survivor of the pass that produced them is emitted (score >= T)
             const LevelPlan& L = P.lv[l];
             int base = 0;
             if (lane == 0) {
-                base = atomicAdd(&candCount[f * P.nlevels + l], nKeep);
+                base = atomicAdd(&candCount[fCur * P.nlevels + l], nKeep);
                 if (base + nKeep > L.candCap) atomicOr(status, ORB_DEV_CAND_OVERFLOW);
             }
             base = __shfl_sync(0xffffffffu, base, 0);
-            uint2* out = cand + (size_t)f * P.candTotal + L.candOff;
+            uint2* out = cand + (size_t)fCur * P.candTotal + L.candOff;
+            const u16* kept = reinterpret_cast<const u16*>(wbase + P.fwGlistOff);
             for (int e = lane; e < nKeep; e += 32) {
-                const int ent = plist[e], py = ent >> 8, px = ent & 0xFF;
+                const int ent = kept[e], py = ent >> 8, px = ent & 0xFF;
                 const int s = score[(py + 1) * SP + px + 2];
                 if (base + e < L.candCap && s >= T)
                     out[base + e] = make_uint2((u32)(iniX + 3 + px) | ((u32)(iniY + 3 + py) << 16), ((u32)s << 24) | (u32)c);
             }
+        }
+        __syncwarp();
+        // leave the score map clean: the corners of the last pass are a superset of every entry this cell wrote (a minThFAST retry
+        // re-scores the iniThFAST corners)
+        for (int e = lane; e < nc; e += 32) {
+            const int ent = plist[e];
+            sts8(scoreS + (u32)(((ent >> 8) + 1) * SP + (ent & 0xFF) + 2), 0u);
         }
         __syncwarp();
     }
@@ -1476,8 +1507,10 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
                     if (iniX >= L.maxBX - 6) continue;
                     const int tw = std::min(iniX + L.wCell + 6, L.maxBX) - iniX;
                     if (tw - 6 <= 0 || th - 6 <= 0) continue;        // cv::FAST on a ROI < 7 px finds nothing
+                    // .w: 2^32 / ng + 1 with ng = 4-pixel groups per row of the cell's domain as k_fast_tma lays them out (task -> row, group)
+                    const int offq = (((iniX + ORBX_OX) & 15) + 3) & 3, ng = (offq + (tw - 6) + 3) >> 2;
                     cells.push_back(make_uint4((unsigned)iniX | ((unsigned)iniY << 16), (unsigned)tw | ((unsigned)th << 8) | ((unsigned)l << 16),
-                                               (unsigned)(i * L.nCols + j), 0u));
+                                               (unsigned)(i * L.nCols + j), ng > 1 ? 0xFFFFFFFFu / (unsigned)ng + 1u : 0u));
                 }
             }
             if (ex->candPerCell > 0) bound = std::min<long>(bound, (long)L.nCols * L.nRows * ex->candPerCell);
@@ -1770,12 +1803,13 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         if (ex->nCells > 0 && ex->useTma) {
             const int items = ex->nCells * nf;
             const int grid = std::min(ex->fwGrid, orb_div_up(items, ORBX_FW_WARPS));
+            const unsigned long long inv40 = ((1ull << 40) + (unsigned long long)ex->nCells - 1) / (unsigned long long)ex->nCells;
             if (P.fwBoxW == 64 && ex->fastConst)
                 k_fast_tma<64, ORBX_FAST_SPP><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
-                                                                                          ex->d_candCount, ex->d_status, ex->d_workCounter);
+                                                                                          ex->d_candCount, ex->d_status, ex->d_workCounter, inv40);
             else
                 k_fast_tma<0, 0><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
-                                                                             ex->d_candCount, ex->d_status, ex->d_workCounter);
+                                                                             ex->d_candCount, ex->d_status, ex->d_workCounter, inv40);
         } else if (ex->nCells > 0) {
             if (ex->fastConst)
                 k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_cells, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
