@@ -467,7 +467,7 @@ def main():
         d_db = torch.from_numpy(db).cuda()
         q0 = (rank * nq) % ndb
         q1 = min(q0 + nq, ndb)
-        cnt = torch.zeros(((q1 - q0) * ndb + 1) // 2 * 2, dtype=torch.int16, device="cuda")
+        cnt = torch.zeros(((q1 - q0) * ndb + 1) // 2 * 2, dtype=torch.uint16, device="cuda")
 
         from orbslam_mapsave_b200.sharding import gather_match_tables
 

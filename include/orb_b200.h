@@ -62,6 +62,10 @@ void orbx_destroy(orbx_extractor* ex);
  * (include/ORBextractor.h:74-88) and exposes mnFeaturesPerLevel (src/ORBextractor.cc:434-445).  Any pointer may be
  * NULL; arrays have nlevels entries. */
 int orbx_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota);
+/* The same tables without a handle (no CUDA device is touched): what the ORBextractor constructor computes (src/ORBextractor.cc:414-445).
+ * Lets the drop-in class answer GetScaleFactors() ... before the first image has fixed the geometry. */
+int orbx_compute_tables(int nfeatures, float scale_factor, int nlevels, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                        int* quota);
 /* Level sizes (src/ORBextractor.cc:1114-1115). */
 int orbx_level_size(const orbx_extractor* ex, int level, int* w, int* h);
 /* Upper bound on keypoints per frame: nfeatures + 3 per level (the octree may overshoot each quota). */
@@ -153,7 +157,8 @@ int orbm_hamming_top2_batch_device(const uint8_t* d_q, const int* d_q_off, const
                                    void* stream);
 /* All-pairs keyframe matching (BASELINE.json config 4): every keyframe holds `per_kf` descriptors; query keyframes
  * [q_begin, q_end) of d_desc are matched against all n_kf keyframes.  d_count[(q-q_begin)*n_kf + k] = number of query
- * descriptors of q whose top-2 against keyframe k passes best <= th_low && best < ratio*second (uint16).
+ * descriptors of q whose top-2 against keyframe k passes best <= th_low && best < ratio*second (uint16; per_kf <= 65535).  d_count must be
+ * 4-byte aligned and hold an EVEN number of entries (round (q_end - q_begin) * n_kf up): the kernel updates it as 32-bit words.
  * If d_best_kf / d_best_dist are non-NULL they receive, per query descriptor, the keyframe (!= q) holding its
  * overall nearest descriptor and that distance.  Asynchronous on `stream`. */
 int orbm_allpairs_device(const uint8_t* d_desc, int n_kf, int per_kf, int q_begin, int q_end, int th_low, float ratio,

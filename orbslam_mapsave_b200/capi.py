@@ -23,7 +23,7 @@ TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
 # every symbol include/orb_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "orb_last_error", "orb_device_count",
-    "orbx_create", "orbx_destroy", "orbx_tables", "orbx_level_size", "orbx_max_keypoints", "orbx_extract",
+    "orbx_create", "orbx_destroy", "orbx_tables", "orbx_compute_tables", "orbx_level_size", "orbx_max_keypoints", "orbx_extract",
     "orbx_extract_batch", "orbx_extract_batch_device", "orbx_check_status", "orbx_get_pyramid_level", "orbx_get_pyramid",
     "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device", "orbx_stereo_matches",
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
@@ -101,6 +101,8 @@ def lib():
     L.orbx_destroy.argtypes = [vp]
     L.orbx_tables.restype = i32
     L.orbx_tables.argtypes = [vp] * 6
+    L.orbx_compute_tables.restype = i32
+    L.orbx_compute_tables.argtypes = [i32, f32, i32, vp, vp, vp, vp, vp]
     L.orbx_level_size.restype = i32
     L.orbx_level_size.argtypes = [vp, i32, vp, vp]
     L.orbx_max_keypoints.restype = i32

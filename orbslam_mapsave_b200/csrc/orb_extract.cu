@@ -1705,6 +1705,34 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     return ORB_OK;
 }
 
+// ORBextractor::ORBextractor, src/ORBextractor.cc:414-445: mvScaleFactor[i] = mvScaleFactor[i-1] * scaleFactor (double product -> float),
+// sigma^2, inverses; per-level quotas as a geometric series, cvRound per level, remainder to the last level
+static void compute_tables(int nfeatures, float scale_factor, int nlevels, float* sf, float* isf, float* s2, float* is2, int* quota) {
+    const double scaleFactor = scale_factor;
+    std::vector<float> f(nlevels), q(nlevels);
+    f[0] = 1.0f; q[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) { f[i] = (float)(f[i - 1] * scaleFactor); q[i] = f[i] * f[i]; }
+    for (int i = 0; i < nlevels; i++) {
+        if (sf) sf[i] = f[i];
+        if (s2) s2[i] = q[i];
+        if (isf) isf[i] = 1.0f / f[i];
+        if (is2) is2[i] = 1.0f / q[i];
+    }
+    if (!quota) return;
+    float factor = (float)(1.0f / scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) { quota[l] = h_cvRoundF(nDesired); sum += quota[l]; nDesired *= factor; }
+    quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+}
+
+extern "C" int orbx_compute_tables(int nfeatures, float scale_factor, int nlevels, float* scale, float* inv_scale, float* sigma2,
+                                   float* inv_sigma2, int* quota) {
+    ORB_REQUIRE(nfeatures > 0 && nlevels >= 1 && nlevels <= ORBX_MAX_LEVELS && scale_factor > 1.f, ORB_ERR_ARG, "bad extractor parameters");
+    compute_tables(nfeatures, scale_factor, nlevels, scale, inv_scale, sigma2, inv_sigma2, quota);
+    return ORB_OK;
+}
+
 extern "C" int orbx_create(orbx_extractor** out, int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
                            int width, int height, int max_batch, int device) {
     ORB_REQUIRE(out, ORB_ERR_ARG, "out is NULL");
@@ -1720,14 +1748,7 @@ extern "C" int orbx_create(orbx_extractor** out, int nfeatures, float scale_fact
     if (const char* e = getenv("ORBX_CAND_PER_CELL")) ex->candPerCell = std::max(8, atoi(e));
     // scale tables and per-level quotas (ORBextractor.cc:414-445)
     ex->sf.resize(nlevels); ex->s2.resize(nlevels); ex->isf.resize(nlevels); ex->is2.resize(nlevels); ex->quota.resize(nlevels);
-    ex->sf[0] = 1.0f; ex->s2[0] = 1.0f;
-    for (int i = 1; i < nlevels; i++) { ex->sf[i] = (float)(ex->sf[i - 1] * ex->scaleFactor); ex->s2[i] = ex->sf[i] * ex->sf[i]; }
-    for (int i = 0; i < nlevels; i++) { ex->isf[i] = 1.0f / ex->sf[i]; ex->is2[i] = 1.0f / ex->s2[i]; }
-    float factor = (float)(1.0f / ex->scaleFactor);
-    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
-    int sum = 0;
-    for (int l = 0; l < nlevels - 1; l++) { ex->quota[l] = h_cvRoundF(nDesired); sum += ex->quota[l]; nDesired *= factor; }
-    ex->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    compute_tables(nfeatures, scale_factor, nlevels, ex->sf.data(), ex->isf.data(), ex->s2.data(), ex->is2.data(), ex->quota.data());
     int rc = make_plan(ex, width, height);
     if (rc == ORB_OK && cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) != cudaSuccess) {
         orb_set_error("cudaStreamCreate failed"); rc = ORB_ERR_CUDA;

@@ -568,6 +568,8 @@ extern "C" int orbm_allpairs_device(const uint8_t* d_desc, int n_kf, int per_kf,
     ORB_REQUIRE(n_kf <= 65535 && (q_end - q_begin) <= 65535 && n_kf <= (int)KEY_IDX_MASK, ORB_ERR_ARG, "too many keyframes per call");
     ORB_REQUIRE((d_best_kf == nullptr) == (d_best_dist == nullptr), ORB_ERR_ARG, "d_best_kf and d_best_dist go together");
     ORB_REQUIRE(((uintptr_t)d_count & 3) == 0, ORB_ERR_ARG, "d_count must be 4-byte aligned");
+    // two 16-bit counts share one 32-bit word that the kernel updates with atomicAdd: a count can reach per_kf
+    ORB_REQUIRE(per_kf <= 65535, ORB_ERR_ARG, "per_kf = %d: the match counts are 16 bit", per_kf);
     cudaStream_t st = (cudaStream_t)stream;
     const int nq = q_end - q_begin;
     if (nq == 0) return ORB_OK;

@@ -57,6 +57,14 @@ struct Arena {
     cudaStream_t stream = nullptr;
     // `bytes`: inputs + outputs (taken first; mirrored in pinned host memory when small); `scratch`: device-only work space
     // taken after them (candidate lists etc.), never mirrored.
+    ~Arena() {                                               // thread exit: give the device / pinned memory and the stream back
+        if (device < 0) return;
+        if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }   // (the runtime may already be gone at process exit)
+        if (base) cudaFree(base);
+        if (hbase) cudaFreeHost(hbase);
+        if (stream) cudaStreamDestroy(stream);
+        cudaGetLastError();
+    }
     int ensure(int dev, size_t bytes, size_t scratch = 0) {
         if (device != dev) {
             if (base) { cudaSetDevice(device); cudaFree(base); base = nullptr; cap = 0; }
@@ -82,6 +90,7 @@ struct Arena {
         }
         staged = hbase != nullptr && bytes <= hcap && bytes <= (2u << 20);
         used = 0; inEnd = 0;
+        pend.clear();                                        // a call that failed between fetch() and finish() leaves nothing behind
         return ORB_OK;
     }
     template <typename T>

@@ -61,8 +61,11 @@ class ORBextractor:
         return float(np.float32(self.scaleFactor))
 
     def _need_tables(self):
-        if self._tables is None:
-            self._plan(640, 480)       # tables do not depend on the image size
+        if self._tables is None:       # the constructor's tables depend on the parameters only: no handle, no device
+            n = self.nlevels
+            t = [np.zeros(n, np.float32) for _ in range(4)] + [np.zeros(n, np.int32)]
+            capi.check(capi.lib().orbx_compute_tables(self.nfeatures, self.scaleFactor, n, *[capi._p(a) for a in t]))
+            self._tables = t
         return self._tables
 
     def GetScaleFactors(self):

@@ -15,9 +15,13 @@ static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "cv::KeyPoint must 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST) {
     mvImagePyramid.resize(nlevels);
-    // The scale tables do not depend on the image size: plan once for a nominal VGA frame to obtain them
-    // (reference: computed in the constructor, ORBextractor.cc:414-445); operator() re-plans for the real size.
-    Plan(640, 480);
+    // The tables of the reference's constructor (ORBextractor.cc:414-445) depend on the parameters only: no device memory, no plan.
+    // The workspace is planned by the first operator() call, for the size of the image it is given.
+    mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+    mnFeaturesPerLevel.resize(nlevels);
+    mLastStatus = orbx_compute_tables(nfeatures, (float)scaleFactor, nlevels, mvScaleFactor.data(), mvInvScaleFactor.data(),
+                                      mvLevelSigma2.data(), mvInvLevelSigma2.data(), mnFeaturesPerLevel.data());
+    if (mLastStatus != ORB_OK) std::fprintf(stderr, "ORBextractor: %s\n", orb_last_error());
 }
 
 ORBextractor::~ORBextractor() { orbx_destroy(mHandle); }
@@ -79,11 +83,7 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::
         }
         if (orbx_get_pyramid(mHandle, 0, 1, ptrs.data(), strides.data()) == ORB_OK)
             for (int l = 0; l < nlevels; l++) {
-#if defined(OPENCV_CORE_HPP) || defined(__OPENCV_CORE_HPP__)
-                mvImagePyramid[l] = whole[l](cv::Rect(19, 19, ws[l], hs[l]));
-#else
-                mvImagePyramid[l] = whole[l].roi(19, 19, ws[l], hs[l]);
-#endif
+                mvImagePyramid[l] = whole[l].rowRange(19, 19 + hs[l]).colRange(19, 19 + ws[l]);      // the ROI inside the bordered buffer
             }
     }
 }

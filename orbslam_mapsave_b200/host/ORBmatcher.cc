@@ -28,9 +28,23 @@ static void report(int rc) {
 }
 
 int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
-    int d = -1;
+    int d = 257;                 // on a CUDA error: larger than any Hamming distance, so that no caller reads the failure as a match
     report(orbm_descriptor_distance(a.ptr<unsigned char>(), b.ptr<unsigned char>(), 1, &d, g_device));
-    return d;
+    return g_status == ORB_OK ? d : 257;
+}
+
+int ORBmatcher::DescriptorDistances(const cv::Mat& A, const cv::Mat& B, int* out) {
+    const int n = A.rows < B.rows ? A.rows : B.rows;
+    if (n <= 0) return 0;
+    if (A.isContinuous() && B.isContinuous()) {
+        report(orbm_descriptor_distance(A.ptr<unsigned char>(), B.ptr<unsigned char>(), n, out, g_device));
+    } else {                     // row views with a stride: gather
+        std::vector<unsigned char> a((size_t)n * 32), b((size_t)n * 32);
+        for (int i = 0; i < n; i++) { std::memcpy(&a[32 * (size_t)i], A.ptr<unsigned char>(i), 32); std::memcpy(&b[32 * (size_t)i], B.ptr<unsigned char>(i), 32); }
+        report(orbm_descriptor_distance(a.data(), b.data(), n, out, g_device));
+    }
+    if (g_status != ORB_OK) for (int i = 0; i < n; i++) out[i] = 257;
+    return n;
 }
 
 namespace {

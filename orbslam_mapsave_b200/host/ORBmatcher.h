@@ -19,7 +19,12 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);                                // reference :41
 
     // Hamming distance between two ORB descriptors (reference :44, src/ORBmatcher.cc:1650-1666)
+    // src/ORBmatcher.cc:1650-1666.  NOTE: one call is one device round trip (two 32-byte uploads, a kernel, a 4-byte download): right for
+    // the odd stray call, wrong inside a loop — loops over descriptor pairs belong in DescriptorDistances below (one round trip for all
+    // pairs) or in the searches of this class.  Returns 257 (more than any distance) if the device call fails; see LastStatus().
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    // Batched form (not in the reference): out[i] = distance(A.row(i), B.row(i)) for i < min(A.rows, B.rows); returns that count.
+    static int DescriptorDistances(const cv::Mat& A, const cv::Mat& B, int* out);
 
     // Brute force constrained to ORB that belong to the same vocabulary node (reference :65-66)
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);

@@ -16,7 +16,8 @@ def shard_range(n, rank, world):
 
 
 def gather_match_tables(local_counts, n_queries, rank=None, world=None):
-    """local_counts: int16/int32 tensor [q_local, n_db] for this rank's query shard = shard_range(n_queries, rank, world).
+    """local_counts: uint16 / int16 / int32 tensor [q_local, n_db] for this rank's query shard = shard_range(n_queries, rank, world)
+    (the kernel's counts are UNSIGNED 16 bit: view them as torch.uint16, an int16 view turns counts above 32767 negative).
     Returns the full [n_queries, n_db] table on every rank.  Uses the default process group (NCCL on GPUs, gloo on CPU)."""
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1

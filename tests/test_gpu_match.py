@@ -44,6 +44,42 @@ def test_hamming_top2_vs_oracle(nq, ndb):
         assert bi[0] == 1 and bd[0] == 0 and sd[0] == 0
 
 
+def _ratio_edge_scene():
+    """Constructed ties of the ratio test: per vocabulary node one keyframe feature and two frame features at Hamming
+    distances (best, second); `float(best) < nnratio * float(second)` (src/ORBmatcher.cc:231-233) is an equality for
+    (25, 50) at ratio 0.5 and for (30, 40) at ratio 0.75, true one bit below and false one bit above; TH_LOW = 50 is hit exactly."""
+    rng = np.random.default_rng(77)
+    cases = [(25, 50), (24, 50), (26, 50), (30, 40), (29, 40), (31, 40), (50, 100), (49, 99), (50, 101), (0, 0), (0, 1), (10, 10)]
+    n1 = len(cases)
+    d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    d2 = np.zeros((2 * n1, 32), np.uint8)
+    for i, (b, s2) in enumerate(cases):
+        d2[2 * i] = _flip(d1[i], b, rng)
+        # the second candidate at distance s2 from d1[i]: flip s2 bits chosen independently of the first candidate's
+        d2[2 * i + 1] = _flip(d1[i], s2, rng)
+    node1 = np.arange(n1) * 2 + 3
+    node2 = np.repeat(node1, 2)
+    ang1 = np.full(n1, 10.0, np.float32)
+    return dict(d1=d1, d2=d2, node1=node1, node2=node2, ang1=ang1, ang2=np.full(2 * n1, 10.0, np.float32), flag1=np.ones(n1, np.uint8),
+                flag2=np.ones(2 * n1, np.uint8), cases=cases)
+
+
+@pytest.mark.parametrize("ratio", [0.5, 0.75, 0.6, 1.0])
+def test_ratio_test_equality_edge(ratio):
+    s = _ratio_edge_scene()
+    f1, f2 = orc.FeatVec(s["node1"]), orc.FeatVec(s["node2"])
+    on, om = orc.search_bow_kf_f(s["d1"], s["flag1"], s["ang1"], f1, s["d2"], s["ang2"], f2, ratio, False)
+    k = orb.View(s["d1"], orb.FeatureVector(s["node1"]), s["ang1"], flag=s["flag1"])
+    f = orb.View(s["d2"], orb.FeatureVector(s["node2"]), s["ang2"])
+    gn, gm = orb.ORBmatcher(ratio, False).SearchByBoW(k, f)
+    assert gn == on and np.array_equal(gm, om)
+    # the expected outcome, from the definition: accepted iff best <= 50 and float32(best) < float32(ratio) * float32(second)
+    for i, (b, s2) in enumerate(s["cases"]):
+        lo, hi = min(b, s2), max(b, s2)
+        want = lo <= 50 and np.float32(lo) < np.float32(ratio) * np.float32(hi)
+        assert (om[2 * i] == i or om[2 * i + 1] == i) == bool(want), (i, b, s2, ratio)
+
+
 def _scene(n1, n2, seed, nnodes=40, tri=False):
     rng = np.random.default_rng(seed)
     d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)

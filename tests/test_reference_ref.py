@@ -77,6 +77,26 @@ def test_reference_search_by_bow_kf_frame_equals_oracle(n1, n2, seed, ratio, ori
 
 
 @matcher
+@pytest.mark.parametrize("ratio", [0.5, 0.75, 0.6, 1.0])
+def test_reference_ratio_test_equality_edge(ratio):
+    """Constructed equalities of `float(best) < nnratio * float(second)` and of `best <= TH_LOW` (src/ORBmatcher.cc:231-233): the
+    reference's own code, the oracle and the definition agree case by case."""
+    import test_gpu_match as tgm
+    s = tgm._ratio_edge_scene()
+    f1, f2 = orc.FeatVec(s["node1"]), orc.FeatVec(s["node2"])
+    on, om = orc.search_bow_kf_f(s["d1"], s["flag1"], s["ang1"], f1, s["d2"], s["ang2"], f2, ratio, False)
+    rn, rm = ref_py.ref_search_bow_kf_f(s["d1"], s["flag1"], s["ang1"], f1, s["d2"], s["ang2"], f2, ratio, False)
+    assert rn == on and np.array_equal(rm, om)
+    hits = 0
+    for i, (b, s2) in enumerate(s["cases"]):
+        lo, hi = min(b, s2), max(b, s2)
+        want = lo <= 50 and np.float32(lo) < np.float32(ratio) * np.float32(hi)
+        assert (rm[2 * i] == i or rm[2 * i + 1] == i) == bool(want), (i, b, s2, ratio)
+        hits += bool(want)
+    assert 0 < hits < len(s["cases"]) or ratio == 1.0
+
+
+@matcher
 @pytest.mark.parametrize("n1,n2,seed", [(300, 280, 10), (2000, 2000, 11), (700, 64, 12), (0, 0, 13)])
 @pytest.mark.parametrize("ratio,ori", [(0.75, True), (0.6, False)])
 def test_reference_search_by_bow_kf_kf_equals_oracle(n1, n2, seed, ratio, ori):

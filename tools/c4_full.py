@@ -44,7 +44,7 @@ def main():
     del fb
     q0, q1 = shard_range(K, rank, world)
     nq = q1 - q0
-    cnt = torch.zeros((nq * K + 1) // 2 * 2, dtype=torch.int16, device="cuda")
+    cnt = torch.zeros((nq * K + 1) // 2 * 2, dtype=torch.uint16, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     lib = capi.lib()
     torch.cuda.synchronize()
