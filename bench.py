@@ -122,6 +122,33 @@ def bind_to_gpu_numa_node(torch, local_rank):
     return None
 
 
+def load_ncu_constants():
+    """profiles/ncu_constants.json (tools/ncu_summary.py --json): per-launch DRAM bytes / executed warp instructions of the kernels, taken
+    from a committed ncu capture, with the SHA-256 of the CUDA sources they were measured on.  Returns (captures or None, info): the
+    constants are dropped (info["stale"] = True) when the sources have changed since."""
+    path = os.path.join(ROOT, "profiles", "ncu_constants.json")
+    try:
+        doc = json.load(open(path))
+    except (OSError, ValueError):
+        return None, {"stale": True, "reason": "profiles/ncu_constants.json missing"}
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from ncu_summary import source_sha
+    sha = source_sha()
+    if sha != doc.get("source_sha256"):
+        return None, {"stale": True, "reason": "csrc changed since the capture", "captured_sha256": doc.get("source_sha256"), "current_sha256": sha}
+    return doc["captures"], {"stale": False, "source_sha256": sha}
+
+
+def ncu_kernel(captures, label, name):
+    """(kernel record, units per launch) of the first launch whose name starts with `name` in capture `label`."""
+    if not captures or label not in captures:
+        return None, None
+    for k in captures[label]["kernels"]:
+        if k["kernel"].startswith(name):
+            return k, captures[label]["units_per_launch"]
+    return None, None
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -299,7 +326,20 @@ def main():
             out["C3"] = blk
             del ctx
         if c5_frames is not None:
-            blk, ctx = bc.batch_config("C5", torch, orb, capi, local_rank, hbm, c5_frames, 8, args.c5_batch, min(args.steps, 5), stream)
+            caps, info = load_ncu_constants()
+            c5ncu = dict(info)
+            if caps and "c5_pass" in caps:                             # per-frame DRAM traffic / warp instructions of the 4K pass's kernels
+                u = caps["c5_pass"]["units_per_launch"]
+                agg = {}
+                for k in caps["c5_pass"]["kernels"]:
+                    a = agg.setdefault(k["kernel"].split("<")[0], {"dram_bytes_per_frame": 0.0, "warp_inst_per_frame": 0.0, "launches": 0})
+                    a["dram_bytes_per_frame"] += k["dram_bytes"] / u
+                    a["warp_inst_per_frame"] += (k["warp_inst"] or 0) / u
+                    a["launches"] += 1
+                c5ncu["kernels"] = agg
+                c5ncu["dram_bytes_per_frame"] = sum(a["dram_bytes_per_frame"] for a in agg.values())
+            blk, ctx = bc.batch_config("C5", torch, orb, capi, local_rank, hbm, c5_frames, 8, args.c5_batch, min(args.steps, 5), stream,
+                                       ncu_constants=c5ncu)
             out["C5"] = blk
             del ctx
         torch.cuda.empty_cache()
@@ -388,20 +428,25 @@ def main():
     dom_launches = {"pyramid": NLEVELS, "fast": 1, "octree": 1, "blur": 1, "describe": 1}[dom] * passes
     dom_launch_s = stage_s[dom] / dom_launches
     achieved = stage_bytes[dom] * nF / stage_s[dom] / 1e9
-    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize", "fast": "k_fast_tma", "octree": "k_octree", "blur": "k_blur",
-                                           "describe": "k_describe"}[dom],
+    kname = {"pyramid": "k_resize", "fast": "k_fast_tma", "octree": "k_octree", "blur": "k_blur", "describe": "k_describe"}[dom]
+    captures, ncu_info = load_ncu_constants()
+    krec, kunits = ncu_kernel(captures, "c2_pass", kname)
+    sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    traffic = issue = None
+    if krec and dom != "pyramid":                                     # (the pyramid stage is several launches: no single-kernel constants)
+        scale = args.chunk / kunits                                    # the capture's launch processed `kunits` frames
+        traffic = krec["dram_bytes"] * scale
+        winst = krec["warp_inst"] * scale
+        # what actually bounds these kernels: warp-instruction issue, against 148 SMs x 4 schedulers x the SM clock seen in this run
+        issue = {"warp_inst_per_launch": winst, "achieved_ginst_s": winst / dom_launch_s / 1e9, "peak_ginst_s": 148 * 4 * sm_hz / 1e9,
+                 "frac": winst / dom_launch_s / (148 * 4 * sm_hz), "issue_pct_under_ncu": krec["issue_pct"]}
+    roofline = {"bound": "hbm", "kernel": {"pyramid": "k_level0+k_resize"}.get(dom, kname),
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch (profiles/r1q_all_kernels_ncu_full.md)
-                "traffic": ({"fast": 285.5e6, "describe": 581.7e6, "blur": 523.2e6, "octree": 15.9e6}.get(dom, 0) * args.chunk / 256) or None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed capture (profiles/ncu_constants.json)
+                "traffic": traffic, "ncu_constants": ncu_info,
                 "peak_source": peak_src, "avg_launch_ms": dom_launch_s * 1e3, "algorithmic_bytes_per_frame": stage_bytes[dom],
                 "stage_ms_per_step": {k: v * 1e3 for k, v in stage_s.items()},
-                # what actually bounds it: warp-instruction issue.  540.3 M warp-instructions per 256-frame k_fast_tma launch (ncu,
-                # profiles/r1q_all_kernels_ncu_full.md) against 148 SMs x 4 schedulers x the SM clock seen in this run
-                "issue": ({"warp_inst_per_launch": 540.3e6 * args.chunk / 256,
-                           "achieved_ginst_s": 540.3e6 * args.chunk / 256 / dom_launch_s / 1e9,
-                           "peak_ginst_s": 148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                           "frac": 540.3e6 * args.chunk / 256 / dom_launch_s / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6)}
-                          if dom == "fast" else None),
+                "issue": issue,
                 "step_hbm_frac": (B_FRAME * nF / (secs / args.steps) / 1e9) / hbm_peak,
                 "note": "640x480 pyramids are L2-resident and this stage is integer-issue bound, not HBM bound (SURVEY.md §7)"}
 
@@ -486,12 +531,13 @@ def main():
                                "collective": "all_gather(match-count table)" if world > 1 else "none"},
                     "roofline": {"bound": "popc", "achieved": pairs / msecs * 8 / 1e12, "peak": popc / 1e12 * world, "unit": "TPOPC/s",
                                  "frac": pairs / msecs * 8 / (popc * world), "peak_source": "orbm_popc_peak microbenchmark, this run",
-                                 "note": "achieved = ALGORITHMIC POPC (8 per pair, SURVEY 8d); the kernel EXECUTES 4 POPC + 18.5 ALU-pipe ops "
-                                         "per pair (carry-save compression of the XOR words), so frac > 1 is expected",
-                                 "executed": {"popc_per_pair": 4, "alu_ops_per_pair": 18.5,
-                                              "popc_pipe_frac": pairs / msecs * 4 / (popc * world),
-                                              "alu_pipe_frac": pairs / msecs * 18.5 / (148 * 64 * clk * world),
-                                              "alu_peak_source": "148 SMs x 64 lanes/clk (B300_MICROARCH: alu pipe rt_SMSP=2) x SM clock"}}}
+                                 "note": "achieved = ALGORITHMIC POPC (8 per pair, SURVEY 8d); the kernel EXECUTES 4 POPC per pair (carry-save "
+                                         "compression of the XOR words, orb_match.cu), so frac > 1 is expected",
+                                 "executed": {"popc_per_pair": 4, "popc_pipe_frac": pairs / msecs * 4 / (popc * world)}}}
+        mrec, munits = ncu_kernel(load_ncu_constants()[0], "matching", "k_allpairs")
+        if mrec:                                                       # pipe shares as ncu measured them (committed capture, same sources)
+            matching["roofline"]["executed"].update({"warp_inst_per_pair": mrec["warp_inst"] / munits, "alu_pipe_pct_under_ncu": mrec["alu_pct"],
+                                                     "xu_pipe_pct_under_ncu": mrec["xu_pct"], "issue_pct_under_ncu": mrec["issue_pct"]})
         if rank == 0 and not args.no_cpu:
             from oracle import orb_oracle_py as orc
             thr = host_threads()

@@ -25,7 +25,73 @@ WANT = [
 ]
 
 
+def source_sha():
+    """SHA-256 over the CUDA sources the constants were measured on (bench.py recomputes it and flags stale constants)."""
+    import glob
+    import hashlib
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "orbslam_mapsave_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(root, "*.cu")) + glob.glob(os.path.join(root, "*.cuh")) + glob.glob(os.path.join(root, "*.inc"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def emit_json(rep, out_path, units, label, command):
+    """profiles/ncu_constants.json: per kernel of the capture the per-launch DRAM bytes, executed warp instructions and pipe shares,
+    with the number of work units (frames / descriptor pairs) one launch processed and the SHA of the sources.  Several captures
+    (extractor pass, matching) are merged under their labels."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    H, U = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(H)}
+
+    def val(r, m, scale=None):
+        if m not in idx:
+            return None
+        try:
+            x = float(r[idx[m]].replace(",", ""))
+        except ValueError:
+            return None
+        u = U[idx[m]]
+        if scale == "bytes":
+            x *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        if scale == "us":
+            x *= {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(u, 1)
+        return x
+    kernels = []
+    for r in rows[2:]:
+        if len(r) < len(H):
+            continue
+        rd, wr = val(r, "dram__bytes_read.sum", "bytes"), val(r, "dram__bytes_write.sum", "bytes")
+        kernels.append({"kernel": r[idx["Kernel Name"]].split("(")[0].replace("void ", ""), "grid": r[idx["Grid Size"]],
+                        "time_us_under_ncu": val(r, "gpu__time_duration.sum", "us"),
+                        "dram_bytes": (rd or 0) + (wr or 0), "warp_inst": val(r, "smsp__inst_executed.sum"),
+                        "issue_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                        "alu_pct": val(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                        "xu_pct": val(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                        "alu_inst": val(r, "sm__inst_executed_pipe_alu.sum"), "xu_inst": val(r, "sm__inst_executed_pipe_xu.sum"),
+                        "dram_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")})
+    doc = {}
+    if os.path.exists(out_path):
+        try:
+            doc = json.load(open(out_path))
+        except ValueError:
+            doc = {}
+    doc["source_sha256"] = source_sha()
+    doc.setdefault("captures", {})[label] = {"report": os.path.basename(rep), "command": command, "units_per_launch": units, "kernels": kernels}
+    json.dump(doc, open(out_path, "w"), indent=1)
+    print(f"{out_path}: {len(kernels)} kernels under '{label}', sha {doc['source_sha256'][:12]}")
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "--json":
+        # ncu_summary.py --json out.json report.ncu-rep label units_per_launch "command line of the capture"
+        emit_json(sys.argv[3], sys.argv[2], float(sys.argv[5]), sys.argv[4], sys.argv[6] if len(sys.argv) > 6 else "")
+        return
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
