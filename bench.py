@@ -616,6 +616,44 @@ def main():
         t_st, (u_r, _) = lat(lambda: exL.ComputeStereoMatches(exR, kL, dL, kR, dR, 40.0, 0.08))
         tracking["compute_stereo_matches"] = {"ms_per_call": 1e3 * t_st, "left_keypoints": int(len(kL)), "matched": int((u_r >= 0).sum()),
                                               "note": "640x480, on the device-resident pyramids of two extractor handles"}
+        # batched node-constrained searches: one frame against 10 candidate keyframes (Tracking::Relocalization's loop,
+        # src/Tracking.cc:1621-1643) and one keyframe against 20 neighbours (LocalMapping::CreateNewMapPoints, src/LocalMapping.cc:215-268),
+        # each as ONE call against the same work as a loop of single calls
+        nodes_of = lambda m: rng.integers(0, 100, m) * 7 + 3
+
+        def mk(m, nodes=None):
+            nodes = nodes_of(m) if nodes is None else nodes
+            v = orb.View(rng.integers(0, 256, (m, 32), dtype=np.uint8), orb.FeatureVector(nodes), rng.uniform(0, 360, m).astype(np.float32),
+                         flag=(rng.random(m) < 0.7).astype(np.uint8), x=rng.uniform(0, 640, m).astype(np.float32),
+                         y=rng.uniform(0, 480, m).astype(np.float32), octave=rng.integers(0, 8, m).astype(np.int32),
+                         uright=np.full(m, -1, np.float32))
+            v.nodes = nodes
+            return v
+        frame_v = mk(n)
+        cands = []
+        for _ in range(20):                                            # candidates share a third of the frame's features (true matches)
+            nd, src = nodes_of(n), rng.choice(n, n // 3, replace=False)
+            nd[src] = frame_v.nodes[src]
+            c_ = mk(n, nd)
+            c_.desc[src] = frame_v.desc[src] ^ np.packbits(rng.random((len(src), 32, 8)) < 0.04, axis=2).reshape(len(src), 32)
+            cands.append(c_)
+        mb_ = orb.ORBmatcher(0.75, True, device=local_rank)
+        t_b, (nmb, _) = lat(lambda: mb_.SearchByBoWBatch(frame_v, cands[:10], kf_kf=False), 20)
+        t_l, _ = lat(lambda: [mb_.SearchByBoW(c_, frame_v) for c_ in cands[:10]], 5)
+        cnt_f = np.bincount(frame_v.nodes, minlength=1024).astype(np.float64)
+        pairs_bow = float(sum(np.dot(np.bincount(c_.nodes[c_.flag == 1], minlength=1024).astype(np.float64), cnt_f) for c_ in cands[:10]))
+        tracking["search_by_bow_batch"] = {"candidates": 10, "features": n, "ms_per_batch_call": 1e3 * t_b, "ms_looping_single_calls": 1e3 * t_l,
+                                           "searches_per_s": 10 / t_b, "descriptor_pairs_per_s": pairs_bow / t_b, "matches": int(nmb.sum()),
+                                           "note": "one frame against 10 candidate keyframes, ~100 vocabulary nodes: 2 launches, 1 upload, 1 download"}
+        F12s = (rng.normal(0, 1, (20, 3, 3)) * np.array([[1e-6, 1e-5, 1e-3], [1e-5, 1e-6, 1e-3], [1e-3, 1e-3, 1e-1]])).astype(np.float32)
+        eps = rng.uniform(100, 500, (20, 2)).astype(np.float32)
+        sig = (sc * sc * 5000).astype(np.float32)
+        for c_ in cands + [frame_v]:
+            c_.flag = (rng.random(n) < 0.3).astype(np.uint8)           # triangulation looks at features WITHOUT map points
+        t_tb, (nmt, _) = lat(lambda: mb_.SearchForTriangulationBatch(frame_v, cands, F12s, eps, [sc] * 20, [sig] * 20, False), 10)
+        t_tl, _ = lat(lambda: [mb_.SearchForTriangulation(frame_v, c_, F12s[i], eps[i, 0], eps[i, 1], sc, sig, False) for i, c_ in enumerate(cands)], 3)
+        tracking["search_for_triangulation_batch"] = {"neighbours": 20, "features": n, "ms_per_batch_call": 1e3 * t_tb,
+                                                      "ms_looping_single_calls": 1e3 * t_tl, "searches_per_s": 20 / t_tb, "matches": int(nmt.sum())}
         if not args.no_cpu:
             from oracle import orb_oracle_py as orc
             og = orc.Grid(dsc, x, y, octv, sc, (0.0, 0.0, 640.0, 480.0), angle=ang, uright=ur, blocked=np.zeros(n, np.uint8))

@@ -205,6 +205,25 @@ int orbm_search_for_triangulation(const orbm_view* kf1, const orbm_view* kf2, co
                                   const float* scale_factors2, const float* level_sigma2_2, int n_levels2,
                                   int only_stereo, int check_orientation,
                                   int* pairs_out, int* n_pairs, int* n_matches, int device);
+/* Batched forms of the node-constrained searches (not in the reference, which calls them in loops): one view against n_others views
+ * in ONE call — two kernel launches for the whole batch (grid = nodes x candidates), one upload, one download.  Results are identical to
+ * calling the single-pair entry points in a loop.
+ * orbm_search_by_bow_batch:
+ *   mode 0: SearchByBoW(KeyFrame* others[i], Frame& anchor) for every i — the candidate loop of Tracking::Relocalization
+ *           (src/Tracking.cc:1621-1643); match_out + i * anchor->n = match21 of candidate i;
+ *   mode 1: SearchByBoW(KeyFrame* anchor, KeyFrame* others[i]) — LoopClosing::ComputeSim3 (src/LoopClosing.cc:240-266);
+ *           match_out + i * anchor->n = match12 of candidate i.
+ *   n_matches[n_others] = the reference's return values.
+ * orbm_search_for_triangulation_batch: SearchForTriangulation(anchor, others[i], F12[i], ...) for every i — the loop over up to 20
+ *   neighbours of LocalMapping::CreateNewMapPoints (src/LocalMapping.cc:215-268).  F12: n_others x 9; epipoles: n_others x 2 (ex, ey);
+ *   scale_factors2 / level_sigma2_2: n_others x n_levels2; pairs_out + 2 * i * anchor->n = the (idx1, idx2) pairs of neighbour i,
+ *   n_pairs[i] of them; n_matches[i] = the reference's return value. */
+int orbm_search_by_bow_batch(const orbm_view* anchor, const orbm_view* others, int n_others, int mode, float nnratio,
+                             int check_orientation, int* match_out, int* n_matches, int device);
+int orbm_search_for_triangulation_batch(const orbm_view* anchor, const orbm_view* others, int n_others, const float* F12,
+                                        const float* epipoles, const float* scale_factors2, const float* level_sigma2_2, int n_levels2,
+                                        int only_stereo, int check_orientation, int* pairs_out, int* n_pairs, int* n_matches, int device);
+
 /* Replaces ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1604-1645) on bin sizes; runs on the device as part of the
  * searches above; this entry exposes it for tests.  ind[3]. */
 int orbm_three_maxima(const int* histo, int n_bins, int* ind, int device);

@@ -28,6 +28,7 @@ SYMBOLS = [
     "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device", "orbx_stereo_matches",
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
+    "orbm_search_by_bow_batch", "orbm_search_for_triangulation_batch",
     "orbm_popc_peak", "orbm_distinctive_descriptors",
     "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_for_initialization", "orbm_search_windows", "orbm_search_windows_best",
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
@@ -144,6 +145,10 @@ def lib():
     L.orbm_search_for_triangulation.restype = i32
     L.orbm_search_for_triangulation.argtypes = [C.POINTER(ViewC), C.POINTER(ViewC), vp, f32, f32, vp, vp, i32, i32, i32,
                                                 vp, vp, vp, i32]
+    L.orbm_search_by_bow_batch.restype = i32
+    L.orbm_search_by_bow_batch.argtypes = [C.POINTER(ViewC), C.POINTER(ViewC), i32, i32, f32, i32, vp, vp, i32]
+    L.orbm_search_for_triangulation_batch.restype = i32
+    L.orbm_search_for_triangulation_batch.argtypes = [C.POINTER(ViewC), C.POINTER(ViewC), i32, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32]
     L.orbm_three_maxima.restype = i32
     L.orbm_three_maxima.argtypes = [vp, i32, vp, i32]
     L.orbm_popc_peak.restype = i32

@@ -245,10 +245,10 @@ __global__ void k_three_maxima(const int* histo, int L, int* ind) {
 // Scratch (zeroed by the host before the launch): taken2[B.n], hist[HISTO_LENGTH], nmatch[1]; out[] preset to -1.
 #define SB_WARPS 4
 template <bool KFKF>
-__global__ void __launch_bounds__(32 * SB_WARPS) k_search_bow_nodes(DevView A, DevView B, float nnratio, int checkOri,
-                                                                    int* __restrict__ out, int* __restrict__ taken2,
-                                                                    int* __restrict__ binOf, int* __restrict__ hist,
-                                                                    int* __restrict__ nmatch) {
+__device__ __forceinline__ void search_bow_nodes_body(const DevView& A, const DevView& B, float nnratio, int checkOri,
+                                                      int* __restrict__ out, int* __restrict__ taken2,
+                                                      int* __restrict__ binOf, int* __restrict__ hist,
+                                                      int* __restrict__ nmatch) {
     const int lane = threadIdx.x & 31, a = blockIdx.x * SB_WARPS + (threadIdx.x >> 5);
     if (a >= A.nn) return;
     const int b = find_node(B.ids, B.nn, A.ids[a]);
@@ -297,9 +297,25 @@ __global__ void __launch_bounds__(32 * SB_WARPS) k_search_bow_nodes(DevView A, D
     }
     if (lane == 0 && nm) atomicAdd(nmatch, nm);
 }
+template <bool KFKF>
+__global__ void __launch_bounds__(32 * SB_WARPS) k_search_bow_nodes(DevView A, DevView B, float nnratio, int checkOri,
+                                                                    int* __restrict__ out, int* __restrict__ taken2,
+                                                                    int* __restrict__ binOf, int* __restrict__ hist,
+                                                                    int* __restrict__ nmatch) {
+    search_bow_nodes_body<KFKF>(A, B, nnratio, checkOri, out, taken2, binOf, hist, nmatch);
+}
+// Batched form: blockIdx.y = pair of the batch (one keyframe / frame against N candidates, e.g. the candidate loops of
+// Tracking::Relocalization, src/Tracking.cc:1621-1643, and LoopClosing::ComputeSim3, src/LoopClosing.cc:240-266); the pairs are
+// independent searches, so the grid is simply (nodes, pairs) and the whole batch is two launches.
+struct BowJob { DevView A, B; int *out, *taken2, *binOf, *hist, *nmatch; int nOut; };
+template <bool KFKF>
+__global__ void __launch_bounds__(32 * SB_WARPS) k_search_bow_nodes_batch(const BowJob* __restrict__ jobs, float nnratio, int checkOri) {
+    const BowJob& J = jobs[blockIdx.y];
+    search_bow_nodes_body<KFKF>(J.A, J.B, nnratio, checkOri, J.out, J.taken2, J.binOf, J.hist, J.nmatch);
+}
 
-__global__ void __launch_bounds__(256) k_search_bow_finish(int nOut, int checkOri, int* __restrict__ out, const int* __restrict__ binOf,
-                                                           const int* __restrict__ hist, int* __restrict__ nmatch) {
+__device__ __forceinline__ void search_bow_finish_body(int nOut, int checkOri, int* __restrict__ out, const int* __restrict__ binOf,
+                                                       const int* __restrict__ hist, int* __restrict__ nmatch) {
     __shared__ int s_ind[3], s_drop;
     const int tid = threadIdx.x;
     if (!checkOri) return;
@@ -315,6 +331,14 @@ __global__ void __launch_bounds__(256) k_search_bow_finish(int nOut, int checkOr
     __syncthreads();
     if (tid == 0) *nmatch -= s_drop;
 }
+__global__ void __launch_bounds__(256) k_search_bow_finish(int nOut, int checkOri, int* __restrict__ out, const int* __restrict__ binOf,
+                                                           const int* __restrict__ hist, int* __restrict__ nmatch) {
+    search_bow_finish_body(nOut, checkOri, out, binOf, hist, nmatch);
+}
+__global__ void __launch_bounds__(256) k_search_bow_finish_batch(const BowJob* __restrict__ jobs, int checkOri) {
+    const BowJob& J = jobs[blockIdx.x];
+    search_bow_finish_body(J.nOut, checkOri, J.out, J.binOf, J.hist, J.nmatch);
+}
 
 // SearchForTriangulation.  No cross-query coupling (vbMatched2 is never set in the reference, :680,728), so one thread
 // per side-1 CSR slot walks its node's side-2 features serially, which keeps the reference's "last candidate wins a
@@ -323,9 +347,9 @@ __global__ void __launch_bounds__(256) k_search_bow_finish(int nOut, int checkOr
 // Scratch zeroed by the host: hist[HISTO_LENGTH], cnt[2]; m12[] preset to -1.
 struct TriParams { float F[9]; float ex, ey; int onlyStereo, checkOri; };
 
-__global__ void __launch_bounds__(128) k_search_tri_slots(DevView A, DevView B, TriParams tp, const float* __restrict__ sf2,
-                                                          const float* __restrict__ sigma2, int* __restrict__ m12,
-                                                          int* __restrict__ hist, int* __restrict__ cnt) {
+__device__ __forceinline__ void search_tri_slots_body(const DevView& A, const DevView& B, const TriParams& tp, const float* __restrict__ sf2,
+                                                      const float* __restrict__ sigma2, int* __restrict__ m12,
+                                                      int* __restrict__ hist, int* __restrict__ cnt) {
     const int total1 = A.nn > 0 ? A.off[A.nn] : 0;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total1) return;
@@ -372,10 +396,22 @@ __global__ void __launch_bounds__(128) k_search_tri_slots(DevView A, DevView B, 
         if (tp.checkOri) atomicAdd(&hist[rot_bin(A.angle[idx1], B.angle[bestIdx2])], 1);
     }
 }
+__global__ void __launch_bounds__(128) k_search_tri_slots(DevView A, DevView B, TriParams tp, const float* __restrict__ sf2,
+                                                          const float* __restrict__ sigma2, int* __restrict__ m12,
+                                                          int* __restrict__ hist, int* __restrict__ cnt) {
+    search_tri_slots_body(A, B, tp, sf2, sigma2, m12, hist, cnt);
+}
+// Batched form (blockIdx.y = neighbour): LocalMapping::CreateNewMapPoints matches the new keyframe against up to 20 neighbours
+// (src/LocalMapping.cc:215-268), each with its own fundamental matrix and epipole.
+struct TriJob { DevView A, B; TriParams tp; const float *sf2, *sigma2; int *m12, *hist, *pairs, *cnt; };
+__global__ void __launch_bounds__(128) k_search_tri_slots_batch(const TriJob* __restrict__ jobs) {
+    const TriJob& J = jobs[blockIdx.y];
+    search_tri_slots_body(J.A, J.B, J.tp, J.sf2, J.sigma2, J.m12, J.hist, J.cnt);
+}
 
-__global__ void __launch_bounds__(256) k_search_tri_finish(DevView A, DevView B, int checkOri, int* __restrict__ m12,
-                                                           const int* __restrict__ hist, int* __restrict__ pairs,
-                                                           int* __restrict__ cnt) {
+__device__ __forceinline__ void search_tri_finish_body(const DevView& A, const DevView& B, int checkOri, int* __restrict__ m12,
+                                                       const int* __restrict__ hist, int* __restrict__ pairs,
+                                                       int* __restrict__ cnt) {
     __shared__ int s_ind[3], s_drop, s_wsum[34];
     const int tid = threadIdx.x;
     if (checkOri) {
@@ -416,6 +452,15 @@ __global__ void __launch_bounds__(256) k_search_tri_finish(DevView A, DevView B,
         __syncthreads();
     }
     if (tid == 0) cnt[0] = base;
+}
+__global__ void __launch_bounds__(256) k_search_tri_finish(DevView A, DevView B, int checkOri, int* __restrict__ m12,
+                                                           const int* __restrict__ hist, int* __restrict__ pairs,
+                                                           int* __restrict__ cnt) {
+    search_tri_finish_body(A, B, checkOri, m12, hist, pairs, cnt);
+}
+__global__ void __launch_bounds__(256) k_search_tri_finish_batch(const TriJob* __restrict__ jobs) {
+    const TriJob& J = jobs[blockIdx.x];
+    search_tri_finish_body(J.A, J.B, J.tp.checkOri, J.m12, J.hist, J.pairs, J.cnt);
 }
 
 // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:483-548), one warp per map point.  Row i of the N x N distance matrix is
@@ -729,6 +774,152 @@ extern "C" int orbm_search_for_triangulation(const orbm_view* kf1, const orbm_vi
         }
     }
     *n_pairs = cnt[0]; *n_matches = cnt[1];
+    return ORB_OK;
+}
+
+// ---- batched node-constrained searches: one view against N others, two launches for the whole batch -----------------------------
+template <bool KFKF>
+static int search_bow_batch(const orbm_view* anchor, const orbm_view* others, int n_others, float nnratio, int checkOri, int* match_out,
+                            int* n_matches, int device) {
+    // KFKF = false: SearchByBoW(others[i] (KeyFrame), anchor (Frame)); KFKF = true: SearchByBoW(anchor (KF1), others[i] (KF2)).
+    // Either way the output rows are anchor->n long.
+    ORB_REQUIRE(match_out && n_matches && n_others >= 0 && (n_others == 0 || others), ORB_ERR_ARG, "bad arguments");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_view(anchor, KFKF, false))) return rc;
+    for (int i = 0; i < n_others; i++) if ((rc = check_view(&others[i], true, false))) return rc;
+    if (n_others == 0) return ORB_OK;
+    const int nOut = anchor->n, nOutP = std::max(nOut, 1);
+    size_t bytes = view_bytes(anchor, false) + pad((size_t)n_others * sizeof(BowJob)) + pad((size_t)n_others * 4) + 1024, maxTaken = 0;
+    int maxNodes = 0;
+    for (int i = 0; i < n_others; i++) {
+        const int n2 = KFKF ? others[i].n : anchor->n;                     // side 2 of pair i
+        bytes += view_bytes(&others[i], false) + 2 * pad((size_t)nOutP * 4) + pad(((size_t)std::max(n2, 1) + ORBM_HISTO_LENGTH + 1) * 4);
+        maxTaken += (size_t)std::max(n2, 1) + ORBM_HISTO_LENGTH + 1;
+        maxNodes = std::max(maxNodes, KFKF ? anchor->fv.n_nodes : others[i].fv.n_nodes);
+    }
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, bytes))) return rc;
+    DevView dA;
+    if ((rc = upload_view(A, anchor, false, &dA))) return rc;
+    std::vector<BowJob> jobs(n_others);
+    for (int i = 0; i < n_others; i++) {
+        DevView dO;
+        if ((rc = upload_view(A, &others[i], false, &dO))) return rc;
+        jobs[i].A = KFKF ? dA : dO;
+        jobs[i].B = KFKF ? dO : dA;
+        jobs[i].nOut = nOut;
+    }
+    const BowJob* d_jobs = nullptr;
+    BowJob* d_jobs_w = A.take<BowJob>(n_others);                            // filled below, after the output pointers are known
+    (void)d_jobs;
+    // outputs: out rows back to back (one fetch), then bins, then the zeroed scratch of every pair back to back (one memset)
+    int* d_out = A.take<int>((size_t)nOutP * n_others);
+    int* d_bin = A.take<int>((size_t)nOutP * n_others);
+    int* d_zero = A.take<int>(maxTaken);
+    int* d_nm = A.take<int>(n_others);
+    size_t zo = 0;
+    for (int i = 0; i < n_others; i++) {
+        const int n2 = std::max(KFKF ? others[i].n : anchor->n, 1);
+        jobs[i].out = d_out + (size_t)i * nOutP;
+        jobs[i].binOf = d_bin + (size_t)i * nOutP;
+        jobs[i].taken2 = d_zero + zo;
+        jobs[i].hist = d_zero + zo + n2;
+        jobs[i].nmatch = d_nm + i;
+        zo += (size_t)n2 + ORBM_HISTO_LENGTH + 1;
+    }
+    if (A.staged) memcpy(A.hbase + (reinterpret_cast<u8*>(d_jobs_w) - A.base), jobs.data(), jobs.size() * sizeof(BowJob));
+    if ((rc = A.flush())) return rc;                                        // (flush sends everything taken so far, the job table included)
+    if (!A.staged) ORB_CUDA_TRY(cudaMemcpyAsync(d_jobs_w, jobs.data(), jobs.size() * sizeof(BowJob), cudaMemcpyHostToDevice, A.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_out, 0xFF, (size_t)nOutP * n_others * 4, A.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_zero, 0, maxTaken * 4, A.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_nm, 0, (size_t)n_others * 4, A.stream));
+    if (maxNodes > 0) {
+        dim3 g(orb_div_up(maxNodes, SB_WARPS), n_others);
+        k_search_bow_nodes_batch<KFKF><<<g, 32 * SB_WARPS, 0, A.stream>>>(d_jobs_w, nnratio, checkOri);
+    }
+    k_search_bow_finish_batch<<<n_others, 256, 0, A.stream>>>(d_jobs_w, checkOri);
+    ORB_CUDA_TRY(cudaGetLastError());
+    if (nOut > 0) {
+        if (nOutP == nOut) { if ((rc = A.fetch(match_out, d_out, (size_t)nOut * n_others))) return rc; }
+    }
+    if ((rc = A.fetch(n_matches, d_nm, (size_t)n_others))) return rc;
+    return A.finish();
+}
+
+extern "C" int orbm_search_by_bow_batch(const orbm_view* anchor, const orbm_view* others, int n_others, int mode, float nnratio,
+                                        int check_orientation, int* match_out, int* n_matches, int device) {
+    ORB_REQUIRE(mode == 0 || mode == 1, ORB_ERR_ARG, "mode must be 0 (KeyFrame others[i], Frame anchor) or 1 (KeyFrame anchor, KeyFrame others[i])");
+    return mode ? search_bow_batch<true>(anchor, others, n_others, nnratio, check_orientation, match_out, n_matches, device)
+                : search_bow_batch<false>(anchor, others, n_others, nnratio, check_orientation, match_out, n_matches, device);
+}
+
+extern "C" int orbm_search_for_triangulation_batch(const orbm_view* anchor, const orbm_view* others, int n_others, const float* F12,
+                                                   const float* epipoles, const float* scale_factors2, const float* level_sigma2_2,
+                                                   int n_levels2, int only_stereo, int check_orientation, int* pairs_out, int* n_pairs,
+                                                   int* n_matches, int device) {
+    ORB_REQUIRE(n_others >= 0 && (n_others == 0 || (others && F12 && epipoles && scale_factors2 && level_sigma2_2)) && n_levels2 > 0 &&
+                pairs_out && n_pairs && n_matches, ORB_ERR_ARG, "bad arguments");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if ((rc = check_view(anchor, true, true))) return rc;
+    for (int i = 0; i < n_others; i++) {
+        if ((rc = check_view(&others[i], true, true))) return rc;
+        for (int j = 0; j < others[i].n; j++)
+            ORB_REQUIRE(others[i].octave[j] >= 0 && others[i].octave[j] < n_levels2, ORB_ERR_ARG, "octave out of range");
+    }
+    if (n_others == 0) return ORB_OK;
+    const int n1 = anchor->n, n1P = std::max(n1, 1);
+    size_t bytes = view_bytes(anchor, true) + pad((size_t)n_others * sizeof(TriJob)) + 2 * pad((size_t)n_others * n_levels2 * 4) + 1024;
+    for (int i = 0; i < n_others; i++) bytes += view_bytes(&others[i], true) + 3 * pad((size_t)n1P * 4) + pad((2 + ORBM_HISTO_LENGTH) * 4);
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, bytes))) return rc;
+    DevView dA;
+    if ((rc = upload_view(A, anchor, true, &dA))) return rc;
+    const float *d_sf, *d_s2;
+    if ((rc = upload(A, scale_factors2, (size_t)n_others * n_levels2, &d_sf))) return rc;
+    if ((rc = upload(A, level_sigma2_2, (size_t)n_others * n_levels2, &d_s2))) return rc;
+    std::vector<TriJob> jobs(n_others);
+    const int total1 = anchor->fv.n_nodes > 0 ? anchor->fv.offsets[anchor->fv.n_nodes] : 0;
+    for (int i = 0; i < n_others; i++) {
+        if ((rc = upload_view(A, &others[i], true, &jobs[i].B))) return rc;
+        jobs[i].A = dA;
+        for (int k = 0; k < 9; k++) jobs[i].tp.F[k] = F12[9 * (size_t)i + k];
+        jobs[i].tp.ex = epipoles[2 * (size_t)i]; jobs[i].tp.ey = epipoles[2 * (size_t)i + 1];
+        jobs[i].tp.onlyStereo = only_stereo; jobs[i].tp.checkOri = check_orientation;
+        jobs[i].sf2 = d_sf + (size_t)i * n_levels2;
+        jobs[i].sigma2 = d_s2 + (size_t)i * n_levels2;
+    }
+    TriJob* d_jobs = A.take<TriJob>(n_others);
+    int* d_m12 = A.take<int>((size_t)n1P * n_others);
+    int* d_pairs = A.take<int>((size_t)2 * n1P * n_others);
+    int* d_cnt = A.take<int>((size_t)(2 + ORBM_HISTO_LENGTH) * n_others);   // per pair: cnt[2] | hist
+    for (int i = 0; i < n_others; i++) {
+        jobs[i].m12 = d_m12 + (size_t)i * n1P;
+        jobs[i].pairs = d_pairs + (size_t)2 * i * n1P;
+        jobs[i].cnt = d_cnt + (size_t)i * (2 + ORBM_HISTO_LENGTH);
+        jobs[i].hist = jobs[i].cnt + 2;
+    }
+    if (A.staged) memcpy(A.hbase + (reinterpret_cast<u8*>(d_jobs) - A.base), jobs.data(), jobs.size() * sizeof(TriJob));
+    if ((rc = A.flush())) return rc;
+    if (!A.staged) ORB_CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(TriJob), cudaMemcpyHostToDevice, A.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_m12, 0xFF, (size_t)n1P * n_others * 4, A.stream));
+    ORB_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, (size_t)(2 + ORBM_HISTO_LENGTH) * n_others * 4, A.stream));
+    if (total1 > 0) {
+        dim3 g(orb_div_up(total1, 128), n_others);
+        k_search_tri_slots_batch<<<g, 128, 0, A.stream>>>(d_jobs);
+    }
+    k_search_tri_finish_batch<<<n_others, 256, 0, A.stream>>>(d_jobs);
+    ORB_CUDA_TRY(cudaGetLastError());
+    std::vector<int> cnt((size_t)(2 + ORBM_HISTO_LENGTH) * n_others), tmp((size_t)2 * n1P * n_others);
+    if ((rc = A.fetch(cnt.data(), d_cnt, cnt.size()))) return rc;
+    if (n1 > 0 && (rc = A.fetch(tmp.data(), d_pairs, tmp.size()))) return rc;
+    if ((rc = A.finish())) return rc;
+    for (int i = 0; i < n_others; i++) {
+        n_pairs[i] = cnt[(size_t)i * (2 + ORBM_HISTO_LENGTH)];
+        n_matches[i] = cnt[(size_t)i * (2 + ORBM_HISTO_LENGTH) + 1];
+        if (n_pairs[i]) memcpy(pairs_out + (size_t)2 * i * n1, tmp.data() + (size_t)2 * i * n1P, (size_t)n_pairs[i] * 8);
+    }
     return ORB_OK;
 }
 

@@ -121,6 +121,42 @@ class ORBmatcher:
                                                           capi._p(m), C.byref(n), self.device))
         return n.value, m[:other.n]
 
+    def SearchByBoWBatch(self, anchor, others, kf_kf=False):
+        """One view against many in one call (the candidate loops of Tracking::Relocalization / LoopClosing::ComputeSim3).
+        kf_kf=False: SearchByBoW(KeyFrame* others[i], Frame& anchor); kf_kf=True: SearchByBoW(KeyFrame* anchor, KeyFrame* others[i]).
+        Returns (nmatches[len(others)], matches[len(others), anchor.N])."""
+        k = len(others)
+        arr = (capi.ViewC * max(k, 1))(*[o.c() for o in others])
+        va = anchor.c()
+        m = np.zeros((max(k, 1), max(anchor.n, 1)), np.int32)
+        nm = np.zeros(max(k, 1), np.int32)
+        out = np.zeros(max(k * anchor.n, 1), np.int32)
+        capi.check(capi.lib().orbm_search_by_bow_batch(C.byref(va), arr, k, int(kf_kf), self.mfNNratio, int(self.mbCheckOrientation),
+                                                       capi._p(out), capi._p(nm), self.device))
+        if anchor.n:
+            m = out[:k * anchor.n].reshape(k, anchor.n)
+        return nm[:k], m[:k, :anchor.n]
+
+    def SearchForTriangulationBatch(self, kf1, neighbours, F12s, epipoles, scale_factors2, level_sigma2_2, bOnlyStereo):
+        """SearchForTriangulation(kf1, neighbours[i], F12s[i], ...) for every neighbour in one call (LocalMapping::CreateNewMapPoints).
+        scale_factors2 / level_sigma2_2: (len(neighbours), n_levels).  Returns (nmatches[k], [pairs_i])."""
+        k = len(neighbours)
+        arr = (capi.ViewC * max(k, 1))(*[o.c() for o in neighbours])
+        va = kf1.c()
+        F = np.ascontiguousarray(F12s, np.float32).reshape(max(k, 1), 9) if k else np.zeros((1, 9), np.float32)
+        ep = np.ascontiguousarray(epipoles, np.float32).reshape(-1, 2) if k else np.zeros((1, 2), np.float32)
+        sf2 = np.ascontiguousarray(scale_factors2, np.float32).reshape(max(k, 1), -1)
+        s2 = np.ascontiguousarray(level_sigma2_2, np.float32).reshape(max(k, 1), -1)
+        pairs = np.zeros((max(k, 1), max(kf1.n, 1), 2), np.int32)
+        flat = np.zeros(max(2 * k * kf1.n, 1), np.int32)
+        npairs, nm = np.zeros(max(k, 1), np.int32), np.zeros(max(k, 1), np.int32)
+        capi.check(capi.lib().orbm_search_for_triangulation_batch(C.byref(va), arr, k, capi._p(F), capi._p(ep), capi._p(sf2), capi._p(s2),
+                                                                  sf2.shape[1], int(bOnlyStereo), int(self.mbCheckOrientation),
+                                                                  capi._p(flat), capi._p(npairs), capi._p(nm), self.device))
+        if kf1.n:
+            pairs = flat[:2 * k * kf1.n].reshape(k, kf1.n, 2)
+        return nm[:k], [pairs[i, :npairs[i]].copy() for i in range(k)]
+
     def SearchForTriangulation(self, kf1, kf2, F12, ex, ey, scale_factors2, level_sigma2_2, bOnlyStereo):
         v1, v2 = kf1.c(), kf2.c()
         F12 = np.ascontiguousarray(F12, np.float32).reshape(9)

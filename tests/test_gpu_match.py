@@ -266,3 +266,72 @@ def test_distances_and_top2_match_cv2_golden():
     assert np.array_equal(b1, g["best"]) and np.array_equal(b2, g["second"])
     uniq = g["best"] < g["second"]
     assert np.array_equal(bi[uniq], g["best_idx"][uniq])
+
+
+@pytest.mark.parametrize("kf_kf,ori,ratio", [(False, True, 0.75), (True, True, 0.75), (False, False, 0.6), (True, False, 0.9)])
+def test_search_by_bow_batch_equals_single_calls(kf_kf, ori, ratio):
+    """orbm_search_by_bow_batch (one frame / keyframe against N candidates, two launches): identical to the oracle's single searches
+    in a loop — candidates of different sizes, an empty one, one without common nodes."""
+    rng = np.random.default_rng(5)
+    sizes = [(1500, 1400), (1500, 300), (1500, 2000), (1500, 0), (1500, 50), (1500, 1500), (1500, 900)]
+    base = _scene(1500, 1500, 100)
+    anchor_d, anchor_node, anchor_ang, anchor_flag = base["d1"], base["node1"], base["ang1"], base["flag1"]
+    others, want = [], []
+    for i, (_, n2) in enumerate(sizes):
+        s = _scene(1500, n2, 200 + i)
+        # candidates share descriptors with the anchor so that real matches exist
+        d2, node2 = s["d2"].copy(), s["node2"].copy()
+        k = min(n2, 1500) // 2
+        src = rng.choice(1500, k, replace=False) if k else np.zeros(0, int)
+        for t, sidx in enumerate(src):
+            d2[t] = _flip(anchor_d[sidx], int(rng.choice([0, 3, 20, 49, 50, 51])), rng)
+            node2[t] = anchor_node[sidx] if i != 4 else anchor_node[sidx] + 1000        # candidate 4: no common nodes
+        others.append((d2, node2, s["ang2"], s["flag2"]))
+    A = orb.View(anchor_d, orb.FeatureVector(anchor_node), anchor_ang, flag=anchor_flag)
+    O = [orb.View(d, orb.FeatureVector(nd), a, flag=f) for d, nd, a, f in others]
+    nm, m = orb.ORBmatcher(ratio, ori).SearchByBoWBatch(A, O, kf_kf=kf_kf)
+    fa = orc.FeatVec(anchor_node)
+    total = 0
+    for i, (d, nd, a, f) in enumerate(others):
+        fo = orc.FeatVec(nd)
+        if kf_kf:
+            on, om = orc.search_bow_kf_kf(anchor_d, anchor_flag, anchor_ang, fa, d, f, a, fo, ratio, ori)
+        else:
+            on, om = orc.search_bow_kf_f(d, f, a, fo, anchor_d, anchor_ang, fa, ratio, ori)
+        assert nm[i] == on and np.array_equal(m[i], om), i
+        total += on
+    assert total > 200
+
+
+@pytest.mark.parametrize("only_stereo,ori", [(False, False), (True, False), (False, True)])
+def test_search_for_triangulation_batch_equals_single_calls(only_stereo, ori):
+    rng = np.random.default_rng(9)
+    sf2 = (1.2 ** np.arange(8)).astype(np.float32)
+    n1 = 1200
+    base = _scene(n1, n1, 300, tri=True)
+    views, args = [], []
+    for i, n2 in enumerate([1100, 0, 1300, 64, 900]):
+        s = _scene(n1, n2, 310 + i, tri=True)
+        d2, node2 = s["d2"].copy(), s["node2"].copy()
+        k = min(n2, n1) // 2
+        src = rng.choice(n1, k, replace=False) if k else np.zeros(0, int)
+        for t, sidx in enumerate(src):
+            d2[t] = _flip(base["d1"][sidx], int(rng.choice([0, 3, 20, 49, 50, 51])), rng)
+            node2[t] = base["node1"][sidx]
+        F12 = (rng.normal(0, 1, (3, 3)) * np.array([[1e-6, 1e-5, 1e-3], [1e-5, 1e-6, 1e-3], [1e-3, 1e-3, 1e-1]])).astype(np.float32)
+        ep = rng.uniform(100, 500, 2).astype(np.float32)
+        sig = (sf2 * sf2 * rng.uniform(2000, 8000)).astype(np.float32)
+        views.append(orb.View(d2, orb.FeatureVector(node2), s["ang2"], flag=s["flag2"], x=s["x2"], y=s["y2"], octave=s["oct2"], uright=s["ur2"]))
+        args.append((d2, s["flag2"], s["ur2"], s["x2"], s["y2"], s["ang2"], s["oct2"], node2, F12, ep, sig))
+    K1 = orb.View(base["d1"], orb.FeatureVector(base["node1"]), base["ang1"], flag=base["flag1"], x=base["x1"], y=base["y1"],
+                  octave=np.zeros(n1, np.int32), uright=base["ur1"])
+    nm, pairs = orb.ORBmatcher(0.6, ori).SearchForTriangulationBatch(K1, views, [a[8] for a in args], [a[9] for a in args],
+                                                                     [sf2] * len(args), [a[10] for a in args], only_stereo)
+    total = 0
+    for i, (d2, f2, ur2, x2, y2, a2, o2, node2, F12, ep, sig) in enumerate(args):
+        on, op = orc.search_triangulation(base["d1"], base["flag1"], base["ur1"], base["x1"], base["y1"], base["ang1"], orc.FeatVec(base["node1"]),
+                                          d2, f2, ur2, x2, y2, a2, o2, orc.FeatVec(node2), F12, float(ep[0]), float(ep[1]), sf2, sig,
+                                          only_stereo, ori)
+        assert len(pairs[i]) == len(op) and np.array_equal(pairs[i], op), i
+        total += len(op)
+    assert only_stereo or total > 20
