@@ -471,6 +471,40 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {"value": world * nF * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(nF * W * H),
            "d2h_bytes_per_step": int(h_n.sum()) * 60 + nF * 4, "ms_per_step": 1e3 * e2e_s / args.steps}
+    # the same call from PAGEABLE caller buffers (what a caller holding cv::Mat frames hands over): the copies go through the driver's
+    # staging and cannot overlap the way DMA from pinned memory does.  Reported next to the pinned figure, N=1 only.
+    if world == 1:
+        p_frames = frames if frames.flags.c_contiguous else np.ascontiguousarray(frames)
+        p_kp = np.zeros((nF, cap, 7), np.float32)
+        p_desc = np.zeros((nF, cap, 32), np.uint8)
+        p_n = np.zeros(nF, np.int32)
+
+        def pageable_step():
+            capi.check(capi.lib().orbx_extract_batch(ex2.handle, capi._p(p_frames), nF, W, H, W, W * H, None, 0, 0,
+                                                     capi._p(p_kp), capi._p(p_desc), cap, capi._p(p_n)))
+        pageable_step()
+        t0 = time.perf_counter()
+        kp_ = max(2, min(args.steps, 5))
+        for _ in range(kp_):
+            pageable_step()
+        ps = (time.perf_counter() - t0) / kp_
+        e2e["pageable_caller_buffers"] = {"value": nF / ps, "unit": "frames/s", "ms_per_step": 1e3 * ps,
+                                          "note": "orbx_extract_batch from ordinary (unpinned) host arrays"}
+        # the same arrays after the caller registered them once (orbx_host_register = cudaHostRegister)
+        t0 = time.perf_counter()
+        for a_ in (p_frames, p_kp, p_desc):
+            capi.check(capi.lib().orbx_host_register(capi._p(a_), a_.nbytes))
+        reg_s = time.perf_counter() - t0
+        pageable_step()
+        t0 = time.perf_counter()
+        for _ in range(kp_):
+            pageable_step()
+        rs = (time.perf_counter() - t0) / kp_
+        for a_ in (p_frames, p_kp, p_desc):
+            capi.check(capi.lib().orbx_host_unregister(capi._p(a_)))
+        e2e["registered_caller_buffers"] = {"value": nF / rs, "unit": "frames/s", "ms_per_step": 1e3 * rs, "register_once_ms": 1e3 * reg_s,
+                                            "note": "the same arrays after orbx_host_register (one-off page-locking by the caller)"}
+        del p_kp, p_desc
     # the floor the platform sets for e2e: the same bytes moved with no compute at all (all ranks at once, same pinned buffers).
     # At N=1 the copies hide behind the kernels; with 8 ranks streaming 1.26 GB per step each the host side becomes the limit.
     d_stage = torch.empty((args.e2e_chunk, H, W), dtype=torch.uint8, device="cuda")

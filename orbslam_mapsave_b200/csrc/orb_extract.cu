@@ -2151,6 +2151,20 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
     return ORB_OK;
 }
 
+// Page-lock / unlock caller-owned host memory (cudaHostRegister) so that the batch call can DMA straight from / into it: from
+// ordinary pageable arrays every copy goes through the driver's staging buffers (measured: 27 k instead of 169 k frames/s end to end).
+extern "C" int orbx_host_register(void* p, size_t bytes) {
+    ORB_REQUIRE(p && bytes > 0, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE(orb_device_count() > 0, ORB_ERR_CUDA, "no CUDA device (no CPU fallback)");
+    ORB_CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return ORB_OK;
+}
+extern "C" int orbx_host_unregister(void* p) {
+    ORB_REQUIRE(p, ORB_ERR_ARG, "bad arguments");
+    ORB_CUDA_TRY(cudaHostUnregister(p));
+    return ORB_OK;
+}
+
 extern "C" int orbx_extract(orbx_extractor* ex, const uint8_t* image, int width, int height, int stride, const uint8_t* mask,
                             int mask_stride, orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
     return orbx_extract_batch(ex, image, 1, width, height, stride, (size_t)stride * height, mask, mask_stride,

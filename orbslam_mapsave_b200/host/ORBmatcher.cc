@@ -147,6 +147,66 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
     return nmatches;
 }
 
+// Batched overloads (not in the reference): the candidate loops of Tracking::Relocalization (src/Tracking.cc:1621-1643) and
+// LoopClosing::ComputeSim3 (src/LoopClosing.cc:240-266) as ONE device call; results equal calling the overloads above per candidate.
+std::vector<int> ORBmatcher::SearchByBoW(const std::vector<KeyFrame*>& vpKFs, Frame& F, std::vector<std::vector<MapPoint*> >& vvpMapPointMatches) {
+    const size_t k = vpKFs.size();
+    std::vector<int> counts(k, 0);
+    vvpMapPointMatches.assign(k, std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL)));
+    if (k == 0) return counts;
+    std::vector<std::vector<MapPoint*> > mps(k);
+    std::vector<Side> sides(k);
+    std::vector<orbm_view> views(k);
+    for (size_t i = 0; i < k; i++) {
+        mps[i] = vpKFs[i]->GetMapPointMatches();
+        snapshot_kf_bow(vpKFs[i], mps[i], sides[i]);
+        views[i] = sides[i].view;
+    }
+    Side b;
+    copy_desc(F.mDescriptors, F.N, b);
+    b.angle.resize(F.N);
+    for (int i = 0; i < F.N; i++) b.angle[i] = F.mvKeys[i].angle;
+    flatten_featvec(F.mFeatVec, b);
+    finish(b, F.N, false);
+    std::vector<int> m21(k * (size_t)(F.N > 0 ? F.N : 1), -1);
+    report(orbm_search_by_bow_batch(&b.view, views.data(), (int)k, 0, mfNNratio, mbCheckOrientation ? 1 : 0, m21.data(), counts.data(), g_device));
+    if (g_status != ORB_OK) return std::vector<int>(k, 0);
+    for (size_t i = 0; i < k; i++)
+        for (int j = 0; j < F.N; j++) {
+            const int idx1 = m21[i * (size_t)F.N + j];
+            if (idx1 >= 0) vvpMapPointMatches[i][j] = mps[i][idx1];
+        }
+    return counts;
+}
+
+std::vector<int> ORBmatcher::SearchByBoW(KeyFrame* pKF1, const std::vector<KeyFrame*>& vpKF2s, std::vector<std::vector<MapPoint*> >& vvpMatches12) {
+    const size_t k = vpKF2s.size();
+    std::vector<int> counts(k, 0);
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const size_t n1 = vpMapPoints1.size();
+    vvpMatches12.assign(k, std::vector<MapPoint*>(n1, static_cast<MapPoint*>(NULL)));
+    if (k == 0) return counts;
+    Side a;
+    snapshot_kf_bow(pKF1, vpMapPoints1, a);
+    std::vector<std::vector<MapPoint*> > mps(k);
+    std::vector<Side> sides(k);
+    std::vector<orbm_view> views(k);
+    for (size_t i = 0; i < k; i++) {
+        mps[i] = vpKF2s[i]->GetMapPointMatches();
+        snapshot_kf_bow(vpKF2s[i], mps[i], sides[i]);
+        views[i] = sides[i].view;
+    }
+    std::vector<int> m12(k * (n1 ? n1 : 1), -1);
+    report(orbm_search_by_bow_batch(&a.view, views.data(), (int)k, 1, mfNNratio, mbCheckOrientation ? 1 : 0, m12.data(), counts.data(), g_device));
+    if (g_status != ORB_OK) return std::vector<int>(k, 0);
+    for (size_t i = 0; i < k; i++)
+        for (size_t j = 0; j < n1; j++) {
+            const int idx2 = m12[i * n1 + j];
+            if (idx2 >= 0) vvpMatches12[i][j] = mps[i][idx2];
+        }
+    return counts;
+}
+
 int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
                                        std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
     // Epipole in the second image (ORBmatcher.cc:667-673).  `R2w*Cw+t2w` is one cv::gemm(A, B, 1, C, 1) on 3x3 / 3x1 floats:

@@ -29,6 +29,10 @@ public:
     // Brute force constrained to ORB that belong to the same vocabulary node (reference :65-66)
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
     int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12);
+    // Batched overloads (not in the reference): the candidate loops of Tracking::Relocalization (src/Tracking.cc:1621-1643) and
+    // LoopClosing::ComputeSim3 (src/LoopClosing.cc:240-266) as one device call; element i equals the single overload on candidate i.
+    std::vector<int> SearchByBoW(const std::vector<KeyFrame*>& vpKFs, Frame& F, std::vector<std::vector<MapPoint*> >& vvpMapPointMatches);
+    std::vector<int> SearchByBoW(KeyFrame* pKF1, const std::vector<KeyFrame*>& vpKF2s, std::vector<std::vector<MapPoint*> >& vvpMatches12);
 
     // Search matches between Frame keypoints and projected MapPoints. Returns number of matches.  Used to track the local map
     // (Tracking) (reference :48, src/ORBmatcher.cc:45-129)

@@ -150,6 +150,28 @@ static int run_match(int argc, char** argv) {
         const int c[3] = {ORBmatcher::TH_LOW, ORBmatcher::TH_HIGH, ORBmatcher::HISTO_LENGTH};
         put(out, c, 3);
     }
+    {   // batched overloads: {kf0, kf0} against the frame and kf0 against {kf1, kf1} — every element must equal the single call
+        std::vector<KeyFrame*> two0(2, &w.kf[0]), two1(2, &w.kf[1]);
+        std::vector<std::vector<MapPoint*> > res;
+        std::vector<int> cnt = m.SearchByBoW(two0, w.fr, res);
+        for (int c = 0; c < 2; c++) {
+            put(out, &cnt[c], 1);
+            std::vector<int> idx(res[c].size(), -1);
+            for (size_t j = 0; j < res[c].size(); j++) if (res[c][j]) idx[j] = (int)(res[c][j] - &w.pool[0][0]);
+            const int sz = (int)idx.size(); put(out, &sz, 1); put(out, idx.data(), idx.size());
+        }
+        cnt = m.SearchByBoW(&w.kf[0], two1, res);
+        for (int c = 0; c < 2; c++) {
+            put(out, &cnt[c], 1);
+            std::vector<int> idx(res[c].size(), -1);
+            for (size_t j = 0; j < res[c].size(); j++) if (res[c][j]) idx[j] = (int)(res[c][j] - &w.pool[1][0]);
+            const int sz = (int)idx.size(); put(out, &sz, 1); put(out, idx.data(), idx.size());
+        }
+        const int nd = std::min(w.kf[0].mDescriptors.rows, w.kf[1].mDescriptors.rows);
+        std::vector<int> dist(nd > 0 ? nd : 1, -1);
+        const int got = ORBmatcher::DescriptorDistances(w.kf[0].mDescriptors, w.kf[1].mDescriptors, dist.data());
+        put(out, &got, 1); put(out, dist.data(), (size_t)got);
+    }
     return ORBmatcher::LastStatus() == 0 ? 0 : 4;
 }
 
@@ -184,6 +206,7 @@ static int run_bow(int argc, char** argv) {
 
 // driver project <in.bin> <out.bin>: the window searches the way Tracking calls them (SearchLocalPoints, TrackWithMotionModel,
 // MonocularInitialization).  The Frame is assembled like Frame::Frame does: AssignFeaturesToGrid with PosInGrid's round().
+#include <algorithm>
 #include <cmath>
 static void build_frame(Reader& r, Frame& F) {
     const int n = r.get<int>();

@@ -139,6 +139,20 @@ def test_cpp_orbmatcher_matches_oracle(tmp_path, seed, ratio, ori, only_stereo):
     assert nm == on and np.array_equal(got, op)
     d, lo, hi, hl = take("<iiii")
     assert d == orc.descriptor_distance(desc[0][0], desc[1][0]) and (lo, hi, hl) == (50, 100, 30)
+    # batched overloads: every element equals the single call; DescriptorDistances equals the bit hack row by row
+    on, om = orc.search_bow_kf_f(desc[0], good[0], ang[0], fv[0], desc[1], ang[1], fv[1], np.float32(ratio), ori)
+    for _ in range(2):
+        nm, sz = take("<ii")
+        got = np.frombuffer(out, np.int32, sz, pos); pos += 4 * sz
+        assert nm == on and np.array_equal(got, om)
+    on, om = orc.search_bow_kf_kf(desc[0], good[0], ang[0], fv[0], desc[1], good[1], ang[1], fv[1], np.float32(ratio), ori)
+    for _ in range(2):
+        nm, sz = take("<ii")
+        got = np.frombuffer(out, np.int32, sz, pos); pos += 4 * sz
+        assert nm == on and np.array_equal(got, om)
+    nd, = take("<i")
+    got = np.frombuffer(out, np.int32, nd, pos); pos += 4 * nd
+    assert nd == min(n) and np.array_equal(got, np.unpackbits(desc[0][:nd] ^ desc[1][:nd], axis=1).sum(1))
 
 
 def test_cpp_vocabulary_transform_matches_oracle(tmp_path):
