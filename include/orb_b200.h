@@ -355,6 +355,14 @@ int orbm_search_windows_best(const orbm_grid_view* target, int nq, const uint8_t
  * per second on `device` over a register-resident loop. */
 int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used);
 
+/* Platform probe (a measurement aid for bench.py, not on the product path): the host->device rate the box sustains when n_dev GPUs
+ * stream frames at once from pinned memory — one thread per GPU, plain cudaMemcpyAsync per chunk, all released together.
+ * flags: 1 = write-combined pinned memory, 2 = also 20 % of the volume device->host concurrently, 4 = bind every copy thread (and its
+ * first-touched pinned buffer) to the NUMA node of its GPU.  gbs_each[n_dev], *gbs_total: GB/s; numa_nodes[n_dev] (may be NULL): the
+ * sysfs numa_node of every GPU (-1: the kernel reports none; -3: sysfs entry not visible). */
+int orb_h2d_probe(int n_dev, const int* devices, size_t bytes_per_step, size_t chunk_bytes, int steps, int flags, double* gbs_each,
+                  double* gbs_total, int* numa_nodes);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Map archive: the fork's System::SaveMap / LoadMap file (src/System.cc:552-574) as a source of real keyframe
  * descriptor sets for the matcher.  Host-only: parses / writes the Boost binary archive (`no_header`, `oa << mpMap`) whose
