@@ -1176,6 +1176,33 @@ __device__ __forceinline__ float dev_fast_atan2(float y, float x) {
     return a;
 }
 
+// sin and cos of x in [0, 2 pi] in double: quadrant by k = rint(x * 2/pi), Cody-Waite reduction with a two-part pi/2, the fdlibm
+// kernel polynomials on [-pi/4, pi/4] (< 1 ulp in double).  Only the float rounding of the results is used, so this agrees with a
+// correctly rounded cosf / sinf except within ~1e-16 (relative) of a float rounding boundary.  ~30 instructions against ~80 of the
+// library's sincos (large-argument and special-case paths that cannot occur here).
+__device__ __forceinline__ void dev_sincos_0_2pi(double x, double& s, double& c) {
+    const int q = __double2int_rn(x * 0.63661977236758138243);
+    const double k = (double)q;
+    double r = fma(-k, 1.57079632679489655800e+00, x);
+    r = fma(-k, 6.12323399573676603587e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sn = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cn = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const double ss = (q & 1) ? cn : sn, cc = (q & 1) ? sn : cn;
+    s = (q & 2) ? -ss : ss;
+    c = ((q + 1) & 2) ? -cc : cc;
+}
+
 #define DESC_WARPS 8
 #define DESC_PW 11            // aligned words per staged blurred-patch row: covers kx-18 .. kx+18 for any alignment
 #define DESC_AW 9             // aligned words per staged disc row: covers kx-15 .. kx+15 for any alignment
@@ -1350,26 +1377,27 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
             const float factorPI = (float)(3.1415926535897932384626433832795 / 180.f);
             const float ang = __fmul_rn(angle, factorPI);
             float cs = 0.f;
-            if (lane < 2) {                                         // one non-divergent sincos for both (shared range reduction)
+            if (lane < 2) {                                         // lane 0: cos, lane 1: sin (double, then rounded to float)
                 double sd, cd;
-                sincos((double)ang, &sd, &cd);
+                dev_sincos_0_2pi((double)ang, sd, cd);
                 cs = (float)(lane == 0 ? cd : sd);
             }
             const float a = __shfl_sync(0xffffffffu, cs, 0), b = __shfl_sync(0xffffffffu, cs, 1);
-            const u8* center = reinterpret_cast<const u8*>(patch) + 18 * PWB + 18 + shift;
             const float4* pat = reinterpret_cast<const float4*>(s_pat + lane * 36);
             u32 val = 0;
-            // round-half-even without the XU pipe: x + 1.5*2^23 leaves rint(x) in the low mantissa bits (|x| < 2^22), == cvRound
+            // round-half-even without the XU pipe: x + 1.5*2^23 leaves rint(x) in the low mantissa bits (|x| < 2^22), == cvRound;
+            // the bias of both coordinates (0x4B400000 each) is folded into the patch address once: byte (r, q) of the patch is at
+            // centerB + asint(r + MAGIC) * PWB + asint(q + MAGIC)   (32-bit shared address arithmetic, wraps)
             const float MAGIC = 12582912.f;
-            const int MAGIC_I = 0x4B400000;
+            const u32 centerB = smem_u32(patch) + (u32)(18 * PWB + 18 + shift) - 0x4B400000u * (u32)(PWB + 1);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float4 pp = pat[j];                               // x0, y0, x1, y1
-                const int r0 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)), MAGIC)) - MAGIC_I;
-                const int q0 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)), MAGIC)) - MAGIC_I;
-                const int r1 = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.z, b), __fmul_rn(pp.w, a)), MAGIC)) - MAGIC_I;
-                const int q1 = __float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.z, a), __fmul_rn(pp.w, b)), MAGIC)) - MAGIC_I;
-                const int t0 = center[r0 * PWB + q0], t1 = center[r1 * PWB + q1];
+                const u32 r0 = (u32)__float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)), MAGIC));
+                const u32 q0 = (u32)__float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)), MAGIC));
+                const u32 r1 = (u32)__float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(pp.z, b), __fmul_rn(pp.w, a)), MAGIC));
+                const u32 q1 = (u32)__float_as_int(__fadd_rn(__fsub_rn(__fmul_rn(pp.z, a), __fmul_rn(pp.w, b)), MAGIC));
+                const u32 t0 = lds8i<0>(centerB + r0 * (u32)PWB + q0), t1 = lds8i<0>(centerB + r1 * (u32)PWB + q1);
                 val |= (u32)(t0 < t1) << j;
             }
             descOut[((size_t)f * cap + pos) * 32 + lane] = (u8)val;
