@@ -648,6 +648,13 @@ def main():
         t_gpu, (nm, _) = lat(lambda: m.SearchByProjectionFrame(grid, *args_f))
         tracking = {"search_by_projection_last_frame": {"ms_per_call": 1e3 * t_gpu, "features": n, "matches": int(nm),
                                                         "note": "C ABI from pageable host arrays: upload + 3 kernels + download"}}
+        # many-frame form: 16 independent (CurrentFrame, LastFrame) pairs (several cameras / sessions) in ONE call
+        jobs16 = [(grid,) + args_f] * 16
+        t_fb, rb = lat(lambda: m.SearchByProjectionFrameBatch(jobs16), 10)
+        tracking["search_by_projection_frame_batch"] = {
+            "frames": 16, "features": n, "ms_per_batch_call": 1e3 * t_fb, "ms_looping_single_calls": 16 * 1e3 * t_gpu,
+            "frames_per_s": 16 / t_fb, "matches": int(sum(r[0] for r in rb)),
+            "note": "16 frame pairs: one upload, 3 launches (one resolve CTA per pair), one download"}
         left = frames[0]
         right = np.roll(left, -12, axis=1)
         exL, exR = orb.ORBextractor(1000, 1.2, 8, 20, 7, device=local_rank), orb.ORBextractor(1000, 1.2, 8, 20, 7, device=local_rank)

@@ -322,6 +322,30 @@ int orbm_search_by_projection_frame(const orbm_grid_view* cur, const float* Tcw_
                                     const float* angle, const uint8_t* desc, const uint8_t* claims,
                                     float th, int mono, int check_orientation, int* owner, int* n_matches, int device);
 
+/* Many-frame form of orbm_search_by_projection_frame (not in the reference, which tracks one camera per process): n_jobs independent
+ * (CurrentFrame, LastFrame) pairs — several cameras / sessions, or a recorded sequence whose poses are already predicted — in ONE call:
+ * one upload, three kernel launches (the serial claim replay of every pair runs in its own CTA), one download.  Every field has the
+ * meaning of the same-named argument above; owner (cur->n entries) and n_matches are the outputs of job k.  Results are identical to
+ * calling orbm_search_by_projection_frame once per job. */
+typedef struct orbm_frame_search_job {
+    const orbm_grid_view* cur;
+    const float* Tcw_cur;
+    const float* Tcw_last;
+    float fx, fy, cx, cy, mbf, mb;
+    int n_last;
+    const uint8_t* has_point;
+    const float* world;
+    const int* octave;
+    const float* angle;
+    const uint8_t* desc;
+    const uint8_t* claims;
+    float th;
+    int mono;
+    int* owner;                     /* out */
+    int n_matches;                  /* out */
+} orbm_frame_search_job;
+int orbm_search_by_projection_frame_batch(orbm_frame_search_job* jobs, int n_jobs, int check_orientation, int device);
+
 /* Replaces int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
  * vector<int>& vnMatches12, int windowSize) (src/ORBmatcher.cc:408-523; monocular initialisation).
  * f2: F2.  Per F1 feature (n1): desc1, octave1 = mvKeysUn[i].octave, angle1, prev_xy = vbPrevMatched (2 floats each, updated

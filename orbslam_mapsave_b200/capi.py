@@ -30,7 +30,8 @@ SYMBOLS = [
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
     "orbm_search_by_bow_batch", "orbm_search_for_triangulation_batch",
     "orbm_popc_peak", "orbm_distinctive_descriptors", "orb_h2d_probe",
-    "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_for_initialization", "orbm_search_windows", "orbm_search_windows_best",
+    "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_by_projection_frame_batch",
+    "orbm_search_for_initialization", "orbm_search_windows", "orbm_search_windows_best",
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
     "orbv_transform_device",
     "orbmap_load", "orbmap_save", "orbmap_create", "orbmap_destroy", "orbmap_get_info", "orbmap_keyframe_get_info",
@@ -61,6 +62,14 @@ class GridViewC(C.Structure):
                 ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("inv_w", C.c_float),
                 ("inv_h", C.c_float), ("cell_offsets", C.c_void_p), ("cell_features", C.c_void_p), ("scale_factors", C.c_void_p),
                 ("n_levels", C.c_int)]
+
+
+class FrameSearchJobC(C.Structure):
+    """orbm_frame_search_job of include/orb_b200.h"""
+    _fields_ = [("cur", C.POINTER(GridViewC)), ("Tcw_cur", C.c_void_p), ("Tcw_last", C.c_void_p), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float), ("mb", C.c_float), ("n_last", C.c_int), ("has_point", C.c_void_p),
+                ("world", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p), ("desc", C.c_void_p), ("claims", C.c_void_p),
+                ("th", C.c_float), ("mono", C.c_int), ("owner", C.c_void_p), ("n_matches", C.c_int)]
 
 
 class MapInfoC(C.Structure):
@@ -166,6 +175,8 @@ def lib():
     L.orbm_search_by_projection_frame.restype = i32
     L.orbm_search_by_projection_frame.argtypes = [C.POINTER(GridViewC), vp, vp, f32, f32, f32, f32, f32, f32, i32, vp, vp, vp, vp, vp,
                                                   vp, f32, i32, i32, vp, vp, i32]
+    L.orbm_search_by_projection_frame_batch.restype = i32
+    L.orbm_search_by_projection_frame_batch.argtypes = [vp, i32, i32, i32]
     L.orbm_search_for_initialization.restype = i32
     L.orbm_search_for_initialization.argtypes = [C.POINTER(GridViewC), i32, vp, vp, vp, vp, i32, f32, i32, vp, vp, i32]
     L.orbm_search_windows.restype = i32

@@ -65,7 +65,8 @@ struct Arena {
         if (stream) cudaStreamDestroy(stream);
         cudaGetLastError();
     }
-    int ensure(int dev, size_t bytes, size_t scratch = 0) {
+    // stageMax: calls whose inputs + outputs fit are packed into the pinned mirror (one copy each way); the batched searches raise it
+    int ensure(int dev, size_t bytes, size_t scratch = 0, size_t stageMax = 2u << 20) {
         if (device != dev) {
             if (base) { cudaSetDevice(device); cudaFree(base); base = nullptr; cap = 0; }
             if (hbase) { cudaFreeHost(hbase); hbase = nullptr; hcap = 0; }
@@ -82,13 +83,14 @@ struct Arena {
             cap = orb_align_up(bytes + scratch + ((bytes + scratch) >> 2), 1 << 20);
             ORB_CUDA_TRY(cudaMalloc(&base, cap));
         }
-        if (bytes > hcap && bytes <= (8u << 20)) {
+        const size_t hmax = std::max<size_t>(8u << 20, stageMax);
+        if (bytes > hcap && bytes <= hmax) {
             if (hbase) ORB_CUDA_TRY(cudaFreeHost(hbase));
             hbase = nullptr;
-            hcap = std::min<size_t>(orb_align_up(bytes + (bytes >> 2), 1 << 20), 8u << 20);
+            hcap = std::min<size_t>(orb_align_up(bytes + (bytes >> 2), 1 << 20), hmax);
             ORB_CUDA_TRY(cudaMallocHost(&hbase, hcap));
         }
-        staged = hbase != nullptr && bytes <= hcap && bytes <= (2u << 20);
+        staged = hbase != nullptr && bytes <= hcap && bytes <= stageMax;
         used = 0; inEnd = 0;
         pend.clear();                                        // a call that failed between fetch() and finish() leaves nothing behind
         return ORB_OK;
@@ -100,9 +102,10 @@ struct Arena {
         return p;
     }
     // send everything put() so far (staged mode); call once, after the last input and before the launch
-    int flush() {
-        if (staged && used > 0) ORB_CUDA_TRY(cudaMemcpyAsync(base, hbase, used, cudaMemcpyHostToDevice, stream));
-        inEnd = used;
+    int flush(size_t upto = ~(size_t)0) {                    // upto: end of the inputs when outputs have already been taken behind them
+        const size_t n = std::min(upto, used);
+        if (staged && n > 0) ORB_CUDA_TRY(cudaMemcpyAsync(base, hbase, n, cudaMemcpyHostToDevice, stream));
+        inEnd = n;
         return ORB_OK;
     }
     // bring `count` elements at device pointer d back to host pointer h; finish() completes the transfer

@@ -63,10 +63,9 @@ __global__ void k_win_map(DevGrid G, int nq, const u8* __restrict__ in_view, con
 
 // SearchByProjection(CurrentFrame, LastFrame): ORBmatcher.cc:1357-1396
 struct FrameProj { float T[12]; float fx, fy, cx, cy, mbf, th; int forward, backward; };
-__global__ void k_win_frame(DevGrid G, FrameProj P, int nq, const u8* __restrict__ has_point, const float* __restrict__ world,
-                            const int* __restrict__ octave, const u8* __restrict__ claims, Win* __restrict__ win) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
+__device__ __forceinline__ void win_frame_one(const DevGrid& G, const FrameProj& P, int q, const u8* __restrict__ has_point,
+                                              const float* __restrict__ world, const int* __restrict__ octave,
+                                              const u8* __restrict__ claims, Win* __restrict__ win) {
     Win w = {0.f, 0.f, 0.f, 0.f, 0.f, -1, -1, 0};
     if (has_point[q]) {
         const float X = world[3 * q], Y = world[3 * q + 1], Z = world[3 * q + 2];
@@ -92,6 +91,11 @@ __global__ void k_win_frame(DevGrid G, FrameProj P, int nq, const u8* __restrict
         }
     }
     win[q] = w;
+}
+__global__ void k_win_frame(DevGrid G, FrameProj P, int nq, const u8* __restrict__ has_point, const float* __restrict__ world,
+                            const int* __restrict__ octave, const u8* __restrict__ claims, Win* __restrict__ win) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) win_frame_one(G, P, q, has_point, world, octave, claims, win);
 }
 
 // SearchForInitialization: ORBmatcher.cc:422-430 (level-0 features only, window = windowSize around vbPrevMatched)
@@ -153,11 +157,8 @@ __device__ __forceinline__ bool cand_pass(const DevGrid& G, const Win& w, bool c
 }
 
 #define WC_WARPS 4
-__global__ void __launch_bounds__(32 * WC_WARPS) k_win_candidates(DevGrid G, const Win* __restrict__ win, const u8* __restrict__ qdesc,
-                                                                  int nq, int stride, int drop_above, u32* __restrict__ list,
-                                                                  int* __restrict__ cnt) {
-    const int lane = threadIdx.x & 31, q = blockIdx.x * WC_WARPS + (threadIdx.x >> 5);
-    if (q >= nq) return;
+__device__ __forceinline__ void win_candidates_one(const DevGrid& G, const Win* __restrict__ win, const u8* __restrict__ qdesc, int q,
+                                                   int lane, int stride, int drop_above, u32* __restrict__ list, int* __restrict__ cnt) {
     const Win w = win[q];
     int total = 0;
     if (w.flags & WIN_ACTIVE) {
@@ -205,6 +206,12 @@ __global__ void __launch_bounds__(32 * WC_WARPS) k_win_candidates(DevGrid G, con
     }
     if (lane == 0) cnt[q] = total;
 }
+__global__ void __launch_bounds__(32 * WC_WARPS) k_win_candidates(DevGrid G, const Win* __restrict__ win, const u8* __restrict__ qdesc,
+                                                                  int nq, int stride, int drop_above, u32* __restrict__ list,
+                                                                  int* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31, q = blockIdx.x * WC_WARPS + (threadIdx.x >> 5);
+    if (q < nq) win_candidates_one(G, win, qdesc, q, lane, stride, drop_above, list, cnt);
+}
 
 // ---- 3. resolution ------------------------------------------------------------------------------------------------------------
 // State per searched feature c:
@@ -226,12 +233,12 @@ __device__ __forceinline__ bool entry_avail(bool init, int th_dist, int d, int i
     return (init && d <= th_dist) ? d < thr[idx] : claimq[idx] > q;
 }
 
-__global__ void __launch_bounds__(WR_THREADS) k_win_resolve(ResolveParams P, const u32* __restrict__ list, const int* __restrict__ cnt,
-                                                            const Win* __restrict__ win, const int* __restrict__ t_octave,
-                                                            const float* __restrict__ q_angle, const float* __restrict__ t_angle,
-                                                            int* __restrict__ thr, int* __restrict__ minq, int* __restrict__ claimq,
-                                                            int* __restrict__ state, int* __restrict__ dec, int* __restrict__ qbin,
-                                                            int* __restrict__ owner, int* __restrict__ match, int* __restrict__ out_cnt) {
+__device__ __forceinline__ void win_resolve_cta(const ResolveParams& P, const u32* __restrict__ list, const int* __restrict__ cnt,
+                                                const Win* __restrict__ win, const int* __restrict__ t_octave,
+                                                const float* __restrict__ q_angle, const float* __restrict__ t_angle,
+                                                int* __restrict__ thr, int* __restrict__ minq, int* __restrict__ claimq,
+                                                int* __restrict__ state, int* __restrict__ dec, int* __restrict__ qbin,
+                                                int* __restrict__ owner, int* __restrict__ match, int* __restrict__ out_cnt) {
     __shared__ int s_unres, s_hist[ORBM_HISTO_LENGTH], s_nm, s_ind[3], s_rounds, s_entries, s_active;
     const int tid = threadIdx.x;
     const bool init = P.mode == MODE_INIT, needSecond = P.mode != MODE_BEST;
@@ -348,6 +355,43 @@ __global__ void __launch_bounds__(WR_THREADS) k_win_resolve(ResolveParams P, con
     }
     if (tid == 0) { out_cnt[0] = s_nm; out_cnt[1] = s_rounds; }
 }
+__global__ void __launch_bounds__(WR_THREADS) k_win_resolve(ResolveParams P, const u32* __restrict__ list, const int* __restrict__ cnt,
+                                                            const Win* __restrict__ win, const int* __restrict__ t_octave,
+                                                            const float* __restrict__ q_angle, const float* __restrict__ t_angle,
+                                                            int* __restrict__ thr, int* __restrict__ minq, int* __restrict__ claimq,
+                                                            int* __restrict__ state, int* __restrict__ dec, int* __restrict__ qbin,
+                                                            int* __restrict__ owner, int* __restrict__ match, int* __restrict__ out_cnt) {
+    win_resolve_cta(P, list, cnt, win, t_octave, q_angle, t_angle, thr, minq, claimq, state, dec, qbin, owner, match, out_cnt);
+}
+
+// ---- many-frame form: one job = one (CurrentFrame, LastFrame) pair; blockIdx.y (blockIdx.x in the resolve) selects the job ----
+struct WinWork {
+    Win* win; int* owner; int* match; int* out_cnt;                    // (owner, match, out_cnt) stay inside the mirrored part
+    u32* list; int* cnt; int* thr; int* minq; int* claimq; int* state; int* dec; int* qbin;
+};
+struct FrameJobDev {
+    DevGrid G; FrameProj P; int nq, stride;
+    const u8* has_point; const float* world; const int* octave; const u8* claims; const u8* desc; const float* angle;
+    WinWork w;
+};
+__global__ void k_win_frame_batch(const FrameJobDev* __restrict__ jobs) {
+    const FrameJobDev& J = jobs[blockIdx.y];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < J.nq) win_frame_one(J.G, J.P, q, J.has_point, J.world, J.octave, J.claims, J.w.win);
+}
+__global__ void __launch_bounds__(32 * WC_WARPS) k_win_candidates_batch(const FrameJobDev* __restrict__ jobs, int drop_above) {
+    const FrameJobDev& J = jobs[blockIdx.y];
+    const int lane = threadIdx.x & 31, q = blockIdx.x * WC_WARPS + (threadIdx.x >> 5);
+    if (q < J.nq) win_candidates_one(J.G, J.w.win, J.desc, q, lane, J.stride, drop_above, J.w.list, J.w.cnt);
+}
+__global__ void __launch_bounds__(WR_THREADS) k_win_resolve_batch(const FrameJobDev* __restrict__ jobs, int mode, int th_dist, int checkOri,
+                                                                  float nnratio) {
+    const FrameJobDev& J = jobs[blockIdx.x];
+    ResolveParams P;
+    P.nq = J.nq; P.nt = J.G.n; P.stride = J.stride; P.mode = mode; P.th_dist = th_dist; P.checkOri = checkOri; P.nnratio = nnratio;
+    win_resolve_cta(P, J.w.list, J.w.cnt, J.w.win, J.G.octave, J.angle, J.G.angle, J.w.thr, J.w.minq, J.w.claimq, J.w.state, J.w.dec, J.w.qbin,
+                    J.w.owner, J.w.match, J.w.out_cnt);
+}
 
 // =====================================================================================================
 // Host side
@@ -392,18 +436,16 @@ static int upload_grid(Arena& A, const orbm_grid_view* g, DevGrid* d) {
 }
 
 // outputs + scratch of one search, taken from the arena after the inputs have been flushed
-struct WinWork {
-    Win* win; int* owner; int* match; int* out_cnt;                    // (owner, match, out_cnt) stay inside the mirrored part
-    u32* list; int* cnt; int* thr; int* minq; int* claimq; int* state; int* dec; int* qbin;
-};
 static size_t work_small_bytes(int nq, int nt) { return pad((size_t)nt * 4) + pad((size_t)nq * 4) + pad(8); }
 static size_t work_scratch_bytes(int nq, int nt) {
     return pad((size_t)nq * sizeof(Win)) + pad((size_t)nq * (size_t)std::max(nt, 1) * 4) + 4 * pad((size_t)nq * 4) + 3 * pad((size_t)nt * 4);
 }
-static void take_work(Arena& A, int nq, int nt, WinWork* w) {
+static void take_work_small(Arena& A, int nq, int nt, WinWork* w) {
     w->owner = A.take<int>(std::max(nt, 1));
     w->match = A.take<int>(std::max(nq, 1));
     w->out_cnt = A.take<int>(2);
+}
+static void take_work_scratch(Arena& A, int nq, int nt, WinWork* w) {
     w->win = A.take<Win>(std::max(nq, 1));
     w->list = A.take<u32>((size_t)std::max(nq, 1) * std::max(nt, 1));
     w->cnt = A.take<int>(std::max(nq, 1));
@@ -413,6 +455,10 @@ static void take_work(Arena& A, int nq, int nt, WinWork* w) {
     w->thr = A.take<int>(std::max(nt, 1));
     w->minq = A.take<int>(std::max(nt, 1));
     w->claimq = A.take<int>(std::max(nt, 1));
+}
+static void take_work(Arena& A, int nq, int nt, WinWork* w) {
+    take_work_small(A, nq, nt, w);
+    take_work_scratch(A, nq, nt, w);
 }
 static int run_search(Arena& A, const DevGrid& G, const WinWork& w, const u8* d_qdesc, const float* d_qangle, int nq, int mode,
                       int th_dist, float nnratio, int checkOri) {
@@ -515,6 +561,84 @@ extern "C" int orbm_search_by_projection_frame(const orbm_grid_view* cur, const 
     if ((rc = A.fetch(cnt, w.out_cnt, 2))) return rc;
     if ((rc = A.finish())) return rc;
     *n_matches = cnt[0];
+    return ORB_OK;
+}
+
+// Many-frame form of the per-frame tracking search: n_jobs independent (CurrentFrame, LastFrame) pairs — several cameras or sessions
+// tracked by one process — in ONE call: all inputs in one upload, three launches (windows, candidates: grid.y = job; resolve: one CTA
+// per job, so the serial claim replay of every frame runs on its own SM), one download.  Same device code as the single call.
+static void frame_proj(const orbm_frame_search_job& j, FrameProj* P) {
+    // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw (src/ORBmatcher.cc:1344-1355); A*x+b: float32, left to right (cv::gemm on 3x3 floats)
+    const float *Tc = j.Tcw_cur, *Tl = j.Tcw_last;
+    for (int i = 0; i < 12; i++) P->T[i] = Tc[i];
+    float twc[3];
+    for (int r = 0; r < 3; r++)           // transposed product: cv::gemm's general path accumulates in double
+        twc[r] = (float)(-(((double)Tc[r] * Tc[3] + (double)Tc[4 + r] * Tc[7]) + (double)Tc[8 + r] * Tc[11]));
+    const float tlcz = ((Tl[8] * twc[0] + Tl[9] * twc[1]) + Tl[10] * twc[2]) + Tl[11];
+    P->forward = (tlcz > j.mb && !j.mono) ? 1 : 0;
+    P->backward = (-tlcz > j.mb && !j.mono) ? 1 : 0;
+    P->fx = j.fx; P->fy = j.fy; P->cx = j.cx; P->cy = j.cy; P->mbf = j.mbf; P->th = j.th;
+}
+
+extern "C" int orbm_search_by_projection_frame_batch(orbm_frame_search_job* jobs, int n_jobs, int check_orientation, int device) {
+    ORB_REQUIRE(n_jobs >= 0 && (jobs || n_jobs == 0), ORB_ERR_ARG, "bad arguments");
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (n_jobs == 0) return ORB_OK;
+    size_t bytes = pad((size_t)n_jobs * sizeof(FrameJobDev)), scratch = 0;
+    int maxNq = 0;
+    for (int k = 0; k < n_jobs; k++) {
+        const orbm_frame_search_job& j = jobs[k];
+        ORB_REQUIRE(j.cur && j.owner && j.n_last >= 0 && j.Tcw_cur && j.Tcw_last, ORB_ERR_ARG, "job %d: bad arguments", k);
+        ORB_REQUIRE(j.n_last == 0 || (j.has_point && j.world && j.octave && j.desc && j.claims && (j.angle || !check_orientation)), ORB_ERR_ARG,
+                    "job %d: null LastFrame array", k);
+        if ((rc = check_grid(j.cur, check_orientation != 0))) return rc;
+        for (int i = 0; i < j.n_last; i++)
+            ORB_REQUIRE(!j.has_point[i] || (j.octave[i] >= 0 && j.octave[i] < j.cur->n_levels), ORB_ERR_ARG, "job %d: LastFrame octave out of range", k);
+        const size_t nq = (size_t)j.n_last;
+        bytes += grid_bytes(j.cur) + 2 * pad(nq) + pad(nq * 12) + 2 * pad(nq * 4) + pad(nq * 32) + work_small_bytes(j.n_last, j.cur->n);
+        scratch += work_scratch_bytes(j.n_last, j.cur->n);
+        maxNq = std::max(maxNq, j.n_last);
+    }
+    Arena& A = g_arena;
+    if ((rc = A.ensure(device, bytes, scratch, 64u << 20))) return rc;
+    std::vector<FrameJobDev> J(n_jobs);
+    for (int k = 0; k < n_jobs; k++) {
+        const orbm_frame_search_job& j = jobs[k];
+        FrameJobDev& D = J[k];
+        const size_t nq = (size_t)j.n_last;
+        frame_proj(j, &D.P);
+        D.nq = j.n_last; D.stride = std::max(j.cur->n, 1);
+        D.angle = nullptr;
+        if ((rc = upload_grid(A, j.cur, &D.G))) return rc;
+        if ((rc = upload(A, j.has_point, nq, &D.has_point))) return rc;
+        if ((rc = upload(A, j.claims, nq, &D.claims))) return rc;
+        if ((rc = upload(A, j.world, nq * 3, &D.world))) return rc;
+        if ((rc = upload(A, j.octave, nq, &D.octave))) return rc;
+        if (check_orientation) { if ((rc = upload(A, j.angle, nq, &D.angle))) return rc; }
+        if ((rc = upload(A, j.desc, nq * 32, &D.desc))) return rc;
+    }
+    // the job table follows the inputs; the outputs (mirrored) and the scratch come after it, so their addresses are known now
+    FrameJobDev* d_jobs = A.take<FrameJobDev>(n_jobs);
+    const size_t inEnd = A.used;
+    for (int k = 0; k < n_jobs; k++) take_work_small(A, jobs[k].n_last, jobs[k].cur->n, &J[k].w);
+    for (int k = 0; k < n_jobs; k++) take_work_scratch(A, jobs[k].n_last, jobs[k].cur->n, &J[k].w);
+    if (A.staged) memcpy(A.hbase + (reinterpret_cast<u8*>(d_jobs) - A.base), J.data(), (size_t)n_jobs * sizeof(FrameJobDev));
+    else ORB_CUDA_TRY(cudaMemcpyAsync(d_jobs, J.data(), (size_t)n_jobs * sizeof(FrameJobDev), cudaMemcpyHostToDevice, A.stream));
+    if ((rc = A.flush(inEnd))) return rc;
+    if (maxNq > 0) {
+        k_win_frame_batch<<<dim3(orb_div_up(maxNq, 256), n_jobs), 256, 0, A.stream>>>(d_jobs);
+        k_win_candidates_batch<<<dim3(orb_div_up(maxNq, WC_WARPS), n_jobs), 32 * WC_WARPS, 0, A.stream>>>(d_jobs, ORBM_TH_HIGH);
+    }
+    k_win_resolve_batch<<<n_jobs, WR_THREADS, 0, A.stream>>>(d_jobs, MODE_BEST, ORBM_TH_HIGH, check_orientation, 0.f);
+    ORB_CUDA_TRY(cudaGetLastError());
+    std::vector<int> cnt(2 * (size_t)n_jobs, 0);
+    for (int k = 0; k < n_jobs; k++) {
+        if ((rc = A.fetch(jobs[k].owner, J[k].w.owner, (size_t)jobs[k].cur->n))) return rc;
+        if ((rc = A.fetch(&cnt[2 * k], J[k].w.out_cnt, 2))) return rc;
+    }
+    if ((rc = A.finish())) return rc;
+    for (int k = 0; k < n_jobs; k++) jobs[k].n_matches = cnt[2 * k];
     return ORB_OK;
 }
 

@@ -307,38 +307,80 @@ int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMap
     return nmatches;
 }
 
-int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+namespace {
+// flat copy of what SearchByProjection(CurrentFrame, LastFrame) reads of the two frames (src/ORBmatcher.cc:1344-1396)
+struct FramePairSide {
     GridSide g;
-    snapshot_frame_grid(CurrentFrame, true, g);
     float Tc[12], Tl[12];
+    std::vector<unsigned char> has, claims, desc;
+    std::vector<float> world, angle;
+    std::vector<int> octave, owner;
+};
+void snapshot_frame_pair(Frame& CurrentFrame, const Frame& LastFrame, FramePairSide& s) {
+    snapshot_frame_grid(CurrentFrame, true, s.g);
     for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 4; c++) { Tc[4 * r + c] = CurrentFrame.mTcw.at<float>(r, c); Tl[4 * r + c] = LastFrame.mTcw.at<float>(r, c); }
+        for (int c = 0; c < 4; c++) { s.Tc[4 * r + c] = CurrentFrame.mTcw.at<float>(r, c); s.Tl[4 * r + c] = LastFrame.mTcw.at<float>(r, c); }
     const int nl = LastFrame.N;
-    std::vector<unsigned char> has(nl, 0), claims(nl, 0), desc((size_t)nl * 32);
-    std::vector<float> world((size_t)nl * 3), angle(nl);
-    std::vector<int> octave(nl);
+    s.has.assign(nl, 0); s.claims.assign(nl, 0); s.desc.assign((size_t)nl * 32, 0);
+    s.world.assign((size_t)nl * 3, 0.f); s.angle.assign(nl, 0.f); s.octave.assign(nl, 0);
     for (int i = 0; i < nl; i++) {
         MapPoint* pMP = LastFrame.mvpMapPoints[i];
         if (!pMP || LastFrame.mvbOutlier[i]) continue;                                   // ORBmatcher.cc:1359-1363
-        has[i] = 1;
+        s.has[i] = 1;
         const cv::Mat x3Dw = pMP->GetWorldPos();
-        for (int k = 0; k < 3; k++) world[3 * (size_t)i + k] = x3Dw.at<float>(k);
-        octave[i] = LastFrame.mvKeys[i].octave;
-        angle[i] = LastFrame.mvKeysUn[i].angle;
-        claims[i] = pMP->Observations() > 0 ? 1 : 0;
+        for (int k = 0; k < 3; k++) s.world[3 * (size_t)i + k] = x3Dw.at<float>(k);
+        s.octave[i] = LastFrame.mvKeys[i].octave;
+        s.angle[i] = LastFrame.mvKeysUn[i].angle;
+        s.claims[i] = pMP->Observations() > 0 ? 1 : 0;
         const cv::Mat d = pMP->GetDescriptor();
-        std::memcpy(&desc[(size_t)i * 32], d.ptr(0), 32);
+        std::memcpy(&s.desc[(size_t)i * 32], d.ptr(0), 32);
     }
-    std::vector<int> owner(CurrentFrame.N > 0 ? CurrentFrame.N : 1, -1);
-    int nmatches = 0;
-    report(orbm_search_by_projection_frame(&g.view, Tc, Tl, CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy,
-                                           CurrentFrame.mbf, CurrentFrame.mb, nl, has.data(), world.data(), octave.data(), angle.data(),
-                                           desc.data(), claims.data(), th, bMono ? 1 : 0, mbCheckOrientation ? 1 : 0, owner.data(),
-                                           &nmatches, g_device));
-    if (g_status != ORB_OK) return 0;
+    s.owner.assign(CurrentFrame.N > 0 ? CurrentFrame.N : 1, -1);
+}
+void apply_frame_owner(Frame& CurrentFrame, const Frame& LastFrame, const std::vector<int>& owner) {
     for (int j = 0; j < CurrentFrame.N; j++) {
         if (owner[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[owner[j]];
         else if (owner[j] == -2) CurrentFrame.mvpMapPoints[j] = static_cast<MapPoint*>(NULL);   // rotation cull, :1452-1456
+    }
+}
+}  // namespace
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+    FramePairSide s;
+    snapshot_frame_pair(CurrentFrame, LastFrame, s);
+    int nmatches = 0;
+    report(orbm_search_by_projection_frame(&s.g.view, s.Tc, s.Tl, CurrentFrame.fx, CurrentFrame.fy, CurrentFrame.cx, CurrentFrame.cy,
+                                           CurrentFrame.mbf, CurrentFrame.mb, LastFrame.N, s.has.data(), s.world.data(), s.octave.data(),
+                                           s.angle.data(), s.desc.data(), s.claims.data(), th, bMono ? 1 : 0, mbCheckOrientation ? 1 : 0,
+                                           s.owner.data(), &nmatches, g_device));
+    if (g_status != ORB_OK) return 0;
+    apply_frame_owner(CurrentFrame, LastFrame, s.owner);
+    return nmatches;
+}
+
+std::vector<int> ORBmatcher::SearchByProjection(const std::vector<Frame*>& vpCurrentFrames, const std::vector<const Frame*>& vpLastFrames,
+                                                const float th, const bool bMono) {
+    const size_t n = std::min(vpCurrentFrames.size(), vpLastFrames.size());
+    std::vector<FramePairSide> sides(n);
+    std::vector<orbm_frame_search_job> jobs(n);
+    for (size_t k = 0; k < n; k++) {
+        Frame& C = *vpCurrentFrames[k];
+        FramePairSide& s = sides[k];
+        snapshot_frame_pair(C, *vpLastFrames[k], s);
+        orbm_frame_search_job& j = jobs[k];
+        std::memset(&j, 0, sizeof(j));
+        j.cur = &s.g.view; j.Tcw_cur = s.Tc; j.Tcw_last = s.Tl;
+        j.fx = C.fx; j.fy = C.fy; j.cx = C.cx; j.cy = C.cy; j.mbf = C.mbf; j.mb = C.mb;
+        j.n_last = vpLastFrames[k]->N;
+        j.has_point = s.has.data(); j.world = s.world.data(); j.octave = s.octave.data(); j.angle = s.angle.data();
+        j.desc = s.desc.data(); j.claims = s.claims.data(); j.th = th; j.mono = bMono ? 1 : 0; j.owner = s.owner.data();
+    }
+    std::vector<int> nmatches(n, 0);
+    report(orbm_search_by_projection_frame_batch(jobs.data(), (int)n, mbCheckOrientation ? 1 : 0, g_device));
+    if (g_status != ORB_OK) return nmatches;
+    for (size_t k = 0; k < n; k++) {
+        apply_frame_owner(*vpCurrentFrames[k], *vpLastFrames[k], sides[k].owner);
+        nmatches[k] = jobs[k].n_matches;
     }
     return nmatches;
 }

@@ -40,6 +40,10 @@ public:
     // Project MapPoints tracked in last frame into the current frame and search matches.  Used to track from previous frame
     // (Tracking) (reference :52, src/ORBmatcher.cc:1331-1463)
     int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono);
+    // Batched overload (not in the reference): independent (CurrentFrame, LastFrame) pairs — several cameras or sessions tracked by one
+    // process — as one device call; element i equals the single overload on pair i.
+    std::vector<int> SearchByProjection(const std::vector<Frame*>& vpCurrentFrames, const std::vector<const Frame*>& vpLastFrames,
+                                        const float th, const bool bMono);
     // Project MapPoints seen in KeyFrame into the Frame and search matches.  Used in relocalisation (Tracking)
     // (reference :56, src/ORBmatcher.cc:1465-1602)
     int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);

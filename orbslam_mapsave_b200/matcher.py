@@ -205,6 +205,32 @@ class ORBmatcher:
                                                               int(self.mbCheckOrientation), capi._p(owner), C.byref(n), self.device))
         return n.value, owner[:cur.n]
 
+    def SearchByProjectionFrameBatch(self, jobs):
+        """Many-frame form (orbm_search_by_projection_frame_batch): `jobs` is a list of argument tuples of SearchByProjectionFrame, one per
+        independent (CurrentFrame, LastFrame) pair.  Returns [(nmatches, owner), ...], identical to calling the single form per job."""
+        u8 = lambda a: np.ascontiguousarray(a, np.uint8)
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        J = (capi.FrameSearchJobC * max(len(jobs), 1))()
+        keep, owners = [], []
+        for k, (cur, Tcw_cur, Tcw_last, fx, fy, cx, cy, mbf, mb, has_point, world, octave, angle, desc, claims, th, bMono) in enumerate(jobs):
+            has_point, claims, desc = u8(has_point), u8(claims), u8(desc).reshape(-1, 32)
+            world, angle = f32(world).reshape(-1, 3), f32(angle)
+            octave = np.ascontiguousarray(octave, np.int32)
+            Tc, Tl = f32(Tcw_cur).reshape(-1)[:12].copy(), f32(Tcw_last).reshape(-1)[:12].copy()
+            g = cur.c()
+            owner = np.zeros(max(cur.n, 1), np.int32)
+            keep.append((g, has_point, claims, desc, world, angle, octave, Tc, Tl))
+            owners.append((owner, cur.n))
+            j = J[k]
+            j.cur = C.pointer(g)
+            j.Tcw_cur, j.Tcw_last = capi._p(Tc), capi._p(Tl)
+            j.fx, j.fy, j.cx, j.cy, j.mbf, j.mb = fx, fy, cx, cy, mbf, mb
+            j.n_last = len(has_point)
+            j.has_point, j.world, j.octave, j.angle = capi._p(has_point), capi._p(world), capi._p(octave), capi._p(angle)
+            j.desc, j.claims, j.th, j.mono, j.owner = capi._p(desc), capi._p(claims), float(th), int(bMono), capi._p(owner)
+        capi.check(capi.lib().orbm_search_by_projection_frame_batch(C.cast(J, C.c_void_p), len(jobs), int(self.mbCheckOrientation), self.device))
+        return [(J[k].n_matches, owners[k][0][:owners[k][1]]) for k in range(len(jobs))]
+
     def SearchForInitialization(self, f2, desc1, octave1, angle1, prev_matched, windowSize=10):
         """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:408-523).
         prev_matched: (n1, 2) float32, updated in place.  Returns (nmatches, vnMatches12)."""

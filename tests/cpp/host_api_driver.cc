@@ -297,6 +297,7 @@ static int run_project(int argc, char** argv) {
             if (has[i]) L->mvpMapPoints[i] = &pool[i];
             else if (i % 2) { L->mvpMapPoints[i] = &pool[i]; L->mvbOutlier[i] = true; }      // outliers are skipped like missing points
         }
+        const std::vector<MapPoint*> before = C->mvpMapPoints;
         const int n = m.SearchByProjection(*C, *L, th, mono != 0);
         put(out, &n, 1);
         std::vector<int> owner(C->N, -1);
@@ -306,6 +307,14 @@ static int run_project(int argc, char** argv) {
             else if (!p && (j % 3 == 0 || blocked[j])) owner[j] = -2;                        // a pre-existing point was set to NULL
         }
         put(out, owner.data(), owner.size());
+        // the batched overload on three copies of the pair must leave every copy exactly like the single call left C
+        Frame* Cs[3];
+        for (int k = 0; k < 3; k++) { Cs[k] = new Frame(*C); Cs[k]->mvpMapPoints = before; }
+        const std::vector<int> nb = m.SearchByProjection(std::vector<Frame*>(Cs, Cs + 3), std::vector<const Frame*>(3, L), th, mono != 0);
+        int batch_ok = nb.size() == 3 ? 1 : 0;
+        for (int k = 0; k < 3 && batch_ok; k++) batch_ok = (nb[k] == n && Cs[k]->mvpMapPoints == C->mvpMapPoints) ? 1 : 0;
+        put(out, &batch_ok, 1);
+        for (int k = 0; k < 3; k++) delete Cs[k];
         delete C; delete L;
     }
     {   // SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)

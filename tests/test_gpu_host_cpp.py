@@ -255,6 +255,8 @@ def test_cpp_window_searches_match_oracle(tmp_path, seed, mono, ori):
     had_point = (np.arange(n) % 3 == 0) | (blockedB != 0)
     want = np.where((oo == -2) & ~had_point, -1, oo)        # NULLing an entry that held nothing is invisible to the caller
     assert nm == on and np.array_equal(got, want) and (oo >= 0).sum() > 100
+    (batch_ok,) = struct.unpack_from("<i", out, pos); pos += 4      # the batched overload on three copies == the single call
+    assert batch_ok == 1
     # C
     nm, sz = struct.unpack_from("<ii", out, pos); pos += 8
     got = np.frombuffer(out, np.int32, sz, pos); pos += 4 * sz

@@ -65,6 +65,39 @@ def test_search_by_projection_last_frame(n, nlast, seed, mono, tz, ori, cluster)
             assert (want == -2).sum() > 0            # the rotation cull fired
 
 
+@pytest.mark.parametrize("ori", [True, False])
+def test_search_by_projection_last_frame_batch(ori):
+    """orbm_search_by_projection_frame_batch: ragged jobs (different feature counts, mono / stereo, forward / backward motion, an empty
+    LastFrame, a three-feature frame) in one call == the oracle per job == the single call per job."""
+    specs = [(2000, 2000, 130, True, 0.0, False), (2000, 2000, 131, False, 0.5, False), (1500, 2500, 132, False, -0.5, True),
+             (1200, 3000, 133, False, 0.0, True), (2000, 0, 134, True, 0.0, False), (3, 10, 135, False, 0.0, False),
+             (4000, 4000, 136, False, 0.0, False), (2000, 2000, 137, True, 0.0, True)]
+    jobs, ojobs = [], []
+    for n, nlast, seed, mono, tz, cluster in specs:
+        rng = np.random.default_rng(seed)
+        fa = pu.frame_arrays(n, rng, stereo=not mono, cluster=cluster)
+        blocked = (rng.random(n) < 0.1).astype(np.uint8)
+        g, og = pu.make_grids(fa, blocked, orb, orc)
+        lf = pu.last_frame_for(fa, nlast, rng, tz=tz)
+        mbf, mb, th = 40.0, 40.0 / lf["fx"], 15.0 if mono else 7.0
+        args = (lf["Tcw"], lf["Tlw"], lf["fx"], lf["fy"], lf["cx"], lf["cy"], mbf, mb, lf["has_point"], lf["world"], lf["octave"], lf["angle"],
+                lf["desc"], lf["claims"], th, mono)
+        jobs.append((g,) + args)
+        ojobs.append((og,) + args)
+    m = orb.ORBmatcher(0.9, ori)
+    got = m.SearchByProjectionFrameBatch(jobs)
+    assert len(got) == len(specs)
+    total = 0
+    for k, (gn, gown) in enumerate(got):
+        wn, wown = orc.search_projection_frame(*ojobs[k], ori)
+        sn, sown = m.SearchByProjectionFrame(*jobs[k])
+        assert gn == wn == sn, k
+        assert np.array_equal(gown, wown) and np.array_equal(gown, sown), k
+        total += wn
+    assert total > 3000
+    assert m.SearchByProjectionFrameBatch([]) == []
+
+
 @pytest.mark.parametrize("n2,n1,seed,window,ori", [(2000, 2000, 40, 100, True), (2000, 2000, 41, 10, True), (1000, 3000, 42, 50, False),
                                                    (2000, 0, 43, 100, True), (2, 9, 44, 100, True), (6000, 6000, 45, 100, True)])
 def test_search_for_initialization(n2, n1, seed, window, ori):
