@@ -489,7 +489,8 @@ def main():
             pageable_step()
         ps = (time.perf_counter() - t0) / kp_
         e2e["pageable_caller_buffers"] = {"value": nF / ps, "unit": "frames/s", "ms_per_step": 1e3 * ps,
-                                          "note": "orbx_extract_batch from ordinary (unpinned) host arrays"}
+                                          "note": "orbx_extract_batch from ordinary (unpinned) host arrays: the handle's host-thread pool stages "
+                                                  "them through pinned memory (non-temporal copies); 28 k frames/s before the pool existed"}
         # the same arrays after the caller registered them once (orbx_host_register = cudaHostRegister)
         t0 = time.perf_counter()
         for a_ in (p_frames, p_kp, p_desc):

@@ -166,6 +166,43 @@ def test_ramped_chunk_schedule_matches_single_calls():
     _compare(kp[137, :n[137]], desc[137, :n[137]], okp, odesc)
 
 
+def test_pageable_strided_and_pinned_pipelines_agree():
+    """orbx_extract_batch with slot reuse (700 frames in 64-frame chunks over six slots): ordinary numpy memory (host-pool staging in and
+    out), a strided view of a wider array (rows packed by the pool) and page-locked buffers (direct DMA) must give identical results."""
+    import ctypes as C
+    import torch
+    from orbslam_mapsave_b200 import capi
+    base = [synth(640, 480, s) for s in range(60, 67)]
+    frames = np.stack([np.roll(base[i % 7], 5 * (i // 7), axis=0) for i in range(700)])
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=64)
+    kp, desc, n = ex.extract_batch(frames)                               # pageable in, pageable out
+    cap = ex.max_keypoints()
+    wide = np.zeros((700, 483, 656), np.uint8)
+    wide[:, :480, :640] = frames
+    kp2 = np.zeros((700, cap), capi.KP_DTYPE)
+    desc2 = np.zeros((700, cap, 32), np.uint8)
+    n2 = np.zeros(700, np.int32)
+    capi.check(capi.lib().orbx_extract_batch(ex.handle, capi._p(wide), 700, 640, 480, 656, 483 * 656, None, 0, 0, capi._p(kp2), capi._p(desc2),
+                                             cap, capi._p(n2)))
+    h_frames = torch.from_numpy(frames).pin_memory()
+    h_kp = torch.zeros((700, cap, 7), dtype=torch.float32).pin_memory()
+    h_desc = torch.zeros((700, cap, 32), dtype=torch.uint8).pin_memory()
+    n3 = np.zeros(700, np.int32)
+    capi.check(capi.lib().orbx_extract_batch(ex.handle, capi._p(h_frames), 700, 640, 480, 640, 640 * 480, None, 0, 0, capi._p(h_kp),
+                                             capi._p(h_desc), cap, capi._p(n3)))
+    kp3 = h_kp.numpy().view(np.uint32)
+    assert np.array_equal(n, n2) and np.array_equal(n, n3) and n.min() > 900
+    for f in range(700):
+        a = kp[f, :n[f]].view(np.uint32).reshape(-1, 7)
+        assert np.array_equal(a, kp2[f, :n[f]].view(np.uint32).reshape(-1, 7)), f
+        assert np.array_equal(a, kp3[f, :n[f]]), f
+        assert np.array_equal(desc[f, :n[f]], desc2[f, :n[f]]) and np.array_equal(desc[f, :n[f]], h_desc[f, :n[f]].numpy()), f
+    one = orb.ORBextractor(1000, 1.2, 8, 20, 7)
+    for f in (0, 63, 64, 389, 699):
+        k1, d1 = one(frames[f])
+        assert n[f] == len(k1) and np.array_equal(kp[f, :n[f]].tobytes(), k1.tobytes()) and np.array_equal(desc[f, :n[f]], d1), f
+
+
 def test_device_resident_multi_pass_matches_single_calls():
     """orbx_extract_batch_device over more frames than the workspace holds runs several passes; results must land in the right
     rows and equal single-frame calls, and later work on the caller's stream must see them."""
