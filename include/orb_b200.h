@@ -175,6 +175,15 @@ int orbm_hamming_top2_batch_device(const uint8_t* d_q, const int* d_q_off, const
 int orbm_allpairs_device(const uint8_t* d_desc, int n_kf, int per_kf, int q_begin, int q_end, int th_low, float ratio,
                          uint16_t* d_count, int* d_best_kf, int* d_best_dist, void* stream);
 
+/* The same on several GPUs of one node from ONE process (the multi-GPU form of SURVEY §8e for a C / C++ host; under torchrun the
+ * per-rank call above plus one all-gather does the same).  desc: HOST pointer, n_kf x per_kf x 32 bytes; devices[n_devices]: CUDA ordinals
+ * (a device may be listed more than once: its shards run on separate streams).  The database is uploaded once and replicated device
+ * to device (NVLink where peer access exists); query keyframes are sharded contiguously and evenly over the listed devices, one host thread
+ * each; the gather of the shard tables into count_out — HOST, n_kf x n_kf uint16, row = query keyframe — is the only exchange.
+ * best_kf_out / best_dist_out (HOST, n_kf x per_kf ints, or both NULL) as in orbm_allpairs_device.  Blocks until done. */
+int orbm_allpairs_multi(const uint8_t* desc, int n_kf, int per_kf, int th_low, float ratio, const int* devices, int n_devices,
+                        uint16_t* count_out, int* best_kf_out, int* best_dist_out);
+
 /* A DBoW2::FeatureVector (Thirdparty/DBoW2/DBoW2/FeatureVector.h:21-22, std::map<NodeId, vector<unsigned>>) flattened:
  * node ids ascending, CSR offsets (n_nodes+1), feature indices (ascending inside a node, as transform() appends). */
 typedef struct orbm_featvec {

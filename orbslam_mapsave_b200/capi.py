@@ -26,7 +26,7 @@ SYMBOLS = [
     "orbx_create", "orbx_destroy", "orbx_tables", "orbx_compute_tables", "orbx_level_size", "orbx_max_keypoints", "orbx_extract",
     "orbx_extract_batch", "orbx_extract_batch_device", "orbx_host_register", "orbx_host_unregister", "orbx_check_status", "orbx_get_pyramid_level", "orbx_get_pyramid",
     "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device", "orbx_stereo_matches",
-    "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device",
+    "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device", "orbm_allpairs_multi",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
     "orbm_search_by_bow_batch", "orbm_search_for_triangulation_batch",
     "orbm_popc_peak", "orbm_distinctive_descriptors", "orb_h2d_probe",
@@ -151,6 +151,8 @@ def lib():
     L.orbm_hamming_top2_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.orbm_allpairs_device.restype = i32
     L.orbm_allpairs_device.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.orbm_allpairs_multi.restype = i32
+    L.orbm_allpairs_multi.argtypes = [vp, i32, i32, i32, f32, vp, i32, vp, vp, vp]
     L.orbm_search_by_bow_kf_frame.restype = i32
     L.orbm_search_by_bow_kf_frame.argtypes = [C.POINTER(ViewC), C.POINTER(ViewC), f32, i32, vp, vp, i32]
     L.orbm_search_by_bow_kf_kf.restype = i32

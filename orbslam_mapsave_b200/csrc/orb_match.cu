@@ -638,6 +638,119 @@ extern "C" int orbm_allpairs_device(const uint8_t* d_desc, int n_kf, int per_kf,
     return ORB_OK;
 }
 
+// All-pairs keyframe matching on several GPUs of one node driven from ONE process (SURVEY §8e as a C entry: the C++ host of a
+// map-merging / loop-closing service has no torch.distributed).  One host thread per device.  The descriptor database is uploaded once,
+// to the first device, and replicated from there device-to-device (cudaMemcpyPeerAsync: NVLink where peer access exists); query keyframes
+// are sharded contiguously over the devices; the gather of the per-shard match tables into the caller's table is the only exchange.
+// The same device may be listed more than once (its shards then run on separate streams), which is how the single-GPU tests cover the
+// sharding logic.
+#include <thread>
+extern "C" int orbm_allpairs_multi(const uint8_t* desc, int n_kf, int per_kf, int th_low, float ratio, const int* devices, int n_devices,
+                                   uint16_t* count_out, int* best_kf_out, int* best_dist_out) {
+    ORB_REQUIRE(desc && count_out && devices && n_devices > 0 && n_devices <= 64 && n_kf > 0 && per_kf > 0, ORB_ERR_ARG, "bad arguments");
+    ORB_REQUIRE((best_kf_out == nullptr) == (best_dist_out == nullptr), ORB_ERR_ARG, "best_kf_out and best_dist_out go together");
+    ORB_REQUIRE(n_kf <= 65535 && per_kf <= 65535, ORB_ERR_ARG, "n_kf / per_kf above 65535");
+    const int ndev = orb_device_count();
+    ORB_REQUIRE(ndev > 0, ORB_ERR_CUDA, "no CUDA device (no CPU fallback)");
+    for (int i = 0; i < n_devices; i++) ORB_REQUIRE(devices[i] >= 0 && devices[i] < ndev, ORB_ERR_CUDA, "CUDA device %d not available", devices[i]);
+    const size_t dbBytes = (size_t)n_kf * per_kf * 32;
+    struct Shard {
+        int dev = 0, q0 = 0, q1 = 0, rc = ORB_OK;
+        u8* d_desc = nullptr; uint16_t* d_count = nullptr; int *d_bk = nullptr, *d_bd = nullptr;
+        cudaStream_t st = nullptr; cudaEvent_t ready = nullptr;
+        bool ownsDb = false;
+        char err[256] = "";
+    };
+    std::vector<Shard> sh(n_devices);
+    const int base = n_kf / n_devices, rem = n_kf % n_devices;
+    for (int i = 0; i < n_devices; i++) {
+        sh[i].dev = devices[i];
+        sh[i].q0 = i * base + std::min(i, rem);
+        sh[i].q1 = sh[i].q0 + base + (i < rem ? 1 : 0);
+    }
+    // phase 1 (this thread): allocations, the one upload, and the device-to-device replication, all asynchronous
+    auto fail = [&](Shard& s, cudaError_t e, const char* what) {
+        s.rc = ORB_ERR_CUDA;
+        snprintf(s.err, sizeof(s.err), "%s failed on device %d: %s", what, s.dev, cudaGetErrorString(e));
+        cudaGetLastError();
+    };
+#define MG_TRY(s, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(s, e_, #call); goto done; } } while (0)
+    {
+        for (int i = 0; i < n_devices; i++) {
+            Shard& s = sh[i];
+            MG_TRY(s, cudaSetDevice(s.dev));
+            MG_TRY(s, cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+            MG_TRY(s, cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+            // devices listed twice share the first listing's copy of the database
+            int first = i;
+            for (int j = 0; j < i; j++) if (sh[j].dev == s.dev) { first = j; break; }
+            if (first == i) { MG_TRY(s, cudaMalloc(&s.d_desc, dbBytes)); s.ownsDb = true; }
+            else s.d_desc = sh[first].d_desc;
+            const int nq = s.q1 - s.q0;
+            MG_TRY(s, cudaMalloc(&s.d_count, orb_align_up((size_t)std::max(nq, 1) * n_kf * 2, 4)));
+            if (best_kf_out) {
+                MG_TRY(s, cudaMalloc(&s.d_bk, (size_t)std::max(nq, 1) * per_kf * 4));
+                MG_TRY(s, cudaMalloc(&s.d_bd, (size_t)std::max(nq, 1) * per_kf * 4));
+            }
+        }
+        MG_TRY(sh[0], cudaSetDevice(sh[0].dev));
+        MG_TRY(sh[0], cudaMemcpyAsync(sh[0].d_desc, desc, dbBytes, cudaMemcpyHostToDevice, sh[0].st));
+        MG_TRY(sh[0], cudaEventRecord(sh[0].ready, sh[0].st));
+        for (int i = 1; i < n_devices; i++) {
+            Shard& s = sh[i];
+            MG_TRY(s, cudaSetDevice(s.dev));
+            int src = 0;
+            for (int j = 0; j < i; j++) if (sh[j].dev == s.dev) { src = j; break; }
+            MG_TRY(s, cudaStreamWaitEvent(s.st, sh[src].ready, 0));        // the copy this shard reads (its own device's, or device 0's) has landed
+            if (s.ownsDb) {
+                MG_TRY(s, cudaMemcpyPeerAsync(s.d_desc, s.dev, sh[0].d_desc, sh[0].dev, dbBytes, s.st));
+            }
+            MG_TRY(s, cudaEventRecord(s.ready, s.st));
+        }
+    }
+    // phase 2: one host thread per shard — kernel, download of its rows straight into the caller's table
+    {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_devices; i++)
+            th.emplace_back([&, i] {
+                Shard& s = sh[i];
+                const int nq = s.q1 - s.q0;
+                auto chk = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && s.rc == ORB_OK) fail(s, e, what); return e == cudaSuccess; };
+                if (!chk(cudaSetDevice(s.dev), "cudaSetDevice")) return;
+                if (nq > 0) {
+                    const int rc = orbm_allpairs_device(s.d_desc, n_kf, per_kf, s.q0, s.q1, th_low, ratio, s.d_count, s.d_bk, s.d_bd, s.st);
+                    if (rc != ORB_OK) { s.rc = rc; snprintf(s.err, sizeof(s.err), "%s", orb_last_error()); return; }
+                    if (!chk(cudaMemcpyAsync(count_out + (size_t)s.q0 * n_kf, s.d_count, (size_t)nq * n_kf * 2, cudaMemcpyDeviceToHost, s.st), "D2H counts")) return;
+                    if (best_kf_out) {
+                        if (!chk(cudaMemcpyAsync(best_kf_out + (size_t)s.q0 * per_kf, s.d_bk, (size_t)nq * per_kf * 4, cudaMemcpyDeviceToHost, s.st), "D2H best_kf")) return;
+                        if (!chk(cudaMemcpyAsync(best_dist_out + (size_t)s.q0 * per_kf, s.d_bd, (size_t)nq * per_kf * 4, cudaMemcpyDeviceToHost, s.st), "D2H best_dist")) return;
+                    }
+                }
+                chk(cudaStreamSynchronize(s.st), "cudaStreamSynchronize");
+            });
+        for (std::thread& t : th) t.join();
+    }
+done:
+#undef MG_TRY
+    int rc = ORB_OK;
+    for (int i = 0; i < n_devices; i++) {
+        Shard& s = sh[i];
+        if (s.rc != ORB_OK && rc == ORB_OK) { rc = s.rc; orb_set_error("%s", s.err); }
+        if (cudaSetDevice(s.dev) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (s.st) cudaStreamSynchronize(s.st);
+    }
+    for (int i = 0; i < n_devices; i++) {
+        Shard& s = sh[i];
+        if (cudaSetDevice(s.dev) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (s.ownsDb) cudaFree(s.d_desc);
+        cudaFree(s.d_count); cudaFree(s.d_bk); cudaFree(s.d_bd);
+        if (s.ready) cudaEventDestroy(s.ready);
+        if (s.st) cudaStreamDestroy(s.st);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
 static size_t view_bytes(const orbm_view* v, bool tri) {
     size_t b = pad((size_t)v->n * 32) + pad(v->n) + pad((size_t)v->n * 4);
     if (tri) b += 4 * pad((size_t)v->n * 4);

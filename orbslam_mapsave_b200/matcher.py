@@ -285,6 +285,21 @@ class ORBmatcher:
         return tuple(int(v) for v in ind)
 
 
+def allpairs_multi(desc, th_low=capi.TH_LOW, ratio=0.75, devices=(0,), want_best=False):
+    """All-pairs keyframe matching (BASELINE config 4) on the listed GPUs from this one process (orbm_allpairs_multi).
+    desc: (n_kf, per_kf, 32) uint8 host array.  Returns the (n_kf, n_kf) uint16 table of ratio-test matches per (query keyframe, keyframe)
+    and, with want_best, per query descriptor the keyframe holding its nearest descriptor and that distance."""
+    desc = np.ascontiguousarray(desc, np.uint8)
+    n_kf, per_kf = desc.shape[0], desc.shape[1]
+    dev = np.ascontiguousarray(devices, np.int32)
+    counts = np.zeros((n_kf, n_kf), np.uint16)
+    bk = np.zeros((n_kf, per_kf), np.int32) if want_best else None
+    bd = np.zeros((n_kf, per_kf), np.int32) if want_best else None
+    capi.check(capi.lib().orbm_allpairs_multi(capi._p(desc), n_kf, per_kf, int(th_low), float(ratio), capi._p(dev), len(dev), capi._p(counts),
+                                              capi._p(bk), capi._p(bd)))
+    return (counts, bk, bd) if want_best else counts
+
+
 def distinctive_descriptors(desc, offsets, device=0):
     """MapPoint::ComputeDistinctiveDescriptors for a batch of map points (src/MapPoint.cc:483-548): index, inside each set
     desc[offsets[s]:offsets[s+1]], of the descriptor with the least median distance to the set."""

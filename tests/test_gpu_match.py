@@ -205,6 +205,49 @@ def test_allpairs_counts_and_best_vs_oracle():
         assert np.array_equal(bd[qi], best_d) and np.array_equal(bkf[qi], best_k)
 
 
+@pytest.mark.parametrize("devices", [(0,), (0, 0, 0), (0, 0, 0, 0, 0, 0, 0, 0, 0)])
+def test_allpairs_multi_shards_and_gathers_like_the_oracle(devices):
+    """orbm_allpairs_multi: query keyframes sharded over the listed devices (a device listed several times = several shards, more
+    shards than keyframes = empty shards), one host thread per shard, rows gathered into the caller's table."""
+    import torch
+    from orbslam_mapsave_b200.matcher import allpairs_multi
+    if max(devices) >= torch.cuda.device_count():
+        pytest.skip("not enough GPUs")
+    n_kf, per = 7, 260
+    base = synth_descriptors(per, 300)
+    desc = np.stack([base] + [synth_descriptors(per, 301 + i, dup_of=base, dup_rate=0.4) for i in range(n_kf - 1)])
+    cnt, bk, bd = allpairs_multi(desc, 50, 0.75, devices, want_best=True)
+    for q in range(n_kf):
+        best_d = np.full(per, 1 << 30)
+        best_k = np.full(per, -1)
+        for k in range(n_kf):
+            if k == q:
+                assert cnt[q, k] == 0
+                continue
+            _, b1, b2 = orc.hamming_top2(desc[q], desc[k])
+            ok = (b1 <= 50) & (b1.astype(np.float32) < np.float32(0.75) * b2.astype(np.float32))
+            assert cnt[q, k] == int(ok.sum()), (q, k)
+            upd = b1 < best_d
+            best_k[upd] = k
+            best_d[upd] = b1[upd]
+        assert np.array_equal(bd[q], best_d) and np.array_equal(bk[q], best_k)
+    assert np.array_equal(allpairs_multi(desc, 50, 0.75, devices), cnt)
+
+
+def test_allpairs_multi_every_visible_gpu():
+    """With N GPUs visible the table from all of them equals the single-GPU table (runs as a 1-GPU identity check on a 1-GPU box)."""
+    import torch
+    from orbslam_mapsave_b200.matcher import allpairs_multi
+    n_kf, per = 24, 500
+    base = synth_descriptors(per, 400)
+    desc = np.stack([base] + [synth_descriptors(per, 401 + i, dup_of=base, dup_rate=0.3) for i in range(n_kf - 1)])
+    one = allpairs_multi(desc, 50, 0.75, (0,))
+    every = allpairs_multi(desc, 50, 0.75, tuple(range(torch.cuda.device_count())))
+    assert np.array_equal(one, every) and one.sum() > 0
+    with pytest.raises(orb.OrbError):
+        allpairs_multi(desc, 50, 0.75, (torch.cuda.device_count(),))
+
+
 def test_popc_peak_is_sane():
     v, clk = orb.popc_peak()
     print(f"POPC peak {v / 1e12:.3f} T/s at nominal {clk / 1e9:.3f} GHz -> {v / clk / 148:.2f} POPC/clk/SM")
