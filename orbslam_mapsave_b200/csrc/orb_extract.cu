@@ -98,25 +98,43 @@ __global__ void __launch_bounds__(256) k_level0(const __grid_constant__ Plan P, 
     *reinterpret_cast<u32*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = out;
 }
 
-// 16 pixels per thread with 128-bit loads / stores when the frame width and base pointers are 16-byte aligned (VGA, 720p, 4K ...)
+// 16-pixel groups with 128-bit loads / stores when the frame width and base pointers are 16-byte aligned (VGA, 720p, 4K ...).  A pure
+// copy is bound by bytes in flight: flat indexing over the groups of a frame (no idle lanes at the row end: 640 / 16 = 40 groups do not
+// fill 64-lane rows) and FOUR independent loads per thread before the first store.
+#define L0_UNROLL 4
 __global__ void __launch_bounds__(256) k_level0_v16(const __grid_constant__ Plan P, const u8* __restrict__ images,
-                                                    const u8* __restrict__ masks, u8* __restrict__ pyr) {
+                                                    const u8* __restrict__ masks, u8* __restrict__ pyr, u32 gprInv) {
     const LevelPlan& L = P.lv[0];
-    const int x = (blockIdx.x * 64 + threadIdx.x) * 16, y = blockIdx.y * 4 + threadIdx.y, f = blockIdx.z;
-    if (x >= L.w || y >= L.h) return;
-    const size_t fo = (size_t)f * P.width * P.height + (size_t)y * P.width + x;
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(images + fo));
-    if (masks) {
-        const uint4 m = __ldg(reinterpret_cast<const uint4*>(masks + fo));
-        // per byte: keep the pixel where the mask byte is non-zero (0x80 trick: (m | (m & 0x7f..) + 0x7f..) & 0x80.. marks non-zero bytes)
-        auto keep = [](u32 px, u32 mk) {
-            const u32 nz = ((mk & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | mk;       // bit 7 of each byte set iff that mask byte != 0
-            const u32 full = ((nz & 0x80808080u) >> 7) * 0xFFu;            // 0xFF in the bytes to keep
-            return px & full;
-        };
-        v.x = keep(v.x, m.x); v.y = keep(v.y, m.y); v.z = keep(v.z, m.z); v.w = keep(v.w, m.w);
+    const u32 gpr = (u32)L.w >> 4, total = gpr * (u32)L.h;              // groups per row / per frame
+    const int f = blockIdx.y;
+    const size_t fo = (size_t)f * P.width * P.height;
+    u8* dst0 = pyr + (size_t)f * P.frameBytes + L.off + (size_t)ORBX_OY * L.pitch + ORBX_OX;
+    const u32 g0 = blockIdx.x * (256 * L0_UNROLL) + threadIdx.x;
+    uint4 v[L0_UNROLL], m[L0_UNROLL];
+#pragma unroll
+    for (int k = 0; k < L0_UNROLL; k++) {
+        const u32 g = g0 + k * 256;
+        if (g < total) {
+            v[k] = __ldg(reinterpret_cast<const uint4*>(images + fo) + g);
+            if (masks) m[k] = __ldg(reinterpret_cast<const uint4*>(masks + fo) + g);
+        }
     }
-    *reinterpret_cast<uint4*>(pyr + (size_t)f * P.frameBytes + L.off + (size_t)(y + ORBX_OY) * L.pitch + x + ORBX_OX) = v;
+#pragma unroll
+    for (int k = 0; k < L0_UNROLL; k++) {
+        const u32 g = g0 + k * 256;
+        if (g >= total) continue;
+        if (masks) {
+            // per byte: keep the pixel where the mask byte is non-zero (0x80 trick: (m | (m & 0x7f..) + 0x7f..) & 0x80.. marks non-zero bytes)
+            auto keep = [](u32 px, u32 mk) {
+                const u32 nz = ((mk & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | mk;       // bit 7 of each byte set iff that mask byte != 0
+                const u32 full = ((nz & 0x80808080u) >> 7) * 0xFFu;            // 0xFF in the bytes to keep
+                return px & full;
+            };
+            v[k].x = keep(v[k].x, m[k].x); v[k].y = keep(v[k].y, m[k].y); v[k].z = keep(v[k].z, m[k].z); v[k].w = keep(v[k].w, m[k].w);
+        }
+        const u32 y = __umulhi(g, gprInv), xg = g - y * gpr;          // exact: g * gpr < 2^32 (checked by the caller)
+        *reinterpret_cast<uint4*>(dst0 + (size_t)y * L.pitch + 16 * xg) = v[k];
+    }
 }
 
 // Generic gather form (any scale factor): one thread = 4 adjacent ROI pixels, 4 byte gathers each.
@@ -1924,10 +1942,12 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     if (stages & ORBX_STAGE_PYRAMID) {
         {
             const LevelPlan& L = P.lv[0];
-            const bool v16 = (L.w % 16 == 0) && ((uintptr_t)d_images % 16 == 0) && (!d_masks || (uintptr_t)d_masks % 16 == 0);
+            const bool v16 = (L.w % 16 == 0) && ((uintptr_t)d_images % 16 == 0) && (!d_masks || (uintptr_t)d_masks % 16 == 0) &&
+                             (unsigned long long)(L.w >> 4) * (L.w >> 4) * L.h < (1ull << 32);
             if (v16) {
-                dim3 g(orb_div_up(L.w, 1024), orb_div_up(L.h, 4), nf), b(64, 4);
-                k_level0_v16<<<g, b, 0, st>>>(P, d_images, d_masks, ex->d_pyr);
+                const u32 gpr = (u32)L.w >> 4;
+                dim3 g(orb_div_up((int)gpr * L.h, 256 * L0_UNROLL), nf);
+                k_level0_v16<<<g, 256, 0, st>>>(P, d_images, d_masks, ex->d_pyr, 0xFFFFFFFFu / gpr + 1);
             } else {
                 dim3 g(orb_div_up(L.w, 256), orb_div_up(L.h, 4), nf), b(64, 4);
                 k_level0<<<g, b, 0, st>>>(P, d_images, d_masks, ex->d_pyr);
