@@ -64,6 +64,7 @@ struct Plan {
     int totalCells, candTotal, selTotal, maxNodes, sortN;
     int tilePitch, tileRows, scorePitch, scoreRows;   // FAST shared-memory tile geometry (max over levels)
     int fwBoxW, fwBoxH, fwTileBytes, fwScoreOff, fwPlistOff, fwGlistOff, fwBarOff, fwStride;   // k_fast_tma per-warp shared-memory layout
+    int fwScorePitch;                     // score-map pitch of k_fast_tma: 40 or 48 (compile-time variants) or the generic pitch
     int width, height;
     unsigned long long frameBytes;
     int umax[16];
@@ -449,7 +450,8 @@ __global__ void __launch_bounds__(ORBX_FAST_THREADS) k_fast(const __grid_constan
 // mbarrier), so the load of the next cell overlaps the work on the current one and costs no per-thread instructions.
 // Nothing inside a cell needs a CTA barrier or a shared atomic: compaction is ballot + popc on a warp-uniform counter.
 // ---------------------------------------------------------------------------------------------------
-#define ORBX_FW_WARPS 8
+#define ORBX_FW_MAXWARPS 32          // warps per CTA are chosen per launch (blockDim.x / 32): the warps of a CTA never meet at a barrier,
+                                     // so ONE CTA per SM with as many warps as its shared memory holds gives the highest occupancy
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u32 bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -493,22 +495,22 @@ __device__ __forceinline__ void sts16(u32 addr, u32 v) { asm volatile("st.shared
 // sign-agnostic 4-pair test passes 13.4 % of the pixels at t = 20 (the signed 3-pair u16x2 test it replaces passed 20.1 % at twice
 // the instructions per pixel; FAST-9 corners are 5.6 %): tools/fast_filter_rates.py.
 template <int BOXW, int SPP>
-__global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_constant__ Plan P, const CUtensorMap* __restrict__ maps,
+__global__ void __launch_bounds__(32 * ORBX_FW_MAXWARPS) k_fast_tma(const __grid_constant__ Plan P, const CUtensorMap* __restrict__ maps,
                                                                   const uint4* __restrict__ cells, int nCells, int nf,
                                                                   uint2* __restrict__ cand, int* __restrict__ candCount,
                                                                   int* __restrict__ status, int* __restrict__ workCounter,
                                                                   unsigned long long cellsInv40) {
     extern __shared__ __align__(128) u8 smem_fw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int BW = BOXW > 0 ? BOXW : P.fwBoxW, SP = SPP > 0 ? SPP : P.scorePitch;
+    const int BW = BOXW > 0 ? BOXW : P.fwBoxW, SP = SPP > 0 ? SPP : P.fwScorePitch;
     u8* wbase = smem_fw + (size_t)warp * P.fwStride;
     u8* score = wbase + P.fwScoreOff;
     u16* plist = reinterpret_cast<u16*>(wbase + P.fwPlistOff);
     const u32 bar0 = smem_u32(wbase + P.fwBarOff), bar1 = bar0 + 8;
     const u32 boxBytes = (u32)(BW * P.fwBoxH);
     const int nItems = nCells * nf;
-    const int Wt = gridDim.x * ORBX_FW_WARPS;
-    int item = blockIdx.x * ORBX_FW_WARPS + warp;
+    const int wpc = blockDim.x >> 5, Wt = gridDim.x * wpc;
+    int item = blockIdx.x * wpc + warp;
     if (item >= nItems) return;
 
     if (lane == 0) {
@@ -565,7 +567,30 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
             const int t = pass ? P.minTh : P.iniTh;
             T = t;
             // ---- phase A
-            int nl = 0, ngl = 0;
+            int nl = 0, gh = 0, gn = 0;                               // pixel-list length; head / fill of the 64-entry group ring
+            // expand up to 32 group entries of the ring (from its head) into the pixel list (order is irrelevant: every entry carries
+            // its coordinates).  The ring keeps the group list at 256 bytes instead of one entry per group of the cell, which is what
+            // lets 30 instead of 27 warps share an SM's shared memory.
+            auto expand = [&](int cnt) {
+                const u32 ge = lane < cnt ? lds32i<0>(glS + 4 * (u32)((gh + lane) & 63)) : 0u;
+                const u32 fb = ge & 0x80808080u;
+                int pos = __popc(fb), tot;
+                // exclusive prefix sum of the per-lane pixel counts: SHFL.UP delivers the in-range predicate with the value
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v;
+                    asm volatile("{\n\t.reg .pred p;\n\tshfl.sync.up.b32 %0|p, %1, %2, 0, 0xffffffff;\n\t@p add.s32 %1, %1, %0;\n\t}"
+                                 : "=r"(v), "+r"(pos) : "r"(o));
+                }
+                tot = __shfl_sync(0xffffffffu, pos, 31);
+                pos = nl + pos - __popc(fb);
+                const u32 px0 = (ge & 0x3F7Fu) - 4u;                   // row << 8 | lo  (as the u16 the list holds)
+                if (fb & 0x80u) { sts16(plS + 2 * (u32)pos, px0); pos++; }
+                if (fb & 0x8000u) { sts16(plS + 2 * (u32)pos, px0 + 1); pos++; }
+                if (fb & 0x800000u) { sts16(plS + 2 * (u32)pos, px0 + 2); pos++; }
+                if ((int)fb < 0) sts16(plS + 2 * (u32)pos, px0 + 3);
+                nl += tot;
+            };
             {
                 // no `& 0x7f` before the add: a byte with d >= 129 + t carries into its left neighbour, whose test then reads
                 // d >= t instead of d > t — weaker, hence still a necessary condition (its own bit 7 comes from `| d`)
@@ -611,32 +636,17 @@ __global__ void __launch_bounds__(32 * ORBX_FW_WARPS) k_fast_tma(const __grid_co
                     // bits 7 / 15 / 23 / 31 (lo + 4 <= 67 and row <= 63 keep those bits free); expanded to pixels below
                     const u32 bg = __ballot_sync(0xffffffffu, fl != 0u);
                     if (bg == 0u) continue;                            // warp-uniform: flat neighbourhoods leave nothing to compact
-                    if (fl) sts32(glS + 4 * (u32)(ngl + __popc(bg & lt)), (u32)(ent + 4) | fl);
-                    ngl += __popc(bg);
+                    if (fl) sts32(glS + 4 * (u32)((gh + gn + __popc(bg & lt)) & 63), (u32)(ent + 4) | fl);
+                    gn += __popc(bg);
+                    if (gn >= 32) {                                    // warp-uniform
+                        __syncwarp();
+                        expand(32);
+                        gh = (gh + 32) & 63; gn -= 32;
+                        __syncwarp();
+                    }
                 }
                 __syncwarp();
-                // ---- expand the passing groups into the pixel list (order is irrelevant: every entry carries its coordinates)
-                for (int e0 = 0; e0 < ngl; e0 += 32) {
-                    const int e = e0 + lane;
-                    const u32 ge = e < ngl ? lds32i<0>(glS + 4 * (u32)e) : 0u;
-                    const u32 fb = ge & 0x80808080u;
-                    int pos = __popc(fb), tot;
-                    // exclusive prefix sum of the per-lane pixel counts: SHFL.UP delivers the in-range predicate with the value
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        int v;
-                        asm volatile("{\n\t.reg .pred p;\n\tshfl.sync.up.b32 %0|p, %1, %2, 0, 0xffffffff;\n\t@p add.s32 %1, %1, %0;\n\t}"
-                                     : "=r"(v), "+r"(pos) : "r"(o));
-                    }
-                    tot = __shfl_sync(0xffffffffu, pos, 31);
-                    pos = nl + pos - __popc(fb);
-                    const u32 px0 = (ge & 0x3F7Fu) - 4u;               // row << 8 | lo  (as the u16 the list holds)
-                    if (fb & 0x80u) { sts16(plS + 2 * (u32)pos, px0); pos++; }
-                    if (fb & 0x8000u) { sts16(plS + 2 * (u32)pos, px0 + 1); pos++; }
-                    if (fb & 0x800000u) { sts16(plS + 2 * (u32)pos, px0 + 2); pos++; }
-                    if ((int)fb < 0) sts16(plS + 2 * (u32)pos, px0 + 3);
-                    nl += tot;
-                }
+                if (gn > 0) expand(gn);
             }
             __syncwarp();
 
@@ -1555,7 +1565,7 @@ struct orbx_extractor {
     CUtensorMap* d_maps = nullptr;         // one TMA descriptor per pyramid level (k_fast_tma)
     bool useTma = false, descTma = false;
     size_t fwSmem = 0;
-    int fwGrid = 0, descGrid = 0;
+    int fwGrid = 0, descGrid = 0, fwWarps = 0, smCount = 148;
     uint4* d_cells = nullptr;              // valid FAST cells: {iniX | iniY<<16, tw | th<<8 | level<<16, cell id, 0}
     int nCells = 0;
     int capInternal = 0;
@@ -1737,15 +1747,27 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         P.fwBoxW = boxW; P.fwBoxH = boxH;
         P.fwTileBytes = (int)orb_align_up((size_t)boxW * boxH, 128);
         P.fwScoreOff = P.fwTileBytes;                                 // one tile buffer: more warps per SM beat double buffering here
-        P.fwPlistOff = P.fwScoreOff + (int)orb_align_up((size_t)P.scorePitch * P.scoreRows, 16);
-        P.fwGlistOff = P.fwPlistOff + (int)orb_align_up((size_t)(maxCW + 2) * maxCH * 2, 16);      // <= (3 + maxCW + 3) / 4 groups per row
-        P.fwBarOff = P.fwGlistOff + (int)orb_align_up((size_t)((maxCW + 9) / 4) * maxCH * 4, 16);
+        // score map: pixel (px, py) of the domain (px < cell width, py < cell height) at byte (py + 1) * pitch + px + 2, one zero column
+        // on either side for the 3x3 NMS: pitch >= cell width + 3.  Pitches 40 and 48 exist as compile-time variants.
+        P.fwScorePitch = (boxW == 64 && ex->fastConst) ? (maxCW + 3 <= 40 ? 40 : 48) : P.scorePitch;
+        P.fwPlistOff = P.fwScoreOff + (int)orb_align_up((size_t)P.fwScorePitch * P.scoreRows, 16);
+        P.fwGlistOff = P.fwPlistOff + (int)orb_align_up((size_t)maxCW * maxCH * 2, 16);            // one u16 per domain pixel: every pixel may pass
+        // group ring (64 x u32) during phase A; afterwards the same bytes hold the 3x3-NMS survivors (u16; at most one per 2x2 block)
+        P.fwBarOff = P.fwGlistOff + (int)orb_align_up(std::max<size_t>(256, (size_t)((maxCW + 1) / 2 + 1) * ((maxCH + 1) / 2 + 1) * 2), 16);
         P.fwStride = (int)orb_align_up((size_t)P.fwBarOff + 16, 128);
-        ex->fwSmem = (size_t)P.fwStride * ORBX_FW_WARPS;
+        {   // warps per SM = what its shared memory holds (one CTA per SM in batch passes), at most 32
+            cudaDeviceProp prop;
+            ORB_CUDA_TRY(cudaGetDeviceProperties(&prop, ex->device));
+            static const int envW = [] { const char* e = getenv("ORBX_FW_WARPS"); return e ? atoi(e) : 0; }();
+            ex->fwWarps = std::min(ORBX_FW_MAXWARPS, (int)(prop.sharedMemPerBlockOptin / (size_t)P.fwStride));
+            if (envW > 0) ex->fwWarps = std::min(ex->fwWarps, envW);
+            ex->smCount = prop.multiProcessorCount;
+        }
+        ex->fwSmem = (size_t)P.fwStride * std::max(ex->fwWarps, 1);
         ex->useTma = false;
         const char* env = getenv("ORBX_FAST_TMA");
         const bool want = !(env && atoi(env) == 0);
-        if (want && boxW <= 256 && boxH <= 256 && maxCW <= 62 && maxCH <= 62 && ex->fwSmem <= 200 * 1024) {
+        if (want && boxW <= 256 && boxH <= 256 && maxCW <= 62 && maxCH <= 62 && ex->fwWarps >= 1) {
             typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1784,13 +1806,13 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         if (ex->useTma) {
             cudaDeviceProp prop;
             ORB_CUDA_TRY(cudaGetDeviceProperties(&prop, ex->device));
-            const int perSM = std::max(1, std::min(8, (int)((prop.sharedMemPerMultiprocessor - 4096) / (ex->fwSmem + 1024))));
-            ex->fwGrid = prop.multiProcessorCount * perSM;
+            ex->fwGrid = prop.multiProcessorCount;
             static std::mutex amu2;
             static size_t maxFwDev[64] = {0};                         // the opt-in is per function AND per device
             size_t& maxFw = maxFwDev[ex->device & 63];
             std::lock_guard<std::mutex> lk(amu2);
             if (ex->fwSmem > maxFw) {
+                ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
                 ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<64, ORBX_FAST_SPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
                 ORB_CUDA_TRY(cudaFuncSetAttribute(k_fast_tma<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fwSmem));
                 maxFw = ex->fwSmem;
@@ -1976,14 +1998,20 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         dim3 g(ex->nCells, nf);
         if (ex->nCells > 0 && ex->useTma) {
             const int items = ex->nCells * nf;
-            const int grid = std::min(ex->fwGrid, orb_div_up(items, ORBX_FW_WARPS));
+            // batch passes: one CTA of fwWarps warps per SM; small passes (single frames): fewer warps per CTA so that every SM gets work
+            const int wpc = std::min(ex->fwWarps, std::max(4, orb_div_up(items, ex->smCount)));
+            const int grid = std::min(ex->smCount * std::max(1, ex->fwWarps / wpc), orb_div_up(items, wpc));
+            const size_t smem = (size_t)P.fwStride * wpc;
             const unsigned long long inv40 = ((1ull << 40) + (unsigned long long)ex->nCells - 1) / (unsigned long long)ex->nCells;
-            if (P.fwBoxW == 64 && ex->fastConst)
-                k_fast_tma<64, ORBX_FAST_SPP><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
-                                                                                          ex->d_candCount, ex->d_status, ex->d_workCounter, inv40);
+            if (P.fwBoxW == 64 && ex->fastConst && P.fwScorePitch == 40)
+                k_fast_tma<64, 40><<<grid, 32 * wpc, smem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
+                                                                 ex->d_candCount, ex->d_status, ex->d_workCounter, inv40);
+            else if (P.fwBoxW == 64 && ex->fastConst)
+                k_fast_tma<64, ORBX_FAST_SPP><<<grid, 32 * wpc, smem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
+                                                                            ex->d_candCount, ex->d_status, ex->d_workCounter, inv40);
             else
-                k_fast_tma<0, 0><<<grid, 32 * ORBX_FW_WARPS, ex->fwSmem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
-                                                                             ex->d_candCount, ex->d_status, ex->d_workCounter, inv40);
+                k_fast_tma<0, 0><<<grid, 32 * wpc, smem, st>>>(P, ex->d_maps, ex->d_cells, ex->nCells, nf, ex->d_cand,
+                                                               ex->d_candCount, ex->d_status, ex->d_workCounter, inv40);
         } else if (ex->nCells > 0) {
             if (ex->fastConst)
                 k_fast<ORBX_FAST_TPP, ORBX_FAST_SPP><<<g, ORBX_FAST_THREADS, ex->fastSmem, st>>>(P, ex->d_cells, ex->d_pyr, ex->d_cand, ex->d_candCount, ex->d_status);
