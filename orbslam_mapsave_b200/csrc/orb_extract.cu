@@ -1235,13 +1235,13 @@ __device__ __forceinline__ void dev_sincos_0_2pi(double x, double& s, double& c)
     c = ((q + 1) & 2) ? -cc : cc;
 }
 
-#define DESC_WARPS 8
+#define DESC_MAXWARPS 32      // warps per CTA are chosen per launch (blockDim.x / 32): one CTA per SM with as many warps as fit, like k_fast_tma
 #define DESC_PW 11            // aligned words per staged blurred-patch row: covers kx-18 .. kx+18 for any alignment
 #define DESC_AW 9             // aligned words per staged disc row: covers kx-15 .. kx+15 for any alignment
 #define DESC_PATCH_WORDS (37 * DESC_PW)
 #define DESC_DISC_WORDS (31 * DESC_AW)
 #define DESC_BUF_WORDS (DESC_PATCH_WORDS + DESC_DISC_WORDS)
-#define DESC_SMEM_BYTES (32 * 36 * 4 + 2 * DESC_WARPS * DESC_BUF_WORDS * 4)
+#define DESC_SMEM_BYTES(W) (32 * 36 * 4 + 2 * (W) * DESC_BUF_WORDS * 4)
 // TMA staging (k_describe<true>): the two neighbourhoods of a keypoint are two boxes of the per-level tensor maps, dropped into
 // shared memory by one elected lane (no per-lane address arithmetic).  A box has to start at a 16-byte aligned pixel column (an
 // unaligned start raises "illegal instruction" on sm_100a), so boxes are 64 / 48 bytes wide and start at the aligned column at or
@@ -1252,7 +1252,7 @@ __device__ __forceinline__ void dev_sincos_0_2pi(double x, double& s, double& c)
 #define DESC_TMA_DISC_BYTES 1536          // 31 x 48 = 1488
 #define DESC_TMA_BUF_BYTES (DESC_TMA_PATCH_BYTES + DESC_TMA_DISC_BYTES)
 #define DESC_TMA_TX_BYTES (37 * DESC_TMA_PW + 31 * DESC_TMA_AW)
-#define DESC_TMA_SMEM_BYTES (32 * 36 * 4 + 2 * DESC_WARPS * DESC_TMA_BUF_BYTES + 2 * DESC_WARPS * 8)
+#define DESC_TMA_SMEM_BYTES(W) (32 * 36 * 4 + 2 * (W) * DESC_TMA_BUF_BYTES + 2 * (W) * 8)
 // Persistent warps over the work items (frame, slot): slot r of a frame is position r of the per-frame selection buffer
 // (level l owns [selOff[l], selOff[l] + selCap[l])), so the selection entry and the per-level counts of an item are two
 // INDEPENDENT loads whose addresses follow from the item number alone.  Software pipeline per warp:
@@ -1263,7 +1263,7 @@ __device__ __forceinline__ void cp_async4(u32 dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 template <bool TMA>
-__global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
+__global__ void __launch_bounds__(32 * DESC_MAXWARPS) k_describe(const __grid_constant__ Plan P, const u8* __restrict__ pyr,
                                                               const u8* __restrict__ blur, const uint2* __restrict__ sel,
                                                               const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
                                                               u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
@@ -1274,7 +1274,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
     constexpr int BUF_WORDS = TMA ? DESC_TMA_BUF_BYTES / 4 : DESC_BUF_WORDS;
     constexpr int PATCH_WORDS = TMA ? DESC_TMA_PATCH_BYTES / 4 : DESC_PATCH_WORDS;
     constexpr int PWB = TMA ? DESC_TMA_PW : DESC_PW * 4, AWB = TMA ? DESC_TMA_AW : DESC_AW * 4;   // row pitches in bytes
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, DESC_WARPS = blockDim.x >> 5;
     // TMA: one mbarrier per (warp, buffer), completed by the two box loads of an item
     const u32 bars = smem_u32(smem_desc + 32 * 36 * 4 + 2 * DESC_WARPS * DESC_TMA_BUF_BYTES) + (u32)warp * 16;
     u32 phases = 0;                                               // bit b: parity of buffer b's barrier
@@ -1286,7 +1286,7 @@ __global__ void __launch_bounds__(32 * DESC_WARPS) k_describe(const __grid_const
         }
         __syncwarp();
     }
-    for (int i = threadIdx.x; i < 1024; i += 32 * DESC_WARPS) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
     __syncthreads();
     const int nItems = nf * P.selTotal, GW = gridDim.x * DESC_WARPS;
     int item = blockIdx.x * DESC_WARPS + warp;
@@ -1565,7 +1565,7 @@ struct orbx_extractor {
     CUtensorMap* d_maps = nullptr;         // one TMA descriptor per pyramid level (k_fast_tma)
     bool useTma = false, descTma = false;
     size_t fwSmem = 0;
-    int fwGrid = 0, descGrid = 0, fwWarps = 0, smCount = 148;
+    int fwGrid = 0, descGrid = 0, fwWarps = 0, descWarps = 8, smCount = 148;
     uint4* d_cells = nullptr;              // valid FAST cells: {iniX | iniY<<16, tw | th<<8 | level<<16, cell id, 0}
     int nCells = 0;
     int capInternal = 0;
@@ -1824,15 +1824,18 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
         ORB_CUDA_TRY(cudaGetDeviceProperties(&prop, ex->device));
         static const bool wantDescTma = [] { const char* e = getenv("ORBX_DESC_TMA"); return !(e && atoi(e) == 0); }();
         ex->descTma = ex->useTma && wantDescTma;
-        const int descSmem = ex->descTma ? DESC_TMA_SMEM_BYTES : DESC_SMEM_BYTES;
-        const int perSM = std::max(1, std::min(8, (int)((prop.sharedMemPerMultiprocessor - 2048) / (descSmem + 1024))));
-        ex->descGrid = prop.multiProcessorCount * perSM;
+        // warps per SM = what its shared memory holds next to ONE copy of the pattern table (one CTA per SM in batch passes)
+        static const int envDW = [] { const char* e = getenv("ORBX_DESC_WARPS"); return e ? atoi(e) : 0; }();
+        const size_t perWarp = ex->descTma ? (size_t)(2 * DESC_TMA_BUF_BYTES + 16) : (size_t)(2 * DESC_BUF_WORDS * 4);
+        ex->descWarps = std::max(1, std::min(DESC_MAXWARPS, (int)((prop.sharedMemPerBlockOptin - 32 * 36 * 4) / perWarp)));
+        if (envDW > 0) ex->descWarps = std::min(ex->descWarps, envDW);
+        ex->descGrid = prop.multiProcessorCount;
         static std::mutex amu3;
         static bool descOptIn[64] = {false};
         std::lock_guard<std::mutex> lk(amu3);
         if (!descOptIn[ex->device & 63]) {
-            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_SMEM_BYTES));
-            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_TMA_SMEM_BYTES));
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+            ORB_CUDA_TRY(cudaFuncSetAttribute(k_describe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
             descOptIn[ex->device & 63] = true;
         }
     }
@@ -2037,13 +2040,15 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
     }
     if (stages & ORBX_STAGE_DESCRIBE) {
         const int items = nf * P.selTotal;
-        const int grid = std::min(ex->descGrid, orb_div_up(items, DESC_WARPS));
+        // batch passes: one CTA of descWarps warps per SM; small passes (single frames): fewer warps per CTA so that every SM gets work
+        const int wpc = std::min(ex->descWarps, std::max(4, orb_div_up(items, ex->smCount)));
+        const int grid = std::min(ex->smCount * std::max(1, ex->descWarps / wpc), orb_div_up(items, wpc));
         if (ex->descTma)
-            k_describe<true><<<grid, 32 * DESC_WARPS, DESC_TMA_SMEM_BYTES, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
-                                                                                d_n, cap, ex->d_status, nf, ex->d_maps);
+            k_describe<true><<<grid, 32 * wpc, DESC_TMA_SMEM_BYTES(wpc), st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
+                                                                              d_n, cap, ex->d_status, nf, ex->d_maps);
         else
-            k_describe<false><<<grid, 32 * DESC_WARPS, DESC_SMEM_BYTES, st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
-                                                                             d_n, cap, ex->d_status, nf, nullptr);
+            k_describe<false><<<grid, 32 * wpc, DESC_SMEM_BYTES(wpc), st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
+                                                                           d_n, cap, ex->d_status, nf, nullptr);
         ex->launches++;
     }
     ORB_CUDA_TRY(cudaGetLastError());
