@@ -1267,7 +1267,8 @@ __global__ void __launch_bounds__(32 * DESC_MAXWARPS) k_describe(const __grid_co
                                                               const u8* __restrict__ blur, const uint2* __restrict__ sel,
                                                               const int* __restrict__ selCount, orbx_keypoint* __restrict__ kpOut,
                                                               u8* __restrict__ descOut, int* __restrict__ nOut, int cap,
-                                                              int* __restrict__ status, int nf, const CUtensorMap* __restrict__ maps) {
+                                                              int* __restrict__ status, int nf, const CUtensorMap* __restrict__ maps,
+                                                              int* __restrict__ workCounter, int DESC_CHUNK) {
     extern __shared__ __align__(128) u8 smem_desc[];
     float* s_pat = reinterpret_cast<float*>(smem_desc);            // pattern as float (no I2F in the tap loop); row stride 36: conflict-free LDS.128
     u32* s_buf = reinterpret_cast<u32*>(smem_desc + 32 * 36 * 4);  // [2][DESC_WARPS][buffer]: blurred 37x37 + unblurred 31x31 neighbourhoods
@@ -1289,20 +1290,36 @@ __global__ void __launch_bounds__(32 * DESC_MAXWARPS) k_describe(const __grid_co
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_pat[(i >> 5) * 36 + (i & 31)] = (float)c_pattern[i];
     __syncthreads();
     const int nItems = nf * P.selTotal, GW = gridDim.x * DESC_WARPS;
-    int item = blockIdx.x * DESC_WARPS + warp;
 
-    // the item stream of this warp: it, it + GW, ...; (frame, slot) advance incrementally (no division per item)
-    const int stepF = GW / P.selTotal, stepR = GW - stepF * P.selTotal;
-    int ldIt = item, ldF = item / P.selTotal, ldR = item - ldF * P.selTotal;
+    // the item stream of this warp: chunks of DESC_CHUNK (4) consecutive items — consecutive selection slots of one frame.  The first
+    // chunk is the warp's own number, further chunks come from a global counter, so the warps in flight always work on one contiguous
+    // window of items (neighbouring keypoints of a few frames: their neighbourhoods share L2 lines) however many warps an SM holds and
+    // however the schedulers' loads differ.  Measured per 4096 frames: fixed stride 3.12 ms at 28 warps per SM but 3.6-3.7 ms at 25-27
+    // (uneven warps per scheduler) ; claims of 1 item 4.35 ms (one atomic per item), 2: 3.39, 4: 3.12, 8: 3.11, 16: 3.14, 32: 3.36
+    // (a warp walking 32 slots alone loses the sharing between concurrent warps).  (frame, slot) advance incrementally inside a chunk.
+    int ldIt = 0, ldEnd = 0, ldF = 0, ldR = 0;
+    bool ldDone = false;
+    auto claim = [&](int chunk) {
+        const long long base = (long long)chunk * DESC_CHUNK;
+        if (base >= nItems) { ldDone = true; return; }
+        ldIt = (int)base; ldEnd = min(ldIt + DESC_CHUNK, nItems);
+        ldF = ldIt / P.selTotal; ldR = ldIt - ldF * P.selTotal;
+    };
+    claim(blockIdx.x * DESC_WARPS + warp);
     auto load_next = [&]() {                                       // stage A: two independent loads
+        if (!ldDone && ldIt >= ldEnd) {
+            int c = 0;
+            if (lane == 0) c = GW + atomicAdd(workCounter, 1);
+            claim(__shfl_sync(0xffffffffu, c, 0));
+        }
         DescItem d;
-        d.k = make_uint2(0u, 0u); d.cntv = 0; d.f = ldF; d.r = ldR; d.valid = ldIt < nItems;
+        d.k = make_uint2(0u, 0u); d.cntv = 0; d.f = ldF; d.r = ldR; d.valid = !ldDone;
         if (d.valid) {
             d.k = __ldg(sel + ldIt);
             d.cntv = lane < P.nlevels ? __ldg(selCount + ldF * P.nlevels + lane) : 0;
+            ldIt++; ldR++;
+            if (ldR >= P.selTotal) { ldR = 0; ldF++; }
         }
-        ldIt += GW; ldF += stepF; ldR += stepR;
-        if (ldR >= P.selTotal) { ldR -= P.selTotal; ldF++; }
         return d;
     };
     // resolves (level, index in level, output position) of an item; returns false for empty slots
@@ -1361,7 +1378,7 @@ __global__ void __launch_bounds__(32 * DESC_MAXWARPS) k_describe(const __grid_co
     if (ok0) stage(0, f0, l0, d0.k);
     if (!TMA) asm volatile("cp.async.commit_group;" ::: "memory");
     int buf = 0;
-    for (; item < nItems; item += GW) {
+    while (d0.valid) {                                             // (chunks are claimed in increasing order: after the first item past the end all are)
         // stage A for item+2 (consumed two iterations from now), stage B for item+1
         const DescItem d2 = load_next();
         int f1 = 0, l1 = 0, pos1 = 0, tot1 = 0;
@@ -1730,7 +1747,7 @@ static int make_plan(orbx_extractor* ex, int width, int height) {
     ORB_CUDA_TRY(cudaMalloc(&ex->d_nodeOf, (size_t)B * P.candTotal * sizeof(u32)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_sel, (size_t)B * P.selTotal * sizeof(uint2)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_candCount, (size_t)B * nl * sizeof(int)));
-    ORB_CUDA_TRY(cudaMalloc(&ex->d_workCounter, sizeof(int)));
+    ORB_CUDA_TRY(cudaMalloc(&ex->d_workCounter, 2 * sizeof(int)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_selCount, (size_t)B * nl * sizeof(int)));
     ORB_CUDA_TRY(cudaMalloc(&ex->d_status, sizeof(int)));
     ORB_CUDA_TRY(cudaMemset(ex->d_status, 0, sizeof(int)));
@@ -2043,12 +2060,14 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         // batch passes: one CTA of descWarps warps per SM; small passes (single frames): fewer warps per CTA so that every SM gets work
         const int wpc = std::min(ex->descWarps, std::max(4, orb_div_up(items, ex->smCount)));
         const int grid = std::min(ex->smCount * std::max(1, ex->descWarps / wpc), orb_div_up(items, wpc));
+        ORB_CUDA_TRY(cudaMemsetAsync(ex->d_workCounter + 1, 0, sizeof(int), st));
+        static const int descChunk = [] { const char* e = getenv("ORBX_DESC_CHUNK"); return std::max(1, e ? atoi(e) : 4); }();
         if (ex->descTma)
             k_describe<true><<<grid, 32 * wpc, DESC_TMA_SMEM_BYTES(wpc), st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
-                                                                              d_n, cap, ex->d_status, nf, ex->d_maps);
+                                                                              d_n, cap, ex->d_status, nf, ex->d_maps, ex->d_workCounter + 1, descChunk);
         else
             k_describe<false><<<grid, 32 * wpc, DESC_SMEM_BYTES(wpc), st>>>(P, ex->d_pyr, ex->d_blur, ex->d_sel, ex->d_selCount, d_kp, d_desc,
-                                                                           d_n, cap, ex->d_status, nf, nullptr);
+                                                                           d_n, cap, ex->d_status, nf, nullptr, ex->d_workCounter + 1, descChunk);
         ex->launches++;
     }
     ORB_CUDA_TRY(cudaGetLastError());
