@@ -1558,6 +1558,8 @@ struct orbx_extractor {
     std::vector<int> quota;
     Plan plan;
     cudaStream_t stream = nullptr;
+    cudaStream_t sBlur = nullptr;          // the blur of a pass runs here, next to FAST / octree, when those leave most SMs idle
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     // device workspace
     u8 *d_pyr = nullptr, *d_blur = nullptr;
     // host-buffer path: two staging slots so that H2D(chunk i+1), compute(chunk i) and D2H(chunk i-1) overlap
@@ -1948,6 +1950,9 @@ extern "C" void orbx_destroy(orbx_extractor* ex) {
     cudaFree(ex->d_cand); cudaFree(ex->d_sel); cudaFree(ex->d_nodeOf); cudaFree(ex->d_candCount); cudaFree(ex->d_workCounter); cudaFree(ex->d_selCount);
     cudaFree(ex->d_status); cudaFree(ex->d_xtab); cudaFree(ex->d_ytab); cudaFree(ex->d_cells); cudaFree(ex->d_maps);
     if (ex->stream) cudaStreamDestroy(ex->stream);
+    if (ex->sBlur) cudaStreamDestroy(ex->sBlur);
+    if (ex->evFork) cudaEventDestroy(ex->evFork);
+    if (ex->evJoin) cudaEventDestroy(ex->evJoin);
     delete ex;
 }
 
@@ -2012,6 +2017,34 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         // frame; a separate pass over the border words costs 0.18 us per frame because every word it touches is a DRAM sector of its
         // own.  The 19-pixel border of the API-visible pyramid is produced on demand by orbx_get_pyramid(bordered).)
     }
+    // The blur depends on the pyramid only.  In a complete pass it is forked onto a second stream next to the kernels that cannot fill
+    // the machine: FAST when the pass has fewer cells than one CTA per SM takes (single frames), else the octree when it has fewer than
+    // two CTAs per SM (one CTA per (level, frame): 4K passes, single frames) — k_octree at 4K runs at 30 % SM throughput for 11 % of the
+    // pass.  In VGA batch passes every kernel fills the machine and the streams would only take turns: no fork.
+    int forkAt = 0;                                                    // 0: none, 1: before FAST, 2: before the octree
+    static const bool wantFork = [] { const char* e = getenv("ORBX_BLUR_FORK"); return !(e && e[0] == '0'); }();
+    if (wantFork && stages == ORBX_STAGE_ALL) {
+        if (ex->useTma && ex->nCells * nf < ex->smCount * 4) forkAt = 1;
+        else if (nl * nf < 2 * ex->smCount) forkAt = 2;
+        if (forkAt && !ex->sBlur) {
+            ORB_CUDA_TRY(cudaStreamCreateWithFlags(&ex->sBlur, cudaStreamNonBlocking));
+            ORB_CUDA_TRY(cudaEventCreateWithFlags(&ex->evFork, cudaEventDisableTiming));
+            ORB_CUDA_TRY(cudaEventCreateWithFlags(&ex->evJoin, cudaEventDisableTiming));
+        }
+    }
+    auto launch_blur = [&](cudaStream_t sb) {
+        dim3 g(P.blurTileBase[nl], nf);
+        k_blur<<<g, 256, 0, sb>>>(P, ex->d_pyr, ex->d_blur);
+        ex->launches++;
+    };
+    auto fork_blur = [&]() -> int {
+        ORB_CUDA_TRY(cudaEventRecord(ex->evFork, st));
+        ORB_CUDA_TRY(cudaStreamWaitEvent(ex->sBlur, ex->evFork, 0));
+        launch_blur(ex->sBlur);
+        ORB_CUDA_TRY(cudaEventRecord(ex->evJoin, ex->sBlur));
+        return ORB_OK;
+    };
+    if (forkAt == 1) { int rcf = fork_blur(); if (rcf != ORB_OK) return rcf; }
     if (stages & ORBX_STAGE_FAST) {
         ORB_CUDA_TRY(cudaMemsetAsync(ex->d_candCount, 0, (size_t)nf * nl * sizeof(int), st));
         ORB_CUDA_TRY(cudaMemsetAsync(ex->d_workCounter, 0, sizeof(int), st));
@@ -2040,6 +2073,7 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
         }
         ex->launches++;
     }
+    if (forkAt == 2) { int rcf = fork_blur(); if (rcf != ORB_OK) return rcf; }
     if (stages & ORBX_STAGE_OCTREE) {
         dim3 g(nl, nf);
         // a (level, frame) CTA at VGA size holds ~1400 candidates at most: in a batch pass (plenty of CTAs) 128 threads keep the many
@@ -2050,11 +2084,8 @@ static int run_pass(orbx_extractor* ex, const u8* d_images, const u8* d_masks, i
                                                            ex->d_selCount, ex->d_status);
         ex->launches++;
     }
-    if (stages & ORBX_STAGE_BLUR) {
-        dim3 g(P.blurTileBase[nl], nf);
-        k_blur<<<g, 256, 0, st>>>(P, ex->d_pyr, ex->d_blur);
-        ex->launches++;
-    }
+    if (forkAt) ORB_CUDA_TRY(cudaStreamWaitEvent(st, ex->evJoin, 0));
+    else if (stages & ORBX_STAGE_BLUR) launch_blur(st);
     if (stages & ORBX_STAGE_DESCRIBE) {
         const int items = nf * P.selTotal;
         // batch passes: one CTA of descWarps warps per SM; small passes (single frames): fewer warps per CTA so that every SM gets work
