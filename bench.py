@@ -540,20 +540,28 @@ def main():
     cpu_barrier()
     # the same probe the way the e2e step itself is laid out: ONE PROCESS PER GPU, every rank streaming its own device at the same time
     # (each process's pinned buffers are first-touched by that process, like the e2e buffers; the single-process form above allocates all
-    # of them from rank 0).  The slowest rank sets the time, as in the e2e measurement.
+    # of them from rank 0).  The ranks agree on a wall-clock start (rank 0's clock + 6 s, broadcast), allocate and warm up on their own
+    # and begin their timed copies together; a rank that misses the start invalidates the figure.  The slowest rank sets the time.
     if world > 1:
-        each1, tot1, node1 = np.zeros(1, np.float64), C.c_double(), np.zeros(1, np.int32)
+        t_start = torch.tensor([time.time_ns() + 6_000_000_000], dtype=torch.int64)
+        dist.broadcast(t_start, src=0, group=cpu_group)
+        each1, tot1, node1, late1 = np.zeros(1, np.float64), C.c_double(), np.zeros(1, np.int32), C.c_double()
         dev1 = np.array([local_rank], np.int32)
-        rc = capi.lib().orb_h2d_probe(1, capi._p(dev1), nF * W * H, args.e2e_chunk * W * H, 3, 2, capi._p(each1), C.byref(tot1), capi._p(node1))
+        rc = capi.lib().orb_h2d_probe_at(1, capi._p(dev1), nF * W * H, args.e2e_chunk * W * H, 6, 2, int(t_start.item()), capi._p(each1),
+                                         C.byref(tot1), capi._p(node1), C.byref(late1))
         mine = torch.tensor([float(each1[0]) if rc == 0 else 0.0], dtype=torch.float64)
         lo = mine.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=cpu_group)
         sm_ = mine.clone()
         dist.all_reduce(sm_, op=dist.ReduceOp.SUM, group=cpu_group)
+        late = torch.tensor([late1.value], dtype=torch.float64)
+        dist.all_reduce(late, op=dist.ReduceOp.MAX, group=cpu_group)
         if rank == 0 and float(lo) > 0:
             ms = 1e3 * nF * W * H / (float(lo) * 1e9)
-            e2e["copy_floor_probe"]["one_process_per_gpu"] = {"h2d_gbs_total": float(sm_), "h2d_gbs_per_gpu_min": float(lo), "ms_per_step": ms}
-            if ms < e2e.get("copy_only_ms_per_step", 1e30):
+            ok_sync = float(late) == 0.0
+            e2e["copy_floor_probe"]["one_process_per_gpu"] = {"h2d_gbs_total": float(sm_), "h2d_gbs_per_gpu_min": float(lo), "ms_per_step": ms,
+                                                              "common_start": ok_sync, "max_late_ms": float(late)}
+            if ok_sync and ms < e2e.get("copy_only_ms_per_step", 1e30):
                 e2e["copy_only_ms_per_step"] = ms
                 e2e["copy_only_h2d_gbs_per_gpu"] = float(lo)
                 e2e["e2e_over_copy_floor"] = e2e["ms_per_step"] / ms

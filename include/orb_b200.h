@@ -400,6 +400,11 @@ int orbm_popc_peak(int device, double* popc_per_second, double* sm_clock_hz_used
  * sysfs numa_node of every GPU (-1: the kernel reports none; -3: sysfs entry not visible). */
 int orb_h2d_probe(int n_dev, const int* devices, size_t bytes_per_step, size_t chunk_bytes, int steps, int flags, double* gbs_each,
                   double* gbs_total, int* numa_nodes);
+/* The same probe with a common start time for several processes (one per GPU, the layout of bench.py's e2e measurement): every process
+ * allocates and warms up on its own and then waits for start_unix_ns (CLOCK_REALTIME, nanoseconds) before its timed copies, so that the
+ * timed windows of all processes coincide.  *late_ms: by how much this process missed the start (0 = on time). */
+int orb_h2d_probe_at(int n_dev, const int* devices, size_t bytes_per_step, size_t chunk_bytes, int steps, int flags,
+                     long long start_unix_ns, double* gbs_each, double* gbs_total, int* numa_nodes, double* late_ms);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Map archive: the fork's System::SaveMap / LoadMap file (src/System.cc:552-574) as a source of real keyframe

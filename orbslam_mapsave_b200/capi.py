@@ -29,7 +29,7 @@ SYMBOLS = [
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device", "orbm_allpairs_multi",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
     "orbm_search_by_bow_batch", "orbm_search_for_triangulation_batch",
-    "orbm_popc_peak", "orbm_distinctive_descriptors", "orb_h2d_probe",
+    "orbm_popc_peak", "orbm_distinctive_descriptors", "orb_h2d_probe", "orb_h2d_probe_at",
     "orbm_search_by_projection_map", "orbm_search_by_projection_frame", "orbm_search_by_projection_frame_batch",
     "orbm_search_for_initialization", "orbm_search_windows", "orbm_search_windows_best",
     "orbv_create", "orbv_load_text", "orbv_load_binary", "orbv_save_binary", "orbv_destroy", "orbv_info", "orbv_transform",
@@ -170,6 +170,8 @@ def lib():
     L.orbm_popc_peak.argtypes = [i32, vp, vp]
     L.orb_h2d_probe.restype = i32
     L.orb_h2d_probe.argtypes = [i32, vp, sz, sz, i32, i32, vp, vp, vp]
+    L.orb_h2d_probe_at.restype = i32
+    L.orb_h2d_probe_at.argtypes = [i32, vp, sz, sz, i32, i32, C.c_longlong, vp, vp, vp, vp]
     L.orbm_distinctive_descriptors.restype = i32
     L.orbm_distinctive_descriptors.argtypes = [vp, vp, i32, vp, i32]
     L.orbm_search_by_projection_map.restype = i32

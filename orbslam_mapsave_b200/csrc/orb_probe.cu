@@ -52,8 +52,22 @@ static bool bind_thread_to_node(int node) {
 // bit 2 = bind every copy thread (and therefore its first-touched pinned buffer) to the NUMA node of its GPU.
 // gbs_each[n_dev]: per-GPU H2D GB/s; *gbs_total: aggregate; numa_nodes[n_dev]: sysfs numa_node of each GPU (-1 = the kernel reports
 // none, -3 = sysfs entry not visible).
+// orb_h2d_probe_at: the same with a common start time for SEVERAL PROCESSES (one per GPU, the layout of the e2e measurement): every
+// process allocates and warms up on its own, then all of them wait for `start_unix_ns` (CLOCK_REALTIME) before the timed copies, so
+// that the timed windows coincide.  *late_ms receives by how much this process missed the start (0 = on time; a late process measured
+// against less contention and its figure must be discarded).  start_unix_ns = 0: start as soon as this process's threads are ready.
+static int h2d_probe_impl(int n_dev, const int* devices, size_t bytes_per_step, size_t chunk_bytes, int steps, int flags,
+                          long long start_unix_ns, double* gbs_each, double* gbs_total, int* numa_nodes, double* late_ms);
 extern "C" int orb_h2d_probe(int n_dev, const int* devices, size_t bytes_per_step, size_t chunk_bytes, int steps, int flags,
                              double* gbs_each, double* gbs_total, int* numa_nodes) {
+    return h2d_probe_impl(n_dev, devices, bytes_per_step, chunk_bytes, steps, flags, 0, gbs_each, gbs_total, numa_nodes, nullptr);
+}
+extern "C" int orb_h2d_probe_at(int n_dev, const int* devices, size_t bytes_per_step, size_t chunk_bytes, int steps, int flags,
+                                long long start_unix_ns, double* gbs_each, double* gbs_total, int* numa_nodes, double* late_ms) {
+    return h2d_probe_impl(n_dev, devices, bytes_per_step, chunk_bytes, steps, flags, start_unix_ns, gbs_each, gbs_total, numa_nodes, late_ms);
+}
+static int h2d_probe_impl(int n_dev, const int* devices, size_t bytes_per_step, size_t chunk_bytes, int steps, int flags,
+                          long long start_unix_ns, double* gbs_each, double* gbs_total, int* numa_nodes, double* late_ms) {
     ORB_REQUIRE(n_dev > 0 && devices && bytes_per_step > 0 && chunk_bytes > 0 && steps > 0 && gbs_each && gbs_total, ORB_ERR_ARG, "bad arguments");
     ORB_REQUIRE(orb_device_count() >= n_dev, ORB_ERR_CUDA, "need %d CUDA devices (no CPU fallback)", n_dev);
     std::atomic<int> ready(0), failed(0);
@@ -104,6 +118,13 @@ extern "C" int orb_h2d_probe(int n_dev, const int* devices, size_t bytes_per_ste
             if (hout) cudaFreeHost(hout);
         });
     while (ready.load() < n_dev) std::this_thread::yield();
+    if (late_ms) *late_ms = 0.0;
+    if (start_unix_ns > 0) {
+        auto now_ns = [] { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::system_clock::now().time_since_epoch()).count(); };
+        const long long t = now_ns();
+        if (t > start_unix_ns) { if (late_ms) *late_ms = (double)(t - start_unix_ns) * 1e-6; }
+        else while (now_ns() < start_unix_ns) std::this_thread::yield();
+    }
     go.store(true);
     for (auto& t : th) t.join();
     ORB_REQUIRE(failed.load() == 0, ORB_ERR_CUDA, "a CUDA call failed in the copy probe");
