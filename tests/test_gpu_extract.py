@@ -203,6 +203,38 @@ def test_pageable_strided_and_pinned_pipelines_agree():
         assert n[f] == len(k1) and np.array_equal(kp[f, :n[f]].tobytes(), k1.tobytes()) and np.array_equal(desc[f, :n[f]], d1), f
 
 
+def test_non_tma_fallback_kernels_match_oracle():
+    """ORBX_FAST_TMA=0 / ORBX_DESC_TMA=0 select k_fast (one CTA per cell) and k_describe<false> (cp.async staging) — the kernels that
+    run when tensor maps cannot be encoded or cells exceed the TMA box.  Separate process: the switches are read when the library plans."""
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, orbslam_mapsave_b200 as orb\n"
+        "from orbslam_mapsave_b200.synth import synth\n"
+        "from oracle import orb_oracle_py as orc\n"
+        "for (W, H, seed, nf, nl) in ((640, 480, 3, 1000, 8), (400, 300, 5, 500, 5)):\n"
+        "    img = synth(W, H, seed)\n"
+        "    kp, desc = orb.ORBextractor(nf, 1.2, nl, 20, 7)(img)\n"
+        "    okp, odesc = orc.Extractor(nf, 1.2, nl, 20, 7).extract(img)\n"
+        "    assert len(kp) == len(okp) and len(kp) > 300\n"
+        "    for f in ('x', 'y', 'octave', 'response', 'size'):\n"
+        "        assert np.array_equal(kp[f], okp[f]), f\n"
+        "    assert np.abs(kp['angle'] - okp['angle']).max() <= 1e-3\n"
+        "    assert np.unpackbits(desc ^ odesc).sum() <= 1e-4 * desc.size * 8\n"
+        "frames = np.stack([synth(640, 480, s) for s in range(8)])\n"
+        "ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=4)\n"
+        "k, d, n = ex.extract_batch(frames)\n"
+        "one = orb.ORBextractor(1000, 1.2, 8, 20, 7)\n"
+        "for f in range(8):\n"
+        "    k1, d1 = one(frames[f])\n"
+        "    assert n[f] == len(k1) and np.array_equal(k[f, :n[f]].tobytes(), k1.tobytes()) and np.array_equal(d[f, :n[f]], d1)\n"
+        "print('fallback ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env in ({"ORBX_FAST_TMA": "0"}, {"ORBX_DESC_TMA": "0"}, {"ORBX_BLUR_FORK": "0", "ORBX_FW_WARPS": "5", "ORBX_DESC_WARPS": "7", "ORBX_DESC_CHUNK": "3"}):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "fallback ok" in r.stdout, (env, r.stdout[-400:], r.stderr[-1200:])
+
+
 def test_device_resident_multi_pass_matches_single_calls():
     """orbx_extract_batch_device over more frames than the workspace holds runs several passes; results must land in the right
     rows and equal single-frame calls, and later work on the caller's stream must see them."""
