@@ -96,6 +96,11 @@ int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int n_frames, 
                        size_t frame_stride, const uint8_t* masks, int mask_stride, size_t mask_frame_stride,
                        orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
 
+/* The same for frames held as SEPARATE allocations (std::vector<cv::Mat>): images[f] points at frame f (all width x height, rows `stride`
+ * bytes apart); no masks.  Pinned frames are copied by DMA one 2-D copy each, pageable ones go through the host staging pool. */
+int orbx_extract_batch_ptrs(orbx_extractor* ex, const uint8_t* const* images, int n_frames, int width, int height, int stride,
+                            orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out);
+
 /* Page-lock (cudaHostRegister) / unlock a caller-owned host buffer that is handed to orbx_extract_batch repeatedly: frames and results
  * then move by DMA straight from / into the caller's memory (no host copy at all; pageable buffers cost the host-pool copy above).
  * A one-off cost (the pages are pinned one by one), so register long-lived buffers, not per call. */

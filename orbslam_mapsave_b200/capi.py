@@ -24,7 +24,7 @@ TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
 SYMBOLS = [
     "orb_last_error", "orb_device_count",
     "orbx_create", "orbx_destroy", "orbx_tables", "orbx_compute_tables", "orbx_level_size", "orbx_max_keypoints", "orbx_extract",
-    "orbx_extract_batch", "orbx_extract_batch_device", "orbx_host_register", "orbx_host_unregister", "orbx_check_status", "orbx_get_pyramid_level", "orbx_get_pyramid",
+    "orbx_extract_batch", "orbx_extract_batch_ptrs", "orbx_extract_batch_device", "orbx_host_register", "orbx_host_unregister", "orbx_check_status", "orbx_get_pyramid_level", "orbx_get_pyramid",
     "orbx_get_blurred_level", "orbx_get_candidates", "orbx_launch_count", "orbx_run_stages_device", "orbx_stereo_matches",
     "orbm_descriptor_distance", "orbm_hamming_top2", "orbm_hamming_top2_batch_device", "orbm_allpairs_device", "orbm_allpairs_multi",
     "orbm_search_by_bow_kf_frame", "orbm_search_by_bow_kf_kf", "orbm_search_for_triangulation", "orbm_three_maxima",
@@ -121,6 +121,8 @@ def lib():
     L.orbx_extract.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp]
     L.orbx_extract_batch.restype = i32
     L.orbx_extract_batch.argtypes = [vp, vp, i32, i32, i32, i32, sz, vp, i32, sz, vp, vp, i32, vp]
+    L.orbx_extract_batch_ptrs.restype = i32
+    L.orbx_extract_batch_ptrs.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
     L.orbx_host_register.restype = i32
     L.orbx_host_register.argtypes = [vp, sz]
     L.orbx_host_unregister.restype = i32

@@ -2149,10 +2149,13 @@ extern "C" int orbx_check_status(orbx_extractor* ex) {
     return ORB_OK;
 }
 
-extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int n_frames, int width, int height, int stride,
-                                  size_t frame_stride, const uint8_t* masks, int mask_stride, size_t mask_frame_stride,
-                                  orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
+// `image_ptrs` (or NULL): one pointer per frame instead of base + frame_stride — frames held as separate allocations
+// (std::vector<cv::Mat>); `images` then only stands for "frame 0" in the pinned / pageable test.
+static int extract_batch_impl(orbx_extractor* ex, const uint8_t* images, const uint8_t* const* image_ptrs, int n_frames, int width, int height,
+                              int stride, size_t frame_stride, const uint8_t* masks, int mask_stride, size_t mask_frame_stride,
+                              orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
     ORB_REQUIRE(ex && images && kp_out && desc_out && n_out && n_frames >= 0 && cap > 0, ORB_ERR_ARG, "bad arguments");
+    auto frame_at = [&](int f) -> const u8* { return image_ptrs ? image_ptrs[f] : images + (size_t)f * frame_stride; };
     ORB_REQUIRE(width == ex->plan.width && height == ex->plan.height, ORB_ERR_ARG,
                 "image is %dx%d but the handle was planned for %dx%d", width, height, ex->plan.width, ex->plan.height);
     ORB_REQUIRE(stride >= width && (!masks || mask_stride >= width), ORB_ERR_ARG, "stride < width");
@@ -2209,7 +2212,7 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
             if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
             return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
         };
-        const bool tight = (size_t)stride == (size_t)width && frame_stride == fpx;
+        const bool tight = !image_ptrs && (size_t)stride == (size_t)width && frame_stride == fpx;
         const bool stageIn = !(tight && pinned(images)) && (size_t)n_frames * fpx <= (4u << 20);   // large frames: direct copy is cheaper
         const bool stageOut = !(pinned(kp_out) && pinned(desc_out)) && (size_t)n_frames * icap <= 65536;
         const size_t inBytes = (size_t)n_frames * fpx, kpBytes = (size_t)n_frames * icap * sizeof(orbx_keypoint), dBytes = (size_t)n_frames * icap * 32;
@@ -2226,13 +2229,13 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
         if (stageIn) {
             for (int f = 0; f < n_frames; f++)
                 for (int y = 0; y < height; y++)
-                    memcpy(hIn + f * fpx + (size_t)y * width, images + (size_t)f * frame_stride + (size_t)y * stride, width);
+                    memcpy(hIn + f * fpx + (size_t)y * width, frame_at(f) + (size_t)y * stride, width);
             ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[0], hIn, inBytes, cudaMemcpyHostToDevice, st));
         } else if (tight) {
             ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[0], images, inBytes, cudaMemcpyHostToDevice, st));
         } else {
             for (int f = 0; f < n_frames; f++)
-                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in[0] + f * fpx, width, images + (size_t)f * frame_stride, stride, width, height,
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in[0] + f * fpx, width, frame_at(f), stride, width, height,
                                                cudaMemcpyHostToDevice, st));
         }
         if (masks)
@@ -2351,7 +2354,7 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
             const int perFrame = orb_div_up(height, rowsPer);
             ex->pool->run(nf * perFrame, [&](int it) {
                 const int f = it / perFrame, y0 = (it - f * perFrame) * rowsPer, y1 = std::min(height, y0 + rowsPer);
-                const u8* src = images + (size_t)(f0 + f) * frame_stride;
+                const u8* src = frame_at(f0 + f);
                 u8* dst = hin + (size_t)f * fpx;
                 static const bool nt = [] { const char* e = getenv("ORBX_HOST_NT"); return !(e && e[0] == '0'); }();
                 if (!nt) {
@@ -2361,11 +2364,11 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
                 else for (int y = y0; y < y1; y++) copy_stream(dst + (size_t)y * width, src + (size_t)y * stride, width);
             });
             ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[sl], hin, (size_t)nf * fpx, cudaMemcpyHostToDevice, ex->sH2D));
-        } else if ((size_t)stride == (size_t)width && frame_stride == fpx) {
+        } else if (!image_ptrs && (size_t)stride == (size_t)width && frame_stride == fpx) {
             ORB_CUDA_TRY(cudaMemcpyAsync(ex->d_in[sl], images + (size_t)f0 * frame_stride, (size_t)nf * fpx, cudaMemcpyHostToDevice, ex->sH2D));
         } else {
             for (int f = 0; f < nf; f++)
-                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in[sl] + f * fpx, width, images + (size_t)(f0 + f) * frame_stride, stride, width,
+                ORB_CUDA_TRY(cudaMemcpy2DAsync(ex->d_in[sl] + f * fpx, width, frame_at(f0 + f), stride, width,
                                                height, cudaMemcpyHostToDevice, ex->sH2D));
         }
         if (masks)
@@ -2438,6 +2441,21 @@ extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int
         ORB_REQUIRE(ex->h_n[f] <= cap, ORB_ERR_CAPACITY, "frame %d has %d keypoints but cap is %d", f, ex->h_n[f], cap);
     }
     return ORB_OK;
+}
+
+extern "C" int orbx_extract_batch(orbx_extractor* ex, const uint8_t* images, int n_frames, int width, int height, int stride,
+                                  size_t frame_stride, const uint8_t* masks, int mask_stride, size_t mask_frame_stride,
+                                  orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
+    return extract_batch_impl(ex, images, nullptr, n_frames, width, height, stride, frame_stride, masks, mask_stride, mask_frame_stride, kp_out,
+                              desc_out, cap, n_out);
+}
+extern "C" int orbx_extract_batch_ptrs(orbx_extractor* ex, const uint8_t* const* images, int n_frames, int width, int height, int stride,
+                                       orbx_keypoint* kp_out, uint8_t* desc_out, int cap, int* n_out) {
+    ORB_REQUIRE(ex && kp_out && desc_out && n_out && n_frames >= 0 && cap > 0 && (images || n_frames == 0), ORB_ERR_ARG, "bad arguments");
+    if (n_frames == 0) return ORB_OK;
+    for (int f = 0; f < n_frames; f++) ORB_REQUIRE(images[f], ORB_ERR_ARG, "image %d is NULL", f);
+    return extract_batch_impl(ex, images[0], images, n_frames, width, height, stride, (size_t)stride * height, nullptr, 0, 0, kp_out, desc_out,
+                              cap, n_out);
 }
 
 // Page-lock / unlock caller-owned host memory (cudaHostRegister) so that the batch call can DMA straight from / into it: from

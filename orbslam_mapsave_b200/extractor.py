@@ -129,6 +129,23 @@ class ORBextractor:
                                                  capi._p(kp), capi._p(desc), cap, capi._p(n)))
         return kp, desc, n
 
+    def extract_batch_list(self, images):
+        """images: a list of (H, W) uint8 host arrays, each its own allocation (row stride = the arrays' common strides[0]).
+        Returns (kp[B, cap], desc[B, cap, 32], n[B]) like extract_batch (orbx_extract_batch_ptrs)."""
+        B = len(images)
+        h, w = images[0].shape
+        stride = images[0].strides[0]
+        assert all(im.dtype == np.uint8 and im.shape == (h, w) and im.strides == (stride, 1) for im in images)
+        self._plan(w, h)
+        cap = self.max_keypoints()
+        kp = np.zeros((B, cap), capi.KP_DTYPE)
+        desc = np.zeros((B, cap, 32), np.uint8)
+        n = np.zeros(B, np.int32)
+        ptrs = (C.c_void_p * B)(*[im.ctypes.data for im in images])
+        capi.check(capi.lib().orbx_extract_batch_ptrs(self._h, C.cast(ptrs, C.c_void_p), B, w, h, stride, capi._p(kp), capi._p(desc), cap,
+                                                      capi._p(n)))
+        return kp, desc, n
+
     def extract_batch_device(self, d_images, d_kp, d_desc, d_n, cap, d_masks=None, stream=None, stages=capi.STAGE_ALL):
         """All arguments are torch CUDA tensors (or objects with data_ptr()); asynchronous on `stream`."""
         B, h, w = d_images.shape

@@ -24,7 +24,7 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
     if (mLastStatus != ORB_OK) std::fprintf(stderr, "ORBextractor: %s\n", orb_last_error());
 }
 
-ORBextractor::~ORBextractor() { orbx_destroy(mHandle); }
+ORBextractor::~ORBextractor() { orbx_destroy(mHandle); orbx_destroy(mBatchHandle); }
 
 void ORBextractor::Plan(int width, int height) {
     if (mHandle && width == mPlanW && height == mPlanH) return;
@@ -88,6 +88,42 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray _mask, std::
     }
 }
 
+
+void ORBextractor::operator()(const std::vector<cv::Mat>& images, std::vector<std::vector<cv::KeyPoint> >& keypoints,
+                              std::vector<cv::Mat>& descriptors) {
+    const int N = (int)images.size();
+    keypoints.assign(N, std::vector<cv::KeyPoint>());
+    descriptors.assign(N, cv::Mat());
+    if (N == 0) return;
+    const int w = images[0].cols, h = images[0].rows;
+    const int step = (int)images[0].step;
+    std::vector<const uint8_t*> ptrs(N);
+    for (int i = 0; i < N; i++) {
+        assert(images[i].type() == CV_8UC1 && images[i].cols == w && images[i].rows == h && (int)images[i].step == step);
+        ptrs[i] = images[i].data;
+    }
+    if (!mBatchHandle || w != mBatchW || h != mBatchH) {
+        orbx_destroy(mBatchHandle);
+        mBatchHandle = nullptr;
+        mLastStatus = orbx_create(&mBatchHandle, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, w, h, 128, mDevice);
+        if (mLastStatus != ORB_OK) { std::fprintf(stderr, "ORBextractor: %s\n", orb_last_error()); return; }
+        mBatchW = w; mBatchH = h;
+    }
+    const int cap = orbx_max_keypoints(mBatchHandle);
+    std::vector<cv::KeyPoint> kps((size_t)N * cap);
+    std::vector<uint8_t> desc((size_t)N * cap * 32);
+    std::vector<int> n(N, 0);
+    mLastStatus = orbx_extract_batch_ptrs(mBatchHandle, ptrs.data(), N, w, h, step, reinterpret_cast<orbx_keypoint*>(kps.data()), desc.data(), cap,
+                                          n.data());
+    if (mLastStatus != ORB_OK) { std::fprintf(stderr, "ORBextractor: %s\n", orb_last_error()); return; }
+    for (int i = 0; i < N; i++) {
+        keypoints[i].assign(kps.begin() + (size_t)i * cap, kps.begin() + (size_t)i * cap + n[i]);
+        if (n[i] > 0) {
+            descriptors[i] = cv::Mat(n[i], 32, CV_8U);
+            for (int r = 0; r < n[i]; r++) std::memcpy(descriptors[i].ptr(r), &desc[((size_t)i * cap + r) * 32], 32);
+        }
+    }
+}
 
 void ORBextractor::ComputeStereoMatches(ORBextractor* left, ORBextractor* right, const std::vector<cv::KeyPoint>& mvKeys,
                                         const cv::Mat& mDescriptors, const std::vector<cv::KeyPoint>& mvKeysRight,

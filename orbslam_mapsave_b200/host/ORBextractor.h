@@ -24,6 +24,11 @@ public:
     void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints,
                     cv::OutputArray descriptors);                                        // reference :64-66
 
+    // Batch form (not in the reference): N images of one size, each its own cv::Mat, in ONE pipelined call (orbx_extract_batch_ptrs:
+    // copies overlapped with the kernels, 128-frame device passes).  keypoints[i] / descriptors[i] equal what operator() returns for
+    // images[i] without a mask; mvImagePyramid is left alone.
+    void operator()(const std::vector<cv::Mat>& images, std::vector<std::vector<cv::KeyPoint> >& keypoints, std::vector<cv::Mat>& descriptors);
+
     int inline GetLevels() { return nlevels; }                                            // :68-69
     float inline GetScaleFactor() { return scaleFactor; }                                 // :71-72
     std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }                 // :74-76
@@ -62,6 +67,8 @@ protected:
     std::vector<float> mvInvLevelSigma2;
 
     orbx_extractor* mHandle = nullptr;
+    orbx_extractor* mBatchHandle = nullptr;   // 128-frame workspace of the batch form, created on its first call
+    int mBatchW = 0, mBatchH = 0;
     int mPlanW = 0, mPlanH = 0, mDevice = 0, mLastStatus = 0;
     bool mbDownloadPyramid = true;
 };

@@ -56,6 +56,28 @@ static int run_extract(int argc, char** argv) {
             for (int y = -19; y < m.rows + 19; y++) put(f, m.data + (ptrdiff_t)y * (ptrdiff_t)m.step - 19, m.cols + 38);   // the border is addressable around the ROI
         }
     }
+    if (mask.empty()) {   // batch overload: separately allocated frames; every copy of `image` must come back exactly like the single call
+        const int nb = 150;                                        // > 128: two chunks through the pipelined path
+        std::vector<std::vector<unsigned char> > store(nb, img);
+        std::vector<cv::Mat> frames(nb);
+        for (int i = 0; i < nb; i++) {
+            if (i % 3 == 1) for (int y = 0; y < h; y++) for (int x = 0; x + 1 < w; x++) store[i][(size_t)y * w + x] = img[(size_t)y * w + x + 1];   // a different frame
+            frames[i] = cv::Mat(h, w, CV_8U, store[i].data());
+        }
+        std::vector<std::vector<cv::KeyPoint> > bk;
+        std::vector<cv::Mat> bd;
+        ex(frames, bk, bd);
+        if (ex.LastStatus() != 0 || (int)bk.size() != nb) return 6;
+        std::vector<cv::KeyPoint> k1; cv::Mat d1;
+        ex(frames[1], cv::Mat(), k1, d1);
+        for (int i = 0; i < nb; i++) {
+            const std::vector<cv::KeyPoint>& want = (i % 3 == 1) ? k1 : kps;
+            const cv::Mat& wd = (i % 3 == 1) ? d1 : desc;
+            if (bk[i].size() != want.size() || bd[i].rows != wd.rows) return 7;
+            if (memcmp(bk[i].data(), want.data(), want.size() * sizeof(cv::KeyPoint))) return 8;
+            for (int r = 0; r < wd.rows; r++) if (memcmp(bd[i].ptr(r), wd.ptr(r), 32)) return 9;
+        }
+    }
     // empty image: silent no-op, outputs untouched (reference :1045-1046)
     cv::Mat empty;
     std::vector<cv::KeyPoint> keep(kps);

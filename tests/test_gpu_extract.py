@@ -203,6 +203,33 @@ def test_pageable_strided_and_pinned_pipelines_agree():
         assert n[f] == len(k1) and np.array_equal(kp[f, :n[f]].tobytes(), k1.tobytes()) and np.array_equal(desc[f, :n[f]], d1), f
 
 
+def test_batch_of_separately_allocated_frames():
+    """orbx_extract_batch_ptrs (frames as separate allocations, like std::vector<cv::Mat>): pageable arrays through the staging pool,
+    strided views, page-locked tensors by per-frame DMA, and the single-pass (latency) form all equal orbx_extract_batch."""
+    import torch
+    base = [synth(640, 480, s) for s in range(80, 85)]
+    frames = [np.roll(base[i % 5], 7 * (i // 5), axis=1).copy() for i in range(300)]
+    ex = orb.ORBextractor(1000, 1.2, 8, 20, 7, max_batch=64)
+    kp0, desc0, n0 = ex.extract_batch(np.stack(frames))
+    kp1, desc1, n1 = ex.extract_batch_list(frames)                       # pageable, 5 chunks
+    wide = [np.zeros((480, 656), np.uint8) for _ in range(300)]
+    for w_, f_ in zip(wide, frames):
+        w_[:, :640] = f_
+    kp2, desc2, n2 = ex.extract_batch_list([w_[:, :640] for w_ in wide])   # row stride 656
+    pinned = [torch.from_numpy(f_).pin_memory() for f_ in frames[:100]]
+    kp3, desc3, n3 = ex.extract_batch_list([t.numpy() for t in pinned])    # page-locked frames: one 2-D DMA each
+    kp4, desc4, n4 = ex.extract_batch_list(frames[:9])                     # one pass (the latency path)
+    assert np.array_equal(n0, n1) and np.array_equal(n0, n2) and np.array_equal(n0[:100], n3) and np.array_equal(n0[:9], n4) and n0.min() > 900
+    for f in range(300):
+        a, d = kp0[f, :n0[f]].tobytes(), desc0[f, :n0[f]]
+        assert a == kp1[f, :n0[f]].tobytes() and np.array_equal(d, desc1[f, :n0[f]]), f
+        assert a == kp2[f, :n0[f]].tobytes() and np.array_equal(d, desc2[f, :n0[f]]), f
+        if f < 100:
+            assert a == kp3[f, :n0[f]].tobytes() and np.array_equal(d, desc3[f, :n0[f]]), f
+        if f < 9:
+            assert a == kp4[f, :n0[f]].tobytes() and np.array_equal(d, desc4[f, :n0[f]]), f
+
+
 def test_non_tma_fallback_kernels_match_oracle():
     """ORBX_FAST_TMA=0 / ORBX_DESC_TMA=0 select k_fast (one CTA per cell) and k_describe<false> (cp.async staging) — the kernels that
     run when tensor maps cannot be encoded or cells exceed the TMA box.  Separate process: the switches are read when the library plans."""
