@@ -207,10 +207,10 @@ std::vector<int> ORBmatcher::SearchByBoW(KeyFrame* pKF1, const std::vector<KeyFr
     return counts;
 }
 
-int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
-                                       std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
-    // Epipole in the second image (ORBmatcher.cc:667-673).  `R2w*Cw+t2w` is one cv::gemm(A, B, 1, C, 1) on 3x3 / 3x1 floats:
-    // float32, left to right (cv2 4.13, tests/golden/prim_gemm3.npz).
+namespace {
+// Epipole of pKF1's centre in the second image (ORBmatcher.cc:667-673).  `R2w*Cw+t2w` is one cv::gemm(A, B, 1, C, 1) on 3x3 / 3x1 floats:
+// float32, left to right (cv2 4.13, tests/golden/prim_gemm3.npz).
+void epipole_in(KeyFrame* pKF1, KeyFrame* pKF2, float& ex, float& ey) {
     cv::Mat Cw = pKF1->GetCameraCenter();
     cv::Mat R2w = pKF2->GetRotation();
     cv::Mat t2w = pKF2->GetTranslation();
@@ -219,8 +219,57 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
         C2[i] = ((R2w.at<float>(i, 0) * Cw.at<float>(0) + R2w.at<float>(i, 1) * Cw.at<float>(1)) + R2w.at<float>(i, 2) * Cw.at<float>(2)) +
                 t2w.at<float>(i);
     const float invz = 1.0f / C2[2];
-    const float ex = pKF2->fx * C2[0] * invz + pKF2->cx;
-    const float ey = pKF2->fy * C2[1] * invz + pKF2->cy;
+    ex = pKF2->fx * C2[0] * invz + pKF2->cx;
+    ey = pKF2->fy * C2[1] * invz + pKF2->cy;
+}
+}  // namespace
+
+std::vector<int> ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, const std::vector<KeyFrame*>& vpKF2s, const std::vector<cv::Mat>& vF12,
+                                                    std::vector<std::vector<std::pair<size_t, size_t> > >& vvMatchedPairs,
+                                                    const bool bOnlyStereo) {
+    const size_t k = std::min(vpKF2s.size(), vF12.size());
+    std::vector<int> counts(k, 0);
+    vvMatchedPairs.assign(k, std::vector<std::pair<size_t, size_t> >());
+    if (k == 0) return counts;
+    // the C entry takes one scale table width for all neighbours: keyframes of one map share it (mnScaleLevels is a system constant)
+    const size_t nlv = vpKF2s[0]->mvScaleFactors.size();
+    bool uniform = true;
+    for (size_t i = 0; i < k; i++) uniform = uniform && vpKF2s[i]->mvScaleFactors.size() == nlv && vpKF2s[i]->mvLevelSigma2.size() == nlv;
+    if (!uniform) {                                                   // (never in the reference; keep the semantics anyway)
+        for (size_t i = 0; i < k; i++) counts[i] = SearchForTriangulation(pKF1, vpKF2s[i], vF12[i], vvMatchedPairs[i], bOnlyStereo);
+        return counts;
+    }
+    Side a;
+    snapshot_kf_tri(pKF1, a);
+    std::vector<Side> sides(k);
+    std::vector<orbm_view> views(k);
+    std::vector<float> F(9 * k), ep(2 * k), sf(nlv * k), s2(nlv * k);
+    for (size_t i = 0; i < k; i++) {
+        snapshot_kf_tri(vpKF2s[i], sides[i]);
+        views[i] = sides[i].view;
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) F[9 * i + 3 * r + c] = vF12[i].at<float>(r, c);
+        epipole_in(pKF1, vpKF2s[i], ep[2 * i], ep[2 * i + 1]);
+        for (size_t l = 0; l < nlv; l++) { sf[i * nlv + l] = vpKF2s[i]->mvScaleFactors[l]; s2[i * nlv + l] = vpKF2s[i]->mvLevelSigma2[l]; }
+    }
+    const size_t n1 = (size_t)(pKF1->N > 0 ? pKF1->N : 1);
+    std::vector<int> pairs(2 * n1 * k), npairs(k, 0);
+    report(orbm_search_for_triangulation_batch(&a.view, views.data(), (int)k, F.data(), ep.data(), sf.data(), s2.data(), (int)nlv,
+                                               bOnlyStereo ? 1 : 0, mbCheckOrientation ? 1 : 0, pairs.data(), npairs.data(), counts.data(),
+                                               g_device));
+    if (g_status != ORB_OK) return std::vector<int>(k, 0);
+    for (size_t i = 0; i < k; i++) {
+        vvMatchedPairs[i].reserve(npairs[i]);
+        const int* p = &pairs[2 * (size_t)pKF1->N * i];
+        for (int j = 0; j < npairs[i]; j++) vvMatchedPairs[i].push_back(std::make_pair((size_t)p[2 * j], (size_t)p[2 * j + 1]));
+    }
+    return counts;
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+                                       std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
+    float ex, ey;
+    epipole_in(pKF1, pKF2, ex, ey);
 
     Side a, b;
     snapshot_kf_tri(pKF1, a);

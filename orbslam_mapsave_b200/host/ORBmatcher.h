@@ -66,6 +66,11 @@ public:
     int SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
                                const bool bOnlyStereo);
 
+    // Batched overload (not in the reference): the loop over the neighbours of LocalMapping::CreateNewMapPoints
+    // (src/LocalMapping.cc:215-268) as one device call; element i equals the single overload on (pKF1, vpKF2s[i], vF12[i]).
+    std::vector<int> SearchForTriangulation(KeyFrame* pKF1, const std::vector<KeyFrame*>& vpKF2s, const std::vector<cv::Mat>& vF12,
+                                            std::vector<std::vector<std::pair<size_t, size_t> > >& vvMatchedPairs, const bool bOnlyStereo);
+
     static const int TH_LOW;                                                              // reference :87-89
     static const int TH_HIGH;
     static const int HISTO_LENGTH;

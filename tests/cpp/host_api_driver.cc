@@ -194,6 +194,16 @@ static int run_match(int argc, char** argv) {
         const int got = ORBmatcher::DescriptorDistances(w.kf[0].mDescriptors, w.kf[1].mDescriptors, dist.data());
         put(out, &got, 1); put(out, dist.data(), (size_t)got);
     }
+    {   // batched SearchForTriangulation: kf0 against {kf1, kf1, kf1} — every element must equal the single call
+        std::vector<std::pair<size_t, size_t> > single;
+        const int n1 = m.SearchForTriangulation(&w.kf[0], &w.kf[1], F12, single, onlyStereo != 0);
+        std::vector<std::vector<std::pair<size_t, size_t> > > many;
+        const std::vector<int> nb = m.SearchForTriangulation(&w.kf[0], std::vector<KeyFrame*>(3, &w.kf[1]), std::vector<cv::Mat>(3, F12), many,
+                                                             onlyStereo != 0);
+        if (nb.size() != 3 || many.size() != 3) return 10;
+        for (int c = 0; c < 3; c++)
+            if (nb[c] != n1 || many[c] != single) return 11;
+    }
     return ORBmatcher::LastStatus() == 0 ? 0 : 4;
 }
 
